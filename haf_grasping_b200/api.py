@@ -1,0 +1,293 @@
+"""ctypes binding of libhafgpu.so (include/hafgpu.h).  Thin: every call goes straight to the C ABI.
+
+There is no CPU fallback anywhere in this package: if libhafgpu.so is missing or no sm_100 device is
+visible, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+HAF_SVM_FP32_GUARD = 0
+HAF_SVM_FP64_EXACT = 1
+HAF_SVM_TENSOR_GUARD = 2
+
+
+class HafError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libhafgpu error %d: %s" % (code, msg))
+        self.code = code
+
+
+class haf_config(C.Structure):
+    _fields_ = [("features_path", C.c_char_p), ("range_path", C.c_char_p), ("model_path", C.c_char_p),
+                ("nr_features_without_shaf", C.c_int), ("grid", C.c_int), ("roll_step_deg", C.c_int),
+                ("roll_max_deg", C.c_int), ("device", C.c_int), ("emulate_text_roundtrip", C.c_int),
+                ("svm_mode", C.c_int), ("guard_rel", C.c_float), ("reserved", C.c_int * 4)]
+
+
+class haf_request(C.Structure):
+    _fields_ = [("center", C.c_double * 3), ("area_len_x", C.c_float), ("area_len_y", C.c_float),
+                ("approach", C.c_double * 3), ("gripper_opening_width", C.c_int), ("return_only_best", C.c_int),
+                ("graspval_top", C.c_int), ("roll_limit", C.c_int)]
+
+
+class haf_best(C.Structure):
+    _fields_ = [("row", C.c_int), ("col", C.c_int), ("roll", C.c_int), ("tilt", C.c_int), ("approach_idx", C.c_int),
+                ("topval", C.c_int), ("eval", C.c_int), ("roll_rad", C.c_float), ("M", C.c_float * 16),
+                ("rolls_done", C.c_int), ("n_windows_scored", C.c_int), ("n_guard", C.c_int), ("reserved", C.c_int)]
+
+    def astuple(self):
+        return (self.row, self.col, self.roll, self.tilt, self.topval)
+
+
+class haf_info(C.Structure):
+    _fields_ = [("n_features", C.c_int), ("n_dims", C.c_int), ("n_sv", C.c_int), ("n_rolls", C.c_int), ("grid", C.c_int),
+                ("label0", C.c_int), ("label1", C.c_int), ("sm_count", C.c_int), ("gamma", C.c_double),
+                ("rho", C.c_double), ("reserved", C.c_int * 4)]
+
+
+class haf_timing(C.Structure):
+    _fields_ = [("ms_total", C.c_float), ("ms_bin", C.c_float), ("ms_integral", C.c_float), ("ms_mask", C.c_float),
+                ("ms_features", C.c_float), ("ms_svm", C.c_float), ("ms_guard", C.c_float), ("ms_score", C.c_float),
+                ("n_points", C.c_longlong), ("n_units", C.c_longlong), ("n_windows", C.c_longlong),
+                ("n_guard", C.c_longlong), ("launches", C.c_longlong)]
+
+
+EXPORTS = ["haf_create", "haf_destroy", "haf_last_error", "haf_get_info", "haf_set_stream", "haf_set_profiling",
+           "haf_get_timing", "haf_launch_count", "haf_search", "haf_search_batch", "haf_search_batch_packed",
+           "haf_build_transform", "haf_best_key", "haf_debug_window_count", "haf_debug_windows", "haf_debug_features",
+           "haf_debug_decisions", "haf_debug_integral", "haf_debug_cell_indices", "haf_debug_text_roundtrip",
+           "haf_version"]
+
+_lib = None
+
+
+def load_library(build_if_missing: bool = True) -> C.CDLL:
+    """Loads (building first if the .so is absent or stale and nvcc is here) libhafgpu.so.  Raises if impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if build_if_missing and _build.needs_build():
+        try:
+            _build.build_lib()
+        except Exception as exc:  # no nvcc on this box: use the prebuilt file if there is one
+            if not os.path.exists(path):
+                raise RuntimeError("libhafgpu.so is not built and cannot be built here: %s" % exc)
+    if not os.path.exists(path):
+        raise RuntimeError("libhafgpu.so missing at %s (run __graft_entry__.build())" % path)
+    L = C.CDLL(path)
+    vp, ci, cs = C.c_void_p, C.c_int, C.c_size_t
+    L.haf_create.argtypes = [C.POINTER(vp), C.POINTER(haf_config)]
+    L.haf_destroy.argtypes = [vp]
+    L.haf_destroy.restype = None
+    L.haf_last_error.argtypes = [vp]
+    L.haf_last_error.restype = C.c_char_p
+    L.haf_get_info.argtypes = [vp, C.POINTER(haf_info)]
+    L.haf_set_stream.argtypes = [vp, vp]
+    L.haf_set_profiling.argtypes = [vp, ci]
+    L.haf_get_timing.argtypes = [vp, C.POINTER(haf_timing)]
+    L.haf_launch_count.argtypes = [vp]
+    L.haf_launch_count.restype = C.c_longlong
+    L.haf_search.argtypes = [vp, vp, cs, cs, C.POINTER(haf_request), ci, C.POINTER(haf_best), C.POINTER(haf_best), vp, vp, vp, vp]
+    L.haf_search_batch.argtypes = [vp, C.POINTER(vp), C.POINTER(cs), ci, C.POINTER(haf_request), C.POINTER(haf_best)]
+    L.haf_search_batch_packed.argtypes = [vp, vp, C.POINTER(cs), ci, C.POINTER(haf_request), C.POINTER(haf_best)]
+    L.haf_build_transform.argtypes = [C.POINTER(haf_request), ci, ci, C.POINTER(C.c_float)]
+    L.haf_best_key.argtypes = [ci, C.c_uint32]
+    L.haf_best_key.restype = C.c_uint64
+    L.haf_debug_window_count.argtypes = [vp]
+    L.haf_debug_windows.argtypes = [vp, vp, ci]
+    L.haf_debug_features.argtypes = [vp, vp, vp, ci]
+    L.haf_debug_decisions.argtypes = [vp, vp, vp, vp, ci]
+    L.haf_debug_integral.argtypes = [vp, vp, cs]
+    L.haf_debug_cell_indices.argtypes = [vp, vp, cs, cs, C.POINTER(haf_request), ci, vp]
+    L.haf_debug_text_roundtrip.argtypes = [vp, vp, ci, vp, vp, ci, vp]
+    L.haf_version.restype = C.c_char_p
+    _lib = L
+    return L
+
+
+def make_request(center=(0.0, 0.0, 0.0), area=(32.0, 44.0), approach=(0.0, 0.0, 1.0), width=1, return_only_best=0,
+                 graspval_top=119, roll_limit=0) -> haf_request:
+    """GraspInput defaults of the reference client (client.cpp:79-118; area = size + 14, client.cpp:183-184)."""
+    rq = haf_request()
+    rq.center[:] = center
+    rq.area_len_x, rq.area_len_y = area
+    rq.approach[:] = approach
+    rq.gripper_opening_width = width
+    rq.return_only_best = return_only_best
+    rq.graspval_top = graspval_top
+    rq.roll_limit = roll_limit
+    return rq
+
+
+def _ptr(a):
+    """host numpy array, torch tensor (host or cuda) or raw int address -> void*"""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    if hasattr(a, "data_ptr"):
+        return C.c_void_p(a.data_ptr())
+    return C.c_void_p(int(a))
+
+
+class GraspSearch:
+    """One context = one GPU.  Mirrors the reference's per-goal flow: construct once with the three files the
+    action server is configured with (server.cpp:218-225), then ``search`` per goal."""
+
+    def __init__(self, features_path, range_path, model_path, grid=56, roll_step_deg=15, roll_max_deg=190,
+                 nr_features_without_shaf=302, device=0, emulate_text_roundtrip=True, svm_mode=HAF_SVM_FP32_GUARD,
+                 guard_rel=0.0):
+        self.L = load_library()
+        cfg = haf_config()
+        self._keep = [features_path.encode(), range_path.encode(), model_path.encode()]
+        cfg.features_path, cfg.range_path, cfg.model_path = self._keep
+        cfg.nr_features_without_shaf = nr_features_without_shaf
+        cfg.grid, cfg.roll_step_deg, cfg.roll_max_deg = grid, roll_step_deg, roll_max_deg
+        cfg.device = device
+        cfg.emulate_text_roundtrip = int(bool(emulate_text_roundtrip))
+        cfg.svm_mode = svm_mode
+        cfg.guard_rel = guard_rel
+        self.h = C.c_void_p()
+        rc = self.L.haf_create(C.byref(self.h), C.byref(cfg))
+        if rc != 0:
+            raise HafError(rc, (self.L.haf_last_error(None) or b"").decode())
+        self.info = haf_info()
+        self.L.haf_get_info(self.h, C.byref(self.info))
+        self.G, self.R, self.F, self.D = self.info.grid, self.info.n_rolls, self.info.n_features, self.info.n_dims
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.haf_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc < 0:
+            raise HafError(rc, (self.L.haf_last_error(self.h) or b"").decode())
+        return rc
+
+    def set_stream(self, cuda_stream_handle: int):
+        self._check(self.L.haf_set_stream(self.h, C.c_void_p(cuda_stream_handle)))
+
+    def set_profiling(self, on: bool):
+        self._check(self.L.haf_set_profiling(self.h, int(on)))
+
+    def timing(self) -> haf_timing:
+        t = haf_timing()
+        self._check(self.L.haf_get_timing(self.h, C.byref(t)))
+        return t
+
+    def launch_count(self) -> int:
+        return int(self.L.haf_launch_count(self.h))
+
+    def search(self, xyz, requests=None, n_points=None, stride_bytes=None, outputs=True):
+        """xyz: numpy float32 [n,3] (host), or a torch CUDA tensor [n,3]/[n,4] (device pointer).  Returns a dict."""
+        if requests is None:
+            requests = [make_request()]
+        if isinstance(requests, haf_request):
+            requests = [requests]
+        nreq = len(requests)
+        reqs = (haf_request * nreq)(*requests)
+        if isinstance(xyz, np.ndarray):
+            xyz = np.ascontiguousarray(xyz, np.float32)
+            n = len(xyz) if n_points is None else n_points
+            stride = xyz.strides[0] if stride_bytes is None else stride_bytes
+        else:
+            n = xyz.shape[0] if n_points is None else n_points
+            stride = xyz.stride(0) * 4 if stride_bytes is None else stride_bytes
+        best = haf_best()
+        per = (haf_best * nreq)()
+        out = {}
+        G, R = self.G, self.R
+        if outputs:
+            out["graspseval"] = np.zeros((nreq, R, G, G), np.float32)
+            out["mask"] = np.zeros((nreq, R, G, G), np.uint8)
+            out["heights"] = np.zeros((nreq, R, G, G), np.float32)
+        out["per_roll_top"] = np.full((nreq, R, 3), -1, np.int32)
+        self._check(self.L.haf_search(self.h, _ptr(xyz), n, stride, reqs, nreq, C.byref(best), per,
+                                      _ptr(out.get("graspseval")), _ptr(out.get("mask")), _ptr(out.get("heights")),
+                                      _ptr(out["per_roll_top"])))
+        out["best"] = best
+        out["best_per_request"] = list(per)
+        return out
+
+    def search_batch_packed(self, xyz_all, point_offsets, request=None):
+        """xyz_all: packed float32 [N,3] host array or CUDA tensor; point_offsets: n_clouds+1 ints."""
+        rq = request or make_request()
+        off = (C.c_size_t * len(point_offsets))(*[int(o) for o in point_offsets])
+        n_clouds = len(point_offsets) - 1
+        best = (haf_best * n_clouds)()
+        if isinstance(xyz_all, np.ndarray):
+            xyz_all = np.ascontiguousarray(xyz_all, np.float32)
+        self._check(self.L.haf_search_batch_packed(self.h, _ptr(xyz_all), off, n_clouds, C.byref(rq), best))
+        return best
+
+    def search_batch(self, clouds, request=None):
+        """clouds: list of float32 [n_i,3] host arrays or CUDA tensors."""
+        rq = request or make_request()
+        n_clouds = len(clouds)
+        keep = [np.ascontiguousarray(c, np.float32) if isinstance(c, np.ndarray) else c for c in clouds]
+        ptrs = (C.c_void_p * n_clouds)(*[_ptr(c) for c in keep])
+        npts = (C.c_size_t * n_clouds)(*[int(c.shape[0]) for c in keep])
+        best = (haf_best * n_clouds)()
+        self._check(self.L.haf_search_batch(self.h, ptrs, npts, n_clouds, C.byref(rq), best))
+        return best
+
+    # ---- parity / inspection -----------------------------------------------------------
+    def debug_windows(self):
+        W = self._check(self.L.haf_debug_window_count(self.h))
+        a = np.zeros((max(W, 1), 2), np.int32)
+        self._check(self.L.haf_debug_windows(self.h, _ptr(a), W))
+        return a[:W]
+
+    def debug_features(self, raw=True, scaled=True):
+        W = self._check(self.L.haf_debug_window_count(self.h))
+        r = np.zeros((max(W, 1), self.F), np.float32) if raw else None
+        s = np.zeros((max(W, 1), self.D), np.float64) if scaled else None
+        self._check(self.L.haf_debug_features(self.h, _ptr(r), _ptr(s), W))
+        return (r[:W] if raw else None), (s[:W] if scaled else None)
+
+    def debug_decisions(self):
+        W = self._check(self.L.haf_debug_window_count(self.h))
+        d = np.zeros(max(W, 1), np.float64)
+        lab = np.zeros(max(W, 1), np.int32)
+        g = np.zeros(max(W, 1), np.uint8)
+        self._check(self.L.haf_debug_decisions(self.h, _ptr(d), _ptr(lab), _ptr(g), W))
+        return d[:W], lab[:W], g[:W]
+
+    def debug_integral(self, n_units):
+        a = np.zeros((n_units, self.G + 1, self.G + 1), np.float32)
+        self._check(self.L.haf_debug_integral(self.h, _ptr(a), a.size))
+        return a
+
+    def debug_cell_indices(self, xyz, request, roll):
+        xyz = np.ascontiguousarray(xyz, np.float32)
+        out = np.zeros(len(xyz), np.int32)
+        self._check(self.L.haf_debug_cell_indices(self.h, _ptr(xyz), len(xyz), xyz.strides[0], C.byref(request), roll, _ptr(out)))
+        return out
+
+    def debug_text_roundtrip(self, in4=None, in6=None):
+        in4 = np.ascontiguousarray(in4 if in4 is not None else np.zeros(0), np.float32)
+        in6 = np.ascontiguousarray(in6 if in6 is not None else np.zeros(0), np.float64)
+        o4, o6 = np.zeros(len(in4), np.float64), np.zeros(len(in6), np.float64)
+        self._check(self.L.haf_debug_text_roundtrip(self.h, _ptr(in4), len(in4), _ptr(o4), _ptr(in6), len(in6), _ptr(o6)))
+        return o4, o6
+
+
+def build_transform(request: haf_request, roll: int, roll_step_deg: int = 15) -> np.ndarray:
+    L = load_library()
+    M = (C.c_float * 16)()
+    L.haf_build_transform(C.byref(request), roll, roll_step_deg, M)
+    return np.array(M, np.float32)

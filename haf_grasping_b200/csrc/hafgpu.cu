@@ -1,0 +1,856 @@
+// hafgpu.cu -- C ABI of libhafgpu.so (include/hafgpu.h): context, buffers, launch sequence.
+// One context = one GPU = one stream.  No CPU fallback: every stage below is a CUDA kernel from kernels.cuh.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/hafgpu.h"
+#include "haf_host.hpp"
+#include "kernels.cuh"
+
+using namespace hafk;
+
+static thread_local std::string g_create_error;
+
+#define HAF_VERSION_STRING "hafgpu 0.1 (sm_100a)"
+
+namespace {
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;  // elements
+    int ensure(size_t n) {
+        if (n <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 8 + 256;
+        if (cudaMalloc(&p, want * sizeof(T)) != cudaSuccess) { cudaGetLastError(); if (cudaMalloc(&p, n * sizeof(T)) != cudaSuccess) { cudaGetLastError(); return -1; } want = n; }
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+template <typename T>
+struct PinBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t n) {
+        if (n <= cap) return 0;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 8 + 64;
+        if (cudaMallocHost(&p, want * sizeof(T)) != cudaSuccess) { cudaGetLastError(); return -1; }
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct Job {  // one (cloud, request)
+    int cloud;
+    haf_request rq;
+    int n_rolls_active;
+    long long wbound;  // upper bound on valid windows of this job (all active rolls)
+};
+
+}  // namespace
+
+struct haf_ctx {
+    haf_config cfg;
+    std::string err;
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = 0;
+    bool profiling = false;
+    long long launches = 0;
+    haf_timing timing;
+    cudaEvent_t ev[10];
+    bool ev_ok = false;
+
+    // model-side constants
+    int F = 0, D = 0, Dsv = 0, Kpad = 0, S = 0, Spad = 0, R = 0, G = 0;
+    double lower = -1, upper = 1, gamma = 0, rho = 0;
+    int label[2] = {0, 0}, gv[2] = {0, 0};
+    float guard_rel = 2e-5f;
+    DevBuf<FeatDev> d_feats;
+    DevBuf<DimDev> d_dims;
+    DevBuf<float> d_svT, d_svn, d_coef;
+    DevBuf<double> d_sv64T, d_coef64;
+
+    // per-call state
+    DevBuf<unsigned char> d_xyz;       // staging for host clouds
+    DevBuf<long long> d_ptoff;
+    DevBuf<int> d_cloud_ubegin;
+    DevBuf<UnitParams> d_units;
+    DevBuf<JobParams> d_jobs;
+    DevBuf<JobResult> d_results;
+    DevBuf<int> d_per_roll_top;
+    DevBuf<unsigned> d_keys;            // [Uc][G][G] keys -> heights
+    DevBuf<float> d_integral;           // [Uc][G+1][G+1]
+    DevBuf<double> d_rowscan;           // large-G scratch
+    DevBuf<unsigned char> d_mask;
+    DevBuf<signed char> d_labelgrid;
+    DevBuf<float> d_evals;
+    DevBuf<unsigned long long> d_unit_top, d_unit_run;  // [U_total]
+    DevBuf<unsigned> d_unit_windows;                    // [U_total]
+    DevBuf<int2> d_win;
+    DevBuf<float> d_X, d_xn;
+    DevBuf<double> d_dec;
+    DevBuf<unsigned char> d_guardflag;
+    DevBuf<int> d_guardlist;
+    DevBuf<double> d_kscratch;
+    DevBuf<unsigned> d_counters;        // [0]=win_count [1]=guard_count [2]=overflow [3]=unsupported ; [4..5] clamp (u64)
+    PinBuf<unsigned char> h_stage;      // pinned staging for params / results
+    PinBuf<JobResult> h_results;
+    PinBuf<int> h_per_roll_top;
+    PinBuf<unsigned> h_counters;
+
+    // state of the last search kept for the debug entry points
+    int last_units = 0, last_unit_base = 0;
+    unsigned last_W = 0;
+    size_t last_ldx = 0;
+    bool last_valid = false;
+
+    int fail(int code, const char* fmt, ...) {
+        char buf[1024];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        err = buf;
+        return code;
+    }
+};
+
+#define CUDA_TRY(ctx, expr)                                                                                   \
+    do {                                                                                                      \
+        cudaError_t _e = (expr);                                                                              \
+        if (_e != cudaSuccess) return (ctx)->fail(HAF_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+#define ENSURE(ctx, buf, n)                                                                                   \
+    do {                                                                                                      \
+        if ((buf).ensure(n) != 0) return (ctx)->fail(HAF_ERR_NOMEM, "out of device/pinned memory for %s (%zu elements)", #buf, (size_t)(n)); \
+    } while (0)
+#define LAUNCHED(ctx)                                                                                         \
+    do {                                                                                                      \
+        (ctx)->launches++;                                                                                    \
+        cudaError_t _e = cudaGetLastError();                                                                  \
+        if (_e != cudaSuccess) return (ctx)->fail(HAF_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+static size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
+
+// ------------------------------------------------------------------------------------------------------------
+// context creation: parse the three files once, derive the per-dimension scaling table, upload everything
+// ------------------------------------------------------------------------------------------------------------
+extern "C" const char* haf_version(void) { return HAF_VERSION_STRING; }
+
+extern "C" const char* haf_last_error(const haf_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+static int create_fail(int code, const std::string& msg) {
+    g_create_error = msg;
+    return code;
+}
+
+extern "C" int haf_create(haf_ctx** out, const haf_config* cfg) {
+    if (!out || !cfg) return create_fail(HAF_ERR_ARG, "haf_create: null argument");
+    *out = nullptr;
+    if (!cfg->features_path || !cfg->range_path || !cfg->model_path) return create_fail(HAF_ERR_ARG, "haf_create: features_path, range_path and model_path are required");
+    const int G = cfg->grid > 0 ? cfg->grid : 56;
+    if (G < 16 || G > 1024 || (G & 1)) return create_fail(HAF_ERR_ARG, "haf_create: grid must be even and within 16..1024");
+    const int step = cfg->roll_step_deg > 0 ? cfg->roll_step_deg : 15;
+    const int rmax = cfg->roll_max_deg > 0 ? cfg->roll_max_deg : 190;
+    const int R = rmax / step;
+    if (R < 1 || R > 360) return create_fail(HAF_ERR_ARG, "haf_create: roll_max_deg / roll_step_deg must give 1..360 rolls");
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { cudaGetLastError(); return create_fail(HAF_ERR_NO_DEVICE, "no CUDA device visible: libhafgpu has no CPU fallback"); }
+    if (cfg->device < 0 || cfg->device >= ndev) return create_fail(HAF_ERR_ARG, "haf_create: device ordinal out of range");
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) { cudaGetLastError(); return create_fail(HAF_ERR_CUDA, "cudaGetDeviceProperties failed"); }
+    if (prop.major != 10) {
+        char b[256];
+        snprintf(b, sizeof b, "device %d is sm_%d%d; libhafgpu is built for sm_100a only and has no fallback", cfg->device, prop.major, prop.minor);
+        return create_fail(HAF_ERR_NO_DEVICE, b);
+    }
+
+    std::string err;
+    std::vector<hafhost::Feature> feats;
+    if (!hafhost::load_features(cfg->features_path, feats, err)) return create_fail(HAF_ERR_IO, err);
+    hafhost::Range range;
+    if (!hafhost::load_range(cfg->range_path, range, err)) return create_fail(HAF_ERR_IO, err);
+    hafhost::Model model;
+    bool unsupported = false;
+    if (!hafhost::load_model(cfg->model_path, model, err, unsupported)) return create_fail(unsupported ? HAF_ERR_UNSUPPORTED : HAF_ERR_IO, err);
+
+    const int F = (int)feats.size();
+    const int nshaf = cfg->nr_features_without_shaf > 0 ? cfg->nr_features_without_shaf : 302;
+    // region corners index the 15x15 patch: x2+1, y2+1 must stay <= 14 (the reference would read out of bounds)
+    for (int k = 0; k < F; k++)
+        for (int r = 0; r < 3; r++) {
+            if (hafhost::region_skipped(feats[k], r)) continue;
+            for (int q = 0; q < 4; q++)
+                if (feats[k].reg[4 * r + q] < 0 || feats[k].reg[4 * r + q] > 13) {
+                    char b[256];
+                    snprintf(b, sizeof b, "feature %d region %d has a corner outside 0..13: outside the reference's 15x15 patch", k + 1, r + 1);
+                    return create_fail(HAF_ERR_UNSUPPORTED, b);
+                }
+        }
+
+    // svm-scale's dimension table.  max_index = max(range file, data) (svm-scale.c:106-146); features without a
+    // range entry would be scaled by the min/max of each roll's own data (:165-198): reproduced only when the
+    // feature is structurally constant (all regions skipped -> single-valued -> dropped, :336-337).
+    const int max_index = std::max(range.max_index, F);
+    std::vector<DimDev> dims(max_index);
+    int D_eff = 0;
+    for (int i = 1; i <= max_index; i++) {
+        DimDev d;
+        memset(&d, 0, sizeof d);
+        const bool has = i < (int)range.has.size() && range.has[i];
+        if (i <= F) {
+            d.feat = i - 1;
+            if (has) {
+                d.fmin = range.fmin[i]; d.fmax = range.fmax[i]; d.den = d.fmax - d.fmin;
+                d.drop = (d.fmax == d.fmin) ? 1 : 0;
+            } else {
+                bool constant = true;
+                for (int r = 0; r < 3; r++) if (!hafhost::region_skipped(feats[i - 1], r)) constant = false;
+                if (!constant) {
+                    char b[320];
+                    snprintf(b, sizeof b, "feature %d has no entry in the range file: svm-scale -r would scale it with the min/max of each roll's own data, which this path does not reproduce", i);
+                    return create_fail(HAF_ERR_UNSUPPORTED, b);
+                }
+                d.drop = 1;
+            }
+        } else {  // index only in the range file: the data never carries it -> value 0 every time (svm-scale.c:281-282)
+            d.feat = -1;
+            d.fmin = range.fmin[i]; d.fmax = range.fmax[i]; d.den = d.fmax - d.fmin;
+            d.drop = (d.fmax == d.fmin) ? 1 : 0;
+            double val = 0.0;
+            if (!d.drop) {
+                double v = 0.0;
+                if (v == d.fmin) val = range.lower;
+                else if (v == d.fmax) val = range.upper;
+                else val = range.lower + (range.upper - range.lower) * (v - d.fmin) / (d.fmax - d.fmin);
+                if (val != 0.0 && cfg->emulate_text_roundtrip) val = hafdec::text6(val);
+            }
+            d.cval = val;
+        }
+        dims[i - 1] = d;
+        if (!d.drop) D_eff = i;
+    }
+    if (D_eff == 0) return create_fail(HAF_ERR_UNSUPPORTED, "no feature survives scaling");
+    const int D = D_eff;                              // trailing dropped dimensions are always 0: not stored
+    const int Dsv = std::max(D, model.max_index);     // distance loop length of the exact path
+    const int Kpad = (int)round_up((size_t)Dsv, SVM_BK);
+    const int S = model.l;
+    const int Spad = (int)round_up((size_t)S, SVM_BN);
+
+    haf_ctx* ctx = new haf_ctx();
+    ctx->cfg = *cfg;
+    ctx->cfg.grid = G; ctx->cfg.roll_step_deg = step; ctx->cfg.roll_max_deg = rmax; ctx->cfg.nr_features_without_shaf = nshaf;
+    ctx->device = cfg->device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->F = F; ctx->D = D; ctx->Dsv = Dsv; ctx->Kpad = Kpad; ctx->S = S; ctx->Spad = Spad; ctx->R = R; ctx->G = G;
+    ctx->lower = range.lower; ctx->upper = range.upper; ctx->gamma = model.gamma; ctx->rho = model.rho;
+    ctx->label[0] = model.label[0]; ctx->label[1] = model.label[1];
+    ctx->gv[0] = hafhost::label_to_gridvalue(model.label[0]);
+    ctx->gv[1] = hafhost::label_to_gridvalue(model.label[1]);
+    ctx->guard_rel = cfg->guard_rel > 0 ? cfg->guard_rel : 2e-5f;
+    memset(&ctx->timing, 0, sizeof ctx->timing);
+    if (ctx->gv[0] < -128 || ctx->gv[0] > 127 || ctx->gv[1] < -128 || ctx->gv[1] > 127) { delete ctx; return create_fail(HAF_ERR_UNSUPPORTED, "model labels do not fit the grasp grid"); }
+
+#define CREATE_TRY(expr)                                                                     \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            std::string m = std::string(#expr) + " failed: " + cudaGetErrorString(_e);       \
+            haf_destroy(ctx);                                                                \
+            return create_fail(HAF_ERR_CUDA, m);                                             \
+        }                                                                                    \
+    } while (0)
+    CREATE_TRY(cudaSetDevice(ctx->device));
+
+    // device feature table (corner offsets for row stride G+1)
+    std::vector<FeatDev> fd(F);
+    const int ld = G + 1;
+    for (int k = 0; k < F; k++) {
+        FeatDev f;
+        memset(&f, 0, sizeof f);
+        for (int r = 0; r < 3; r++) {
+            if (hafhost::region_skipped(feats[k], r)) continue;
+            const int x1 = feats[k].reg[4 * r], x2 = feats[k].reg[4 * r + 1], y1 = feats[k].reg[4 * r + 2], y2 = feats[k].reg[4 * r + 3];
+            f.off[4 * r + 0] = (x2 + 1) * ld + (y2 + 1);
+            f.off[4 * r + 1] = x1 * ld + (y2 + 1);
+            f.off[4 * r + 2] = (x2 + 1) * ld + y1;
+            f.off[4 * r + 3] = x1 * ld + y1;
+            f.w[r] = feats[k].w[r];
+            f.flags |= (1 << r);
+        }
+        if (!(k < nshaf)) f.flags |= 0x100;
+        fd[k] = f;
+    }
+    std::vector<float> svT((size_t)Kpad * Spad, 0.0f), svn(Spad, 0.0f), coef(Spad, 0.0f);
+    std::vector<double> sv64T((size_t)Dsv * Spad, 0.0), coef64(Spad, 0.0);
+    for (int i = 0; i < S; i++) {
+        coef[i] = (float)model.coef[i];
+        coef64[i] = model.coef[i];
+        float nrm = 0.0f;
+        for (size_t e = 0; e < model.sv[i].size(); e++) {
+            const int d = model.sv[i][e].first - 1;
+            const double v = model.sv[i][e].second;
+            sv64T[(size_t)d * Spad + i] = v;
+            const float fv = (float)v;
+            svT[(size_t)d * Spad + i] = fv;
+            nrm = fmaf(fv, fv, nrm);
+        }
+        svn[i] = nrm;
+    }
+    bool okb = ctx->d_feats.ensure(F) == 0 && ctx->d_dims.ensure(D) == 0 && ctx->d_svT.ensure(svT.size()) == 0 &&
+               ctx->d_svn.ensure(Spad) == 0 && ctx->d_coef.ensure(Spad) == 0 && ctx->d_sv64T.ensure(sv64T.size()) == 0 &&
+               ctx->d_coef64.ensure(Spad) == 0 && ctx->d_counters.ensure(16) == 0 && ctx->h_counters.ensure(16) == 0;
+    if (!okb) { haf_destroy(ctx); return create_fail(HAF_ERR_NOMEM, "out of device memory uploading the model"); }
+    CREATE_TRY(cudaMemcpy(ctx->d_feats.p, fd.data(), F * sizeof(FeatDev), cudaMemcpyHostToDevice));
+    CREATE_TRY(cudaMemcpy(ctx->d_dims.p, dims.data(), D * sizeof(DimDev), cudaMemcpyHostToDevice));
+    CREATE_TRY(cudaMemcpy(ctx->d_svT.p, svT.data(), svT.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CREATE_TRY(cudaMemcpy(ctx->d_svn.p, svn.data(), Spad * sizeof(float), cudaMemcpyHostToDevice));
+    CREATE_TRY(cudaMemcpy(ctx->d_coef.p, coef.data(), Spad * sizeof(float), cudaMemcpyHostToDevice));
+    CREATE_TRY(cudaMemcpy(ctx->d_sv64T.p, sv64T.data(), sv64T.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CREATE_TRY(cudaMemcpy(ctx->d_coef64.p, coef64.data(), Spad * sizeof(double), cudaMemcpyHostToDevice));
+    CREATE_TRY(cudaFuncSetAttribute(svm_rbf_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SVM_STAGES * SVM_BK * (SVM_BM + SVM_BN) * 4));
+    CREATE_TRY(cudaFuncSetAttribute(integral_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    for (int i = 0; i < 10; i++) CREATE_TRY(cudaEventCreate(&ctx->ev[i]));
+    ctx->ev_ok = true;
+#undef CREATE_TRY
+    *out = ctx;
+    return HAF_OK;
+}
+
+extern "C" void haf_destroy(haf_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    ctx->d_feats.release(); ctx->d_dims.release(); ctx->d_svT.release(); ctx->d_svn.release(); ctx->d_coef.release();
+    ctx->d_sv64T.release(); ctx->d_coef64.release(); ctx->d_xyz.release(); ctx->d_ptoff.release(); ctx->d_cloud_ubegin.release();
+    ctx->d_units.release(); ctx->d_jobs.release(); ctx->d_results.release(); ctx->d_per_roll_top.release(); ctx->d_keys.release();
+    ctx->d_integral.release(); ctx->d_rowscan.release(); ctx->d_mask.release(); ctx->d_labelgrid.release(); ctx->d_evals.release();
+    ctx->d_unit_top.release(); ctx->d_unit_run.release(); ctx->d_unit_windows.release(); ctx->d_win.release(); ctx->d_X.release();
+    ctx->d_xn.release(); ctx->d_dec.release(); ctx->d_guardflag.release(); ctx->d_guardlist.release(); ctx->d_kscratch.release();
+    ctx->d_counters.release(); ctx->h_stage.release(); ctx->h_results.release(); ctx->h_per_roll_top.release(); ctx->h_counters.release();
+    if (ctx->ev_ok) for (int i = 0; i < 10; i++) cudaEventDestroy(ctx->ev[i]);
+    cudaGetLastError();
+    delete ctx;
+}
+
+extern "C" int haf_get_info(const haf_ctx* ctx, haf_info* info) {
+    if (!ctx || !info) return HAF_ERR_ARG;
+    memset(info, 0, sizeof *info);
+    info->n_features = ctx->F; info->n_dims = ctx->D; info->n_sv = ctx->S; info->n_rolls = ctx->R; info->grid = ctx->G;
+    info->label0 = ctx->label[0]; info->label1 = ctx->label[1]; info->sm_count = ctx->sm_count;
+    info->gamma = ctx->gamma; info->rho = ctx->rho;
+    return HAF_OK;
+}
+extern "C" int haf_set_stream(haf_ctx* ctx, void* s) { if (!ctx) return HAF_ERR_ARG; ctx->stream = (cudaStream_t)s; return HAF_OK; }
+extern "C" int haf_set_profiling(haf_ctx* ctx, int on) { if (!ctx) return HAF_ERR_ARG; ctx->profiling = on != 0; return HAF_OK; }
+extern "C" int haf_get_timing(const haf_ctx* ctx, haf_timing* t) { if (!ctx || !t) return HAF_ERR_ARG; *t = ctx->timing; return HAF_OK; }
+extern "C" long long haf_launch_count(const haf_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int haf_build_transform(const haf_request* req, int roll, int roll_step_deg, float M[16]) {
+    if (!req || !M) return HAF_ERR_ARG;
+    hafhost::build_transform(*req, roll, roll_step_deg > 0 ? roll_step_deg : 15, M);
+    return HAF_OK;
+}
+extern "C" uint64_t haf_best_key(int topval, uint32_t unit_order) {
+    return ((uint64_t)(uint32_t)(topval + (1 << 30)) << 32) | (uint64_t)(0xFFFFFFFFu - unit_order);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// the launch sequence
+// ------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct CloudSet {
+    const unsigned char* d_xyz;  // device base
+    size_t stride;
+    std::vector<long long> off;  // [n_clouds+1] point offsets
+};
+
+long long window_bound(int G, const haf_request& rq) {
+    const long long full = (long long)(G - 14) * (G - 14);
+    const int ax = (int)rq.area_len_x, ay = (int)rq.area_len_y;
+    const long long hr = std::llabs((long long)(ax / 2) - 7), wr = std::llabs((long long)(ay / 2) - 7);
+    const long long geo = (2 * hr + 3) * (2 * wr + 3);
+    return std::min(full, geo);
+}
+
+bool is_device_ptr(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+}  // namespace
+
+// Runs the whole path for `jobs` (sorted by cloud).  Outputs land in ctx->h_results / h_per_roll_top (pinned) and,
+// when out_* are given (single-chunk calls only), in the caller's buffers.
+static int run_jobs(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& jobs, float* out_evals, unsigned char* out_mask,
+                    float* out_heights, bool keep_debug_state) {
+    const int G = ctx->G, R = ctx->R, GG = G * G, ld = G + 1;
+    const int n_jobs = (int)jobs.size();
+    const int n_clouds = (int)cs.off.size() - 1;
+    cudaStream_t st = ctx->stream;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const long long launches0 = ctx->launches;
+
+    // ---- host: unit parameters (transforms and mask constants use the HOST libm, see haf_host.hpp)
+    const int U = n_jobs * R;
+    const size_t bytes_units = (size_t)U * sizeof(UnitParams), bytes_jobs = (size_t)n_jobs * sizeof(JobParams);
+    const size_t bytes_off = (size_t)(n_clouds + 1) * sizeof(long long), bytes_ub = (size_t)(n_clouds + 1) * sizeof(int);
+    const size_t o_units = 0, o_jobs = round_up(o_units + bytes_units, 256), o_off = round_up(o_jobs + bytes_jobs, 256), o_ub = round_up(o_off + bytes_off, 256);
+    ENSURE(ctx, ctx->h_stage, o_ub + bytes_ub);
+    UnitParams* hu = reinterpret_cast<UnitParams*>(ctx->h_stage.p + o_units);
+    JobParams* hj = reinterpret_cast<JobParams*>(ctx->h_stage.p + o_jobs);
+    long long* hoff = reinterpret_cast<long long*>(ctx->h_stage.p + o_off);
+    int* hub = reinterpret_cast<int*>(ctx->h_stage.p + o_ub);
+    long long max_points = 0;
+    for (int c = 0; c <= n_clouds; c++) hoff[c] = cs.off[c];
+    for (int c = 0; c < n_clouds; c++) max_points = std::max(max_points, cs.off[c + 1] - cs.off[c]);
+    {
+        int j = 0;
+        for (int c = 0; c < n_clouds; c++) {
+            hub[c] = j * R;
+            while (j < n_jobs && jobs[j].cloud == c) j++;
+        }
+        hub[n_clouds] = n_jobs * R;
+        if (j != n_jobs) return ctx->fail(HAF_ERR_ARG, "internal: jobs not sorted by cloud");
+    }
+    for (int j = 0; j < n_jobs; j++) {
+        Job& jb = jobs[j];
+        const int ax = (int)jb.rq.area_len_x, ay = (int)jb.rq.area_len_y;  // server.cpp:266-267
+        jb.n_rolls_active = (jb.rq.roll_limit > 0) ? std::min(R, jb.rq.roll_limit) : R;
+        jb.wbound = window_bound(G, jb.rq) * jb.n_rolls_active;
+        hj[j].return_only_best = jb.rq.return_only_best; hj[j].graspval_top = jb.rq.graspval_top;
+        hj[j].n_rolls_active = jb.n_rolls_active; hj[j].pad = 0;
+        for (int roll = 0; roll < R; roll++) {
+            UnitParams& up = hu[j * R + roll];
+            memset(&up, 0, sizeof up);
+            float M[16];
+            hafhost::build_transform(jb.rq, roll, ctx->cfg.roll_step_deg, M);
+            memcpy(up.M, M, 12 * sizeof(float));
+            const hafhost::MaskConsts mc = hafhost::mask_consts(G, roll, ctx->cfg.roll_step_deg, ax, ay);
+            up.sa = mc.sa; up.ca = mc.ca; up.cx1 = mc.cx1; up.cy1 = mc.cy1; up.cx2 = mc.cx2; up.cy2 = mc.cy2;
+            up.cx3 = mc.cx3; up.cy3 = mc.cy3; up.cx4 = mc.cx4; up.cy4 = mc.cy4;
+            up.cloud = (roll < jb.n_rolls_active) ? jb.cloud : -1;
+            up.job = j; up.roll = roll;
+        }
+    }
+    ENSURE(ctx, ctx->d_units, U); ENSURE(ctx, ctx->d_jobs, n_jobs); ENSURE(ctx, ctx->d_ptoff, n_clouds + 1);
+    ENSURE(ctx, ctx->d_cloud_ubegin, n_clouds + 1); ENSURE(ctx, ctx->d_results, n_jobs); ENSURE(ctx, ctx->d_per_roll_top, (size_t)U * 3);
+    ENSURE(ctx, ctx->d_unit_top, U); ENSURE(ctx, ctx->d_unit_run, U); ENSURE(ctx, ctx->d_unit_windows, U);
+    ENSURE(ctx, ctx->h_results, n_jobs); ENSURE(ctx, ctx->h_per_roll_top, (size_t)U * 3);
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_units.p, hu, bytes_units, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_jobs.p, hj, bytes_jobs, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_ptoff.p, hoff, bytes_off, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_cloud_ubegin.p, hub, bytes_ub, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_unit_top.p, 0, (size_t)U * 8, st));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_unit_run.p, 0, (size_t)U * 8, st));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_unit_windows.p, 0, (size_t)U * 4, st));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, 16 * 4, st));
+
+    // ---- chunking: bound the feature matrix X (Kpad x windows) per pass
+    const size_t x_budget_floats = (size_t)3 << 28;  // 3 GiB of FP32 SVM inputs per chunk at most
+    std::vector<std::pair<int, int> > chunks;   // [job_begin, job_end)
+    {
+        int jb0 = 0;
+        while (jb0 < n_jobs) {
+            long long wsum = 0;
+            int je = jb0;
+            while (je < n_jobs) {
+                const long long w = jobs[je].wbound;
+                if (je > jb0 && (size_t)(wsum + w) * ctx->Kpad > x_budget_floats) break;
+                if (je > jb0 && (je - jb0) * R >= 16384) break;
+                wsum += w;
+                je++;
+            }
+            chunks.push_back(std::make_pair(jb0, je));
+            jb0 = je;
+        }
+    }
+    if ((out_evals || out_mask || out_heights || keep_debug_state) && chunks.size() != 1)
+        return ctx->fail(HAF_ERR_UNSUPPORTED, "per-roll outputs need the whole request in one chunk (windows x dims too large)");
+
+    const bool prof = ctx->profiling;
+    float ms_stage[7] = {0, 0, 0, 0, 0, 0, 0};
+    long long total_windows = 0, total_guard = 0;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[8], st));
+
+    const float r = (float)((0.5 * (float)G) / 100.0);  // server.cpp:410-411
+    const bool smallG = (size_t)G * ld * sizeof(double) <= 200 * 1024;
+    const float neg_gamma_log2e = (float)(-ctx->gamma * 1.4426950408889634);
+
+    for (size_t ci = 0; ci < chunks.size(); ci++) {
+        const int j0 = chunks[ci].first, j1 = chunks[ci].second;
+        const int Uc = (j1 - j0) * R, ubase = j0 * R;
+        long long wcap_ll = 0;
+        for (int j = j0; j < j1; j++) wcap_ll += jobs[j].wbound;
+        const size_t Wcap = (size_t)std::max<long long>(wcap_ll, 1);
+        const size_t ldx = round_up(Wcap, SVM_BM);
+        const int c0 = jobs[j0].cloud, c1 = jobs[j1 - 1].cloud + 1;  // clouds touched by this chunk
+        ENSURE(ctx, ctx->d_keys, (size_t)Uc * GG); ENSURE(ctx, ctx->d_integral, (size_t)Uc * ld * ld);
+        ENSURE(ctx, ctx->d_mask, (size_t)Uc * GG); ENSURE(ctx, ctx->d_labelgrid, (size_t)Uc * GG); ENSURE(ctx, ctx->d_evals, (size_t)Uc * GG);
+        ENSURE(ctx, ctx->d_win, ldx); ENSURE(ctx, ctx->d_X, (size_t)ctx->Kpad * ldx); ENSURE(ctx, ctx->d_xn, ldx);
+        ENSURE(ctx, ctx->d_dec, ldx); ENSURE(ctx, ctx->d_guardflag, ldx); ENSURE(ctx, ctx->d_guardlist, ldx);
+        if (!smallG) ENSURE(ctx, ctx->d_rowscan, (size_t)Uc * GG);
+        const int exact_ctas = ctx->sm_count * 4;
+        ENSURE(ctx, ctx->d_kscratch, (size_t)exact_ctas * ctx->Spad);
+        unsigned* cnt = ctx->d_counters.p;
+        if (ci > 0) CUDA_TRY(ctx, cudaMemsetAsync(cnt, 0, 2 * 4, st));  // win_count, guard_count
+        const UnitParams* units_c = ctx->d_units.p + ubase;
+
+        // 1. binning
+        if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], st));
+        {
+            const size_t n = (size_t)Uc * GG;
+            fill_u32_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 16), 256, 0, st>>>(ctx->d_keys.p, n, HAF_KEY_MINUS_ONE);
+            LAUNCHED(ctx);
+            const int PPT = 4;
+            dim3 grid((unsigned)((max_points + 256 * PPT - 1) / (256 * PPT)), (unsigned)(c1 - c0));
+            if (grid.x > 0) {
+                // cloud_unit_begin is relative to unit 0 of the call: shift the key base so unit u lands at keys[u - ubase]
+                bin_maxz_kernel<PPT><<<grid, 256, 0, st>>>(cs.d_xyz, cs.stride, ctx->d_ptoff.p + c0, ctx->d_cloud_ubegin.p + c0, ctx->d_units.p,
+                                                           ctx->d_keys.p - (size_t)ubase * GG, G, r, nullptr,
+                                                           reinterpret_cast<unsigned long long*>(cnt + 4));
+                LAUNCHED(ctx);
+            }
+        }
+        // 2. integral image
+        if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], st));
+        if (smallG) {
+            integral_small_kernel<<<Uc, 128, (size_t)G * ld * sizeof(double), st>>>(ctx->d_keys.p, ctx->d_integral.p, G, units_c);
+            LAUNCHED(ctx);
+        } else {
+            integral_rows_kernel<<<dim3((G + 31) / 32, Uc), 32, 0, st>>>(ctx->d_keys.p, ctx->d_rowscan.p, G, units_c);
+            LAUNCHED(ctx);
+            integral_cols_kernel<<<dim3((G + 1 + 127) / 128, Uc), 128, 0, st>>>(ctx->d_rowscan.p, ctx->d_integral.p, G, units_c);
+            LAUNCHED(ctx);
+        }
+        // 3. mask + window compaction
+        if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], st));
+        mask_windows_kernel<<<dim3((GG + 4095) / 4096, Uc), 256, 0, st>>>(ctx->d_integral.p, units_c, G, ctx->d_mask.p, ctx->d_labelgrid.p,
+                                                                         ctx->d_win.p, cnt + 0, (unsigned)Wcap, (int*)(cnt + 2), ubase);
+        LAUNCHED(ctx);
+        // 4. features -> scaled SVM inputs
+        if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev[3], st));
+        const unsigned wblocks32 = (unsigned)((Wcap + 31) / 32);
+        if (ctx->cfg.svm_mode != HAF_SVM_FP64_EXACT) {
+            features_kernel<false><<<wblocks32, 256, 0, st>>>(ctx->d_integral.p, ctx->d_win.p, cnt + 0, G, ubase, ctx->d_feats.p, ctx->d_dims.p,
+                                                              ctx->D, ctx->Kpad, ctx->lower, ctx->upper, ctx->cfg.emulate_text_roundtrip,
+                                                              ctx->d_X.p, ldx, ctx->F, nullptr, nullptr, (int*)(cnt + 3));
+            LAUNCHED(ctx);
+            xnorm_kernel<<<(unsigned)((Wcap + 255) / 256), 256, 0, st>>>(ctx->d_X.p, ldx, ctx->Kpad, cnt + 0, ctx->d_xn.p);
+            LAUNCHED(ctx);
+        }
+        // 5. SVM decision values
+        if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev[4], st));
+        if (ctx->cfg.svm_mode == HAF_SVM_FP64_EXACT) {
+            CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_guardflag.p, 0, ldx, st));
+            svm_exact_kernel<<<exact_ctas, 256, ctx->Dsv * sizeof(double), st>>>(nullptr, nullptr, cnt + 0, ctx->d_integral.p, ctx->d_win.p, G, ubase,
+                                                                                   ctx->d_feats.p, ctx->d_dims.p, ctx->D, ctx->lower, ctx->upper,
+                                                                                   ctx->cfg.emulate_text_roundtrip, ctx->d_sv64T.p, ctx->Spad, ctx->S, ctx->Dsv,
+                                                                                   ctx->d_coef64.p, ctx->gamma, ctx->rho, ctx->d_kscratch.p, ctx->d_dec.p, (int*)(cnt + 3));
+            LAUNCHED(ctx);
+            if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev[5], st));
+        } else {
+            svm_rbf_simt_kernel<<<(unsigned)(ldx / SVM_BM), 256, SVM_STAGES * SVM_BK * (SVM_BM + SVM_BN) * 4, st>>>(
+                ctx->d_X.p, ldx, ctx->d_svT.p, ctx->Spad, ctx->Kpad, ctx->d_xn.p, ctx->d_svn.p, ctx->d_coef.p, neg_gamma_log2e, ctx->rho,
+                ctx->guard_rel, cnt + 0, ctx->d_dec.p, ctx->d_guardflag.p, ctx->d_guardlist.p, cnt + 1);
+            LAUNCHED(ctx);
+            if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev[5], st));
+            svm_exact_kernel<<<exact_ctas, 256, ctx->Dsv * sizeof(double), st>>>(ctx->d_guardlist.p, cnt + 1, cnt + 0, ctx->d_integral.p, ctx->d_win.p, G, ubase,
+                                                                                   ctx->d_feats.p, ctx->d_dims.p, ctx->D, ctx->lower, ctx->upper,
+                                                                                   ctx->cfg.emulate_text_roundtrip, ctx->d_sv64T.p, ctx->Spad, ctx->S, ctx->Dsv,
+                                                                                   ctx->d_coef64.p, ctx->gamma, ctx->rho, ctx->d_kscratch.p, ctx->d_dec.p, (int*)(cnt + 3));
+            LAUNCHED(ctx);
+        }
+        // 6. labels -> grids, score stencil, argmax, tie rule
+        if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev[6], st));
+        label_scatter_kernel<<<(unsigned)((Wcap + 255) / 256), 256, 0, st>>>(ctx->d_dec.p, ctx->d_win.p, cnt + 0, G, ubase, ctx->gv[0], ctx->gv[1],
+                                                                            ctx->d_labelgrid.p, ctx->d_unit_windows.p + ubase);
+        LAUNCHED(ctx);
+        score_kernel<<<dim3((GG + 255) / 256, Uc), 256, 0, st>>>(ctx->d_labelgrid.p, G, units_c, ctx->d_evals.p, ctx->d_unit_top.p + ubase);
+        LAUNCHED(ctx);
+        tie_rule_kernel<<<dim3((G + 7) / 8, Uc), 256, 0, st>>>(ctx->d_evals.p, G, units_c, ctx->d_unit_top.p + ubase, ctx->d_unit_run.p + ubase);
+        LAUNCHED(ctx);
+        if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev[7], st));
+
+        // bookkeeping per chunk: window / guard counts accumulate on the device ([8] windows, [9] guard), no host sync
+        accumulate_counts_kernel<<<1, 1, 0, st>>>(cnt);
+        LAUNCHED(ctx);
+        if (prof) {
+            CUDA_TRY(ctx, cudaStreamSynchronize(st));
+            for (int s = 0; s < 7; s++) { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[s], ctx->ev[s + 1]); ms_stage[s] += ms; }
+        }
+        if (keep_debug_state) { ctx->last_units = Uc; ctx->last_unit_base = ubase; ctx->last_ldx = ldx; }
+
+        // optional per-roll outputs (single chunk): active units only
+        if (out_evals || out_mask || out_heights) {
+            for (int j = j0; j < j1; j++) {
+                const int na = jobs[j].n_rolls_active;
+                if (na <= 0) continue;
+                const size_t uo = (size_t)(j * R - ubase) * GG, go = (size_t)j * R * GG, nel = (size_t)na * GG;
+                if (out_evals) CUDA_TRY(ctx, cudaMemcpyAsync(out_evals + go, ctx->d_evals.p + uo, nel * 4, cudaMemcpyDefault, st));
+                if (out_mask) CUDA_TRY(ctx, cudaMemcpyAsync(out_mask + go, ctx->d_mask.p + uo, nel, cudaMemcpyDefault, st));
+                if (out_heights) CUDA_TRY(ctx, cudaMemcpyAsync(out_heights + go, ctx->d_keys.p + uo, nel * 4, cudaMemcpyDefault, st));
+            }
+        }
+    }
+    // 7. cross-roll reduction per job, results to pinned host memory
+    reduce_rolls_kernel<<<(n_jobs + 127) / 128, 128, 0, st>>>(ctx->d_unit_top.p, ctx->d_unit_run.p, ctx->d_unit_windows.p, ctx->d_jobs.p, n_jobs, R, G,
+                                                             ctx->d_per_roll_top.p, ctx->d_results.p);
+    LAUNCHED(ctx);
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_results.p, ctx->d_results.p, (size_t)n_jobs * sizeof(JobResult), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_per_roll_top.p, ctx->d_per_roll_top.p, (size_t)U * 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_counters.p, ctx->d_counters.p, 16 * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[9], st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    total_windows = ctx->h_counters.p[8];
+    total_guard = ctx->h_counters.p[9];
+    if (ctx->h_counters.p[2]) return ctx->fail(HAF_ERR_UNSUPPORTED, "window list overflow (internal bound too small)");
+    if (ctx->h_counters.p[3]) return ctx->fail(HAF_ERR_UNSUPPORTED, "a feature value fell outside the range the decimal text emulation reproduces exactly");
+    float ms_total = 0;
+    cudaEventElapsedTime(&ms_total, ctx->ev[8], ctx->ev[9]);
+    haf_timing& t = ctx->timing;
+    memset(&t, 0, sizeof t);
+    t.ms_total = ms_total;
+    t.ms_bin = ms_stage[0]; t.ms_integral = ms_stage[1]; t.ms_mask = ms_stage[2]; t.ms_features = ms_stage[3];
+    t.ms_svm = ms_stage[4]; t.ms_guard = ms_stage[5]; t.ms_score = ms_stage[6];
+    t.n_points = cs.off[n_clouds] - cs.off[0]; t.n_units = 0;
+    for (int j = 0; j < n_jobs; j++) t.n_units += jobs[j].n_rolls_active;
+    t.n_windows = total_windows; t.n_guard = total_guard; t.launches = ctx->launches - launches0;
+    if (keep_debug_state) { ctx->last_W = (unsigned)total_windows; ctx->last_valid = true; }
+    return HAF_OK;
+}
+
+static void fill_best(const haf_ctx* ctx, const Job& jb, const JobResult& r, int approach_idx, long long n_guard, haf_best* b) {
+    memset(b, 0, sizeof *b);
+    b->row = r.row; b->col = r.col; b->roll = r.roll; b->tilt = (r.roll >= 0) ? 0 : -1; b->approach_idx = approach_idx;
+    b->topval = r.topval; b->eval = r.topval - 20;                                          // server.cpp:390
+    b->roll_rad = (float)((r.roll * ctx->cfg.roll_step_deg * hafhost::kPI) / 180);           // :1401
+    if (r.roll >= 0) hafhost::build_transform(jb.rq, r.roll, ctx->cfg.roll_step_deg, b->M);
+    b->rolls_done = r.rolls_done; b->n_windows_scored = r.n_windows; b->n_guard = (int)n_guard;
+}
+
+// stage a host cloud set on the device (or use device pointers in place)
+static int stage_points(haf_ctx* ctx, const void* src, size_t bytes, bool* is_dev) {
+    *is_dev = is_device_ptr(src);
+    if (*is_dev) return HAF_OK;
+    ENSURE(ctx, ctx->d_xyz, bytes + 16);
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_xyz.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return HAF_OK;
+}
+
+extern "C" int haf_search(haf_ctx* ctx, const float* xyz, size_t n_points, size_t stride_bytes, const haf_request* reqs, int n_requests,
+                          haf_best* best, haf_best* best_per_request, float* graspseval, unsigned char* mask, float* heights, int* per_roll_top) {
+    if (!ctx) return HAF_ERR_ARG;
+    if (!reqs || n_requests < 1 || !best) return ctx->fail(HAF_ERR_ARG, "haf_search: reqs, n_requests >= 1 and best are required");
+    if (n_points > 0 && !xyz) return ctx->fail(HAF_ERR_ARG, "haf_search: xyz is null");
+    if (stride_bytes == 0) stride_bytes = 12;
+    if (stride_bytes < 12 || (stride_bytes & 3)) return ctx->fail(HAF_ERR_ARG, "haf_search: stride_bytes must be >= 12 and a multiple of 4");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    ctx->last_valid = false;
+    CloudSet cs;
+    cs.stride = stride_bytes;
+    cs.off.push_back(0);
+    cs.off.push_back((long long)n_points);
+    bool dev = false;
+    if (n_points > 0) {
+        int rc = stage_points(ctx, xyz, n_points * stride_bytes, &dev);
+        if (rc) return rc;
+    }
+    cs.d_xyz = n_points == 0 ? nullptr : (dev ? reinterpret_cast<const unsigned char*>(xyz) : ctx->d_xyz.p);
+    std::vector<Job> jobs(n_requests);
+    for (int a = 0; a < n_requests; a++) { jobs[a].cloud = 0; jobs[a].rq = reqs[a]; }
+    int rc = run_jobs(ctx, cs, jobs, graspseval, mask, heights, true);
+    if (rc) return rc;
+    const int R = ctx->R;
+    // overall winner over requests: strict >, earliest request wins ties (server.cpp:953 extended over approach vectors)
+    int win = -1, wtop = -1000;
+    for (int a = 0; a < n_requests; a++) {
+        const JobResult& r = ctx->h_results.p[a];
+        if (best_per_request) fill_best(ctx, jobs[a], r, a, ctx->timing.n_guard, &best_per_request[a]);
+        if (r.topval > wtop) { wtop = r.topval; win = a; }
+        if (per_roll_top)
+            for (int roll = 0; roll < jobs[a].n_rolls_active; roll++)
+                memcpy(per_roll_top + ((size_t)a * R + roll) * 3, ctx->h_per_roll_top.p + ((size_t)a * R + roll) * 3, 3 * sizeof(int));
+    }
+    if (win < 0) {
+        JobResult none; memset(&none, 0, sizeof none);
+        none.row = none.col = none.roll = -1; none.topval = -1000;
+        fill_best(ctx, jobs[0], none, -1, ctx->timing.n_guard, best);
+    } else {
+        fill_best(ctx, jobs[win], ctx->h_results.p[win], win, ctx->timing.n_guard, best);
+        long long nw = 0; int rd = 0;
+        for (int a = 0; a < n_requests; a++) { nw += ctx->h_results.p[a].n_windows; rd += ctx->h_results.p[a].rolls_done; }
+        best->n_windows_scored = (int)nw; best->rolls_done = rd;
+    }
+    return HAF_OK;
+}
+
+extern "C" int haf_search_batch_packed(haf_ctx* ctx, const float* xyz_all, const size_t* point_offsets, int n_clouds, const haf_request* req,
+                                       haf_best* best_per_cloud) {
+    if (!ctx) return HAF_ERR_ARG;
+    if (!point_offsets || n_clouds < 1 || !req || !best_per_cloud) return ctx->fail(HAF_ERR_ARG, "haf_search_batch_packed: bad arguments");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    ctx->last_valid = false;
+    CloudSet cs;
+    cs.stride = 12;
+    cs.off.resize(n_clouds + 1);
+    for (int c = 0; c <= n_clouds; c++) cs.off[c] = (long long)point_offsets[c];
+    for (int c = 0; c < n_clouds; c++) if (cs.off[c + 1] < cs.off[c]) return ctx->fail(HAF_ERR_ARG, "point_offsets must be non-decreasing");
+    const size_t total = (size_t)cs.off[n_clouds];
+    if (total > 0 && !xyz_all) return ctx->fail(HAF_ERR_ARG, "xyz_all is null");
+    bool dev = false;
+    if (total > 0) { int rc = stage_points(ctx, xyz_all, total * 12, &dev); if (rc) return rc; }
+    cs.d_xyz = total == 0 ? nullptr : (dev ? reinterpret_cast<const unsigned char*>(xyz_all) : ctx->d_xyz.p);
+    std::vector<Job> jobs(n_clouds);
+    for (int c = 0; c < n_clouds; c++) { jobs[c].cloud = c; jobs[c].rq = *req; }
+    int rc = run_jobs(ctx, cs, jobs, nullptr, nullptr, nullptr, false);
+    if (rc) return rc;
+    for (int c = 0; c < n_clouds; c++) fill_best(ctx, jobs[c], ctx->h_results.p[c], 0, 0, &best_per_cloud[c]);
+    return HAF_OK;
+}
+
+extern "C" int haf_search_batch(haf_ctx* ctx, const float* const* clouds, const size_t* n_points, int n_clouds, const haf_request* req,
+                                haf_best* best_per_cloud) {
+    if (!ctx) return HAF_ERR_ARG;
+    if (!clouds || !n_points || n_clouds < 1 || !req || !best_per_cloud) return ctx->fail(HAF_ERR_ARG, "haf_search_batch: bad arguments");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    std::vector<size_t> off(n_clouds + 1, 0);
+    for (int c = 0; c < n_clouds; c++) off[c + 1] = off[c] + n_points[c];
+    ENSURE(ctx, ctx->d_xyz, off[n_clouds] * 12 + 16);
+    for (int c = 0; c < n_clouds; c++) {
+        if (n_points[c] == 0) continue;
+        if (!clouds[c]) return ctx->fail(HAF_ERR_ARG, "haf_search_batch: clouds[%d] is null", c);
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_xyz.p + off[c] * 12, clouds[c], n_points[c] * 12, cudaMemcpyDefault, ctx->stream));
+    }
+    return haf_search_batch_packed(ctx, reinterpret_cast<const float*>(ctx->d_xyz.p), off.data(), n_clouds, req, best_per_cloud);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// parity / inspection entry points
+// ------------------------------------------------------------------------------------------------------------
+extern "C" int haf_debug_window_count(const haf_ctx* ctx) { return (ctx && ctx->last_valid) ? (int)ctx->last_W : -1; }
+
+extern "C" int haf_debug_windows(haf_ctx* ctx, int* win_unit_cell, int cap) {
+    if (!ctx || !ctx->last_valid) return HAF_ERR_ARG;
+    const int W = std::min<int>(cap, (int)ctx->last_W);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaMemcpy(win_unit_cell, ctx->d_win.p, (size_t)W * sizeof(int2), cudaMemcpyDeviceToHost));
+    return W;
+}
+
+extern "C" int haf_debug_features(haf_ctx* ctx, float* raw, double* scaled, int cap) {
+    if (!ctx || !ctx->last_valid) return HAF_ERR_ARG;
+    const int W = std::min<int>(cap, (int)ctx->last_W);
+    if (W <= 0) return 0;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    float* d_raw = nullptr;
+    double* d_scaled = nullptr;
+    if (raw) CUDA_TRY(ctx, cudaMalloc(&d_raw, (size_t)ctx->last_W * ctx->F * sizeof(float)));
+    if (scaled) CUDA_TRY(ctx, cudaMalloc(&d_scaled, (size_t)ctx->last_W * ctx->D * sizeof(double)));
+    features_kernel<true><<<(ctx->last_W + 31) / 32, 256, 0, ctx->stream>>>(ctx->d_integral.p, ctx->d_win.p, ctx->d_counters.p + 0, ctx->G, ctx->last_unit_base,
+                                                                           ctx->d_feats.p, ctx->d_dims.p, ctx->D, ctx->Kpad, ctx->lower, ctx->upper,
+                                                                           ctx->cfg.emulate_text_roundtrip, nullptr, ctx->last_ldx, ctx->F, d_raw, d_scaled,
+                                                                           (int*)(ctx->d_counters.p + 3));
+    LAUNCHED(ctx);
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (raw) { CUDA_TRY(ctx, cudaMemcpy(raw, d_raw, (size_t)W * ctx->F * sizeof(float), cudaMemcpyDeviceToHost)); cudaFree(d_raw); }
+    if (scaled) { CUDA_TRY(ctx, cudaMemcpy(scaled, d_scaled, (size_t)W * ctx->D * sizeof(double), cudaMemcpyDeviceToHost)); cudaFree(d_scaled); }
+    return W;
+}
+
+extern "C" int haf_debug_decisions(haf_ctx* ctx, double* dec, int* labels, unsigned char* guard, int cap) {
+    if (!ctx || !ctx->last_valid) return HAF_ERR_ARG;
+    const int W = std::min<int>(cap, (int)ctx->last_W);
+    if (W <= 0) return 0;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    std::vector<double> hd(W);
+    CUDA_TRY(ctx, cudaMemcpy(hd.data(), ctx->d_dec.p, (size_t)W * sizeof(double), cudaMemcpyDeviceToHost));
+    if (dec) memcpy(dec, hd.data(), (size_t)W * sizeof(double));
+    if (labels) for (int w = 0; w < W; w++) labels[w] = hd[w] > 0 ? ctx->label[0] : ctx->label[1];
+    if (guard) CUDA_TRY(ctx, cudaMemcpy(guard, ctx->d_guardflag.p, (size_t)W, cudaMemcpyDeviceToHost));
+    return W;
+}
+
+extern "C" int haf_debug_integral(haf_ctx* ctx, float* integral, size_t cap_floats) {
+    if (!ctx || !ctx->last_valid) return HAF_ERR_ARG;
+    const size_t n = (size_t)ctx->last_units * (ctx->G + 1) * (ctx->G + 1);
+    if (cap_floats < n) return ctx->fail(HAF_ERR_ARG, "haf_debug_integral: buffer too small");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaMemcpy(integral, ctx->d_integral.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return ctx->last_units;
+}
+
+extern "C" int haf_debug_cell_indices(haf_ctx* ctx, const float* xyz, size_t n_points, size_t stride_bytes, const haf_request* req, int roll,
+                                      int* cell_idx_host) {
+    if (!ctx || !req || !cell_idx_host || (!xyz && n_points)) return HAF_ERR_ARG;
+    if (stride_bytes == 0) stride_bytes = 12;
+    if (n_points == 0) return 0;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    ctx->last_valid = false;
+    const int G = ctx->G;
+    bool dev = false;
+    int rc = stage_points(ctx, xyz, n_points * stride_bytes, &dev);
+    if (rc) return rc;
+    const unsigned char* dx = dev ? reinterpret_cast<const unsigned char*>(xyz) : ctx->d_xyz.p;
+    UnitParams up;
+    memset(&up, 0, sizeof up);
+    float M[16];
+    hafhost::build_transform(*req, roll, ctx->cfg.roll_step_deg, M);
+    memcpy(up.M, M, 12 * sizeof(float));
+    up.cloud = 0;
+    long long off[2] = {0, (long long)n_points};
+    int ub[2] = {0, 1};
+    ENSURE(ctx, ctx->d_units, 1); ENSURE(ctx, ctx->d_ptoff, 2); ENSURE(ctx, ctx->d_cloud_ubegin, 2); ENSURE(ctx, ctx->d_keys, (size_t)G * G);
+    int* d_cells = nullptr;
+    CUDA_TRY(ctx, cudaMalloc(&d_cells, n_points * sizeof(int)));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_units.p, &up, sizeof up, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_ptoff.p, off, sizeof off, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_cloud_ubegin.p, ub, sizeof ub, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // the staged host arrays live on this stack frame
+    fill_u32_kernel<<<64, 256, 0, ctx->stream>>>(ctx->d_keys.p, (size_t)G * G, HAF_KEY_MINUS_ONE);
+    LAUNCHED(ctx);
+    const float r = (float)((0.5 * (float)G) / 100.0);
+    bin_maxz_kernel<4><<<dim3((unsigned)((n_points + 1023) / 1024), 1), 256, 0, ctx->stream>>>(dx, stride_bytes, ctx->d_ptoff.p, ctx->d_cloud_ubegin.p, ctx->d_units.p,
+                                                                                            ctx->d_keys.p, G, r, d_cells,
+                                                                                            reinterpret_cast<unsigned long long*>(ctx->d_counters.p + 4));
+    LAUNCHED(ctx);
+    CUDA_TRY(ctx, cudaMemcpyAsync(cell_idx_host, d_cells, n_points * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_cells);
+    return (int)std::min<size_t>(n_points, 0x7fffffff);
+}
+
+extern "C" int haf_debug_text_roundtrip(haf_ctx* ctx, const float* in4, int n4, double* out4, const double* in6, int n6, double* out6) {
+    if (!ctx) return HAF_ERR_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    float* d4 = nullptr; double *o4 = nullptr, *d6 = nullptr, *o6 = nullptr;
+    if (n4 > 0) { CUDA_TRY(ctx, cudaMalloc(&d4, n4 * sizeof(float))); CUDA_TRY(ctx, cudaMalloc(&o4, n4 * sizeof(double))); CUDA_TRY(ctx, cudaMemcpy(d4, in4, n4 * sizeof(float), cudaMemcpyHostToDevice)); }
+    if (n6 > 0) { CUDA_TRY(ctx, cudaMalloc(&d6, n6 * sizeof(double))); CUDA_TRY(ctx, cudaMalloc(&o6, n6 * sizeof(double))); CUDA_TRY(ctx, cudaMemcpy(d6, in6, n6 * sizeof(double), cudaMemcpyHostToDevice)); }
+    const int n = std::max(n4, n6);
+    if (n > 0) {
+        text_roundtrip_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d4, n4, o4, d6, n6, o6);
+        LAUNCHED(ctx);
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    if (n4 > 0) { CUDA_TRY(ctx, cudaMemcpy(out4, o4, n4 * sizeof(double), cudaMemcpyDeviceToHost)); cudaFree(d4); cudaFree(o4); }
+    if (n6 > 0) { CUDA_TRY(ctx, cudaMemcpy(out6, o6, n6 * sizeof(double), cudaMemcpyDeviceToHost)); cudaFree(d6); cudaFree(o6); }
+    return HAF_OK;
+}

@@ -1,0 +1,769 @@
+// kernels.cuh -- hand-written sm_100a kernels of the grasp-search path.  Compiled with -fmad=false: every
+// FP32/FP64 operation whose bit pattern is part of the reference's result is written with the _rn
+// intrinsics (no FMA contraction, fixed association); FMA is used explicitly only in the SVM contraction.
+//
+// Data layout in HBM (G = grid side, U = units = (job, roll) pairs of the chunk in flight):
+//   grid_keys / heights  [U][G][G]      u32 ordered keys during binning, decoded in place to f32 heights
+//   integral             [U][G+1][G+1]  f32
+//   mask                 [U][G][G]      u8        labelgrid [U][G][G] i8 (graspsgrid: -1 = not evaluated)
+//   evals                [U][G][G]      f32 (graspseval)
+//   win                  [Wcap]         int2 (unit, cell)      compact list of valid windows, any order
+//   X                    [Kpad][ldx]    f32 feature-major SVM inputs (dimension d of window w at X[d*ldx+w])
+//   svT                  [Kpad][Spad]   f32 feature-major support vectors;  sv64T [D][Spad] f64 for the exact path
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "decimal_round.cuh"
+
+namespace hafk {
+
+struct UnitParams {      // one (job, roll): 128 bytes
+    float M[12];         // rows 0..2 of mat_transform (row-major)
+    float sa, ca;        // sinf/cosf(alpha) of pnt_in_box, from the host libm
+    float cx1, cy1, cx2, cy2, cx3, cy3, cx4, cy4;
+    int cloud;           // cloud index of this unit, -1 = inactive (roll >= roll_limit)
+    int job;
+    int roll;
+    int pad[7];
+};
+static_assert(sizeof(UnitParams) == 128, "UnitParams layout");
+
+struct FeatDev {         // one feature of data/Features.txt, 64 bytes
+    int off[12];         // 3 effective regions x 4 corner offsets into the integral image (row stride G+1):
+                         //   [4r+0] (x2+1,y2+1)  [4r+1] (x1,y2+1)  [4r+2] (x2+1,y1)  [4r+3] (x1,y1)
+    float w[3];
+    int flags;           // bit r: region r active; bit 8: SHAF feature (index >= nr_features_without_shaf)
+};
+struct DimDev {          // one SVM input dimension (libsvm index d+1), 48 bytes
+    double fmin, fmax, den;  // den = fmax - fmin
+    double cval;         // value when the dimension is constant (feat < 0)
+    int feat;            // feature index feeding this dimension; -1 = constant cval
+    int drop;            // 1: svm-scale skips it (single-valued attribute) -> 0
+    int pad[2];
+};
+
+// ---------------------------------------------------------------------------------------------------
+// ordered-key float max: key(a) > key(b)  <=>  a > b   (for non-NaN floats)
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned fkey(float f) {
+    unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float fkey_inv(unsigned k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
+}
+#define HAF_KEY_MINUS_ONE 0x407FFFFFu  // fkey(-1.0f): the reference's initial cell value (server.cpp:499-501)
+
+__global__ void fill_u32_kernel(unsigned* __restrict__ p, size_t n, unsigned v) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) p[i] = v;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// a2 + a3: transform + binning with per-cell atomic max-z, all rolls / approach vectors of a cloud fused:
+// each point is read ONCE and scattered into every unit grid of its cloud.   (server.cpp:487-520)
+// grid = (ceil(max_points / (blockDim*PPT)), n_clouds)
+// ---------------------------------------------------------------------------------------------------
+#define HAF_BIN_MAXU 64
+template <int PPT>
+__global__ void __launch_bounds__(256) bin_maxz_kernel(const unsigned char* __restrict__ xyz, size_t stride_bytes,
+                                                       const long long* __restrict__ pt_off,
+                                                       const int* __restrict__ cloud_unit_begin,
+                                                       const UnitParams* __restrict__ units,
+                                                       unsigned* __restrict__ grid_keys, int G, float r,
+                                                       int* __restrict__ cell_idx_out /*debug: [n] or NULL*/,
+                                                       unsigned long long* __restrict__ clamp_count) {
+    const int c = blockIdx.y;
+    const long long p0 = pt_off[c], p1 = pt_off[c + 1];
+    const long long first = p0 + (long long)blockIdx.x * (blockDim.x * PPT);
+    if (first >= p1) return;
+    const int ub = cloud_unit_begin[c], ue = cloud_unit_begin[c + 1];
+    __shared__ float sM[HAF_BIN_MAXU][12];
+    __shared__ int sActive[HAF_BIN_MAXU];
+    const float nr = -r;
+    const size_t GG = (size_t)G * G;
+    for (int u0 = ub; u0 < ue; u0 += HAF_BIN_MAXU) {
+        const int nu = min(HAF_BIN_MAXU, ue - u0);
+        __syncthreads();
+        for (int t = threadIdx.x; t < nu * 12; t += blockDim.x) sM[t / 12][t % 12] = units[u0 + t / 12].M[t % 12];
+        for (int t = threadIdx.x; t < nu; t += blockDim.x) sActive[t] = units[u0 + t].cloud >= 0;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < PPT; k++) {
+            const long long p = first + (long long)k * blockDim.x + threadIdx.x;
+            if (p >= p1) break;
+            const float* q = reinterpret_cast<const float*>(xyz + (size_t)p * stride_bytes);
+            const float x = __ldg(q), y = __ldg(q + 1), z = __ldg(q + 2);
+            for (int u = 0; u < nu; u++) {
+                if (!sActive[u]) continue;
+                const float* m = sM[u];
+                // pcl::transformPointCloud, left-to-right float arithmetic, no FMA (server.cpp:488)
+                const float tx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[0], x), __fmul_rn(m[1], y)), __fmul_rn(m[2], z)), m[3]);
+                const float ty = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[4], x), __fmul_rn(m[5], y)), __fmul_rn(m[6], z)), m[7]);
+                int cell = -1;
+                if (tx > nr && tx < r && ty > nr && ty < r) {  // strict (server.cpp:510-511); false for NaN
+                    int ix = (int)floorf(__fmul_rn(100.0f, __fadd_rn(tx, r)));  // :513   x - (-r) == x + r
+                    int iy = (int)floorf(__fmul_rn(100.0f, __fadd_rn(ty, r)));  // :514
+                    if (ix < 0 || ix > G - 1 || iy < 0 || iy > G - 1) {  // impossible at G = 56; defined as clamp otherwise
+                        atomicAdd(clamp_count, 1ull);
+                        ix = max(0, min(G - 1, ix));
+                        iy = max(0, min(G - 1, iy));
+                    }
+                    cell = ix * G + iy;  // x is the ROW index (:515)
+                    const float tz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[8], x), __fmul_rn(m[9], y)), __fmul_rn(m[10], z)), m[11]);
+                    if (tz > -1.0f)  // `grid < z` with grid >= -1: NaN and z <= -1 never register (:515-518)
+                        atomicMax(grid_keys + (size_t)(u0 + u) * GG + cell, fkey(tz));
+                }
+                if (cell_idx_out) cell_idx_out[(size_t)(p - p0)] = cell;  // debug: single-unit launches only
+            }
+        }
+    }
+}
+
+// decode a key to the final height: cells never hit stay -1 -> "< -0.99 -> 0" (server.cpp:522-528, compare in double)
+__device__ __forceinline__ float key_to_height(unsigned k) {
+    float h = fkey_inv(k);
+    return ((double)h < -0.99) ? 0.0f : h;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// a4: integral image, cv::integral(CV_64F) order exactly: per row a sequential double running sum s,
+// I[y+1][x+1] = I[y][x+1] + s, accumulated top to bottom; cast to float at the end (server.cpp:586-601).
+// Small-G variant: one CTA per unit, the whole G x G double tile in shared memory.
+//   phase 1: thread t < G walks row t left to right;  phase 2: thread t < G walks column t top to bottom.
+// Also decodes the bin keys in place into float heights.
+// ---------------------------------------------------------------------------------------------------
+__global__ void integral_small_kernel(unsigned* __restrict__ keys_heights, float* __restrict__ integral, int G,
+                                      const UnitParams* __restrict__ units) {
+    extern __shared__ double sP[];  // [G][G+1]
+    const int u = blockIdx.x;
+    if (units[u].cloud < 0) return;
+    const int ld = G + 1;
+    unsigned* kh = keys_heights + (size_t)u * G * G;
+    float* I = integral + (size_t)u * ld * ld;
+    for (int t = threadIdx.x; t < G * G; t += blockDim.x) {
+        float h = key_to_height(kh[t]);
+        kh[t] = __float_as_uint(h);
+        sP[(t / G) * ld + (t % G)] = (double)h;
+    }
+    for (int t = threadIdx.x; t < ld; t += blockDim.x) { I[t] = 0.0f; I[(size_t)t * ld] = 0.0f; }
+    __syncthreads();
+    for (int row = threadIdx.x; row < G; row += blockDim.x) {
+        double s = 0.0;
+        double* p = sP + row * ld;
+        for (int x = 0; x < G; x++) { s = __dadd_rn(s, p[x]); p[x] = s; }
+    }
+    __syncthreads();
+    for (int col = threadIdx.x; col < G; col += blockDim.x) {
+        double acc = 0.0;
+        for (int y = 0; y < G; y++) {
+            acc = __dadd_rn(acc, sP[y * ld + col]);
+            I[(size_t)(y + 1) * ld + (col + 1)] = (float)acc;
+        }
+    }
+}
+
+// Large-G variant, pass 1: row prefix sums.  One warp per band of 32 rows (lane = row); 32x32 tiles are
+// staged through shared memory so global loads/stores stay coalesced.  P: [U][G][G] double scratch.
+__global__ void __launch_bounds__(32) integral_rows_kernel(unsigned* __restrict__ keys_heights, double* __restrict__ P,
+                                                           int G, const UnitParams* __restrict__ units) {
+    const int u = blockIdx.y;
+    if (units[u].cloud < 0) return;
+    const int row0 = blockIdx.x * 32;
+    const int lane = threadIdx.x;
+    __shared__ double tile[32][33];
+    unsigned* kh = keys_heights + (size_t)u * G * G;
+    double* Pu = P + (size_t)u * G * G;
+    double s = 0.0;  // running sum of row (row0 + lane)
+    for (int c0 = 0; c0 < G; c0 += 32) {
+        for (int rr = 0; rr < 32; rr++) {  // coalesced: lane = column
+            int row = row0 + rr, col = c0 + lane;
+            double v = 0.0;
+            if (row < G && col < G) {
+                float h = key_to_height(kh[(size_t)row * G + col]);
+                kh[(size_t)row * G + col] = __float_as_uint(h);
+                v = (double)h;
+            }
+            tile[rr][lane] = v;
+        }
+        __syncwarp();
+        for (int cc = 0; cc < 32; cc++) {  // lane = row: sequential left-to-right accumulation
+            if (c0 + cc < G) { s = __dadd_rn(s, tile[lane][cc]); tile[lane][cc] = s; }
+        }
+        __syncwarp();
+        for (int rr = 0; rr < 32; rr++) {
+            int row = row0 + rr, col = c0 + lane;
+            if (row < G && col < G) Pu[(size_t)row * G + col] = tile[rr][lane];
+        }
+        __syncwarp();
+    }
+}
+// pass 2: thread = column, sequential top-to-bottom accumulation (loads independent of the chain -> unrolled)
+__global__ void integral_cols_kernel(const double* __restrict__ P, float* __restrict__ integral, int G,
+                                     const UnitParams* __restrict__ units) {
+    const int u = blockIdx.y;
+    if (units[u].cloud < 0) return;
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;  // 0..G  (column index of the integral image)
+    const int ld = G + 1;
+    if (col > G) return;
+    float* I = integral + (size_t)u * ld * ld;
+    I[col] = 0.0f;
+    if (col == 0) {
+        for (int y = 1; y <= G; y++) I[(size_t)y * ld] = 0.0f;
+        return;
+    }
+    const double* Pu = P + (size_t)u * G * G + (col - 1);
+    double acc = 0.0;
+    int y = 0;
+    for (; y + 8 <= G; y += 8) {
+        double v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = Pu[(size_t)(y + k) * G];
+#pragma unroll
+        for (int k = 0; k < 8; k++) { acc = __dadd_rn(acc, v[k]); I[(size_t)(y + k + 1) * ld + col] = (float)acc; }
+    }
+    for (; y < G; y++) { acc = __dadd_rn(acc, Pu[(size_t)y * G]); I[(size_t)(y + 1) * ld + col] = (float)acc; }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// a5: valid-window mask (pnt_in_box, server.cpp:666-749) + compaction of the valid windows into `win`.
+// Each CTA covers 256*16 consecutive cells of one unit; windows are appended in row-major order within
+// the CTA's span with ONE global atomic per CTA.  Also initialises labelgrid to -1 (server.cpp:828-829).
+// grid = (ceil(G*G / 4096), U)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) mask_windows_kernel(const float* __restrict__ integral,
+                                                           const UnitParams* __restrict__ units, int G,
+                                                           unsigned char* __restrict__ mask,
+                                                           signed char* __restrict__ labelgrid,
+                                                           int2* __restrict__ win, unsigned* __restrict__ win_count,
+                                                           unsigned win_cap, int* __restrict__ overflow_flag,
+                                                           int unit_base) {
+    const int u = blockIdx.y;
+    const UnitParams up = units[u];
+    const int GG = G * G, ld = G + 1;
+    const int cell0 = blockIdx.x * 4096;
+    const float* I = integral + (size_t)u * ld * ld;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ unsigned s_cnt[16][8];
+    __shared__ unsigned s_off[16][8];
+    __shared__ unsigned s_base;
+    unsigned ballots[16];
+    const float nsa = -up.sa;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const int cell = cell0 + k * 256 + threadIdx.x;
+        bool in = false;
+        if (cell < GG && up.cloud >= 0) {
+            const int i = cell / G, j = cell - i * G;
+            if (i > 6 && i < G - 7 && j > 6 && j < G - 7) {  // :713
+                // :714-717  float, left to right:  ((I[i+4][j+4] - I[i-5][j+4]) - I[i+4][j-5]) + I[i-5][j-5]
+                const float d = __fadd_rn(__fsub_rn(__fsub_rn(I[(i + 4) * ld + (j + 4)], I[(i - 5) * ld + (j + 4)]), I[(i + 4) * ld + (j - 5)]), I[(i - 5) * ld + (j - 5)]);
+                if (d > 0.03f) {
+                    const float fj = (float)j, fi = (float)i;
+                    const float t1 = __fadd_rn(__fmul_rn(nsa, __fadd_rn(-up.cx1, fj)), __fmul_rn(up.ca, __fadd_rn(-up.cy1, fi)));    // :718
+                    const float t2 = __fadd_rn(__fmul_rn(nsa, __fadd_rn(-up.cx2, fj)), __fmul_rn(up.ca, __fadd_rn(-up.cy2, fi)));    // :719
+                    const float t3 = __fadd_rn(__fmul_rn(up.ca, __fadd_rn(-up.cx3, fj)), __fmul_rn(up.sa, __fadd_rn(-up.cy3, fi)));  // :720
+                    const float t4 = __fadd_rn(__fmul_rn(up.ca, __fadd_rn(-up.cx4, fj)), __fmul_rn(up.sa, __fadd_rn(-up.cy4, fi)));  // :721
+                    in = ((double)t1 < 0.00001) && ((double)t2 > -0.00001) && ((double)t3 > -0.00001) && ((double)t4 < 0.00001);
+                }
+            }
+            mask[(size_t)u * GG + cell] = in ? 1 : 0;
+            labelgrid[(size_t)u * GG + cell] = -1;
+        }
+        ballots[k] = __ballot_sync(0xffffffffu, in);
+        if (lane == 0) s_cnt[k][warp] = __popc(ballots[k]);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {  // 128-entry exclusive scan in (k, warp) order == ascending cell order
+        unsigned run = 0;
+        for (int k = 0; k < 16; k++)
+            for (int w = 0; w < 8; w++) { s_off[k][w] = run; run += s_cnt[k][w]; }
+        unsigned base = run ? atomicAdd(win_count, run) : 0u;
+        if (base + run > win_cap) { *overflow_flag = 1; base = 0xFFFFFFFFu; }
+        s_base = base;
+    }
+    __syncthreads();
+    const unsigned base = s_base;
+    if (base == 0xFFFFFFFFu) return;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        if (ballots[k] & (1u << lane)) {
+            const unsigned pos = base + s_off[k][warp] + __popc(ballots[k] & ((1u << lane) - 1u));
+            win[pos] = make_int2(unit_base + u, cell0 + k * 256 + threadIdx.x);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// a7 + a8 + a9: one SVM input dimension of one window: Haar / SHAF feature value in the reference's float
+// order (calc_featurevalue, II2FV.cpp:141-199), "%.4g" round trip, svm-scale output() in double
+// (svm-scale.c:333-353), "%g" round trip.  P points at I[row-7][col-7] of the window's integral image.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float rect_sum(const float* __restrict__ P, const int* off) {
+    // ((P[x2+1][y2+1] - P[x1][y2+1]) - P[x2+1][y1]) + P[x1][y1]     (II2FV.cpp:161-162)
+    return __fadd_rn(__fsub_rn(__fsub_rn(P[off[0]], P[off[1]]), P[off[2]]), P[off[3]]);
+}
+__device__ __forceinline__ float feature_value(const float* __restrict__ P, const FeatDev& f) {
+    if (!(f.flags & 0x100)) {  // HAF: returnval += wgt * rect, regions in order, skipped regions omitted
+        float v = 0.0f;
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+            if (f.flags & (1 << r)) v = __fadd_rn(v, __fmul_rn(f.w[r], rect_sum(P, f.off + 4 * r)));
+        return v;
+    }
+    float rr[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++) rr[r] = (f.flags & (1 << r)) ? __fmul_rn(f.w[r], rect_sum(P, f.off + 4 * r)) : 0.0f;
+    if (rr[1] > rr[0] && rr[1] > rr[2]) {  // :187-188
+        const float a = __fsub_rn(rr[1], rr[0]), b = __fsub_rn(rr[1], rr[2]);
+        return (b < a) ? b : a;
+    }
+    return -1.0f;
+}
+template <bool DEBUG>
+__global__ void __launch_bounds__(256) features_kernel(const float* __restrict__ integral, const int2* __restrict__ win,
+                                                       const unsigned* __restrict__ win_count, int G, int unit_base,
+                                                       const FeatDev* __restrict__ feats, const DimDev* __restrict__ dims,
+                                                       int D, int Kpad, double lower, double upper, int emulate_text,
+                                                       float* __restrict__ X, size_t ldx, int F,
+                                                       float* __restrict__ dbg_raw, double* __restrict__ dbg_scaled,
+                                                       int* __restrict__ unsupported_flag) {
+    const unsigned W = *win_count;
+    const unsigned w = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int warp = threadIdx.x >> 5;
+    if (blockIdx.x * 32 >= W) return;
+    const bool valid = w < W;
+    const int ld = G + 1;
+    const float* P = integral;
+    if (valid) {
+        const int2 uc = win[w];
+        const int row = uc.y / G, col = uc.y - row * G;
+        P = integral + (size_t)(uc.x - unit_base) * ld * ld + (size_t)(row - 7) * ld + (col - 7);
+    }
+    int uns = 0;
+    for (int d = warp; d < Kpad; d += 8) {
+        double x = 0.0;
+        if (d < D && valid) {
+            const DimDev dd = dims[d];
+            if (dd.feat < 0) {
+                x = dd.cval;
+            } else {
+                const FeatDev f = feats[dd.feat];
+                const float raw = feature_value(P, f);
+                double v;
+                if (emulate_text) {
+                    bool u4 = false;
+                    v = hafdec::text4(raw, &u4);
+                    if (u4) uns = 1;
+                } else {
+                    v = (double)raw;
+                }
+                if (dd.drop) x = 0.0;
+                else {
+                    double val;
+                    if (v == dd.fmin) val = lower;
+                    else if (v == dd.fmax) val = upper;
+                    else val = __dadd_rn(lower, __ddiv_rn(__dmul_rn(__dsub_rn(upper, lower), __dsub_rn(v, dd.fmin)), dd.den));
+                    if (val == 0.0) x = 0.0;
+                    else if (!emulate_text) x = val;
+                    else {
+                        bool u6 = false;
+                        x = hafdec::text6(val, &u6);
+                        if (u6) uns = 1;
+                    }
+                }
+            }
+            if (DEBUG && dbg_scaled) dbg_scaled[(size_t)w * D + d] = x;
+        }
+        if (!DEBUG && valid) X[(size_t)d * ldx + w] = (float)x;
+    }
+    if (DEBUG && dbg_raw && valid) {
+        for (int k = warp; k < F; k += 8) dbg_raw[(size_t)w * F + k] = feature_value(P, feats[k]);
+    }
+    if (uns) *unsupported_flag = 1;
+}
+
+// squared norm of every window's SVM input (FP32)
+__global__ void xnorm_kernel(const float* __restrict__ X, size_t ldx, int Kpad, const unsigned* __restrict__ win_count,
+                             float* __restrict__ xn) {
+    const unsigned W = *win_count;
+    const unsigned w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= W) return;
+    float s = 0.0f;
+    for (int d = 0; d < Kpad; d++) { const float v = X[(size_t)d * ldx + w]; s = fmaf(v, v, s); }
+    xn[w] = s;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// a11 (FP32 SIMT): dec[w] = sum_i coef_i * exp(-gamma * ||x_w - sv_i||^2) - rho with
+// ||x - sv||^2 = ||x||^2 + ||sv||^2 - 2 x.sv; the x.sv contraction is a register-tiled SGEMM
+// (CTA tile 128 windows x 128 SVs, BK = 16, 8x8 micro-tiles, 3-stage cp.async pipeline) with the
+// exp / coef / row-sum epilogue fused, decision sums accumulated in FP64.
+// A window whose |dec| <= guard_rel * sum_i |coef_i| K_i is appended to the guard list and re-evaluated by
+// svm_exact_kernel in FP64 in libsvm's own order, so LABELS equal the reference's.
+// ---------------------------------------------------------------------------------------------------
+#define SVM_BM 128
+#define SVM_BN 128
+#define SVM_BK 16
+#define SVM_STAGES 3
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__global__ void __launch_bounds__(256, 2) svm_rbf_simt_kernel(const float* __restrict__ X, size_t ldx,
+                                                               const float* __restrict__ svT, int Spad, int Kpad,
+                                                               const float* __restrict__ xn, const float* __restrict__ svn,
+                                                               const float* __restrict__ coef, float neg_gamma_log2e,
+                                                               double rho, float guard_rel,
+                                                               const unsigned* __restrict__ win_count,
+                                                               double* __restrict__ dec, unsigned char* __restrict__ guard_flag,
+                                                               int* __restrict__ guard_list, unsigned* __restrict__ guard_count) {
+    const unsigned W = *win_count;
+    const unsigned m0 = blockIdx.x * SVM_BM;
+    if (m0 >= W) return;
+    extern __shared__ __align__(16) float smem[];
+    float* As = smem;                                       // [STAGES][BK][BM]
+    float* Bs = smem + SVM_STAGES * SVM_BK * SVM_BM;        // [STAGES][BK][BN]
+    const int tid = threadIdx.x;
+    const int ty = tid >> 4, tx = tid & 15;                 // 16 x 16 threads, each 8 (m) x 8 (n) as 2x(4) + 2x(4)
+    const int nk = Kpad / SVM_BK;
+    const int ntiles = Spad / SVM_BN;
+
+    double dsum[8];
+    float asum[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { dsum[i] = 0.0; asum[i] = 0.0f; }
+    float xnr[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const unsigned m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+        xnr[i] = (m < W) ? xn[m] : 0.0f;
+    }
+
+    // one stage = 16 rows x 128 floats for A and for B = 2 x 512 16-byte chunks; 256 threads -> 2 + 2 chunks each
+    auto load_stage = [&](int stage, int kb, int n0) {
+        const int k0 = kb * SVM_BK;
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            const int chunk = tid + c * 256;        // 0..511
+            const int kr = chunk >> 5, mc = (chunk & 31) * 4;
+            cp_async16(As + (stage * SVM_BK + kr) * SVM_BM + mc, X + (size_t)(k0 + kr) * ldx + m0 + mc);
+            cp_async16(Bs + (stage * SVM_BK + kr) * SVM_BN + mc, svT + (size_t)(k0 + kr) * Spad + n0 + mc);
+        }
+    };
+
+    const int total = ntiles * nk;  // flattened (n-tile, k-block) iteration space
+    int issued = 0;
+    for (; issued < SVM_STAGES - 1 && issued < total; issued++) {
+        load_stage(issued % SVM_STAGES, issued % nk, (issued / nk) * SVM_BN);
+        cp_async_commit();
+    }
+    for (int s = issued; s < SVM_STAGES - 1; s++) cp_async_commit();
+
+    float acc[8][8];
+    for (int it = 0; it < total; it++) {
+        const int kb = it % nk, nt = it / nk;
+        if (kb == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+#pragma unroll
+                for (int j = 0; j < 8; j++) acc[i][j] = 0.0f;
+        }
+        cp_async_wait<SVM_STAGES - 2>();
+        __syncthreads();
+        if (issued < total) load_stage(issued % SVM_STAGES, issued % nk, (issued / nk) * SVM_BN);
+        cp_async_commit();
+        issued++;
+        const float* a = As + (it % SVM_STAGES) * SVM_BK * SVM_BM;
+        const float* b = Bs + (it % SVM_STAGES) * SVM_BK * SVM_BN;
+#pragma unroll
+        for (int k = 0; k < SVM_BK; k++) {
+            const float4 a0 = *reinterpret_cast<const float4*>(a + k * SVM_BM + ty * 4);
+            const float4 a1 = *reinterpret_cast<const float4*>(a + k * SVM_BM + 64 + ty * 4);
+            const float4 b0 = *reinterpret_cast<const float4*>(b + k * SVM_BN + tx * 4);
+            const float4 b1 = *reinterpret_cast<const float4*>(b + k * SVM_BN + 64 + tx * 4);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+#pragma unroll
+                for (int j = 0; j < 8; j++) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        if (kb == nk - 1) {  // epilogue of this SV tile
+            const int n0 = nt * SVM_BN;
+            float cf[8], sn[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+                cf[j] = __ldg(coef + n);
+                sn[j] = __ldg(svn + n);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                float ps = 0.0f, pa = 0.0f;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const float d2 = fmaxf(fmaf(-2.0f, acc[i][j], xnr[i] + sn[j]), 0.0f);
+                    const float kv = exp2f(neg_gamma_log2e * d2);
+                    ps = fmaf(cf[j], kv, ps);
+                    pa = fmaf(fabsf(cf[j]), kv, pa);
+                }
+                dsum[i] += (double)ps;
+                asum[i] += pa;
+            }
+        }
+    }
+    cp_async_wait<0>();
+    // reduce over the 16 tx lanes that share the same window rows (lanes 0-15 / 16-31 of a warp)
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+#pragma unroll
+        for (int o = 8; o >= 1; o >>= 1) {
+            dsum[i] += __shfl_xor_sync(0xffffffffu, dsum[i], o);
+            asum[i] += __shfl_xor_sync(0xffffffffu, asum[i], o);
+        }
+    }
+    if (tx == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const unsigned m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+            if (m < W) {
+                const double dv = dsum[i] - rho;
+                dec[m] = dv;
+                const bool g = fabs(dv) <= (double)guard_rel * ((double)asum[i] + fabs(rho));
+                guard_flag[m] = g ? 1 : 0;
+                if (g) guard_list[atomicAdd(guard_count, 1u)] = (int)m;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// a11 (FP64, libsvm order): one CTA per listed window.  x is re-derived in double from the integral image
+// (same device functions as features_kernel), K_i = exp(-gamma * sum_d (x_d - sv_i,d)^2) with the d loop
+// sequential and un-fused (Kernel::k_function, svm.cpp:326-365: absent entries are zeros, adding 0.0 is
+// exact), then ONE thread sums coef_i * K_i in file order and subtracts rho (svm.cpp:2500-2514).
+// list == NULL: all windows (HAF_SVM_FP64_EXACT).  grid-stride over the list; kscratch: [gridDim.x][Spad].
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) svm_exact_kernel(const int* __restrict__ list, const unsigned* __restrict__ list_count,
+                                                        const unsigned* __restrict__ win_count,
+                                                        const float* __restrict__ integral, const int2* __restrict__ win,
+                                                        int G, int unit_base, const FeatDev* __restrict__ feats,
+                                                        const DimDev* __restrict__ dims, int D, double lower, double upper,
+                                                        int emulate_text, const double* __restrict__ sv64T, int Spad, int S,
+                                                        int Dsv, const double* __restrict__ coef64, double gamma, double rho,
+                                                        double* __restrict__ kscratch, double* __restrict__ dec,
+                                                        int* __restrict__ unsupported_flag) {
+    extern __shared__ double xs[];  // [Dsv]
+    const unsigned n = list ? *list_count : *win_count;
+    const int ld = G + 1;
+    double* kv = kscratch + (size_t)blockIdx.x * Spad;
+    for (unsigned e = blockIdx.x; e < n; e += gridDim.x) {
+        const int w = list ? list[e] : (int)e;
+        const int2 uc = win[w];
+        const int row = uc.y / G, col = uc.y - row * G;
+        const float* P = integral + (size_t)(uc.x - unit_base) * ld * ld + (size_t)(row - 7) * ld + (col - 7);
+        __syncthreads();
+        for (int d = threadIdx.x; d < Dsv; d += blockDim.x) {
+            double x = 0.0;
+            if (d < D) {
+                const DimDev dd = dims[d];
+                if (dd.feat < 0) x = dd.cval;
+                else {
+                    const float raw = feature_value(P, feats[dd.feat]);
+                    bool u4 = false, u6 = false;
+                    const double v = emulate_text ? hafdec::text4(raw, &u4) : (double)raw;
+                    if (!dd.drop) {
+                        double val;
+                        if (v == dd.fmin) val = lower;
+                        else if (v == dd.fmax) val = upper;
+                        else val = __dadd_rn(lower, __ddiv_rn(__dmul_rn(__dsub_rn(upper, lower), __dsub_rn(v, dd.fmin)), dd.den));
+                        if (val != 0.0) x = emulate_text ? hafdec::text6(val, &u6) : val;
+                    }
+                    if (u4 || u6) *unsupported_flag = 1;
+                }
+            }
+            xs[d] = x;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < S; i += blockDim.x) {
+            double sum = 0.0;
+            for (int d = 0; d < Dsv; d++) {
+                const double diff = __dsub_rn(xs[d], sv64T[(size_t)d * Spad + i]);
+                sum = __dadd_rn(sum, __dmul_rn(diff, diff));
+            }
+            kv[i] = exp(__dmul_rn(-gamma, sum));
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double sum = 0.0;
+            for (int i = 0; i < S; i++) sum = __dadd_rn(sum, __dmul_rn(coef64[i], kv[i]));
+            dec[w] = __dsub_rn(sum, rho);
+        }
+    }
+}
+
+// label -> graspsgrid value (server.cpp:843) scattered into the unit grids
+__global__ void label_scatter_kernel(const double* __restrict__ dec, const int2* __restrict__ win,
+                                     const unsigned* __restrict__ win_count, int G, int unit_base, int gv_pos, int gv_neg,
+                                     signed char* __restrict__ labelgrid, unsigned* __restrict__ unit_windows) {
+    const unsigned W = *win_count;
+    const unsigned w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= W) return;
+    const int2 uc = win[w];
+    labelgrid[(size_t)(uc.x - unit_base) * G * G + uc.y] = (signed char)((dec[w] > 0.0) ? gv_pos : gv_neg);  // svm.cpp:2516
+    atomicAdd(unit_windows + (uc.x - unit_base), 1u);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// a13: 29-tap weighted neighbourhood score + first strict maximum per unit (server.cpp:865-897).
+// grid = (ceil(G*G/256), U).  unit_top key: (val + 2^20) << 32 | (0xFFFFFFFF - cell): max == first strict max.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) score_kernel(const signed char* __restrict__ labelgrid, int G,
+                                                    const UnitParams* __restrict__ units, float* __restrict__ evals,
+                                                    unsigned long long* __restrict__ unit_top) {
+    const int u = blockIdx.y;
+    if (units[u].cloud < 0) return;
+    const int GG = G * G;
+    const int cell = blockIdx.x * 256 + threadIdx.x;
+    const signed char* L = labelgrid + (size_t)u * GG;
+    int e = 0;
+    bool have = cell < GG;
+    if (have) {
+        const int row = cell / G, col = cell - row * G;
+        if (L[cell] >= 0) {  // graspsgrid >= 0 only where the mask is true, i.e. 7 <= row,col <= G-8: taps stay inside
+#define LG(dr, dc) ((int)L[(row + (dr)) * G + (col + (dc))])
+            e = 1 * LG(-2, -2) + 2 * LG(-2, -1) + 3 * LG(-2, 0) + 2 * LG(-2, 1) + 1 * LG(-2, 2) +
+                2 * LG(-1, -2) + 3 * LG(-1, -1) + 4 * LG(-1, 0) + 3 * LG(-1, 1) + 2 * LG(-1, 2) +
+                2 * LG(0, -4) + 2 * LG(0, -3) + 3 * LG(0, -2) + 4 * LG(0, -1) + 55 * LG(0, 0) + 4 * LG(0, 1) + 3 * LG(0, 2) + 2 * LG(0, 3) + 2 * LG(0, 4) +
+                2 * LG(1, -2) + 3 * LG(1, -1) + 4 * LG(1, 0) + 3 * LG(1, 1) + 2 * LG(1, 2) +
+                1 * LG(2, -2) + 2 * LG(2, -1) + 3 * LG(2, 0) + 2 * LG(2, 1) + 1 * LG(2, 2);
+#undef LG
+        }
+        evals[(size_t)u * GG + cell] = (float)e;
+    }
+    unsigned long long key = have ? (((unsigned long long)(unsigned)(e + (1 << 20))) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)cell) : 0ull;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+        key = other > key ? other : key;
+    }
+    __shared__ unsigned long long sk[8];
+    if ((threadIdx.x & 31) == 0) sk[threadIdx.x >> 5] = key;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; w++) key = sk[w] > key ? sk[w] : key;
+        atomicMax(unit_top + u, key);
+    }
+}
+
+// a14: among cells == topval, the first (row-major) strictly longest horizontal run; cell = (row, col_end - len/2)
+// (server.cpp:905-932).  One warp per (unit, row).  unit_run key: len << 32 | (0xFFFF - row) << 16 | col_mid.
+__global__ void __launch_bounds__(256) tie_rule_kernel(const float* __restrict__ evals, int G,
+                                                       const UnitParams* __restrict__ units,
+                                                       const unsigned long long* __restrict__ unit_top,
+                                                       unsigned long long* __restrict__ unit_run) {
+    const int u = blockIdx.y;
+    if (units[u].cloud < 0) return;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= G) return;
+    const int lane = threadIdx.x & 31;
+    const float topval = (float)((int)(unsigned)(unit_top[u] >> 32) - (1 << 20));
+    const float* E = evals + (size_t)u * G * G + (size_t)row * G;
+    // sequential semantics reproduced with a warp-wide segmented scan over chunks of 32 columns
+    int carry = 0;       // length of the run ending at the previous column
+    int best_len = 0, best_col = 0;
+    for (int c0 = 0; c0 < G; c0 += 32) {
+        const int col = c0 + lane;
+        const bool hit = (col < G) && (E[col] == topval);
+        const unsigned b = __ballot_sync(0xffffffffu, hit);
+        // run length ending at this lane = number of consecutive set bits ending at `lane` (+ carry if they reach bit 0)
+        const unsigned upto = b << (31 - lane);          // bit 31 = this lane, lower lanes below
+        const int ones = __clz(~upto);                   // consecutive ones from the top
+        int len = hit ? ones : 0;
+        if (hit && ones == lane + 1) len += carry;
+        // the reference updates "longest" incrementally while a run grows, so the winner is the FIRST run whose final
+        // length is the maximum, at position col_end - len/2; a later run replaces it only if strictly longer.
+        const bool next_hit = (col + 1 < G) && (E[col + 1] == topval);
+        const bool run_end = hit && !next_hit;
+        // candidate key: longer run wins, equal length -> smaller column (the earlier run)
+        unsigned cand = run_end ? (((unsigned)len << 16) | (0xFFFFu - (unsigned)(col - len / 2))) : 0u;
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            const unsigned other = __shfl_xor_sync(0xffffffffu, cand, o);
+            cand = other > cand ? other : cand;
+        }
+        const int cand_len = (int)(cand >> 16);
+        if (cand_len > best_len) { best_len = cand_len; best_col = 0xFFFF - (int)(cand & 0xFFFFu); }
+        carry = __shfl_sync(0xffffffffu, len, 31);
+    }
+    if (lane == 0 && best_len > 0) {
+        const unsigned long long key = ((unsigned long long)(unsigned)best_len << 32) |
+                                       ((unsigned long long)(0xFFFFu - (unsigned)row) << 16) | (unsigned long long)(unsigned)best_col;
+        atomicMax(unit_run + u, key);
+    }
+}
+
+struct JobResult {  // per job (cloud x request)
+    int row, col, roll, topval;
+    int rolls_done, n_windows, pad0, pad1;
+};
+struct JobParams {
+    int return_only_best, graspval_top, n_rolls_active, pad;
+};
+// per-unit tops (after the tie rule) + a15 cross-roll reduction with the loop_control rules
+// (server.cpp:362-365 early exit, :953-960 strict >).  One thread per job.
+__global__ void reduce_rolls_kernel(const unsigned long long* __restrict__ unit_top, const unsigned long long* __restrict__ unit_run,
+                                    const unsigned* __restrict__ unit_windows, const JobParams* __restrict__ jobs, int n_jobs,
+                                    int R, int G, int* __restrict__ per_roll_top /*[n_jobs][R][3]*/,
+                                    JobResult* __restrict__ results) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_jobs) return;
+    const JobParams jp = jobs[j];
+    int best = -1000, brow = -1, bcol = -1, broll = -1, done = 0, nwin = 0;
+    for (int roll = 0; roll < R; roll++) {
+        const int u = j * R + roll;
+        int row = -1, col = -1, val = -1000;
+        if (roll < jp.n_rolls_active) {
+            val = (int)(unsigned)(unit_top[u] >> 32) - (1 << 20);
+            const unsigned long long rk = unit_run[u];
+            row = 0xFFFF - (int)((rk >> 16) & 0xFFFFu);
+            col = (int)(rk & 0xFFFFu);
+        }
+        per_roll_top[(j * R + roll) * 3 + 0] = row;
+        per_roll_top[(j * R + roll) * 3 + 1] = col;
+        per_roll_top[(j * R + roll) * 3 + 2] = val;
+    }
+    for (int roll = 0; roll < jp.n_rolls_active; roll++) {
+        if (jp.return_only_best && best >= jp.graspval_top) break;  // :362-365
+        const int u = j * R + roll;
+        const int val = per_roll_top[u * 3 + 2];
+        if (val > best) { best = val; brow = per_roll_top[u * 3]; bcol = per_roll_top[u * 3 + 1]; broll = roll; }  // :953
+        nwin += (int)unit_windows[u];
+        done++;
+    }
+    JobResult r;
+    r.row = brow; r.col = bcol; r.roll = broll; r.topval = best; r.rolls_done = done; r.n_windows = nwin; r.pad0 = r.pad1 = 0;
+    results[j] = r;
+}
+
+// counters: [0] windows of this chunk, [1] guard windows of this chunk -> running totals in [8], [9]
+__global__ void accumulate_counts_kernel(unsigned* cnt) {
+    cnt[8] += cnt[0];
+    cnt[9] += cnt[1];
+}
+
+// debug: device text round trips
+__global__ void text_roundtrip_kernel(const float* in4, int n4, double* out4, const double* in6, int n6, double* out6) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n4) out4[i] = hafdec::text4(in4[i]);
+    if (i < n6) out6[i] = hafdec::text6(in6[i]);
+}
+
+}  // namespace hafk

@@ -1,0 +1,166 @@
+/* hafgpu.h -- C ABI of libhafgpu.so: the B200-native (sm_100a) grasp-search hot path of haf_grasping.
+ *
+ * The reference has no plugin / FFI interface: the hot path is private members of the ROS node class
+ * CCalc_Grasppoints plus two child processes (svm-scale, svm-predict).  This ABI is the narrowest seam that
+ * leaves every ROS contract (CalcGraspPointsServer.action, GraspInput / GraspOutput, the parameter services)
+ * untouched: inside CCalc_Grasppoints::loop_control (reference src/calc_grasppoints_action_server.cpp:335-402)
+ * the five per-roll calls at :376-385
+ *      generate_grid        (:406-529)   calc_intimage          (:577-613)
+ *      calc_featurevectors  (:616-656)   [pnt_in_box            (:666-749)]
+ *      predict_bestgp_withsvm (:754-800) show_predicted_gps     (:803-973)
+ * and with them CIntImage_to_Featurevec::calc_featurevalue / write_featurevector (src/CIntImage_to_Featurevec.cpp
+ * :122-199), svm-scale (libsvm-3.12/svm-scale.c) and svm-predict (libsvm-3.12/svm-predict.c, svm.cpp:2459-2533)
+ * are replaced by ONE call, haf_search().  See INTEGRATION.md for the patch a maintainer applies.
+ *
+ * Conventions: 0 = OK, negative = error (haf_last_error gives text); no C++ exceptions, ROS or torch types
+ * cross the boundary; the caller owns every output buffer; pointers named *_hostdev may be host or device
+ * memory (detected with cudaPointerGetAttributes); there is NO CPU fallback -- without a usable sm_100
+ * device haf_create fails with HAF_ERR_NO_DEVICE.  A context is entered from one thread at a time (the
+ * action server runs one goal at a time on its execute thread, server.cpp:182, :227).
+ */
+#ifndef HAFGPU_H_
+#define HAFGPU_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HAF_OK 0
+#define HAF_ERR_ARG (-1)         /* bad argument */
+#define HAF_ERR_IO (-2)          /* features / range / model file missing or unparsable */
+#define HAF_ERR_CUDA (-3)        /* CUDA runtime error */
+#define HAF_ERR_NO_DEVICE (-4)   /* no sm_100 device: no fallback exists */
+#define HAF_ERR_UNSUPPORTED (-5) /* input outside what the path reproduces exactly (see haf_last_error) */
+#define HAF_ERR_NOMEM (-6)
+
+typedef struct haf_ctx haf_ctx;
+
+/* svm_mode */
+#define HAF_SVM_FP32_GUARD 0 /* FP32 SIMT contraction, FP64 exact-order re-evaluation inside the guard band */
+#define HAF_SVM_FP64_EXACT 1 /* every window in FP64, libsvm's summation order (svm.cpp:326-365, :2500-2514) */
+#define HAF_SVM_TENSOR_GUARD 2 /* tcgen05 split-bf16 contraction + the same FP64 guard band */
+
+typedef struct {
+    const char* features_path; /* data/Features.txt               (server param feature_file_path, :218-219) */
+    const char* range_path;    /* data/range21062012_allfeatures  (range_file_path, :220-221)                */
+    const char* model_path;    /* libsvm text model               (svmmodel_file_path, :222-223)             */
+    int nr_features_without_shaf; /* 302 (server.cpp:224)                                                   */
+    int grid;                  /* G: 56 = reference HEIGHT/WIDTH (server.cpp:92-93); even, 16..1024          */
+    int roll_step_deg;         /* 15  (ROLL_STEPS_DEGREE, :95)                                               */
+    int roll_max_deg;          /* 190 (ROLL_MAX_DEGREE, :101) -> R = 190/15 = 12 rolls                        */
+    int device;                /* CUDA ordinal; one context (and one process) per GPU                         */
+    int emulate_text_roundtrip; /* 1 = reproduce the "%.4g" / "%g" text round trips (reference-exact)         */
+    int svm_mode;              /* HAF_SVM_*                                                                   */
+    float guard_rel;           /* guard band half-width as a fraction of sum_i |coef_i| K_i; <=0 -> default   */
+    int reserved[4];
+} haf_config;
+
+/* One grasp goal = the hot-path fields of GraspInput (msg/GraspInput.msg:3-15). */
+typedef struct {
+    double center[3];          /* grasp_area_center (server.cpp:258-260)                                      */
+    float area_len_x, area_len_y; /* grasp_area_length_x/y in cm incl. the client's +14 (client.cpp:183-184);
+                                     truncated to int like server.cpp:266-267                                 */
+    double approach[3];        /* approach_vector, un-normalised; normalised like server.cpp:270-273          */
+    int gripper_opening_width; /* :281, :433                                                                  */
+    int return_only_best;      /* show_only_best_grasp: enables the early exit at graspval_top (:362-365)     */
+    int graspval_top;          /* 119 (:203)                                                                  */
+    int roll_limit;            /* evaluate only rolls [0, roll_limit); <=0 = all.  Stand-in for the caller's
+                                  time budget / preempt checks (:350-357, :367-374)                           */
+} haf_request;
+
+typedef struct {
+    int row, col, roll, tilt;  /* id_row_top_overall, id_col_top_overall, nr_roll_top_overall, nr_tilt (=0)   */
+    int approach_idx;          /* index of the winning request (approach vector); earliest wins ties          */
+    int topval;                /* topval_gp_overall (:953-960); -1000 when no roll was evaluated              */
+    int eval;                  /* topval - 20 (:390)                                                          */
+    float roll_rad;            /* roll * step * PI / 180 (:1401)                                              */
+    float M[16];               /* mat_transform of the winning roll, row-major (:483); av_trans_mat           */
+    int rolls_done;            /* rolls the reference loop would have evaluated (early exit / roll_limit)     */
+    int n_windows_scored;      /* feature vectors classified in those rolls                                   */
+    int n_guard;               /* windows re-evaluated in FP64 because |dec| fell inside the guard band       */
+    int reserved;
+} haf_best;
+
+typedef struct {
+    int n_features;   /* F: features parsed (324 for data/Features.txt: 323 lines + the trailing blank line)  */
+    int n_dims;       /* D: dimensions fed to the SVM (323)                                                   */
+    int n_sv;         /* S: support vectors                                                                   */
+    int n_rolls;      /* R                                                                                    */
+    int grid;         /* G                                                                                    */
+    int label0, label1; /* model label order (svm.cpp:2516-2531)                                              */
+    int sm_count;
+    double gamma, rho;
+    int reserved[4];
+} haf_info;
+
+typedef struct {
+    float ms_total;   /* device time of the last haf_search / haf_search_batch* call (CUDA events on its stream) */
+    float ms_bin, ms_integral, ms_mask, ms_features, ms_svm, ms_guard, ms_score;
+    long long n_points, n_units, n_windows, n_guard, launches;
+} haf_timing;
+
+/* ---- lifetime --------------------------------------------------------------------------------------------- */
+int haf_create(haf_ctx** out, const haf_config* cfg);       /* parses + uploads features / range / model ONCE */
+void haf_destroy(haf_ctx* ctx);
+const char* haf_last_error(const haf_ctx* ctx);              /* ctx may be NULL (error of a failed haf_create) */
+int haf_get_info(const haf_ctx* ctx, haf_info* info);
+int haf_set_stream(haf_ctx* ctx, void* cuda_stream);         /* cudaStream_t; default: the legacy default stream */
+int haf_set_profiling(haf_ctx* ctx, int per_stage_events);   /* 1: haf_timing carries per-stage ms (adds events) */
+int haf_get_timing(const haf_ctx* ctx, haf_timing* t);
+long long haf_launch_count(const haf_ctx* ctx);              /* kernels launched by this context so far         */
+
+/* ---- the hot path ------------------------------------------------------------------------------------------ */
+/* One cloud, n_requests goals that differ in approach vector / centre / area (the reference has one approach
+ * vector per goal; units (request, roll) are independent).  xyz: n_points records of 3 floats with a
+ * byte stride (12 = packed, 16 = pcl::PointXYZ).  `best` = overall winner over requests in order (strict >,
+ * earliest request wins ties -- the rule of server.cpp:953 extended); best_per_request [n_requests] optional.
+ * Optional per-roll outputs (NULL to skip), host or device memory, R = n_rolls, G = grid:
+ *   graspseval [n_requests][R][G][G] float  (graspseval of show_predicted_gps, :823-880)
+ *   mask       [n_requests][R][G][G] uint8  (point_inside_box_grid, :138)
+ *   heights    [n_requests][R][G][G] float  (heightsgridroll, :136)
+ *   per_roll_top [n_requests][R][3] int     (id_row_top_all, id_col_top_all, topval_gp_all per roll, :811-815)
+ * Rolls not evaluated (roll_limit) are left untouched. */
+int haf_search(haf_ctx* ctx, const float* xyz_hostdev, size_t n_points, size_t stride_bytes,
+               const haf_request* reqs, int n_requests, haf_best* best, haf_best* best_per_request,
+               float* graspseval, unsigned char* mask, float* heights, int* per_roll_top);
+
+/* Throughput mode: n_clouds independent clouds, one request applied to each.  clouds[i] host or device
+ * pointers to packed xyz (stride 12). */
+int haf_search_batch(haf_ctx* ctx, const float* const* clouds, const size_t* n_points, int n_clouds,
+                     const haf_request* req, haf_best* best_per_cloud);
+/* Same, clouds concatenated in one packed buffer (host or device); point_offsets has n_clouds+1 entries. */
+int haf_search_batch_packed(haf_ctx* ctx, const float* xyz_all_hostdev, const size_t* point_offsets, int n_clouds,
+                            const haf_request* req, haf_best* best_per_cloud);
+
+/* Host-only helpers (no GPU work): the transform of one roll exactly as generate_grid builds it (:406-484),
+ * and the ordered key that turns "strictly greater wins, earliest unit wins ties" into a max-reduction, for the
+ * cross-GPU best-grasp exchange. */
+int haf_build_transform(const haf_request* req, int roll, int roll_step_deg, float M_rowmajor[16]);
+uint64_t haf_best_key(int topval, uint32_t unit_order);
+
+/* ---- parity / inspection entry points (used by tests; they re-run stages on the state of the LAST haf_search) */
+int haf_debug_window_count(const haf_ctx* ctx);
+/* windows of the last search: win_unit_cell [W][2] = (unit = request*R + roll, cell = row*G + col) */
+int haf_debug_windows(haf_ctx* ctx, int* win_unit_cell, int cap_windows);
+/* raw features [W][F] float (calc_featurevalue), scaled SVM inputs [W][D] double (after both text round trips) */
+int haf_debug_features(haf_ctx* ctx, float* raw, double* scaled, int cap_windows);
+/* decision values, libsvm labels and guard flags [W] of the last search */
+int haf_debug_decisions(haf_ctx* ctx, double* dec, int* labels, unsigned char* guard, int cap_windows);
+/* integral images [n_units][G+1][G+1] float of the last search */
+int haf_debug_integral(haf_ctx* ctx, float* integral, size_t cap_floats);
+/* cell index (idx_x*G+idx_y, or -1 outside the box) of every point for one request / roll */
+int haf_debug_cell_indices(haf_ctx* ctx, const float* xyz_hostdev, size_t n_points, size_t stride_bytes,
+                           const haf_request* req, int roll, int* cell_idx_host);
+/* device evaluation of text4 (float -> "%.4g" -> double) and text6 (double -> "%g" -> double) */
+int haf_debug_text_roundtrip(haf_ctx* ctx, const float* in4, int n4, double* out4, const double* in6, int n6,
+                             double* out6);
+
+const char* haf_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HAFGPU_H_ */

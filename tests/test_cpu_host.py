@@ -1,0 +1,132 @@
+"""CPU-side tests (no GPU): decimal text emulation vs glibc, C-ABI exports, loaders' host logic, PCD reader,
+oracle golden pins."""
+import ctypes as C
+import gzip
+import json
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import FEATURES, GOLDEN, RANGE, REFERENCE_DATA, ROOT
+
+
+def test_decimal_round_emulation_matches_glibc(tmp_path):
+    exe = str(tmp_path / "drc")
+    subprocess.run(["/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++", "-O2", "-ffp-contract=off", "-o", exe,
+                    os.path.join(ROOT, "tests", "decimal_round_check.cpp"), "-lm"], check=True)
+    out = subprocess.run([exe, "400000", "11"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout
+    assert "mismatches=0" in out.stdout and "unsupported_text4=0" in out.stdout
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    from haf_grasping_b200 import api, build
+    lib = build.build_lib()
+    L = C.CDLL(lib)
+    header = open(os.path.join(ROOT, "include", "hafgpu.h")).read()
+    declared = set(re.findall(r"\b(haf_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(api.EXPORTS), declared ^ set(api.EXPORTS)
+    for name in declared:
+        assert hasattr(L, name), name
+
+
+def test_no_gpu_means_loud_failure_not_fallback(tmp_models):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import haf_grasping_b200 as h
+    with pytest.raises(h.HafError) as e:
+        h.GraspSearch(FEATURES, RANGE, tmp_models(256))
+    assert e.value.code == -4
+
+
+def test_host_transform_matches_oracle(oracle_lib):
+    import haf_grasping_b200 as h
+    o = oracle_lib.Oracle(FEATURES, RANGE)
+    rng = np.random.default_rng(5)
+    cases = [((0, 0, 0), (0, 0, 1), 1), ((0.1, -0.2, 0.05), (0.5, 0, 0.8660254), 1), ((0, 0, 0), (0, 0, -1), 2),
+             ((0.3, 0.1, 0), (0.2, -0.7, 0.4), 3)]
+    cases += [(tuple(rng.uniform(-1, 1, 3)), tuple(rng.uniform(-1, 1, 3)), int(rng.integers(1, 4))) for _ in range(20)]
+    for center, av, width in cases:
+        for roll in range(12):
+            M = h.build_transform(h.make_request(center=center, approach=av, width=width), roll)
+            M2 = o.build_transform(center, o.normalize_approach(av), width, roll)
+            assert M.tobytes() == M2.tobytes()
+
+
+def test_best_key_orders_like_the_reference_rule():
+    import haf_grasping_b200 as h
+    L = h.load_library()
+    # strictly greater topval wins; equal topval -> the EARLIER unit wins (server.cpp:953 strict >)
+    assert L.haf_best_key(90, 5) > L.haf_best_key(89, 0)
+    assert L.haf_best_key(90, 3) > L.haf_best_key(90, 4)
+    assert L.haf_best_key(-1000, 0) < L.haf_best_key(0, 100)
+
+
+def test_pcd_reader_on_reference_files():
+    if not os.path.isdir(REFERENCE_DATA):
+        pytest.skip("reference data not on this box")
+    from haf_grasping_b200.pcd import read_pcd
+    clouds = np.load(os.path.join(GOLDEN, "clouds.npz"))
+    a = read_pcd(os.path.join(REFERENCE_DATA, "pcd4.pcd"))
+    assert a.shape == (200, 3)  # POINTS 200 although the file carries 208 lines
+    assert a.tobytes() == clouds["pcd4"].tobytes()
+    t = read_pcd(os.path.join(REFERENCE_DATA, "table1_mult_obj_rcs_1428580506606673.pcd"))
+    assert t.tobytes() == clouds["table1"].tobytes()
+    assert os.path.islink(os.path.join(REFERENCE_DATA, "objects_1.pcd"))
+
+
+def test_pcd_roundtrip_formats(tmp_path):
+    from haf_grasping_b200.pcd import read_pcd
+    rng = np.random.default_rng(0)
+    pts = rng.normal(size=(37, 3)).astype(np.float32)
+    hdr = "# .PCD v0.7\nVERSION 0.7\nFIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\nWIDTH 37\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS 37\n"
+    p = tmp_path / "b.pcd"
+    p.write_bytes((hdr + "DATA binary\n").encode() + pts.tobytes())
+    assert read_pcd(str(p)).tobytes() == pts.tobytes()
+    p2 = tmp_path / "a.pcd"
+    p2.write_text(hdr + "DATA ascii\n" + "\n".join(" ".join(repr(float(v)) for v in row) for row in pts) + "\nextra 1 2\n")
+    assert read_pcd(str(p2)).tobytes() == pts.tobytes()
+
+
+def test_oracle_reproduces_committed_pins(oracle_lib, tmp_path):
+    """expected.json was written by the oracle; this guards the oracle (and the fixtures) against drift."""
+    with open(os.path.join(GOLDEN, "expected.json")) as fh:
+        exp = json.load(fh)
+    model = str(tmp_path / "trained.model")
+    with gzip.open(os.path.join(GOLDEN, "substitute_trained.model.gz"), "rb") as src, open(model, "wb") as dst:
+        dst.write(src.read())
+    clouds = np.load(os.path.join(GOLDEN, "clouds.npz"))
+    o = oracle_lib.Oracle(FEATURES, RANGE, model)
+    for name in ("pcd2", "pcd7", "pcd4", "table1"):
+        res = o.search(clouds[name], oracle_lib.make_request())
+        e = exp["trained/" + name]
+        assert list(res["best"].astuple()) == e["best"]
+        assert res["per_roll_top"].tolist() == e["per_roll_top"]
+        assert res["mask"].reshape(12, -1).sum(1).tolist() == e["mask_popcount"]
+
+
+def test_oracle_quirks(oracle_lib):
+    o = oracle_lib.Oracle(FEATURES, RANGE)
+    assert o.F == 324                              # trailing blank line -> phantom feature (II2FV.cpp:60-82)
+    reg, w = o.feature_table()
+    assert (w[:, 3] == 0).all()                    # 4th region weight never set (Haar.cpp:55-60)
+    patch = np.random.default_rng(1).uniform(0, 3, (15, 15)).astype(np.float32)
+    f = o.featurevalues(patch)
+    assert f[323] == -1.0                          # SHAF with every region skipped
+    assert o.text4(0.123449) == 0.1234 and o.text4(1234567.0) == 1235000.0 and o.text4(1e5) == 1e5
+    sc = o.scale(f[None, :])
+    assert sc.shape == (1, 324) and sc[0, 323] == 0.0  # dropped by svm-scale (single-valued attribute)
+
+
+def test_synth_cloud_is_deterministic():
+    from haf_grasping_b200 import synth
+    a, b = synth.synth_cloud(1234, 5000), synth.synth_cloud(1234, 5000)
+    assert a.tobytes() == b.tobytes()
+    assert a.dtype == np.float32 and a.shape == (5000, 3)
+    assert np.abs(a[:, :2]).max() < 0.28
+    import zlib
+    assert zlib.crc32(synth.synth_cloud(1234, 1000).tobytes()) == zlib.crc32(a[:1000].tobytes())  # counter-based

@@ -1,0 +1,321 @@
+"""GPU parity: the CUDA path, called through the C ABI (libhafgpu.so), against the CPU oracle on the same inputs.
+
+Bars (north_star): bit-exact heights / cell indices / integral images / masks / raw features / scaled SVM
+inputs / graspseval / per-roll tops / best grasp; decision values within a stated tolerance; labels identical.
+"""
+import gzip
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import FEATURES, GOLDEN, RANGE
+
+pytestmark = pytest.mark.gpu
+
+# |dec_gpu - dec_ref| <= DEC_RTOL * sum_i |coef_i| K_i  (FP32 contraction, FP64 accumulation of the decision sum);
+# north_star asks <= 1e-5 relative in FP32.
+DEC_RTOL = 1e-5
+# FP64 exact-order path: only exp() implementation differences (glibc vs CUDA, <= 1 ulp each term)
+DEC64_RTOL = 1e-13
+
+
+@pytest.fixture(scope="module")
+def clouds():
+    return np.load(os.path.join(GOLDEN, "clouds.npz"))
+
+
+@pytest.fixture(scope="module")
+def expected():
+    with open(os.path.join(GOLDEN, "expected.json")) as fh:
+        return json.load(fh)
+
+
+@pytest.fixture(scope="module")
+def trained_model(tmp_path_factory):
+    p = str(tmp_path_factory.mktemp("trained") / "substitute_trained.model")
+    with gzip.open(os.path.join(GOLDEN, "substitute_trained.model.gz"), "rb") as src, open(p, "wb") as dst:
+        dst.write(src.read())
+    return p
+
+
+@pytest.fixture(scope="module")
+def hg():
+    import haf_grasping_b200 as h
+    return h
+
+
+class Pair:
+    """GPU context + oracle on the same three files."""
+
+    def __init__(self, hg, orc, model, **kw):
+        self.gpu = hg.GraspSearch(FEATURES, RANGE, model, **kw)
+        self.orc = orc.Oracle(FEATURES, RANGE, model)
+        self.G = kw.get("grid", 56)
+        self.step = kw.get("roll_step_deg", 15)
+        self.rmax = kw.get("roll_max_deg", 190)
+
+    def coefK_scale(self, scaled):
+        """sum_i |coef_i| K_i >= |dec + rho|: the natural scale of the FP32 error; cheap upper bound used here."""
+        return self.abs_coef_sum
+
+    def close(self):
+        self.gpu.close()
+
+
+def abs_coef_sum(model_path):
+    s = 0.0
+    with open(model_path) as fh:
+        in_sv = False
+        for ln in fh:
+            if in_sv and ln.strip():
+                s += abs(float(ln.split()[0]))
+            elif ln.startswith("SV"):
+                in_sv = True
+    return s
+
+
+def mk_requests(hg, orc, **kw):
+    return hg.make_request(**kw), orc.make_request(**kw)
+
+
+def check_search(pair, xyz, hg, orc, model_path, dec_rtol=DEC_RTOL, full=True, **rqkw):
+    grq, orq = mk_requests(hg, orc, **rqkw)
+    G = pair.G
+    ores = pair.orc.search(xyz, orq, G=G, roll_step_deg=pair.step, roll_max_deg=pair.rmax)
+    gres = pair.gpu.search(xyz, [grq])
+    ob, gb = ores["best"], gres["best"]
+    nroll = ob.rolls_done
+    # heights, masks, graspseval: bit-exact (== on floats; the sign of a zero height is the only freedom)
+    lim = nroll  # rolls the reference loop evaluated (roll_limit / early exit); the GPU may have done more
+    assert np.array_equal(gres["heights"][0][:lim], ores["heights"][:lim])
+    assert np.array_equal(gres["mask"][0][:lim], ores["mask"][:lim])
+    integral = pair.gpu.debug_integral(len(ores["integral"]))
+    assert integral[:lim].tobytes() == ores["integral"][:lim].tobytes()
+    # windows: same set; features / scaled inputs / labels per window
+    win = pair.gpu.debug_windows()
+    raw, scaled = pair.gpu.debug_features()
+    dec, lab, guard = pair.gpu.debug_decisions()
+    order = np.lexsort((win[:, 1], win[:, 0]))  # (unit, cell) row-major == the reference's file order per roll
+    win, raw, scaled, dec, lab, guard = win[order], raw[order], scaled[order], dec[order], lab[order], guard[order]
+    o_dec_all = []
+    pos = 0
+    scale = abs_coef_sum(model_path)
+    for roll in range(lim):
+        feats_o, rc = pair.orc.calc_featurevectors(ores["integral"][roll], ores["mask"][roll])
+        W = len(feats_o)
+        sel = slice(pos, pos + W)
+        assert (win[sel, 0] == roll).all()
+        assert np.array_equal(win[sel, 1], rc[:, 0] * G + rc[:, 1])
+        assert raw[sel].tobytes() == feats_o.tobytes(), "raw features differ (roll %d)" % roll
+        scaled_o = pair.orc.scale(feats_o)[:, :pair.gpu.D]
+        assert scaled[sel].tobytes() == scaled_o.tobytes(), "scaled SVM inputs differ (roll %d)" % roll
+        pos += W
+    if nroll == len(ores["heights"]):
+        assert pos == len(win)
+    if full:
+        # decision values of all evaluated rolls (oracle concatenates rolls it evaluated; with early exit fewer)
+        o_dec = ores["dec"]
+        n = len(o_dec)
+        assert n <= len(dec)
+        err = np.abs(dec[:n] - o_dec)
+        assert err.max(initial=0.0) <= dec_rtol * scale, (err.max(), scale)
+        o_lab = np.where(o_dec > 0, pair.gpu.info.label0, pair.gpu.info.label1)
+        assert np.array_equal(lab[:n], o_lab), "labels differ"
+        assert np.array_equal(gres["graspseval"][0][:nroll], ores["graspseval"][:nroll])
+        assert np.array_equal(gres["per_roll_top"][0][:nroll], ores["per_roll_top"][:nroll])
+    assert gb.astuple() == ob.astuple(), (gb.astuple(), ob.astuple())
+    assert gb.eval == ob.eval and gb.rolls_done == ob.rolls_done and gb.n_windows_scored == ob.n_windows
+    assert abs(gb.roll_rad - ob.roll_rad) == 0
+    return gres, ores, guard
+
+
+@pytest.fixture(scope="module")
+def pair_trained(hg, oracle_lib, trained_model):
+    p = Pair(hg, oracle_lib, trained_model)
+    yield p
+    p.close()
+
+
+@pytest.fixture(scope="module")
+def pair_synth(hg, oracle_lib, tmp_models):
+    p = Pair(hg, oracle_lib, tmp_models(256))
+    yield p
+    p.close()
+
+
+ALL_CLOUDS = ["pcd1", "pcd2", "pcd3", "pcd4", "pcd5", "pcd6", "pcd7", "pcd8", "pcd9", "pcd10", "pcd11", "pcd12",
+              "plastic_mug2", "table1", "table2", "table3"]
+
+
+@pytest.mark.parametrize("name", ALL_CLOUDS)
+def test_bundled_pcd_trained_model(pair_trained, clouds, expected, hg, oracle_lib, trained_model, name):
+    gres, ores, _ = check_search(pair_trained, clouds[name], hg, oracle_lib, trained_model)
+    exp = expected["trained/" + name]
+    assert list(gres["best"].astuple()) == exp["best"]
+    assert gres["best"].n_windows_scored == exp["n_windows"]
+    assert gres["per_roll_top"][0].tolist() == exp["per_roll_top"]
+
+
+@pytest.mark.parametrize("name", ["pcd2", "pcd7", "plastic_mug2", "table1", "table3"])
+def test_bundled_pcd_synth_model(pair_synth, clouds, expected, hg, oracle_lib, tmp_models, name):
+    gres, _, _ = check_search(pair_synth, clouds[name], hg, oracle_lib, tmp_models(256))
+    assert list(gres["best"].astuple()) == expected["synth256/" + name]["best"]
+
+
+@pytest.mark.parametrize("name,roll", [("pcd2", 0), ("table1", 4), ("table2", 11), ("plastic_mug2", 7)])
+def test_cell_indices_bit_exact(pair_synth, clouds, hg, oracle_lib, name, roll):
+    xyz = clouds[name]
+    grq, _ = mk_requests(hg, oracle_lib)
+    cells = pair_synth.gpu.debug_cell_indices(xyz, grq, roll)
+    o = pair_synth.orc
+    M = o.build_transform((0, 0, 0), o.normalize_approach((0, 0, 1)), 1, roll)
+    _, ocells, clamped = o.generate_grid(xyz, M, want_cells=True)
+    assert clamped == 0
+    assert np.array_equal(cells, ocells)
+
+
+def test_device_text_roundtrips_match_glibc(pair_synth):
+    rng = np.random.default_rng(3)
+    f = np.concatenate([
+        rng.integers(0, 2 ** 32, 200000, dtype=np.uint64).astype(np.uint32).view(np.float32),
+        (rng.uniform(-1, 1, 200000) * 10.0 ** rng.integers(-8, 5, 200000)).astype(np.float32),
+        np.array([0.0, -0.0, 1.0, 9999.5, 99995.0, 0.00012345, 1e-20, 3e38, 1e-45, 12345.0, 0.5, 1234.5, 1235.5], np.float32)])
+    f = f[np.isfinite(f)]
+    v = np.concatenate([rng.uniform(-1.5, 1.5, 300000), rng.uniform(-1, 1, 100000) * 10.0 ** rng.integers(-30, 30, 100000),
+                        np.array([0.0, 1.0, -1.0, 0.1234565, 1234565.0, 0.9999995, 1e-7, 123456.5, 1e22])])
+    o4, o6 = pair_synth.gpu.debug_text_roundtrip(f, v)
+    r4 = np.array([float("%.4g" % float(x)) for x in f])
+    r6 = np.array([float("%g" % float(x)) for x in v])
+    assert o4.tobytes() == r4.tobytes()
+    assert o6.tobytes() == r6.tobytes()
+
+
+def test_fp64_exact_mode(hg, oracle_lib, trained_model, clouds):
+    p = Pair(hg, oracle_lib, trained_model, svm_mode=hg.HAF_SVM_FP64_EXACT)
+    try:
+        check_search(p, clouds["pcd2"], hg, oracle_lib, trained_model, dec_rtol=DEC64_RTOL)
+        check_search(p, clouds["table2"], hg, oracle_lib, trained_model, dec_rtol=DEC64_RTOL)
+    finally:
+        p.close()
+
+
+def test_guard_band_catches_near_zero_decisions(hg, oracle_lib, tmp_models, clouds):
+    """rho chosen so that many decision values sit next to 0: labels must still equal the oracle's."""
+    model = tmp_models(256, rho=-0.2972253)  # a decision value of pcd2 / roll 0 with the synth model is -0.2972253033...
+    p = Pair(hg, oracle_lib, model, guard_rel=1e-3)
+    try:
+        _, _, guard = check_search(p, clouds["pcd2"], hg, oracle_lib, model)
+        assert guard.sum() > 0
+    finally:
+        p.close()
+
+
+def test_label_order_minus_plus(hg, oracle_lib, tmp_models, clouds):
+    model = tmp_models(256, labels=(-1, 1), rho=0.01)
+    p = Pair(hg, oracle_lib, model)
+    try:
+        check_search(p, clouds["pcd3"], hg, oracle_lib, model)
+    finally:
+        p.close()
+
+
+def test_no_text_emulation_mode(hg, oracle_lib, tmp_models, clouds):
+    model = tmp_models(256)
+    gpu = hg.GraspSearch(FEATURES, RANGE, model, emulate_text_roundtrip=False)
+    o = oracle_lib.Oracle(FEATURES, RANGE, model)
+    try:
+        res = gpu.search(clouds["pcd2"])
+        ores = o.search(clouds["pcd2"], oracle_lib.make_request(), emulate_text=False)
+        raw, scaled = gpu.debug_features()
+        win = gpu.debug_windows()
+        order = np.lexsort((win[:, 1], win[:, 0]))
+        feats_o, _ = o.calc_featurevectors(ores["integral"][0], ores["mask"][0])
+        sc_o = o.scale(feats_o, emulate_text=False)[:, :gpu.D]
+        W0 = len(feats_o)
+        assert scaled[order][:W0].tobytes() == sc_o.tobytes()
+        assert res["best"].astuple() == ores["best"].astuple()
+    finally:
+        gpu.close()
+
+
+def test_request_variants(pair_synth, clouds, hg, oracle_lib, tmp_models):
+    m = tmp_models(256)
+    xyz = clouds["table1"]
+    check_search(pair_synth, xyz, hg, oracle_lib, m, center=(0.1, 0.25, 0.0), area=(30.0, 40.0), full=True)
+    check_search(pair_synth, xyz, hg, oracle_lib, m, width=2)
+    check_search(pair_synth, xyz, hg, oracle_lib, m, roll_limit=5)
+    check_search(pair_synth, xyz, hg, oracle_lib, m, return_only_best=1, graspval_top=60)
+    check_search(pair_synth, xyz, hg, oracle_lib, m, area=(14.9, 20.0))  # height_r = 0
+    check_search(pair_synth, np.zeros((0, 3), np.float32), hg, oracle_lib, m)  # empty cloud
+
+
+def test_padded_stride_and_device_pointer(pair_synth, clouds, hg):
+    import torch
+    xyz = clouds["pcd2"]
+    ref = pair_synth.gpu.search(xyz)["best"].astuple()
+    padded = np.zeros((len(xyz), 4), np.float32)  # pcl::PointXYZ layout (16-byte stride)
+    padded[:, :3] = xyz
+    padded[:, 3] = 1.0
+    assert pair_synth.gpu.search(padded, stride_bytes=16)["best"].astuple() == ref
+    dev = torch.from_numpy(xyz).cuda()
+    assert pair_synth.gpu.search(dev)["best"].astuple() == ref
+
+
+TILTED = [(0.0, 0.0, 1.0), (0.5, 0.0, 0.8660254), (-0.5, 0.0, 0.8660254), (0.0, 0.5, 0.8660254), (0.0, -0.5, 0.8660254)]
+
+
+def test_approach_vectors(pair_synth, clouds, hg, oracle_lib):
+    """config 3: five approach vectors in one call == five oracle goals; overall winner = strict >, earliest."""
+    xyz = clouds["table2"]
+    greqs = [hg.make_request(approach=a) for a in TILTED]
+    gres = pair_synth.gpu.search(xyz, greqs)
+    tops = []
+    for i, a in enumerate(TILTED):
+        ores = pair_synth.orc.search(xyz, oracle_lib.make_request(approach=a))
+        assert gres["best_per_request"][i].astuple() == ores["best"].astuple()
+        assert np.array_equal(gres["heights"][i], ores["heights"])
+        assert np.array_equal(gres["mask"][i], ores["mask"])
+        assert np.array_equal(gres["graspseval"][i], ores["graspseval"])
+        assert np.array_equal(gres["per_roll_top"][i], ores["per_roll_top"])
+        tops.append(ores["best"].topval)
+    win = int(np.argmax(tops))  # argmax returns the first maximum
+    assert gres["best"].approach_idx == win
+    assert gres["best"].astuple() == gres["best_per_request"][win].astuple()
+
+
+def test_batch_matches_single(pair_synth, hg, oracle_lib):
+    from haf_grasping_b200 import synth
+    cl = [synth.synth_cloud(1234 + i, 20000 + 137 * i) for i in range(6)]
+    best = pair_synth.gpu.search_batch(cl)
+    off = np.concatenate([[0], np.cumsum([len(c) for c in cl])])
+    best2 = pair_synth.gpu.search_batch_packed(np.concatenate(cl), off)
+    for i, c in enumerate(cl):
+        ob = pair_synth.orc.search(c, oracle_lib.make_request(), full=False)["best"]
+        assert best[i].astuple() == ob.astuple()
+        assert best2[i].astuple() == ob.astuple()
+        assert best[i].n_windows_scored == ob.n_windows
+
+
+def test_large_grid_path(hg, oracle_lib, tmp_models):
+    """G = 192 exercises the two-kernel integral image and multi-CTA mask compaction."""
+    from haf_grasping_b200 import synth
+    model = tmp_models(64, seed=11)
+    p = Pair(hg, oracle_lib, model, grid=192, roll_step_deg=45, roll_max_deg=190)
+    try:
+        xyz = synth.synth_cloud(77, 150000, r=0.96)
+        check_search(p, xyz, hg, oracle_lib, model, area=(60.0, 52.0))
+    finally:
+        p.close()
+
+
+def test_create_errors(hg, tmp_models, tmp_path):
+    with pytest.raises(hg.HafError) as e:
+        hg.GraspSearch(FEATURES, RANGE, str(tmp_path / "missing.model"))
+    assert e.value.code == -2
+    bad = tmp_path / "lin.model"
+    bad.write_text("svm_type c_svc\nkernel_type linear\nnr_class 2\ntotal_sv 1\nrho 0\nlabel 1 -1\nnr_sv 1 0\nSV\n1 1:0.5 \n")
+    with pytest.raises(hg.HafError) as e:
+        hg.GraspSearch(FEATURES, RANGE, str(bad))
+    assert e.value.code == -5
