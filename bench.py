@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""bench.py -- grasp windows scored per second (all rolls) and ms per cloud, BASELINE.json's metric.
+
+Default workload (N = 1): the per-GPU share of BASELINE.json configs[4] ("throughput mode"): 512 synthetic
+100k-point clouds (seeds 1234 + i), G = 56, 12 rolls, area 32x44, approach (0,0,1), synthetic SVM model with
+2048 support vectors (the trained model is missing from the reference checkout).  Weak scaling: every rank
+processes its own 512 clouds (4096 at N = 8), clouds are sharded by rank with no data-path collective; only the
+best-grasp records are exchanged (NCCL all_gather) inside the timed region.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload batch|grid512|table1]
+
+`value`  : windows/s with the clouds already resident in HBM, K steps timed with CUDA events on the stream the
+           kernels run on, max over ranks.  Inputs (614 MB / rank) are larger than L2, no flush needed.
+`e2e`    : same metric through the C-ABI call with HOST (pinned) buffers: host->device copy of the clouds and
+           device->host copy of the results inside the timed region.
+`--impl reference` : the reference's own CPU path (its feature classes + svm-scale + svm-predict child processes
+           on text files, compiled in place under oracle/_ref; the ROS-bound members restated by the oracle) on
+           all host cores, one cloud per worker process, a bounded sample of the same workload per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+FEATURES = os.path.join(ROOT, "tests", "golden", "refdata", "Features.txt")
+RANGE = os.path.join(ROOT, "tests", "golden", "refdata", "range21062012_allfeatures")
+METRIC = "grasp_windows_scored_per_sec_all_rolls"
+UNIT = "windows/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="batch", choices=["batch", "grid512", "table1"])
+    ap.add_argument("--clouds", type=int, default=512, help="clouds per GPU (batch workload)")
+    ap.add_argument("--points", type=int, default=100000)
+    ap.add_argument("--nsv", type=int, default=2048)
+    ap.add_argument("--svm-mode", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-clouds", type=int, default=2)
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            d = json.load(fh)
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+def model_path(nsv):
+    from haf_grasping_b200 import synth
+    d = os.path.join(tempfile.gettempdir(), "haf_bench_models")
+    os.makedirs(d, exist_ok=True)
+    p = os.path.join(d, "synth_%d_seed7.model" % nsv)
+    if not os.path.exists(p):
+        synth.write_synth_model(p, n_sv=nsv, seed=7)
+    return p
+
+
+def workload_config(args):
+    if args.workload == "batch":
+        return dict(grid=56, rmax=190, step=15, area=(32.0, 44.0), r=0.28, n_clouds=args.clouds, n_points=args.points)
+    if args.workload == "grid512":  # BASELINE.json configs[3]
+        return dict(grid=512, rmax=190, step=15, area=(362.0, 362.0), r=2.56, n_clouds=1, n_points=1000000)
+    return dict(grid=56, rmax=190, step=15, area=(32.0, 44.0), r=0.28, n_clouds=1, n_points=0)
+
+
+def make_clouds(args, wc, rank):
+    """list of float32 [n,3] arrays for this rank (seeds 1234 + global cloud index)"""
+    import numpy as np
+    from haf_grasping_b200 import synth
+    if args.workload == "table1":
+        z = np.load(os.path.join(ROOT, "tests", "golden", "clouds.npz"))
+        return [np.ascontiguousarray(z["table1"])]
+    base = 1234 + rank * wc["n_clouds"]
+    return [synth.synth_cloud(base + i, wc["n_points"], r=wc["r"]) for i in range(wc["n_clouds"])]
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            self.path = tempfile.mktemp(prefix="haf_clocks_", suffix=".csv")
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.fh,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if not self.proc:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.fh.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        with open(self.path) as fh:
+            for ln in fh:
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for k, nm in enumerate(names):
+                    if f[5 + k].lower().startswith("active"):
+                        reasons.add(nm)
+        os.remove(self.path)
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+# ------------------------------------------------------------------------------------------------------
+# reference CPU path (one cloud): reference feature class + svm-scale + svm-predict on files, per roll,
+# exactly as server.cpp:616-656 and :754-800 do; the ROS-bound members come from the oracle restatement.
+# ------------------------------------------------------------------------------------------------------
+def _ref_cloud_worker(job):
+    xyz, model, grid, step, rmax, area, kind = job
+    from oracle import orc
+    o = orc.Oracle(FEATURES, RANGE, model)
+    t0 = time.perf_counter()
+    R = rmax // step
+    windows = 0
+    if kind == "reference":
+        r = orc.Ref(FEATURES, RANGE, model)
+        av = o.normalize_approach((0, 0, 1))
+        wd = tempfile.mkdtemp(prefix="hafref_")
+        best = (-1000, -1, -1, -1)
+        for roll in range(R):
+            M = o.build_transform((0, 0, 0), av, 1, roll, step)
+            integral = o.calc_intimage(o.generate_grid(xyz, M, grid))
+            mask = o.pnt_in_box(integral, roll, (int(area[0]), int(area[1])), step)
+            labels, _ = r.roll_file_exact(integral, mask, workdir=wd)
+            _, top, _ = o.show_predicted_gps(labels, mask)
+            windows += len(labels)
+            if top[2] > best[0]:
+                best = (top[2], top[0], top[1], roll)
+        for f in os.listdir(wd):
+            os.remove(os.path.join(wd, f))
+        os.rmdir(wd)
+    else:  # "port": the in-process oracle
+        res = o.search(xyz, orc.make_request(area=area), G=grid, roll_step_deg=step, roll_max_deg=rmax, full=False)
+        windows = int(res["best"].n_windows)
+    return windows, time.perf_counter() - t0
+
+
+def cpu_reference_rate(args, wc, clouds, n_workers, model):
+    """windows/s of the reference CPU path over `clouds` with n_workers processes (one cloud each at a time)."""
+    import multiprocessing as mp
+    from oracle import orc
+    orc.build(ref=os.path.isdir("/root/reference"))
+    kind = "reference" if orc.ref_available() else "port"
+    jobs = [(c, model, wc["grid"], wc["step"], wc["rmax"], wc["area"], kind) for c in clouds]
+    t0 = time.perf_counter()
+    if n_workers <= 1:
+        res = [_ref_cloud_worker(j) for j in jobs]
+    else:
+        with mp.get_context("fork").Pool(n_workers) as pool:
+            res = pool.map(_ref_cloud_worker, jobs, chunksize=1)
+    dt = time.perf_counter() - t0
+    return sum(r[0] for r in res) / dt, sum(r[0] for r in res), dt, kind
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wc = workload_config(args)
+    model = model_path(args.nsv)
+    cores = max(1, min(os.cpu_count() or 1, 64))
+    per_step = cores
+    if args.workload != "batch":
+        per_step = 1
+        cores = 1
+    import numpy as np  # noqa: F401
+    from haf_grasping_b200 import synth
+    times, wins, kind = [], [], "port"
+    for s in range(args.warmup + args.steps):
+        if args.workload == "batch":
+            clouds = [synth.synth_cloud(1234 + (s * per_step + i) % wc["n_clouds"], wc["n_points"], r=wc["r"]) for i in range(per_step)]
+        else:
+            clouds = make_clouds(args, wc, 0)
+        rate, w, dt, kind = cpu_reference_rate(args, wc, clouds, cores, model)
+        if s >= args.warmup:
+            times.append(dt)
+            wins.append(w)
+    value = sum(wins) / sum(times)
+    sample = "%d cloud(s) per step (one per worker process), %d timed steps; %s" % (
+        per_step, args.steps, "reference feature classes + svm-scale + svm-predict child processes on text files per roll"
+        if kind == "reference" else "in-process oracle port")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": describe(args, wc), "n_sv": args.nsv},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def describe(args, wc):
+    if args.workload == "batch":
+        return ("configs[4] per-GPU share: %d synthetic clouds x %d points per GPU, G=56, 12 rolls, area 32x44, AV (0,0,1)"
+                % (wc["n_clouds"], wc["n_points"]))
+    if args.workload == "grid512":
+        return "configs[3]: synthetic 1M-point cloud, G=512, area 362x362, 12 rolls"
+    return "configs[1]: table1 scene (102876 points), G=56, 12 rolls, default request"
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import haf_grasping_b200 as h
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; libhafgpu has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    wc = workload_config(args)
+    model = model_path(args.nsv) if rank == 0 or world == 1 else None
+    if world > 1:
+        dist.barrier()
+        model = model_path(args.nsv)
+    clouds = make_clouds(args, wc, rank)
+    offsets = np.concatenate([[0], np.cumsum([len(c) for c in clouds])]).astype(np.int64)
+    total_pts = int(offsets[-1])
+    host = torch.empty((total_pts, 3), dtype=torch.float32, pin_memory=True)
+    host.numpy()[:] = np.concatenate(clouds)
+    dev = host.cuda(non_blocking=False)
+    n_clouds = len(clouds)
+
+    gs = h.GraspSearch(FEATURES, RANGE, model, grid=wc["grid"], roll_step_deg=wc["step"], roll_max_deg=wc["rmax"],
+                       device=local, svm_mode=args.svm_mode)
+    stream = torch.cuda.current_stream()
+    gs.set_stream(stream.cuda_stream)
+    gs.set_profiling(True)
+    rq = h.make_request(area=wc["area"])
+    gathered = [torch.zeros((n_clouds, 5), dtype=torch.int32, device="cuda") for _ in range(world)] if world > 1 else None
+
+    def step(buf):
+        best = gs.search_batch_packed(buf, offsets, rq)
+        if world > 1:  # the one exchange of the path: best-grasp records over NCCL
+            rec = torch.tensor([b.astuple() for b in best], dtype=torch.int32).cuda(non_blocking=True)
+            dist.all_gather(gathered, rec)
+        return best
+
+    def timed(buf, steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        acc = dict(svm=0.0, bin=0.0, integral=0.0, mask=0.0, features=0.0, guard=0.0, score=0.0, windows=0, guardw=0, chunks=0, launches=0)
+        for _ in range(steps):
+            step(buf)
+            t = gs.timing()
+            for k in ("svm", "bin", "integral", "mask", "features", "guard", "score"):
+                acc[k] += getattr(t, "ms_" + k)
+            acc["windows"] += t.n_windows
+            acc["guardw"] += t.n_guard
+            acc["chunks"] += t.n_chunks
+            acc["launches"] += t.launches
+        e1.record(stream)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            tm = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            ms = float(tm.item())
+            tw = torch.tensor([float(acc["windows"])], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tw, op=dist.ReduceOp.SUM)
+            acc["windows_all"] = float(tw.item())
+        else:
+            acc["windows_all"] = float(acc["windows"])
+        return ms, wall, acc
+
+    for _ in range(max(args.warmup, 3)):
+        step(dev)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_dev, wall_dev, acc = timed(dev, args.steps)
+    clocks = sampler.stop() if rank == 0 else {}
+    # end to end: host (pinned) buffers in, results out, through the same C-ABI call
+    for _ in range(2):
+        step(host.numpy())
+    ms_e2e, wall_e2e, acc2 = timed(host.numpy(), args.steps)
+
+    if rank == 0:
+        hbm, tf_burst, tf_sust, src = peaks()
+        info = gs.info
+        W_step = acc["windows"] / args.steps          # this rank
+        value = acc["windows_all"] / (ms_dev * 1e-3)
+        e2e = acc2["windows_all"] / (ms_e2e * 1e-3)
+        svm_launches = acc["chunks"]
+        svm_ms = acc["svm"] / max(svm_launches, 1)
+        flops_per_window = info.n_sv * (2.0 * info.n_dims + 4.0)   # W*S*(2D+4)
+        svm_tflops = (acc["windows"] / max(svm_launches, 1)) * flops_per_window / (svm_ms * 1e-3) / 1e12 if svm_ms > 0 else 0.0
+        peak = tf_sust
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.svm_mode != 1 else "f64", "data": "synthetic",
+            "config": {"workload": describe(args, wc), "n_sv": info.n_sv, "n_dims": info.n_dims, "grid": info.grid,
+                       "rolls": info.n_rolls, "clouds_per_gpu": n_clouds, "windows_per_step_per_gpu": W_step,
+                       "svm_mode": args.svm_mode, "l2": "inputs (%.0f MB per GPU per step) larger than L2, no flush" % (total_pts * 12 / 1e6),
+                       "sharding": "clouds by rank, no data-path collective; NCCL all_gather of best-grasp records"},
+            "ms_per_cloud": ms_dev / args.steps / n_clouds,
+            "clocks": clocks,
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": total_pts * 12 + 0, "d2h_bytes_per_step": n_clouds * (32 + info.n_rolls * 12) + 64,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(acc["launches"]),
+            "roofline": {"kernel": "svm_rbf_simt_kernel" if args.svm_mode == 0 else "svm_exact_kernel", "bound": "tensor",
+                         "achieved": svm_tflops, "peak": peak, "unit": "TFLOP/s", "frac": svm_tflops / peak if peak else None,
+                         "traffic": None, "peak_source": src + " bf16 sustained (kernel timed inside a long step)",
+                         "algorithmic": "W*S*(2D+4) flop per launch, W=%.0f S=%d D=%d" % (acc["windows"] / max(svm_launches, 1), info.n_sv, info.n_dims),
+                         "kernel_ms": svm_ms, "share_of_step": acc["svm"] / ms_dev if ms_dev else None,
+                         "note": "FP32 SIMT contraction (CUDA cores): measured against the bf16 tensor peak for comparability"},
+            "stage_ms_per_step": {k: acc[k] / args.steps for k in ("bin", "integral", "mask", "features", "svm", "guard", "score")},
+            "guard_windows_per_step": acc["guardw"] / args.steps,
+            "wall_ms_per_step": 1e3 * wall_dev / args.steps,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            ns = min(args.cpu_sample_clouds, n_clouds)
+            rate, w, dt, kind = cpu_reference_rate(args, wc, clouds[:ns], 1, model)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": 1, "kind": kind,
+                                    "sample": "first %d cloud(s) of the same workload, all 12 rolls, %d windows in %.1f s; %s" % (
+                                        ns, w, dt, "reference feature classes + svm-scale/svm-predict child processes on text files"
+                                        if kind == "reference" else "in-process oracle port")}
+        print(json.dumps(line), flush=True)
+    gs.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

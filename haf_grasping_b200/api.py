@@ -55,7 +55,7 @@ class haf_timing(C.Structure):
     _fields_ = [("ms_total", C.c_float), ("ms_bin", C.c_float), ("ms_integral", C.c_float), ("ms_mask", C.c_float),
                 ("ms_features", C.c_float), ("ms_svm", C.c_float), ("ms_guard", C.c_float), ("ms_score", C.c_float),
                 ("n_points", C.c_longlong), ("n_units", C.c_longlong), ("n_windows", C.c_longlong),
-                ("n_guard", C.c_longlong), ("launches", C.c_longlong)]
+                ("n_guard", C.c_longlong), ("launches", C.c_longlong), ("n_chunks", C.c_longlong)]
 
 
 EXPORTS = ["haf_create", "haf_destroy", "haf_last_error", "haf_get_info", "haf_set_stream", "haf_set_profiling",

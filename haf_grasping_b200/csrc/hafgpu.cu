@@ -71,8 +71,9 @@ struct haf_ctx {
     bool profiling = false;
     long long launches = 0;
     haf_timing timing;
-    cudaEvent_t ev[10];
+    cudaEvent_t ev[10];               // [8] start, [9] end of a call
     bool ev_ok = false;
+    std::vector<cudaEvent_t> ev_pool; // 8 per chunk when per-stage profiling is on (no host sync inside a call)
 
     // model-side constants
     int F = 0, D = 0, Dsv = 0, Kpad = 0, S = 0, Spad = 0, R = 0, G = 0;
@@ -345,6 +346,7 @@ extern "C" void haf_destroy(haf_ctx* ctx) {
     ctx->d_xn.release(); ctx->d_dec.release(); ctx->d_guardflag.release(); ctx->d_guardlist.release(); ctx->d_kscratch.release();
     ctx->d_counters.release(); ctx->h_stage.release(); ctx->h_results.release(); ctx->h_per_roll_top.release(); ctx->h_counters.release();
     if (ctx->ev_ok) for (int i = 0; i < 10; i++) cudaEventDestroy(ctx->ev[i]);
+    for (size_t i = 0; i < ctx->ev_pool.size(); i++) cudaEventDestroy(ctx->ev_pool[i]);
     cudaGetLastError();
     delete ctx;
 }
@@ -487,6 +489,13 @@ static int run_jobs(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& jobs, fl
         return ctx->fail(HAF_ERR_UNSUPPORTED, "per-roll outputs need the whole request in one chunk (windows x dims too large)");
 
     const bool prof = ctx->profiling;
+    if (prof) {
+        while (ctx->ev_pool.size() < chunks.size() * 8) {
+            cudaEvent_t e;
+            CUDA_TRY(ctx, cudaEventCreate(&e));
+            ctx->ev_pool.push_back(e);
+        }
+    }
     float ms_stage[7] = {0, 0, 0, 0, 0, 0, 0};
     long long total_windows = 0, total_guard = 0;
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[8], st));
@@ -515,7 +524,7 @@ static int run_jobs(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& jobs, fl
         const UnitParams* units_c = ctx->d_units.p + ubase;
 
         // 1. binning
-        if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], st));
+        if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[ci * 8 + 0], st));
         {
             const size_t n = (size_t)Uc * GG;
             fill_u32_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 16), 256, 0, st>>>(ctx->d_keys.p, n, HAF_KEY_MINUS_ONE);
@@ -531,7 +540,7 @@ static int run_jobs(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& jobs, fl
             }
         }
         // 2. integral image
-        if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], st));
+        if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[ci * 8 + 1], st));
         if (smallG) {
             integral_small_kernel<<<Uc, 128, (size_t)G * ld * sizeof(double), st>>>(ctx->d_keys.p, ctx->d_integral.p, G, units_c);
             LAUNCHED(ctx);
@@ -542,12 +551,12 @@ static int run_jobs(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& jobs, fl
             LAUNCHED(ctx);
         }
         // 3. mask + window compaction
-        if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], st));
+        if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[ci * 8 + 2], st));
         mask_windows_kernel<<<dim3((GG + 4095) / 4096, Uc), 256, 0, st>>>(ctx->d_integral.p, units_c, G, ctx->d_mask.p, ctx->d_labelgrid.p,
                                                                          ctx->d_win.p, cnt + 0, (unsigned)Wcap, (int*)(cnt + 2), ubase);
         LAUNCHED(ctx);
         // 4. features -> scaled SVM inputs
-        if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev[3], st));
+        if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[ci * 8 + 3], st));
         const unsigned wblocks32 = (unsigned)((Wcap + 31) / 32);
         if (ctx->cfg.svm_mode != HAF_SVM_FP64_EXACT) {
             features_kernel<false><<<wblocks32, 256, 0, st>>>(ctx->d_integral.p, ctx->d_win.p, cnt + 0, G, ubase, ctx->d_feats.p, ctx->d_dims.p,
@@ -558,7 +567,7 @@ static int run_jobs(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& jobs, fl
             LAUNCHED(ctx);
         }
         // 5. SVM decision values
-        if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev[4], st));
+        if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[ci * 8 + 4], st));
         if (ctx->cfg.svm_mode == HAF_SVM_FP64_EXACT) {
             CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_guardflag.p, 0, ldx, st));
             svm_exact_kernel<<<exact_ctas, 256, ctx->Dsv * sizeof(double), st>>>(nullptr, nullptr, cnt + 0, ctx->d_integral.p, ctx->d_win.p, G, ubase,
@@ -566,13 +575,13 @@ static int run_jobs(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& jobs, fl
                                                                                    ctx->cfg.emulate_text_roundtrip, ctx->d_sv64T.p, ctx->Spad, ctx->S, ctx->Dsv,
                                                                                    ctx->d_coef64.p, ctx->gamma, ctx->rho, ctx->d_kscratch.p, ctx->d_dec.p, (int*)(cnt + 3));
             LAUNCHED(ctx);
-            if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev[5], st));
+            if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[ci * 8 + 5], st));
         } else {
             svm_rbf_simt_kernel<<<(unsigned)(ldx / SVM_BM), 256, SVM_STAGES * SVM_BK * (SVM_BM + SVM_BN) * 4, st>>>(
                 ctx->d_X.p, ldx, ctx->d_svT.p, ctx->Spad, ctx->Kpad, ctx->d_xn.p, ctx->d_svn.p, ctx->d_coef.p, neg_gamma_log2e, ctx->rho,
                 ctx->guard_rel, cnt + 0, ctx->d_dec.p, ctx->d_guardflag.p, ctx->d_guardlist.p, cnt + 1);
             LAUNCHED(ctx);
-            if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev[5], st));
+            if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[ci * 8 + 5], st));
             svm_exact_kernel<<<exact_ctas, 256, ctx->Dsv * sizeof(double), st>>>(ctx->d_guardlist.p, cnt + 1, cnt + 0, ctx->d_integral.p, ctx->d_win.p, G, ubase,
                                                                                    ctx->d_feats.p, ctx->d_dims.p, ctx->D, ctx->lower, ctx->upper,
                                                                                    ctx->cfg.emulate_text_roundtrip, ctx->d_sv64T.p, ctx->Spad, ctx->S, ctx->Dsv,
@@ -580,7 +589,7 @@ static int run_jobs(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& jobs, fl
             LAUNCHED(ctx);
         }
         // 6. labels -> grids, score stencil, argmax, tie rule
-        if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev[6], st));
+        if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[ci * 8 + 6], st));
         label_scatter_kernel<<<(unsigned)((Wcap + 255) / 256), 256, 0, st>>>(ctx->d_dec.p, ctx->d_win.p, cnt + 0, G, ubase, ctx->gv[0], ctx->gv[1],
                                                                             ctx->d_labelgrid.p, ctx->d_unit_windows.p + ubase);
         LAUNCHED(ctx);
@@ -588,15 +597,11 @@ static int run_jobs(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& jobs, fl
         LAUNCHED(ctx);
         tie_rule_kernel<<<dim3((G + 7) / 8, Uc), 256, 0, st>>>(ctx->d_evals.p, G, units_c, ctx->d_unit_top.p + ubase, ctx->d_unit_run.p + ubase);
         LAUNCHED(ctx);
-        if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev[7], st));
+        if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[ci * 8 + 7], st));
 
         // bookkeeping per chunk: window / guard counts accumulate on the device ([8] windows, [9] guard), no host sync
         accumulate_counts_kernel<<<1, 1, 0, st>>>(cnt);
         LAUNCHED(ctx);
-        if (prof) {
-            CUDA_TRY(ctx, cudaStreamSynchronize(st));
-            for (int s = 0; s < 7; s++) { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[s], ctx->ev[s + 1]); ms_stage[s] += ms; }
-        }
         if (keep_debug_state) { ctx->last_units = Uc; ctx->last_unit_base = ubase; ctx->last_ldx = ldx; }
 
         // optional per-roll outputs (single chunk): active units only
@@ -626,6 +631,9 @@ static int run_jobs(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& jobs, fl
     if (ctx->h_counters.p[3]) return ctx->fail(HAF_ERR_UNSUPPORTED, "a feature value fell outside the range the decimal text emulation reproduces exactly");
     float ms_total = 0;
     cudaEventElapsedTime(&ms_total, ctx->ev[8], ctx->ev[9]);
+    if (prof)
+        for (size_t ci = 0; ci < chunks.size(); ci++)
+            for (int s = 0; s < 7; s++) { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev_pool[ci * 8 + s], ctx->ev_pool[ci * 8 + s + 1]); ms_stage[s] += ms; }
     haf_timing& t = ctx->timing;
     memset(&t, 0, sizeof t);
     t.ms_total = ms_total;
@@ -634,6 +642,7 @@ static int run_jobs(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& jobs, fl
     t.n_points = cs.off[n_clouds] - cs.off[0]; t.n_units = 0;
     for (int j = 0; j < n_jobs; j++) t.n_units += jobs[j].n_rolls_active;
     t.n_windows = total_windows; t.n_guard = total_guard; t.launches = ctx->launches - launches0;
+    t.n_chunks = (long long)chunks.size();
     if (keep_debug_state) { ctx->last_W = (unsigned)total_windows; ctx->last_valid = true; }
     return HAF_OK;
 }

@@ -100,6 +100,7 @@ typedef struct {
     float ms_total;   /* device time of the last haf_search / haf_search_batch* call (CUDA events on its stream) */
     float ms_bin, ms_integral, ms_mask, ms_features, ms_svm, ms_guard, ms_score;
     long long n_points, n_units, n_windows, n_guard, launches;
+    long long n_chunks; /* passes over the stage sequence (each launches every stage kernel once) */
 } haf_timing;
 
 /* ---- lifetime --------------------------------------------------------------------------------------------- */
