@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--clouds", type=int, default=512, help="clouds per GPU (batch workload)")
     ap.add_argument("--points", type=int, default=100000)
     ap.add_argument("--nsv", type=int, default=2048)
-    ap.add_argument("--svm-mode", type=int, default=0)
+    ap.add_argument("--svm-mode", type=int, default=2, help="0 FP32 SIMT + guard, 1 FP64 exact, 2 tcgen05 split-bf16 + guard")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-clouds", type=int, default=2)
     return ap.parse_args()
@@ -338,7 +338,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if args.svm_mode != 1 else "f64", "data": "synthetic",
+            "dtype": {0: "f32", 1: "f64", 2: "bf16x2-split/f32-accumulate"}[args.svm_mode], "data": "synthetic",
             "config": {"workload": describe(args, wc), "n_sv": info.n_sv, "n_dims": info.n_dims, "grid": info.grid,
                        "rolls": info.n_rolls, "clouds_per_gpu": n_clouds, "windows_per_step_per_gpu": W_step,
                        "svm_mode": args.svm_mode, "l2": "inputs (%.0f MB per GPU per step) larger than L2, no flush" % (total_pts * 12 / 1e6),
@@ -346,14 +346,18 @@ def run_ours(args):
             "ms_per_cloud": ms_dev / args.steps / n_clouds,
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": total_pts * 12 + 0, "d2h_bytes_per_step": n_clouds * (32 + info.n_rolls * 12) + 64,
-                    "ms_per_step": ms_e2e / args.steps},
+                    "ms_per_step": ms_e2e / args.steps,
+                    "stage_ms_per_step": {k: acc2[k] / args.steps for k in ("bin", "integral", "mask", "features", "svm", "guard", "score")},
+                    "chunks_per_step": acc2["chunks"] / args.steps},
             "gpu_launches": int(acc["launches"]),
-            "roofline": {"kernel": "svm_rbf_simt_kernel" if args.svm_mode == 0 else "svm_exact_kernel", "bound": "tensor",
+            "roofline": {"kernel": {0: "svm_rbf_simt_kernel", 1: "svm_exact_kernel", 2: "svm_rbf_tc_kernel"}[args.svm_mode], "bound": "tensor",
                          "achieved": svm_tflops, "peak": peak, "unit": "TFLOP/s", "frac": svm_tflops / peak if peak else None,
                          "traffic": None, "peak_source": src + " bf16 sustained (kernel timed inside a long step)",
                          "algorithmic": "W*S*(2D+4) flop per launch, W=%.0f S=%d D=%d" % (acc["windows"] / max(svm_launches, 1), info.n_sv, info.n_dims),
                          "kernel_ms": svm_ms, "share_of_step": acc["svm"] / ms_dev if ms_dev else None,
-                         "note": "FP32 SIMT contraction (CUDA cores): measured against the bf16 tensor peak for comparability"},
+                         "note": {0: "FP32 SIMT contraction (CUDA cores), measured against the bf16 tensor peak for comparability",
+                                  1: "FP64 exact-order path", 2: "algorithmic flops; the split-bf16 scheme issues 3 tensor-core MMAs per algorithmic MMA, "
+                                  "so frac <= 1/3 by construction (hardware tensor utilisation = 3 x frac x Kpad/D)"}[args.svm_mode]},
             "stage_ms_per_step": {k: acc[k] / args.steps for k in ("bin", "integral", "mask", "features", "svm", "guard", "score")},
             "guard_windows_per_step": acc["guardw"] / args.steps,
             "wall_ms_per_step": 1e3 * wall_dev / args.steps,

@@ -61,7 +61,7 @@ class haf_timing(C.Structure):
 EXPORTS = ["haf_create", "haf_destroy", "haf_last_error", "haf_get_info", "haf_set_stream", "haf_set_profiling",
            "haf_get_timing", "haf_launch_count", "haf_search", "haf_search_batch", "haf_search_batch_packed",
            "haf_build_transform", "haf_best_key", "haf_debug_window_count", "haf_debug_windows", "haf_debug_features",
-           "haf_debug_decisions", "haf_debug_integral", "haf_debug_cell_indices", "haf_debug_text_roundtrip",
+           "haf_debug_decisions", "haf_debug_tensor_inputs", "haf_debug_integral", "haf_debug_cell_indices", "haf_debug_text_roundtrip",
            "haf_version"]
 
 _lib = None
@@ -104,6 +104,7 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     L.haf_debug_windows.argtypes = [vp, vp, ci]
     L.haf_debug_features.argtypes = [vp, vp, vp, ci]
     L.haf_debug_decisions.argtypes = [vp, vp, vp, vp, ci]
+    L.haf_debug_tensor_inputs.argtypes = [vp, vp, ci]
     L.haf_debug_integral.argtypes = [vp, vp, cs]
     L.haf_debug_cell_indices.argtypes = [vp, vp, cs, cs, C.POINTER(haf_request), ci, vp]
     L.haf_debug_text_roundtrip.argtypes = [vp, vp, ci, vp, vp, ci, vp]
@@ -258,6 +259,12 @@ class GraspSearch:
         s = np.zeros((max(W, 1), self.D), np.float64) if scaled else None
         self._check(self.L.haf_debug_features(self.h, _ptr(r), _ptr(s), W))
         return (r[:W] if raw else None), (s[:W] if scaled else None)
+
+    def debug_tensor_inputs(self):
+        W = self._check(self.L.haf_debug_window_count(self.h))
+        x = np.zeros((max(W, 1), self.D), np.float32)
+        self._check(self.L.haf_debug_tensor_inputs(self.h, _ptr(x), W))
+        return x[:W]
 
     def debug_decisions(self):
         W = self._check(self.L.haf_debug_window_count(self.h))

@@ -13,6 +13,7 @@
 #include "../../include/hafgpu.h"
 #include "haf_host.hpp"
 #include "kernels.cuh"
+#include "svm_tc.cuh"
 
 using namespace hafk;
 
@@ -74,16 +75,28 @@ struct haf_ctx {
     cudaEvent_t ev[10];               // [8] start, [9] end of a call
     bool ev_ok = false;
     std::vector<cudaEvent_t> ev_pool; // 8 per chunk when per-stage profiling is on (no host sync inside a call)
+    // host -> device staging of a batch overlapped with compute: pieces copied on copy_stream, one event per piece
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> copy_ev;
+    std::vector<int> copy_cloud_end;  // piece k covers clouds [copy_cloud_end[k-1], copy_cloud_end[k])
+    int copy_pieces = 0;              // > 0 while a plan is active
 
     // model-side constants
     int F = 0, D = 0, Dsv = 0, Kpad = 0, S = 0, Spad = 0, R = 0, G = 0;
     double lower = -1, upper = 1, gamma = 0, rho = 0;
     int label[2] = {0, 0}, gv[2] = {0, 0};
-    float guard_rel = 2e-5f;
+    float guard_rel = 4e-6f;
     DevBuf<FeatDev> d_feats;
     DevBuf<DimDev> d_dims;
     DevBuf<float> d_svT, d_svn, d_coef;
     DevBuf<double> d_sv64T, d_coef64;
+    // tensor-core path (HAF_SVM_TENSOR_GUARD): bf16 hi/lo operands, K-major rows of Krow elements
+    int Krow = 0, SpadT = 0;
+    float c_log2 = 0.0f;
+    DevBuf<__nv_bfloat16> d_SVh, d_SVl, d_Xh, d_Xl;
+    DevBuf<float2> d_svtab;
+    DevBuf<float> d_asum;
+    CUtensorMap tmSh, tmSl;
 
     // per-call state
     DevBuf<unsigned char> d_xyz;       // staging for host clouds
@@ -158,6 +171,47 @@ extern "C" const char* haf_last_error(const haf_ctx* ctx) { return ctx ? ctx->er
 static int create_fail(int code, const std::string& msg) {
     g_create_error = msg;
     return code;
+}
+
+// ---- tensor-core path helpers -------------------------------------------------------------------------------
+static uint16_t f2bf16(float f) {  // round to nearest even
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40u);
+    const uint32_t r = 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)((u + r) >> 16);
+}
+static float bf16f(uint16_t h) {
+    uint32_t u = (uint32_t)h << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+typedef CUresult (*haf_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static haf_encode_tiled_fn get_encode_tiled() {
+    static haf_encode_tiled_fn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (haf_encode_tiled_fn)p;
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+// 2D bf16 tensor [rows][krow] (K contiguous), box = 64 elements (128 B, one swizzle row) x box_rows, 128B swizzle
+static bool make_tensor_map(CUtensorMap* m, void* base, uint64_t krow, uint64_t rows, uint32_t box_rows) {
+    haf_encode_tiled_fn fn = get_encode_tiled();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {krow, rows};
+    cuuint64_t strides[1] = {krow * 2};
+    cuuint32_t box[2] = {(cuuint32_t)haftc::BK, box_rows};
+    cuuint32_t es[2] = {1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 extern "C" int haf_create(haf_ctx** out, const haf_config* cfg) {
@@ -244,6 +298,7 @@ extern "C" int haf_create(haf_ctx** out, const haf_config* cfg) {
             }
             d.cval = val;
         }
+        d.slope = d.drop ? 0.0 : (range.upper - range.lower) / d.den;
         dims[i - 1] = d;
         if (!d.drop) D_eff = i;
     }
@@ -264,7 +319,7 @@ extern "C" int haf_create(haf_ctx** out, const haf_config* cfg) {
     ctx->label[0] = model.label[0]; ctx->label[1] = model.label[1];
     ctx->gv[0] = hafhost::label_to_gridvalue(model.label[0]);
     ctx->gv[1] = hafhost::label_to_gridvalue(model.label[1]);
-    ctx->guard_rel = cfg->guard_rel > 0 ? cfg->guard_rel : 2e-5f;
+    ctx->guard_rel = cfg->guard_rel > 0 ? cfg->guard_rel : 4e-6f;   // measured FP32 error <= 2e-7 of sum|coef|K (tools/dec_error_probe.py)
     memset(&ctx->timing, 0, sizeof ctx->timing);
     if (ctx->gv[0] < -128 || ctx->gv[0] > 127 || ctx->gv[1] < -128 || ctx->gv[1] > 127) { delete ctx; return create_fail(HAF_ERR_UNSUPPORTED, "model labels do not fit the grasp grid"); }
 
@@ -327,6 +382,43 @@ extern "C" int haf_create(haf_ctx** out, const haf_config* cfg) {
     CREATE_TRY(cudaMemcpy(ctx->d_coef64.p, coef64.data(), Spad * sizeof(double), cudaMemcpyHostToDevice));
     CREATE_TRY(cudaFuncSetAttribute(svm_rbf_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SVM_STAGES * SVM_BK * (SVM_BM + SVM_BN) * 4));
     CREATE_TRY(cudaFuncSetAttribute(integral_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CREATE_TRY(cudaFuncSetAttribute(svm_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    if (cfg->svm_mode == HAF_SVM_TENSOR_GUARD) {
+        const int Krow = (int)round_up((size_t)Dsv, 16);
+        const int SpadT = (int)round_up((size_t)S, haftc::BN);
+        ctx->Krow = Krow; ctx->SpadT = SpadT;
+        ctx->c_log2 = (float)(-model.gamma * 1.4426950408889634);
+        if (cfg->guard_rel <= 0) ctx->guard_rel = 2e-5f;  // measured split-bf16 error <= 6e-7 of sum|coef|K
+        std::vector<uint16_t> svh((size_t)SpadT * Krow, 0), svl((size_t)SpadT * Krow, 0);
+        std::vector<float2> tab(SpadT);
+        for (int i = 0; i < SpadT; i++) { tab[i].x = 0.0f; tab[i].y = 0.0f; }
+        for (int i = 0; i < S; i++) {
+            float nrm = 0.0f;
+            for (size_t e = 0; e < model.sv[i].size(); e++) {
+                const int d = model.sv[i][e].first - 1;
+                const float fv = (float)model.sv[i][e].second;
+                const uint16_t h = f2bf16(fv);
+                const uint16_t l = f2bf16(fv - bf16f(h));
+                svh[(size_t)i * Krow + d] = h;
+                svl[(size_t)i * Krow + d] = l;
+                const float rep = bf16f(h) + bf16f(l);
+                nrm = fmaf(rep, rep, nrm);
+            }
+            tab[i].x = ctx->c_log2 * nrm;
+            tab[i].y = (float)model.coef[i];
+        }
+        bool okt = ctx->d_SVh.ensure(svh.size()) == 0 && ctx->d_SVl.ensure(svl.size()) == 0 && ctx->d_svtab.ensure(SpadT) == 0;
+        if (!okt) { haf_destroy(ctx); return create_fail(HAF_ERR_NOMEM, "out of device memory uploading the bf16 model"); }
+        CREATE_TRY(cudaMemcpy(ctx->d_SVh.p, svh.data(), svh.size() * 2, cudaMemcpyHostToDevice));
+        CREATE_TRY(cudaMemcpy(ctx->d_SVl.p, svl.data(), svl.size() * 2, cudaMemcpyHostToDevice));
+        CREATE_TRY(cudaMemcpy(ctx->d_svtab.p, tab.data(), SpadT * sizeof(float2), cudaMemcpyHostToDevice));
+        if (!make_tensor_map(&ctx->tmSh, ctx->d_SVh.p, Krow, SpadT, haftc::BN) || !make_tensor_map(&ctx->tmSl, ctx->d_SVl.p, Krow, SpadT, haftc::BN)) {
+            haf_destroy(ctx);
+            return create_fail(HAF_ERR_CUDA, "cuTensorMapEncodeTiled failed for the support-vector operands");
+        }
+        CREATE_TRY(cudaFuncSetAttribute(haftc::svm_rbf_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, haftc::SMEM_BYTES));
+        CREATE_TRY(cudaFuncSetAttribute(features_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 32 * (Krow + 2) * 2));
+    }
     for (int i = 0; i < 10; i++) CREATE_TRY(cudaEventCreate(&ctx->ev[i]));
     ctx->ev_ok = true;
 #undef CREATE_TRY
@@ -344,9 +436,12 @@ extern "C" void haf_destroy(haf_ctx* ctx) {
     ctx->d_integral.release(); ctx->d_rowscan.release(); ctx->d_mask.release(); ctx->d_labelgrid.release(); ctx->d_evals.release();
     ctx->d_unit_top.release(); ctx->d_unit_run.release(); ctx->d_unit_windows.release(); ctx->d_win.release(); ctx->d_X.release();
     ctx->d_xn.release(); ctx->d_dec.release(); ctx->d_guardflag.release(); ctx->d_guardlist.release(); ctx->d_kscratch.release();
+    ctx->d_SVh.release(); ctx->d_SVl.release(); ctx->d_Xh.release(); ctx->d_Xl.release(); ctx->d_svtab.release(); ctx->d_asum.release();
     ctx->d_counters.release(); ctx->h_stage.release(); ctx->h_results.release(); ctx->h_per_roll_top.release(); ctx->h_counters.release();
     if (ctx->ev_ok) for (int i = 0; i < 10; i++) cudaEventDestroy(ctx->ev[i]);
     for (size_t i = 0; i < ctx->ev_pool.size(); i++) cudaEventDestroy(ctx->ev_pool[i]);
+    for (size_t i = 0; i < ctx->copy_ev.size(); i++) cudaEventDestroy(ctx->copy_ev[i]);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     cudaGetLastError();
     delete ctx;
 }
@@ -478,6 +573,7 @@ static int run_jobs(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& jobs, fl
                 const long long w = jobs[je].wbound;
                 if (je > jb0 && (size_t)(wsum + w) * ctx->Kpad > x_budget_floats) break;
                 if (je > jb0 && (je - jb0) * R >= 16384) break;
+                if (je > jb0 && ctx->copy_pieces > 0 && (je - jb0) >= 64) break;  // small chunks so compute overlaps the staging copies
                 wsum += w;
                 je++;
             }
@@ -504,6 +600,7 @@ static int run_jobs(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& jobs, fl
     const bool smallG = (size_t)G * ld * sizeof(double) <= 200 * 1024;
     const float neg_gamma_log2e = (float)(-ctx->gamma * 1.4426950408889634);
 
+    int next_piece = 0;
     for (size_t ci = 0; ci < chunks.size(); ci++) {
         const int j0 = chunks[ci].first, j1 = chunks[ci].second;
         const int Uc = (j1 - j0) * R, ubase = j0 * R;
@@ -514,15 +611,23 @@ static int run_jobs(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& jobs, fl
         const int c0 = jobs[j0].cloud, c1 = jobs[j1 - 1].cloud + 1;  // clouds touched by this chunk
         ENSURE(ctx, ctx->d_keys, (size_t)Uc * GG); ENSURE(ctx, ctx->d_integral, (size_t)Uc * ld * ld);
         ENSURE(ctx, ctx->d_mask, (size_t)Uc * GG); ENSURE(ctx, ctx->d_labelgrid, (size_t)Uc * GG); ENSURE(ctx, ctx->d_evals, (size_t)Uc * GG);
-        ENSURE(ctx, ctx->d_win, ldx); ENSURE(ctx, ctx->d_X, (size_t)ctx->Kpad * ldx); ENSURE(ctx, ctx->d_xn, ldx);
+        const bool tc = ctx->cfg.svm_mode == HAF_SVM_TENSOR_GUARD;
+        ENSURE(ctx, ctx->d_win, ldx); ENSURE(ctx, ctx->d_xn, ldx);
+        if (tc) { ENSURE(ctx, ctx->d_Xh, ldx * ctx->Krow); ENSURE(ctx, ctx->d_Xl, ldx * ctx->Krow); ENSURE(ctx, ctx->d_asum, ldx); }
+        else if (ctx->cfg.svm_mode == HAF_SVM_FP32_GUARD) ENSURE(ctx, ctx->d_X, (size_t)ctx->Kpad * ldx);
         ENSURE(ctx, ctx->d_dec, ldx); ENSURE(ctx, ctx->d_guardflag, ldx); ENSURE(ctx, ctx->d_guardlist, ldx);
         if (!smallG) ENSURE(ctx, ctx->d_rowscan, (size_t)Uc * GG);
         const int exact_ctas = ctx->sm_count * 4;
-        ENSURE(ctx, ctx->d_kscratch, (size_t)exact_ctas * ctx->Spad);
+        ENSURE(ctx, ctx->d_kscratch, (size_t)exact_ctas * HAF_EXACT_WB * ctx->Spad);
         unsigned* cnt = ctx->d_counters.p;
         if (ci > 0) CUDA_TRY(ctx, cudaMemsetAsync(cnt, 0, 2 * 4, st));  // win_count, guard_count
         const UnitParams* units_c = ctx->d_units.p + ubase;
 
+        // staged host clouds: wait for the copy pieces that cover this chunk's clouds
+        while (next_piece < ctx->copy_pieces && (next_piece == 0 ? 0 : ctx->copy_cloud_end[next_piece - 1]) < c1) {
+            CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->copy_ev[next_piece], 0));
+            next_piece++;
+        }
         // 1. binning
         if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[ci * 8 + 0], st));
         {
@@ -558,7 +663,13 @@ static int run_jobs(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& jobs, fl
         // 4. features -> scaled SVM inputs
         if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[ci * 8 + 3], st));
         const unsigned wblocks32 = (unsigned)((Wcap + 31) / 32);
-        if (ctx->cfg.svm_mode != HAF_SVM_FP64_EXACT) {
+        if (tc) {
+            features_tc_kernel<<<wblocks32, 256, 2 * 32 * (ctx->Krow + 2) * 2, st>>>(ctx->d_integral.p, ctx->d_win.p, cnt + 0, G, ubase, ctx->d_feats.p,
+                                                                                   ctx->d_dims.p, ctx->D, ctx->Krow, ctx->lower, ctx->upper,
+                                                                                   ctx->cfg.emulate_text_roundtrip, ctx->d_Xh.p, ctx->d_Xl.p, ctx->d_xn.p,
+                                                                                   (int*)(cnt + 3));
+            LAUNCHED(ctx);
+        } else if (ctx->cfg.svm_mode != HAF_SVM_FP64_EXACT) {
             features_kernel<false><<<wblocks32, 256, 0, st>>>(ctx->d_integral.p, ctx->d_win.p, cnt + 0, G, ubase, ctx->d_feats.p, ctx->d_dims.p,
                                                               ctx->D, ctx->Kpad, ctx->lower, ctx->upper, ctx->cfg.emulate_text_roundtrip,
                                                               ctx->d_X.p, ldx, ctx->F, nullptr, nullptr, (int*)(cnt + 3));
@@ -570,19 +681,44 @@ static int run_jobs(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& jobs, fl
         if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[ci * 8 + 4], st));
         if (ctx->cfg.svm_mode == HAF_SVM_FP64_EXACT) {
             CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_guardflag.p, 0, ldx, st));
-            svm_exact_kernel<<<exact_ctas, 256, ctx->Dsv * sizeof(double), st>>>(nullptr, nullptr, cnt + 0, ctx->d_integral.p, ctx->d_win.p, G, ubase,
+            svm_exact_kernel<<<exact_ctas, 256, HAF_EXACT_WB * ctx->Dsv * sizeof(double), st>>>(nullptr, nullptr, cnt + 0, ctx->d_integral.p, ctx->d_win.p, G, ubase,
                                                                                    ctx->d_feats.p, ctx->d_dims.p, ctx->D, ctx->lower, ctx->upper,
                                                                                    ctx->cfg.emulate_text_roundtrip, ctx->d_sv64T.p, ctx->Spad, ctx->S, ctx->Dsv,
                                                                                    ctx->d_coef64.p, ctx->gamma, ctx->rho, ctx->d_kscratch.p, ctx->d_dec.p, (int*)(cnt + 3));
             LAUNCHED(ctx);
             if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[ci * 8 + 5], st));
+        } else if (tc) {
+            CUtensorMap tmXh, tmXl;
+            if (!make_tensor_map(&tmXh, ctx->d_Xh.p, ctx->Krow, ldx, haftc::BM) || !make_tensor_map(&tmXl, ctx->d_Xl.p, ctx->Krow, ldx, haftc::BM))
+                return ctx->fail(HAF_ERR_CUDA, "cuTensorMapEncodeTiled failed for the window operands");
+            CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_dec.p, 0, ldx * sizeof(double), st));
+            CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_asum.p, 0, ldx * sizeof(float), st));
+            const int n_ntiles = ctx->SpadT / haftc::BN;
+            const int mt_cap = (int)(ldx / haftc::BM);
+            int nsplit = 1;
+            if (mt_cap < ctx->sm_count) nsplit = std::min(n_ntiles, (2 * ctx->sm_count + mt_cap - 1) / mt_cap);
+            const int kblocks = (ctx->Krow + haftc::BK - 1) / haftc::BK;
+            const int last_slices = (ctx->Krow - haftc::BK * (kblocks - 1)) / 16;
+            const int grid = (int)std::min<long long>((long long)mt_cap * nsplit, ctx->sm_count);
+            haftc::svm_rbf_tc_kernel<<<grid, haftc::THREADS, haftc::SMEM_BYTES, st>>>(tmXh, tmXl, ctx->tmSh, ctx->tmSl, ctx->d_xn.p, ctx->d_svtab.p, ctx->c_log2,
+                                                                                      cnt + 0, n_ntiles, nsplit, kblocks, last_slices, ctx->d_dec.p, ctx->d_asum.p);
+            LAUNCHED(ctx);
+            haftc::svm_finalize_kernel<<<(unsigned)((Wcap + 255) / 256), 256, 0, st>>>(ctx->d_dec.p, ctx->d_asum.p, cnt + 0, ctx->rho, ctx->guard_rel,
+                                                                                       ctx->d_guardflag.p, ctx->d_guardlist.p, cnt + 1);
+            LAUNCHED(ctx);
+            if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[ci * 8 + 5], st));
+            svm_exact_kernel<<<exact_ctas, 256, HAF_EXACT_WB * ctx->Dsv * sizeof(double), st>>>(ctx->d_guardlist.p, cnt + 1, cnt + 0, ctx->d_integral.p, ctx->d_win.p, G, ubase,
+                                                                                   ctx->d_feats.p, ctx->d_dims.p, ctx->D, ctx->lower, ctx->upper,
+                                                                                   ctx->cfg.emulate_text_roundtrip, ctx->d_sv64T.p, ctx->Spad, ctx->S, ctx->Dsv,
+                                                                                   ctx->d_coef64.p, ctx->gamma, ctx->rho, ctx->d_kscratch.p, ctx->d_dec.p, (int*)(cnt + 3));
+            LAUNCHED(ctx);
         } else {
             svm_rbf_simt_kernel<<<(unsigned)(ldx / SVM_BM), 256, SVM_STAGES * SVM_BK * (SVM_BM + SVM_BN) * 4, st>>>(
                 ctx->d_X.p, ldx, ctx->d_svT.p, ctx->Spad, ctx->Kpad, ctx->d_xn.p, ctx->d_svn.p, ctx->d_coef.p, neg_gamma_log2e, ctx->rho,
                 ctx->guard_rel, cnt + 0, ctx->d_dec.p, ctx->d_guardflag.p, ctx->d_guardlist.p, cnt + 1);
             LAUNCHED(ctx);
             if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[ci * 8 + 5], st));
-            svm_exact_kernel<<<exact_ctas, 256, ctx->Dsv * sizeof(double), st>>>(ctx->d_guardlist.p, cnt + 1, cnt + 0, ctx->d_integral.p, ctx->d_win.p, G, ubase,
+            svm_exact_kernel<<<exact_ctas, 256, HAF_EXACT_WB * ctx->Dsv * sizeof(double), st>>>(ctx->d_guardlist.p, cnt + 1, cnt + 0, ctx->d_integral.p, ctx->d_win.p, G, ubase,
                                                                                    ctx->d_feats.p, ctx->d_dims.p, ctx->D, ctx->lower, ctx->upper,
                                                                                    ctx->cfg.emulate_text_roundtrip, ctx->d_sv64T.p, ctx->Spad, ctx->S, ctx->Dsv,
                                                                                    ctx->d_coef64.p, ctx->gamma, ctx->rho, ctx->d_kscratch.p, ctx->d_dec.p, (int*)(cnt + 3));
@@ -725,12 +861,43 @@ extern "C" int haf_search_batch_packed(haf_ctx* ctx, const float* xyz_all, const
     for (int c = 0; c < n_clouds; c++) if (cs.off[c + 1] < cs.off[c]) return ctx->fail(HAF_ERR_ARG, "point_offsets must be non-decreasing");
     const size_t total = (size_t)cs.off[n_clouds];
     if (total > 0 && !xyz_all) return ctx->fail(HAF_ERR_ARG, "xyz_all is null");
-    bool dev = false;
-    if (total > 0) { int rc = stage_points(ctx, xyz_all, total * 12, &dev); if (rc) return rc; }
+    bool dev = total > 0 && is_device_ptr(xyz_all);
+    ctx->copy_pieces = 0;
+    if (total > 0 && !dev) {
+        // stage in pieces on a second stream; run_jobs makes each chunk wait only for the pieces it needs, so the
+        // host->device copy of later clouds overlaps the kernels of earlier ones (pinned host memory copies truly async)
+        ENSURE(ctx, ctx->d_xyz, total * 12 + 16);
+        if (!ctx->copy_stream) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        cudaEvent_t start_ev;
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&start_ev, cudaEventDisableTiming));
+        CUDA_TRY(ctx, cudaEventRecord(start_ev, ctx->stream));            // copies start no earlier than prior work on the stream
+        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, start_ev, 0));
+        cudaEventDestroy(start_ev);
+        ctx->copy_cloud_end.clear();
+        int c = 0, k = 0;
+        while (c < n_clouds) {
+            int ce = c;
+            while (ce < n_clouds && (ce - c) < 32 && (size_t)(cs.off[ce] - cs.off[c]) * 12 < ((size_t)32 << 20)) ce++;
+            if (ce == c) ce = c + 1;
+            const size_t b0 = (size_t)cs.off[c] * 12, b1 = (size_t)cs.off[ce] * 12;
+            if ((int)ctx->copy_ev.size() <= k) {
+                cudaEvent_t e;
+                CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                ctx->copy_ev.push_back(e);
+            }
+            if (b1 > b0) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_xyz.p + b0, reinterpret_cast<const unsigned char*>(xyz_all) + b0, b1 - b0, cudaMemcpyHostToDevice, ctx->copy_stream));
+            CUDA_TRY(ctx, cudaEventRecord(ctx->copy_ev[k], ctx->copy_stream));
+            ctx->copy_cloud_end.push_back(ce);
+            c = ce;
+            k++;
+        }
+        ctx->copy_pieces = k;
+    }
     cs.d_xyz = total == 0 ? nullptr : (dev ? reinterpret_cast<const unsigned char*>(xyz_all) : ctx->d_xyz.p);
     std::vector<Job> jobs(n_clouds);
     for (int c = 0; c < n_clouds; c++) { jobs[c].cloud = c; jobs[c].rq = *req; }
     int rc = run_jobs(ctx, cs, jobs, nullptr, nullptr, nullptr, false);
+    ctx->copy_pieces = 0;
     if (rc) return rc;
     for (int c = 0; c < n_clouds; c++) fill_best(ctx, jobs[c], ctx->h_results.p[c], 0, 0, &best_per_cloud[c]);
     return HAF_OK;
@@ -782,6 +949,21 @@ extern "C" int haf_debug_features(haf_ctx* ctx, float* raw, double* scaled, int 
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     if (raw) { CUDA_TRY(ctx, cudaMemcpy(raw, d_raw, (size_t)W * ctx->F * sizeof(float), cudaMemcpyDeviceToHost)); cudaFree(d_raw); }
     if (scaled) { CUDA_TRY(ctx, cudaMemcpy(scaled, d_scaled, (size_t)W * ctx->D * sizeof(double), cudaMemcpyDeviceToHost)); cudaFree(d_scaled); }
+    return W;
+}
+
+// tensor-core mode only: the SVM inputs as the contraction sees them, x_hi + x_lo as float, [W][n_dims]
+extern "C" int haf_debug_tensor_inputs(haf_ctx* ctx, float* x, int cap) {
+    if (!ctx || !ctx->last_valid || !x) return HAF_ERR_ARG;
+    if (ctx->cfg.svm_mode != HAF_SVM_TENSOR_GUARD) return ctx->fail(HAF_ERR_ARG, "haf_debug_tensor_inputs: context is not in tensor mode");
+    const int W = std::min<int>(cap, (int)ctx->last_W);
+    if (W <= 0) return 0;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    std::vector<uint16_t> hh((size_t)W * ctx->Krow), ll((size_t)W * ctx->Krow);
+    CUDA_TRY(ctx, cudaMemcpy(hh.data(), ctx->d_Xh.p, hh.size() * 2, cudaMemcpyDeviceToHost));
+    CUDA_TRY(ctx, cudaMemcpy(ll.data(), ctx->d_Xl.p, ll.size() * 2, cudaMemcpyDeviceToHost));
+    for (int w = 0; w < W; w++)
+        for (int d = 0; d < ctx->D; d++) x[(size_t)w * ctx->D + d] = bf16f(hh[(size_t)w * ctx->Krow + d]) + bf16f(ll[(size_t)w * ctx->Krow + d]);
     return W;
 }
 

@@ -11,6 +11,7 @@
 //   X                    [Kpad][ldx]    f32 feature-major SVM inputs (dimension d of window w at X[d*ldx+w])
 //   svT                  [Kpad][Spad]   f32 feature-major support vectors;  sv64T [D][Spad] f64 for the exact path
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -40,8 +41,9 @@ struct DimDev {          // one SVM input dimension (libsvm index d+1), 48 bytes
     double cval;         // value when the dimension is constant (feat < 0)
     int feat;            // feature index feeding this dimension; -1 = constant cval
     int drop;            // 1: svm-scale skips it (single-valued attribute) -> 0
-    int pad[2];
+    double slope;        // (upper - lower) / den, used by the fast (non bit-exact) tier only
 };
+static_assert(sizeof(DimDev) == 48, "DimDev layout");
 
 // ---------------------------------------------------------------------------------------------------
 // ordered-key float max: key(a) > key(b)  <=>  a > b   (for non-NaN floats)
@@ -66,6 +68,8 @@ __global__ void fill_u32_kernel(unsigned* __restrict__ p, size_t n, unsigned v) 
 // each point is read ONCE and scattered into every unit grid of its cloud.   (server.cpp:487-520)
 // grid = (ceil(max_points / (blockDim*PPT)), n_clouds)
 // ---------------------------------------------------------------------------------------------------
+// Measured on B200 (profiles/README.md): keeping the points in registers with the unit loop outermost, and a
+// read-before-atomic filter, were both SLOWER than this point-outer / fire-and-forget RED form (3.3 / 3.7 vs 2.5 ms).
 #define HAF_BIN_MAXU 64
 template <int PPT>
 __global__ void __launch_bounds__(256) bin_maxz_kernel(const unsigned char* __restrict__ xyz, size_t stride_bytes,
@@ -385,6 +389,103 @@ __global__ void __launch_bounds__(256) features_kernel(const float* __restrict__
     if (uns) *unsupported_flag = 1;
 }
 
+// 10^k for |k| <= 40 (k >= 23 and negative k are rounded doubles: good to 1e-16, enough for the fast tier)
+__device__ __forceinline__ double pow10_table(int k) {
+    double p = 1.0;
+    const int n = k < 0 ? -k : k;
+    double b = 10.0;
+    int m = n;
+    while (m) { if (m & 1) p *= b; b *= b; m >>= 1; }
+    return k < 0 ? 1.0 / p : p;
+}
+
+// Tensor-core variant: per-dimension values split into two bf16 terms and written K-major ([window][Krow], what the
+// UMMA K-major operand / TMA box wants).  The 32-window x Krow tile is staged in shared memory so the global writes
+// are row-contiguous; the squared norm of the (hi + lo) representation is reduced on the way.
+//
+// FAST TIER.  The values written here are rounded to 16 significant bits (bf16 hi + lo) anyway and every window whose
+// decision value lands inside the guard band is re-evaluated by svm_exact_kernel with the bit-exact emulation, so this
+// tier reproduces the text round trips only to ~1e-7: the "%.4g" rounding is decided in double (a * 10^p, rint: exact
+// ties stay exact, a mis-decided near-tie needs |frac - 0.5| < 1e-12), the division back and svm-scale's affine map
+// use one multiplication / FMA, and the 6-digit "%g" rounding (<= 5e-7 relative, below the 2^-17 operand precision)
+// is skipped.  Raw feature values are the same bit-exact floats as everywhere else.
+__global__ void __launch_bounds__(256) features_tc_kernel(const float* __restrict__ integral, const int2* __restrict__ win,
+                                                          const unsigned* __restrict__ win_count, int G, int unit_base,
+                                                          const FeatDev* __restrict__ feats, const DimDev* __restrict__ dims,
+                                                          int D, int Krow, double lower, double upper, int emulate_text,
+                                                          __nv_bfloat16* __restrict__ Xh, __nv_bfloat16* __restrict__ Xl,
+                                                          float* __restrict__ xn, int* __restrict__ unsupported_flag) {
+    extern __shared__ __nv_bfloat16 s_tile[];  // hi[32][Krow+2] then lo[32][Krow+2]
+    const unsigned W = *win_count;
+    if (blockIdx.x * 32 >= W) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned w = blockIdx.x * 32 + lane;
+    const bool valid = w < W;
+    const int ld = G + 1, rs = Krow + 2;
+    __nv_bfloat16* s_hi = s_tile;
+    __nv_bfloat16* s_lo = s_tile + 32 * rs;
+    const float* P = integral;
+    if (valid) {
+        const int2 uc = win[w];
+        const int row = uc.y / G, col = uc.y - row * G;
+        P = integral + (size_t)(uc.x - unit_base) * ld * ld + (size_t)(row - 7) * ld + (col - 7);
+    }
+    __shared__ double s_pw[81];  // 10^(i-40)
+    if (threadIdx.x < 81) s_pw[threadIdx.x] = pow10_table(threadIdx.x - 40);
+    __syncthreads();
+    for (int d = warp; d < Krow; d += 8) {
+        double x = 0.0;
+        if (d < D && valid) {
+            const DimDev dd = dims[d];
+            if (dd.feat < 0) {
+                x = dd.cval;
+            } else if (!dd.drop) {
+                const float raw = feature_value(P, feats[dd.feat]);
+                double v = (double)raw;
+                if (emulate_text && raw != 0.0f) {
+                    const double a = fabs(v);
+                    const int e2 = (int)((__float_as_uint(raw) >> 23) & 0xFFu) - 127;  // denormals read as 2^-127: E is fixed below
+                    int E = (e2 * 1233 - 3) >> 12;                                    // <= floor(log10 a), at most 2 too low
+                    E = max(-37, min(37, E));
+                    E += (a >= s_pw[40 + E + 1]) ? 1 : 0;
+                    E += (a >= s_pw[40 + E + 1]) ? 1 : 0;
+                    const double r = rint(a * s_pw[40 + 3 - E]);                      // 4 significant digits
+                    const double vv = r * s_pw[40 + E - 3];
+                    v = raw < 0.0f ? -vv : vv;
+                }
+                x = fma(v - dd.fmin, dd.slope, lower);                                // svm-scale.c:344-346
+            }
+        }
+        const float xf = (float)x;
+        const __nv_bfloat16 hi = __float2bfloat16_rn(xf);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(xf - __bfloat162float(hi));
+        s_hi[lane * rs + d] = hi;
+        s_lo[lane * rs + d] = lo;
+    }
+    __syncthreads();
+    for (int wi = warp; wi < 32; wi += 8) {
+        const unsigned ww = blockIdx.x * 32 + wi;
+        if (ww >= W) break;
+        const uint32_t* sh = reinterpret_cast<const uint32_t*>(s_hi + wi * rs);
+        const uint32_t* sl = reinterpret_cast<const uint32_t*>(s_lo + wi * rs);
+        uint32_t* gh = reinterpret_cast<uint32_t*>(Xh + (size_t)ww * Krow);
+        uint32_t* gl = reinterpret_cast<uint32_t*>(Xl + (size_t)ww * Krow);
+        float s = 0.0f;
+        for (int e = lane; e < Krow / 2; e += 32) {
+            const uint32_t h2 = sh[e], l2 = sl[e];
+            gh[e] = h2;
+            gl[e] = l2;
+            const float v0 = __uint_as_float(h2 << 16) + __uint_as_float(l2 << 16);
+            const float v1 = __uint_as_float(h2 & 0xFFFF0000u) + __uint_as_float(l2 & 0xFFFF0000u);
+            s = fmaf(v0, v0, s);
+            s = fmaf(v1, v1, s);
+        }
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) xn[ww] = s;
+    }
+}
+
 // squared norm of every window's SVM input (FP32)
 __global__ void xnorm_kernel(const float* __restrict__ X, size_t ldx, int Kpad, const unsigned* __restrict__ win_count,
                              float* __restrict__ xn) {
@@ -551,6 +652,7 @@ __global__ void __launch_bounds__(256, 2) svm_rbf_simt_kernel(const float* __res
 // exact), then ONE thread sums coef_i * K_i in file order and subtracts rho (svm.cpp:2500-2514).
 // list == NULL: all windows (HAF_SVM_FP64_EXACT).  grid-stride over the list; kscratch: [gridDim.x][Spad].
 // ---------------------------------------------------------------------------------------------------
+#define HAF_EXACT_WB 8   // windows evaluated together by one CTA: every support-vector element is loaded once per 8 windows
 __global__ void __launch_bounds__(256) svm_exact_kernel(const int* __restrict__ list, const unsigned* __restrict__ list_count,
                                                         const unsigned* __restrict__ win_count,
                                                         const float* __restrict__ integral, const int2* __restrict__ win,
@@ -560,19 +662,22 @@ __global__ void __launch_bounds__(256) svm_exact_kernel(const int* __restrict__ 
                                                         int Dsv, const double* __restrict__ coef64, double gamma, double rho,
                                                         double* __restrict__ kscratch, double* __restrict__ dec,
                                                         int* __restrict__ unsupported_flag) {
-    extern __shared__ double xs[];  // [Dsv]
+    extern __shared__ double xs[];  // [HAF_EXACT_WB][Dsv]
     const unsigned n = list ? *list_count : *win_count;
     const int ld = G + 1;
-    double* kv = kscratch + (size_t)blockIdx.x * Spad;
-    for (unsigned e = blockIdx.x; e < n; e += gridDim.x) {
-        const int w = list ? list[e] : (int)e;
-        const int2 uc = win[w];
-        const int row = uc.y / G, col = uc.y - row * G;
-        const float* P = integral + (size_t)(uc.x - unit_base) * ld * ld + (size_t)(row - 7) * ld + (col - 7);
+    double* kv = kscratch + (size_t)blockIdx.x * HAF_EXACT_WB * Spad;  // [WB][Spad]
+    for (unsigned e0 = blockIdx.x * HAF_EXACT_WB; e0 < n; e0 += gridDim.x * HAF_EXACT_WB) {
+        const int nb = min((unsigned)HAF_EXACT_WB, n - e0);
         __syncthreads();
-        for (int d = threadIdx.x; d < Dsv; d += blockDim.x) {
+        // x of every window of the block, bit-exact emulation of both text round trips
+        for (int t = threadIdx.x; t < HAF_EXACT_WB * Dsv; t += blockDim.x) {
+            const int b = t / Dsv, d = t - b * Dsv;
             double x = 0.0;
-            if (d < D) {
+            if (b < nb && d < D) {
+                const int w = list ? list[e0 + b] : (int)(e0 + b);
+                const int2 uc = win[w];
+                const int row = uc.y / G, col = uc.y - row * G;
+                const float* P = integral + (size_t)(uc.x - unit_base) * ld * ld + (size_t)(row - 7) * ld + (col - 7);
                 const DimDev dd = dims[d];
                 if (dd.feat < 0) x = dd.cval;
                 else {
@@ -589,22 +694,32 @@ __global__ void __launch_bounds__(256) svm_exact_kernel(const int* __restrict__ 
                     if (u4 || u6) *unsupported_flag = 1;
                 }
             }
-            xs[d] = x;
+            xs[t] = x;
         }
         __syncthreads();
+        // K_i for the block: d loop sequential and un-fused per (window, SV); sv element shared by the 8 windows
         for (int i = threadIdx.x; i < S; i += blockDim.x) {
-            double sum = 0.0;
+            double sum[HAF_EXACT_WB];
+#pragma unroll
+            for (int b = 0; b < HAF_EXACT_WB; b++) sum[b] = 0.0;
             for (int d = 0; d < Dsv; d++) {
-                const double diff = __dsub_rn(xs[d], sv64T[(size_t)d * Spad + i]);
-                sum = __dadd_rn(sum, __dmul_rn(diff, diff));
+                const double sv = sv64T[(size_t)d * Spad + i];
+#pragma unroll
+                for (int b = 0; b < HAF_EXACT_WB; b++) {
+                    const double diff = __dsub_rn(xs[b * Dsv + d], sv);
+                    sum[b] = __dadd_rn(sum[b], __dmul_rn(diff, diff));
+                }
             }
-            kv[i] = exp(__dmul_rn(-gamma, sum));
+#pragma unroll
+            for (int b = 0; b < HAF_EXACT_WB; b++) kv[(size_t)b * Spad + i] = exp(__dmul_rn(-gamma, sum[b]));
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
+        // decision value: sequential sum in file order, one thread per window (svm.cpp:2500-2514)
+        if (threadIdx.x < nb) {
+            const double* k = kv + (size_t)threadIdx.x * Spad;
             double sum = 0.0;
-            for (int i = 0; i < S; i++) sum = __dadd_rn(sum, __dmul_rn(coef64[i], kv[i]));
-            dec[w] = __dsub_rn(sum, rho);
+            for (int i = 0; i < S; i++) sum = __dadd_rn(sum, __dmul_rn(coef64[i], k[i]));
+            dec[list ? list[e0 + threadIdx.x] : (int)(e0 + threadIdx.x)] = __dsub_rn(sum, rho);
         }
     }
 }

@@ -1,0 +1,258 @@
+// svm_tc.cuh -- the RBF decision contraction on 5th-generation tensor cores (tcgen05 + TMEM + TMA), sm_100a only.
+//
+//   dec[w] = sum_n coef[n] * exp2(c * (||x_w||^2 + ||sv_n||^2 - 2 x_w . sv_n)) - rho,     c = -gamma * log2(e)
+//
+// x and sv are split into two bf16 terms (x = x_hi + x_lo, 16 significant bits together); the contraction is
+// three tensor-core products accumulated in FP32 in TMEM:  x_hi.sv_hi + x_hi.sv_lo + x_lo.sv_hi   (the dropped
+// x_lo.sv_lo term is ~2^-18 relative).  The error of the resulting decision value is measured in the tests and is
+// far inside the guard band; windows inside the band are re-evaluated in FP64 by svm_exact_kernel, so labels equal
+// the reference's (svm.cpp:2459-2533).
+//
+// Kernel structure (one persistent CTA per SM, 192 threads, warp specialised):
+//   warp 0   TMA producer : cp.async.bulk.tensor 2D loads of the four operand tiles of a k-block into a
+//                           2-stage shared-memory ring (128B-swizzled, K-major): X_hi, X_lo [128 x 64] and
+//                           SV_hi, SV_lo [256 x 64] bf16 = 96 KB per stage, mbarrier complete_tx.
+//   warp 1   MMA issuer   : one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=256, K=16),
+//                           3 products x 4 k-slices per stage, into one of two 128x256 FP32 accumulators in TMEM
+//                           (512 columns = all of TMEM); tcgen05.commit releases the smem stage / publishes the
+//                           accumulator.
+//   warps 2-5 epilogue    : tcgen05.ld 32x32b (thread = window row, registers = 32 SV columns), fused
+//                           exp2 / coef / row-sum, FP64 accumulation across SV tiles; overlaps the next tile's MMAs.
+// Work item = (window tile of 128, split of the SV tiles); small problems split the SV range over CTAs.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace haftc {
+
+constexpr int BM = 128;      // windows per tile (UMMA M)
+constexpr int BN = 256;      // support vectors per tile (UMMA N)
+constexpr int BK = 64;       // bf16 elements per k-block = 128 bytes = one swizzle row
+constexpr int STAGES = 2;
+constexpr int A_TILE_BYTES = BM * BK * 2;   // 16 KB
+constexpr int B_TILE_BYTES = BN * BK * 2;   // 32 KB
+constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;  // 96 KB
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int THREADS = 192;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "LAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra LAB_WAIT;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(bar), "r"(parity), "r"(0x989680u)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_dst),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T ; kind::f16 covers bf16 inputs with FP32 accumulation
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// K-major operand tile, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO = 1 (unused)
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: D = F32 (bit 4), A = B = BF16 (bits 7, 10), K-major both, N >> 3 at bit 17, M >> 4 at bit 24
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+#define HAFTC_LD32(taddr, r)                                                                                          \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                            \
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                             \
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"             \
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),     \
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), \
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), \
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]) \
+                 : "r"(taddr))
+
+// svtab[n] = { c * ||sv_n||^2 , coef_n }  (padding SVs: coef = 0).  dec_acc / asum_acc must be zeroed before launch.
+__global__ void __launch_bounds__(THREADS, 1)
+svm_rbf_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl,
+                  const __grid_constant__ CUtensorMap tmSh, const __grid_constant__ CUtensorMap tmSl,
+                  const float* __restrict__ xn, const float2* __restrict__ svtab, float c, const unsigned* __restrict__ win_count,
+                  int n_ntiles, int nsplit, int kblocks, int last_slices, double* __restrict__ dec_acc, float* __restrict__ asum_acc) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // 128B swizzle needs 1024-byte aligned tiles
+    const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+    const uint32_t bar_full = bar_base;                 // [STAGES]
+    const uint32_t bar_empty = bar_base + 8 * STAGES;   // [STAGES]
+    const uint32_t bar_tfull = bar_base + 16 * STAGES;  // [2]
+    const uint32_t bar_tempty = bar_tfull + 16;         // [2]
+    const uint32_t tmem_slot = bar_tempty + 16;         // u32
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    const unsigned W = *win_count;
+    const int n_mtiles = (int)((W + BM - 1) / BM);
+    const int items = n_mtiles * nsplit;
+    const int nt_per = (n_ntiles + nsplit - 1) / nsplit;
+
+    if (warp == 0) {
+        if (lane == 0) {  // ===== TMA producer =====
+            uint32_t it = 0;
+            for (int item = blockIdx.x; item < items; item += gridDim.x) {
+                const int mt = item / nsplit, sp = item - mt * nsplit;
+                const int nt0 = sp * nt_per, nt1 = min(n_ntiles, nt0 + nt_per);
+                for (int nt = nt0; nt < nt1; nt++)
+                    for (int kb = 0; kb < kblocks; kb++, it++) {
+                        const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
+                        mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+                        const uint32_t st = smem_base + s * STAGE_BYTES;
+                        mbar_expect_tx(bar_full + 8 * s, STAGE_BYTES);
+                        tma_load_2d(st, &tmXh, kb * BK, mt * BM, bar_full + 8 * s);
+                        tma_load_2d(st + A_TILE_BYTES, &tmXl, kb * BK, mt * BM, bar_full + 8 * s);
+                        tma_load_2d(st + 2 * A_TILE_BYTES, &tmSh, kb * BK, nt * BN, bar_full + 8 * s);
+                        tma_load_2d(st + 2 * A_TILE_BYTES + B_TILE_BYTES, &tmSl, kb * BK, nt * BN, bar_full + 8 * s);
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {  // ===== MMA issuer =====
+            uint32_t it = 0, acc_it = 0;
+            for (int item = blockIdx.x; item < items; item += gridDim.x) {
+                const int mt = item / nsplit, sp = item - mt * nsplit;
+                const int nt0 = sp * nt_per, nt1 = min(n_ntiles, nt0 + nt_per);
+                for (int nt = nt0; nt < nt1; nt++, acc_it++) {
+                    const uint32_t a = acc_it & 1u, aph = (acc_it >> 1) & 1u;
+                    mbar_wait(bar_tempty + 8 * a, aph ^ 1u);  // epilogue has drained this accumulator
+                    tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + a * BN;
+                    for (int kb = 0; kb < kblocks; kb++, it++) {
+                        const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
+                        mbar_wait(bar_full + 8 * s, ph);
+                        tc_fence_after();
+                        const uint32_t st = smem_base + s * STAGE_BYTES;
+                        const uint64_t d_ah = make_desc_sw128(st), d_al = make_desc_sw128(st + A_TILE_BYTES);
+                        const uint64_t d_bh = make_desc_sw128(st + 2 * A_TILE_BYTES), d_bl = make_desc_sw128(st + 2 * A_TILE_BYTES + B_TILE_BYTES);
+                        const int slices = (kb == kblocks - 1) ? last_slices : (BK / 16);
+                        for (int k = 0; k < slices; k++) {
+                            const uint64_t adv = (uint64_t)(k * 2);  // 16 bf16 = 32 bytes = 2 x 16-byte units
+                            tc_mma(tmem_d, d_ah + adv, d_bh + adv, IDESC, (kb | k) ? 1u : 0u);
+                            tc_mma(tmem_d, d_ah + adv, d_bl + adv, IDESC, 1u);
+                            tc_mma(tmem_d, d_al + adv, d_bh + adv, IDESC, 1u);
+                        }
+                        tc_commit(bar_empty + 8 * s);  // smem stage free once these MMAs have read it
+                    }
+                    tc_commit(bar_tfull + 8 * a);      // accumulator complete
+                }
+            }
+        }
+    } else {  // ===== epilogue warps 2..5 =====
+        const int q = warp & 3;  // TMEM lane quarter this warp may access
+        uint32_t acc_it = 0;
+        const float c2 = -2.0f * c;
+        for (int item = blockIdx.x; item < items; item += gridDim.x) {
+            const int mt = item / nsplit, sp = item - mt * nsplit;
+            const int nt0 = sp * nt_per, nt1 = min(n_ntiles, nt0 + nt_per);
+            const unsigned m = (unsigned)mt * BM + q * 32 + lane;
+            const float u = (m < W) ? c * xn[m] : 0.0f;
+            double dsum = 0.0;
+            float asum = 0.0f;
+            for (int nt = nt0; nt < nt1; nt++, acc_it++) {
+                const uint32_t a = acc_it & 1u, aph = (acc_it >> 1) & 1u;
+                mbar_wait(bar_tfull + 8 * a, aph);
+                tc_fence_after();
+                float ps = 0.0f, pa = 0.0f;
+                const float2* tab = svtab + (size_t)nt * BN;
+#pragma unroll 1
+                for (int ch = 0; ch < BN / 32; ch++) {
+                    uint32_t r[32];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * BN + ch * 32;
+                    HAFTC_LD32(taddr, r);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        const float2 t = __ldg(tab + ch * 32 + j);
+                        float arg = fmaf(__uint_as_float(r[j]), c2, u + t.x);  // c * (xn + svn - 2 dot)
+                        arg = fminf(arg, 0.0f);                                // d^2 >= 0
+                        const float e = ex2_approx(arg);
+                        ps = fmaf(t.y, e, ps);
+                        pa = fmaf(fabsf(t.y), e, pa);
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(bar_tempty + 8 * a);
+                dsum += (double)ps;
+                asum += pa;
+            }
+            if (m < W && nt1 > nt0) {
+                atomicAdd(dec_acc + m, dsum);
+                atomicAdd(asum_acc + m, asum);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// dec = sum - rho, guard test (same rule as the SIMT kernel)
+__global__ void svm_finalize_kernel(double* __restrict__ dec, const float* __restrict__ asum, const unsigned* __restrict__ win_count,
+                                    double rho, float guard_rel, unsigned char* __restrict__ guard_flag, int* __restrict__ guard_list,
+                                    unsigned* __restrict__ guard_count) {
+    const unsigned W = *win_count;
+    const unsigned m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= W) return;
+    const double dv = dec[m] - rho;
+    dec[m] = dv;
+    const bool g = fabs(dv) <= (double)guard_rel * ((double)asum[m] + fabs(rho));
+    guard_flag[m] = g ? 1 : 0;
+    if (g) guard_list[atomicAdd(guard_count, 1u)] = (int)m;
+}
+
+}  // namespace haftc

@@ -148,6 +148,8 @@ int haf_debug_window_count(const haf_ctx* ctx);
 int haf_debug_windows(haf_ctx* ctx, int* win_unit_cell, int cap_windows);
 /* raw features [W][F] float (calc_featurevalue), scaled SVM inputs [W][D] double (after both text round trips) */
 int haf_debug_features(haf_ctx* ctx, float* raw, double* scaled, int cap_windows);
+/* tensor mode: SVM inputs as the tensor-core contraction sees them (bf16 hi + lo, as float) [W][D] */
+int haf_debug_tensor_inputs(haf_ctx* ctx, float* x, int cap_windows);
 /* decision values, libsvm labels and guard flags [W] of the last search */
 int haf_debug_decisions(haf_ctx* ctx, double* dec, int* labels, unsigned char* guard, int cap_windows);
 /* integral images [n_units][G+1][G+1] float of the last search */

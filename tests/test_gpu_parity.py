@@ -201,6 +201,49 @@ def test_fp64_exact_mode(hg, oracle_lib, trained_model, clouds):
         p.close()
 
 
+@pytest.mark.parametrize("name", ["pcd2", "pcd7", "table1", "plastic_mug2"])
+def test_tensor_core_mode(hg, oracle_lib, trained_model, clouds, name):
+    """HAF_SVM_TENSOR_GUARD: tcgen05 split-bf16 contraction + FP64 guard band; everything before and after the
+    decision values is shared with the SIMT mode, labels / evals / best grasp must equal the oracle's."""
+    p = Pair(hg, oracle_lib, trained_model, svm_mode=hg.HAF_SVM_TENSOR_GUARD)
+    try:
+        check_search(p, clouds[name], hg, oracle_lib, trained_model)
+    finally:
+        p.close()
+
+
+def test_tensor_mode_fast_tier_inputs_track_the_exact_scaled_values(hg, oracle_lib, trained_model, clouds):
+    """The tensor path's operands come from a fast tier (double-precision "%.4g" decision, no "%g" step, 16-bit split).
+    They must sit within 16-bit rounding of the exact scaled values; only a mis-decided decimal near-tie may differ by
+    one 4th-digit step, and none is expected on this data."""
+    gpu = hg.GraspSearch(FEATURES, RANGE, trained_model, svm_mode=hg.HAF_SVM_TENSOR_GUARD)
+    try:
+        gpu.search(clouds["table1"])
+        x = gpu.debug_tensor_inputs().astype(np.float64)
+        _, scaled = gpu.debug_features(raw=False)       # bit-exact emulation tier (checked against the oracle elsewhere)
+        err = np.abs(x - scaled)
+        tol = 2.0 ** -16 * np.abs(scaled) + 1e-6          # hi+lo carries >= 16 bits; "%g" skipped: <= 5e-7 relative
+        assert (err <= tol).mean() == 1.0, (err.max(), (err > tol).sum())
+    finally:
+        gpu.close()
+
+
+def test_tensor_core_mode_synth_models_and_batch(hg, oracle_lib, tmp_models):
+    from haf_grasping_b200 import synth
+    for nsv in (256, 300):   # 300: support-vector count not a multiple of the 256-wide tile
+        model = tmp_models(nsv)
+        p = Pair(hg, oracle_lib, model, svm_mode=hg.HAF_SVM_TENSOR_GUARD)
+        try:
+            cl = [synth.synth_cloud(4321 + i, 15000 + 211 * i) for i in range(5)]
+            best = p.gpu.search_batch(cl)
+            for i, c in enumerate(cl):
+                ob = p.orc.search(c, oracle_lib.make_request(), full=False)["best"]
+                assert best[i].astuple() == ob.astuple()
+            check_search(p, cl[0], hg, oracle_lib, model)
+        finally:
+            p.close()
+
+
 def test_guard_band_catches_near_zero_decisions(hg, oracle_lib, tmp_models, clouds):
     """rho chosen so that many decision values sit next to 0: labels must still equal the oracle's."""
     model = tmp_models(256, rho=-0.2972253)  # a decision value of pcd2 / roll 0 with the synth model is -0.2972253033...
