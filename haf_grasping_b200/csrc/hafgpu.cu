@@ -95,11 +95,13 @@ struct haf_ctx {
     float c_log2 = 0.0f;
     DevBuf<__nv_bfloat16> d_SVh, d_SVl, d_Xh, d_Xl;
     DevBuf<float2> d_svtab;
+    DevBuf<DimFeat> d_dimfeat;
     DevBuf<float> d_asum;
     CUtensorMap tmSh, tmSl;
 
     // per-call state
     DevBuf<unsigned char> d_xyz;       // staging for host clouds
+    DevBuf<unsigned char> d_params;    // per-call parameter block (units, jobs, point offsets, unit ranges)
     DevBuf<long long> d_ptoff;
     DevBuf<int> d_cloud_ubegin;
     DevBuf<UnitParams> d_units;
@@ -388,7 +390,7 @@ extern "C" int haf_create(haf_ctx** out, const haf_config* cfg) {
         const int SpadT = (int)round_up((size_t)S, haftc::BN);
         ctx->Krow = Krow; ctx->SpadT = SpadT;
         ctx->c_log2 = (float)(-model.gamma * 1.4426950408889634);
-        if (cfg->guard_rel <= 0) ctx->guard_rel = 2e-5f;  // measured split-bf16 error <= 6e-7 of sum|coef|K
+        if (cfg->guard_rel <= 0) ctx->guard_rel = 1e-5f;  // measured split-bf16 + fast-tier error <= 6e-7 of sum|coef|K (tools/dec_error_probe.py)
         std::vector<uint16_t> svh((size_t)SpadT * Krow, 0), svl((size_t)SpadT * Krow, 0);
         std::vector<float2> tab(SpadT);
         for (int i = 0; i < SpadT; i++) { tab[i].x = 0.0f; tab[i].y = 0.0f; }
@@ -416,8 +418,26 @@ extern "C" int haf_create(haf_ctx** out, const haf_config* cfg) {
             haf_destroy(ctx);
             return create_fail(HAF_ERR_CUDA, "cuTensorMapEncodeTiled failed for the support-vector operands");
         }
+        std::vector<DimFeat> joined(D);
+        for (int d = 0; d < D; d++) {
+            DimFeat j;
+            memset(&j, 0, sizeof j);
+            const DimDev& dd = dims[d];
+            if (dd.feat >= 0) {
+                memcpy(j.off, fd[dd.feat].off, sizeof j.off);
+                memcpy(j.w, fd[dd.feat].w, sizeof j.w);
+                j.flags = fd[dd.feat].flags;
+            } else {
+                j.flags = 0x200;
+            }
+            if (dd.drop) j.flags |= 0x400;
+            j.fmin = dd.fmin; j.slope = dd.slope; j.cval = dd.cval;
+            joined[d] = j;
+        }
+        if (ctx->d_dimfeat.ensure(D) != 0) { haf_destroy(ctx); return create_fail(HAF_ERR_NOMEM, "out of device memory uploading the joined feature table"); }
+        CREATE_TRY(cudaMemcpy(ctx->d_dimfeat.p, joined.data(), D * sizeof(DimFeat), cudaMemcpyHostToDevice));
         CREATE_TRY(cudaFuncSetAttribute(haftc::svm_rbf_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, haftc::SMEM_BYTES));
-        CREATE_TRY(cudaFuncSetAttribute(features_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 32 * (Krow + 2) * 2));
+        CREATE_TRY(cudaFuncSetAttribute(features_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 32 * (Krow / 2 + 2) * 2 + HAF_FT_ROWS * (G + 1) * 4));
     }
     for (int i = 0; i < 10; i++) CREATE_TRY(cudaEventCreate(&ctx->ev[i]));
     ctx->ev_ok = true;
@@ -436,8 +456,8 @@ extern "C" void haf_destroy(haf_ctx* ctx) {
     ctx->d_integral.release(); ctx->d_rowscan.release(); ctx->d_mask.release(); ctx->d_labelgrid.release(); ctx->d_evals.release();
     ctx->d_unit_top.release(); ctx->d_unit_run.release(); ctx->d_unit_windows.release(); ctx->d_win.release(); ctx->d_X.release();
     ctx->d_xn.release(); ctx->d_dec.release(); ctx->d_guardflag.release(); ctx->d_guardlist.release(); ctx->d_kscratch.release();
-    ctx->d_SVh.release(); ctx->d_SVl.release(); ctx->d_Xh.release(); ctx->d_Xl.release(); ctx->d_svtab.release(); ctx->d_asum.release();
-    ctx->d_counters.release(); ctx->h_stage.release(); ctx->h_results.release(); ctx->h_per_roll_top.release(); ctx->h_counters.release();
+    ctx->d_SVh.release(); ctx->d_SVl.release(); ctx->d_Xh.release(); ctx->d_Xl.release(); ctx->d_svtab.release(); ctx->d_asum.release(); ctx->d_dimfeat.release();
+    ctx->d_params.release(); ctx->d_counters.release(); ctx->h_stage.release(); ctx->h_results.release(); ctx->h_per_roll_top.release(); ctx->h_counters.release();
     if (ctx->ev_ok) for (int i = 0; i < 10; i++) cudaEventDestroy(ctx->ev[i]);
     for (size_t i = 0; i < ctx->ev_pool.size(); i++) cudaEventDestroy(ctx->ev_pool[i]);
     for (size_t i = 0; i < ctx->copy_ev.size(); i++) cudaEventDestroy(ctx->copy_ev[i]);
@@ -511,7 +531,7 @@ static int run_jobs(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& jobs, fl
     const size_t bytes_units = (size_t)U * sizeof(UnitParams), bytes_jobs = (size_t)n_jobs * sizeof(JobParams);
     const size_t bytes_off = (size_t)(n_clouds + 1) * sizeof(long long), bytes_ub = (size_t)(n_clouds + 1) * sizeof(int);
     const size_t o_units = 0, o_jobs = round_up(o_units + bytes_units, 256), o_off = round_up(o_jobs + bytes_jobs, 256), o_ub = round_up(o_off + bytes_off, 256);
-    ENSURE(ctx, ctx->h_stage, o_ub + bytes_ub);
+    ENSURE(ctx, ctx->h_stage, o_ub + bytes_ub + 16);
     UnitParams* hu = reinterpret_cast<UnitParams*>(ctx->h_stage.p + o_units);
     JobParams* hj = reinterpret_cast<JobParams*>(ctx->h_stage.p + o_jobs);
     long long* hoff = reinterpret_cast<long long*>(ctx->h_stage.p + o_off);
@@ -548,14 +568,22 @@ static int run_jobs(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& jobs, fl
             up.job = j; up.roll = roll;
         }
     }
-    ENSURE(ctx, ctx->d_units, U); ENSURE(ctx, ctx->d_jobs, n_jobs); ENSURE(ctx, ctx->d_ptoff, n_clouds + 1);
-    ENSURE(ctx, ctx->d_cloud_ubegin, n_clouds + 1); ENSURE(ctx, ctx->d_results, n_jobs); ENSURE(ctx, ctx->d_per_roll_top, (size_t)U * 3);
+    ENSURE(ctx, ctx->d_params, o_ub + bytes_ub + 16); ENSURE(ctx, ctx->d_results, n_jobs); ENSURE(ctx, ctx->d_per_roll_top, (size_t)U * 3);
     ENSURE(ctx, ctx->d_unit_top, U); ENSURE(ctx, ctx->d_unit_run, U); ENSURE(ctx, ctx->d_unit_windows, U);
     ENSURE(ctx, ctx->h_results, n_jobs); ENSURE(ctx, ctx->h_per_roll_top, (size_t)U * 3);
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_units.p, hu, bytes_units, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_jobs.p, hj, bytes_jobs, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_ptoff.p, hoff, bytes_off, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_cloud_ubegin.p, hub, bytes_ub, cudaMemcpyHostToDevice, st));
+    // The parameter block goes up with a tiny kernel that reads the pinned staging buffer directly (UVA), NOT with a
+    // copy-engine memcpy: the H2D engine is a FIFO, and behind a large staging copy of clouds (this call's, or any other
+    // stream's) a small memcpy would stall every kernel of the call until that copy has finished.
+    {
+        const size_t n16 = (o_ub + bytes_ub + 15) / 16;
+        copy_params_kernel<<<(unsigned)std::min<size_t>((n16 + 255) / 256, 1024), 256, 0, st>>>(reinterpret_cast<const uint4*>(ctx->h_stage.p),
+                                                                                              reinterpret_cast<uint4*>(ctx->d_params.p), n16);
+        LAUNCHED(ctx);
+    }
+    UnitParams* const d_units = reinterpret_cast<UnitParams*>(ctx->d_params.p + o_units);
+    JobParams* const d_jobs = reinterpret_cast<JobParams*>(ctx->d_params.p + o_jobs);
+    long long* const d_ptoff = reinterpret_cast<long long*>(ctx->d_params.p + o_off);
+    int* const d_cloud_ubegin = reinterpret_cast<int*>(ctx->d_params.p + o_ub);
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_unit_top.p, 0, (size_t)U * 8, st));
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_unit_run.p, 0, (size_t)U * 8, st));
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_unit_windows.p, 0, (size_t)U * 4, st));
@@ -621,7 +649,7 @@ static int run_jobs(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& jobs, fl
         ENSURE(ctx, ctx->d_kscratch, (size_t)exact_ctas * HAF_EXACT_WB * ctx->Spad);
         unsigned* cnt = ctx->d_counters.p;
         if (ci > 0) CUDA_TRY(ctx, cudaMemsetAsync(cnt, 0, 2 * 4, st));  // win_count, guard_count
-        const UnitParams* units_c = ctx->d_units.p + ubase;
+        const UnitParams* units_c = d_units + ubase;
 
         // staged host clouds: wait for the copy pieces that cover this chunk's clouds
         while (next_piece < ctx->copy_pieces && (next_piece == 0 ? 0 : ctx->copy_cloud_end[next_piece - 1]) < c1) {
@@ -638,7 +666,7 @@ static int run_jobs(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& jobs, fl
             dim3 grid((unsigned)((max_points + 256 * PPT - 1) / (256 * PPT)), (unsigned)(c1 - c0));
             if (grid.x > 0) {
                 // cloud_unit_begin is relative to unit 0 of the call: shift the key base so unit u lands at keys[u - ubase]
-                bin_maxz_kernel<PPT><<<grid, 256, 0, st>>>(cs.d_xyz, cs.stride, ctx->d_ptoff.p + c0, ctx->d_cloud_ubegin.p + c0, ctx->d_units.p,
+                bin_maxz_kernel<PPT><<<grid, 256, 0, st>>>(cs.d_xyz, cs.stride, d_ptoff + c0, d_cloud_ubegin + c0, d_units,
                                                            ctx->d_keys.p - (size_t)ubase * GG, G, r, nullptr,
                                                            reinterpret_cast<unsigned long long*>(cnt + 4));
                 LAUNCHED(ctx);
@@ -664,10 +692,9 @@ static int run_jobs(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& jobs, fl
         if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[ci * 8 + 3], st));
         const unsigned wblocks32 = (unsigned)((Wcap + 31) / 32);
         if (tc) {
-            features_tc_kernel<<<wblocks32, 256, 2 * 32 * (ctx->Krow + 2) * 2, st>>>(ctx->d_integral.p, ctx->d_win.p, cnt + 0, G, ubase, ctx->d_feats.p,
-                                                                                   ctx->d_dims.p, ctx->D, ctx->Krow, ctx->lower, ctx->upper,
-                                                                                   ctx->cfg.emulate_text_roundtrip, ctx->d_Xh.p, ctx->d_Xl.p, ctx->d_xn.p,
-                                                                                   (int*)(cnt + 3));
+            features_tc_kernel<<<wblocks32, 256, 2 * 32 * (ctx->Krow / 2 + 2) * 2 + HAF_FT_ROWS * (G + 1) * 4, st>>>(
+                ctx->d_integral.p, ctx->d_win.p, cnt + 0, G, ubase, ctx->d_dimfeat.p, ctx->D, ctx->Krow, ctx->lower,
+                ctx->cfg.emulate_text_roundtrip, ctx->d_Xh.p, ctx->d_Xl.p, ctx->d_xn.p);
             LAUNCHED(ctx);
         } else if (ctx->cfg.svm_mode != HAF_SVM_FP64_EXACT) {
             features_kernel<false><<<wblocks32, 256, 0, st>>>(ctx->d_integral.p, ctx->d_win.p, cnt + 0, G, ubase, ctx->d_feats.p, ctx->d_dims.p,
@@ -753,7 +780,7 @@ static int run_jobs(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& jobs, fl
         }
     }
     // 7. cross-roll reduction per job, results to pinned host memory
-    reduce_rolls_kernel<<<(n_jobs + 127) / 128, 128, 0, st>>>(ctx->d_unit_top.p, ctx->d_unit_run.p, ctx->d_unit_windows.p, ctx->d_jobs.p, n_jobs, R, G,
+    reduce_rolls_kernel<<<(n_jobs + 127) / 128, 128, 0, st>>>(ctx->d_unit_top.p, ctx->d_unit_run.p, ctx->d_unit_windows.p, d_jobs, n_jobs, R, G,
                                                              ctx->d_per_roll_top.p, ctx->d_results.p);
     LAUNCHED(ctx);
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_results.p, ctx->d_results.p, (size_t)n_jobs * sizeof(JobResult), cudaMemcpyDeviceToHost, st));

@@ -30,18 +30,19 @@ struct UnitParams {      // one (job, roll): 128 bytes
 };
 static_assert(sizeof(UnitParams) == 128, "UnitParams layout");
 
-struct FeatDev {         // one feature of data/Features.txt, 64 bytes
+struct __align__(16) FeatDev {  // one feature of data/Features.txt, 64 bytes
     int off[12];         // 3 effective regions x 4 corner offsets into the integral image (row stride G+1):
                          //   [4r+0] (x2+1,y2+1)  [4r+1] (x1,y2+1)  [4r+2] (x2+1,y1)  [4r+3] (x1,y1)
     float w[3];
     int flags;           // bit r: region r active; bit 8: SHAF feature (index >= nr_features_without_shaf)
 };
-struct DimDev {          // one SVM input dimension (libsvm index d+1), 48 bytes
-    double fmin, fmax, den;  // den = fmax - fmin
-    double cval;         // value when the dimension is constant (feat < 0)
+struct __align__(16) DimDev {   // one SVM input dimension (libsvm index d+1), 48 bytes; the fast tier reads the first 32
+    double fmin;         // svm-scale feature_min
+    double slope;        // (upper - lower) / den, used by the fast (non bit-exact) tier only
     int feat;            // feature index feeding this dimension; -1 = constant cval
     int drop;            // 1: svm-scale skips it (single-valued attribute) -> 0
-    double slope;        // (upper - lower) / den, used by the fast (non bit-exact) tier only
+    double cval;         // value when the dimension is constant (feat < 0)
+    double fmax, den;    // den = fmax - fmin
 };
 static_assert(sizeof(DimDev) == 48, "DimDev layout");
 
@@ -399,8 +400,69 @@ __device__ __forceinline__ double pow10_table(int k) {
     return k < 0 ? 1.0 / p : p;
 }
 
+#define HAF_FT_ROWS 24  // integral-image rows a features_tc CTA can stage in shared memory
+
+// Joined per-dimension record of the tensor-path feature kernel (built once per context): the feature's corner
+// offsets / weights / flags AND the dimension's scaling constants in one 96-byte record, so one dependent-load-free
+// group of six 128-bit loads feeds a value (the dims -> feats indirection was the top stall of the first version).
+struct __align__(16) DimFeat {
+    int off[12];
+    float w[3];
+    int flags;       // bit r: region r active; bit 8: SHAF; bit 9: constant dimension (value = cval); bit 10: dropped (value 0)
+    double fmin;
+    double slope;
+    double cval;
+    double pad;
+};
+static_assert(sizeof(DimFeat) == 96, "DimFeat layout");
+
+// one value of the fast tier; I = integral image rows (shared or global), idx0 = index of the window's patch origin
+template <typename PtrT>
+__device__ __forceinline__ float fast_tier_value(PtrT I, int idx0, const DimFeat* __restrict__ table, int d, double lower,
+                                                 int emulate_text, const double* s_pw) {
+    const uint4* tp = reinterpret_cast<const uint4*>(table + d);
+    const uint4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2), t3 = __ldg(tp + 3), t4 = __ldg(tp + 4), t5 = __ldg(tp + 5);
+    const int flags = (int)t3.w;
+    if (flags & 0x600) return (flags & 0x400) ? 0.0f : (float)__hiloint2double((int)t5.y, (int)t5.x);
+    const int off[12] = {(int)t0.x, (int)t0.y, (int)t0.z, (int)t0.w, (int)t1.x, (int)t1.y, (int)t1.z, (int)t1.w,
+                         (int)t2.x, (int)t2.y, (int)t2.z, (int)t2.w};
+    const float wgt[3] = {__uint_as_float(t3.x), __uint_as_float(t3.y), __uint_as_float(t3.z)};
+    float rr[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        rr[r] = 0.0f;
+        if (flags & (1 << r)) {  // ((P[x2+1][y2+1] - P[x1][y2+1]) - P[x2+1][y1]) + P[x1][y1]   (II2FV.cpp:161-162)
+            const float rect = __fadd_rn(__fsub_rn(__fsub_rn(I[idx0 + off[4 * r]], I[idx0 + off[4 * r + 1]]), I[idx0 + off[4 * r + 2]]), I[idx0 + off[4 * r + 3]]);
+            rr[r] = __fmul_rn(wgt[r], rect);
+        }
+    }
+    float raw;
+    if (!(flags & 0x100)) {  // HAF: adding the +0.0 of a skipped region is an exact identity (the sum is never -0.0)
+        raw = __fadd_rn(__fadd_rn(__fadd_rn(0.0f, rr[0]), rr[1]), rr[2]);
+    } else if (rr[1] > rr[0] && rr[1] > rr[2]) {  // SHAF (II2FV.cpp:187-191)
+        const float a = __fsub_rn(rr[1], rr[0]), b = __fsub_rn(rr[1], rr[2]);
+        raw = (b < a) ? b : a;
+    } else {
+        raw = -1.0f;
+    }
+    double v = (double)raw;
+    if (emulate_text && raw != 0.0f) {
+        const double a = fabs(v);
+        const int e2 = (int)((__float_as_uint(raw) >> 23) & 0xFFu) - 127;  // denormals read as 2^-127: E is fixed below
+        int E = (e2 * 1233 - 3) >> 12;                                    // <= floor(log10 a), at most 2 too low
+        E = max(-37, min(37, E));
+        E += (a >= s_pw[40 + E + 1]) ? 1 : 0;
+        E += (a >= s_pw[40 + E + 1]) ? 1 : 0;
+        const double r = rint(a * s_pw[40 + 3 - E]);                      // 4 significant digits
+        const double vv = r * s_pw[40 + E - 3];
+        v = raw < 0.0f ? -vv : vv;
+    }
+    const double fmin = __hiloint2double((int)t4.y, (int)t4.x), slope = __hiloint2double((int)t4.w, (int)t4.z);
+    return (float)fma(v - fmin, slope, lower);                            // svm-scale.c:344-346
+}
+
 // Tensor-core variant: per-dimension values split into two bf16 terms and written K-major ([window][Krow], what the
-// UMMA K-major operand / TMA box wants).  The 32-window x Krow tile is staged in shared memory so the global writes
+// UMMA K-major operand / TMA box wants).  The 32-window x Krow/2 tile is staged in shared memory so the global writes
 // are row-contiguous; the squared norm of the (hi + lo) representation is reduced on the way.
 //
 // FAST TIER.  The values written here are rounded to 16 significant bits (bf16 hi + lo) anyway and every window whose
@@ -409,80 +471,107 @@ __device__ __forceinline__ double pow10_table(int k) {
 // ties stay exact, a mis-decided near-tie needs |frac - 0.5| < 1e-12), the division back and svm-scale's affine map
 // use one multiplication / FMA, and the 6-digit "%g" rounding (<= 5e-7 relative, below the 2^-17 operand precision)
 // is skipped.  Raw feature values are the same bit-exact floats as everywhere else.
-__global__ void __launch_bounds__(256) features_tc_kernel(const float* __restrict__ integral, const int2* __restrict__ win,
-                                                          const unsigned* __restrict__ win_count, int G, int unit_base,
-                                                          const FeatDev* __restrict__ feats, const DimDev* __restrict__ dims,
-                                                          int D, int Krow, double lower, double upper, int emulate_text,
-                                                          __nv_bfloat16* __restrict__ Xh, __nv_bfloat16* __restrict__ Xl,
-                                                          float* __restrict__ xn, int* __restrict__ unsupported_flag) {
-    extern __shared__ __nv_bfloat16 s_tile[];  // hi[32][Krow+2] then lo[32][Krow+2]
+// (Tables in __constant__ memory were tried and were 1.8x SLOWER: 36 KB of tables thrash the constant cache.)
+__global__ void __launch_bounds__(256, 6) features_tc_kernel(const float* __restrict__ integral, const int2* __restrict__ win,
+                                                             const unsigned* __restrict__ win_count, int G, int unit_base,
+                                                             const DimFeat* __restrict__ table, int D, int Krow, double lower,
+                                                             int emulate_text, __nv_bfloat16* __restrict__ Xh,
+                                                             __nv_bfloat16* __restrict__ Xl, float* __restrict__ xn) {
+    // The K range is processed in two passes so the staging tile is half as large (22 KB): more CTAs per SM -- the
+    // kernel is latency-bound on the table -> integral-image load chain.
+    extern __shared__ __nv_bfloat16 s_tile[];  // hi[32][KP+2] then lo[32][KP+2], KP = Krow / 2, then float s_int[ROWS][ld]
     const unsigned W = *win_count;
     if (blockIdx.x * 32 >= W) return;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // provably warp-uniform for the compiler
     const unsigned w = blockIdx.x * 32 + lane;
     const bool valid = w < W;
-    const int ld = G + 1, rs = Krow + 2;
+    const int ld = G + 1, KP = Krow >> 1, rs = KP + 2;
     __nv_bfloat16* s_hi = s_tile;
     __nv_bfloat16* s_lo = s_tile + 32 * rs;
-    const float* P = integral;
+    // The 32 windows of a CTA are consecutive entries of the window list: normally 2-3 adjacent grid rows of one unit.
+    // Their integral-image rows (row-7 .. row+7) are staged in shared memory (32-bit addressing, conflict-free for
+    // consecutive windows).  CTAs whose windows straddle units or too many rows read global memory instead.
+    float* s_int = reinterpret_cast<float*>(s_tile + 2 * 32 * rs);  // [HAF_FT_ROWS][ld]
+    __shared__ int s_box[3];  // unit, first row, rows (0 = no staging)
+    int2 uc = make_int2(0, 0);
+    int row = 7, col = 7;
     if (valid) {
-        const int2 uc = win[w];
-        const int row = uc.y / G, col = uc.y - row * G;
-        P = integral + (size_t)(uc.x - unit_base) * ld * ld + (size_t)(row - 7) * ld + (col - 7);
+        uc = win[w];
+        row = uc.y / G;
+        col = uc.y - row * G;
+    }
+    if (threadIdx.x < 32) {
+        const int u0 = __shfl_sync(0xffffffffu, uc.x, 0);  // lane 0 is always valid
+        const bool same = __all_sync(0xffffffffu, !valid || uc.x == u0);
+        int rmin = valid ? row : 0x7fffffff, rmax = valid ? row : -1;
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            rmin = min(rmin, __shfl_xor_sync(0xffffffffu, rmin, o));
+            rmax = max(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+        }
+        if (lane == 0) {
+            const int nr = rmax - rmin + 15;
+            s_box[0] = u0;
+            s_box[1] = rmin - 7;
+            s_box[2] = (same && nr <= HAF_FT_ROWS) ? nr : 0;
+        }
     }
     __shared__ double s_pw[81];  // 10^(i-40)
     if (threadIdx.x < 81) s_pw[threadIdx.x] = pow10_table(threadIdx.x - 40);
     __syncthreads();
-    for (int d = warp; d < Krow; d += 8) {
-        double x = 0.0;
-        if (d < D && valid) {
-            const DimDev dd = dims[d];
-            if (dd.feat < 0) {
-                x = dd.cval;
-            } else if (!dd.drop) {
-                const float raw = feature_value(P, feats[dd.feat]);
-                double v = (double)raw;
-                if (emulate_text && raw != 0.0f) {
-                    const double a = fabs(v);
-                    const int e2 = (int)((__float_as_uint(raw) >> 23) & 0xFFu) - 127;  // denormals read as 2^-127: E is fixed below
-                    int E = (e2 * 1233 - 3) >> 12;                                    // <= floor(log10 a), at most 2 too low
-                    E = max(-37, min(37, E));
-                    E += (a >= s_pw[40 + E + 1]) ? 1 : 0;
-                    E += (a >= s_pw[40 + E + 1]) ? 1 : 0;
-                    const double r = rint(a * s_pw[40 + 3 - E]);                      // 4 significant digits
-                    const double vv = r * s_pw[40 + E - 3];
-                    v = raw < 0.0f ? -vv : vv;
-                }
-                x = fma(v - dd.fmin, dd.slope, lower);                                // svm-scale.c:344-346
-            }
-        }
-        const float xf = (float)x;
-        const __nv_bfloat16 hi = __float2bfloat16_rn(xf);
-        const __nv_bfloat16 lo = __float2bfloat16_rn(xf - __bfloat162float(hi));
-        s_hi[lane * rs + d] = hi;
-        s_lo[lane * rs + d] = lo;
+    const int nrows = s_box[2];
+    const float* gI = integral + (size_t)(uc.x - unit_base) * ld * ld;
+    int idx0 = (row - 7) * ld + (col - 7);
+    if (nrows > 0) {
+        const float* src = integral + (size_t)(s_box[0] - unit_base) * ld * ld + (size_t)s_box[1] * ld;
+        for (int t = threadIdx.x; t < nrows * ld; t += blockDim.x) s_int[t] = src[t];
+        idx0 -= s_box[1] * ld;
     }
-    __syncthreads();
-    for (int wi = warp; wi < 32; wi += 8) {
-        const unsigned ww = blockIdx.x * 32 + wi;
-        if (ww >= W) break;
-        const uint32_t* sh = reinterpret_cast<const uint32_t*>(s_hi + wi * rs);
-        const uint32_t* sl = reinterpret_cast<const uint32_t*>(s_lo + wi * rs);
-        uint32_t* gh = reinterpret_cast<uint32_t*>(Xh + (size_t)ww * Krow);
-        uint32_t* gl = reinterpret_cast<uint32_t*>(Xl + (size_t)ww * Krow);
-        float s = 0.0f;
-        for (int e = lane; e < Krow / 2; e += 32) {
-            const uint32_t h2 = sh[e], l2 = sl[e];
-            gh[e] = h2;
-            gl[e] = l2;
-            const float v0 = __uint_as_float(h2 << 16) + __uint_as_float(l2 << 16);
-            const float v1 = __uint_as_float(h2 & 0xFFFF0000u) + __uint_as_float(l2 & 0xFFFF0000u);
-            s = fmaf(v0, v0, s);
-            s = fmaf(v1, v1, s);
+    float nrm[4] = {0.0f, 0.0f, 0.0f, 0.0f};  // squared-norm partials of the 4 windows this warp writes out
+    for (int pass = 0; pass < 2; pass++) {
+        const int d0 = pass * KP;
+        __syncthreads();
+        for (int dl = warp; dl < KP; dl += 8) {
+            const int d = d0 + dl;
+            float xf = 0.0f;
+            if (d < D && valid) xf = (nrows > 0) ? fast_tier_value(s_int, idx0, table, d, lower, emulate_text, s_pw)
+                                                 : fast_tier_value(gI, idx0, table, d, lower, emulate_text, s_pw);
+            const __nv_bfloat16 hi = __float2bfloat16_rn(xf);
+            const __nv_bfloat16 lo = __float2bfloat16_rn(xf - __bfloat162float(hi));
+            s_hi[lane * rs + dl] = hi;
+            s_lo[lane * rs + dl] = lo;
         }
+        __syncthreads();
 #pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) xn[ww] = s;
+        for (int k = 0; k < 4; k++) {
+            const int wi = warp + 8 * k;
+            const unsigned ww = blockIdx.x * 32 + wi;
+            if (ww >= W) break;
+            const uint32_t* sh = reinterpret_cast<const uint32_t*>(s_hi + wi * rs);
+            const uint32_t* sl = reinterpret_cast<const uint32_t*>(s_lo + wi * rs);
+            uint32_t* gh = reinterpret_cast<uint32_t*>(Xh + (size_t)ww * Krow + d0);
+            uint32_t* gl = reinterpret_cast<uint32_t*>(Xl + (size_t)ww * Krow + d0);
+            float sq = nrm[k];
+            for (int e = lane; e < KP / 2; e += 32) {
+                const uint32_t h2 = sh[e], l2 = sl[e];
+                gh[e] = h2;
+                gl[e] = l2;
+                const float v0 = __uint_as_float(h2 << 16) + __uint_as_float(l2 << 16);
+                const float v1 = __uint_as_float(h2 & 0xFFFF0000u) + __uint_as_float(l2 & 0xFFFF0000u);
+                sq = fmaf(v0, v0, sq);
+                sq = fmaf(v1, v1, sq);
+            }
+            nrm[k] = sq;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const unsigned ww = blockIdx.x * 32 + warp + 8 * k;
+        float sq = nrm[k];
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        if (lane == 0 && ww < W) xn[ww] = sq;
     }
 }
 
@@ -866,6 +955,13 @@ __global__ void reduce_rolls_kernel(const unsigned long long* __restrict__ unit_
     JobResult r;
     r.row = brow; r.col = bcol; r.roll = broll; r.topval = best; r.rolls_done = done; r.n_windows = nwin; r.pad0 = r.pad1 = 0;
     results[j] = r;
+}
+
+// parameter block upload: src is pinned HOST memory read over PCIe through its UVA address (see run_jobs)
+__global__ void copy_params_kernel(const uint4* __restrict__ src_host, uint4* __restrict__ dst, size_t n16) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n16; i += stride) dst[i] = src_host[i];
 }
 
 // counters: [0] windows of this chunk, [1] guard windows of this chunk -> running totals in [8], [9]
