@@ -33,7 +33,7 @@ class haf_config(C.Structure):
 class haf_request(C.Structure):
     _fields_ = [("center", C.c_double * 3), ("area_len_x", C.c_float), ("area_len_y", C.c_float),
                 ("approach", C.c_double * 3), ("gripper_opening_width", C.c_int), ("return_only_best", C.c_int),
-                ("graspval_top", C.c_int), ("roll_limit", C.c_int)]
+                ("graspval_top", C.c_int), ("roll_limit", C.c_int), ("roll_begin", C.c_int), ("reserved", C.c_int)]
 
 
 class haf_best(C.Structure):
@@ -114,7 +114,7 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
 
 
 def make_request(center=(0.0, 0.0, 0.0), area=(32.0, 44.0), approach=(0.0, 0.0, 1.0), width=1, return_only_best=0,
-                 graspval_top=119, roll_limit=0) -> haf_request:
+                 graspval_top=119, roll_limit=0, roll_begin=0) -> haf_request:
     """GraspInput defaults of the reference client (client.cpp:79-118; area = size + 14, client.cpp:183-184)."""
     rq = haf_request()
     rq.center[:] = center
@@ -124,6 +124,7 @@ def make_request(center=(0.0, 0.0, 0.0), area=(32.0, 44.0), approach=(0.0, 0.0, 
     rq.return_only_best = return_only_best
     rq.graspval_top = graspval_top
     rq.roll_limit = roll_limit
+    rq.roll_begin = roll_begin
     return rq
 
 

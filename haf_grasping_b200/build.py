@@ -51,5 +51,25 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+CLI = os.path.join(LIB_DIR, "haf_cli")
+HOST_DIR = os.path.join(CSRC, "host")
+
+
+def build_cli(force: bool = False) -> str:
+    """haf_cli: the ROS-free C++ host (csrc/host) on top of the C ABI."""
+    build_lib()
+    srcs = [os.path.join(HOST_DIR, f) for f in ("haf_cli.cpp", "calc_grasppoints_b200.hpp", "pcd_io.hpp")]
+    if not force and os.path.exists(CLI) and all(os.path.getmtime(s) <= os.path.getmtime(CLI) for s in srcs + [LIB]):
+        return CLI
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    cmd = [cxx, "-O2", "-std=c++17", "-ffp-contract=off", "-o", CLI, srcs[0], "-L" + LIB_DIR, "-lhafgpu", "-Wl,-rpath,$ORIGIN"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("g++ failed building haf_cli")
+    return CLI
+
+
 if __name__ == "__main__":
     print(build_lib(force=True, verbose="-v" in sys.argv))
+    print(build_cli(force=True))

@@ -57,7 +57,8 @@ struct PinBuf {
 struct Job {  // one (cloud, request)
     int cloud;
     haf_request rq;
-    int n_rolls_active;
+    int roll_begin;
+    int n_rolls_active;   // rolls [roll_begin, n_rolls_active) are evaluated
     long long wbound;  // upper bound on valid windows of this job (all active rolls)
 };
 
@@ -552,9 +553,10 @@ static int run_jobs(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& jobs, fl
         Job& jb = jobs[j];
         const int ax = (int)jb.rq.area_len_x, ay = (int)jb.rq.area_len_y;  // server.cpp:266-267
         jb.n_rolls_active = (jb.rq.roll_limit > 0) ? std::min(R, jb.rq.roll_limit) : R;
-        jb.wbound = window_bound(G, jb.rq) * jb.n_rolls_active;
+        jb.roll_begin = std::max(0, std::min(jb.rq.roll_begin, jb.n_rolls_active));
+        jb.wbound = window_bound(G, jb.rq) * (jb.n_rolls_active - jb.roll_begin);
         hj[j].return_only_best = jb.rq.return_only_best; hj[j].graspval_top = jb.rq.graspval_top;
-        hj[j].n_rolls_active = jb.n_rolls_active; hj[j].pad = 0;
+        hj[j].n_rolls_active = jb.n_rolls_active; hj[j].roll_begin = jb.roll_begin;
         for (int roll = 0; roll < R; roll++) {
             UnitParams& up = hu[j * R + roll];
             memset(&up, 0, sizeof up);
@@ -564,7 +566,7 @@ static int run_jobs(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& jobs, fl
             const hafhost::MaskConsts mc = hafhost::mask_consts(G, roll, ctx->cfg.roll_step_deg, ax, ay);
             up.sa = mc.sa; up.ca = mc.ca; up.cx1 = mc.cx1; up.cy1 = mc.cy1; up.cx2 = mc.cx2; up.cy2 = mc.cy2;
             up.cx3 = mc.cx3; up.cy3 = mc.cy3; up.cx4 = mc.cx4; up.cy4 = mc.cy4;
-            up.cloud = (roll < jb.n_rolls_active) ? jb.cloud : -1;
+            up.cloud = (roll >= jb.roll_begin && roll < jb.n_rolls_active) ? jb.cloud : -1;
             up.job = j; up.roll = roll;
         }
     }
@@ -770,9 +772,9 @@ static int run_jobs(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& jobs, fl
         // optional per-roll outputs (single chunk): active units only
         if (out_evals || out_mask || out_heights) {
             for (int j = j0; j < j1; j++) {
-                const int na = jobs[j].n_rolls_active;
+                const int na = jobs[j].n_rolls_active - jobs[j].roll_begin;
                 if (na <= 0) continue;
-                const size_t uo = (size_t)(j * R - ubase) * GG, go = (size_t)j * R * GG, nel = (size_t)na * GG;
+                const size_t uo = (size_t)(j * R + jobs[j].roll_begin - ubase) * GG, go = ((size_t)j * R + jobs[j].roll_begin) * GG, nel = (size_t)na * GG;
                 if (out_evals) CUDA_TRY(ctx, cudaMemcpyAsync(out_evals + go, ctx->d_evals.p + uo, nel * 4, cudaMemcpyDefault, st));
                 if (out_mask) CUDA_TRY(ctx, cudaMemcpyAsync(out_mask + go, ctx->d_mask.p + uo, nel, cudaMemcpyDefault, st));
                 if (out_heights) CUDA_TRY(ctx, cudaMemcpyAsync(out_heights + go, ctx->d_keys.p + uo, nel * 4, cudaMemcpyDefault, st));
@@ -803,7 +805,7 @@ static int run_jobs(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& jobs, fl
     t.ms_bin = ms_stage[0]; t.ms_integral = ms_stage[1]; t.ms_mask = ms_stage[2]; t.ms_features = ms_stage[3];
     t.ms_svm = ms_stage[4]; t.ms_guard = ms_stage[5]; t.ms_score = ms_stage[6];
     t.n_points = cs.off[n_clouds] - cs.off[0]; t.n_units = 0;
-    for (int j = 0; j < n_jobs; j++) t.n_units += jobs[j].n_rolls_active;
+    for (int j = 0; j < n_jobs; j++) t.n_units += jobs[j].n_rolls_active - jobs[j].roll_begin;
     t.n_windows = total_windows; t.n_guard = total_guard; t.launches = ctx->launches - launches0;
     t.n_chunks = (long long)chunks.size();
     if (keep_debug_state) { ctx->last_W = (unsigned)total_windows; ctx->last_valid = true; }
@@ -859,7 +861,7 @@ extern "C" int haf_search(haf_ctx* ctx, const float* xyz, size_t n_points, size_
         if (best_per_request) fill_best(ctx, jobs[a], r, a, ctx->timing.n_guard, &best_per_request[a]);
         if (r.topval > wtop) { wtop = r.topval; win = a; }
         if (per_roll_top)
-            for (int roll = 0; roll < jobs[a].n_rolls_active; roll++)
+            for (int roll = jobs[a].roll_begin; roll < jobs[a].n_rolls_active; roll++)
                 memcpy(per_roll_top + ((size_t)a * R + roll) * 3, ctx->h_per_roll_top.p + ((size_t)a * R + roll) * 3, 3 * sizeof(int));
     }
     if (win < 0) {

@@ -919,7 +919,7 @@ struct JobResult {  // per job (cloud x request)
     int rolls_done, n_windows, pad0, pad1;
 };
 struct JobParams {
-    int return_only_best, graspval_top, n_rolls_active, pad;
+    int return_only_best, graspval_top, n_rolls_active, roll_begin;  // rolls [roll_begin, n_rolls_active) are evaluated
 };
 // per-unit tops (after the tie rule) + a15 cross-roll reduction with the loop_control rules
 // (server.cpp:362-365 early exit, :953-960 strict >).  One thread per job.
@@ -934,7 +934,7 @@ __global__ void reduce_rolls_kernel(const unsigned long long* __restrict__ unit_
     for (int roll = 0; roll < R; roll++) {
         const int u = j * R + roll;
         int row = -1, col = -1, val = -1000;
-        if (roll < jp.n_rolls_active) {
+        if (roll >= jp.roll_begin && roll < jp.n_rolls_active) {
             val = (int)(unsigned)(unit_top[u] >> 32) - (1 << 20);
             const unsigned long long rk = unit_run[u];
             row = 0xFFFF - (int)((rk >> 16) & 0xFFFFu);
@@ -944,7 +944,7 @@ __global__ void reduce_rolls_kernel(const unsigned long long* __restrict__ unit_
         per_roll_top[(j * R + roll) * 3 + 1] = col;
         per_roll_top[(j * R + roll) * 3 + 2] = val;
     }
-    for (int roll = 0; roll < jp.n_rolls_active; roll++) {
+    for (int roll = jp.roll_begin; roll < jp.n_rolls_active; roll++) {
         if (jp.return_only_best && best >= jp.graspval_top) break;  // :362-365
         const int u = j * R + roll;
         const int val = per_roll_top[u * 3 + 2];

@@ -67,8 +67,11 @@ typedef struct {
     int gripper_opening_width; /* :281, :433                                                                  */
     int return_only_best;      /* show_only_best_grasp: enables the early exit at graspval_top (:362-365)     */
     int graspval_top;          /* 119 (:203)                                                                  */
-    int roll_limit;            /* evaluate only rolls [0, roll_limit); <=0 = all.  Stand-in for the caller's
-                                  time budget / preempt checks (:350-357, :367-374)                           */
+    int roll_limit;            /* evaluate only rolls [roll_begin, roll_limit); <=0 = up to R.  Stand-in for the
+                                  caller's time budget / preempt checks (:350-357, :367-374)                   */
+    int roll_begin;            /* first roll to evaluate (0 normally); > 0 only when one goal's rolls are sharded
+                                  over several GPUs -- the caller merges the per-roll tops          */
+    int reserved;
 } haf_request;
 
 typedef struct {

@@ -696,4 +696,63 @@ int orc_search(const float* xyz, size_t n, size_t stride_bytes, const orc_reques
     return 0;
 }
 
+// =====================================================================================
+// a16  grasp pose in world coordinates -- transform_gp_in_wcs_and_publish server.cpp:1274-1401
+// =====================================================================================
+// Eigen's Matrix4f::inverse() is not vendored by the reference (unpinned); restated as adjugate / determinant.
+static void orc_invert4(const float* m, float* inv) {
+    float a[16];
+    a[0] = m[5] * m[10] * m[15] - m[5] * m[11] * m[14] - m[9] * m[6] * m[15] + m[9] * m[7] * m[14] + m[13] * m[6] * m[11] - m[13] * m[7] * m[10];
+    a[4] = -m[4] * m[10] * m[15] + m[4] * m[11] * m[14] + m[8] * m[6] * m[15] - m[8] * m[7] * m[14] - m[12] * m[6] * m[11] + m[12] * m[7] * m[10];
+    a[8] = m[4] * m[9] * m[15] - m[4] * m[11] * m[13] - m[8] * m[5] * m[15] + m[8] * m[7] * m[13] + m[12] * m[5] * m[11] - m[12] * m[7] * m[9];
+    a[12] = -m[4] * m[9] * m[14] + m[4] * m[10] * m[13] + m[8] * m[5] * m[14] - m[8] * m[6] * m[13] - m[12] * m[5] * m[10] + m[12] * m[6] * m[9];
+    a[1] = -m[1] * m[10] * m[15] + m[1] * m[11] * m[14] + m[9] * m[2] * m[15] - m[9] * m[3] * m[14] - m[13] * m[2] * m[11] + m[13] * m[3] * m[10];
+    a[5] = m[0] * m[10] * m[15] - m[0] * m[11] * m[14] - m[8] * m[2] * m[15] + m[8] * m[3] * m[14] + m[12] * m[2] * m[11] - m[12] * m[3] * m[10];
+    a[9] = -m[0] * m[9] * m[15] + m[0] * m[11] * m[13] + m[8] * m[1] * m[15] - m[8] * m[3] * m[13] - m[12] * m[1] * m[11] + m[12] * m[3] * m[9];
+    a[13] = m[0] * m[9] * m[14] - m[0] * m[10] * m[13] - m[8] * m[1] * m[14] + m[8] * m[2] * m[13] + m[12] * m[1] * m[10] - m[12] * m[2] * m[9];
+    a[2] = m[1] * m[6] * m[15] - m[1] * m[7] * m[14] - m[5] * m[2] * m[15] + m[5] * m[3] * m[14] + m[13] * m[2] * m[7] - m[13] * m[3] * m[6];
+    a[6] = -m[0] * m[6] * m[15] + m[0] * m[7] * m[14] + m[4] * m[2] * m[15] - m[4] * m[3] * m[14] - m[12] * m[2] * m[7] + m[12] * m[3] * m[6];
+    a[10] = m[0] * m[5] * m[15] - m[0] * m[7] * m[13] - m[4] * m[1] * m[15] + m[4] * m[3] * m[13] + m[12] * m[1] * m[7] - m[12] * m[3] * m[5];
+    a[14] = -m[0] * m[5] * m[14] + m[0] * m[6] * m[13] + m[4] * m[1] * m[14] - m[4] * m[2] * m[13] - m[12] * m[1] * m[6] + m[12] * m[2] * m[5];
+    a[3] = -m[1] * m[6] * m[11] + m[1] * m[7] * m[10] + m[5] * m[2] * m[11] - m[5] * m[3] * m[10] - m[9] * m[2] * m[7] + m[9] * m[3] * m[6];
+    a[7] = m[0] * m[6] * m[11] - m[0] * m[7] * m[10] - m[4] * m[2] * m[11] + m[4] * m[3] * m[10] + m[8] * m[2] * m[7] - m[8] * m[3] * m[6];
+    a[11] = -m[0] * m[5] * m[11] + m[0] * m[7] * m[9] + m[4] * m[1] * m[11] - m[4] * m[3] * m[9] - m[8] * m[1] * m[7] + m[8] * m[3] * m[5];
+    a[15] = m[0] * m[5] * m[10] - m[0] * m[6] * m[9] - m[4] * m[1] * m[10] + m[4] * m[2] * m[9] + m[8] * m[1] * m[6] - m[8] * m[2] * m[5];
+    const float det = m[0] * a[0] + m[1] * a[4] + m[2] * a[8] + m[3] * a[12];
+    const float inv_det = 1.0f / det;
+    for (int i = 0; i < 16; i++) inv[i] = a[i] * inv_det;
+}
+// out[13]: gp1 xyz, gp2 xyz, averaged xyz, approach vector xyz, roll(rad).  heights_best: the G*G grid of the best roll.
+void orc_transform_gp_in_wcs(const double center[3], const double av_raw[3], int gripper_opening_width, int roll_step_deg, int G,
+                             const float* heights_best, int id_row_top_all, int id_col_top_all, int nr_roll_top_all, double* out) {
+    double av[3];
+    orc_normalize_approach(av_raw, av);
+    float M[16], Minv[16];
+    orc_build_transform(center, av, gripper_opening_width, nr_roll_top_all < 0 ? 0 : nr_roll_top_all, roll_step_deg, M);
+    float x_gp_roll = -((float)(G / 2 - id_row_top_all)) / 100;  // :1339
+    float y_gp_roll = -((float)(G / 2 - id_col_top_all)) / 100;  // :1340
+    float h_locmax_roll = -10;
+    if (nr_roll_top_all >= 0)
+        for (int row_z = -4; row_z < 5; row_z++)       // :1343
+            for (int col_z = -4; col_z < 4; col_z++) { // :1344 (asymmetric)
+                int r = id_row_top_all + row_z, c = id_col_top_all + col_z;
+                if (r >= 0 && c >= 0 && r < G && c < G && h_locmax_roll < heights_best[r * G + c]) h_locmax_roll = heights_best[r * G + c];
+            }
+    h_locmax_roll -= 0.01;  // :1354
+    float z_gp_roll = h_locmax_roll;
+    float x_gp_dis = 0.03f;
+    float gp1[4] = {x_gp_roll - x_gp_dis, y_gp_roll, z_gp_roll, 1.0f}, gp2[4] = {x_gp_roll + x_gp_dis, y_gp_roll, z_gp_roll, 1.0f};
+    orc_invert4(M, Minv);
+    float g1[4], g2[4];
+    for (int i = 0; i < 4; i++) {
+        g1[i] = ((Minv[i * 4] * gp1[0] + Minv[i * 4 + 1] * gp1[1]) + Minv[i * 4 + 2] * gp1[2]) + Minv[i * 4 + 3] * gp1[3];
+        g2[i] = ((Minv[i * 4] * gp2[0] + Minv[i * 4 + 1] * gp2[1]) + Minv[i * 4 + 2] * gp2[2]) + Minv[i * 4 + 3] * gp2[3];
+    }
+    out[0] = g1[0]; out[1] = g1[1]; out[2] = g1[2];
+    out[3] = g2[0]; out[4] = g2[1]; out[5] = g2[2];
+    out[6] = (g1[0] + g2[0]) / 2.0; out[7] = (g1[1] + g2[1]) / 2.0; out[8] = (g1[2] + g2[2]) / 2.0;  // :1395-1397
+    out[9] = M[8]; out[10] = M[9]; out[11] = M[10];  // :1370-1374
+    out[12] = (float)((nr_roll_top_all * roll_step_deg * ORC_PI) / 180);  // :1401
+}
+
 }  // extern "C"

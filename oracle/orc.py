@@ -191,6 +191,15 @@ class Oracle:
                                       _fp(np.ascontiguousarray(mask, np.uint8)), G, _fp(ev), _fp(top), _fp(first))
         return ev, tuple(int(t) for t in top), tuple(int(t) for t in first)
 
+    def transform_gp_in_wcs(self, rq: OrcRequest, heights_best: np.ndarray, row: int, col: int, roll: int, roll_step_deg: int = 15):
+        """a16: (gp1 xyz, gp2 xyz, averaged xyz, approach xyz, roll rad) as 13 doubles."""
+        out = np.zeros(13, np.float64)
+        G = heights_best.shape[0]
+        self.L.orc_transform_gp_in_wcs((C.c_double * 3)(*rq.center), (C.c_double * 3)(*rq.approach), int(rq.gripper_opening_width),
+                                       int(roll_step_deg), G, _fp(np.ascontiguousarray(heights_best, np.float32)), int(row), int(col),
+                                       int(roll), _fp(out))
+        return out
+
     def search(self, xyz: np.ndarray, rq: OrcRequest, G: int = 56, roll_step_deg: int = 15, roll_max_deg: int = 190,
                emulate_text: bool = True, full: bool = True):
         xyz = np.ascontiguousarray(xyz, np.float32)

@@ -130,3 +130,50 @@ def test_synth_cloud_is_deterministic():
     assert np.abs(a[:, :2]).max() < 0.28
     import zlib
     assert zlib.crc32(synth.synth_cloud(1234, 1000).tobytes()) == zlib.crc32(a[:1000].tobytes())  # counter-based
+
+
+def _fnv1a(b):
+    h = 1469598103934665603
+    for x in b:
+        h = ((h ^ x) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
+def _lzf_literal_stream(data: bytes) -> bytes:
+    """a valid LZF stream made of literal runs only (enough to exercise the container + SoA layout)"""
+    out = bytearray()
+    for i in range(0, len(data), 32):
+        chunk = data[i:i + 32]
+        out.append(len(chunk) - 1)
+        out += chunk
+    return bytes(out)
+
+
+def test_cpp_pcd_reader_all_formats(tmp_path):
+    """haf_cli --dump-pcd (C++ reader of csrc/host/pcd_io.hpp) == the Python reader, on ASCII / binary / binary_compressed."""
+    import struct
+    from haf_grasping_b200 import build
+    from haf_grasping_b200.pcd import read_pcd
+    cli = build.build_cli()
+    rng = np.random.default_rng(2)
+    pts = rng.normal(size=(53, 3)).astype(np.float32)
+    hdr = "# .PCD v0.7\nVERSION 0.7\nFIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\nWIDTH 53\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS 53\n"
+    files = {}
+    files["a.pcd"] = (hdr + "DATA ascii\n" + "\n".join(" ".join("%.9g" % v for v in row) for row in pts) + "\n0 0 0\n").encode()
+    files["b.pcd"] = (hdr + "DATA binary\n").encode() + pts.tobytes()
+    soa = np.ascontiguousarray(pts.T).tobytes()
+    comp = _lzf_literal_stream(soa)
+    files["c.pcd"] = (hdr + "DATA binary_compressed\n").encode() + struct.pack("<II", len(comp), len(soa)) + comp
+    for name, blob in files.items():
+        f = tmp_path / name
+        f.write_bytes(blob)
+        py = read_pcd(str(f))
+        assert py.tobytes() == pts.tobytes(), name
+        out = subprocess.run([cli, "--pcd", str(f), "--dump-pcd"], capture_output=True, text=True, check=True).stdout.split()
+        assert int(out[0]) == 53 and int(out[1]) == _fnv1a(pts.tobytes()), name
+    if os.path.isdir(REFERENCE_DATA):
+        for name in ("pcd5.pcd", "table2_mult_obj_rcs_1428580941635676.pcd"):
+            path = os.path.join(REFERENCE_DATA, name)
+            out = subprocess.run([cli, "--pcd", path, "--dump-pcd"], capture_output=True, text=True, check=True).stdout.split()
+            py = read_pcd(path)
+            assert int(out[0]) == len(py) and int(out[1]) == _fnv1a(py.tobytes())

@@ -362,3 +362,46 @@ def test_create_errors(hg, tmp_models, tmp_path):
     with pytest.raises(hg.HafError) as e:
         hg.GraspSearch(FEATURES, RANGE, str(bad))
     assert e.value.code == -5
+
+
+def test_cpp_host_cli_matches_oracle_grasp_output(hg, oracle_lib, trained_model, clouds, tmp_path):
+    """haf_cli = C++ host mirror (csrc/host/calc_grasppoints_b200.hpp: read_pc_cb -> loop_control ->
+    transform_gp_in_wcs_and_publish) on the C ABI.  GraspOutput fields vs the oracle's restatement of
+    server.cpp:1274-1401."""
+    import json
+    import subprocess
+    from haf_grasping_b200 import build
+    cli = build.build_cli()
+    o = oracle_lib.Oracle(FEATURES, RANGE, trained_model)
+    for name, kw in (("pcd2", {}), ("table1", {"approach": (0.5, 0.0, 0.8660254), "center": (0.05, 0.2, 0.0)}), ("pcd7", {})):
+        xyz = clouds[name]
+        f = tmp_path / (name + ".pcd")
+        with open(f, "wb") as fh:
+            fh.write(("# .PCD v0.7\nVERSION 0.7\nFIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\nWIDTH %d\nHEIGHT 1\n"
+                      "VIEWPOINT 0 0 0 1 0 0 0\nPOINTS %d\nDATA binary\n" % (len(xyz), len(xyz))).encode())
+            fh.write(np.ascontiguousarray(xyz, np.float32).tobytes())
+        args = [cli, "--features", FEATURES, "--range", RANGE, "--model", trained_model, "--pcd", str(f), "--json"]
+        if "approach" in kw:
+            args += ["--approach"] + [repr(v) for v in kw["approach"]]
+        if "center" in kw:
+            args += ["--center"] + [repr(v) for v in kw["center"]]
+        got = json.loads(subprocess.run(args, capture_output=True, text=True, check=True).stdout)
+        orq = oracle_lib.make_request(**kw)
+        ores = o.search(xyz, orq)
+        b = ores["best"]
+        assert (got["row"], got["col"], got["roll_index"], got["topval"], got["eval"]) == (b.row, b.col, b.roll, b.topval, b.eval)
+        assert got["per_roll_top"] == ores["per_roll_top"].tolist()
+        pose = o.transform_gp_in_wcs(orq, ores["heights"][max(b.roll, 0)], b.row, b.col, b.roll)
+        mine = np.array(got["graspPoint1"] + got["graspPoint2"] + got["averagedGraspPoint"] + got["approachVector"] + [got["roll"]])
+        assert np.allclose(mine, pose, rtol=0, atol=2e-6), (mine, pose)
+
+
+def test_roll_begin_shards_one_goal(pair_synth, clouds, hg, oracle_lib):
+    """rolls [5, 9) only: per-roll tops equal the full run's, the others are untouched (-1)."""
+    xyz = clouds["table3"]
+    full = pair_synth.gpu.search(xyz, [hg.make_request()])
+    part = pair_synth.gpu.search(xyz, [hg.make_request(roll_begin=5, roll_limit=9)])
+    assert np.array_equal(part["per_roll_top"][0][5:9], full["per_roll_top"][0][5:9])
+    assert (part["per_roll_top"][0][:5] == -1).all() and (part["per_roll_top"][0][9:] == -1).all()
+    assert np.array_equal(part["graspseval"][0][5:9], full["graspseval"][0][5:9])
+    assert part["best"].rolls_done == 4
