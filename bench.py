@@ -144,11 +144,13 @@ class ClockSampler:
 # exactly as server.cpp:616-656 and :754-800 do; the ROS-bound members come from the oracle restatement.
 # ------------------------------------------------------------------------------------------------------
 def _ref_cloud_worker(job):
-    xyz, model, grid, step, rmax, area, kind = job
+    xyz, model, grid, step, rmax, area, kind, roll_limit = job
     from oracle import orc
     o = orc.Oracle(FEATURES, RANGE, model)
     t0 = time.perf_counter()
     R = rmax // step
+    if roll_limit > 0:
+        R = min(R, roll_limit)
     windows = 0
     if kind == "reference":
         r = orc.Ref(FEATURES, RANGE, model)
@@ -168,18 +170,19 @@ def _ref_cloud_worker(job):
             os.remove(os.path.join(wd, f))
         os.rmdir(wd)
     else:  # "port": the in-process oracle
-        res = o.search(xyz, orc.make_request(area=area), G=grid, roll_step_deg=step, roll_max_deg=rmax, full=False)
+        res = o.search(xyz, orc.make_request(area=area, roll_limit=roll_limit), G=grid, roll_step_deg=step, roll_max_deg=rmax, full=False)
         windows = int(res["best"].n_windows)
     return windows, time.perf_counter() - t0
 
 
-def cpu_reference_rate(args, wc, clouds, n_workers, model):
-    """windows/s of the reference CPU path over `clouds` with n_workers processes (one cloud each at a time)."""
+def cpu_reference_rate(args, wc, clouds, n_workers, model, area=None, roll_limit=0):
+    """windows/s of the reference CPU path over `clouds` with n_workers processes (one cloud each at a time).
+    area / roll_limit bound the sample for the big-grid workload (windows/s is a per-window rate)."""
     import multiprocessing as mp
     from oracle import orc
     orc.build(ref=os.path.isdir("/root/reference"))
     kind = "reference" if orc.ref_available() else "port"
-    jobs = [(c, model, wc["grid"], wc["step"], wc["rmax"], wc["area"], kind) for c in clouds]
+    jobs = [(c, model, wc["grid"], wc["step"], wc["rmax"], area or wc["area"], kind, roll_limit) for c in clouds]
     t0 = time.perf_counter()
     if n_workers <= 1:
         res = [_ref_cloud_worker(j) for j in jobs]
@@ -204,18 +207,19 @@ def run_reference(args):
     import numpy as np  # noqa: F401
     from haf_grasping_b200 import synth
     times, wins, kind = [], [], "port"
+    sample_kw = {"area": (100.0, 100.0), "roll_limit": 1} if args.workload == "grid512" else {}
     for s in range(args.warmup + args.steps):
         if args.workload == "batch":
             clouds = [synth.synth_cloud(1234 + (s * per_step + i) % wc["n_clouds"], wc["n_points"], r=wc["r"]) for i in range(per_step)]
         else:
             clouds = make_clouds(args, wc, 0)
-        rate, w, dt, kind = cpu_reference_rate(args, wc, clouds, cores, model)
+        rate, w, dt, kind = cpu_reference_rate(args, wc, clouds, cores, model, **sample_kw)
         if s >= args.warmup:
             times.append(dt)
             wins.append(w)
     value = sum(wins) / sum(times)
-    sample = "%d cloud(s) per step (one per worker process), %d timed steps; %s" % (
-        per_step, args.steps, "reference feature classes + svm-scale + svm-predict child processes on text files per roll"
+    sample = "%s%d cloud(s) per step (one per worker process), %d timed steps; %s" % (
+        "roll 0 of a 100x100 cm sub-area of the 512-grid cloud; " if sample_kw else "", per_step, args.steps, "reference feature classes + svm-scale + svm-predict child processes on text files per roll"
         if kind == "reference" else "in-process oracle port")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
@@ -223,7 +227,7 @@ def run_reference(args):
             "config": {"workload": describe(args, wc), "n_sv": args.nsv},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def describe(args, wc):
@@ -364,19 +368,39 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             ns = min(args.cpu_sample_clouds, n_clouds)
-            rate, w, dt, kind = cpu_reference_rate(args, wc, clouds[:ns], 1, model)
+            skw = {"area": (100.0, 100.0), "roll_limit": 1} if args.workload == "grid512" else {}
+            rate, w, dt, kind = cpu_reference_rate(args, wc, clouds[:ns], 1, model, **skw)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": 1, "kind": kind,
-                                    "sample": "first %d cloud(s) of the same workload, all 12 rolls, %d windows in %.1f s; %s" % (
-                                        ns, w, dt, "reference feature classes + svm-scale/svm-predict child processes on text files"
+                                    "sample": "%sfirst %d cloud(s) of the same workload, %s, %d windows in %.1f s; %s" % (
+                                        "roll 0 of a 100x100 cm sub-area; " if skw else "", ns, "1 roll" if skw else "all 12 rolls", w, dt, "reference feature classes + svm-scale/svm-predict child processes on text files"
                                         if kind == "reference" else "in-process oracle port")}
-        print(json.dumps(line), flush=True)
+        emit(line)
     gs.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def protect_stdout():
+    """Everything that is not the ONE JSON line (NCCL's version banner, library chatter) goes to stderr: fd 1 is
+    pointed at stderr and the JSON line is written to a private duplicate of the original stdout."""
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     args = parse()
+    protect_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -516,6 +516,22 @@ bool is_device_ptr(const void* p) {
 
 }  // namespace
 
+static size_t exact_smem_bytes(const haf_ctx* ctx) {
+    const size_t base = (size_t)HAF_EXACT_WB * ctx->Dsv * sizeof(double);
+    const size_t with_kv = (size_t)(ctx->Dsv + ctx->Spad) * sizeof(double);
+    return (with_kv <= 96 * 1024) ? std::max(base, with_kv) : base;
+}
+static ExactArgs make_exact_args(haf_ctx* ctx, const int* list, const unsigned* list_count, unsigned* cnt, int G, int ubase) {
+    ExactArgs a;
+    a.list = list; a.list_count = list_count; a.win_count = cnt + 0; a.integral = ctx->d_integral.p; a.win = ctx->d_win.p;
+    a.G = G; a.unit_base = ubase; a.feats = ctx->d_feats.p; a.dims = ctx->d_dims.p; a.D = ctx->D; a.lower = ctx->lower; a.upper = ctx->upper;
+    a.emulate_text = ctx->cfg.emulate_text_roundtrip; a.sv64T = ctx->d_sv64T.p; a.Spad = ctx->Spad; a.S = ctx->S; a.Dsv = ctx->Dsv;
+    a.coef64 = ctx->d_coef64.p; a.gamma = ctx->gamma; a.rho = ctx->rho; a.kscratch = ctx->d_kscratch.p; a.dec = ctx->d_dec.p;
+    a.unsupported_flag = (int*)(cnt + 3);
+    a.kv_in_smem = exact_smem_bytes(ctx) >= (size_t)(ctx->Dsv + ctx->Spad) * sizeof(double) ? 1 : 0;
+    return a;
+}
+
 // Runs the whole path for `jobs` (sorted by cloud).  Outputs land in ctx->h_results / h_per_roll_top (pinned) and,
 // when out_* are given (single-chunk calls only), in the caller's buffers.
 static int run_jobs(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& jobs, float* out_evals, unsigned char* out_mask,
@@ -710,10 +726,7 @@ static int run_jobs(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& jobs, fl
         if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[ci * 8 + 4], st));
         if (ctx->cfg.svm_mode == HAF_SVM_FP64_EXACT) {
             CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_guardflag.p, 0, ldx, st));
-            svm_exact_kernel<<<exact_ctas, 256, HAF_EXACT_WB * ctx->Dsv * sizeof(double), st>>>(nullptr, nullptr, cnt + 0, ctx->d_integral.p, ctx->d_win.p, G, ubase,
-                                                                                   ctx->d_feats.p, ctx->d_dims.p, ctx->D, ctx->lower, ctx->upper,
-                                                                                   ctx->cfg.emulate_text_roundtrip, ctx->d_sv64T.p, ctx->Spad, ctx->S, ctx->Dsv,
-                                                                                   ctx->d_coef64.p, ctx->gamma, ctx->rho, ctx->d_kscratch.p, ctx->d_dec.p, (int*)(cnt + 3));
+            svm_exact_kernel<<<exact_ctas, 256, exact_smem_bytes(ctx), st>>>(make_exact_args(ctx, nullptr, nullptr, cnt, G, ubase));
             LAUNCHED(ctx);
             if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[ci * 8 + 5], st));
         } else if (tc) {
@@ -736,10 +749,7 @@ static int run_jobs(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& jobs, fl
                                                                                        ctx->d_guardflag.p, ctx->d_guardlist.p, cnt + 1);
             LAUNCHED(ctx);
             if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[ci * 8 + 5], st));
-            svm_exact_kernel<<<exact_ctas, 256, HAF_EXACT_WB * ctx->Dsv * sizeof(double), st>>>(ctx->d_guardlist.p, cnt + 1, cnt + 0, ctx->d_integral.p, ctx->d_win.p, G, ubase,
-                                                                                   ctx->d_feats.p, ctx->d_dims.p, ctx->D, ctx->lower, ctx->upper,
-                                                                                   ctx->cfg.emulate_text_roundtrip, ctx->d_sv64T.p, ctx->Spad, ctx->S, ctx->Dsv,
-                                                                                   ctx->d_coef64.p, ctx->gamma, ctx->rho, ctx->d_kscratch.p, ctx->d_dec.p, (int*)(cnt + 3));
+            svm_exact_kernel<<<exact_ctas, 256, exact_smem_bytes(ctx), st>>>(make_exact_args(ctx, ctx->d_guardlist.p, cnt + 1, cnt, G, ubase));
             LAUNCHED(ctx);
         } else {
             svm_rbf_simt_kernel<<<(unsigned)(ldx / SVM_BM), 256, SVM_STAGES * SVM_BK * (SVM_BM + SVM_BN) * 4, st>>>(
@@ -747,10 +757,7 @@ static int run_jobs(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& jobs, fl
                 ctx->guard_rel, cnt + 0, ctx->d_dec.p, ctx->d_guardflag.p, ctx->d_guardlist.p, cnt + 1);
             LAUNCHED(ctx);
             if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[ci * 8 + 5], st));
-            svm_exact_kernel<<<exact_ctas, 256, HAF_EXACT_WB * ctx->Dsv * sizeof(double), st>>>(ctx->d_guardlist.p, cnt + 1, cnt + 0, ctx->d_integral.p, ctx->d_win.p, G, ubase,
-                                                                                   ctx->d_feats.p, ctx->d_dims.p, ctx->D, ctx->lower, ctx->upper,
-                                                                                   ctx->cfg.emulate_text_roundtrip, ctx->d_sv64T.p, ctx->Spad, ctx->S, ctx->Dsv,
-                                                                                   ctx->d_coef64.p, ctx->gamma, ctx->rho, ctx->d_kscratch.p, ctx->d_dec.p, (int*)(cnt + 3));
+            svm_exact_kernel<<<exact_ctas, 256, exact_smem_bytes(ctx), st>>>(make_exact_args(ctx, ctx->d_guardlist.p, cnt + 1, cnt, G, ubase));
             LAUNCHED(ctx);
         }
         // 6. labels -> grids, score stencil, argmax, tie rule

@@ -742,75 +742,107 @@ __global__ void __launch_bounds__(256, 2) svm_rbf_simt_kernel(const float* __res
 // list == NULL: all windows (HAF_SVM_FP64_EXACT).  grid-stride over the list; kscratch: [gridDim.x][Spad].
 // ---------------------------------------------------------------------------------------------------
 #define HAF_EXACT_WB 8   // windows evaluated together by one CTA: every support-vector element is loaded once per 8 windows
-__global__ void __launch_bounds__(256) svm_exact_kernel(const int* __restrict__ list, const unsigned* __restrict__ list_count,
-                                                        const unsigned* __restrict__ win_count,
-                                                        const float* __restrict__ integral, const int2* __restrict__ win,
-                                                        int G, int unit_base, const FeatDev* __restrict__ feats,
-                                                        const DimDev* __restrict__ dims, int D, double lower, double upper,
-                                                        int emulate_text, const double* __restrict__ sv64T, int Spad, int S,
-                                                        int Dsv, const double* __restrict__ coef64, double gamma, double rho,
-                                                        double* __restrict__ kscratch, double* __restrict__ dec,
-                                                        int* __restrict__ unsupported_flag) {
-    extern __shared__ double xs[];  // [HAF_EXACT_WB][Dsv]
-    const unsigned n = list ? *list_count : *win_count;
-    const int ld = G + 1;
-    double* kv = kscratch + (size_t)blockIdx.x * HAF_EXACT_WB * Spad;  // [WB][Spad]
-    for (unsigned e0 = blockIdx.x * HAF_EXACT_WB; e0 < n; e0 += gridDim.x * HAF_EXACT_WB) {
-        const int nb = min((unsigned)HAF_EXACT_WB, n - e0);
+struct ExactArgs {
+    const int* list; const unsigned* list_count; const unsigned* win_count; const float* integral; const int2* win;
+    int G, unit_base; const FeatDev* feats; const DimDev* dims; int D; double lower, upper; int emulate_text;
+    const double* sv64T; int Spad, S, Dsv; const double* coef64; double gamma, rho; double* kscratch; double* dec;
+    int* unsupported_flag;
+    int kv_in_smem;   // 1: the latency variant (WB = 1) keeps coef_i*K_i in shared memory (dynamic smem holds Dsv + S doubles)
+};
+// WB windows per CTA pass.  WB = 8 for long lists (throughput: each SV element is read once per 8 windows), WB = 1 when
+// the list is shorter than the grid (latency: a single goal has only a handful of guard-band windows).
+template <int WB>
+__device__ __forceinline__ void svm_exact_body(const ExactArgs& A, double* xs, unsigned n) {
+    const int ld = A.G + 1, Dsv = A.Dsv, Spad = A.Spad;
+    // [WB][Spad]; the single thread that sums a window sequentially must not wait on L2 for every batch of terms
+    double* kv = (WB == 1 && A.kv_in_smem) ? (xs + Dsv) : (A.kscratch + (size_t)blockIdx.x * HAF_EXACT_WB * Spad);
+    for (unsigned e0 = blockIdx.x * WB; e0 < n; e0 += gridDim.x * WB) {
+        const int nb = min((unsigned)WB, n - e0);
         __syncthreads();
         // x of every window of the block, bit-exact emulation of both text round trips
-        for (int t = threadIdx.x; t < HAF_EXACT_WB * Dsv; t += blockDim.x) {
+        for (int t = threadIdx.x; t < WB * Dsv; t += blockDim.x) {
             const int b = t / Dsv, d = t - b * Dsv;
             double x = 0.0;
-            if (b < nb && d < D) {
-                const int w = list ? list[e0 + b] : (int)(e0 + b);
-                const int2 uc = win[w];
-                const int row = uc.y / G, col = uc.y - row * G;
-                const float* P = integral + (size_t)(uc.x - unit_base) * ld * ld + (size_t)(row - 7) * ld + (col - 7);
-                const DimDev dd = dims[d];
+            if (b < nb && d < A.D) {
+                const int w = A.list ? A.list[e0 + b] : (int)(e0 + b);
+                const int2 uc = A.win[w];
+                const int row = uc.y / A.G, col = uc.y - row * A.G;
+                const float* P = A.integral + (size_t)(uc.x - A.unit_base) * ld * ld + (size_t)(row - 7) * ld + (col - 7);
+                const DimDev dd = A.dims[d];
                 if (dd.feat < 0) x = dd.cval;
                 else {
-                    const float raw = feature_value(P, feats[dd.feat]);
+                    const float raw = feature_value(P, A.feats[dd.feat]);
                     bool u4 = false, u6 = false;
-                    const double v = emulate_text ? hafdec::text4(raw, &u4) : (double)raw;
+                    const double v = A.emulate_text ? hafdec::text4(raw, &u4) : (double)raw;
                     if (!dd.drop) {
                         double val;
-                        if (v == dd.fmin) val = lower;
-                        else if (v == dd.fmax) val = upper;
-                        else val = __dadd_rn(lower, __ddiv_rn(__dmul_rn(__dsub_rn(upper, lower), __dsub_rn(v, dd.fmin)), dd.den));
-                        if (val != 0.0) x = emulate_text ? hafdec::text6(val, &u6) : val;
+                        if (v == dd.fmin) val = A.lower;
+                        else if (v == dd.fmax) val = A.upper;
+                        else val = __dadd_rn(A.lower, __ddiv_rn(__dmul_rn(__dsub_rn(A.upper, A.lower), __dsub_rn(v, dd.fmin)), dd.den));
+                        if (val != 0.0) x = A.emulate_text ? hafdec::text6(val, &u6) : val;
                     }
-                    if (u4 || u6) *unsupported_flag = 1;
+                    if (u4 || u6) *A.unsupported_flag = 1;
                 }
             }
             xs[t] = x;
         }
         __syncthreads();
-        // K_i for the block: d loop sequential and un-fused per (window, SV); sv element shared by the 8 windows
-        for (int i = threadIdx.x; i < S; i += blockDim.x) {
-            double sum[HAF_EXACT_WB];
+        // K_i for the block: d loop sequential and un-fused per (window, SV); sv element shared by the WB windows
+        for (int i = threadIdx.x; i < A.S; i += blockDim.x) {
+            double sum[WB];
 #pragma unroll
-            for (int b = 0; b < HAF_EXACT_WB; b++) sum[b] = 0.0;
-            for (int d = 0; d < Dsv; d++) {
-                const double sv = sv64T[(size_t)d * Spad + i];
+            for (int b = 0; b < WB; b++) sum[b] = 0.0;
+            // loads are independent of the (sequential) accumulation chain: fetch 8 ahead so the L2 latency overlaps
+            constexpr int UN = (WB == 1) ? 8 : 2;
+            int d = 0;
+            for (; d + UN <= Dsv; d += UN) {
+                double sv[UN];
 #pragma unroll
-                for (int b = 0; b < HAF_EXACT_WB; b++) {
+                for (int k = 0; k < UN; k++) sv[k] = A.sv64T[(size_t)(d + k) * Spad + i];
+#pragma unroll
+                for (int k = 0; k < UN; k++) {
+#pragma unroll
+                    for (int b = 0; b < WB; b++) {
+                        const double diff = __dsub_rn(xs[b * Dsv + d + k], sv[k]);
+                        sum[b] = __dadd_rn(sum[b], __dmul_rn(diff, diff));
+                    }
+                }
+            }
+            for (; d < Dsv; d++) {
+                const double sv = A.sv64T[(size_t)d * Spad + i];
+#pragma unroll
+                for (int b = 0; b < WB; b++) {
                     const double diff = __dsub_rn(xs[b * Dsv + d], sv);
                     sum[b] = __dadd_rn(sum[b], __dmul_rn(diff, diff));
                 }
             }
+            // the product coef_i * K_i is formed here (same bits wherever it is computed); the SUM stays sequential
 #pragma unroll
-            for (int b = 0; b < HAF_EXACT_WB; b++) kv[(size_t)b * Spad + i] = exp(__dmul_rn(-gamma, sum[b]));
+            for (int b = 0; b < WB; b++) kv[(size_t)b * Spad + i] = __dmul_rn(A.coef64[i], exp(__dmul_rn(-A.gamma, sum[b])));
         }
         __syncthreads();
         // decision value: sequential sum in file order, one thread per window (svm.cpp:2500-2514)
-        if (threadIdx.x < nb) {
+        if ((int)threadIdx.x < nb) {
             const double* k = kv + (size_t)threadIdx.x * Spad;
             double sum = 0.0;
-            for (int i = 0; i < S; i++) sum = __dadd_rn(sum, __dmul_rn(coef64[i], k[i]));
-            dec[list ? list[e0 + threadIdx.x] : (int)(e0 + threadIdx.x)] = __dsub_rn(sum, rho);
+            int i = 0;
+            for (; i + 8 <= A.S; i += 8) {
+                double t[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++) t[q] = k[i + q];
+#pragma unroll
+                for (int q = 0; q < 8; q++) sum = __dadd_rn(sum, t[q]);
+            }
+            for (; i < A.S; i++) sum = __dadd_rn(sum, k[i]);
+            A.dec[A.list ? A.list[e0 + threadIdx.x] : (int)(e0 + threadIdx.x)] = __dsub_rn(sum, A.rho);
         }
     }
+}
+__global__ void __launch_bounds__(256) svm_exact_kernel(const ExactArgs A) {
+    extern __shared__ double xs[];  // [HAF_EXACT_WB][Dsv]
+    const unsigned n = A.list ? *A.list_count : *A.win_count;
+    if (n >= (unsigned)gridDim.x * 2u) svm_exact_body<HAF_EXACT_WB>(A, xs, n);
+    else svm_exact_body<1>(A, xs, n);
 }
 
 // label -> graspsgrid value (server.cpp:843) scattered into the unit grids
