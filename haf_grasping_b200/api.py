@@ -145,7 +145,7 @@ class GraspSearch:
 
     def __init__(self, features_path, range_path, model_path, grid=56, roll_step_deg=15, roll_max_deg=190,
                  nr_features_without_shaf=302, device=0, emulate_text_roundtrip=True, svm_mode=HAF_SVM_FP32_GUARD,
-                 guard_rel=0.0):
+                 guard_rel=0.0, tc_variant=0):
         self.L = load_library()
         cfg = haf_config()
         self._keep = [features_path.encode(), range_path.encode(), model_path.encode()]
@@ -156,6 +156,7 @@ class GraspSearch:
         cfg.emulate_text_roundtrip = int(bool(emulate_text_roundtrip))
         cfg.svm_mode = svm_mode
         cfg.guard_rel = guard_rel
+        cfg.reserved[0] = tc_variant
         self.h = C.c_void_p()
         rc = self.L.haf_create(C.byref(self.h), C.byref(cfg))
         if rc != 0:

@@ -98,7 +98,9 @@ struct haf_ctx {
     DevBuf<float2> d_svtab;
     DevBuf<DimFeat> d_dimfeat;
     DevBuf<float> d_asum;
-    CUtensorMap tmSh, tmSl;
+    CUtensorMap tmSh, tmSl;     // 256-row boxes (single-CTA kernel)
+    CUtensorMap tmSh2, tmSl2;   // 128-row boxes (CTA-pair kernel)
+    int tc_variant = 0;         // 0: CTA-pair kernel (cta_group::2), 1: single-CTA kernel
 
     // per-call state
     DevBuf<unsigned char> d_xyz;       // staging for host clouds
@@ -415,7 +417,9 @@ extern "C" int haf_create(haf_ctx** out, const haf_config* cfg) {
         CREATE_TRY(cudaMemcpy(ctx->d_SVh.p, svh.data(), svh.size() * 2, cudaMemcpyHostToDevice));
         CREATE_TRY(cudaMemcpy(ctx->d_SVl.p, svl.data(), svl.size() * 2, cudaMemcpyHostToDevice));
         CREATE_TRY(cudaMemcpy(ctx->d_svtab.p, tab.data(), SpadT * sizeof(float2), cudaMemcpyHostToDevice));
-        if (!make_tensor_map(&ctx->tmSh, ctx->d_SVh.p, Krow, SpadT, haftc::BN) || !make_tensor_map(&ctx->tmSl, ctx->d_SVl.p, Krow, SpadT, haftc::BN)) {
+        ctx->tc_variant = cfg->reserved[0];
+        if (!make_tensor_map(&ctx->tmSh, ctx->d_SVh.p, Krow, SpadT, haftc::BN) || !make_tensor_map(&ctx->tmSl, ctx->d_SVl.p, Krow, SpadT, haftc::BN) ||
+            !make_tensor_map(&ctx->tmSh2, ctx->d_SVh.p, Krow, SpadT, haftc::BN / 2) || !make_tensor_map(&ctx->tmSl2, ctx->d_SVl.p, Krow, SpadT, haftc::BN / 2)) {
             haf_destroy(ctx);
             return create_fail(HAF_ERR_CUDA, "cuTensorMapEncodeTiled failed for the support-vector operands");
         }
@@ -438,6 +442,7 @@ extern "C" int haf_create(haf_ctx** out, const haf_config* cfg) {
         if (ctx->d_dimfeat.ensure(D) != 0) { haf_destroy(ctx); return create_fail(HAF_ERR_NOMEM, "out of device memory uploading the joined feature table"); }
         CREATE_TRY(cudaMemcpy(ctx->d_dimfeat.p, joined.data(), D * sizeof(DimFeat), cudaMemcpyHostToDevice));
         CREATE_TRY(cudaFuncSetAttribute(haftc::svm_rbf_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, haftc::SMEM_BYTES));
+        CREATE_TRY(cudaFuncSetAttribute(haftc::svm_rbf_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, haftc::SMEM2_BYTES));
         CREATE_TRY(cudaFuncSetAttribute(features_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 32 * (Krow / 2 + 2) * 2 + HAF_FT_ROWS * (G + 1) * 4));
     }
     for (int i = 0; i < 10; i++) CREATE_TRY(cudaEventCreate(&ctx->ev[i]));
@@ -653,7 +658,7 @@ static int run_jobs(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& jobs, fl
         long long wcap_ll = 0;
         for (int j = j0; j < j1; j++) wcap_ll += jobs[j].wbound;
         const size_t Wcap = (size_t)std::max<long long>(wcap_ll, 1);
-        const size_t ldx = round_up(Wcap, SVM_BM);
+        const size_t ldx = round_up(Wcap, 2 * haftc::BM);  // whole window-tile pairs (CTA-pair kernel); also a multiple of SVM_BM
         const int c0 = jobs[j0].cloud, c1 = jobs[j1 - 1].cloud + 1;  // clouds touched by this chunk
         ENSURE(ctx, ctx->d_keys, (size_t)Uc * GG); ENSURE(ctx, ctx->d_integral, (size_t)Uc * ld * ld);
         ENSURE(ctx, ctx->d_mask, (size_t)Uc * GG); ENSURE(ctx, ctx->d_labelgrid, (size_t)Uc * GG); ENSURE(ctx, ctx->d_evals, (size_t)Uc * GG);
@@ -741,9 +746,20 @@ static int run_jobs(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& jobs, fl
             if (mt_cap < ctx->sm_count) nsplit = std::min(n_ntiles, (2 * ctx->sm_count + mt_cap - 1) / mt_cap);
             const int kblocks = (ctx->Krow + haftc::BK - 1) / haftc::BK;
             const int last_slices = (ctx->Krow - haftc::BK * (kblocks - 1)) / 16;
-            const int grid = (int)std::min<long long>((long long)mt_cap * nsplit, ctx->sm_count);
-            haftc::svm_rbf_tc_kernel<<<grid, haftc::THREADS, haftc::SMEM_BYTES, st>>>(tmXh, tmXl, ctx->tmSh, ctx->tmSl, ctx->d_xn.p, ctx->d_svtab.p, ctx->c_log2,
-                                                                                      cnt + 0, n_ntiles, nsplit, kblocks, last_slices, ctx->d_dec.p, ctx->d_asum.p);
+            if (ctx->tc_variant == 0) {
+                const int pairs_cap = (mt_cap + 1) / 2;
+                int nsplit2 = 1;
+                if (pairs_cap < ctx->sm_count / 2) nsplit2 = std::min(n_ntiles, (ctx->sm_count + pairs_cap - 1) / pairs_cap);
+                int grid2 = (int)std::min<long long>((long long)pairs_cap * nsplit2 * 2, ctx->sm_count);
+                grid2 &= ~1;  // whole clusters
+                haftc::svm_rbf_tc2_kernel<<<grid2, haftc::THREADS, haftc::SMEM2_BYTES, st>>>(tmXh, tmXl, ctx->tmSh2, ctx->tmSl2, ctx->d_xn.p, ctx->d_svtab.p,
+                                                                                             ctx->c_log2, cnt + 0, n_ntiles, nsplit2, kblocks, last_slices,
+                                                                                             ctx->d_dec.p, ctx->d_asum.p);
+            } else {
+                const int grid = (int)std::min<long long>((long long)mt_cap * nsplit, ctx->sm_count);
+                haftc::svm_rbf_tc_kernel<<<grid, haftc::THREADS, haftc::SMEM_BYTES, st>>>(tmXh, tmXl, ctx->tmSh, ctx->tmSl, ctx->d_xn.p, ctx->d_svtab.p, ctx->c_log2,
+                                                                                          cnt + 0, n_ntiles, nsplit, kblocks, last_slices, ctx->d_dec.p, ctx->d_asum.p);
+            }
             LAUNCHED(ctx);
             haftc::svm_finalize_kernel<<<(unsigned)((Wcap + 255) / 256), 256, 0, st>>>(ctx->d_dec.p, ctx->d_asum.p, cnt + 0, ctx->rho, ctx->guard_rel,
                                                                                        ctx->d_guardflag.p, ctx->d_guardlist.p, cnt + 1);

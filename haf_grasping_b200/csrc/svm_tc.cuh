@@ -233,11 +233,212 @@ svm_rbf_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constan
             }
         }
     }
+    __syncwarp();  // the role loops run on one elected lane: reconverge before the block-wide barrier
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ==================================================================================================================
+// CTA-pair variant (cta_group::2).  The single-CTA kernel above is bound by L2 -> shared-memory bandwidth: 96 KB per
+// 1536 MMA clocks = 64 B/clk/SM against a measured ~42-46 B/clk/SM (ncu: xbar2l1tex 11.7 TB/s, tensor pipe 60-73 %).
+// Here two CTAs of a cluster form one UMMA of M = 256 (128 window rows each) x N = 256: each CTA stages its own X tile
+// and only HALF of the SV tile (128 rows), so a stage is 64 KB per CTA for the same MMA time -> 42 B/clk/SM, and three
+// stages fit.  Only the leader CTA issues tcgen05.mma; tcgen05.commit multicasts the "stage free" / "accumulator
+// ready" arrivals to both CTAs; both CTAs' TMA loads complete_tx on the LEADER's full barrier; the peer's epilogue
+// threads arrive remotely on the leader's tmem_empty barrier.
+// ==================================================================================================================
+constexpr int STAGES2 = 3;
+constexpr int B2_TILE_BYTES = (BN / 2) * BK * 2;                      // 16 KB: this CTA's half of the SV tile
+constexpr int STAGE2_BYTES = 2 * A_TILE_BYTES + 2 * B2_TILE_BYTES;    // 64 KB per CTA
+constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 + 256;
+constexpr uint32_t IDESC2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address -> the leader CTA's copy
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t n_clusters_x() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t smem_dst, const CUtensorMap* map, int c0, int c1, uint32_t leader_bar) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_dst),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm_mc(uint32_t bar) {  // arrive on `bar` (same offset) in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_mma_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+
+// tmSh2 / tmSl2: SV tensor maps with a 128-row box.  Work item = (pair of window tiles, split of the SV tiles).
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+svm_rbf_tc2_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl,
+                   const __grid_constant__ CUtensorMap tmSh2, const __grid_constant__ CUtensorMap tmSl2,
+                   const float* __restrict__ xn, const float2* __restrict__ svtab, float c, const unsigned* __restrict__ win_count,
+                   int n_ntiles, int nsplit, int kblocks, int last_slices, double* __restrict__ dec_acc, float* __restrict__ asum_acc) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + STAGES2 * STAGE2_BYTES;
+    const uint32_t bar_full = bar_base;                   // [STAGES2]  (used in the leader CTA)
+    const uint32_t bar_empty = bar_base + 8 * STAGES2;    // [STAGES2]  (one per CTA)
+    const uint32_t bar_tfull = bar_base + 16 * STAGES2;   // [2]        (one per CTA)
+    const uint32_t bar_tempty = bar_tfull + 16;           // [2]        (used in the leader CTA)
+    const uint32_t tmem_slot = bar_tempty + 16;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES2; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 256); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    const unsigned W = *win_count;
+    const int n_pairs = (int)((W + 2 * BM - 1) / (2 * BM));
+    const int items = n_pairs * nsplit;
+    const int nt_per = (n_ntiles + nsplit - 1) / nsplit;
+    const int cid = (int)cluster_id_x(), ncl = (int)n_clusters_x();
+
+    if (warp == 0) {
+        if (lane == 0) {  // ===== TMA producer (both CTAs) =====
+            uint32_t it = 0;
+            for (int item = cid; item < items; item += ncl) {
+                const int mp = item / nsplit, sp = item - mp * nsplit;
+                const int nt0 = sp * nt_per, nt1 = min(n_ntiles, nt0 + nt_per);
+                const int mrow = (2 * mp + (int)rank) * BM;
+                for (int nt = nt0; nt < nt1; nt++)
+                    for (int kb = 0; kb < kblocks; kb++, it++) {
+                        const uint32_t s = it % STAGES2, ph = (it / STAGES2) & 1u;
+                        mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+                        const uint32_t st = smem_base + s * STAGE2_BYTES;
+                        const uint32_t lfull = (bar_full + 8 * s) & PEER_MASK;  // the LEADER's full barrier
+                        if (leader) mbar_expect_tx(bar_full + 8 * s, 2 * STAGE2_BYTES);
+                        tma_load_2d_2sm(st, &tmXh, kb * BK, mrow, lfull);
+                        tma_load_2d_2sm(st + A_TILE_BYTES, &tmXl, kb * BK, mrow, lfull);
+                        tma_load_2d_2sm(st + 2 * A_TILE_BYTES, &tmSh2, kb * BK, nt * BN + (int)rank * (BN / 2), lfull);
+                        tma_load_2d_2sm(st + 2 * A_TILE_BYTES + B2_TILE_BYTES, &tmSl2, kb * BK, nt * BN + (int)rank * (BN / 2), lfull);
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        if (leader && lane == 0) {  // ===== MMA issuer (leader CTA only) =====
+            uint32_t it = 0, acc_it = 0;
+            for (int item = cid; item < items; item += ncl) {
+                const int mp = item / nsplit, sp = item - mp * nsplit;
+                const int nt0 = sp * nt_per, nt1 = min(n_ntiles, nt0 + nt_per);
+                for (int nt = nt0; nt < nt1; nt++, acc_it++) {
+                    const uint32_t a = acc_it & 1u, aph = (acc_it >> 1) & 1u;
+                    mbar_wait(bar_tempty + 8 * a, aph ^ 1u);  // both CTAs' epilogues have drained this accumulator
+                    tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + a * BN;
+                    for (int kb = 0; kb < kblocks; kb++, it++) {
+                        const uint32_t s = it % STAGES2, ph = (it / STAGES2) & 1u;
+                        mbar_wait(bar_full + 8 * s, ph);
+                        tc_fence_after();
+                        const uint32_t st = smem_base + s * STAGE2_BYTES;
+                        const uint64_t d_ah = make_desc_sw128(st), d_al = make_desc_sw128(st + A_TILE_BYTES);
+                        const uint64_t d_bh = make_desc_sw128(st + 2 * A_TILE_BYTES), d_bl = make_desc_sw128(st + 2 * A_TILE_BYTES + B2_TILE_BYTES);
+                        const int slices = (kb == kblocks - 1) ? last_slices : (BK / 16);
+                        for (int k = 0; k < slices; k++) {
+                            const uint64_t adv = (uint64_t)(k * 2);
+                            tc_mma_2sm(tmem_d, d_ah + adv, d_bh + adv, IDESC2, (kb | k) ? 1u : 0u);
+                            tc_mma_2sm(tmem_d, d_ah + adv, d_bl + adv, IDESC2, 1u);
+                            tc_mma_2sm(tmem_d, d_al + adv, d_bh + adv, IDESC2, 1u);
+                        }
+                        tc_commit_2sm_mc(bar_empty + 8 * s);   // stage free in BOTH CTAs
+                    }
+                    tc_commit_2sm_mc(bar_tfull + 8 * a);       // accumulator halves ready in BOTH CTAs
+                }
+            }
+        }
+    } else {  // ===== epilogue warps 2..5 (both CTAs, each on its own 128 accumulator rows) =====
+        const int q = warp & 3;
+        uint32_t acc_it = 0;
+        const float c2 = -2.0f * c;
+        for (int item = cid; item < items; item += ncl) {
+            const int mp = item / nsplit, sp = item - mp * nsplit;
+            const int nt0 = sp * nt_per, nt1 = min(n_ntiles, nt0 + nt_per);
+            const unsigned m = (unsigned)(2 * mp + (int)rank) * BM + q * 32 + lane;
+            const float u = (m < W) ? c * xn[m] : 0.0f;
+            double dsum = 0.0;
+            float asum = 0.0f;
+            for (int nt = nt0; nt < nt1; nt++, acc_it++) {
+                const uint32_t a = acc_it & 1u, aph = (acc_it >> 1) & 1u;
+                mbar_wait(bar_tfull + 8 * a, aph);
+                tc_fence_after();
+                float ps = 0.0f, pa = 0.0f;
+                const float2* tab = svtab + (size_t)nt * BN;
+#pragma unroll 1
+                for (int ch = 0; ch < BN / 32; ch++) {
+                    uint32_t r[32];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * BN + ch * 32;
+                    HAFTC_LD32(taddr, r);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        const float2 t = __ldg(tab + ch * 32 + j);
+                        float arg = fmaf(__uint_as_float(r[j]), c2, u + t.x);
+                        arg = fminf(arg, 0.0f);
+                        const float e = ex2_approx(arg);
+                        ps = fmaf(t.y, e, ps);
+                        pa = fmaf(fabsf(t.y), e, pa);
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive_cluster((bar_tempty + 8 * a) & PEER_MASK);  // on the LEADER's barrier (count 256)
+                dsum += (double)ps;
+                asum += pa;
+            }
+            if (m < W && nt1 > nt0) {
+                atomicAdd(dec_acc + m, dsum);
+                atomicAdd(asum_acc + m, asum);
+            }
+        }
+    }
+    __syncwarp();  // reconverge the elected-lane role loops before the .aligned cluster barrier
+    tc_fence_before();
+    cluster_sync_all();   // nobody leaves (or frees TMEM) while the partner may still touch its shared memory / barriers
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 

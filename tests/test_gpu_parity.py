@@ -201,6 +201,16 @@ def test_fp64_exact_mode(hg, oracle_lib, trained_model, clouds):
         p.close()
 
 
+@pytest.mark.parametrize("name", ["pcd2", "table3"])
+def test_tensor_core_mode_single_cta_variant(hg, oracle_lib, trained_model, clouds, name):
+    """tc_variant = 1: the cta_group::1 kernel (kept as the reference point for the CTA-pair kernel)."""
+    p = Pair(hg, oracle_lib, trained_model, svm_mode=hg.HAF_SVM_TENSOR_GUARD, tc_variant=1)
+    try:
+        check_search(p, clouds[name], hg, oracle_lib, trained_model)
+    finally:
+        p.close()
+
+
 @pytest.mark.parametrize("name", ["pcd2", "pcd7", "table1", "plastic_mug2"])
 def test_tensor_core_mode(hg, oracle_lib, trained_model, clouds, name):
     """HAF_SVM_TENSOR_GUARD: tcgen05 split-bf16 contraction + FP64 guard band; everything before and after the
