@@ -429,21 +429,29 @@ extern "C" int haf_create(haf_ctx** out, const haf_config* cfg) {
             memset(&j, 0, sizeof j);
             const DimDev& dd = dims[d];
             if (dd.feat >= 0) {
-                memcpy(j.off, fd[dd.feat].off, sizeof j.off);
-                memcpy(j.w, fd[dd.feat].w, sizeof j.w);
-                j.flags = fd[dd.feat].flags;
+                const FeatDev& ff = fd[dd.feat];
+                for (int r = 0; r < 3; r++) {
+                    if (ff.flags & (1 << r)) {
+                        for (int q = 0; q < 4; q++) j.off[4 * r + q] = ff.off[4 * r + q] * 4;  // bytes
+                        j.w[r] = ff.w[r];
+                    } else {  // skipped region: identical corners, weight +0.0 -> contributes exactly +0.0
+                        for (int q = 0; q < 4; q++) j.off[4 * r + q] = 0;
+                        j.w[r] = 0.0f;
+                    }
+                }
+                j.flags = ff.flags & 0x100;
             } else {
                 j.flags = 0x200;
             }
             if (dd.drop) j.flags |= 0x400;
-            j.fmin = dd.fmin; j.slope = dd.slope; j.cval = dd.cval;
+            j.fmin = (float)dd.fmin; j.slope = (float)dd.slope; j.cval = (float)dd.cval;
             joined[d] = j;
         }
         if (ctx->d_dimfeat.ensure(D) != 0) { haf_destroy(ctx); return create_fail(HAF_ERR_NOMEM, "out of device memory uploading the joined feature table"); }
         CREATE_TRY(cudaMemcpy(ctx->d_dimfeat.p, joined.data(), D * sizeof(DimFeat), cudaMemcpyHostToDevice));
         CREATE_TRY(cudaFuncSetAttribute(haftc::svm_rbf_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, haftc::SMEM_BYTES));
         CREATE_TRY(cudaFuncSetAttribute(haftc::svm_rbf_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, haftc::SMEM2_BYTES));
-        CREATE_TRY(cudaFuncSetAttribute(features_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 32 * (Krow / 2 + 2) * 2 + HAF_FT_ROWS * (G + 1) * 4));
+        CREATE_TRY(cudaFuncSetAttribute(features_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * HAF_FT_WT * (Krow / 2 + 1) * 4 + HAF_FT_ROWS * (G + 1) * 4));
     }
     for (int i = 0; i < 10; i++) CREATE_TRY(cudaEventCreate(&ctx->ev[i]));
     ctx->ev_ok = true;
@@ -521,6 +529,9 @@ bool is_device_ptr(const void* p) {
 
 }  // namespace
 
+static size_t ft_smem_bytes(const haf_ctx* ctx) {
+    return (size_t)32 * HAF_FT_WT * (ctx->Krow / 2 + 1) * 4 + (size_t)HAF_FT_ROWS * (ctx->G + 1) * 4;
+}
 static size_t exact_smem_bytes(const haf_ctx* ctx) {
     const size_t base = (size_t)HAF_EXACT_WB * ctx->Dsv * sizeof(double);
     const size_t with_kv = (size_t)(ctx->Dsv + ctx->Spad) * sizeof(double);
@@ -715,9 +726,10 @@ static int run_jobs(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& jobs, fl
         if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[ci * 8 + 3], st));
         const unsigned wblocks32 = (unsigned)((Wcap + 31) / 32);
         if (tc) {
-            features_tc_kernel<<<wblocks32, 256, 2 * 32 * (ctx->Krow / 2 + 2) * 2 + HAF_FT_ROWS * (G + 1) * 4, st>>>(
-                ctx->d_integral.p, ctx->d_win.p, cnt + 0, G, ubase, ctx->d_dimfeat.p, ctx->D, ctx->Krow, ctx->lower,
-                ctx->cfg.emulate_text_roundtrip, ctx->d_Xh.p, ctx->d_Xl.p, ctx->d_xn.p);
+            const unsigned fblocks = (unsigned)((Wcap + 32 * HAF_FT_WT - 1) / (32 * HAF_FT_WT));
+            features_tc_kernel<<<fblocks, 256, ft_smem_bytes(ctx), st>>>(ctx->d_integral.p, ctx->d_win.p, cnt + 0, G, ubase, ctx->d_dimfeat.p, ctx->D,
+                                                                      ctx->Krow, (float)ctx->lower, ctx->cfg.emulate_text_roundtrip, ctx->d_Xh.p,
+                                                                      ctx->d_Xl.p, ctx->d_xn.p);
             LAUNCHED(ctx);
         } else if (ctx->cfg.svm_mode != HAF_SVM_FP64_EXACT) {
             features_kernel<false><<<wblocks32, 256, 0, st>>>(ctx->d_integral.p, ctx->d_win.p, cnt + 0, G, ubase, ctx->d_feats.p, ctx->d_dims.p,

@@ -406,105 +406,130 @@ __device__ __forceinline__ double pow10_table(int k) {
 // offsets / weights / flags AND the dimension's scaling constants in one 96-byte record, so one dependent-load-free
 // group of six 128-bit loads feeds a value (the dims -> feats indirection was the top stall of the first version).
 struct __align__(16) DimFeat {
-    int off[12];
+    int off[12];     // BYTE offsets of the corners; skipped regions: four identical corners (and weight +0.0)
     float w[3];
-    int flags;       // bit r: region r active; bit 8: SHAF; bit 9: constant dimension (value = cval); bit 10: dropped (value 0)
-    double fmin;
-    double slope;
-    double cval;
-    double pad;
+    int flags;       // bit 8: SHAF; bit 9: constant dimension (value = cval); bit 10: dropped (value 0)
+    float fmin, slope, cval, padf;   // float copies: the fast tier needs ~1e-7 only
+    double pad[2];
 };
 static_assert(sizeof(DimFeat) == 96, "DimFeat layout");
 
-// one value of the fast tier; I = integral image rows (shared or global), idx0 = index of the window's patch origin
-template <typename PtrT>
-__device__ __forceinline__ float fast_tier_value(PtrT I, int idx0, const DimFeat* __restrict__ table, int d, double lower,
-                                                 int emulate_text, const double* s_pw) {
+// one value of the fast tier; I = integral image rows (shared or global), idx0 = index of the window's patch origin.
+// Branch-free over regions: the host encodes a skipped region as four identical corners and weight +0.0, for which
+// ((P - P) - P) + P == +0.0 exactly, so the reference's "skip" (II2FV.cpp:155-159) and this uniform code give the same
+// float (a + (+0.0) == a, and the running sum is never -0.0).  All 12 loads can therefore be issued back to back.
+struct FastTab {       // decoded 96-byte DimFeat record
+    int off[12];
+    float w[3];
+    int flags;
+    float fmin, slope, cval;
+};
+__device__ __forceinline__ FastTab load_fast_tab(const DimFeat* __restrict__ table, int d) {
     const uint4* tp = reinterpret_cast<const uint4*>(table + d);
-    const uint4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2), t3 = __ldg(tp + 3), t4 = __ldg(tp + 4), t5 = __ldg(tp + 5);
-    const int flags = (int)t3.w;
-    if (flags & 0x600) return (flags & 0x400) ? 0.0f : (float)__hiloint2double((int)t5.y, (int)t5.x);
-    const int off[12] = {(int)t0.x, (int)t0.y, (int)t0.z, (int)t0.w, (int)t1.x, (int)t1.y, (int)t1.z, (int)t1.w,
-                         (int)t2.x, (int)t2.y, (int)t2.z, (int)t2.w};
-    const float wgt[3] = {__uint_as_float(t3.x), __uint_as_float(t3.y), __uint_as_float(t3.z)};
+    const uint4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2), t3 = __ldg(tp + 3), t4 = __ldg(tp + 4);
+    FastTab f;
+    f.off[0] = (int)t0.x; f.off[1] = (int)t0.y; f.off[2] = (int)t0.z; f.off[3] = (int)t0.w;
+    f.off[4] = (int)t1.x; f.off[5] = (int)t1.y; f.off[6] = (int)t1.z; f.off[7] = (int)t1.w;
+    f.off[8] = (int)t2.x; f.off[9] = (int)t2.y; f.off[10] = (int)t2.z; f.off[11] = (int)t2.w;
+    f.w[0] = __uint_as_float(t3.x); f.w[1] = __uint_as_float(t3.y); f.w[2] = __uint_as_float(t3.z);
+    f.flags = (int)t3.w;
+    f.fmin = __uint_as_float(t4.x); f.slope = __uint_as_float(t4.y); f.cval = __uint_as_float(t4.z);
+    return f;
+}
+struct SmemRows { uint32_t base; };  // 32-bit shared-window byte address of the staged integral rows
+__device__ __forceinline__ float load_corner(const float* I, int idx0, int off_bytes) {
+    return *reinterpret_cast<const float*>(reinterpret_cast<const char*>(I + idx0) + off_bytes);
+}
+__device__ __forceinline__ float load_corner(SmemRows I, int idx0_bytes, int off_bytes) {  // one IADD + LDS per corner
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(I.base + (uint32_t)(idx0_bytes + off_bytes)));
+    return v;
+}
+// idx0: element index of the window's patch origin for global rows, BYTE offset for staged rows; f.off[] are byte offsets
+template <typename PtrT>
+__device__ __forceinline__ float fast_tier_value(PtrT I, int idx0, const FastTab& f, float lower, int emulate_text,
+                                                 const double* s_pwd, const float* s_pwf) {
+    float c[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) c[k] = load_corner(I, idx0, f.off[k]);
     float rr[3];
 #pragma unroll
-    for (int r = 0; r < 3; r++) {
-        rr[r] = 0.0f;
-        if (flags & (1 << r)) {  // ((P[x2+1][y2+1] - P[x1][y2+1]) - P[x2+1][y1]) + P[x1][y1]   (II2FV.cpp:161-162)
-            const float rect = __fadd_rn(__fsub_rn(__fsub_rn(I[idx0 + off[4 * r]], I[idx0 + off[4 * r + 1]]), I[idx0 + off[4 * r + 2]]), I[idx0 + off[4 * r + 3]]);
-            rr[r] = __fmul_rn(wgt[r], rect);
-        }
+    for (int r = 0; r < 3; r++)  // ((P[x2+1][y2+1] - P[x1][y2+1]) - P[x2+1][y1]) + P[x1][y1]   (II2FV.cpp:161-162)
+        rr[r] = __fmul_rn(f.w[r], __fadd_rn(__fsub_rn(__fsub_rn(c[4 * r], c[4 * r + 1]), c[4 * r + 2]), c[4 * r + 3]));
+    const float haf = __fadd_rn(__fadd_rn(__fadd_rn(0.0f, rr[0]), rr[1]), rr[2]);
+    const float sa = __fsub_rn(rr[1], rr[0]), sb = __fsub_rn(rr[1], rr[2]);
+    const float shaf = (rr[1] > rr[0] && rr[1] > rr[2]) ? ((sb < sa) ? sb : sa) : -1.0f;  // II2FV.cpp:187-191
+    const float raw = (f.flags & 0x100) ? shaf : haf;
+    float v = raw;
+    if (emulate_text) {
+        // "%.4g": a * 10^(3-E) is formed and rounded in DOUBLE (exact ties stay exact; a mis-decided near-tie needs
+        // |frac - 0.5| < 1e-12); everything after the rounding decision only needs float accuracy here
+        const float a = fabsf(raw);
+        const int e2 = (int)((__float_as_uint(raw) >> 23) & 0xFFu) - 127;
+        int E = (e2 * 1233 - 3) >> 12;          // <= floor(log10 a), at most 2 too low
+        E = max(-37, min(36, E));
+        E += (a >= s_pwf[40 + E + 1]) ? 1 : 0;
+        E += (a >= s_pwf[40 + E + 1]) ? 1 : 0;
+        const float r = (float)rint((double)a * s_pwd[40 + 3 - E]);
+        const float vv = r * s_pwf[40 + E - 3];
+        v = (raw == 0.0f) ? 0.0f : copysignf(vv, raw);
     }
-    float raw;
-    if (!(flags & 0x100)) {  // HAF: adding the +0.0 of a skipped region is an exact identity (the sum is never -0.0)
-        raw = __fadd_rn(__fadd_rn(__fadd_rn(0.0f, rr[0]), rr[1]), rr[2]);
-    } else if (rr[1] > rr[0] && rr[1] > rr[2]) {  // SHAF (II2FV.cpp:187-191)
-        const float a = __fsub_rn(rr[1], rr[0]), b = __fsub_rn(rr[1], rr[2]);
-        raw = (b < a) ? b : a;
-    } else {
-        raw = -1.0f;
-    }
-    double v = (double)raw;
-    if (emulate_text && raw != 0.0f) {
-        const double a = fabs(v);
-        const int e2 = (int)((__float_as_uint(raw) >> 23) & 0xFFu) - 127;  // denormals read as 2^-127: E is fixed below
-        int E = (e2 * 1233 - 3) >> 12;                                    // <= floor(log10 a), at most 2 too low
-        E = max(-37, min(37, E));
-        E += (a >= s_pw[40 + E + 1]) ? 1 : 0;
-        E += (a >= s_pw[40 + E + 1]) ? 1 : 0;
-        const double r = rint(a * s_pw[40 + 3 - E]);                      // 4 significant digits
-        const double vv = r * s_pw[40 + E - 3];
-        v = raw < 0.0f ? -vv : vv;
-    }
-    const double fmin = __hiloint2double((int)t4.y, (int)t4.x), slope = __hiloint2double((int)t4.w, (int)t4.z);
-    return (float)fma(v - fmin, slope, lower);                            // svm-scale.c:344-346
+    const float x = fmaf(v - f.fmin, f.slope, lower);  // svm-scale.c:344-346
+    return (f.flags & 0x400) ? 0.0f : ((f.flags & 0x200) ? f.cval : x);
 }
 
 // Tensor-core variant: per-dimension values split into two bf16 terms and written K-major ([window][Krow], what the
-// UMMA K-major operand / TMA box wants).  The 32-window x Krow/2 tile is staged in shared memory so the global writes
-// are row-contiguous; the squared norm of the (hi + lo) representation is reduced on the way.
+// UMMA K-major operand / TMA box wants).  A (32*WT)-window x Krow/2 tile is staged in shared memory so the global
+// writes are row-contiguous; the squared norm of the (hi + lo) representation is reduced on the way.
 //
 // FAST TIER.  The values written here are rounded to 16 significant bits (bf16 hi + lo) anyway and every window whose
 // decision value lands inside the guard band is re-evaluated by svm_exact_kernel with the bit-exact emulation, so this
-// tier reproduces the text round trips only to ~1e-7: the "%.4g" rounding is decided in double (a * 10^p, rint: exact
-// ties stay exact, a mis-decided near-tie needs |frac - 0.5| < 1e-12), the division back and svm-scale's affine map
-// use one multiplication / FMA, and the 6-digit "%g" rounding (<= 5e-7 relative, below the 2^-17 operand precision)
-// is skipped.  Raw feature values are the same bit-exact floats as everywhere else.
+// tier reproduces the text round trips only to ~1e-7 (see fast_tier_value); the 6-digit "%g" rounding (<= 5e-7
+// relative, below the 2^-17 operand precision) is skipped.  Raw feature values are the same bit-exact floats as
+// everywhere else.  Each lane handles WT windows per table record, so the six 128-bit table loads are amortised.
 // (Tables in __constant__ memory were tried and were 1.8x SLOWER: 36 KB of tables thrash the constant cache.)
-__global__ void __launch_bounds__(256, 6) features_tc_kernel(const float* __restrict__ integral, const int2* __restrict__ win,
+#define HAF_FT_WT 2
+__global__ void __launch_bounds__(256, 4) features_tc_kernel(const float* __restrict__ integral, const int2* __restrict__ win,
                                                              const unsigned* __restrict__ win_count, int G, int unit_base,
-                                                             const DimFeat* __restrict__ table, int D, int Krow, double lower,
+                                                             const DimFeat* __restrict__ table, int D, int Krow, float lower,
                                                              int emulate_text, __nv_bfloat16* __restrict__ Xh,
                                                              __nv_bfloat16* __restrict__ Xl, float* __restrict__ xn) {
-    // The K range is processed in two passes so the staging tile is half as large (22 KB): more CTAs per SM -- the
-    // kernel is latency-bound on the table -> integral-image load chain.
-    extern __shared__ __nv_bfloat16 s_tile[];  // hi[32][KP+2] then lo[32][KP+2], KP = Krow / 2, then float s_int[ROWS][ld]
+    constexpr int WT = HAF_FT_WT, NW = 32 * WT;
+    extern __shared__ uint32_t s_words[];  // tile [NW][KP+1] of (hi | lo << 16), KP = Krow / 2; then float s_int[ROWS][ld]
     const unsigned W = *win_count;
-    if (blockIdx.x * 32 >= W) return;
+    const unsigned w0 = blockIdx.x * NW;
+    if (w0 >= W) return;
     const int lane = threadIdx.x & 31;
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // provably warp-uniform for the compiler
-    const unsigned w = blockIdx.x * 32 + lane;
-    const bool valid = w < W;
-    const int ld = G + 1, KP = Krow >> 1, rs = KP + 2;
-    __nv_bfloat16* s_hi = s_tile;
-    __nv_bfloat16* s_lo = s_tile + 32 * rs;
-    // The 32 windows of a CTA are consecutive entries of the window list: normally 2-3 adjacent grid rows of one unit.
-    // Their integral-image rows (row-7 .. row+7) are staged in shared memory (32-bit addressing, conflict-free for
-    // consecutive windows).  CTAs whose windows straddle units or too many rows read global memory instead.
-    float* s_int = reinterpret_cast<float*>(s_tile + 2 * 32 * rs);  // [HAF_FT_ROWS][ld]
-    __shared__ int s_box[3];  // unit, first row, rows (0 = no staging)
-    int2 uc = make_int2(0, 0);
-    int row = 7, col = 7;
-    if (valid) {
-        uc = win[w];
-        row = uc.y / G;
-        col = uc.y - row * G;
+    const int ld = G + 1, KP = Krow >> 1, rs = KP + 1;
+    float* s_int = reinterpret_cast<float*>(s_words + NW * rs);  // [HAF_FT_ROWS][ld]
+    __shared__ int s_box[3];       // unit, first row, rows (0 = no staging)
+    __shared__ double s_pwd[81];   // 10^(i-40)
+    __shared__ float s_pwf[81];
+    int unit[WT], row[WT], col[WT];
+    bool valid[WT];
+#pragma unroll
+    for (int t = 0; t < WT; t++) {
+        const unsigned w = w0 + t * 32 + lane;
+        valid[t] = w < W;
+        unit[t] = 0; row[t] = 7; col[t] = 7;
+        if (valid[t]) {
+            const int2 uc = win[w];
+            unit[t] = uc.x;
+            row[t] = uc.y / G;
+            col[t] = uc.y - row[t] * G;
+        }
     }
     if (threadIdx.x < 32) {
-        const int u0 = __shfl_sync(0xffffffffu, uc.x, 0);  // lane 0 is always valid
-        const bool same = __all_sync(0xffffffffu, !valid || uc.x == u0);
-        int rmin = valid ? row : 0x7fffffff, rmax = valid ? row : -1;
+        const int u0 = __shfl_sync(0xffffffffu, unit[0], 0);  // window w0 is always valid
+        bool same = true;
+        int rmin = 0x7fffffff, rmax = -1;
+#pragma unroll
+        for (int t = 0; t < WT; t++) {
+            same = same && (!valid[t] || unit[t] == u0);
+            if (valid[t]) { rmin = min(rmin, row[t]); rmax = max(rmax, row[t]); }
+        }
+        same = __all_sync(0xffffffffu, same);
 #pragma unroll
         for (int o = 16; o >= 1; o >>= 1) {
             rmin = min(rmin, __shfl_xor_sync(0xffffffffu, rmin, o));
@@ -517,48 +542,74 @@ __global__ void __launch_bounds__(256, 6) features_tc_kernel(const float* __rest
             s_box[2] = (same && nr <= HAF_FT_ROWS) ? nr : 0;
         }
     }
-    __shared__ double s_pw[81];  // 10^(i-40)
-    if (threadIdx.x < 81) s_pw[threadIdx.x] = pow10_table(threadIdx.x - 40);
+    if (threadIdx.x < 81) {
+        const double p = pow10_table(threadIdx.x - 40);
+        s_pwd[threadIdx.x] = p;
+        s_pwf[threadIdx.x] = (float)p;
+    }
     __syncthreads();
     const int nrows = s_box[2];
-    const float* gI = integral + (size_t)(uc.x - unit_base) * ld * ld;
-    int idx0 = (row - 7) * ld + (col - 7);
+    int idx0[WT];
+    const float* gI[WT];
+#pragma unroll
+    for (int t = 0; t < WT; t++) {
+        idx0[t] = (row[t] - 7) * ld + (col[t] - 7);
+        gI[t] = integral + (size_t)(unit[t] - unit_base) * ld * ld;
+    }
     if (nrows > 0) {
         const float* src = integral + (size_t)(s_box[0] - unit_base) * ld * ld + (size_t)s_box[1] * ld;
         for (int t = threadIdx.x; t < nrows * ld; t += blockDim.x) s_int[t] = src[t];
-        idx0 -= s_box[1] * ld;
+#pragma unroll
+        for (int t = 0; t < WT; t++) idx0[t] = valid[t] ? idx0[t] - s_box[1] * ld : 0;  // padding lanes read row 0 harmlessly
     }
-    float nrm[4] = {0.0f, 0.0f, 0.0f, 0.0f};  // squared-norm partials of the 4 windows this warp writes out
+    SmemRows srows;
+    srows.base = (uint32_t)__cvta_generic_to_shared(s_int);
+    float nrm[NW / 8];  // squared-norm partials of the windows this warp writes out
+#pragma unroll
+    for (int k = 0; k < NW / 8; k++) nrm[k] = 0.0f;
     for (int pass = 0; pass < 2; pass++) {
         const int d0 = pass * KP;
         __syncthreads();
         for (int dl = warp; dl < KP; dl += 8) {
             const int d = d0 + dl;
-            float xf = 0.0f;
-            if (d < D && valid) xf = (nrows > 0) ? fast_tier_value(s_int, idx0, table, d, lower, emulate_text, s_pw)
-                                                 : fast_tier_value(gI, idx0, table, d, lower, emulate_text, s_pw);
-            const __nv_bfloat16 hi = __float2bfloat16_rn(xf);
-            const __nv_bfloat16 lo = __float2bfloat16_rn(xf - __bfloat162float(hi));
-            s_hi[lane * rs + dl] = hi;
-            s_lo[lane * rs + dl] = lo;
+            float xf[WT];
+#pragma unroll
+            for (int t = 0; t < WT; t++) xf[t] = 0.0f;
+            if (d < D) {
+                const FastTab f = load_fast_tab(table, d);
+                if (nrows > 0) {
+#pragma unroll
+                    for (int t = 0; t < WT; t++) xf[t] = fast_tier_value(srows, idx0[t] * 4, f, lower, emulate_text, s_pwd, s_pwf);
+                } else {
+#pragma unroll
+                    for (int t = 0; t < WT; t++) xf[t] = valid[t] ? fast_tier_value(gI[t], idx0[t], f, lower, emulate_text, s_pwd, s_pwf) : 0.0f;
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < WT; t++) {
+                const __nv_bfloat16 hi = __float2bfloat16_rn(xf[t]);
+                const __nv_bfloat16 lo = __float2bfloat16_rn(xf[t] - __bfloat162float(hi));
+                s_words[(t * 32 + lane) * rs + dl] = (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16);
+            }
         }
         __syncthreads();
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
+        for (int k = 0; k < NW / 8; k++) {
             const int wi = warp + 8 * k;
-            const unsigned ww = blockIdx.x * 32 + wi;
+            const unsigned ww = w0 + wi;
             if (ww >= W) break;
-            const uint32_t* sh = reinterpret_cast<const uint32_t*>(s_hi + wi * rs);
-            const uint32_t* sl = reinterpret_cast<const uint32_t*>(s_lo + wi * rs);
+            const uint32_t* sw = s_words + wi * rs;
             uint32_t* gh = reinterpret_cast<uint32_t*>(Xh + (size_t)ww * Krow + d0);
             uint32_t* gl = reinterpret_cast<uint32_t*>(Xl + (size_t)ww * Krow + d0);
             float sq = nrm[k];
             for (int e = lane; e < KP / 2; e += 32) {
-                const uint32_t h2 = sh[e], l2 = sl[e];
+                const uint32_t a0 = sw[2 * e], a1 = sw[2 * e + 1];   // dims 2e, 2e+1: (hi | lo << 16)
+                const uint32_t h2 = __byte_perm(a0, a1, 0x5410);     // hi(2e) | hi(2e+1) << 16
+                const uint32_t l2 = __byte_perm(a0, a1, 0x7632);     // lo(2e) | lo(2e+1) << 16
                 gh[e] = h2;
                 gl[e] = l2;
-                const float v0 = __uint_as_float(h2 << 16) + __uint_as_float(l2 << 16);
-                const float v1 = __uint_as_float(h2 & 0xFFFF0000u) + __uint_as_float(l2 & 0xFFFF0000u);
+                const float v0 = __uint_as_float(a0 << 16) + __uint_as_float(a0 & 0xFFFF0000u);
+                const float v1 = __uint_as_float(a1 << 16) + __uint_as_float(a1 & 0xFFFF0000u);
                 sq = fmaf(v0, v0, sq);
                 sq = fmaf(v1, v1, sq);
             }
@@ -566,8 +617,8 @@ __global__ void __launch_bounds__(256, 6) features_tc_kernel(const float* __rest
         }
     }
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const unsigned ww = blockIdx.x * 32 + warp + 8 * k;
+    for (int k = 0; k < NW / 8; k++) {
+        const unsigned ww = w0 + warp + 8 * k;
         float sq = nrm[k];
 #pragma unroll
         for (int o = 16; o >= 1; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
