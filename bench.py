@@ -103,7 +103,7 @@ class ClockSampler:
             self.path = tempfile.mktemp(prefix="haf_clocks_", suffix=".csv")
             self.fh = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.fh,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.fh,
                                          stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -339,6 +339,16 @@ def run_ours(args):
         flops_per_window = info.n_sv * (2.0 * info.n_dims + 4.0)   # W*S*(2D+4)
         svm_tflops = (acc["windows"] / max(svm_launches, 1)) * flops_per_window / (svm_ms * 1e-3) / 1e12 if svm_ms > 0 else 0.0
         peak = tf_sust
+        kname = {0: "svm_rbf_simt_kernel", 1: "svm_exact_kernel", 2: "svm_rbf_tc2_kernel"}[args.svm_mode]
+        traffic = None
+        try:  # DRAM bytes of the dominant kernel from the committed ncu --set full capture, if it is the same launch size
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+                tr = json.load(fh).get(kname)
+            w_launch = acc["windows"] / max(svm_launches, 1)
+            if tr and tr["n_sv"] == info.n_sv and abs(tr["windows_per_launch"] - w_launch) <= 0.01 * w_launch:
+                traffic = tr["dram_bytes_per_launch"]
+        except Exception:
+            traffic = None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -354,9 +364,11 @@ def run_ours(args):
                     "stage_ms_per_step": {k: acc2[k] / args.steps for k in ("bin", "integral", "mask", "features", "svm", "guard", "score")},
                     "chunks_per_step": acc2["chunks"] / args.steps},
             "gpu_launches": int(acc["launches"]),
-            "roofline": {"kernel": {0: "svm_rbf_simt_kernel", 1: "svm_exact_kernel", 2: "svm_rbf_tc_kernel"}[args.svm_mode], "bound": "tensor",
+            "roofline": {"kernel": kname, "bound": "tensor",
                          "achieved": svm_tflops, "peak": peak, "unit": "TFLOP/s", "frac": svm_tflops / peak if peak else None,
-                         "traffic": None, "peak_source": src + " bf16 sustained (kernel timed inside a long step)",
+                         "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
+                         "algorithmic_bytes": 4.0 * info.n_dims * (acc["windows"] / max(svm_launches, 1) + info.n_sv) + 4.0 * acc["windows"] / max(svm_launches, 1),
+                         "peak_source": src + " bf16 sustained (kernel timed inside a long step)",
                          "algorithmic": "W*S*(2D+4) flop per launch, W=%.0f S=%d D=%d" % (acc["windows"] / max(svm_launches, 1), info.n_sv, info.n_dims),
                          "kernel_ms": svm_ms, "share_of_step": acc["svm"] / ms_dev if ms_dev else None,
                          "note": {0: "FP32 SIMT contraction (CUDA cores), measured against the bf16 tensor peak for comparability",
