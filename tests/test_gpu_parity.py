@@ -415,3 +415,30 @@ def test_roll_begin_shards_one_goal(pair_synth, clouds, hg, oracle_lib):
     assert (part["per_roll_top"][0][:5] == -1).all() and (part["per_roll_top"][0][9:] == -1).all()
     assert np.array_equal(part["graspseval"][0][5:9], full["graspseval"][0][5:9])
     assert part["best"].rolls_done == 4
+
+
+def test_full_size_batch_properties(hg, oracle_lib, tmp_models):
+    """BASELINE-size inputs (100k-point clouds, 2048 SVs), checked through size-independent properties:
+    (1) a batch equals the same clouds searched one by one, (2) the result does not depend on the order of the points
+    (max-z binning is order-free), (3) repeating a cloud inside the batch repeats its result, (4) a spot-checked
+    cloud equals the oracle."""
+    from haf_grasping_b200 import synth
+    model = tmp_models(2048)
+    gpu = hg.GraspSearch(FEATURES, RANGE, model, svm_mode=hg.HAF_SVM_TENSOR_GUARD)
+    try:
+        rng = np.random.default_rng(9)
+        cl = [synth.synth_cloud(1234 + i, 100000) for i in range(12)]
+        cl.append(cl[3].copy())                          # duplicate
+        cl.append(cl[5][rng.permutation(len(cl[5]))])    # same points, shuffled
+        best = gpu.search_batch(cl)
+        tup = [b.astuple() for b in best]
+        assert tup[12] == tup[3] and tup[13] == tup[5]
+        for i in (0, 5, 11):
+            assert gpu.search(cl[i], outputs=False)["best"].astuple() == tup[i]
+        dev_windows = [b.n_windows_scored for b in best]
+        assert dev_windows[12] == dev_windows[3] and dev_windows[13] == dev_windows[5]
+        o = oracle_lib.Oracle(FEATURES, RANGE, model)
+        ob = o.search(cl[0], oracle_lib.make_request(), full=False)["best"]
+        assert tup[0] == ob.astuple() and dev_windows[0] == ob.n_windows
+    finally:
+        gpu.close()
