@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="batch", choices=["batch", "grid512", "table1"])
+    ap.add_argument("--workload", default="batch", choices=["batch", "grid512", "table1", "approach"])
     ap.add_argument("--clouds", type=int, default=512, help="clouds per GPU (batch workload)")
     ap.add_argument("--points", type=int, default=100000)
     ap.add_argument("--nsv", type=int, default=2048)
@@ -75,6 +75,8 @@ def model_path(nsv):
 def workload_config(args):
     if args.workload == "batch":
         return dict(grid=56, rmax=190, step=15, area=(32.0, 44.0), r=0.28, n_clouds=args.clouds, n_points=args.points)
+    if args.workload == "approach":
+        return dict(grid=56, rmax=190, step=15, area=(32.0, 44.0), r=0.28, n_clouds=1, n_points=0)
     if args.workload == "grid512":  # BASELINE.json configs[3]
         return dict(grid=512, rmax=190, step=15, area=(362.0, 362.0), r=2.56, n_clouds=1, n_points=1000000)
     return dict(grid=56, rmax=190, step=15, area=(32.0, 44.0), r=0.28, n_clouds=1, n_points=0)
@@ -84,7 +86,7 @@ def make_clouds(args, wc, rank):
     """list of float32 [n,3] arrays for this rank (seeds 1234 + global cloud index)"""
     import numpy as np
     from haf_grasping_b200 import synth
-    if args.workload == "table1":
+    if args.workload in ("table1", "approach"):
         z = np.load(os.path.join(ROOT, "tests", "golden", "clouds.npz"))
         return [np.ascontiguousarray(z["table1"])]
     base = 1234 + rank * wc["n_clouds"]
@@ -239,6 +241,112 @@ def describe(args, wc):
     return "configs[1]: table1 scene (102876 points), G=56, 12 rolls, default request"
 
 
+TILTED = [(0.0, 0.0, 1.0), (0.5, 0.0, 0.8660254), (-0.5, 0.0, 0.8660254), (0.0, 0.5, 0.8660254), (0.0, -0.5, 0.8660254)]
+
+
+def run_approach(args):
+    """BASELINE configs[2]: one goal on the objects_1 (= table1) scene with 5 approach vectors x 12 rolls = 60 units,
+    sharded by (approach vector, roll) over the ranks; the per-unit tops are exchanged (NCCL all_reduce MAX) and the
+    reference's sequential rules replayed on the merged array.  Strong scaling (total work fixed).  Every rank also
+    checks the merged answer against its own unsharded search."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import haf_grasping_b200 as h
+    from haf_grasping_b200 import distributed as hd
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    model = model_path(args.nsv) if rank == 0 or world == 1 else None
+    if world > 1:
+        dist.barrier()
+        model = model_path(args.nsv)
+    xyz = np.ascontiguousarray(np.load(os.path.join(ROOT, "tests", "golden", "clouds.npz"))["table1"])
+    host = torch.empty((len(xyz), 3), dtype=torch.float32, pin_memory=True)
+    host.numpy()[:] = xyz
+    dev = host.cuda()
+    gs = h.GraspSearch(FEATURES, RANGE, model, device=local, svm_mode=args.svm_mode)
+    stream = torch.cuda.current_stream()
+    gs.set_stream(stream.cuda_stream)
+    R, A = gs.R, len(TILTED)
+    windows = [0]
+
+    def evaluate_on(buf):
+        def evaluate(a, rb, re):
+            res = gs.search(buf, [h.make_request(approach=TILTED[a], roll_begin=rb, roll_limit=re)], outputs=False)
+            windows[0] += gs.timing().n_windows
+            return res["per_roll_top"][0][rb:re]
+        return evaluate
+
+    def step(buf):
+        return hd.sharded_goal_search(evaluate_on(buf), A, R, [0] * A, [119] * A, rank, world)
+
+    ref = gs.search(dev, [h.make_request(approach=a) for a in TILTED], outputs=False)
+    per, overall, tops = step(dev)
+    assert overall[0] == ref["best"].approach_idx and overall[1:] == ref["best"].astuple()[:3] + (ref["best"].topval,), (overall, ref["best"].astuple())
+    assert np.array_equal(tops.reshape(A, R, 3), ref["per_roll_top"])
+
+    def timed(buf, steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        windows[0] = 0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            step(buf)
+        e1.record(stream)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        w = float(windows[0])
+        if world > 1:
+            t = torch.tensor([ms, w], dtype=torch.float64, device="cuda")
+            tm = t.clone()
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            ms, w = float(tm[0].item()), float(t[1].item())
+        return ms, w
+
+    for _ in range(max(args.warmup, 3)):
+        step(dev)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = gs.launch_count()
+    ms_dev, w_dev = timed(dev, args.steps)
+    launches = gs.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else {}
+    ms_e2e, w_e2e = timed(host.numpy(), args.steps)
+    if rank == 0:
+        line = {"metric": METRIC, "value": w_dev / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": DTYPES[args.svm_mode], "data": "tests/golden/clouds.npz:table1 (= data/objects_1.pcd of the reference)",
+                "config": {"workload": "configs[2]: objects_1 scene x 5 approach vectors x 12 rolls = 60 units sharded by (approach vector, roll) over the ranks; "
+                                       "merged best grasp verified against the unsharded search on every rank",
+                           "n_sv": gs.info.n_sv, "l2": "single goal: latency-bound, working set far below L2 (no flush: that is the operating point of one goal)",
+                           "units_per_rank": [sum(re - rb for _, rb, re in hd.unit_blocks(A, R, r, world)) for r in range(world)]},
+                "ms_per_goal": ms_dev / args.steps, "clocks": clocks,
+                "e2e": {"value": w_e2e / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(len(xyz) * 12 * len(hd.unit_blocks(A, R, 0, world))),
+                        "d2h_bytes_per_step": A * R * 12, "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": int(launches),
+                "roofline": {"kernel": "svm_rbf_tc2_kernel", "bound": "tensor", "achieved": None, "peak": peaks()[2], "unit": "TFLOP/s", "frac": None,
+                             "traffic": None, "note": "latency-bound single goal: see the default (batch) workload for the roofline of this kernel"}}
+        emit(line)
+    gs.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+DTYPES = {0: "f32", 1: "f64", 2: "f32 (contraction: split-bf16 x3 on tensor cores, f32 accumulate; f64 guard band)"}
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -352,7 +460,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {0: "f32", 1: "f64", 2: "bf16x2-split/f32-accumulate"}[args.svm_mode], "data": "synthetic",
+            "dtype": DTYPES[args.svm_mode], "data": "synthetic",
             "config": {"workload": describe(args, wc), "n_sv": info.n_sv, "n_dims": info.n_dims, "grid": info.grid,
                        "rolls": info.n_rolls, "clouds_per_gpu": n_clouds, "windows_per_step_per_gpu": W_step,
                        "svm_mode": args.svm_mode, "l2": "inputs (%.0f MB per GPU per step) larger than L2, no flush" % (total_pts * 12 / 1e6),
@@ -415,6 +523,8 @@ def main():
     protect_stdout()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "approach":
+        run_approach(args)
     else:
         run_ours(args)
 
