@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--clouds", type=int, default=512, help="clouds per GPU (batch workload)")
     ap.add_argument("--points", type=int, default=100000)
     ap.add_argument("--nsv", type=int, default=2048)
-    ap.add_argument("--svm-mode", type=int, default=2, help="0 FP32 SIMT + guard, 1 FP64 exact, 2 tcgen05 split-bf16 + guard")
+    ap.add_argument("--svm-mode", type=int, default=0, help="0 tcgen05 split-bf16 + FP64 guard (default), 1 FP64 exact, 2 FP32 SIMT + guard")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-clouds", type=int, default=2)
     return ap.parse_args()
@@ -344,7 +344,7 @@ def run_approach(args):
         dist.destroy_process_group()
 
 
-DTYPES = {0: "f32", 1: "f64", 2: "f32 (contraction: split-bf16 x3 on tensor cores, f32 accumulate; f64 guard band)"}
+DTYPES = {2: "f32", 1: "f64", 0: "f32 (contraction: split-bf16 x3 on tensor cores, f32 accumulate; f64 guard band)"}
 
 
 def run_ours(args):
@@ -447,7 +447,7 @@ def run_ours(args):
         flops_per_window = info.n_sv * (2.0 * info.n_dims + 4.0)   # W*S*(2D+4)
         svm_tflops = (acc["windows"] / max(svm_launches, 1)) * flops_per_window / (svm_ms * 1e-3) / 1e12 if svm_ms > 0 else 0.0
         peak = tf_sust
-        kname = {0: "svm_rbf_simt_kernel", 1: "svm_exact_kernel", 2: "svm_rbf_tc2_kernel"}[args.svm_mode]
+        kname = {2: "svm_rbf_simt_kernel", 1: "svm_exact_kernel", 0: "svm_rbf_tc2_kernel"}[args.svm_mode]
         traffic = None
         try:  # DRAM bytes of the dominant kernel from the committed ncu --set full capture, if it is the same launch size
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
@@ -479,8 +479,8 @@ def run_ours(args):
                          "peak_source": src + " bf16 sustained (kernel timed inside a long step)",
                          "algorithmic": "W*S*(2D+4) flop per launch, W=%.0f S=%d D=%d" % (acc["windows"] / max(svm_launches, 1), info.n_sv, info.n_dims),
                          "kernel_ms": svm_ms, "share_of_step": acc["svm"] / ms_dev if ms_dev else None,
-                         "note": {0: "FP32 SIMT contraction (CUDA cores), measured against the bf16 tensor peak for comparability",
-                                  1: "FP64 exact-order path", 2: "algorithmic flops; the split-bf16 scheme issues 3 tensor-core MMAs per algorithmic MMA, "
+                         "note": {2: "FP32 SIMT contraction (CUDA cores), measured against the bf16 tensor peak for comparability",
+                                  1: "FP64 exact-order path", 0: "algorithmic flops; the split-bf16 scheme issues 3 tensor-core MMAs per algorithmic MMA, "
                                   "so frac <= 1/3 by construction (hardware tensor utilisation = 3 x frac x Kpad/D)"}[args.svm_mode]},
             "stage_ms_per_step": {k: acc[k] / args.steps for k in ("bin", "integral", "mask", "features", "svm", "guard", "score")},
             "guard_windows_per_step": acc["guardw"] / args.steps,

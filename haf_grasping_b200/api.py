@@ -12,9 +12,9 @@ import numpy as np
 
 from . import build as _build
 
-HAF_SVM_FP32_GUARD = 0
+HAF_SVM_TENSOR_GUARD = 0
 HAF_SVM_FP64_EXACT = 1
-HAF_SVM_TENSOR_GUARD = 2
+HAF_SVM_FP32_GUARD = 2
 
 
 class HafError(RuntimeError):
@@ -144,7 +144,7 @@ class GraspSearch:
     action server is configured with (server.cpp:218-225), then ``search`` per goal."""
 
     def __init__(self, features_path, range_path, model_path, grid=56, roll_step_deg=15, roll_max_deg=190,
-                 nr_features_without_shaf=302, device=0, emulate_text_roundtrip=True, svm_mode=HAF_SVM_FP32_GUARD,
+                 nr_features_without_shaf=302, device=0, emulate_text_roundtrip=True, svm_mode=HAF_SVM_TENSOR_GUARD,
                  guard_rel=0.0, tc_variant=0):
         self.L = load_library()
         cfg = haf_config()

@@ -38,10 +38,10 @@ extern "C" {
 
 typedef struct haf_ctx haf_ctx;
 
-/* svm_mode */
-#define HAF_SVM_FP32_GUARD 0 /* FP32 SIMT contraction, FP64 exact-order re-evaluation inside the guard band */
-#define HAF_SVM_FP64_EXACT 1 /* every window in FP64, libsvm's summation order (svm.cpp:326-365, :2500-2514) */
-#define HAF_SVM_TENSOR_GUARD 2 /* tcgen05 split-bf16 contraction + the same FP64 guard band */
+/* svm_mode (0 = what a zero-initialised config gets = the production path) */
+#define HAF_SVM_TENSOR_GUARD 0 /* tcgen05 split-bf16 contraction in TMEM + FP64 exact-order re-evaluation inside the guard band */
+#define HAF_SVM_FP64_EXACT 1   /* every window in FP64, libsvm's summation order (svm.cpp:326-365, :2500-2514) */
+#define HAF_SVM_FP32_GUARD 2   /* FP32 SIMT contraction (CUDA cores) + the same FP64 guard band; conservative mode */
 
 typedef struct {
     const char* features_path; /* data/Features.txt               (server param feature_file_path, :218-219) */

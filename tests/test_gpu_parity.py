@@ -140,7 +140,8 @@ def pair_trained(hg, oracle_lib, trained_model):
 
 @pytest.fixture(scope="module")
 def pair_synth(hg, oracle_lib, tmp_models):
-    p = Pair(hg, oracle_lib, tmp_models(256))
+    """synthetic 256-SV model on the FP32 SIMT mode (the bundled-PCD / trained-model tests run the default tensor mode)"""
+    p = Pair(hg, oracle_lib, tmp_models(256), svm_mode=hg.HAF_SVM_FP32_GUARD)
     yield p
     p.close()
 
@@ -254,10 +255,11 @@ def test_tensor_core_mode_synth_models_and_batch(hg, oracle_lib, tmp_models):
             p.close()
 
 
-def test_guard_band_catches_near_zero_decisions(hg, oracle_lib, tmp_models, clouds):
+@pytest.mark.parametrize("mode", ["tensor", "simt"])
+def test_guard_band_catches_near_zero_decisions(hg, oracle_lib, tmp_models, clouds, mode):
     """rho chosen so that many decision values sit next to 0: labels must still equal the oracle's."""
     model = tmp_models(256, rho=-0.2972253)  # a decision value of pcd2 / roll 0 with the synth model is -0.2972253033...
-    p = Pair(hg, oracle_lib, model, guard_rel=1e-3)
+    p = Pair(hg, oracle_lib, model, guard_rel=1e-3, svm_mode=hg.HAF_SVM_TENSOR_GUARD if mode == "tensor" else hg.HAF_SVM_FP32_GUARD)
     try:
         _, _, guard = check_search(p, clouds["pcd2"], hg, oracle_lib, model)
         assert guard.sum() > 0

@@ -12,7 +12,7 @@ off = np.concatenate([[0], np.cumsum([len(c) for c in clouds])]).astype(np.int64
 host = torch.empty((int(off[-1]), 3), dtype=torch.float32, pin_memory=True)
 host.numpy()[:] = np.concatenate(clouds)
 dev = host.cuda()
-gs = h.GraspSearch(F, R, model, svm_mode=2)
+gs = h.GraspSearch(F, R, model, svm_mode=h.HAF_SVM_TENSOR_GUARD)
 st = torch.cuda.current_stream(); print("stream handle", st.cuda_stream)
 gs.set_stream(st.cuda_stream)
 rq = h.make_request()
