@@ -388,6 +388,7 @@ extern "C" int haf_create(haf_ctx** out, const haf_config* cfg) {
     CREATE_TRY(cudaFuncSetAttribute(svm_rbf_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SVM_STAGES * SVM_BK * (SVM_BM + SVM_BN) * 4));
     CREATE_TRY(cudaFuncSetAttribute(integral_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CREATE_TRY(cudaFuncSetAttribute(svm_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CREATE_TRY(cudaFuncSetAttribute(bin_maxz_cloud_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     if (cfg->svm_mode == HAF_SVM_TENSOR_GUARD) {
         const int Krow = (int)round_up((size_t)Dsv, 16);
         const int SpadT = (int)round_up((size_t)S, haftc::BN);
@@ -696,14 +697,30 @@ static int run_jobs(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& jobs, fl
             const size_t n = (size_t)Uc * GG;
             fill_u32_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 16), 256, 0, st>>>(ctx->d_keys.p, n, HAF_KEY_MINUS_ONE);
             LAUNCHED(ctx);
-            const int PPT = 4;
-            dim3 grid((unsigned)((max_points + 256 * PPT - 1) / (256 * PPT)), (unsigned)(c1 - c0));
-            if (grid.x > 0) {
-                // cloud_unit_begin is relative to unit 0 of the call: shift the key base so unit u lands at keys[u - ubase]
-                bin_maxz_kernel<PPT><<<grid, 256, 0, st>>>(cs.d_xyz, cs.stride, d_ptoff + c0, d_cloud_ubegin + c0, d_units,
-                                                           ctx->d_keys.p - (size_t)ubase * GG, G, r, nullptr,
-                                                           reinterpret_cast<unsigned long long*>(cnt + 4));
+            // small grids with enough points per cloud: whole-cloud CTAs with shared-memory lower bounds (fewer REDs)
+            const int upg = std::min(16, (int)((200 * 1024) / ((size_t)GG * 4)));
+            const long long avg_points = (cs.off[c1] - cs.off[c0]) / std::max(1, c1 - c0);
+            if (upg >= 1 && avg_points >= 8 * (long long)GG && (c1 - c0) * 8 >= ctx->sm_count && !ctx->cfg.reserved[1]) {
+                int max_units_per_cloud = 0;
+                for (int c = c0; c < c1; c++) max_units_per_cloud = std::max(max_units_per_cloud, hub[c + 1] - hub[c]);
+                const int ug = std::min(upg, std::max(1, max_units_per_cloud));
+                // measured: the kernel is instruction-bound once the REDs are filtered; 1 slice at 256 clouds, 2-4 at 64
+                const int slices = std::max(1, std::min(8, (3 * ctx->sm_count / 2 + (c1 - c0) - 1) / (c1 - c0)));
+                dim3 gridc((unsigned)(c1 - c0), (unsigned)((max_units_per_cloud + ug - 1) / ug), (unsigned)slices);
+                bin_maxz_cloud_kernel<<<gridc, 1024, (size_t)ug * GG * 4, st>>>(cs.d_xyz, cs.stride, d_ptoff + c0, d_cloud_ubegin + c0, d_units,
+                                                                              ctx->d_keys.p - (size_t)ubase * GG, G, r, ug,
+                                                                              reinterpret_cast<unsigned long long*>(cnt + 4));
                 LAUNCHED(ctx);
+            } else {
+                const int PPT = 4;
+                dim3 grid((unsigned)((max_points + 256 * PPT - 1) / (256 * PPT)), (unsigned)(c1 - c0));
+                if (grid.x > 0) {
+                    // cloud_unit_begin is relative to unit 0 of the call: shift the key base so unit u lands at keys[u - ubase]
+                    bin_maxz_kernel<PPT><<<grid, 256, 0, st>>>(cs.d_xyz, cs.stride, d_ptoff + c0, d_cloud_ubegin + c0, d_units,
+                                                               ctx->d_keys.p - (size_t)ubase * GG, G, r, nullptr,
+                                                               reinterpret_cast<unsigned long long*>(cnt + 4));
+                    LAUNCHED(ctx);
+                }
             }
         }
         // 2. integral image

@@ -127,6 +127,69 @@ __global__ void __launch_bounds__(256) bin_maxz_kernel(const unsigned char* __re
     }
 }
 
+// Small-grid variant: one CTA walks a whole cloud and keeps, per unit grid, a shared-memory array of LOWER BOUNDS of the
+// cell maxima.  The binning is bound by the issue rate of scattered REDG (~0.75 lanes/clk/SM, profiles/); a point whose
+// key does not beat the bound cannot change the global cell and skips its RED.  The bound is maintained with plain
+// (racy) shared loads/stores: whatever value survives a race was also sent to global memory by its writer, so it never
+// exceeds the true maximum and skipping stays safe; with ~30 points per cell only the few running maxima reach L2.
+// grid = (n_clouds, unit groups, slices of the cloud), block = 1024, dynamic smem = units_per_group * G * G * 4 bytes.
+__global__ void __launch_bounds__(1024, 1) bin_maxz_cloud_kernel(const unsigned char* __restrict__ xyz, size_t stride_bytes,
+                                                                 const long long* __restrict__ pt_off,
+                                                                 const int* __restrict__ cloud_unit_begin,
+                                                                 const UnitParams* __restrict__ units,
+                                                                 unsigned* __restrict__ grid_keys, int G, float r, int units_per_group,
+                                                                 unsigned long long* __restrict__ clamp_count) {
+    extern __shared__ unsigned s_bound[];  // [units_per_group][G*G]
+    __shared__ float sM[16][12];
+    __shared__ int sActive[16];
+    const int c = blockIdx.x;
+    long long p0 = pt_off[c], p1 = pt_off[c + 1];
+    {   // blockIdx.z: contiguous slice of the cloud (several CTAs per cloud when there are few clouds)
+        const long long per = (p1 - p0 + gridDim.z - 1) / gridDim.z;
+        p0 = p0 + per * blockIdx.z;
+        p1 = min(p1, p0 + per);
+    }
+    const int ub = cloud_unit_begin[c] + blockIdx.y * units_per_group;
+    const int ue = min(cloud_unit_begin[c + 1], ub + units_per_group);
+    if (ub >= ue || p0 >= p1) return;
+    const int nu = ue - ub, GG = G * G;
+    for (int t = threadIdx.x; t < nu * GG; t += blockDim.x) s_bound[t] = HAF_KEY_MINUS_ONE;
+    for (int t = threadIdx.x; t < nu * 12; t += blockDim.x) sM[t / 12][t % 12] = units[ub + t / 12].M[t % 12];
+    for (int t = threadIdx.x; t < nu; t += blockDim.x) sActive[t] = units[ub + t].cloud >= 0;
+    __syncthreads();
+    const float nr = -r;
+    for (long long p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
+        const float* q = reinterpret_cast<const float*>(xyz + (size_t)p * stride_bytes);
+        const float x = __ldg(q), y = __ldg(q + 1), z = __ldg(q + 2);
+        for (int u = 0; u < nu; u++) {
+            if (!sActive[u]) continue;
+            const float* m = sM[u];
+            // pcl::transformPointCloud, left-to-right float arithmetic, no FMA (server.cpp:488)
+            const float tx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[0], x), __fmul_rn(m[1], y)), __fmul_rn(m[2], z)), m[3]);
+            const float ty = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[4], x), __fmul_rn(m[5], y)), __fmul_rn(m[6], z)), m[7]);
+            if (tx > nr && tx < r && ty > nr && ty < r) {  // strict (server.cpp:510-511); false for NaN
+                int ix = (int)floorf(__fmul_rn(100.0f, __fadd_rn(tx, r)));  // :513
+                int iy = (int)floorf(__fmul_rn(100.0f, __fadd_rn(ty, r)));  // :514
+                if (ix < 0 || ix > G - 1 || iy < 0 || iy > G - 1) {
+                    atomicAdd(clamp_count, 1ull);
+                    ix = max(0, min(G - 1, ix));
+                    iy = max(0, min(G - 1, iy));
+                }
+                const int cell = ix * G + iy;
+                const float tz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[8], x), __fmul_rn(m[9], y)), __fmul_rn(m[10], z)), m[11]);
+                if (tz > -1.0f) {
+                    const unsigned key = fkey(tz);
+                    volatile unsigned* b = s_bound + u * GG + cell;
+                    if (key > *b) {
+                        *b = key;
+                        atomicMax(grid_keys + (size_t)(ub + u) * GG + cell, key);
+                    }
+                }
+            }
+        }
+    }
+}
+
 // decode a key to the final height: cells never hit stay -1 -> "< -0.99 -> 0" (server.cpp:522-528, compare in double)
 __device__ __forceinline__ float key_to_height(unsigned k) {
     float h = fkey_inv(k);

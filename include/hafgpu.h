@@ -55,7 +55,8 @@ typedef struct {
     int emulate_text_roundtrip; /* 1 = reproduce the "%.4g" / "%g" text round trips (reference-exact)         */
     int svm_mode;              /* HAF_SVM_*                                                                   */
     float guard_rel;           /* guard band half-width as a fraction of sum_i |coef_i| K_i; <=0 -> default   */
-    int reserved[4];           /* [0]: tensor-path kernel variant, 0 = CTA-pair (cta_group::2, default), 1 = single CTA */
+    int reserved[4];           /* [0]: tensor-path kernel variant, 0 = CTA-pair (cta_group::2, default), 1 = single CTA;
+                                  [1]: 1 = always use the point-parallel binning kernel (no whole-cloud CTAs) */
 } haf_config;
 
 /* One grasp goal = the hot-path fields of GraspInput (msg/GraspInput.msg:3-15). */
