@@ -387,7 +387,7 @@ extern "C" int haf_create(haf_ctx** out, const haf_config* cfg) {
     CREATE_TRY(cudaMemcpy(ctx->d_coef64.p, coef64.data(), Spad * sizeof(double), cudaMemcpyHostToDevice));
     CREATE_TRY(cudaFuncSetAttribute(svm_rbf_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SVM_STAGES * SVM_BK * (SVM_BM + SVM_BN) * 4));
     CREATE_TRY(cudaFuncSetAttribute(integral_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CREATE_TRY(cudaFuncSetAttribute(svm_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CREATE_TRY(cudaFuncSetAttribute(svm_exact_terms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CREATE_TRY(cudaFuncSetAttribute(bin_maxz_cloud_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     if (cfg->svm_mode == HAF_SVM_TENSOR_GUARD) {
         const int Krow = (int)round_up((size_t)Dsv, 16);
@@ -533,19 +533,31 @@ bool is_device_ptr(const void* p) {
 static size_t ft_smem_bytes(const haf_ctx* ctx) {
     return (size_t)32 * HAF_FT_WT * (ctx->Krow / 2 + 1) * 4 + (size_t)HAF_FT_ROWS * (ctx->G + 1) * 4;
 }
-static size_t exact_smem_bytes(const haf_ctx* ctx) {
-    const size_t base = (size_t)HAF_EXACT_WB * ctx->Dsv * sizeof(double);
-    const size_t with_kv = (size_t)(ctx->Dsv + ctx->Spad) * sizeof(double);
-    return (with_kv <= 96 * 1024) ? std::max(base, with_kv) : base;
+static size_t exact_smem_bytes(const haf_ctx* ctx) { return (size_t)HAF_EXACT_WB * ctx->Dsv * sizeof(double); }
+// launches the two phases of the FP64 exact-order path on stream st
+static int launch_exact(haf_ctx* ctx, ExactArgs a, cudaStream_t st, size_t max_windows) {
+    const int slices = (ctx->S + HAF_EXACT_SLICE - 1) / HAF_EXACT_SLICE;
+    // all-windows mode (list == NULL) walks the windows in passes of max_entries; guard mode is a single pass
+    const size_t passes = a.list ? 1 : (max_windows + a.max_entries - 1) / (size_t)a.max_entries;
+    for (size_t p = 0; p < passes; p++) {
+        a.entry_begin = (int)(p * (size_t)a.max_entries);
+        svm_exact_terms_kernel<<<dim3((unsigned)(ctx->sm_count * 2), (unsigned)slices), 256, exact_smem_bytes(ctx), st>>>(a);
+        LAUNCHED(ctx);
+        svm_exact_sum_kernel<<<ctx->sm_count * 4, 128, 0, st>>>(a);
+        LAUNCHED(ctx);
+    }
+    return HAF_OK;
 }
 static ExactArgs make_exact_args(haf_ctx* ctx, const int* list, const unsigned* list_count, unsigned* cnt, int G, int ubase) {
     ExactArgs a;
     a.list = list; a.list_count = list_count; a.win_count = cnt + 0; a.integral = ctx->d_integral.p; a.win = ctx->d_win.p;
     a.G = G; a.unit_base = ubase; a.feats = ctx->d_feats.p; a.dims = ctx->d_dims.p; a.D = ctx->D; a.lower = ctx->lower; a.upper = ctx->upper;
     a.emulate_text = ctx->cfg.emulate_text_roundtrip; a.sv64T = ctx->d_sv64T.p; a.Spad = ctx->Spad; a.S = ctx->S; a.Dsv = ctx->Dsv;
-    a.coef64 = ctx->d_coef64.p; a.gamma = ctx->gamma; a.rho = ctx->rho; a.kscratch = ctx->d_kscratch.p; a.dec = ctx->d_dec.p;
+    a.coef64 = ctx->d_coef64.p; a.gamma = ctx->gamma; a.rho = ctx->rho; a.terms = ctx->d_kscratch.p; a.dec = ctx->d_dec.p;
     a.unsupported_flag = (int*)(cnt + 3);
-    a.kv_in_smem = exact_smem_bytes(ctx) >= (size_t)(ctx->Dsv + ctx->Spad) * sizeof(double) ? 1 : 0;
+    a.max_entries = (int)std::min<size_t>(ctx->d_kscratch.cap / (size_t)ctx->Spad, 0x7fffffff);
+    a.entry_begin = 0;
+    a.overflow_flag = list ? (int*)(cnt + 10) : nullptr;   // guard mode: one launch must cover the whole list
     return a;
 }
 
@@ -680,8 +692,10 @@ static int run_jobs(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& jobs, fl
         else if (ctx->cfg.svm_mode == HAF_SVM_FP32_GUARD) ENSURE(ctx, ctx->d_X, (size_t)ctx->Kpad * ldx);
         ENSURE(ctx, ctx->d_dec, ldx); ENSURE(ctx, ctx->d_guardflag, ldx); ENSURE(ctx, ctx->d_guardlist, ldx);
         if (!smallG) ENSURE(ctx, ctx->d_rowscan, (size_t)Uc * GG);
-        const int exact_ctas = ctx->sm_count * 4;
-        ENSURE(ctx, ctx->d_kscratch, (size_t)exact_ctas * HAF_EXACT_WB * ctx->Spad);
+        // terms scratch of the exact path: one row of Spad doubles per entry; the guard list is bounded by what fits in 1 GiB
+        // (a guard band wider than that means a mis-configured guard_rel: the call then fails loudly below)
+        const size_t exact_cap = std::min<size_t>(ldx, std::max<size_t>(4096, ((size_t)1 << 30) / ((size_t)ctx->Spad * 8)));
+        ENSURE(ctx, ctx->d_kscratch, exact_cap * ctx->Spad);
         unsigned* cnt = ctx->d_counters.p;
         if (ci > 0) CUDA_TRY(ctx, cudaMemsetAsync(cnt, 0, 2 * 4, st));  // win_count, guard_count
         const UnitParams* units_c = d_units + ubase;
@@ -760,8 +774,7 @@ static int run_jobs(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& jobs, fl
         if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[ci * 8 + 4], st));
         if (ctx->cfg.svm_mode == HAF_SVM_FP64_EXACT) {
             CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_guardflag.p, 0, ldx, st));
-            svm_exact_kernel<<<exact_ctas, 256, exact_smem_bytes(ctx), st>>>(make_exact_args(ctx, nullptr, nullptr, cnt, G, ubase));
-            LAUNCHED(ctx);
+            { int rce = launch_exact(ctx, make_exact_args(ctx, nullptr, nullptr, cnt, G, ubase), st, Wcap); if (rce) return rce; }
             if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[ci * 8 + 5], st));
         } else if (tc) {
             CUtensorMap tmXh, tmXl;
@@ -794,16 +807,14 @@ static int run_jobs(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& jobs, fl
                                                                                        ctx->d_guardflag.p, ctx->d_guardlist.p, cnt + 1);
             LAUNCHED(ctx);
             if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[ci * 8 + 5], st));
-            svm_exact_kernel<<<exact_ctas, 256, exact_smem_bytes(ctx), st>>>(make_exact_args(ctx, ctx->d_guardlist.p, cnt + 1, cnt, G, ubase));
-            LAUNCHED(ctx);
+            { int rce = launch_exact(ctx, make_exact_args(ctx, ctx->d_guardlist.p, cnt + 1, cnt, G, ubase), st, Wcap); if (rce) return rce; }
         } else {
             svm_rbf_simt_kernel<<<(unsigned)(ldx / SVM_BM), 256, SVM_STAGES * SVM_BK * (SVM_BM + SVM_BN) * 4, st>>>(
                 ctx->d_X.p, ldx, ctx->d_svT.p, ctx->Spad, ctx->Kpad, ctx->d_xn.p, ctx->d_svn.p, ctx->d_coef.p, neg_gamma_log2e, ctx->rho,
                 ctx->guard_rel, cnt + 0, ctx->d_dec.p, ctx->d_guardflag.p, ctx->d_guardlist.p, cnt + 1);
             LAUNCHED(ctx);
             if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[ci * 8 + 5], st));
-            svm_exact_kernel<<<exact_ctas, 256, exact_smem_bytes(ctx), st>>>(make_exact_args(ctx, ctx->d_guardlist.p, cnt + 1, cnt, G, ubase));
-            LAUNCHED(ctx);
+            { int rce = launch_exact(ctx, make_exact_args(ctx, ctx->d_guardlist.p, cnt + 1, cnt, G, ubase), st, Wcap); if (rce) return rce; }
         }
         // 6. labels -> grids, score stencil, argmax, tie rule
         if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[ci * 8 + 6], st));
@@ -845,6 +856,7 @@ static int run_jobs(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& jobs, fl
     total_windows = ctx->h_counters.p[8];
     total_guard = ctx->h_counters.p[9];
     if (ctx->h_counters.p[2]) return ctx->fail(HAF_ERR_UNSUPPORTED, "window list overflow (internal bound too small)");
+    if (ctx->h_counters.p[10]) return ctx->fail(HAF_ERR_UNSUPPORTED, "the guard band holds more windows than the exact path is provisioned for (guard_rel too wide for this model)");
     if (ctx->h_counters.p[3]) return ctx->fail(HAF_ERR_UNSUPPORTED, "a feature value fell outside the range the decimal text emulation reproduces exactly");
     float ms_total = 0;
     cudaEventElapsedTime(&ms_total, ctx->ev[8], ctx->ev[9]);

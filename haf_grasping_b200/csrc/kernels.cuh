@@ -855,25 +855,31 @@ __global__ void __launch_bounds__(256, 2) svm_rbf_simt_kernel(const float* __res
 // exact), then ONE thread sums coef_i * K_i in file order and subtracts rho (svm.cpp:2500-2514).
 // list == NULL: all windows (HAF_SVM_FP64_EXACT).  grid-stride over the list; kscratch: [gridDim.x][Spad].
 // ---------------------------------------------------------------------------------------------------
-#define HAF_EXACT_WB 8   // windows evaluated together by one CTA: every support-vector element is loaded once per 8 windows
+#define HAF_EXACT_WB 8     // windows evaluated together by one CTA: every support-vector element is loaded once per 8 windows
+#define HAF_EXACT_SVT 2    // support vectors per thread (register tile WB x SVT)
+#define HAF_EXACT_SLICE (256 * HAF_EXACT_SVT)   // support vectors per CTA
 struct ExactArgs {
     const int* list; const unsigned* list_count; const unsigned* win_count; const float* integral; const int2* win;
     int G, unit_base; const FeatDev* feats; const DimDev* dims; int D; double lower, upper; int emulate_text;
-    const double* sv64T; int Spad, S, Dsv; const double* coef64; double gamma, rho; double* kscratch; double* dec;
+    const double* sv64T; int Spad, S, Dsv; const double* coef64; double gamma, rho; double* terms; double* dec;
     int* unsupported_flag;
-    int kv_in_smem;   // 1: the latency variant (WB = 1) keeps coef_i*K_i in shared memory (dynamic smem holds Dsv + S doubles)
+    int* overflow_flag;   // set when the list holds more entries than this launch covers (guard mode: one launch only)
+    int entry_begin;      // this launch covers list entries [entry_begin, entry_begin + max_entries)
+    int max_entries;      // capacity of `terms` in windows
 };
-// WB windows per CTA pass.  WB = 8 for long lists (throughput: each SV element is read once per 8 windows), WB = 1 when
-// the list is shorter than the grid (latency: a single goal has only a handful of guard-band windows).
+// Phase 1: terms[e][i] = coef_i * K_i for list entry e (window list[e], or window e when list == NULL).
+// grid = (window blocks, SV slices).  x is re-derived in double from the integral image with the bit-exact emulation of
+// both text round trips; K_i = exp(-gamma * sum_d (x_d - sv_i,d)^2) with the d loop sequential and un-fused
+// (Kernel::k_function, svm.cpp:326-365: absent entries are zeros, adding 0.0 is exact).  WB = 8 windows share every SV
+// element (throughput); WB = 1 spreads a short list over many CTAs (latency of a single goal).
 template <int WB>
-__device__ __forceinline__ void svm_exact_body(const ExactArgs& A, double* xs, unsigned n) {
+__device__ __forceinline__ void svm_exact_terms_body(const ExactArgs& A, double* xs, unsigned n) {
     const int ld = A.G + 1, Dsv = A.Dsv, Spad = A.Spad;
-    // [WB][Spad]; the single thread that sums a window sequentially must not wait on L2 for every batch of terms
-    double* kv = (WB == 1 && A.kv_in_smem) ? (xs + Dsv) : (A.kscratch + (size_t)blockIdx.x * HAF_EXACT_WB * Spad);
-    for (unsigned e0 = blockIdx.x * WB; e0 < n; e0 += gridDim.x * WB) {
+    const int i0 = blockIdx.y * HAF_EXACT_SLICE;
+    if (i0 >= A.S) return;
+    for (unsigned e0 = A.entry_begin + blockIdx.x * WB; e0 < n; e0 += gridDim.x * WB) {
         const int nb = min((unsigned)WB, n - e0);
         __syncthreads();
-        // x of every window of the block, bit-exact emulation of both text round trips
         for (int t = threadIdx.x; t < WB * Dsv; t += blockDim.x) {
             const int b = t / Dsv, d = t - b * Dsv;
             double x = 0.0;
@@ -901,62 +907,63 @@ __device__ __forceinline__ void svm_exact_body(const ExactArgs& A, double* xs, u
             xs[t] = x;
         }
         __syncthreads();
-        // K_i for the block: d loop sequential and un-fused per (window, SV); sv element shared by the WB windows
-        for (int i = threadIdx.x; i < A.S; i += blockDim.x) {
-            double sum[WB];
+        double sum[WB][HAF_EXACT_SVT];
 #pragma unroll
-            for (int b = 0; b < WB; b++) sum[b] = 0.0;
-            // loads are independent of the (sequential) accumulation chain: fetch 8 ahead so the L2 latency overlaps
-            constexpr int UN = (WB == 1) ? 8 : 2;
-            int d = 0;
-            for (; d + UN <= Dsv; d += UN) {
-                double sv[UN];
+        for (int b = 0; b < WB; b++)
 #pragma unroll
-                for (int k = 0; k < UN; k++) sv[k] = A.sv64T[(size_t)(d + k) * Spad + i];
+            for (int k = 0; k < HAF_EXACT_SVT; k++) sum[b][k] = 0.0;
+        const int ia = i0 + threadIdx.x;  // this thread's SVs: ia, ia + 256 (padding SVs are all-zero columns, coef 0)
+        for (int d = 0; d < Dsv; d++) {
+            double sv[HAF_EXACT_SVT];
 #pragma unroll
-                for (int k = 0; k < UN; k++) {
+            for (int k = 0; k < HAF_EXACT_SVT; k++) sv[k] = A.sv64T[(size_t)d * Spad + ia + 256 * k];
 #pragma unroll
-                    for (int b = 0; b < WB; b++) {
-                        const double diff = __dsub_rn(xs[b * Dsv + d + k], sv[k]);
-                        sum[b] = __dadd_rn(sum[b], __dmul_rn(diff, diff));
-                    }
+            for (int b = 0; b < WB; b++) {
+                const double xb = xs[b * Dsv + d];
+#pragma unroll
+                for (int k = 0; k < HAF_EXACT_SVT; k++) {
+                    const double diff = __dsub_rn(xb, sv[k]);
+                    sum[b][k] = __dadd_rn(sum[b][k], __dmul_rn(diff, diff));
                 }
             }
-            for (; d < Dsv; d++) {
-                const double sv = A.sv64T[(size_t)d * Spad + i];
-#pragma unroll
-                for (int b = 0; b < WB; b++) {
-                    const double diff = __dsub_rn(xs[b * Dsv + d], sv);
-                    sum[b] = __dadd_rn(sum[b], __dmul_rn(diff, diff));
-                }
-            }
-            // the product coef_i * K_i is formed here (same bits wherever it is computed); the SUM stays sequential
-#pragma unroll
-            for (int b = 0; b < WB; b++) kv[(size_t)b * Spad + i] = __dmul_rn(A.coef64[i], exp(__dmul_rn(-A.gamma, sum[b])));
         }
-        __syncthreads();
-        // decision value: sequential sum in file order, one thread per window (svm.cpp:2500-2514)
-        if ((int)threadIdx.x < nb) {
-            const double* k = kv + (size_t)threadIdx.x * Spad;
-            double sum = 0.0;
-            int i = 0;
-            for (; i + 8 <= A.S; i += 8) {
-                double t[8];
 #pragma unroll
-                for (int q = 0; q < 8; q++) t[q] = k[i + q];
+        for (int k = 0; k < HAF_EXACT_SVT; k++) {
+            const int i = ia + 256 * k;
+            if (i < A.S) {
+                const double cf = A.coef64[i];
 #pragma unroll
-                for (int q = 0; q < 8; q++) sum = __dadd_rn(sum, t[q]);
+                for (int b = 0; b < WB; b++)
+                    if (b < nb) A.terms[(size_t)(e0 - A.entry_begin + b) * Spad + i] = __dmul_rn(cf, exp(__dmul_rn(-A.gamma, sum[b][k])));
             }
-            for (; i < A.S; i++) sum = __dadd_rn(sum, k[i]);
-            A.dec[A.list ? A.list[e0 + threadIdx.x] : (int)(e0 + threadIdx.x)] = __dsub_rn(sum, A.rho);
         }
     }
 }
-__global__ void __launch_bounds__(256) svm_exact_kernel(const ExactArgs A) {
+__global__ void __launch_bounds__(256) svm_exact_terms_kernel(const ExactArgs A) {
     extern __shared__ double xs[];  // [HAF_EXACT_WB][Dsv]
-    const unsigned n = A.list ? *A.list_count : *A.win_count;
-    if (n >= (unsigned)gridDim.x * 2u) svm_exact_body<HAF_EXACT_WB>(A, xs, n);
-    else svm_exact_body<1>(A, xs, n);
+    unsigned n = A.list ? *A.list_count : *A.win_count;
+    n = min(n, (unsigned)(A.entry_begin + A.max_entries));
+    if (n <= (unsigned)A.entry_begin) return;
+    if (n - A.entry_begin >= (unsigned)gridDim.x * 2u) svm_exact_terms_body<HAF_EXACT_WB>(A, xs, n);
+    else svm_exact_terms_body<1>(A, xs, n);
+}
+// Phase 2: dec = (sum of the terms in FILE ORDER, one sequential chain) - rho   (svm.cpp:2500-2514).  One warp per
+// entry: 32 terms are fetched with one coalesced load and broadcast lane by lane, every lane runs the same chain.
+__global__ void __launch_bounds__(128) svm_exact_sum_kernel(const ExactArgs A) {
+    const unsigned total = A.list ? *A.list_count : *A.win_count;
+    if (A.overflow_flag && total > (unsigned)(A.entry_begin + A.max_entries) && blockIdx.x == 0 && threadIdx.x == 0) *A.overflow_flag = 1;
+    const unsigned n = min(total, (unsigned)(A.entry_begin + A.max_entries));
+    const int lane = threadIdx.x & 31;
+    for (unsigned e = A.entry_begin + blockIdx.x * 4 + (threadIdx.x >> 5); e < n; e += gridDim.x * 4) {
+        const double* t = A.terms + (size_t)(e - A.entry_begin) * A.Spad;
+        double sum = 0.0;
+        for (int i0 = 0; i0 < A.S; i0 += 32) {
+            const double mine = (i0 + lane < A.S) ? t[i0 + lane] : 0.0;
+            const int cnt = min(32, A.S - i0);
+            for (int k = 0; k < cnt; k++) sum = __dadd_rn(sum, __shfl_sync(0xffffffffu, mine, k));
+        }
+        if (lane == 0) A.dec[A.list ? A.list[e] : (int)e] = __dsub_rn(sum, A.rho);
+    }
 }
 
 // label -> graspsgrid value (server.cpp:843) scattered into the unit grids
