@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--clouds", type=int, default=512, help="clouds per GPU (batch workload)")
     ap.add_argument("--points", type=int, default=100000)
     ap.add_argument("--nsv", type=int, default=2048)
-    ap.add_argument("--svm-mode", type=int, default=0, help="0 tcgen05 split-bf16 + FP64 guard (default), 1 FP64 exact, 2 FP32 SIMT + guard")
+    ap.add_argument("--svm-mode", type=int, default=0, help="0 tcgen05 split-fp16 + FP64 guard (default), 1 FP64 exact, 2 FP32 SIMT + guard")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-clouds", type=int, default=2)
     return ap.parse_args()
@@ -344,7 +344,7 @@ def run_approach(args):
         dist.destroy_process_group()
 
 
-DTYPES = {2: "f32", 1: "f64", 0: "f32 (contraction: split-bf16 x3 on tensor cores, f32 accumulate; f64 guard band)"}
+DTYPES = {2: "f32", 1: "f64", 0: "f32 (contraction: split-fp16 x3 on tensor cores, f32 accumulate; f64 guard band)"}
 
 
 def run_ours(args):
@@ -480,7 +480,7 @@ def run_ours(args):
                          "algorithmic": "W*S*(2D+4) flop per launch, W=%.0f S=%d D=%d" % (acc["windows"] / max(svm_launches, 1), info.n_sv, info.n_dims),
                          "kernel_ms": svm_ms, "share_of_step": acc["svm"] / ms_dev if ms_dev else None,
                          "note": {2: "FP32 SIMT contraction (CUDA cores), measured against the bf16 tensor peak for comparability",
-                                  1: "FP64 exact-order path", 0: "algorithmic flops; the split-bf16 scheme issues 3 tensor-core MMAs per algorithmic MMA, "
+                                  1: "FP64 exact-order path", 0: "algorithmic flops; the split-fp16 scheme issues 3 tensor-core MMAs per algorithmic MMA, "
                                   "executed tensor flops = 3 x (Krow/D) x algorithmic (ncu: tensor pipe 98.5 % active, profiles/r1_final_full.md)"}[args.svm_mode]},
             "stage_ms_per_step": {k: acc[k] / args.steps for k in ("bin", "integral", "mask", "features", "svm", "guard", "score")},
             "guard_windows_per_step": acc["guardw"] / args.steps,

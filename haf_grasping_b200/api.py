@@ -55,7 +55,8 @@ class haf_timing(C.Structure):
     _fields_ = [("ms_total", C.c_float), ("ms_bin", C.c_float), ("ms_integral", C.c_float), ("ms_mask", C.c_float),
                 ("ms_features", C.c_float), ("ms_svm", C.c_float), ("ms_guard", C.c_float), ("ms_score", C.c_float),
                 ("n_points", C.c_longlong), ("n_units", C.c_longlong), ("n_windows", C.c_longlong),
-                ("n_guard", C.c_longlong), ("launches", C.c_longlong), ("n_chunks", C.c_longlong)]
+                ("n_guard", C.c_longlong), ("launches", C.c_longlong), ("n_chunks", C.c_longlong),
+                ("n_exact", C.c_longlong)]
 
 
 EXPORTS = ["haf_create", "haf_destroy", "haf_last_error", "haf_get_info", "haf_set_stream", "haf_set_profiling",
@@ -145,7 +146,7 @@ class GraspSearch:
 
     def __init__(self, features_path, range_path, model_path, grid=56, roll_step_deg=15, roll_max_deg=190,
                  nr_features_without_shaf=302, device=0, emulate_text_roundtrip=True, svm_mode=HAF_SVM_TENSOR_GUARD,
-                 guard_rel=0.0, tc_variant=0):
+                 guard_rel=0.0, tc_variant=0, guard_tier2=0):
         self.L = load_library()
         cfg = haf_config()
         self._keep = [features_path.encode(), range_path.encode(), model_path.encode()]
@@ -157,6 +158,7 @@ class GraspSearch:
         cfg.svm_mode = svm_mode
         cfg.guard_rel = guard_rel
         cfg.reserved[0] = tc_variant
+        cfg.reserved[2] = guard_tier2   # 0 on, 1 off, 2 on + escalate everything (tests)
         self.h = C.c_void_p()
         rc = self.L.haf_create(C.byref(self.h), C.byref(cfg))
         if rc != 0:

@@ -91,11 +91,11 @@ struct haf_ctx {
     DevBuf<DimDev> d_dims;
     DevBuf<float> d_svT, d_svn, d_coef;
     DevBuf<double> d_sv64T, d_coef64;
-    // tensor-core path (HAF_SVM_TENSOR_GUARD): bf16 hi/lo operands, K-major rows of Krow elements
+    // tensor-core path (HAF_SVM_TENSOR_GUARD): fp16 hi/lo operands, K-major rows of Krow elements
     int Krow = 0, SpadT = 0;
     float c_log2 = 0.0f;
-    DevBuf<__nv_bfloat16> d_SVh, d_SVl, d_Xh, d_Xl;
-    DevBuf<float2> d_svtab;
+    DevBuf<__half> d_SVh, d_SVl, d_Xh, d_Xl;
+    DevBuf<float4> d_svtab;
     DevBuf<DimFeat> d_dimfeat;
     DevBuf<float> d_asum;
     CUtensorMap tmSh, tmSl;     // 256-row boxes (single-CTA kernel)
@@ -125,6 +125,11 @@ struct haf_ctx {
     DevBuf<unsigned char> d_guardflag;
     DevBuf<int> d_guardlist;
     DevBuf<double> d_kscratch;
+    // guard band tier 2 (FP64 FMA contraction on the exact inputs, kernels.cuh guard_fma_kernel)
+    int tier2_mode = 0;                 // cfg.reserved[2]: 0 on, 1 off (guard list straight to the exact-order kernels), 2 on but everything escalates (tests)
+    DevBuf<double> d_svn64, d_Xg, d_g2accum;
+    DevBuf<unsigned> d_g2tickets;
+    DevBuf<int> d_guardlist2;
     DevBuf<unsigned> d_counters;        // [0]=win_count [1]=guard_count [2]=overflow [3]=unsupported ; [4..5] clamp (u64)
     PinBuf<unsigned char> h_stage;      // pinned staging for params / results
     PinBuf<JobResult> h_results;
@@ -179,19 +184,9 @@ static int create_fail(int code, const std::string& msg) {
 }
 
 // ---- tensor-core path helpers -------------------------------------------------------------------------------
-static uint16_t f2bf16(float f) {  // round to nearest even
-    uint32_t u;
-    memcpy(&u, &f, 4);
-    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40u);
-    const uint32_t r = 0x7fffu + ((u >> 16) & 1u);
-    return (uint16_t)((u + r) >> 16);
-}
-static float bf16f(uint16_t h) {
-    uint32_t u = (uint32_t)h << 16;
-    float f;
-    memcpy(&f, &u, 4);
-    return f;
-}
+// IEEE binary16 <-> float on the host (round to nearest even, subnormals kept): the operand format of the contraction
+static uint16_t f2h16(float f) { return __half_as_ushort(__float2half_rn(f)); }
+static float h16f(uint16_t h) { return __half2float(__ushort_as_half(h)); }
 typedef CUresult (*haf_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                         const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -207,7 +202,7 @@ static haf_encode_tiled_fn get_encode_tiled() {
     }
     return fn;
 }
-// 2D bf16 tensor [rows][krow] (K contiguous), box = 64 elements (128 B, one swizzle row) x box_rows, 128B swizzle
+// 2D fp16 tensor [rows][krow] (K contiguous), box = 64 elements (128 B, one swizzle row) x box_rows, 128B swizzle
 static bool make_tensor_map(CUtensorMap* m, void* base, uint64_t krow, uint64_t rows, uint32_t box_rows) {
     haf_encode_tiled_fn fn = get_encode_tiled();
     if (!fn) return false;
@@ -215,7 +210,7 @@ static bool make_tensor_map(CUtensorMap* m, void* base, uint64_t krow, uint64_t 
     cuuint64_t strides[1] = {krow * 2};
     cuuint32_t box[2] = {(cuuint32_t)haftc::BK, box_rows};
     cuuint32_t es[2] = {1, 1};
-    return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -324,7 +319,7 @@ extern "C" int haf_create(haf_ctx** out, const haf_config* cfg) {
     ctx->label[0] = model.label[0]; ctx->label[1] = model.label[1];
     ctx->gv[0] = hafhost::label_to_gridvalue(model.label[0]);
     ctx->gv[1] = hafhost::label_to_gridvalue(model.label[1]);
-    ctx->guard_rel = cfg->guard_rel > 0 ? cfg->guard_rel : 4e-6f;   // measured FP32 error <= 2e-7 of sum|coef|K (tools/dec_error_probe.py)
+    ctx->guard_rel = cfg->guard_rel > 0 ? cfg->guard_rel : 2e-6f;   // of E = sum|coef|K(1+|c|(xn+svn)) + |rho|; measured FP32 SIMT error <= 1.3e-7 E (tools/dec_error_probe.py)
     memset(&ctx->timing, 0, sizeof ctx->timing);
     if (ctx->gv[0] < -128 || ctx->gv[0] > 127 || ctx->gv[1] < -128 || ctx->gv[1] > 127) { delete ctx; return create_fail(HAF_ERR_UNSUPPORTED, "model labels do not fit the grasp grid"); }
 
@@ -359,10 +354,11 @@ extern "C" int haf_create(haf_ctx** out, const haf_config* cfg) {
         fd[k] = f;
     }
     std::vector<float> svT((size_t)Kpad * Spad, 0.0f), svn(Spad, 0.0f), coef(Spad, 0.0f);
-    std::vector<double> sv64T((size_t)Dsv * Spad, 0.0), coef64(Spad, 0.0);
+    std::vector<double> sv64T((size_t)Dsv * Spad, 0.0), coef64(Spad, 0.0), svn64(Spad, 0.0);
     for (int i = 0; i < S; i++) {
         coef[i] = (float)model.coef[i];
         coef64[i] = model.coef[i];
+        for (size_t e = 0; e < model.sv[i].size(); e++) svn64[i] = fma(model.sv[i][e].second, model.sv[i][e].second, svn64[i]);
         float nrm = 0.0f;
         for (size_t e = 0; e < model.sv[i].size(); e++) {
             const int d = model.sv[i][e].first - 1;
@@ -376,7 +372,7 @@ extern "C" int haf_create(haf_ctx** out, const haf_config* cfg) {
     }
     bool okb = ctx->d_feats.ensure(F) == 0 && ctx->d_dims.ensure(D) == 0 && ctx->d_svT.ensure(svT.size()) == 0 &&
                ctx->d_svn.ensure(Spad) == 0 && ctx->d_coef.ensure(Spad) == 0 && ctx->d_sv64T.ensure(sv64T.size()) == 0 &&
-               ctx->d_coef64.ensure(Spad) == 0 && ctx->d_counters.ensure(16) == 0 && ctx->h_counters.ensure(16) == 0;
+               ctx->d_coef64.ensure(Spad) == 0 && ctx->d_svn64.ensure(Spad) == 0 && ctx->d_counters.ensure(16) == 0 && ctx->h_counters.ensure(16) == 0;
     if (!okb) { haf_destroy(ctx); return create_fail(HAF_ERR_NOMEM, "out of device memory uploading the model"); }
     CREATE_TRY(cudaMemcpy(ctx->d_feats.p, fd.data(), F * sizeof(FeatDev), cudaMemcpyHostToDevice));
     CREATE_TRY(cudaMemcpy(ctx->d_dims.p, dims.data(), D * sizeof(DimDev), cudaMemcpyHostToDevice));
@@ -385,6 +381,10 @@ extern "C" int haf_create(haf_ctx** out, const haf_config* cfg) {
     CREATE_TRY(cudaMemcpy(ctx->d_coef.p, coef.data(), Spad * sizeof(float), cudaMemcpyHostToDevice));
     CREATE_TRY(cudaMemcpy(ctx->d_sv64T.p, sv64T.data(), sv64T.size() * sizeof(double), cudaMemcpyHostToDevice));
     CREATE_TRY(cudaMemcpy(ctx->d_coef64.p, coef64.data(), Spad * sizeof(double), cudaMemcpyHostToDevice));
+    CREATE_TRY(cudaMemcpy(ctx->d_svn64.p, svn64.data(), Spad * sizeof(double), cudaMemcpyHostToDevice));
+    ctx->tier2_mode = cfg->reserved[2];
+    CREATE_TRY(cudaFuncSetAttribute(guard_fma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CREATE_TRY(cudaFuncSetAttribute(guard_fma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CREATE_TRY(cudaFuncSetAttribute(svm_rbf_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SVM_STAGES * SVM_BK * (SVM_BM + SVM_BN) * 4));
     CREATE_TRY(cudaFuncSetAttribute(integral_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CREATE_TRY(cudaFuncSetAttribute(svm_exact_terms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -394,30 +394,35 @@ extern "C" int haf_create(haf_ctx** out, const haf_config* cfg) {
         const int SpadT = (int)round_up((size_t)S, haftc::BN);
         ctx->Krow = Krow; ctx->SpadT = SpadT;
         ctx->c_log2 = (float)(-model.gamma * 1.4426950408889634);
-        if (cfg->guard_rel <= 0) ctx->guard_rel = 1e-5f;  // measured split-bf16 + fast-tier error <= 6e-7 of sum|coef|K (tools/dec_error_probe.py)
+        if (cfg->guard_rel <= 0) ctx->guard_rel = 4e-6f;  // of E (see svm_tc.cuh); measured split-fp16 + fast-tier error <= 3.3e-7 E (tools/dec_error_probe.py)
         std::vector<uint16_t> svh((size_t)SpadT * Krow, 0), svl((size_t)SpadT * Krow, 0);
-        std::vector<float2> tab(SpadT);
-        for (int i = 0; i < SpadT; i++) { tab[i].x = 0.0f; tab[i].y = 0.0f; }
+        std::vector<float4> tab(SpadT);
+        for (int i = 0; i < SpadT; i++) tab[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         for (int i = 0; i < S; i++) {
             float nrm = 0.0f;
             for (size_t e = 0; e < model.sv[i].size(); e++) {
                 const int d = model.sv[i][e].first - 1;
                 const float fv = (float)model.sv[i][e].second;
-                const uint16_t h = f2bf16(fv);
-                const uint16_t l = f2bf16(fv - bf16f(h));
+                if (!(fabsf(fv) <= 65504.0f)) {
+                    haf_destroy(ctx);
+                    return create_fail(HAF_ERR_UNSUPPORTED, "a support-vector component exceeds the fp16 range of the tensor path (use svm_mode HAF_SVM_FP32_GUARD)");
+                }
+                const uint16_t h = f2h16(fv);
+                const uint16_t l = f2h16(fv - h16f(h));
                 svh[(size_t)i * Krow + d] = h;
                 svl[(size_t)i * Krow + d] = l;
-                const float rep = bf16f(h) + bf16f(l);
+                const float rep = h16f(h) + h16f(l);
                 nrm = fmaf(rep, rep, nrm);
             }
             tab[i].x = ctx->c_log2 * nrm;
             tab[i].y = (float)model.coef[i];
+            tab[i].z = fabsf(tab[i].y) * fabsf(tab[i].x);   // guard scale term, see svm_tc.cuh
         }
         bool okt = ctx->d_SVh.ensure(svh.size()) == 0 && ctx->d_SVl.ensure(svl.size()) == 0 && ctx->d_svtab.ensure(SpadT) == 0;
-        if (!okt) { haf_destroy(ctx); return create_fail(HAF_ERR_NOMEM, "out of device memory uploading the bf16 model"); }
+        if (!okt) { haf_destroy(ctx); return create_fail(HAF_ERR_NOMEM, "out of device memory uploading the fp16 model"); }
         CREATE_TRY(cudaMemcpy(ctx->d_SVh.p, svh.data(), svh.size() * 2, cudaMemcpyHostToDevice));
         CREATE_TRY(cudaMemcpy(ctx->d_SVl.p, svl.data(), svl.size() * 2, cudaMemcpyHostToDevice));
-        CREATE_TRY(cudaMemcpy(ctx->d_svtab.p, tab.data(), SpadT * sizeof(float2), cudaMemcpyHostToDevice));
+        CREATE_TRY(cudaMemcpy(ctx->d_svtab.p, tab.data(), SpadT * sizeof(float4), cudaMemcpyHostToDevice));
         ctx->tc_variant = cfg->reserved[0];
         if (!make_tensor_map(&ctx->tmSh, ctx->d_SVh.p, Krow, SpadT, haftc::BN) || !make_tensor_map(&ctx->tmSl, ctx->d_SVl.p, Krow, SpadT, haftc::BN) ||
             !make_tensor_map(&ctx->tmSh2, ctx->d_SVh.p, Krow, SpadT, haftc::BN / 2) || !make_tensor_map(&ctx->tmSl2, ctx->d_SVl.p, Krow, SpadT, haftc::BN / 2)) {
@@ -471,6 +476,7 @@ extern "C" void haf_destroy(haf_ctx* ctx) {
     ctx->d_integral.release(); ctx->d_rowscan.release(); ctx->d_mask.release(); ctx->d_labelgrid.release(); ctx->d_evals.release();
     ctx->d_unit_top.release(); ctx->d_unit_run.release(); ctx->d_unit_windows.release(); ctx->d_win.release(); ctx->d_X.release();
     ctx->d_xn.release(); ctx->d_dec.release(); ctx->d_guardflag.release(); ctx->d_guardlist.release(); ctx->d_kscratch.release();
+    ctx->d_svn64.release(); ctx->d_Xg.release(); ctx->d_g2accum.release(); ctx->d_g2tickets.release(); ctx->d_guardlist2.release();
     ctx->d_SVh.release(); ctx->d_SVl.release(); ctx->d_Xh.release(); ctx->d_Xl.release(); ctx->d_svtab.release(); ctx->d_asum.release(); ctx->d_dimfeat.release();
     ctx->d_params.release(); ctx->d_counters.release(); ctx->h_stage.release(); ctx->h_results.release(); ctx->h_per_roll_top.release(); ctx->h_counters.release();
     if (ctx->ev_ok) for (int i = 0; i < 10; i++) cudaEventDestroy(ctx->ev[i]);
@@ -547,6 +553,33 @@ static int launch_exact(haf_ctx* ctx, ExactArgs a, cudaStream_t st, size_t max_w
         LAUNCHED(ctx);
     }
     return HAF_OK;
+}
+// Guard band after the FP32 / tensor contraction: tier 2 (FP64 FMA contraction on the bit-exact inputs) settles every
+// window whose sign it can guarantee; the rest (list 2, counter cnt[6]) and -- with tier 2 switched off -- the whole
+// guard list go through the exact-order kernels.
+static ExactArgs make_exact_args(haf_ctx* ctx, const int* list, const unsigned* list_count, unsigned* cnt, int G, int ubase);
+static int launch_guard(haf_ctx* ctx, unsigned* cnt, int G, int ubase, cudaStream_t st, size_t Wcap, size_t ldx) {
+    if (ctx->tier2_mode == 1) return launch_exact(ctx, make_exact_args(ctx, ctx->d_guardlist.p, cnt + 1, cnt, G, ubase), st, Wcap);
+    const size_t cap = std::min<size_t>(ldx, 32768);
+    const size_t acc_cap0 = ctx->d_g2accum.cap, tk_cap0 = ctx->d_g2tickets.cap;
+    ENSURE(ctx, ctx->d_Xg, cap * ctx->Dsv); ENSURE(ctx, ctx->d_g2accum, cap * 2); ENSURE(ctx, ctx->d_g2tickets, cap / HAF_G2_WB + 1);
+    ENSURE(ctx, ctx->d_guardlist2, ldx);
+    if (ctx->d_g2accum.cap != acc_cap0) CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_g2accum.p, 0, ctx->d_g2accum.cap * sizeof(double), st));
+    if (ctx->d_g2tickets.cap != tk_cap0) CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_g2tickets.p, 0, ctx->d_g2tickets.cap * sizeof(unsigned), st));
+    ExactArgs a = make_exact_args(ctx, ctx->d_guardlist.p, cnt + 1, cnt, G, ubase);
+    Guard2Args q;
+    q.list = ctx->d_guardlist.p; q.list_count = cnt + 1; q.cap = (int)cap; q.Xg = ctx->d_Xg.p; q.svn64 = ctx->d_svn64.p;
+    q.accum = ctx->d_g2accum.p; q.tickets = ctx->d_g2tickets.p; q.tol2 = ctx->tier2_mode == 2 ? 1e30 : 1e-10;
+    q.list2 = ctx->d_guardlist2.p; q.list2_count = cnt + 6;
+    const size_t smem = ((size_t)ctx->Dsv * HAF_G2_WB + HAF_G2_WB + 8 * HAF_G2_WB * 2) * sizeof(double);
+    if (smem > 100 * 1024) return launch_exact(ctx, a, st, Wcap);   // models with > ~780 dimensions: exact-order kernels only
+    const bool few = Wcap < 65536;   // a single goal: a handful of guard windows -> spread the support vectors over more CTAs
+    guard_inputs_kernel<<<few ? 32 : ctx->sm_count * 4, 256, 0, st>>>(a, q);
+    LAUNCHED(ctx);
+    if (few) guard_fma_kernel<1><<<dim3(16, (unsigned)((ctx->Spad + 255) / 256)), 256, smem, st>>>(a, q);
+    else guard_fma_kernel<2><<<dim3((unsigned)ctx->sm_count, (unsigned)((ctx->Spad + 511) / 512)), 256, smem, st>>>(a, q);
+    LAUNCHED(ctx);
+    return launch_exact(ctx, make_exact_args(ctx, ctx->d_guardlist2.p, cnt + 6, cnt, G, ubase), st, Wcap);
 }
 static ExactArgs make_exact_args(haf_ctx* ctx, const int* list, const unsigned* list_count, unsigned* cnt, int G, int ubase) {
     ExactArgs a;
@@ -803,18 +836,18 @@ static int run_jobs(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& jobs, fl
                                                                                           cnt + 0, n_ntiles, nsplit, kblocks, last_slices, ctx->d_dec.p, ctx->d_asum.p);
             }
             LAUNCHED(ctx);
-            haftc::svm_finalize_kernel<<<(unsigned)((Wcap + 255) / 256), 256, 0, st>>>(ctx->d_dec.p, ctx->d_asum.p, cnt + 0, ctx->rho, ctx->guard_rel,
+            haftc::svm_finalize_kernel<<<(unsigned)((Wcap + 255) / 256), 256, 0, st>>>(ctx->d_dec.p, ctx->d_asum.p, ctx->d_xn.p, cnt + 0, ctx->rho, ctx->guard_rel,
                                                                                        ctx->d_guardflag.p, ctx->d_guardlist.p, cnt + 1);
             LAUNCHED(ctx);
             if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[ci * 8 + 5], st));
-            { int rce = launch_exact(ctx, make_exact_args(ctx, ctx->d_guardlist.p, cnt + 1, cnt, G, ubase), st, Wcap); if (rce) return rce; }
+            { int rce = launch_guard(ctx, cnt, G, ubase, st, Wcap, ldx); if (rce) return rce; }
         } else {
             svm_rbf_simt_kernel<<<(unsigned)(ldx / SVM_BM), 256, SVM_STAGES * SVM_BK * (SVM_BM + SVM_BN) * 4, st>>>(
                 ctx->d_X.p, ldx, ctx->d_svT.p, ctx->Spad, ctx->Kpad, ctx->d_xn.p, ctx->d_svn.p, ctx->d_coef.p, neg_gamma_log2e, ctx->rho,
                 ctx->guard_rel, cnt + 0, ctx->d_dec.p, ctx->d_guardflag.p, ctx->d_guardlist.p, cnt + 1);
             LAUNCHED(ctx);
             if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[ci * 8 + 5], st));
-            { int rce = launch_exact(ctx, make_exact_args(ctx, ctx->d_guardlist.p, cnt + 1, cnt, G, ubase), st, Wcap); if (rce) return rce; }
+            { int rce = launch_guard(ctx, cnt, G, ubase, st, Wcap, ldx); if (rce) return rce; }
         }
         // 6. labels -> grids, score stencil, argmax, tie rule
         if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[ci * 8 + 6], st));
@@ -872,6 +905,7 @@ static int run_jobs(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& jobs, fl
     for (int j = 0; j < n_jobs; j++) t.n_units += jobs[j].n_rolls_active - jobs[j].roll_begin;
     t.n_windows = total_windows; t.n_guard = total_guard; t.launches = ctx->launches - launches0;
     t.n_chunks = (long long)chunks.size();
+    t.n_exact = (ctx->tier2_mode == 1 && ctx->cfg.svm_mode != HAF_SVM_FP64_EXACT) ? total_guard : ctx->h_counters.p[11];
     if (keep_debug_state) { ctx->last_W = (unsigned)total_windows; ctx->last_valid = true; }
     return HAF_OK;
 }
@@ -1056,7 +1090,7 @@ extern "C" int haf_debug_tensor_inputs(haf_ctx* ctx, float* x, int cap) {
     CUDA_TRY(ctx, cudaMemcpy(hh.data(), ctx->d_Xh.p, hh.size() * 2, cudaMemcpyDeviceToHost));
     CUDA_TRY(ctx, cudaMemcpy(ll.data(), ctx->d_Xl.p, ll.size() * 2, cudaMemcpyDeviceToHost));
     for (int w = 0; w < W; w++)
-        for (int d = 0; d < ctx->D; d++) x[(size_t)w * ctx->D + d] = bf16f(hh[(size_t)w * ctx->Krow + d]) + bf16f(ll[(size_t)w * ctx->Krow + d]);
+        for (int d = 0; d < ctx->D; d++) x[(size_t)w * ctx->D + d] = h16f(hh[(size_t)w * ctx->Krow + d]) + h16f(ll[(size_t)w * ctx->Krow + d]);
     return W;
 }
 

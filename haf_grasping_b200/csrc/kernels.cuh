@@ -11,7 +11,7 @@
 //   X                    [Kpad][ldx]    f32 feature-major SVM inputs (dimension d of window w at X[d*ldx+w])
 //   svT                  [Kpad][Spad]   f32 feature-major support vectors;  sv64T [D][Spad] f64 for the exact path
 #pragma once
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -541,22 +541,22 @@ __device__ __forceinline__ float fast_tier_value(PtrT I, int idx0, const FastTab
     return (f.flags & 0x400) ? 0.0f : ((f.flags & 0x200) ? f.cval : x);
 }
 
-// Tensor-core variant: per-dimension values split into two bf16 terms and written K-major ([window][Krow], what the
+// Tensor-core variant: per-dimension values split into two fp16 terms and written K-major ([window][Krow], what the
 // UMMA K-major operand / TMA box wants).  A (32*WT)-window x Krow/2 tile is staged in shared memory so the global
 // writes are row-contiguous; the squared norm of the (hi + lo) representation is reduced on the way.
 //
-// FAST TIER.  The values written here are rounded to 16 significant bits (bf16 hi + lo) anyway and every window whose
+// FAST TIER.  The values written here are rounded to 22 significant bits (fp16 hi + lo) anyway and every window whose
 // decision value lands inside the guard band is re-evaluated by svm_exact_kernel with the bit-exact emulation, so this
 // tier reproduces the text round trips only to ~1e-7 (see fast_tier_value); the 6-digit "%g" rounding (<= 5e-7
-// relative, below the 2^-17 operand precision) is skipped.  Raw feature values are the same bit-exact floats as
+// relative: now the largest input error of this tier, see tools/dec_error_probe.py) is skipped.  Raw feature values are the same bit-exact floats as
 // everywhere else.  Each lane handles WT windows per table record, so the six 128-bit table loads are amortised.
 // (Tables in __constant__ memory were tried and were 1.8x SLOWER: 36 KB of tables thrash the constant cache.)
 #define HAF_FT_WT 2
 __global__ void __launch_bounds__(256, 4) features_tc_kernel(const float* __restrict__ integral, const int2* __restrict__ win,
                                                              const unsigned* __restrict__ win_count, int G, int unit_base,
                                                              const DimFeat* __restrict__ table, int D, int Krow, float lower,
-                                                             int emulate_text, __nv_bfloat16* __restrict__ Xh,
-                                                             __nv_bfloat16* __restrict__ Xl, float* __restrict__ xn) {
+                                                             int emulate_text, __half* __restrict__ Xh,
+                                                             __half* __restrict__ Xl, float* __restrict__ xn) {
     constexpr int WT = HAF_FT_WT, NW = 32 * WT;
     extern __shared__ uint32_t s_words[];  // tile [NW][KP+1] of (hi | lo << 16), KP = Krow / 2; then float s_int[ROWS][ld]
     const unsigned W = *win_count;
@@ -650,9 +650,12 @@ __global__ void __launch_bounds__(256, 4) features_tc_kernel(const float* __rest
             }
 #pragma unroll
             for (int t = 0; t < WT; t++) {
-                const __nv_bfloat16 hi = __float2bfloat16_rn(xf[t]);
-                const __nv_bfloat16 lo = __float2bfloat16_rn(xf[t] - __bfloat162float(hi));
-                s_words[(t * 32 + lane) * rs + dl] = (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16);
+                // fp16 hi + fp16 lo = 22 significant bits (absolute floor 2^-25 once lo is subnormal); values beyond the
+                // fp16 range are clamped to +-65504 and the window is sent to the FP64 exact path (xn = +inf below)
+                const float xc = fminf(fmaxf(xf[t], -65504.0f), 65504.0f);
+                const __half hi = __float2half_rn(xc);
+                const __half lo = __float2half_rn(xc - __half2float(hi));
+                s_words[(t * 32 + lane) * rs + dl] = (uint32_t)__half_as_ushort(hi) | ((uint32_t)__half_as_ushort(lo) << 16);
             }
         }
         __syncthreads();
@@ -671,10 +674,12 @@ __global__ void __launch_bounds__(256, 4) features_tc_kernel(const float* __rest
                 const uint32_t l2 = __byte_perm(a0, a1, 0x7632);     // lo(2e) | lo(2e+1) << 16
                 gh[e] = h2;
                 gl[e] = l2;
-                const float v0 = __uint_as_float(a0 << 16) + __uint_as_float(a0 & 0xFFFF0000u);
-                const float v1 = __uint_as_float(a1 << 16) + __uint_as_float(a1 & 0xFFFF0000u);
+                const float2 h01 = __half22float2(*reinterpret_cast<const __half2*>(&h2));
+                const float2 l01 = __half22float2(*reinterpret_cast<const __half2*>(&l2));
+                const float v0 = h01.x + l01.x, v1 = h01.y + l01.y;
                 sq = fmaf(v0, v0, sq);
                 sq = fmaf(v1, v1, sq);
+                if (fmaxf(fabsf(h01.x), fabsf(h01.y)) >= 65504.0f) sq = __int_as_float(0x7f800000);  // clamped: force exact
             }
             nrm[k] = sq;
         }
@@ -813,10 +818,13 @@ __global__ void __launch_bounds__(256, 2) svm_rbf_simt_kernel(const float* __res
                 float ps = 0.0f, pa = 0.0f;
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
-                    const float d2 = fmaxf(fmaf(-2.0f, acc[i][j], xnr[i] + sn[j]), 0.0f);
+                    const float base = xnr[i] + sn[j];
+                    const float d2 = fmaxf(fmaf(-2.0f, acc[i][j], base), 0.0f);
                     const float kv = exp2f(neg_gamma_log2e * d2);
                     ps = fmaf(cf[j], kv, ps);
-                    pa = fmaf(fabsf(cf[j]), kv, pa);
+                    // guard scale: |coef| K (1 + |c| (xn + svn)) -- the exponent's absolute FP32 error grows with the
+                    // magnitude of the numbers it is assembled from (see svm_tc.cuh, GUARD SCALE)
+                    pa = fmaf(fabsf(cf[j]) * kv, fmaf(-neg_gamma_log2e, base, 1.0f), pa);
                 }
                 dsum[i] += (double)ps;
                 asum[i] += pa;
@@ -840,7 +848,7 @@ __global__ void __launch_bounds__(256, 2) svm_rbf_simt_kernel(const float* __res
             if (m < W) {
                 const double dv = dsum[i] - rho;
                 dec[m] = dv;
-                const bool g = fabs(dv) <= (double)guard_rel * ((double)asum[i] + fabs(rho));
+                const bool g = !(fabs(dv) > (double)guard_rel * ((double)asum[i] + fabs(rho)));   // NaN-safe
                 guard_flag[m] = g ? 1 : 0;
                 if (g) guard_list[atomicAdd(guard_count, 1u)] = (int)m;
             }
@@ -867,6 +875,30 @@ struct ExactArgs {
     int entry_begin;      // this launch covers list entries [entry_begin, entry_begin + max_entries)
     int max_entries;      // capacity of `terms` in windows
 };
+// SVM input d of window w, re-derived in double from the integral image with the bit-exact emulation of both text round
+// trips (a7-a9: calc_featurevalue, "%.4g", svm-scale.c:339-352 with "%g"): exactly what svm-predict parses.
+__device__ __forceinline__ double exact_scaled_input(const ExactArgs& A, int w, int d) {
+    const int ld = A.G + 1;
+    const int2 uc = A.win[w];
+    const int row = uc.y / A.G, col = uc.y - row * A.G;
+    const float* P = A.integral + (size_t)(uc.x - A.unit_base) * ld * ld + (size_t)(row - 7) * ld + (col - 7);
+    const DimDev dd = A.dims[d];
+    if (dd.feat < 0) return dd.cval;
+    double x = 0.0;
+    const float raw = feature_value(P, A.feats[dd.feat]);
+    bool u4 = false, u6 = false;
+    const double v = A.emulate_text ? hafdec::text4(raw, &u4) : (double)raw;
+    if (!dd.drop) {
+        double val;
+        if (v == dd.fmin) val = A.lower;
+        else if (v == dd.fmax) val = A.upper;
+        else val = __dadd_rn(A.lower, __ddiv_rn(__dmul_rn(__dsub_rn(A.upper, A.lower), __dsub_rn(v, dd.fmin)), dd.den));
+        if (val != 0.0) x = A.emulate_text ? hafdec::text6(val, &u6) : val;
+    }
+    if (u4 || u6) *A.unsupported_flag = 1;
+    return x;
+}
+
 // Phase 1: terms[e][i] = coef_i * K_i for list entry e (window list[e], or window e when list == NULL).
 // grid = (window blocks, SV slices).  x is re-derived in double from the integral image with the bit-exact emulation of
 // both text round trips; K_i = exp(-gamma * sum_d (x_d - sv_i,d)^2) with the d loop sequential and un-fused
@@ -874,7 +906,7 @@ struct ExactArgs {
 // element (throughput); WB = 1 spreads a short list over many CTAs (latency of a single goal).
 template <int WB>
 __device__ __forceinline__ void svm_exact_terms_body(const ExactArgs& A, double* xs, unsigned n) {
-    const int ld = A.G + 1, Dsv = A.Dsv, Spad = A.Spad;
+    const int Dsv = A.Dsv, Spad = A.Spad;
     const int i0 = blockIdx.y * HAF_EXACT_SLICE;
     if (i0 >= A.S) return;
     for (unsigned e0 = A.entry_begin + blockIdx.x * WB; e0 < n; e0 += gridDim.x * WB) {
@@ -883,27 +915,7 @@ __device__ __forceinline__ void svm_exact_terms_body(const ExactArgs& A, double*
         for (int t = threadIdx.x; t < WB * Dsv; t += blockDim.x) {
             const int b = t / Dsv, d = t - b * Dsv;
             double x = 0.0;
-            if (b < nb && d < A.D) {
-                const int w = A.list ? A.list[e0 + b] : (int)(e0 + b);
-                const int2 uc = A.win[w];
-                const int row = uc.y / A.G, col = uc.y - row * A.G;
-                const float* P = A.integral + (size_t)(uc.x - A.unit_base) * ld * ld + (size_t)(row - 7) * ld + (col - 7);
-                const DimDev dd = A.dims[d];
-                if (dd.feat < 0) x = dd.cval;
-                else {
-                    const float raw = feature_value(P, A.feats[dd.feat]);
-                    bool u4 = false, u6 = false;
-                    const double v = A.emulate_text ? hafdec::text4(raw, &u4) : (double)raw;
-                    if (!dd.drop) {
-                        double val;
-                        if (v == dd.fmin) val = A.lower;
-                        else if (v == dd.fmax) val = A.upper;
-                        else val = __dadd_rn(A.lower, __ddiv_rn(__dmul_rn(__dsub_rn(A.upper, A.lower), __dsub_rn(v, dd.fmin)), dd.den));
-                        if (val != 0.0) x = A.emulate_text ? hafdec::text6(val, &u6) : val;
-                    }
-                    if (u4 || u6) *A.unsupported_flag = 1;
-                }
-            }
+            if (b < nb && d < A.D) x = exact_scaled_input(A, A.list ? A.list[e0 + b] : (int)(e0 + b), d);
             xs[t] = x;
         }
         __syncthreads();
@@ -963,6 +975,145 @@ __global__ void __launch_bounds__(128) svm_exact_sum_kernel(const ExactArgs A) {
             for (int k = 0; k < cnt; k++) sum = __dadd_rn(sum, __shfl_sync(0xffffffffu, mine, k));
         }
         if (lane == 0) A.dec[A.list ? A.list[e] : (int)e] = __dsub_rn(sum, A.rho);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Guard band, tier 2: FP64 FMA contraction.  Every window the FP32 / tensor contraction left inside the guard band is
+// re-evaluated from the bit-exact inputs with  d^2 = |x|^2 + |sv|^2 - 2 x.sv  in FP64 (one DFMA per element instead of
+// the reference order's sub / mul / add) and an unordered FP64 sum.  Its error is <= ~1e-12 of
+// E = sum |coef_i| K_i (1 + gamma log2(e) (|x|^2 + |sv_i|^2)) -- the same order as the distance between libsvm's own
+// sequential evaluation and the real number -- so a window whose |dec| > tol2 * (E + |rho|) (tol2 = 1e-10) has the sign
+// libsvm computes; the rest (practically none) go on to tier 3, the exact-order kernels above.
+//   guard_inputs_kernel : Xg[e][d] = exact_scaled_input(list[e], d)           (entries e < cap)
+//   guard_fma_kernel    : grid (window blocks, SV slices); 16 windows x SVT support vectors per thread in registers;
+//                         partial sums per slice -> atomicAdd; the last slice to arrive finalises the 16 windows
+//                         (and re-zeroes the accumulators, so they need zeroing only once at allocation).
+// Entries beyond cap (a guard band mis-configured to be huge) are handed to tier 3 unchanged.
+// ---------------------------------------------------------------------------------------------------
+#define HAF_G2_WB 16
+struct Guard2Args {
+    const int* list; const unsigned* list_count; int cap;   // tier-1 guard list, capacity of Xg in entries
+    double* Xg;                  // [cap][Dsv]
+    const double* svn64;         // [Spad]  sum_d sv_d^2 in double
+    double* accum;               // [cap][2]  (decision sum, E), zero on entry, left zero
+    unsigned* tickets;           // [cap / WB + 1], zero on entry, left zero
+    double tol2;
+    int* list2; unsigned* list2_count;   // tier-3 list
+};
+__global__ void __launch_bounds__(256) guard_inputs_kernel(const ExactArgs A, const Guard2Args Q) {
+    const unsigned n = min(*Q.list_count, (unsigned)Q.cap);
+    const size_t total = (size_t)n * A.Dsv;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const unsigned e = (unsigned)(t / A.Dsv);
+        const int d = (int)(t - (size_t)e * A.Dsv);
+        Q.Xg[t] = d < A.D ? exact_scaled_input(A, Q.list[e], d) : 0.0;
+    }
+}
+template <int SVT>
+__global__ void __launch_bounds__(256) guard_fma_kernel(const ExactArgs A, const Guard2Args Q) {
+    constexpr int WB = HAF_G2_WB;
+    extern __shared__ double g2s[];       // xs [Dsv][WB], then xn [WB], red [8][WB][2]
+    const int Dsv = A.Dsv, Spad = A.Spad;
+    double* xs = g2s;
+    double* xn = g2s + (size_t)Dsv * WB;
+    double* red = xn + WB;
+    __shared__ unsigned s_ticket;
+    const unsigned total = *Q.list_count;
+    const unsigned n = min(total, (unsigned)Q.cap);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (blockIdx.x == 0 && blockIdx.y == 0)   // overflow of the tier-2 buffers: straight to tier 3
+        for (unsigned e = (unsigned)Q.cap + threadIdx.x; e < total; e += blockDim.x) Q.list2[atomicAdd(Q.list2_count, 1u)] = Q.list[e];
+    const int i0 = blockIdx.y * (256 * SVT);
+    const double g2 = A.gamma * 1.4426950408889634;
+    for (unsigned e0 = blockIdx.x * WB; e0 < n; e0 += gridDim.x * WB) {
+        const int nb = min((unsigned)WB, n - e0);
+        __syncthreads();
+        for (int t = threadIdx.x; t < WB * Dsv; t += blockDim.x) {
+            const int b = t / Dsv, d = t - b * Dsv;    // coalesced read of Xg rows
+            xs[d * WB + b] = b < nb ? Q.Xg[(size_t)(e0 + b) * Dsv + d] : 0.0;
+        }
+        __syncthreads();
+        for (int b = warp; b < WB; b += 8) {
+            double sq = 0.0;
+            for (int d = lane; d < Dsv; d += 32) { const double v = xs[d * WB + b]; sq = fma(v, v, sq); }
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+            if (lane == 0) xn[b] = sq;
+        }
+        __syncthreads();
+        double acc[WB][SVT];
+#pragma unroll
+        for (int b = 0; b < WB; b++)
+#pragma unroll
+            for (int k = 0; k < SVT; k++) acc[b][k] = 0.0;
+        const int ia = i0 + threadIdx.x;
+        for (int d = 0; d < Dsv; d++) {
+            double sv[SVT];
+#pragma unroll
+            for (int k = 0; k < SVT; k++) sv[k] = (ia + 256 * k < Spad) ? A.sv64T[(size_t)d * Spad + ia + 256 * k] : 0.0;
+            const double2* xr = reinterpret_cast<const double2*>(xs + d * WB);
+#pragma unroll
+            for (int b2 = 0; b2 < WB / 2; b2++) {
+                const double2 xv = xr[b2];   // broadcast 128-bit shared load: two windows
+#pragma unroll
+                for (int k = 0; k < SVT; k++) {
+                    acc[2 * b2][k] = fma(xv.x, sv[k], acc[2 * b2][k]);
+                    acc[2 * b2 + 1][k] = fma(xv.y, sv[k], acc[2 * b2 + 1][k]);
+                }
+            }
+        }
+        double ds[WB], es[WB];
+#pragma unroll
+        for (int b = 0; b < WB; b++) { ds[b] = 0.0; es[b] = 0.0; }
+#pragma unroll
+        for (int k = 0; k < SVT; k++) {
+            const int i = ia + 256 * k;
+            if (i < A.S) {
+                const double cf = A.coef64[i], sn = Q.svn64[i];
+#pragma unroll
+                for (int b = 0; b < WB; b++) {
+                    const double base = xn[b] + sn;
+                    const double d2 = fmax(fma(-2.0, acc[b][k], base), 0.0);
+                    const double tk = cf * exp(-A.gamma * d2);
+                    ds[b] += tk;
+                    es[b] = fma(fabs(tk), fma(g2, base, 1.0), es[b]);
+                }
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < WB; b++) {
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) {
+                ds[b] += __shfl_xor_sync(0xffffffffu, ds[b], o);
+                es[b] += __shfl_xor_sync(0xffffffffu, es[b], o);
+            }
+            if (lane == 0) { red[(warp * WB + b) * 2] = ds[b]; red[(warp * WB + b) * 2 + 1] = es[b]; }
+        }
+        __syncthreads();
+        if (threadIdx.x < 2 * WB) {
+            const int b = threadIdx.x >> 1, c = threadIdx.x & 1;
+            double v = 0.0;
+            for (int w8 = 0; w8 < 8; w8++) v += red[(w8 * WB + b) * 2 + c];
+            if (b < nb) atomicAdd(Q.accum + (size_t)(e0 + b) * 2 + c, v);
+        }
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) s_ticket = atomicAdd(Q.tickets + e0 / WB, 1u);
+        __syncthreads();
+        if (s_ticket == gridDim.y - 1) {   // every slice of these windows has been added: finalise
+            __threadfence();
+            if (threadIdx.x < nb) {
+                const unsigned e = e0 + threadIdx.x;
+                const double sum = atomicAdd(Q.accum + (size_t)e * 2, 0.0), E = atomicAdd(Q.accum + (size_t)e * 2 + 1, 0.0);
+                Q.accum[(size_t)e * 2] = 0.0; Q.accum[(size_t)e * 2 + 1] = 0.0;
+                const int w = Q.list[e];
+                const double dv = sum - A.rho;
+                A.dec[w] = dv;
+                if (!(fabs(dv) > Q.tol2 * (E + fabs(A.rho)))) Q.list2[atomicAdd(Q.list2_count, 1u)] = w;
+            }
+            if (threadIdx.x == 0) Q.tickets[e0 / WB] = 0;
+        }
     }
 }
 
@@ -1117,10 +1268,12 @@ __global__ void copy_params_kernel(const uint4* __restrict__ src_host, uint4* __
     for (; i < n16; i += stride) dst[i] = src_host[i];
 }
 
-// counters: [0] windows of this chunk, [1] guard windows of this chunk -> running totals in [8], [9]
+// counters: [0] windows of this chunk, [1] guard windows, [6] exact-order windows of this chunk -> running totals in [8], [9], [11]
 __global__ void accumulate_counts_kernel(unsigned* cnt) {
     cnt[8] += cnt[0];
     cnt[9] += cnt[1];
+    cnt[11] += cnt[6];   // windows that went on to the exact-order kernels (tier 3)
+    cnt[6] = 0;
 }
 
 // debug: device text round trips

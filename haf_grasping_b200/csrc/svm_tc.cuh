@@ -2,16 +2,16 @@
 //
 //   dec[w] = sum_n coef[n] * exp2(c * (||x_w||^2 + ||sv_n||^2 - 2 x_w . sv_n)) - rho,     c = -gamma * log2(e)
 //
-// x and sv are split into two bf16 terms (x = x_hi + x_lo, 16 significant bits together); the contraction is
-// three tensor-core products accumulated in FP32 in TMEM:  x_hi.sv_hi + x_hi.sv_lo + x_lo.sv_hi   (the dropped
-// x_lo.sv_lo term is ~2^-18 relative).  The error of the resulting decision value is measured in the tests and is
+// x and sv are split into two fp16 terms (x = x_hi + x_lo, 22 significant bits together, absolute floor 2^-25);
+// the contraction is three tensor-core products accumulated in FP32 in TMEM:  x_hi.sv_hi + x_hi.sv_lo + x_lo.sv_hi
+// (the dropped x_lo.sv_lo term is ~2^-24 relative).  Round 1 used bf16 pairs (16 bits): same cost, 30x the error.  The error of the resulting decision value is measured in the tests and is
 // far inside the guard band; windows inside the band are re-evaluated in FP64 by svm_exact_kernel, so labels equal
 // the reference's (svm.cpp:2459-2533).
 //
 // Kernel structure (one persistent CTA per SM, 192 threads, warp specialised):
 //   warp 0   TMA producer : cp.async.bulk.tensor 2D loads of the four operand tiles of a k-block into a
 //                           2-stage shared-memory ring (128B-swizzled, K-major): X_hi, X_lo [128 x 64] and
-//                           SV_hi, SV_lo [256 x 64] bf16 = 96 KB per stage, mbarrier complete_tx.
+//                           SV_hi, SV_lo [256 x 64] fp16 = 96 KB per stage, mbarrier complete_tx.
 //   warp 1   MMA issuer   : one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=256, K=16),
 //                           3 products x 4 k-slices per stage, into one of two 128x256 FP32 accumulators in TMEM
 //                           (512 columns = all of TMEM); tcgen05.commit releases the smem stage / publishes the
@@ -21,7 +21,7 @@
 // Work item = (window tile of 128, split of the SV tiles); small problems split the SV range over CTAs.
 #pragma once
 #include <cuda.h>
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -29,7 +29,7 @@ namespace haftc {
 
 constexpr int BM = 128;      // windows per tile (UMMA M)
 constexpr int BN = 256;      // support vectors per tile (UMMA N)
-constexpr int BK = 64;       // bf16 elements per k-block = 128 bytes = one swizzle row
+constexpr int BK = 64;       // fp16 elements per k-block = 128 bytes = one swizzle row
 constexpr int STAGES = 2;
 constexpr int A_TILE_BYTES = BM * BK * 2;   // 16 KB
 constexpr int B_TILE_BYTES = BN * BK * 2;   // 32 KB
@@ -70,7 +70,7 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem]^T ; kind::f16 covers bf16 inputs with FP32 accumulation
+// D[tmem] (+)= A[smem] * B[smem]^T ; kind::f16: fp16 (or bf16) inputs, FP32 accumulation
 __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t"
@@ -84,8 +84,8 @@ __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t
 __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
     return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
-// instruction descriptor: D = F32 (bit 4), A = B = BF16 (bits 7, 10), K-major both, N >> 3 at bit 17, M >> 4 at bit 24
-constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// instruction descriptor: D = F32 (bit 4), A = B = F16 (format fields at bits 7 and 10 = 0; 1 would be BF16), K-major both, N >> 3 at bit 17, M >> 4 at bit 24
+constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
@@ -103,11 +103,18 @@ __device__ __forceinline__ float ex2_approx(float x) {
                    "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]) \
                  : "r"(taddr))
 
-// svtab[n] = { c * ||sv_n||^2 , coef_n }  (padding SVs: coef = 0).  dec_acc / asum_acc must be zeroed before launch.
+// svtab[n] = { c * ||sv_n||^2 , coef_n , |coef_n| * |c| * ||sv_n||^2 , 0 }  (padding SVs: coef = 0).
+// dec_acc / asum_acc must be zeroed before launch.
+//
+// GUARD SCALE.  Next to the decision sum the epilogue accumulates  E = sum_i |coef_i| K_i (1 + |c| (||x||^2 + ||sv_i||^2)):
+// a term's FP32 error is K_i times the absolute error of its exponent argument, which grows with the magnitude of the
+// three numbers the argument is assembled from (c xn, c svn, -2 c dot; |2 dot| <= xn + svn) -- a flat fraction of
+// sum |coef| K under-estimates it by that factor for models with a large gamma (measured: tools/dec_error_probe.py).
+// Windows with |dec| <= guard_rel * (E + |rho|) are re-evaluated by the FP64 exact path.
 __global__ void __launch_bounds__(THREADS, 1)
 svm_rbf_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl,
                   const __grid_constant__ CUtensorMap tmSh, const __grid_constant__ CUtensorMap tmSl,
-                  const float* __restrict__ xn, const float2* __restrict__ svtab, float c, const unsigned* __restrict__ win_count,
+                  const float* __restrict__ xn, const float4* __restrict__ svtab, float c, const unsigned* __restrict__ win_count,
                   int n_ntiles, int nsplit, int kblocks, int last_slices, double* __restrict__ dec_acc, float* __restrict__ asum_acc) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // 128B swizzle needs 1024-byte aligned tiles
@@ -178,7 +185,7 @@ svm_rbf_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constan
                         const uint64_t d_bh = make_desc_sw128(st + 2 * A_TILE_BYTES), d_bl = make_desc_sw128(st + 2 * A_TILE_BYTES + B_TILE_BYTES);
                         const int slices = (kb == kblocks - 1) ? last_slices : (BK / 16);
                         for (int k = 0; k < slices; k++) {
-                            const uint64_t adv = (uint64_t)(k * 2);  // 16 bf16 = 32 bytes = 2 x 16-byte units
+                            const uint64_t adv = (uint64_t)(k * 2);  // 16 fp16 = 32 bytes = 2 x 16-byte units
                             tc_mma(tmem_d, d_ah + adv, d_bh + adv, IDESC, (kb | k) ? 1u : 0u);
                             tc_mma(tmem_d, d_ah + adv, d_bl + adv, IDESC, 1u);
                             tc_mma(tmem_d, d_al + adv, d_bh + adv, IDESC, 1u);
@@ -204,8 +211,8 @@ svm_rbf_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constan
                 const uint32_t a = acc_it & 1u, aph = (acc_it >> 1) & 1u;
                 mbar_wait(bar_tfull + 8 * a, aph);
                 tc_fence_after();
-                float ps = 0.0f, pa = 0.0f;
-                const float2* tab = svtab + (size_t)nt * BN;
+                float ps = 0.0f, pa = 0.0f, pb = 0.0f;
+                const float4* tab = svtab + (size_t)nt * BN;
 #pragma unroll 1
                 for (int ch = 0; ch < BN / 32; ch++) {
                     uint32_t r[32];
@@ -214,18 +221,19 @@ svm_rbf_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constan
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                     for (int j = 0; j < 32; j++) {
-                        const float2 t = __ldg(tab + ch * 32 + j);
+                        const float4 t = __ldg(tab + ch * 32 + j);
                         float arg = fmaf(__uint_as_float(r[j]), c2, u + t.x);  // c * (xn + svn - 2 dot)
                         arg = fminf(arg, 0.0f);                                // d^2 >= 0
                         const float e = ex2_approx(arg);
                         ps = fmaf(t.y, e, ps);
-                        pa = fmaf(fabsf(t.y), e, pa);
+                        pa = fmaf(fabsf(t.y), e, pa);   // sum |coef| K
+                        pb = fmaf(t.z, e, pb);          // sum |coef| K |c| svn
                     }
                 }
                 tc_fence_before();
                 mbar_arrive(bar_tempty + 8 * a);
                 dsum += (double)ps;
-                asum += pa;
+                asum += fmaf(1.0f - u, pa, pb);   // sum_i |coef_i| K_i (1 + |c| (xn + svn_i)): the scale of the FP32 error
             }
             if (m < W && nt1 > nt0) {
                 atomicAdd(dec_acc + m, dsum);
@@ -255,7 +263,7 @@ constexpr int STAGES2 = 3;
 constexpr int B2_TILE_BYTES = (BN / 2) * BK * 2;                      // 16 KB: this CTA's half of the SV tile
 constexpr int STAGE2_BYTES = 2 * A_TILE_BYTES + 2 * B2_TILE_BYTES;    // 64 KB per CTA
 constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 + 256;
-constexpr uint32_t IDESC2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+constexpr uint32_t IDESC2 = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address -> the leader CTA's copy
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -302,7 +310,7 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 svm_rbf_tc2_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl,
                    const __grid_constant__ CUtensorMap tmSh2, const __grid_constant__ CUtensorMap tmSl2,
-                   const float* __restrict__ xn, const float2* __restrict__ svtab, float c, const unsigned* __restrict__ win_count,
+                   const float* __restrict__ xn, const float4* __restrict__ svtab, float c, const unsigned* __restrict__ win_count,
                    int n_ntiles, int nsplit, int kblocks, int last_slices, double* __restrict__ dec_acc, float* __restrict__ asum_acc) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -404,8 +412,8 @@ svm_rbf_tc2_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_consta
                 const uint32_t a = acc_it & 1u, aph = (acc_it >> 1) & 1u;
                 mbar_wait(bar_tfull + 8 * a, aph);
                 tc_fence_after();
-                float ps = 0.0f, pa = 0.0f;
-                const float2* tab = svtab + (size_t)nt * BN;
+                float ps = 0.0f, pa = 0.0f, pb = 0.0f;
+                const float4* tab = svtab + (size_t)nt * BN;
 #pragma unroll 1
                 for (int ch = 0; ch < BN / 32; ch++) {
                     uint32_t r[32];
@@ -414,18 +422,19 @@ svm_rbf_tc2_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_consta
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                     for (int j = 0; j < 32; j++) {
-                        const float2 t = __ldg(tab + ch * 32 + j);
-                        float arg = fmaf(__uint_as_float(r[j]), c2, u + t.x);
-                        arg = fminf(arg, 0.0f);
+                        const float4 t = __ldg(tab + ch * 32 + j);
+                        float arg = fmaf(__uint_as_float(r[j]), c2, u + t.x);  // c * (xn + svn - 2 dot)
+                        arg = fminf(arg, 0.0f);                                // d^2 >= 0
                         const float e = ex2_approx(arg);
                         ps = fmaf(t.y, e, ps);
-                        pa = fmaf(fabsf(t.y), e, pa);
+                        pa = fmaf(fabsf(t.y), e, pa);   // sum |coef| K
+                        pb = fmaf(t.z, e, pb);          // sum |coef| K |c| svn
                     }
                 }
                 tc_fence_before();
                 mbar_arrive_cluster((bar_tempty + 8 * a) & PEER_MASK);  // on the LEADER's barrier (count 256)
                 dsum += (double)ps;
-                asum += pa;
+                asum += fmaf(1.0f - u, pa, pb);   // sum_i |coef_i| K_i (1 + |c| (xn + svn_i)): the scale of the FP32 error
             }
             if (m < W && nt1 > nt0) {
                 atomicAdd(dec_acc + m, dsum);
@@ -442,16 +451,17 @@ svm_rbf_tc2_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_consta
     }
 }
 
-// dec = sum - rho, guard test (same rule as the SIMT kernel)
-__global__ void svm_finalize_kernel(double* __restrict__ dec, const float* __restrict__ asum, const unsigned* __restrict__ win_count,
-                                    double rho, float guard_rel, unsigned char* __restrict__ guard_flag, int* __restrict__ guard_list,
+// dec = sum - rho, guard test (same rule as the SIMT kernel; NaN-safe: anything not provably outside the band is inside)
+__global__ void svm_finalize_kernel(double* __restrict__ dec, const float* __restrict__ asum, const float* __restrict__ xn,
+                                    const unsigned* __restrict__ win_count, double rho, float guard_rel, unsigned char* __restrict__ guard_flag, int* __restrict__ guard_list,
                                     unsigned* __restrict__ guard_count) {
     const unsigned W = *win_count;
     const unsigned m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= W) return;
     const double dv = dec[m] - rho;
     dec[m] = dv;
-    const bool g = fabs(dv) <= (double)guard_rel * ((double)asum[m] + fabs(rho));
+    // xn = +inf marks a window whose inputs left the fp16 range (features_tc_kernel): always re-evaluated exactly
+    const bool g = !(fabs(dv) > (double)guard_rel * ((double)asum[m] + fabs(rho))) || !(xn[m] < 3.0e38f);  // asum = E above
     guard_flag[m] = g ? 1 : 0;
     if (g) guard_list[atomicAdd(guard_count, 1u)] = (int)m;
 }

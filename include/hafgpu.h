@@ -39,7 +39,7 @@ extern "C" {
 typedef struct haf_ctx haf_ctx;
 
 /* svm_mode (0 = what a zero-initialised config gets = the production path) */
-#define HAF_SVM_TENSOR_GUARD 0 /* tcgen05 split-bf16 contraction in TMEM + FP64 exact-order re-evaluation inside the guard band */
+#define HAF_SVM_TENSOR_GUARD 0 /* tcgen05 split-fp16 contraction in TMEM + FP64 re-evaluation inside the guard band (FMA tier, then exact order) */
 #define HAF_SVM_FP64_EXACT 1   /* every window in FP64, libsvm's summation order (svm.cpp:326-365, :2500-2514) */
 #define HAF_SVM_FP32_GUARD 2   /* FP32 SIMT contraction (CUDA cores) + the same FP64 guard band; conservative mode */
 
@@ -54,9 +54,13 @@ typedef struct {
     int device;                /* CUDA ordinal; one context (and one process) per GPU                         */
     int emulate_text_roundtrip; /* 1 = reproduce the "%.4g" / "%g" text round trips (reference-exact)         */
     int svm_mode;              /* HAF_SVM_*                                                                   */
-    float guard_rel;           /* guard band half-width as a fraction of sum_i |coef_i| K_i; <=0 -> default   */
+    float guard_rel;           /* guard band half-width as a fraction of E + |rho|,
+                                  E = sum_i |coef_i| K_i (1 + gamma log2(e) (|x|^2 + |sv_i|^2)); <=0 -> default
+                                  (4e-6 tensor, 2e-6 FP32 SIMT: >= 12x the measured error)                    */
     int reserved[4];           /* [0]: tensor-path kernel variant, 0 = CTA-pair (cta_group::2, default), 1 = single CTA;
-                                  [1]: 1 = always use the point-parallel binning kernel (no whole-cloud CTAs) */
+                                  [1]: 1 = always use the point-parallel binning kernel (no whole-cloud CTAs);
+                                  [2]: guard band tier 2 (FP64 FMA re-evaluation): 0 = on, 1 = off (every guard window goes
+                                       to the exact-order kernels), 2 = on, but every window escalates as well (tests) */
 } haf_config;
 
 /* One grasp goal = the hot-path fields of GraspInput (msg/GraspInput.msg:3-15). */
@@ -105,6 +109,7 @@ typedef struct {
     float ms_bin, ms_integral, ms_mask, ms_features, ms_svm, ms_guard, ms_score;
     long long n_points, n_units, n_windows, n_guard, launches;
     long long n_chunks; /* passes over the stage sequence (each launches every stage kernel once) */
+    long long n_exact;  /* guard windows that went on to the exact-order FP64 kernels (tier 3); svm_mode 1: 0 */
 } haf_timing;
 
 /* ---- lifetime --------------------------------------------------------------------------------------------- */
@@ -152,7 +157,7 @@ int haf_debug_window_count(const haf_ctx* ctx);
 int haf_debug_windows(haf_ctx* ctx, int* win_unit_cell, int cap_windows);
 /* raw features [W][F] float (calc_featurevalue), scaled SVM inputs [W][D] double (after both text round trips) */
 int haf_debug_features(haf_ctx* ctx, float* raw, double* scaled, int cap_windows);
-/* tensor mode: SVM inputs as the tensor-core contraction sees them (bf16 hi + lo, as float) [W][D] */
+/* tensor mode: SVM inputs as the tensor-core contraction sees them (fp16 hi + lo, as float) [W][D] */
 int haf_debug_tensor_inputs(haf_ctx* ctx, float* x, int cap_windows);
 /* decision values, libsvm labels and guard flags [W] of the last search */
 int haf_debug_decisions(haf_ctx* ctx, double* dec, int* labels, unsigned char* guard, int cap_windows);

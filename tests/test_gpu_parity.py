@@ -49,9 +49,9 @@ def hg():
 class Pair:
     """GPU context + oracle on the same three files."""
 
-    def __init__(self, hg, orc, model, **kw):
-        self.gpu = hg.GraspSearch(FEATURES, RANGE, model, **kw)
-        self.orc = orc.Oracle(FEATURES, RANGE, model)
+    def __init__(self, hg, orc, model, range_path=RANGE, **kw):
+        self.gpu = hg.GraspSearch(FEATURES, range_path, model, **kw)
+        self.orc = orc.Oracle(FEATURES, range_path, model)
         self.G = kw.get("grid", 56)
         self.step = kw.get("roll_step_deg", 15)
         self.rmax = kw.get("roll_max_deg", 190)
@@ -214,7 +214,7 @@ def test_tensor_core_mode_single_cta_variant(hg, oracle_lib, trained_model, clou
 
 @pytest.mark.parametrize("name", ["pcd2", "pcd7", "table1", "plastic_mug2"])
 def test_tensor_core_mode(hg, oracle_lib, trained_model, clouds, name):
-    """HAF_SVM_TENSOR_GUARD: tcgen05 split-bf16 contraction + FP64 guard band; everything before and after the
+    """HAF_SVM_TENSOR_GUARD: tcgen05 split-fp16 contraction + FP64 guard band; everything before and after the
     decision values is shared with the SIMT mode, labels / evals / best grasp must equal the oracle's."""
     p = Pair(hg, oracle_lib, trained_model, svm_mode=hg.HAF_SVM_TENSOR_GUARD)
     try:
@@ -224,16 +224,17 @@ def test_tensor_core_mode(hg, oracle_lib, trained_model, clouds, name):
 
 
 def test_tensor_mode_fast_tier_inputs_track_the_exact_scaled_values(hg, oracle_lib, trained_model, clouds):
-    """The tensor path's operands come from a fast tier (double-precision "%.4g" decision, no "%g" step, 16-bit split).
-    They must sit within 16-bit rounding of the exact scaled values; only a mis-decided decimal near-tie may differ by
-    one 4th-digit step, and none is expected on this data."""
+    """The tensor path's operands come from a fast tier (double-precision "%.4g" decision, float scaling, no "%g" step,
+    fp16 hi + lo split = 22 bits).  They must sit within the skipped 6-digit rounding (<= 5e-6 relative) plus the float
+    scaling error (a few 1e-7 absolute: svm-scale's -1 + 2 (v - min) / (max - min) cancels) of the exact scaled values;
+    only a mis-decided decimal near-tie may differ by one 4th-digit step, and none is expected on this data."""
     gpu = hg.GraspSearch(FEATURES, RANGE, trained_model, svm_mode=hg.HAF_SVM_TENSOR_GUARD)
     try:
         gpu.search(clouds["table1"])
         x = gpu.debug_tensor_inputs().astype(np.float64)
         _, scaled = gpu.debug_features(raw=False)       # bit-exact emulation tier (checked against the oracle elsewhere)
         err = np.abs(x - scaled)
-        tol = 2.0 ** -16 * np.abs(scaled) + 1e-6          # hi+lo carries >= 16 bits; "%g" skipped: <= 5e-7 relative
+        tol = 5.5e-6 * np.abs(scaled) + 5e-7
         assert (err <= tol).mean() == 1.0, (err.max(), (err > tol).sum())
     finally:
         gpu.close()
@@ -255,14 +256,59 @@ def test_tensor_core_mode_synth_models_and_batch(hg, oracle_lib, tmp_models):
             p.close()
 
 
+@pytest.mark.parametrize("tier2", [0, 1, 2])
 @pytest.mark.parametrize("mode", ["tensor", "simt"])
-def test_guard_band_catches_near_zero_decisions(hg, oracle_lib, tmp_models, clouds, mode):
-    """rho chosen so that many decision values sit next to 0: labels must still equal the oracle's."""
+def test_guard_band_catches_near_zero_decisions(hg, oracle_lib, tmp_models, clouds, mode, tier2):
+    """rho chosen so that many decision values sit next to 0: labels must still equal the oracle's.
+    tier2 = 0: guard windows are settled by the FP64 FMA tier (none should need the exact-order kernels);
+    1: FMA tier off, all of them go through the exact-order kernels; 2: both tiers run on every guard window."""
     model = tmp_models(256, rho=-0.2972253)  # a decision value of pcd2 / roll 0 with the synth model is -0.2972253033...
-    p = Pair(hg, oracle_lib, model, guard_rel=1e-3, svm_mode=hg.HAF_SVM_TENSOR_GUARD if mode == "tensor" else hg.HAF_SVM_FP32_GUARD)
+    p = Pair(hg, oracle_lib, model, guard_rel=1e-3, guard_tier2=tier2,
+             svm_mode=hg.HAF_SVM_TENSOR_GUARD if mode == "tensor" else hg.HAF_SVM_FP32_GUARD)
     try:
+        # tier 2 alone leaves FMA-order decision values (<= 1e-12 relative) on the guard windows; the exact-order
+        # kernels leave libsvm's order (only exp() differs)
         _, _, guard = check_search(p, clouds["pcd2"], hg, oracle_lib, model)
         assert guard.sum() > 0
+        t = p.gpu.timing()
+        assert t.n_guard == guard.sum()
+        assert t.n_exact == (0 if tier2 == 0 else t.n_guard)
+    finally:
+        p.close()
+
+
+def test_guard_tier2_decision_values_match_fp64_order(hg, oracle_lib, tmp_models, clouds):
+    """With a guard band so wide that EVERY window is re-evaluated by the FP64 FMA tier, all decision values must sit
+    within 1e-12 * sum|coef| of the oracle's libsvm-order values (the bound tier 2's own escalation test relies on)."""
+    model = tmp_models(256)
+    p = Pair(hg, oracle_lib, model, guard_rel=1e6, svm_mode=hg.HAF_SVM_TENSOR_GUARD)
+    try:
+        _, _, guard = check_search(p, clouds["pcd3"], hg, oracle_lib, model, dec_rtol=1e-12)
+        assert guard.all()
+        assert p.gpu.timing().n_exact == 0
+    finally:
+        p.close()
+
+
+def test_tensor_mode_inputs_beyond_fp16_range_take_the_exact_path(hg, oracle_lib, tmp_models, clouds, tmp_path):
+    """A range file whose span for one feature is tiny scales that feature far beyond +-65504 (svm-scale does not clamp,
+    svm-scale.c:339-346).  The tensor path clamps its fp16 operands and must send every such window to the FP64 exact
+    path: labels, scores and the best grasp still equal the oracle's."""
+    lines = open(RANGE).read().split("\n")
+    idx, lo, hi = lines[2 + 4].split()          # 5th feature line ("idx min max")
+    lines[2 + 4] = "%s %s %.12g" % (idx, lo, float(lo) + 1e-7)
+    rp = str(tmp_path / "narrow.range")
+    open(rp, "w").write("\n".join(lines))
+    model = tmp_models(256)
+    p = Pair(hg, oracle_lib, model, range_path=rp, svm_mode=hg.HAF_SVM_TENSOR_GUARD)
+    try:
+        _, _, guard = check_search(p, clouds["pcd2"], hg, oracle_lib, model)
+        win = p.gpu.debug_windows()
+        _, scaled = p.gpu.debug_features(raw=False)
+        scaled = scaled[np.lexsort((win[:, 1], win[:, 0]))]     # same order as the guard flags check_search returns
+        big = (np.abs(scaled) > 65000.0).any(axis=1)
+        assert big.sum() > 0, "the narrowed range did not push any value beyond the fp16 range"
+        assert guard[big].all()
     finally:
         p.close()
 

@@ -16,15 +16,56 @@ F = os.path.join(ROOT, "tests", "golden", "refdata", "Features.txt")
 R = os.path.join(ROOT, "tests", "golden", "refdata", "range21062012_allfeatures")
 
 
-def run(model, xyz, mode):
+def run(model, xyz, mode, want_scaled=False):
     g = h.GraspSearch(F, R, model, svm_mode=mode)
     res = g.search(xyz)
     win = g.debug_windows()
     dec, lab, guard = g.debug_decisions()
     order = np.lexsort((win[:, 1], win[:, 0]))
     t = g.timing()
+    scaled = g.debug_features(raw=False)[1][order] if want_scaled else None
     g.close()
-    return dec[order], lab[order], guard[order], res["best"].astuple(), t
+    return dec[order], lab[order], guard[order], res["best"].astuple(), t, scaled
+
+
+def load_model(path):
+    """libsvm text model -> (gamma, rho, coef [S], sv [S][D]) dense float64"""
+    gamma = rho = 0.0
+    coefs, rows, dmax = [], [], 0
+    with open(path) as fh:
+        sv = False
+        for ln in fh:
+            if sv:
+                t = ln.split()
+                if not t:
+                    continue
+                coefs.append(float(t[0]))
+                r = [(int(a.split(":")[0]), float(a.split(":")[1])) for a in t[1:]]
+                rows.append(r)
+                dmax = max([dmax] + [i for i, _ in r])
+            elif ln.startswith("gamma"):
+                gamma = float(ln.split()[1])
+            elif ln.startswith("rho"):
+                rho = float(ln.split()[1])
+            elif ln.startswith("SV"):
+                sv = True
+    m = np.zeros((len(rows), dmax))
+    for k, r in enumerate(rows):
+        for i, v in r:
+            m[k, i - 1] = v
+    return gamma, rho, np.array(coefs), m
+
+
+def guard_scale(model, scaled):
+    """E + |rho| per window in float64, E = sum_i |coef_i| K_i (1 + gamma log2(e) (|x|^2 + |sv_i|^2)): the quantity the
+    guard band is a fraction of (svm_tc.cuh, GUARD SCALE)"""
+    gamma, rho, coef, sv = model
+    D = max(sv.shape[1], scaled.shape[1])
+    x = np.zeros((len(scaled), D)); x[:, :scaled.shape[1]] = scaled
+    s = np.zeros((len(sv), D)); s[:, :sv.shape[1]] = sv
+    base = (x * x).sum(1)[:, None] + (s * s).sum(1)[None, :]
+    d2 = base - 2.0 * x @ s.T
+    return (np.exp(-gamma * np.maximum(d2, 0.0)) * (1.0 + gamma * 1.4426950408889634 * base)) @ np.abs(coef) + abs(rho)
 
 
 def main():
@@ -47,14 +88,15 @@ def main():
                     sv = True
         scale = sum(coefs)
         for cn, xyz in clouds.items():
-            d64, l64, _, b64, _ = run(mp, xyz, h.HAF_SVM_FP64_EXACT)
+            d64, l64, _, b64, _, scaled = run(mp, xyz, h.HAF_SVM_FP64_EXACT, want_scaled=True)
+            gs = guard_scale(load_model(mp), scaled)
             for mode, name in ((h.HAF_SVM_FP32_GUARD, "simt"), (h.HAF_SVM_TENSOR_GUARD, "tensor")):
-                d, lab, guard, b, t = run(mp, xyz, mode)
+                d, lab, guard, b, t, _ = run(mp, xyz, mode)
                 ng = ~guard.astype(bool)
                 err = np.abs(d - d64)
-                print("%-10s %-10s %-7s W=%d max|err|=%.3e (%.2e of sum|coef|=%.1f) rms=%.2e guard=%d labels_equal=%s best_equal=%s min|dec| outside guard=%.3e device_ms=%.3f"
-                      % (mn, cn, name, len(d), err[ng].max(), err[ng].max() / scale, scale, np.sqrt((err[ng] ** 2).mean()), int(guard.sum()),
-                         bool((lab == l64).all()), b == b64, np.abs(d[ng]).min(), t.ms_total))
+                print("%-10s %-10s %-7s W=%d max|err|=%.3e (%.2e of sum|coef|=%.1f; max err/(E+|rho|)=%.2e, rms %.2e) guard=%d labels_equal=%s best_equal=%s min|dec| outside guard=%.3e device_ms=%.3f"
+                      % (mn, cn, name, len(d), err[ng].max(), err[ng].max() / scale, scale, (err[ng] / gs[ng]).max(), np.sqrt(((err[ng] / gs[ng]) ** 2).mean()),
+                         int(guard.sum()), bool((lab == l64).all()), b == b64, np.abs(d[ng]).min(), t.ms_total))
 
 
 if __name__ == "__main__":
