@@ -63,7 +63,7 @@ EXPORTS = ["haf_create", "haf_destroy", "haf_last_error", "haf_get_info", "haf_s
            "haf_get_timing", "haf_launch_count", "haf_search", "haf_search_batch", "haf_search_batch_packed",
            "haf_build_transform", "haf_best_key", "haf_debug_window_count", "haf_debug_windows", "haf_debug_features",
            "haf_debug_decisions", "haf_debug_tensor_inputs", "haf_debug_integral", "haf_debug_cell_indices", "haf_debug_text_roundtrip",
-           "haf_version"]
+           "haf_version", "haf_svm_create", "haf_svm_destroy", "haf_svm_predict", "haf_scale_minmax", "haf_scale_apply"]
 
 _lib = None
 
@@ -110,6 +110,12 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     L.haf_debug_cell_indices.argtypes = [vp, vp, cs, cs, C.POINTER(haf_request), ci, vp]
     L.haf_debug_text_roundtrip.argtypes = [vp, vp, ci, vp, vp, ci, vp]
     L.haf_version.restype = C.c_char_p
+    L.haf_svm_create.argtypes = [C.POINTER(vp), C.c_char_p, ci, ci, ci, C.c_float]
+    L.haf_svm_destroy.argtypes = [vp]
+    L.haf_svm_destroy.restype = None
+    L.haf_svm_predict.argtypes = [vp, vp, vp, vp, ci, vp, vp]
+    L.haf_scale_minmax.argtypes = [ci, vp, vp, vp, ci, ci, vp, vp]
+    L.haf_scale_apply.argtypes = [ci, vp, vp, vp, ci, ci, vp, vp, C.c_double, C.c_double, vp]
     _lib = L
     return L
 
@@ -302,3 +308,74 @@ def build_transform(request: haf_request, roll: int, roll_step_deg: int = 15) ->
     M = (C.c_float * 16)()
     L.haf_build_transform(C.byref(request), roll, roll_step_deg, M)
     return np.array(M, np.float32)
+
+
+# ---- libsvm front ends (include/hafgpu.h) ---------------------------------------------------------
+def _csr(rows_or_dense):
+    """dense [n][D] array (zeros = absent) or (row_ptr, index, value) -> CSR arrays with libsvm's 1-based indices"""
+    if isinstance(rows_or_dense, tuple):
+        rp, idx, val = rows_or_dense
+        return (np.ascontiguousarray(rp, np.int64), np.ascontiguousarray(idx, np.int32), np.ascontiguousarray(val, np.float64))
+    x = np.asarray(rows_or_dense, np.float64)
+    nz = x != 0
+    rp = np.zeros(len(x) + 1, np.int64)
+    rp[1:] = np.cumsum(nz.sum(1))
+    r, c = np.nonzero(nz)
+    return rp, (c + 1).astype(np.int32), np.ascontiguousarray(x[r, c])
+
+
+class SvmPredictor:
+    """svm_predict on the GPU for a libsvm text model (C-SVC, RBF, two classes): what svm-predict-b200 binds."""
+
+    def __init__(self, model_path, device=0, svm_mode=HAF_SVM_TENSOR_GUARD, min_dims=0, guard_rel=0.0):
+        self.L = load_library()
+        self.h = C.c_void_p()
+        rc = self.L.haf_svm_create(C.byref(self.h), model_path.encode(), device, svm_mode, min_dims, guard_rel)
+        if rc != 0:
+            raise HafError(rc, (self.L.haf_last_error(None) or b"").decode())
+        self.info = haf_info()
+        self.L.haf_get_info(self.h, C.byref(self.info))
+
+    def predict(self, rows, want_dec=True):
+        rp, idx, val = _csr(rows)
+        n = len(rp) - 1
+        labels = np.zeros(max(n, 1), np.float64)
+        dec = np.zeros(max(n, 1), np.float64) if want_dec else None
+        rc = self.L.haf_svm_predict(self.h, _ptr(rp), _ptr(idx), _ptr(val), n, _ptr(labels), _ptr(dec))
+        if rc != 0:
+            raise HafError(rc, (self.L.haf_last_error(self.h) or b"").decode())
+        return labels[:n], (dec[:n] if want_dec else None)
+
+    def timing(self):
+        t = haf_timing()
+        self.L.haf_get_timing(self.h, C.byref(t))
+        return t
+
+    def close(self):
+        if self.h:
+            self.L.haf_svm_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+def scale_minmax(rows, max_index, fmin=None, fmax=None, device=0):
+    """svm-scale pass 2 on the device; returns (fmin, fmax) arrays of max_index + 1 entries (entry 0 unused)."""
+    L = load_library()
+    rp, idx, val = _csr(rows)
+    fmin = np.full(max_index + 1, np.finfo(np.float64).max) if fmin is None else np.ascontiguousarray(fmin, np.float64)
+    fmax = np.full(max_index + 1, -np.finfo(np.float64).max) if fmax is None else np.ascontiguousarray(fmax, np.float64)
+    rc = L.haf_scale_minmax(device, _ptr(rp), _ptr(idx), _ptr(val), len(rp) - 1, max_index, _ptr(fmin), _ptr(fmax))
+    if rc != 0:
+        raise HafError(rc, (L.haf_last_error(None) or b"").decode())
+    return fmin, fmax
+
+
+def scale_apply(rows, max_index, fmin, fmax, lower=-1.0, upper=1.0, device=0):
+    """svm-scale pass 3 on the device: dense [n][max_index] scaled values (0 = not printed)."""
+    L = load_library()
+    rp, idx, val = _csr(rows)
+    out = np.zeros((len(rp) - 1, max_index), np.float64)
+    rc = L.haf_scale_apply(device, _ptr(rp), _ptr(idx), _ptr(val), len(rp) - 1, max_index, _ptr(np.ascontiguousarray(fmin, np.float64)),
+                           _ptr(np.ascontiguousarray(fmax, np.float64)), lower, upper, _ptr(out))
+    if rc != 0:
+        raise HafError(rc, (L.haf_last_error(None) or b"").decode())
+    return out

@@ -70,6 +70,28 @@ def build_cli(force: bool = False) -> str:
     return CLI
 
 
+SVM_PREDICT = os.path.join(LIB_DIR, "svm-predict-b200")
+SVM_SCALE = os.path.join(LIB_DIR, "svm-scale-b200")
+
+
+def build_svm_tools(force: bool = False):
+    """svm-predict-b200 / svm-scale-b200: command-line compatible front ends of libsvm's two programs."""
+    build_lib()
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    outs = []
+    for src, out in (("svm_predict_b200.cpp", SVM_PREDICT), ("svm_scale_b200.cpp", SVM_SCALE)):
+        srcs = [os.path.join(HOST_DIR, src), os.path.join(HOST_DIR, "libsvm_text.hpp")]
+        if force or not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs + [LIB]):
+            cmd = [cxx, "-O2", "-std=c++17", "-ffp-contract=off", "-o", out, srcs[0], "-L" + LIB_DIR, "-lhafgpu", "-Wl,-rpath,$ORIGIN"]
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                sys.stderr.write(res.stdout + res.stderr)
+                raise RuntimeError("g++ failed building " + os.path.basename(out))
+        outs.append(out)
+    return outs
+
+
 if __name__ == "__main__":
     print(build_lib(force=True, verbose="-v" in sys.argv))
     print(build_cli(force=True))
+    print(build_svm_tools(force=True))

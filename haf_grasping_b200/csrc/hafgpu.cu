@@ -136,6 +136,14 @@ struct haf_ctx {
     PinBuf<int> h_per_roll_top;
     PinBuf<unsigned> h_counters;
 
+    // libsvm front end (haf_svm_*): inputs given by the caller
+    bool svm_only = false;
+    const double* cur_xdense = nullptr;   // non-null while haf_svm_predict runs: exact_scaled_input reads it
+    DevBuf<double> d_xdense, d_labels;
+    DevBuf<long long> d_csr_ptr;
+    DevBuf<int> d_csr_idx;
+    DevBuf<double> d_csr_val;
+
     // state of the last search kept for the debug entry points
     int last_units = 0, last_unit_base = 0;
     unsigned last_W = 0;
@@ -214,10 +222,13 @@ static bool make_tensor_map(CUtensorMap* m, void* base, uint64_t krow, uint64_t 
               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-extern "C" int haf_create(haf_ctx** out, const haf_config* cfg) {
+// svm_only: context of the libsvm front end (haf_svm_create): model only, the SVM inputs are given by the caller, at
+// least min_dims dimensions wide.
+static int create_impl(haf_ctx** out, const haf_config* cfg, bool svm_only, int min_dims) {
     if (!out || !cfg) return create_fail(HAF_ERR_ARG, "haf_create: null argument");
     *out = nullptr;
-    if (!cfg->features_path || !cfg->range_path || !cfg->model_path) return create_fail(HAF_ERR_ARG, "haf_create: features_path, range_path and model_path are required");
+    if (!cfg->model_path || (!svm_only && (!cfg->features_path || !cfg->range_path)))
+        return create_fail(HAF_ERR_ARG, "haf_create: features_path, range_path and model_path are required");
     const int G = cfg->grid > 0 ? cfg->grid : 56;
     if (G < 16 || G > 1024 || (G & 1)) return create_fail(HAF_ERR_ARG, "haf_create: grid must be even and within 16..1024");
     const int step = cfg->roll_step_deg > 0 ? cfg->roll_step_deg : 15;
@@ -238,9 +249,9 @@ extern "C" int haf_create(haf_ctx** out, const haf_config* cfg) {
 
     std::string err;
     std::vector<hafhost::Feature> feats;
-    if (!hafhost::load_features(cfg->features_path, feats, err)) return create_fail(HAF_ERR_IO, err);
+    if (!svm_only && !hafhost::load_features(cfg->features_path, feats, err)) return create_fail(HAF_ERR_IO, err);
     hafhost::Range range;
-    if (!hafhost::load_range(cfg->range_path, range, err)) return create_fail(HAF_ERR_IO, err);
+    if (!svm_only && !hafhost::load_range(cfg->range_path, range, err)) return create_fail(HAF_ERR_IO, err);
     hafhost::Model model;
     bool unsupported = false;
     if (!hafhost::load_model(cfg->model_path, model, err, unsupported)) return create_fail(unsupported ? HAF_ERR_UNSUPPORTED : HAF_ERR_IO, err);
@@ -262,7 +273,7 @@ extern "C" int haf_create(haf_ctx** out, const haf_config* cfg) {
     // svm-scale's dimension table.  max_index = max(range file, data) (svm-scale.c:106-146); features without a
     // range entry would be scaled by the min/max of each roll's own data (:165-198): reproduced only when the
     // feature is structurally constant (all regions skipped -> single-valued -> dropped, :336-337).
-    const int max_index = std::max(range.max_index, F);
+    const int max_index = svm_only ? 0 : std::max(range.max_index, F);
     std::vector<DimDev> dims(max_index);
     int D_eff = 0;
     for (int i = 1; i <= max_index; i++) {
@@ -301,6 +312,13 @@ extern "C" int haf_create(haf_ctx** out, const haf_config* cfg) {
         d.slope = d.drop ? 0.0 : (range.upper - range.lower) / d.den;
         dims[i - 1] = d;
         if (!d.drop) D_eff = i;
+    }
+    if (svm_only) {   // inputs are given: every dimension up to the widest of model / data takes part (svm.cpp:328-364)
+        D_eff = std::max(std::max(model.max_index, min_dims), 1);
+        DimDev dz;
+        memset(&dz, 0, sizeof dz);
+        dz.feat = -1;
+        dims.assign(D_eff, dz);
     }
     if (D_eff == 0) return create_fail(HAF_ERR_UNSUPPORTED, "no feature survives scaling");
     const int D = D_eff;                              // trailing dropped dimensions are always 0: not stored
@@ -466,6 +484,189 @@ extern "C" int haf_create(haf_ctx** out, const haf_config* cfg) {
     return HAF_OK;
 }
 
+extern "C" int haf_create(haf_ctx** out, const haf_config* cfg) { return create_impl(out, cfg, false, 0); }
+
+// ---- libsvm front ends -------------------------------------------------------------------------
+static int svm_stage(haf_ctx* ctx, unsigned* cnt, size_t Wcap, size_t ldx, int G, int ubase, cudaStream_t st, cudaEvent_t ev_guard);
+extern "C" int haf_svm_create(haf_svm** out, const char* model_path, int device, int svm_mode, int min_dims, float guard_rel) {
+    haf_config cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.model_path = model_path;
+    cfg.device = device;
+    cfg.svm_mode = svm_mode;
+    cfg.guard_rel = guard_rel;
+    const int rc = create_impl(out, &cfg, true, min_dims);
+    if (rc == HAF_OK) (*out)->svm_only = true;
+    return rc;
+}
+extern "C" void haf_svm_destroy(haf_svm* s) { haf_destroy(s); }
+
+static int check_csr(haf_ctx* ctx, const long long* row_ptr, const int* index, const double* value, int n_rows) {
+    if (!row_ptr || n_rows < 0) return ctx->fail(HAF_ERR_ARG, "null row_ptr / negative row count");
+    for (int r = 0; r < n_rows; r++)
+        if (row_ptr[r + 1] < row_ptr[r]) return ctx->fail(HAF_ERR_ARG, "row_ptr is not non-decreasing at row %d", r);
+    if (n_rows && row_ptr[n_rows] > row_ptr[0] && (!index || !value)) return ctx->fail(HAF_ERR_ARG, "null index / value arrays");
+    return HAF_OK;
+}
+
+extern "C" int haf_svm_predict(haf_svm* ctx, const long long* row_ptr, const int* index, const double* value, int n_rows,
+                               double* labels, double* dec_values) {
+    if (!ctx) return HAF_ERR_ARG;
+    if (!ctx->svm_only) return ctx->fail(HAF_ERR_ARG, "haf_svm_predict needs a context made by haf_svm_create");
+    { int rc = check_csr(ctx, row_ptr, index, value, n_rows); if (rc) return rc; }
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const long long launches0 = ctx->launches;
+    const int W = ctx->Dsv;
+    for (int r = 0; r < n_rows; r++)   // svm-predict would index past the model's width: the caller sizes the context (min_dims)
+        for (long long e = row_ptr[r]; e < row_ptr[r + 1]; e++)
+            if (index[e] < 1 || index[e] > W) return ctx->fail(HAF_ERR_ARG, "row %d carries index %d outside 1..%d (create the context with min_dims >= the data's largest index)", r, index[e], W);
+    memset(&ctx->timing, 0, sizeof ctx->timing);
+    ctx->last_valid = false;
+    if (n_rows == 0) return HAF_OK;
+    const bool tc = ctx->cfg.svm_mode == HAF_SVM_TENSOR_GUARD;
+    const size_t chunk_rows = std::max<size_t>(256, std::min<size_t>((size_t)n_rows, ((size_t)512 << 20) / ((size_t)W * sizeof(double))));
+    ENSURE(ctx, ctx->h_stage, 64);
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[8], st));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, 16 * 4, st));
+    long long total_guard = 0;
+    for (size_t r0 = 0; r0 < (size_t)n_rows; r0 += chunk_rows) {
+        const size_t rows = std::min(chunk_rows, (size_t)n_rows - r0);
+        const size_t ldx = round_up(rows, 2 * haftc::BM);
+        const long long e0 = row_ptr[r0], e1 = row_ptr[r0 + rows];
+        ENSURE(ctx, ctx->d_csr_ptr, rows + 1); ENSURE(ctx, ctx->d_csr_idx, (size_t)std::max<long long>(e1 - e0, 1)); ENSURE(ctx, ctx->d_csr_val, (size_t)std::max<long long>(e1 - e0, 1));
+        ENSURE(ctx, ctx->d_xdense, rows * W); ENSURE(ctx, ctx->d_labels, rows);
+        ENSURE(ctx, ctx->d_xn, ldx); ENSURE(ctx, ctx->d_dec, ldx); ENSURE(ctx, ctx->d_guardflag, ldx); ENSURE(ctx, ctx->d_guardlist, ldx);
+        if (tc) { ENSURE(ctx, ctx->d_Xh, ldx * ctx->Krow); ENSURE(ctx, ctx->d_Xl, ldx * ctx->Krow); ENSURE(ctx, ctx->d_asum, ldx); }
+        else if (ctx->cfg.svm_mode == HAF_SVM_FP32_GUARD) ENSURE(ctx, ctx->d_X, (size_t)ctx->Kpad * ldx);
+        const size_t exact_cap = std::min<size_t>(ldx, std::max<size_t>(4096, ((size_t)1 << 30) / ((size_t)ctx->Spad * 8)));
+        ENSURE(ctx, ctx->d_kscratch, exact_cap * ctx->Spad);
+        unsigned* cnt = ctx->d_counters.p;
+        // the pinned word must not be rewritten while an earlier chunk's copy may still be in flight
+        CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        *reinterpret_cast<unsigned*>(ctx->h_stage.p) = (unsigned)rows;
+        if (r0 > 0) CUDA_TRY(ctx, cudaMemsetAsync(cnt, 0, 2 * 4, st));
+        CUDA_TRY(ctx, cudaMemcpyAsync(cnt, ctx->h_stage.p, 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_csr_ptr.p, row_ptr + r0, (rows + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
+        if (e1 > e0) {
+            CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_csr_idx.p, index + e0, (size_t)(e1 - e0) * sizeof(int), cudaMemcpyHostToDevice, st));
+            CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_csr_val.p, value + e0, (size_t)(e1 - e0) * sizeof(double), cudaMemcpyHostToDevice, st));
+        }
+        CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_xdense.p, 0, rows * W * sizeof(double), st));
+        csr_to_dense_kernel<<<(unsigned)rows, 128, 0, st>>>(ctx->d_csr_ptr.p, ctx->d_csr_idx.p, ctx->d_csr_val.p, (int)rows, W, ctx->d_xdense.p);
+        LAUNCHED(ctx);
+        if (ctx->cfg.svm_mode != HAF_SVM_FP64_EXACT) {
+            pack_svm_inputs_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(ctx->d_xdense.p, (int)rows, W, ctx->Krow, tc ? ctx->d_Xh.p : nullptr,
+                                                                              tc ? ctx->d_Xl.p : nullptr, tc ? nullptr : ctx->d_X.p, ldx, ctx->Kpad, ctx->d_xn.p);
+            LAUNCHED(ctx);
+        }
+        ctx->cur_xdense = ctx->d_xdense.p;
+        const int rcs = svm_stage(ctx, cnt, rows, ldx, ctx->G, 0, st, nullptr);
+        ctx->cur_xdense = nullptr;
+        if (rcs) return rcs;
+        labels_from_dec_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(ctx->d_dec.p, (int)rows, (double)ctx->label[0], (double)ctx->label[1], ctx->d_labels.p);
+        LAUNCHED(ctx);
+        accumulate_counts_kernel<<<1, 1, 0, st>>>(cnt);
+        LAUNCHED(ctx);
+        if (labels) CUDA_TRY(ctx, cudaMemcpyAsync(labels + r0, ctx->d_labels.p, rows * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (dec_values) CUDA_TRY(ctx, cudaMemcpyAsync(dec_values + r0, ctx->d_dec.p, rows * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_counters.p, ctx->d_counters.p, 16 * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[9], st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    if (ctx->h_counters.p[10]) return ctx->fail(HAF_ERR_UNSUPPORTED, "the guard band holds more rows than the exact path is provisioned for (guard_rel too wide for this model)");
+    total_guard = ctx->h_counters.p[9];
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev[8], ctx->ev[9]);
+    ctx->timing.ms_total = ms;
+    ctx->timing.n_windows = n_rows;
+    ctx->timing.n_guard = total_guard;
+    ctx->timing.n_exact = (ctx->tier2_mode == 1 && ctx->cfg.svm_mode != HAF_SVM_FP64_EXACT) ? total_guard : ctx->h_counters.p[11];
+    ctx->timing.launches = ctx->launches - launches0;
+    ctx->timing.n_chunks = (long long)((n_rows + chunk_rows - 1) / chunk_rows);
+    return HAF_OK;
+}
+
+// svm-scale on the device.  fmin / fmax: [max_index + 1] (entry 0 unused), in/out for haf_scale_minmax so that a file can
+// be walked in pieces (initialise with +DBL_MAX / -DBL_MAX like svm-scale.c:158-162).
+struct ScaleBufs {
+    long long* ptr = nullptr; int* idx = nullptr; double* val = nullptr; double* dense = nullptr;
+    ~ScaleBufs() { cudaFree(ptr); cudaFree(idx); cudaFree(val); cudaFree(dense); }
+};
+static int scale_upload(int device, const long long* row_ptr, const int* index, const double* value, int n_rows, int max_index, ScaleBufs& b) {
+    if (!row_ptr || n_rows < 0 || max_index < 1) return create_fail(HAF_ERR_ARG, "haf_scale: bad arguments");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { cudaGetLastError(); return create_fail(HAF_ERR_NO_DEVICE, "no CUDA device visible: libhafgpu has no CPU fallback"); }
+    if (device < 0 || device >= ndev) return create_fail(HAF_ERR_ARG, "haf_scale: device ordinal out of range");
+    const long long e0 = row_ptr[0], e1 = row_ptr[n_rows];
+    for (long long e = e0; e < e1; e++)
+        if (index[e - 0] < 1 || index[e] > max_index) return create_fail(HAF_ERR_ARG, "haf_scale: index outside 1..max_index");
+#define SC_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return create_fail(HAF_ERR_CUDA, std::string(#expr) + " failed: " + cudaGetErrorString(_e)); } while (0)
+    SC_TRY(cudaSetDevice(device));
+    const size_t nnz = (size_t)std::max<long long>(e1 - e0, 1);
+    SC_TRY(cudaMalloc(&b.ptr, ((size_t)n_rows + 1) * sizeof(long long)));
+    SC_TRY(cudaMalloc(&b.idx, nnz * sizeof(int)));
+    SC_TRY(cudaMalloc(&b.val, nnz * sizeof(double)));
+    SC_TRY(cudaMalloc(&b.dense, std::max<size_t>((size_t)n_rows * max_index, 1) * sizeof(double)));
+    SC_TRY(cudaMemcpy(b.ptr, row_ptr, ((size_t)n_rows + 1) * sizeof(long long), cudaMemcpyHostToDevice));
+    if (e1 > e0) {
+        SC_TRY(cudaMemcpy(b.idx, index + e0, (size_t)(e1 - e0) * sizeof(int), cudaMemcpyHostToDevice));
+        SC_TRY(cudaMemcpy(b.val, value + e0, (size_t)(e1 - e0) * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    SC_TRY(cudaMemset(b.dense, 0, std::max<size_t>((size_t)n_rows * max_index, 1) * sizeof(double)));
+    if (n_rows) csr_to_dense_kernel<<<(unsigned)n_rows, 128>>>(b.ptr, b.idx, b.val, n_rows, max_index, b.dense);
+    SC_TRY(cudaGetLastError());
+    return HAF_OK;
+}
+static unsigned long long host_dkey(double v) {
+    unsigned long long u;
+    memcpy(&u, &v, 8);
+    return (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull);
+}
+extern "C" int haf_scale_minmax(int device, const long long* row_ptr, const int* index, const double* value, int n_rows, int max_index,
+                                double* fmin, double* fmax) {
+    if (!fmin || !fmax) return create_fail(HAF_ERR_ARG, "haf_scale_minmax: null output");
+    if (n_rows == 0) return HAF_OK;
+    ScaleBufs b;
+    { int rc = scale_upload(device, row_ptr, index, value, n_rows, max_index, b); if (rc) return rc; }
+    std::vector<unsigned long long> kmin(max_index), kmax(max_index);
+    for (int d = 0; d < max_index; d++) { kmin[d] = host_dkey(fmin[d + 1]); kmax[d] = host_dkey(fmax[d + 1]); }
+    unsigned long long *dmin = nullptr, *dmax = nullptr; double* dout = nullptr; int* dflag = nullptr;
+    struct Free { unsigned long long*& a; unsigned long long*& b; double*& c; int*& d; ~Free() { cudaFree(a); cudaFree(b); cudaFree(c); cudaFree(d); } } fr{dmin, dmax, dout, dflag};
+    SC_TRY(cudaMalloc(&dmin, max_index * 8)); SC_TRY(cudaMalloc(&dmax, max_index * 8)); SC_TRY(cudaMalloc(&dout, 2 * (size_t)max_index * 8)); SC_TRY(cudaMalloc(&dflag, 4));
+    SC_TRY(cudaMemcpy(dmin, kmin.data(), max_index * 8, cudaMemcpyHostToDevice));
+    SC_TRY(cudaMemcpy(dmax, kmax.data(), max_index * 8, cudaMemcpyHostToDevice));
+    SC_TRY(cudaMemset(dflag, 0, 4));
+    const int rpb = 256;
+    scale_minmax_kernel<<<dim3((max_index + 127) / 128, (n_rows + rpb - 1) / rpb), 128>>>(b.dense, n_rows, max_index, rpb, dmin, dmax, dflag);
+    scale_minmax_decode_kernel<<<(max_index + 127) / 128, 128>>>(dmin, dmax, max_index, dout, dout + max_index);
+    SC_TRY(cudaGetLastError());
+    int flag = 0;
+    SC_TRY(cudaMemcpy(&flag, dflag, 4, cudaMemcpyDeviceToHost));
+    if (flag) return create_fail(HAF_ERR_UNSUPPORTED, "haf_scale_minmax: NaN in the data (svm-scale's max/min macros are order-dependent for NaN)");
+    SC_TRY(cudaMemcpy(fmin + 1, dout, (size_t)max_index * 8, cudaMemcpyDeviceToHost));
+    SC_TRY(cudaMemcpy(fmax + 1, dout + max_index, (size_t)max_index * 8, cudaMemcpyDeviceToHost));
+    return HAF_OK;
+}
+extern "C" int haf_scale_apply(int device, const long long* row_ptr, const int* index, const double* value, int n_rows, int max_index,
+                               const double* fmin, const double* fmax, double lower, double upper, double* dense_out) {
+    if (!fmin || !fmax || !dense_out) return create_fail(HAF_ERR_ARG, "haf_scale_apply: null argument");
+    if (n_rows == 0) return HAF_OK;
+    ScaleBufs b;
+    { int rc = scale_upload(device, row_ptr, index, value, n_rows, max_index, b); if (rc) return rc; }
+    double* dmm = nullptr;
+    struct Free { double*& a; ~Free() { cudaFree(a); } } fr{dmm};
+    SC_TRY(cudaMalloc(&dmm, 2 * (size_t)max_index * 8));
+    SC_TRY(cudaMemcpy(dmm, fmin + 1, (size_t)max_index * 8, cudaMemcpyHostToDevice));
+    SC_TRY(cudaMemcpy(dmm + max_index, fmax + 1, (size_t)max_index * 8, cudaMemcpyHostToDevice));
+    const size_t n = (size_t)n_rows * max_index;
+    scale_apply_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 32), 256>>>(b.dense, n, max_index, dmm, dmm + max_index, lower, upper);
+    SC_TRY(cudaGetLastError());
+    SC_TRY(cudaMemcpy(dense_out, b.dense, n * sizeof(double), cudaMemcpyDeviceToHost));
+    return HAF_OK;
+#undef SC_TRY
+}
+
 extern "C" void haf_destroy(haf_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
@@ -476,6 +677,7 @@ extern "C" void haf_destroy(haf_ctx* ctx) {
     ctx->d_integral.release(); ctx->d_rowscan.release(); ctx->d_mask.release(); ctx->d_labelgrid.release(); ctx->d_evals.release();
     ctx->d_unit_top.release(); ctx->d_unit_run.release(); ctx->d_unit_windows.release(); ctx->d_win.release(); ctx->d_X.release();
     ctx->d_xn.release(); ctx->d_dec.release(); ctx->d_guardflag.release(); ctx->d_guardlist.release(); ctx->d_kscratch.release();
+    ctx->d_xdense.release(); ctx->d_labels.release(); ctx->d_csr_ptr.release(); ctx->d_csr_idx.release(); ctx->d_csr_val.release();
     ctx->d_svn64.release(); ctx->d_Xg.release(); ctx->d_g2accum.release(); ctx->d_g2tickets.release(); ctx->d_guardlist2.release();
     ctx->d_SVh.release(); ctx->d_SVl.release(); ctx->d_Xh.release(); ctx->d_Xl.release(); ctx->d_svtab.release(); ctx->d_asum.release(); ctx->d_dimfeat.release();
     ctx->d_params.release(); ctx->d_counters.release(); ctx->h_stage.release(); ctx->h_results.release(); ctx->h_per_roll_top.release(); ctx->h_counters.release();
@@ -591,7 +793,61 @@ static ExactArgs make_exact_args(haf_ctx* ctx, const int* list, const unsigned* 
     a.max_entries = (int)std::min<size_t>(ctx->d_kscratch.cap / (size_t)ctx->Spad, 0x7fffffff);
     a.entry_begin = 0;
     a.overflow_flag = list ? (int*)(cnt + 10) : nullptr;   // guard mode: one launch must cover the whole list
+    a.xdense = ctx->cur_xdense;
     return a;
+}
+
+// Stage 5 of the path, also the whole of haf_svm_predict: decision values of the windows [0, *cnt[0]) whose SVM inputs
+// are in ctx->d_Xh/d_Xl (tensor mode), ctx->d_X (SIMT mode) or re-derivable by exact_scaled_input (FP64 mode / guard
+// band), then the guard band.  ev_guard (optional) is recorded between the contraction and the guard-band kernels.
+static int svm_stage(haf_ctx* ctx, unsigned* cnt, size_t Wcap, size_t ldx, int G, int ubase, cudaStream_t st, cudaEvent_t ev_guard) {
+    const bool tc = ctx->cfg.svm_mode == HAF_SVM_TENSOR_GUARD;
+    const float neg_gamma_log2e = (float)(-ctx->gamma * 1.4426950408889634);
+    if (ctx->cfg.svm_mode == HAF_SVM_FP64_EXACT) {
+        CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_guardflag.p, 0, ldx, st));
+        { int rce = launch_exact(ctx, make_exact_args(ctx, nullptr, nullptr, cnt, G, ubase), st, Wcap); if (rce) return rce; }
+        if (ev_guard) CUDA_TRY(ctx, cudaEventRecord(ev_guard, st));
+    } else if (tc) {
+        CUtensorMap tmXh, tmXl;
+        if (!make_tensor_map(&tmXh, ctx->d_Xh.p, ctx->Krow, ldx, haftc::BM) || !make_tensor_map(&tmXl, ctx->d_Xl.p, ctx->Krow, ldx, haftc::BM))
+            return ctx->fail(HAF_ERR_CUDA, "cuTensorMapEncodeTiled failed for the window operands");
+        CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_dec.p, 0, ldx * sizeof(double), st));
+        CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_asum.p, 0, ldx * sizeof(float), st));
+        const int n_ntiles = ctx->SpadT / haftc::BN;
+        const int mt_cap = (int)(ldx / haftc::BM);
+        int nsplit = 1;
+        if (mt_cap < ctx->sm_count) nsplit = std::min(n_ntiles, (2 * ctx->sm_count + mt_cap - 1) / mt_cap);
+        const int kblocks = (ctx->Krow + haftc::BK - 1) / haftc::BK;
+        const int last_slices = (ctx->Krow - haftc::BK * (kblocks - 1)) / 16;
+        if (ctx->tc_variant == 0) {
+            const int pairs_cap = (mt_cap + 1) / 2;
+            int nsplit2 = 1;
+            if (pairs_cap < ctx->sm_count / 2) nsplit2 = std::min(n_ntiles, (ctx->sm_count + pairs_cap - 1) / pairs_cap);
+            int grid2 = (int)std::min<long long>((long long)pairs_cap * nsplit2 * 2, ctx->sm_count);
+            grid2 &= ~1;  // whole clusters
+            haftc::svm_rbf_tc2_kernel<<<grid2, haftc::THREADS, haftc::SMEM2_BYTES, st>>>(tmXh, tmXl, ctx->tmSh2, ctx->tmSl2, ctx->d_xn.p, ctx->d_svtab.p,
+                                                                                         ctx->c_log2, cnt + 0, n_ntiles, nsplit2, kblocks, last_slices,
+                                                                                         ctx->d_dec.p, ctx->d_asum.p);
+        } else {
+            const int grid = (int)std::min<long long>((long long)mt_cap * nsplit, ctx->sm_count);
+            haftc::svm_rbf_tc_kernel<<<grid, haftc::THREADS, haftc::SMEM_BYTES, st>>>(tmXh, tmXl, ctx->tmSh, ctx->tmSl, ctx->d_xn.p, ctx->d_svtab.p, ctx->c_log2,
+                                                                                      cnt + 0, n_ntiles, nsplit, kblocks, last_slices, ctx->d_dec.p, ctx->d_asum.p);
+        }
+        LAUNCHED(ctx);
+        haftc::svm_finalize_kernel<<<(unsigned)((Wcap + 255) / 256), 256, 0, st>>>(ctx->d_dec.p, ctx->d_asum.p, ctx->d_xn.p, cnt + 0, ctx->rho, ctx->guard_rel,
+                                                                                   ctx->d_guardflag.p, ctx->d_guardlist.p, cnt + 1);
+        LAUNCHED(ctx);
+        if (ev_guard) CUDA_TRY(ctx, cudaEventRecord(ev_guard, st));
+        { int rce = launch_guard(ctx, cnt, G, ubase, st, Wcap, ldx); if (rce) return rce; }
+    } else {
+        svm_rbf_simt_kernel<<<(unsigned)(ldx / SVM_BM), 256, SVM_STAGES * SVM_BK * (SVM_BM + SVM_BN) * 4, st>>>(
+            ctx->d_X.p, ldx, ctx->d_svT.p, ctx->Spad, ctx->Kpad, ctx->d_xn.p, ctx->d_svn.p, ctx->d_coef.p, neg_gamma_log2e, ctx->rho,
+            ctx->guard_rel, cnt + 0, ctx->d_dec.p, ctx->d_guardflag.p, ctx->d_guardlist.p, cnt + 1);
+        LAUNCHED(ctx);
+        if (ev_guard) CUDA_TRY(ctx, cudaEventRecord(ev_guard, st));
+        { int rce = launch_guard(ctx, cnt, G, ubase, st, Wcap, ldx); if (rce) return rce; }
+    }
+    return HAF_OK;
 }
 
 // Runs the whole path for `jobs` (sorted by cloud).  Outputs land in ctx->h_results / h_per_roll_top (pinned) and,
@@ -803,52 +1059,9 @@ static int run_jobs(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& jobs, fl
             xnorm_kernel<<<(unsigned)((Wcap + 255) / 256), 256, 0, st>>>(ctx->d_X.p, ldx, ctx->Kpad, cnt + 0, ctx->d_xn.p);
             LAUNCHED(ctx);
         }
-        // 5. SVM decision values
+        // 5. SVM decision values (+ guard band)
         if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[ci * 8 + 4], st));
-        if (ctx->cfg.svm_mode == HAF_SVM_FP64_EXACT) {
-            CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_guardflag.p, 0, ldx, st));
-            { int rce = launch_exact(ctx, make_exact_args(ctx, nullptr, nullptr, cnt, G, ubase), st, Wcap); if (rce) return rce; }
-            if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[ci * 8 + 5], st));
-        } else if (tc) {
-            CUtensorMap tmXh, tmXl;
-            if (!make_tensor_map(&tmXh, ctx->d_Xh.p, ctx->Krow, ldx, haftc::BM) || !make_tensor_map(&tmXl, ctx->d_Xl.p, ctx->Krow, ldx, haftc::BM))
-                return ctx->fail(HAF_ERR_CUDA, "cuTensorMapEncodeTiled failed for the window operands");
-            CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_dec.p, 0, ldx * sizeof(double), st));
-            CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_asum.p, 0, ldx * sizeof(float), st));
-            const int n_ntiles = ctx->SpadT / haftc::BN;
-            const int mt_cap = (int)(ldx / haftc::BM);
-            int nsplit = 1;
-            if (mt_cap < ctx->sm_count) nsplit = std::min(n_ntiles, (2 * ctx->sm_count + mt_cap - 1) / mt_cap);
-            const int kblocks = (ctx->Krow + haftc::BK - 1) / haftc::BK;
-            const int last_slices = (ctx->Krow - haftc::BK * (kblocks - 1)) / 16;
-            if (ctx->tc_variant == 0) {
-                const int pairs_cap = (mt_cap + 1) / 2;
-                int nsplit2 = 1;
-                if (pairs_cap < ctx->sm_count / 2) nsplit2 = std::min(n_ntiles, (ctx->sm_count + pairs_cap - 1) / pairs_cap);
-                int grid2 = (int)std::min<long long>((long long)pairs_cap * nsplit2 * 2, ctx->sm_count);
-                grid2 &= ~1;  // whole clusters
-                haftc::svm_rbf_tc2_kernel<<<grid2, haftc::THREADS, haftc::SMEM2_BYTES, st>>>(tmXh, tmXl, ctx->tmSh2, ctx->tmSl2, ctx->d_xn.p, ctx->d_svtab.p,
-                                                                                             ctx->c_log2, cnt + 0, n_ntiles, nsplit2, kblocks, last_slices,
-                                                                                             ctx->d_dec.p, ctx->d_asum.p);
-            } else {
-                const int grid = (int)std::min<long long>((long long)mt_cap * nsplit, ctx->sm_count);
-                haftc::svm_rbf_tc_kernel<<<grid, haftc::THREADS, haftc::SMEM_BYTES, st>>>(tmXh, tmXl, ctx->tmSh, ctx->tmSl, ctx->d_xn.p, ctx->d_svtab.p, ctx->c_log2,
-                                                                                          cnt + 0, n_ntiles, nsplit, kblocks, last_slices, ctx->d_dec.p, ctx->d_asum.p);
-            }
-            LAUNCHED(ctx);
-            haftc::svm_finalize_kernel<<<(unsigned)((Wcap + 255) / 256), 256, 0, st>>>(ctx->d_dec.p, ctx->d_asum.p, ctx->d_xn.p, cnt + 0, ctx->rho, ctx->guard_rel,
-                                                                                       ctx->d_guardflag.p, ctx->d_guardlist.p, cnt + 1);
-            LAUNCHED(ctx);
-            if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[ci * 8 + 5], st));
-            { int rce = launch_guard(ctx, cnt, G, ubase, st, Wcap, ldx); if (rce) return rce; }
-        } else {
-            svm_rbf_simt_kernel<<<(unsigned)(ldx / SVM_BM), 256, SVM_STAGES * SVM_BK * (SVM_BM + SVM_BN) * 4, st>>>(
-                ctx->d_X.p, ldx, ctx->d_svT.p, ctx->Spad, ctx->Kpad, ctx->d_xn.p, ctx->d_svn.p, ctx->d_coef.p, neg_gamma_log2e, ctx->rho,
-                ctx->guard_rel, cnt + 0, ctx->d_dec.p, ctx->d_guardflag.p, ctx->d_guardlist.p, cnt + 1);
-            LAUNCHED(ctx);
-            if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[ci * 8 + 5], st));
-            { int rce = launch_guard(ctx, cnt, G, ubase, st, Wcap, ldx); if (rce) return rce; }
-        }
+        { int rcs = svm_stage(ctx, cnt, Wcap, ldx, G, ubase, st, prof ? ctx->ev_pool[ci * 8 + 5] : nullptr); if (rcs) return rcs; }
         // 6. labels -> grids, score stencil, argmax, tie rule
         if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[ci * 8 + 6], st));
         label_scatter_kernel<<<(unsigned)((Wcap + 255) / 256), 256, 0, st>>>(ctx->d_dec.p, ctx->d_win.p, cnt + 0, G, ubase, ctx->gv[0], ctx->gv[1],

@@ -874,10 +874,12 @@ struct ExactArgs {
     int* overflow_flag;   // set when the list holds more entries than this launch covers (guard mode: one launch only)
     int entry_begin;      // this launch covers list entries [entry_begin, entry_begin + max_entries)
     int max_entries;      // capacity of `terms` in windows
+    const double* xdense; // haf_svm_predict: the SVM inputs are GIVEN ([window][Dsv] doubles) instead of derived from a cloud
 };
 // SVM input d of window w, re-derived in double from the integral image with the bit-exact emulation of both text round
 // trips (a7-a9: calc_featurevalue, "%.4g", svm-scale.c:339-352 with "%g"): exactly what svm-predict parses.
 __device__ __forceinline__ double exact_scaled_input(const ExactArgs& A, int w, int d) {
+    if (A.xdense) return A.xdense[(size_t)w * A.Dsv + d];
     const int ld = A.G + 1;
     const int2 uc = A.win[w];
     const int row = uc.y / A.G, col = uc.y - row * A.G;
@@ -1274,6 +1276,105 @@ __global__ void accumulate_counts_kernel(unsigned* cnt) {
     cnt[9] += cnt[1];
     cnt[11] += cnt[6];   // windows that went on to the exact-order kernels (tier 3)
     cnt[6] = 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// libsvm front ends: svm-predict / svm-scale on rows given in libsvm's sparse text layout (CSR here).
+// ---------------------------------------------------------------------------------------------------
+// dense[r][index-1] = value for the entries of rows [0, n_rows); dense must be zeroed (absent = 0, svm.cpp:328-364).
+__global__ void csr_to_dense_kernel(const long long* __restrict__ row_ptr, const int* __restrict__ index, const double* __restrict__ value,
+                                    int n_rows, int width, double* __restrict__ dense) {
+    const int r = blockIdx.x;
+    if (r >= n_rows) return;
+    const long long base = row_ptr[0];
+    for (long long e = row_ptr[r] - base + threadIdx.x; e < row_ptr[r + 1] - base; e += blockDim.x) {
+        const int i = index[e];
+        if (i >= 1 && i <= width) dense[(size_t)r * width + (i - 1)] = value[e];
+    }
+}
+// SVM operands of given inputs: tensor mode (Xh != NULL): fp16 hi/lo rows [row][Krow] + ||x||^2 of the float values;
+// SIMT mode (Xf != NULL): feature-major floats [Kpad][ldx] + ||x||^2.  One warp per row.
+__global__ void __launch_bounds__(256) pack_svm_inputs_kernel(const double* __restrict__ dense, int n_rows, int width, int Krow,
+                                                              __half* __restrict__ Xh, __half* __restrict__ Xl, float* __restrict__ Xf,
+                                                              size_t ldx, int Kpad, float* __restrict__ xn) {
+    const int lane = threadIdx.x & 31;
+    const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= n_rows) return;
+    float sq = 0.0f;
+    const int K = Xh ? Krow : Kpad;
+    for (int d = lane; d < K; d += 32) {
+        const float xf = d < width ? (float)dense[(size_t)r * width + d] : 0.0f;
+        if (Xh) {
+            const float xc = fminf(fmaxf(xf, -65504.0f), 65504.0f);
+            const __half hi = __float2half_rn(xc);
+            const __half lo = __float2half_rn(xc - __half2float(hi));
+            Xh[(size_t)r * Krow + d] = hi;
+            Xl[(size_t)r * Krow + d] = lo;
+            const float v = __half2float(hi) + __half2float(lo);
+            sq = fmaf(v, v, sq);
+            if (!(fabsf(xf) < 65504.0f)) sq = __int_as_float(0x7f800000);   // clamped or NaN: force the exact path
+        } else {
+            Xf[(size_t)d * ldx + r] = xf;
+            sq = fmaf(xf, xf, sq);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    if (lane == 0) xn[r] = sq;
+}
+// predicted label per row: dec > 0 ? label[0] : label[1]   (svm.cpp:2516-2531)
+__global__ void labels_from_dec_kernel(const double* __restrict__ dec, int n, double l0, double l1, double* __restrict__ labels) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) labels[i] = dec[i] > 0.0 ? l0 : l1;
+}
+// svm-scale pass 2 (svm-scale.c:165-198): per-feature min / max over all rows, absent entries counting as 0.
+// dense [n_rows][width]; ordered 64-bit keys so that atomicMax / atomicMin on integers order doubles.
+__device__ __forceinline__ unsigned long long dkey(double v) {
+    const unsigned long long u = (unsigned long long)__double_as_longlong(v);
+    return (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double dkey_inv(unsigned long long k) {
+    const unsigned long long u = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)u);
+}
+__global__ void scale_minmax_kernel(const double* __restrict__ dense, int n_rows, int width, int rows_per_block,
+                                    unsigned long long* __restrict__ kmin, unsigned long long* __restrict__ kmax, int* __restrict__ nan_flag) {
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= width) return;
+    const int r0 = blockIdx.y * rows_per_block, r1 = min(n_rows, r0 + rows_per_block);
+    if (r0 >= r1) return;
+    double mn = dense[(size_t)r0 * width + d], mx = mn;
+    bool bad = mn != mn;
+    for (int r = r0 + 1; r < r1; r++) {
+        const double v = dense[(size_t)r * width + d];
+        bad = bad || (v != v);
+        mn = v < mn ? v : mn;
+        mx = v > mx ? v : mx;
+    }
+    if (bad) *nan_flag = 1;
+    atomicMin(kmin + d, dkey(mn));
+    atomicMax(kmax + d, dkey(mx));
+}
+__global__ void scale_minmax_decode_kernel(const unsigned long long* __restrict__ kmin, const unsigned long long* __restrict__ kmax, int width,
+                                           double* __restrict__ fmin, double* __restrict__ fmax) {
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d < width) { fmin[d] = dkey_inv(kmin[d]); fmax[d] = dkey_inv(kmax[d]); }
+}
+// svm-scale pass 3, output() (svm-scale.c:333-353), in place on the dense matrix: single-valued features become 0
+// (they are skipped, i.e. absent, in the output), the rest  v == min -> lower, v == max -> upper, else
+// lower + (upper - lower) * (v - min) / (max - min)  evaluated left to right in double.
+__global__ void scale_apply_kernel(double* __restrict__ dense, size_t n_elems, int width, const double* __restrict__ fmin,
+                                   const double* __restrict__ fmax, double lower, double upper) {
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_elems; t += (size_t)gridDim.x * blockDim.x) {
+        const int d = (int)(t % (size_t)width);
+        const double mn = fmin[d], mx = fmax[d];
+        double v = dense[t];
+        if (mx == mn) v = 0.0;
+        else if (v == mn) v = lower;
+        else if (v == mx) v = upper;
+        else v = __dadd_rn(lower, __ddiv_rn(__dmul_rn(__dsub_rn(upper, lower), __dsub_rn(v, mn)), __dsub_rn(mx, mn)));
+        dense[t] = v;
+    }
 }
 
 // debug: device text round trips

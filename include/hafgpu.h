@@ -145,6 +145,33 @@ int haf_search_batch(haf_ctx* ctx, const float* const* clouds, const size_t* n_p
 int haf_search_batch_packed(haf_ctx* ctx, const float* xyz_all_hostdev, const size_t* point_offsets, int n_clouds,
                             const haf_request* req, haf_best* best_per_cloud);
 
+/* ---- libsvm-compatible front ends ----------------------------------------------------------------
+ * The reference classifies by running two child processes per roll on text files (server.cpp:775-776, :786-792):
+ *     svm-scale -r <range> /tmp/features.txt > /tmp/features.txt.scale      (libsvm-3.12/svm-scale.c)
+ *     svm-predict /tmp/features.txt.scale <model> /tmp/output_calc_gp.txt   (libsvm-3.12/svm-predict.c)
+ * These entry points are what CLI-compatible replacements of the two programs bind (csrc/host/svm_predict_b200.cpp,
+ * svm_scale_b200.cpp): a second drop-in seam that needs no server patch.  Rows are given in CSR form with libsvm's
+ * 1-based, ascending feature indices; row_ptr has n_rows + 1 entries indexing `index` / `value` (host memory).
+ * No CPU fallback: all arithmetic runs on the device; text parsing / printing stays with the caller. */
+typedef struct haf_ctx haf_svm;
+/* model only (C-SVC, RBF, 2 classes: what svm_load_model reads for this path, svm.cpp:2714-2927).  min_dims: largest
+ * feature index the data will carry (the distance loop covers max(model, data) dimensions, svm.cpp:328-364). */
+int haf_svm_create(haf_svm** out, const char* model_path, int device, int svm_mode, int min_dims, float guard_rel);
+void haf_svm_destroy(haf_svm* s);
+/* svm_predict for every row (svm.cpp:2535-2548): labels [n_rows] (as doubles, what svm-predict prints with %g) and,
+ * optionally, the decision values [n_rows] (svm_predict_values, svm.cpp:2459-2533).  Labels equal libsvm's; decision
+ * values carry the tolerance of the chosen svm_mode.  haf_last_error / haf_get_timing / haf_get_info take the handle. */
+int haf_svm_predict(haf_svm* s, const long long* row_ptr, const int* index, const double* value, int n_rows,
+                    double* labels, double* dec_values);
+/* svm-scale pass 2 (svm-scale.c:165-198): per-feature min / max over the rows, absent entries counting as 0.
+ * fmin / fmax: [max_index + 1], entry 0 unused, IN/OUT (start from +DBL_MAX / -DBL_MAX; call per piece of a file). */
+int haf_scale_minmax(int device, const long long* row_ptr, const int* index, const double* value, int n_rows, int max_index,
+                     double* fmin, double* fmax);
+/* svm-scale pass 3 (output(), svm-scale.c:333-353) for every feature 1..max_index of every row (absent = 0):
+ * dense_out [n_rows][max_index]; single-valued features (max == min) give 0 = "not printed". */
+int haf_scale_apply(int device, const long long* row_ptr, const int* index, const double* value, int n_rows, int max_index,
+                    const double* fmin, const double* fmax, double lower, double upper, double* dense_out);
+
 /* Host-only helpers (no GPU work): the transform of one roll exactly as generate_grid builds it (:406-484),
  * and the ordered key that turns "strictly greater wins, earliest unit wins ties" into a max-reduction, for the
  * cross-GPU best-grasp exchange. */
