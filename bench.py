@@ -483,6 +483,7 @@ def run_ours(args):
                                   1: "FP64 exact-order path", 0: "algorithmic flops; the split-fp16 scheme issues 3 tensor-core MMAs per algorithmic MMA, "
                                   "executed tensor flops = 3 x (Krow/D) x algorithmic (ncu: tensor pipe 98.5 % active, profiles/r1_final_full.md)"}[args.svm_mode]},
             "stage_ms_per_step": {k: acc[k] / args.steps for k in ("bin", "integral", "mask", "features", "svm", "guard", "score")},
+            "stage_roofline": stage_roofline(acc, args.steps, total_pts, n_clouds * info.n_rolls, info.grid, info.n_dims, W_step, hbm),
             "guard_windows_per_step": acc["guardw"] / args.steps,
             "wall_ms_per_step": 1e3 * wall_dev / args.steps,
         }
@@ -498,6 +499,23 @@ def run_ours(args):
     gs.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def stage_roofline(acc, steps, n_points, n_units, G, D, W, hbm_gbs):
+    """HBM-bound stages against the measured copy bandwidth: ALGORITHMIC bytes per step / stage time.
+    bin: 12 N + 4 U G^2; integral: 4 U G^2 + 4 U (G+1)^2; mask + Haar + scale: 4 U (G+1)^2 + U G^2 + 4 D W (the operand
+    matrix counted once, FP32, as 8d defines it); stencil + argmax: U G^2 + 4 U G^2 + 32 U."""
+    GG, LL = G * G, (G + 1) * (G + 1)
+    rows = {"bin": (12.0 * n_points + 4.0 * n_units * GG, acc["bin"]),
+            "integral": (4.0 * n_units * GG + 4.0 * n_units * LL, acc["integral"]),
+            "mask+features": (4.0 * n_units * LL + n_units * GG + 4.0 * D * W, acc["mask"] + acc["features"]),
+            "score": (5.0 * n_units * GG + 32.0 * n_units, acc["score"])}
+    out = {}
+    for k, (b, ms_total) in rows.items():
+        ms = ms_total / steps
+        gbs = b / (ms * 1e-3) / 1e9 if ms > 0 else None
+        out[k] = {"algorithmic_bytes": b, "ms": ms, "GBps": gbs, "frac_of_hbm_peak": (gbs / hbm_gbs) if gbs and hbm_gbs else None}
+    return out
 
 
 _JSON_OUT = None

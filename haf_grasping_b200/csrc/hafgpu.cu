@@ -97,6 +97,7 @@ struct haf_ctx {
     DevBuf<__half> d_SVh, d_SVl, d_Xh, d_Xl;
     DevBuf<float4> d_svtab;
     DevBuf<DimFeat> d_dimfeat;
+    DevBuf<Round4Tab> d_round4;   // "%.4g" tables of the fast tier
     DevBuf<float> d_asum;
     CUtensorMap tmSh, tmSl;     // 256-row boxes (single-CTA kernel)
     CUtensorMap tmSh2, tmSl2;   // 128-row boxes (CTA-pair kernel)
@@ -209,6 +210,10 @@ static haf_encode_tiled_fn get_encode_tiled() {
             cudaGetLastError();
     }
     return fn;
+}
+// "%.4g" tables of the fast feature tier (kernels.cuh, Round4Tab): powers of ten 10^(i-48)
+static void make_round4_table(Round4Tab& tab) {
+    for (int i = 0; i < 96; i++) { tab.pwd[i] = pow(10.0, i - 48); tab.pwf[i] = (float)tab.pwd[i]; }
 }
 // 2D fp16 tensor [rows][krow] (K contiguous), box = 64 elements (128 B, one swizzle row) x box_rows, 128B swizzle
 static bool make_tensor_map(CUtensorMap* m, void* base, uint64_t krow, uint64_t rows, uint32_t box_rows) {
@@ -447,7 +452,9 @@ static int create_impl(haf_ctx** out, const haf_config* cfg, bool svm_only, int 
             haf_destroy(ctx);
             return create_fail(HAF_ERR_CUDA, "cuTensorMapEncodeTiled failed for the support-vector operands");
         }
-        std::vector<DimFeat> joined(D);
+        // one table per row-stride class of the staged integral rows (features_tc_kernel: bank-conflict-free staging)
+        std::vector<DimFeat> joined((size_t)32 * D);
+        for (int cls = 0; cls < 32; cls++)
         for (int d = 0; d < D; d++) {
             DimFeat j;
             memset(&j, 0, sizeof j);
@@ -456,7 +463,10 @@ static int create_impl(haf_ctx** out, const haf_config* cfg, bool svm_only, int 
                 const FeatDev& ff = fd[dd.feat];
                 for (int r = 0; r < 3; r++) {
                     if (ff.flags & (1 << r)) {
-                        for (int q = 0; q < 4; q++) j.off[4 * r + q] = ff.off[4 * r + q] * 4;  // bytes
+                        for (int q = 0; q < 4; q++) {   // ff.off = x * ld + y  ->  (x * (ld + cls) + y) bytes
+                            const int x = ff.off[4 * r + q] / ld, y = ff.off[4 * r + q] % ld;
+                            j.off[4 * r + q] = (x * (ld + cls) + y) * 4;
+                        }
                         j.w[r] = ff.w[r];
                     } else {  // skipped region: identical corners, weight +0.0 -> contributes exactly +0.0
                         for (int q = 0; q < 4; q++) j.off[4 * r + q] = 0;
@@ -469,13 +479,19 @@ static int create_impl(haf_ctx** out, const haf_config* cfg, bool svm_only, int 
             }
             if (dd.drop) j.flags |= 0x400;
             j.fmin = (float)dd.fmin; j.slope = (float)dd.slope; j.cval = (float)dd.cval;
-            joined[d] = j;
+            joined[(size_t)cls * D + d] = j;
         }
-        if (ctx->d_dimfeat.ensure(D) != 0) { haf_destroy(ctx); return create_fail(HAF_ERR_NOMEM, "out of device memory uploading the joined feature table"); }
-        CREATE_TRY(cudaMemcpy(ctx->d_dimfeat.p, joined.data(), D * sizeof(DimFeat), cudaMemcpyHostToDevice));
+        Round4Tab r4;
+        make_round4_table(r4);
+        if (ctx->d_round4.ensure(1) != 0) { haf_destroy(ctx); return create_fail(HAF_ERR_NOMEM, "out of device memory uploading the rounding table"); }
+        CREATE_TRY(cudaMemcpy(ctx->d_round4.p, &r4, sizeof(Round4Tab), cudaMemcpyHostToDevice));
+        if (ctx->d_dimfeat.ensure(joined.size()) != 0) { haf_destroy(ctx); return create_fail(HAF_ERR_NOMEM, "out of device memory uploading the joined feature table"); }
+        CREATE_TRY(cudaMemcpy(ctx->d_dimfeat.p, joined.data(), joined.size() * sizeof(DimFeat), cudaMemcpyHostToDevice));
         CREATE_TRY(cudaFuncSetAttribute(haftc::svm_rbf_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, haftc::SMEM_BYTES));
         CREATE_TRY(cudaFuncSetAttribute(haftc::svm_rbf_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, haftc::SMEM2_BYTES));
-        CREATE_TRY(cudaFuncSetAttribute(features_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * HAF_FT_WT * (Krow / 2 + 1) * 4 + HAF_FT_ROWS * (G + 1) * 4));
+        CREATE_TRY(cudaFuncSetAttribute(features_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * HAF_FT_WT * (HAF_FT_KPASS + 1) * 4 + HAF_FT_ROWS * (G + 1 + 31) * 4 + 16 + HAF_FT_KPASS * 96));
+        // 4 CTAs x ~47 KB: ask for just that much shared memory so that the rest of the SM's 256 KB stays L1 (the corner-offset table)
+        CREATE_TRY(cudaFuncSetAttribute(features_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 85));
     }
     for (int i = 0; i < 10; i++) CREATE_TRY(cudaEventCreate(&ctx->ev[i]));
     ctx->ev_ok = true;
@@ -679,7 +695,7 @@ extern "C" void haf_destroy(haf_ctx* ctx) {
     ctx->d_xn.release(); ctx->d_dec.release(); ctx->d_guardflag.release(); ctx->d_guardlist.release(); ctx->d_kscratch.release();
     ctx->d_xdense.release(); ctx->d_labels.release(); ctx->d_csr_ptr.release(); ctx->d_csr_idx.release(); ctx->d_csr_val.release();
     ctx->d_svn64.release(); ctx->d_Xg.release(); ctx->d_g2accum.release(); ctx->d_g2tickets.release(); ctx->d_guardlist2.release();
-    ctx->d_SVh.release(); ctx->d_SVl.release(); ctx->d_Xh.release(); ctx->d_Xl.release(); ctx->d_svtab.release(); ctx->d_asum.release(); ctx->d_dimfeat.release();
+    ctx->d_SVh.release(); ctx->d_SVl.release(); ctx->d_Xh.release(); ctx->d_Xl.release(); ctx->d_svtab.release(); ctx->d_asum.release(); ctx->d_dimfeat.release(); ctx->d_round4.release();
     ctx->d_params.release(); ctx->d_counters.release(); ctx->h_stage.release(); ctx->h_results.release(); ctx->h_per_roll_top.release(); ctx->h_counters.release();
     if (ctx->ev_ok) for (int i = 0; i < 10; i++) cudaEventDestroy(ctx->ev[i]);
     for (size_t i = 0; i < ctx->ev_pool.size(); i++) cudaEventDestroy(ctx->ev_pool[i]);
@@ -739,7 +755,7 @@ bool is_device_ptr(const void* p) {
 }  // namespace
 
 static size_t ft_smem_bytes(const haf_ctx* ctx) {
-    return (size_t)32 * HAF_FT_WT * (ctx->Krow / 2 + 1) * 4 + (size_t)HAF_FT_ROWS * (ctx->G + 1) * 4;
+    return (size_t)32 * HAF_FT_WT * (HAF_FT_KPASS + 1) * 4 + (size_t)HAF_FT_ROWS * (ctx->G + 1 + 31) * 4 + 16 + (size_t)HAF_FT_KPASS * 96;
 }
 static size_t exact_smem_bytes(const haf_ctx* ctx) { return (size_t)HAF_EXACT_WB * ctx->Dsv * sizeof(double); }
 // launches the two phases of the FP64 exact-order path on stream st
@@ -1048,7 +1064,7 @@ static int run_jobs(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& jobs, fl
         if (tc) {
             const unsigned fblocks = (unsigned)((Wcap + 32 * HAF_FT_WT - 1) / (32 * HAF_FT_WT));
             features_tc_kernel<<<fblocks, 256, ft_smem_bytes(ctx), st>>>(ctx->d_integral.p, ctx->d_win.p, cnt + 0, G, ubase, ctx->d_dimfeat.p, ctx->D,
-                                                                      ctx->Krow, (float)ctx->lower, ctx->cfg.emulate_text_roundtrip, ctx->d_Xh.p,
+                                                                      ctx->Krow, (float)ctx->lower, ctx->cfg.emulate_text_roundtrip, ctx->d_round4.p, ctx->d_Xh.p,
                                                                       ctx->d_Xl.p, ctx->d_xn.p);
             LAUNCHED(ctx);
         } else if (ctx->cfg.svm_mode != HAF_SVM_FP64_EXACT) {

@@ -499,6 +499,22 @@ __device__ __forceinline__ FastTab load_fast_tab(const DimFeat* __restrict__ tab
     f.fmin = __uint_as_float(t4.x); f.slope = __uint_as_float(t4.y); f.cval = __uint_as_float(t4.z);
     return f;
 }
+// same record from the copy the CTA staged in shared memory: five broadcast LDS.128 = five wavefronts, where the same
+// loads from global memory returned 16 B to each of 32 lanes = twenty (the kernel is bound by the LSU data pipe)
+__device__ __forceinline__ FastTab load_fast_tab_smem(uint32_t rec_addr) {
+    uint4 t[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++)
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(t[k].x), "=r"(t[k].y), "=r"(t[k].z), "=r"(t[k].w) : "r"(rec_addr + 16u * k));
+    FastTab f;
+    f.off[0] = (int)t[0].x; f.off[1] = (int)t[0].y; f.off[2] = (int)t[0].z; f.off[3] = (int)t[0].w;
+    f.off[4] = (int)t[1].x; f.off[5] = (int)t[1].y; f.off[6] = (int)t[1].z; f.off[7] = (int)t[1].w;
+    f.off[8] = (int)t[2].x; f.off[9] = (int)t[2].y; f.off[10] = (int)t[2].z; f.off[11] = (int)t[2].w;
+    f.w[0] = __uint_as_float(t[3].x); f.w[1] = __uint_as_float(t[3].y); f.w[2] = __uint_as_float(t[3].z);
+    f.flags = (int)t[3].w;
+    f.fmin = __uint_as_float(t[4].x); f.slope = __uint_as_float(t[4].y); f.cval = __uint_as_float(t[4].z);
+    return f;
+}
 struct SmemRows { uint32_t base; };  // 32-bit shared-window byte address of the staged integral rows
 __device__ __forceinline__ float load_corner(const float* I, int idx0, int off_bytes) {
     return *reinterpret_cast<const float*>(reinterpret_cast<const char*>(I + idx0) + off_bytes);
@@ -508,10 +524,18 @@ __device__ __forceinline__ float load_corner(SmemRows I, int idx0_bytes, int off
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(I.base + (uint32_t)(idx0_bytes + off_bytes)));
     return v;
 }
+// "%.4g" of the fast tier: powers of ten 10^(i-48) as double and float (built on the host, staged in shared memory by the
+// kernel -- as global loads they cost more LSU wavefronts than the instructions they saved).
+struct Round4Tab {
+    double pwd[96];
+    float pwf[96];
+};
+static_assert(sizeof(Round4Tab) == 96 * 8 + 96 * 4, "Round4Tab layout");
+struct Round4Smem { uint32_t pwd, pwf; };   // 32-bit shared-window addresses of the staged tables
 // idx0: element index of the window's patch origin for global rows, BYTE offset for staged rows; f.off[] are byte offsets
 template <typename PtrT>
 __device__ __forceinline__ float fast_tier_value(PtrT I, int idx0, const FastTab& f, float lower, int emulate_text,
-                                                 const double* s_pwd, const float* s_pwf) {
+                                                 const Round4Smem rt) {
     float c[12];
 #pragma unroll
     for (int k = 0; k < 12; k++) c[k] = load_corner(I, idx0, f.off[k]);
@@ -526,16 +550,21 @@ __device__ __forceinline__ float fast_tier_value(PtrT I, int idx0, const FastTab
     float v = raw;
     if (emulate_text) {
         // "%.4g": a * 10^(3-E) is formed and rounded in DOUBLE (exact ties stay exact; a mis-decided near-tie needs
-        // |frac - 0.5| < 1e-12); everything after the rounding decision only needs float accuracy here
+        // |frac - 0.5| < 1e-12); everything after the rounding decision only needs float accuracy here.  Branch-free:
+        // raw = +-0 runs through the subnormal record and comes out as +-0.
+        // E0 = floor(log10 2^k) = (k * 1233) >> 12 exactly for every float binade k in [-126, 127]; subnormals count as
+        // binade -126.  (a >= 10^(E0+1) as a float rounded to nearest: a value sitting exactly on a rounded-down power of
+        // ten is then scaled by one decade more and still rounds to the same four digits.)
         const float a = fabsf(raw);
-        const int e2 = (int)((__float_as_uint(raw) >> 23) & 0xFFu) - 127;
-        int E = (e2 * 1233 - 3) >> 12;          // <= floor(log10 a), at most 2 too low
-        E = max(-37, min(36, E));
-        E += (a >= s_pwf[40 + E + 1]) ? 1 : 0;
-        E += (a >= s_pwf[40 + E + 1]) ? 1 : 0;
-        const float r = (float)rint((double)a * s_pwd[40 + 3 - E]);
-        const float vv = r * s_pwf[40 + E - 3];
-        v = (raw == 0.0f) ? 0.0f : copysignf(vv, raw);
+        int E = ((max((int)(__float_as_uint(a) >> 23), 1) - 127) * 1233) >> 12;
+        float thr;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(thr) : "r"(rt.pwf + (uint32_t)((48 + E + 1) << 2)));
+        E += (a >= thr) ? 1 : 0;
+        double mul; float inv;
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(mul) : "r"(rt.pwd + (uint32_t)((48 + 3 - E) << 3)));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(inv) : "r"(rt.pwf + (uint32_t)((48 + E - 3) << 2)));
+        const float r = (float)rint((double)a * mul);
+        v = copysignf(r * inv, raw);
     }
     const float x = fmaf(v - f.fmin, f.slope, lower);  // svm-scale.c:344-346
     return (f.flags & 0x400) ? 0.0f : ((f.flags & 0x200) ? f.cval : x);
@@ -552,23 +581,25 @@ __device__ __forceinline__ float fast_tier_value(PtrT I, int idx0, const FastTab
 // everywhere else.  Each lane handles WT windows per table record, so the six 128-bit table loads are amortised.
 // (Tables in __constant__ memory were tried and were 1.8x SLOWER: 36 KB of tables thrash the constant cache.)
 #define HAF_FT_WT 2
+#define HAF_FT_KPASS 96   // dimensions per pass of the shared-memory tile: 192 B = 6 whole sectors of a row of Xh / Xl
 __global__ void __launch_bounds__(256, 4) features_tc_kernel(const float* __restrict__ integral, const int2* __restrict__ win,
                                                              const unsigned* __restrict__ win_count, int G, int unit_base,
                                                              const DimFeat* __restrict__ table, int D, int Krow, float lower,
-                                                             int emulate_text, __half* __restrict__ Xh,
-                                                             __half* __restrict__ Xl, float* __restrict__ xn) {
+                                                             int emulate_text, const Round4Tab* __restrict__ rtab,
+                                                             __half* __restrict__ Xh, __half* __restrict__ Xl, float* __restrict__ xn) {
     constexpr int WT = HAF_FT_WT, NW = 32 * WT;
-    extern __shared__ uint32_t s_words[];  // tile [NW][KP+1] of (hi | lo << 16), KP = Krow / 2; then float s_int[ROWS][ld]
+    extern __shared__ uint32_t s_words[];  // tile [NW][KPASS+1] of (hi | lo << 16); then float s_int[ROWS][ld .. ld + 31]
     const unsigned W = *win_count;
     const unsigned w0 = blockIdx.x * NW;
     if (w0 >= W) return;
     const int lane = threadIdx.x & 31;
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // provably warp-uniform for the compiler
-    const int ld = G + 1, KP = Krow >> 1, rs = KP + 1;
-    float* s_int = reinterpret_cast<float*>(s_words + NW * rs);  // [HAF_FT_ROWS][ld]
-    __shared__ int s_box[3];       // unit, first row, rows (0 = no staging)
-    __shared__ double s_pwd[81];   // 10^(i-40)
-    __shared__ float s_pwf[81];
+    const int ld = G + 1;
+    constexpr int rs = HAF_FT_KPASS + 1;
+    float* s_int = reinterpret_cast<float*>(s_words + NW * rs);  // [HAF_FT_ROWS][ld .. ld + 31]
+    uint4* s_tab = reinterpret_cast<uint4*>(s_words + ((NW * rs + HAF_FT_ROWS * (ld + 31) + 3) & ~3));  // [KPASS] DimFeat records of the pass
+    __shared__ int s_box[4];       // unit, first row, rows (0 = no staging), row stride of the staged image
+    __shared__ Round4Tab s_rt;
     int unit[WT], row[WT], col[WT];
     bool valid[WT];
 #pragma unroll
@@ -598,20 +629,40 @@ __global__ void __launch_bounds__(256, 4) features_tc_kernel(const float* __rest
             rmin = min(rmin, __shfl_xor_sync(0xffffffffu, rmin, o));
             rmax = max(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
         }
+        // BANK-CONFLICT-FREE STAGING.  Lanes are consecutive windows of the compact list: a warp-load touches columns
+        // a..b of one image row and a'..b' of the next.  With the natural row stride G + 1 the two runs overlap in banks
+        // and EVERY corner load took two wavefronts (ncu: 13 conflict wavefronts per 12 loads; the kernel is LSU-bound).
+        // The rows are therefore staged with the stride s = (b + 1 - a') mod 32 that makes the second run continue in the
+        // bank after the first; the per-dimension corner offsets for each of the 32 stride classes are precomputed
+        // (table[cls][d]).  The first row break of the CTA's windows picks s (axis-aligned masks break identically in
+        // every row; rotated ones differ by +-1 between rows, which leaves some two-wavefront loads).
+        int o = ld;
+        bool have = false;
+#pragma unroll
+        for (int t = 0; t < WT; t++) {
+            const int pc = __shfl_up_sync(0xffffffffu, col[t], 1), pr = __shfl_up_sync(0xffffffffu, row[t], 1);
+            const int pu = __shfl_up_sync(0xffffffffu, unit[t], 1);
+            const bool brk = lane > 0 && valid[t] && pu == unit[t] && row[t] == pr + 1;
+            const unsigned m = __ballot_sync(0xffffffffu, brk);
+            if (m && !have) { o = __shfl_sync(0xffffffffu, pc + 1 - col[t], __ffs(m) - 1); have = true; }
+        }
         if (lane == 0) {
             const int nr = rmax - rmin + 15;
             s_box[0] = u0;
             s_box[1] = rmin - 7;
             s_box[2] = (same && nr <= HAF_FT_ROWS) ? nr : 0;
+            s_box[3] = ld + (((o - ld) % 32) + 32) % 32;
         }
     }
-    if (threadIdx.x < 81) {
-        const double p = pow10_table(threadIdx.x - 40);
-        s_pwd[threadIdx.x] = p;
-        s_pwf[threadIdx.x] = (float)p;
-    }
+    for (int t = threadIdx.x; t < (int)(sizeof(Round4Tab) / 8); t += blockDim.x)
+        reinterpret_cast<uint2*>(&s_rt)[t] = __ldg(reinterpret_cast<const uint2*>(rtab) + t);
     __syncthreads();
+    Round4Smem rt;
+    rt.pwd = (uint32_t)__cvta_generic_to_shared(s_rt.pwd);
+    rt.pwf = (uint32_t)__cvta_generic_to_shared(s_rt.pwf);
     const int nrows = s_box[2];
+    const int sst = nrows > 0 ? s_box[3] : ld;           // row stride the corner offsets must be built for
+    table += (size_t)(sst - ld) * D;                      // stride class
     int idx0[WT];
     const float* gI[WT];
 #pragma unroll
@@ -621,17 +672,29 @@ __global__ void __launch_bounds__(256, 4) features_tc_kernel(const float* __rest
     }
     if (nrows > 0) {
         const float* src = integral + (size_t)(s_box[0] - unit_base) * ld * ld + (size_t)s_box[1] * ld;
-        for (int t = threadIdx.x; t < nrows * ld; t += blockDim.x) s_int[t] = src[t];
+        for (int t = threadIdx.x; t < nrows * ld; t += blockDim.x) {
+            const int r = t / ld, c = t - r * ld;
+            s_int[r * sst + c] = src[t];
+        }
 #pragma unroll
-        for (int t = 0; t < WT; t++) idx0[t] = valid[t] ? idx0[t] - s_box[1] * ld : 0;  // padding lanes read row 0 harmlessly
+        for (int t = 0; t < WT; t++) idx0[t] = valid[t] ? (row[t] - 7 - s_box[1]) * sst + (col[t] - 7) : 0;  // padding lanes read row 0 harmlessly
     }
+    const uint32_t tab_base = (uint32_t)__cvta_generic_to_shared(s_tab);
     SmemRows srows;
     srows.base = (uint32_t)__cvta_generic_to_shared(s_int);
     float nrm[NW / 8];  // squared-norm partials of the windows this warp writes out
 #pragma unroll
     for (int k = 0; k < NW / 8; k++) nrm[k] = 0.0f;
-    for (int pass = 0; pass < 2; pass++) {
-        const int d0 = pass * KP;
+    // The tile is kept small (4 passes at Krow = 336) on purpose: 4 resident CTAs then leave ~100 KB of the SM's unified
+    // memory to L1, where the 31 KB corner-offset table lives (with a 2-pass tile only ~30 KB remained, the table loads
+    // missed to L2 and their latency was the top stall).
+    for (int d0 = 0; d0 < Krow; d0 += HAF_FT_KPASS) {
+        const int KP = min(HAF_FT_KPASS, Krow - d0);   // a multiple of 16
+        {   // this pass's records of the stride class, coalesced
+            const int nrec = min(KP, D - d0);
+            const uint4* src = reinterpret_cast<const uint4*>(table + d0);
+            for (int t = threadIdx.x; t < nrec * 6; t += blockDim.x) s_tab[t] = __ldg(src + t);
+        }
         __syncthreads();
         for (int dl = warp; dl < KP; dl += 8) {
             const int d = d0 + dl;
@@ -639,24 +702,25 @@ __global__ void __launch_bounds__(256, 4) features_tc_kernel(const float* __rest
 #pragma unroll
             for (int t = 0; t < WT; t++) xf[t] = 0.0f;
             if (d < D) {
-                const FastTab f = load_fast_tab(table, d);
+                const FastTab f = load_fast_tab_smem(tab_base + 96u * dl);
                 if (nrows > 0) {
 #pragma unroll
-                    for (int t = 0; t < WT; t++) xf[t] = fast_tier_value(srows, idx0[t] * 4, f, lower, emulate_text, s_pwd, s_pwf);
+                    for (int t = 0; t < WT; t++) xf[t] = fast_tier_value(srows, idx0[t] * 4, f, lower, emulate_text, rt);
                 } else {
 #pragma unroll
-                    for (int t = 0; t < WT; t++) xf[t] = valid[t] ? fast_tier_value(gI[t], idx0[t], f, lower, emulate_text, s_pwd, s_pwf) : 0.0f;
+                    for (int t = 0; t < WT; t++) xf[t] = valid[t] ? fast_tier_value(gI[t], idx0[t], f, lower, emulate_text, rt) : 0.0f;
                 }
             }
-#pragma unroll
-            for (int t = 0; t < WT; t++) {
-                // fp16 hi + fp16 lo = 22 significant bits (absolute floor 2^-25 once lo is subnormal); values beyond the
-                // fp16 range are clamped to +-65504 and the window is sent to the FP64 exact path (xn = +inf below)
-                const float xc = fminf(fmaxf(xf[t], -65504.0f), 65504.0f);
-                const __half hi = __float2half_rn(xc);
-                const __half lo = __float2half_rn(xc - __half2float(hi));
-                s_words[(t * 32 + lane) * rs + dl] = (uint32_t)__half_as_ushort(hi) | ((uint32_t)__half_as_ushort(lo) << 16);
-            }
+            // fp16 hi + fp16 lo = 22 significant bits (absolute floor 2^-25 once lo is subnormal), two windows per conversion.
+            // A value beyond the fp16 range becomes hi = +-inf, lo = -+inf: the NaN / inf it produces stays inside this
+            // window's own accumulator row, and the window is sent to the FP64 exact path (xn = +inf below).
+            static_assert(WT == 2, "the packing below converts the two windows of a lane together");
+            const __half2 hi2 = __floats2half2_rn(xf[0], xf[1]);
+            const float2 hif = __half22float2(hi2);
+            const __half2 lo2 = __floats2half2_rn(xf[0] - hif.x, xf[1] - hif.y);
+            const uint32_t hu = *reinterpret_cast<const uint32_t*>(&hi2), lu = *reinterpret_cast<const uint32_t*>(&lo2);
+            s_words[lane * rs + dl] = __byte_perm(hu, lu, 0x5410);          // hi(w0) | lo(w0) << 16
+            s_words[(32 + lane) * rs + dl] = __byte_perm(hu, lu, 0x7632);   // hi(w1) | lo(w1) << 16
         }
         __syncthreads();
 #pragma unroll
@@ -679,7 +743,7 @@ __global__ void __launch_bounds__(256, 4) features_tc_kernel(const float* __rest
                 const float v0 = h01.x + l01.x, v1 = h01.y + l01.y;
                 sq = fmaf(v0, v0, sq);
                 sq = fmaf(v1, v1, sq);
-                if (fmaxf(fabsf(h01.x), fabsf(h01.y)) >= 65504.0f) sq = __int_as_float(0x7f800000);  // clamped: force exact
+                if (!(fmaxf(fabsf(h01.x), fabsf(h01.y)) < 65504.0f)) sq = __int_as_float(0x7f800000);  // left the fp16 range: force exact
             }
             nrm[k] = sq;
         }
