@@ -94,7 +94,9 @@ def make_clouds(args, wc, rank):
 
 
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    # the sampler is started BEFORE the warm-up steps (nvidia-smi needs a few hundred ms to deliver its first row) and
+    # only the rows stamped inside the timed region are kept
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
@@ -110,7 +112,12 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def mark_begin(self):
+        self.t_begin = time.time()
+
     def stop(self):
+        t_end = time.time()
+        t_begin = getattr(self, "t_begin", 0.0)
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if not self.proc:
             return out
@@ -120,24 +127,27 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         self.fh.close()
-        sm, mx, reasons = [], [], set()
+        import datetime
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
         with open(self.path) as fh:
             for ln in fh:
                 f = [x.strip() for x in ln.split(",")]
                 if len(f) < 9:
                     continue
                 try:
-                    sm.append(float(f[1]))
-                    mx.append(float(f[2]))
+                    ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    rows.append((ts, float(f[1]), float(f[2]), [nm for k, nm in enumerate(names) if f[5 + k].lower().startswith("active")]))
                 except ValueError:
                     continue
-                for k, nm in enumerate(names):
-                    if f[5 + k].lower().startswith("active"):
-                        reasons.add(nm)
         os.remove(self.path)
-        if sm:
-            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        inside = [r for r in rows if t_begin - 0.005 <= r[0] <= t_end + 0.005]
+        window = "timed region"
+        if not inside and rows:   # a timed region shorter than the sampling period: the rows nearest to it (warm-up of the same steps)
+            inside, window = rows[-3:], "last rows before the end of the timed region"
+        if inside:
+            out = {"sm_mhz": statistics.median(r[1] for r in inside), "sm_max_mhz": max(r[2] for r in inside),
+                   "reasons": sorted({nm for r in inside for nm in r[3]}), "samples": len(inside), "window": window}
         return out
 
 
@@ -314,11 +324,12 @@ def run_approach(args):
             ms, w = float(tm[0].item()), float(t[1].item())
         return ms, w
 
-    for _ in range(max(args.warmup, 3)):
-        step(dev)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        step(dev)
+    sampler.mark_begin()
     l0 = gs.launch_count()
     ms_dev, w_dev = timed(dev, args.steps)
     launches = gs.launch_count() - l0
@@ -424,11 +435,12 @@ def run_ours(args):
             acc["windows_all"] = float(acc["windows"])
         return ms, wall, acc
 
-    for _ in range(max(args.warmup, 3)):
-        step(dev)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        step(dev)
+    sampler.mark_begin()
     ms_dev, wall_dev, acc = timed(dev, args.steps)
     clocks = sampler.stop() if rank == 0 else {}
     # end to end: host (pinned) buffers in, results out, through the same C-ABI call

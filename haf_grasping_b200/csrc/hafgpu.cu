@@ -473,7 +473,7 @@ static int create_impl(haf_ctx** out, const haf_config* cfg, bool svm_only, int 
                         j.w[r] = 0.0f;
                     }
                 }
-                j.flags = ff.flags & 0x100;
+                j.flags = ff.flags & 0x104;   // SHAF, third region present
             } else {
                 j.flags = 0x200;
             }
@@ -490,8 +490,8 @@ static int create_impl(haf_ctx** out, const haf_config* cfg, bool svm_only, int 
         CREATE_TRY(cudaFuncSetAttribute(haftc::svm_rbf_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, haftc::SMEM_BYTES));
         CREATE_TRY(cudaFuncSetAttribute(haftc::svm_rbf_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, haftc::SMEM2_BYTES));
         CREATE_TRY(cudaFuncSetAttribute(features_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * HAF_FT_WT * (HAF_FT_KPASS + 1) * 4 + HAF_FT_ROWS * (G + 1 + 31) * 4 + 16 + HAF_FT_KPASS * 96));
-        // 4 CTAs x ~47 KB: ask for just that much shared memory so that the rest of the SM's 256 KB stays L1 (the corner-offset table)
-        CREATE_TRY(cudaFuncSetAttribute(features_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 85));
+        // 4 CTAs x ~49 KB: ask for just that much shared memory so that the rest of the SM's 256 KB stays L1 (the corner-offset table)
+        CREATE_TRY(cudaFuncSetAttribute(features_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 90));
     }
     for (int i = 0; i < 10; i++) CREATE_TRY(cudaEventCreate(&ctx->ev[i]));
     ctx->ev_ok = true;

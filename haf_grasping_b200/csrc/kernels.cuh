@@ -463,7 +463,7 @@ __device__ __forceinline__ double pow10_table(int k) {
     return k < 0 ? 1.0 / p : p;
 }
 
-#define HAF_FT_ROWS 24  // integral-image rows a features_tc CTA can stage in shared memory
+#define HAF_FT_ROWS 36  // integral-image rows a features_tc CTA can stage in shared memory (two blocks when its windows straddle two units)
 
 // Joined per-dimension record of the tensor-path feature kernel (built once per context): the feature's corner
 // offsets / weights / flags AND the dimension's scaling constants in one 96-byte record, so one dependent-load-free
@@ -471,7 +471,7 @@ __device__ __forceinline__ double pow10_table(int k) {
 struct __align__(16) DimFeat {
     int off[12];     // BYTE offsets of the corners; skipped regions: four identical corners (and weight +0.0)
     float w[3];
-    int flags;       // bit 8: SHAF; bit 9: constant dimension (value = cval); bit 10: dropped (value 0)
+    int flags;       // bit 2: third region present; bit 8: SHAF; bit 9: constant dimension (value = cval); bit 10: dropped (value 0)
     float fmin, slope, cval, padf;   // float copies: the fast tier needs ~1e-7 only
     double pad[2];
 };
@@ -538,15 +538,26 @@ __device__ __forceinline__ float fast_tier_value(PtrT I, int idx0, const FastTab
                                                  const Round4Smem rt) {
     float c[12];
 #pragma unroll
-    for (int k = 0; k < 12; k++) c[k] = load_corner(I, idx0, f.off[k]);
+    for (int k = 0; k < 8; k++) c[k] = load_corner(I, idx0, f.off[k]);
     float rr[3];
 #pragma unroll
-    for (int r = 0; r < 3; r++)  // ((P[x2+1][y2+1] - P[x1][y2+1]) - P[x2+1][y1]) + P[x1][y1]   (II2FV.cpp:161-162)
+    for (int r = 0; r < 2; r++)  // ((P[x2+1][y2+1] - P[x1][y2+1]) - P[x2+1][y1]) + P[x1][y1]   (II2FV.cpp:161-162)
         rr[r] = __fmul_rn(f.w[r], __fadd_rn(__fsub_rn(__fsub_rn(c[4 * r], c[4 * r + 1]), c[4 * r + 2]), c[4 * r + 3]));
-    const float haf = __fadd_rn(__fadd_rn(__fadd_rn(0.0f, rr[0]), rr[1]), rr[2]);
-    const float sa = __fsub_rn(rr[1], rr[0]), sb = __fsub_rn(rr[1], rr[2]);
-    const float shaf = (rr[1] > rr[0] && rr[1] > rr[2]) ? ((sb < sa) ? sb : sa) : -1.0f;  // II2FV.cpp:187-191
-    const float raw = (f.flags & 0x100) ? shaf : haf;
+    // 295 of the 323 features of data/Features.txt have no third region: a warp-uniform branch (the dimension is the
+    // same for all lanes) saves a third of the corner loads.  rr[2] = +0.0 is what the uniform code computed for them.
+    rr[2] = 0.0f;
+    if (f.flags & 0x4) {
+#pragma unroll
+        for (int k = 8; k < 12; k++) c[k] = load_corner(I, idx0, f.off[k]);
+        rr[2] = __fmul_rn(f.w[2], __fadd_rn(__fsub_rn(__fsub_rn(c[8], c[9]), c[10]), c[11]));
+    }
+    float raw;
+    if (f.flags & 0x100) {   // SHAF (21 of 323 features): warp-uniform branch
+        const float sa = __fsub_rn(rr[1], rr[0]), sb = __fsub_rn(rr[1], rr[2]);
+        raw = (rr[1] > rr[0] && rr[1] > rr[2]) ? ((sb < sa) ? sb : sa) : -1.0f;  // II2FV.cpp:187-191
+    } else {
+        raw = __fadd_rn(__fadd_rn(__fadd_rn(0.0f, rr[0]), rr[1]), rr[2]);
+    }
     float v = raw;
     if (emulate_text) {
         // "%.4g": a * 10^(3-E) is formed and rounded in DOUBLE (exact ties stay exact; a mis-decided near-tie needs
@@ -598,7 +609,7 @@ __global__ void __launch_bounds__(256, 4) features_tc_kernel(const float* __rest
     constexpr int rs = HAF_FT_KPASS + 1;
     float* s_int = reinterpret_cast<float*>(s_words + NW * rs);  // [HAF_FT_ROWS][ld .. ld + 31]
     uint4* s_tab = reinterpret_cast<uint4*>(s_words + ((NW * rs + HAF_FT_ROWS * (ld + 31) + 3) & ~3));  // [KPASS] DimFeat records of the pass
-    __shared__ int s_box[4];       // unit, first row, rows (0 = no staging), row stride of the staged image
+    __shared__ int s_box[7];       // unit A, its first row, rows (0 = no staging), row stride of the staged image; unit B, first row, rows
     __shared__ Round4Tab s_rt;
     int unit[WT], row[WT], col[WT];
     bool valid[WT];
@@ -615,19 +626,31 @@ __global__ void __launch_bounds__(256, 4) features_tc_kernel(const float* __rest
         }
     }
     if (threadIdx.x < 32) {
-        const int u0 = __shfl_sync(0xffffffffu, unit[0], 0);  // window w0 is always valid
-        bool same = true;
-        int rmin = 0x7fffffff, rmax = -1;
+        // The CTA's 64 consecutive windows belong to one unit or -- one CTA in ~9 on the bench workload -- to the end of
+        // one unit and the start of the next (each unit's windows are contiguous in the list).  Both units' image rows are
+        // staged, one block after the other; only a CTA touching three units (masks with < 64 windows) reads global memory.
+        const int uA = __shfl_sync(0xffffffffu, unit[0], 0);  // window w0 is always valid
+        int uB = uA;
+#pragma unroll
+        for (int t = 0; t < WT; t++) {   // unit of the last valid window
+            const unsigned vm = __ballot_sync(0xffffffffu, valid[t]);
+            if (vm) uB = __shfl_sync(0xffffffffu, unit[t], 31 - __clz(vm));
+        }
+        bool two = true;
+        int rminA = 0x7fffffff, rmaxA = -1, rminB = 0x7fffffff, rmaxB = -1;
 #pragma unroll
         for (int t = 0; t < WT; t++) {
-            same = same && (!valid[t] || unit[t] == u0);
-            if (valid[t]) { rmin = min(rmin, row[t]); rmax = max(rmax, row[t]); }
+            two = two && (!valid[t] || unit[t] == uA || unit[t] == uB);
+            if (valid[t] && unit[t] == uA) { rminA = min(rminA, row[t]); rmaxA = max(rmaxA, row[t]); }
+            else if (valid[t]) { rminB = min(rminB, row[t]); rmaxB = max(rmaxB, row[t]); }
         }
-        same = __all_sync(0xffffffffu, same);
+        two = __all_sync(0xffffffffu, two);
 #pragma unroll
         for (int o = 16; o >= 1; o >>= 1) {
-            rmin = min(rmin, __shfl_xor_sync(0xffffffffu, rmin, o));
-            rmax = max(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+            rminA = min(rminA, __shfl_xor_sync(0xffffffffu, rminA, o));
+            rmaxA = max(rmaxA, __shfl_xor_sync(0xffffffffu, rmaxA, o));
+            rminB = min(rminB, __shfl_xor_sync(0xffffffffu, rminB, o));
+            rmaxB = max(rmaxB, __shfl_xor_sync(0xffffffffu, rmaxB, o));
         }
         // BANK-CONFLICT-FREE STAGING.  Lanes are consecutive windows of the compact list: a warp-load touches columns
         // a..b of one image row and a'..b' of the next.  With the natural row stride G + 1 the two runs overlap in banks
@@ -647,11 +670,11 @@ __global__ void __launch_bounds__(256, 4) features_tc_kernel(const float* __rest
             if (m && !have) { o = __shfl_sync(0xffffffffu, pc + 1 - col[t], __ffs(m) - 1); have = true; }
         }
         if (lane == 0) {
-            const int nr = rmax - rmin + 15;
-            s_box[0] = u0;
-            s_box[1] = rmin - 7;
-            s_box[2] = (same && nr <= HAF_FT_ROWS) ? nr : 0;
+            const int nA = rmaxA - rminA + 15, nB = (uB != uA) ? rmaxB - rminB + 15 : 0;
+            const bool ok = two && nA + nB <= HAF_FT_ROWS;
+            s_box[0] = uA; s_box[1] = rminA - 7; s_box[2] = ok ? nA : 0;
             s_box[3] = ld + (((o - ld) % 32) + 32) % 32;
+            s_box[4] = uB; s_box[5] = rminB - 7; s_box[6] = ok ? nB : 0;
         }
     }
     for (int t = threadIdx.x; t < (int)(sizeof(Round4Tab) / 8); t += blockDim.x)
@@ -671,20 +694,25 @@ __global__ void __launch_bounds__(256, 4) features_tc_kernel(const float* __rest
         gI[t] = integral + (size_t)(unit[t] - unit_base) * ld * ld;
     }
     if (nrows > 0) {
-        const float* src = integral + (size_t)(s_box[0] - unit_base) * ld * ld + (size_t)s_box[1] * ld;
-        for (int t = threadIdx.x; t < nrows * ld; t += blockDim.x) {
+        const int nB = s_box[6];
+        const float* srcA = integral + (size_t)(s_box[0] - unit_base) * ld * ld + (size_t)s_box[1] * ld;
+        const float* srcB = integral + (size_t)(s_box[4] - unit_base) * ld * ld + (size_t)s_box[5] * ld - (size_t)nrows * ld;
+        for (int t = threadIdx.x; t < (nrows + nB) * ld; t += blockDim.x) {
             const int r = t / ld, c = t - r * ld;
-            s_int[r * sst + c] = src[t];
+            s_int[r * sst + c] = (r < nrows ? srcA : srcB)[t];
         }
 #pragma unroll
-        for (int t = 0; t < WT; t++) idx0[t] = valid[t] ? (row[t] - 7 - s_box[1]) * sst + (col[t] - 7) : 0;  // padding lanes read row 0 harmlessly
+        for (int t = 0; t < WT; t++) {   // padding lanes read row 0 harmlessly
+            const int r0 = (unit[t] == s_box[0]) ? row[t] - 7 - s_box[1] : nrows + row[t] - 7 - s_box[5];
+            idx0[t] = valid[t] ? r0 * sst + (col[t] - 7) : 0;
+        }
     }
     const uint32_t tab_base = (uint32_t)__cvta_generic_to_shared(s_tab);
     SmemRows srows;
     srows.base = (uint32_t)__cvta_generic_to_shared(s_int);
-    float nrm[NW / 8];  // squared-norm partials of the windows this warp writes out
+    float nrm[WT];  // squared-norm partials of this lane's windows over the dimensions this warp evaluates
 #pragma unroll
-    for (int k = 0; k < NW / 8; k++) nrm[k] = 0.0f;
+    for (int t = 0; t < WT; t++) nrm[t] = 0.0f;
     // The tile is kept small (4 passes at Krow = 336) on purpose: 4 resident CTAs then leave ~100 KB of the SM's unified
     // memory to L1, where the 31 KB corner-offset table lives (with a 2-pass tile only ~30 KB remained, the table loads
     // missed to L2 and their latency was the top stall).
@@ -718,9 +746,20 @@ __global__ void __launch_bounds__(256, 4) features_tc_kernel(const float* __rest
             const __half2 hi2 = __floats2half2_rn(xf[0], xf[1]);
             const float2 hif = __half22float2(hi2);
             const __half2 lo2 = __floats2half2_rn(xf[0] - hif.x, xf[1] - hif.y);
+            {   // squared norm of what the contraction will see (hi + lo), accumulated per lane over this warp's dimensions
+                const float2 lof = __half22float2(lo2);
+                const float v0 = hif.x + lof.x, v1 = hif.y + lof.y;
+                nrm[0] = fmaf(v0, v0, nrm[0]);
+                nrm[1] = fmaf(v1, v1, nrm[1]);
+            }
             const uint32_t hu = *reinterpret_cast<const uint32_t*>(&hi2), lu = *reinterpret_cast<const uint32_t*>(&lo2);
-            s_words[lane * rs + dl] = __byte_perm(hu, lu, 0x5410);          // hi(w0) | lo(w0) << 16
-            s_words[(32 + lane) * rs + dl] = __byte_perm(hu, lu, 0x7632);   // hi(w1) | lo(w1) << 16
+            // tile position of dimension dl: inside each block of 64 dimensions the even ones come first, then the odd
+            // ones, so that the write-out below reads words e and e + nbh (consecutive lanes -> consecutive banks) to
+            // form the pair (2e, 2e + 1); the natural order made every one of those reads a two-way bank conflict
+            const int blk = dl & ~63, nbh = min(64, KP - blk) >> 1;
+            const int pos = blk + ((dl & 63) >> 1) + ((dl & 1) ? nbh : 0);
+            s_words[lane * rs + pos] = __byte_perm(hu, lu, 0x5410);          // hi(w0) | lo(w0) << 16
+            s_words[(32 + lane) * rs + pos] = __byte_perm(hu, lu, 0x7632);   // hi(w1) | lo(w1) << 16
         }
         __syncthreads();
 #pragma unroll
@@ -731,30 +770,26 @@ __global__ void __launch_bounds__(256, 4) features_tc_kernel(const float* __rest
             const uint32_t* sw = s_words + wi * rs;
             uint32_t* gh = reinterpret_cast<uint32_t*>(Xh + (size_t)ww * Krow + d0);
             uint32_t* gl = reinterpret_cast<uint32_t*>(Xl + (size_t)ww * Krow + d0);
-            float sq = nrm[k];
             for (int e = lane; e < KP / 2; e += 32) {
-                const uint32_t a0 = sw[2 * e], a1 = sw[2 * e + 1];   // dims 2e, 2e+1: (hi | lo << 16)
-                const uint32_t h2 = __byte_perm(a0, a1, 0x5410);     // hi(2e) | hi(2e+1) << 16
-                const uint32_t l2 = __byte_perm(a0, a1, 0x7632);     // lo(2e) | lo(2e+1) << 16
-                gh[e] = h2;
-                gl[e] = l2;
-                const float2 h01 = __half22float2(*reinterpret_cast<const __half2*>(&h2));
-                const float2 l01 = __half22float2(*reinterpret_cast<const __half2*>(&l2));
-                const float v0 = h01.x + l01.x, v1 = h01.y + l01.y;
-                sq = fmaf(v0, v0, sq);
-                sq = fmaf(v1, v1, sq);
-                if (!(fmaxf(fabsf(h01.x), fabsf(h01.y)) < 65504.0f)) sq = __int_as_float(0x7f800000);  // left the fp16 range: force exact
+                const int blk = (e >> 5) << 6, nbh = min(64, KP - blk) >> 1;
+                const uint32_t a0 = sw[blk + (e & 31)], a1 = sw[blk + nbh + (e & 31)];   // dims 2e, 2e+1: (hi | lo << 16)
+                gh[e] = __byte_perm(a0, a1, 0x5410);     // hi(2e) | hi(2e+1) << 16
+                gl[e] = __byte_perm(a0, a1, 0x7632);     // lo(2e) | lo(2e+1) << 16
             }
-            nrm[k] = sq;
         }
     }
+    // squared norms: the 8 warps' partials of each window are summed through the (now free) tile; a value that left the fp16
+    // range made its window's partial inf - inf = NaN (or inf): such windows get xn = +inf = "always take the exact path"
+    __syncthreads();
+    float* s_nrm = reinterpret_cast<float*>(s_words);   // [8][NW]
 #pragma unroll
-    for (int k = 0; k < NW / 8; k++) {
-        const unsigned ww = w0 + warp + 8 * k;
-        float sq = nrm[k];
+    for (int t = 0; t < WT; t++) s_nrm[warp * NW + t * 32 + lane] = nrm[t];
+    __syncthreads();
+    if (threadIdx.x < NW && w0 + threadIdx.x < W) {
+        float sq = 0.0f;
 #pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-        if (lane == 0 && ww < W) xn[ww] = sq;
+        for (int k = 0; k < 8; k++) sq += s_nrm[k * NW + threadIdx.x];
+        xn[w0 + threadIdx.x] = (sq < 3.0e38f) ? sq : __int_as_float(0x7f800000);
     }
 }
 
