@@ -945,7 +945,7 @@ static int run_jobs(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& jobs, fl
     const size_t x_budget_floats = (size_t)3 << 28;  // 3 GiB of FP32 SVM inputs per chunk at most
     std::vector<std::pair<int, int> > chunks;   // [job_begin, job_end)
     {
-        int jb0 = 0;
+        int jb0 = 0, stage_limit = 16;
         while (jb0 < n_jobs) {
             long long wsum = 0;
             int je = jb0;
@@ -953,12 +953,16 @@ static int run_jobs(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& jobs, fl
                 const long long w = jobs[je].wbound;
                 if (je > jb0 && (size_t)(wsum + w) * ctx->Kpad > x_budget_floats) break;
                 if (je > jb0 && (je - jb0) * R >= 16384) break;
-                if (je > jb0 && ctx->copy_pieces > 0 && (je - jb0) >= 64) break;  // small chunks so compute overlaps the staging copies
+                // clouds being staged from host memory: the first chunk is small so that compute starts after ~1 ms of
+                // copying, later chunks grow by 1.5x -- a chunk's compute (~0.036 ms per cloud) then always outlasts the copy
+                // of the next one (~0.023 ms per cloud), and the bulk of the work runs in large, tail-free launches
+                if (je > jb0 && ctx->copy_pieces > 0 && (je - jb0) >= stage_limit) break;
                 wsum += w;
                 je++;
             }
             chunks.push_back(std::make_pair(jb0, je));
             jb0 = je;
+            stage_limit = std::min(256, stage_limit + stage_limit / 2);
         }
     }
     if ((out_evals || out_mask || out_heights || keep_debug_state) && chunks.size() != 1)
