@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--clouds", type=int, default=512, help="clouds per GPU (batch workload)")
     ap.add_argument("--points", type=int, default=100000)
     ap.add_argument("--nsv", type=int, default=2048)
+    ap.add_argument("--sv-table-global", type=int, default=0, help="experiment: 1 = tensor kernels read the SV table from global memory")
     ap.add_argument("--svm-mode", type=int, default=0, help="0 tcgen05 split-fp16 + FP64 guard (default), 1 FP64 exact, 2 FP32 SIMT + guard")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-clouds", type=int, default=2)
@@ -387,7 +388,7 @@ def run_ours(args):
     n_clouds = len(clouds)
 
     gs = h.GraspSearch(FEATURES, RANGE, model, grid=wc["grid"], roll_step_deg=wc["step"], roll_max_deg=wc["rmax"],
-                       device=local, svm_mode=args.svm_mode)
+                       device=local, svm_mode=args.svm_mode, sv_table_global=args.sv_table_global)
     stream = torch.cuda.current_stream()
     gs.set_stream(stream.cuda_stream)
     gs.set_profiling(True)

@@ -94,8 +94,9 @@ struct haf_ctx {
     // tensor-core path (HAF_SVM_TENSOR_GUARD): fp16 hi/lo operands, K-major rows of Krow elements
     int Krow = 0, SpadT = 0;
     float c_log2 = 0.0f;
+    float csvn_max = 0.0f;      // |c| * max_n ||sv_n||^2 (guard scale of the tensor kernels)
     DevBuf<__half> d_SVh, d_SVl, d_Xh, d_Xl;
-    DevBuf<float4> d_svtab;
+    DevBuf<float2> d_svtab;
     DevBuf<DimFeat> d_dimfeat;
     DevBuf<Round4Tab> d_round4;   // "%.4g" tables of the fast tier
     DevBuf<float> d_asum;
@@ -419,8 +420,8 @@ static int create_impl(haf_ctx** out, const haf_config* cfg, bool svm_only, int 
         ctx->c_log2 = (float)(-model.gamma * 1.4426950408889634);
         if (cfg->guard_rel <= 0) ctx->guard_rel = 4e-6f;  // of E (see svm_tc.cuh); measured split-fp16 + fast-tier error <= 3.3e-7 E (tools/dec_error_probe.py)
         std::vector<uint16_t> svh((size_t)SpadT * Krow, 0), svl((size_t)SpadT * Krow, 0);
-        std::vector<float4> tab(SpadT);
-        for (int i = 0; i < SpadT; i++) tab[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        std::vector<float2> tab(SpadT);
+        for (int i = 0; i < SpadT; i++) tab[i] = make_float2(0.0f, 0.0f);
         for (int i = 0; i < S; i++) {
             float nrm = 0.0f;
             for (size_t e = 0; e < model.sv[i].size(); e++) {
@@ -439,13 +440,13 @@ static int create_impl(haf_ctx** out, const haf_config* cfg, bool svm_only, int 
             }
             tab[i].x = ctx->c_log2 * nrm;
             tab[i].y = (float)model.coef[i];
-            tab[i].z = fabsf(tab[i].y) * fabsf(tab[i].x);   // guard scale term, see svm_tc.cuh
+            ctx->csvn_max = std::max(ctx->csvn_max, fabsf(tab[i].x));
         }
         bool okt = ctx->d_SVh.ensure(svh.size()) == 0 && ctx->d_SVl.ensure(svl.size()) == 0 && ctx->d_svtab.ensure(SpadT) == 0;
         if (!okt) { haf_destroy(ctx); return create_fail(HAF_ERR_NOMEM, "out of device memory uploading the fp16 model"); }
         CREATE_TRY(cudaMemcpy(ctx->d_SVh.p, svh.data(), svh.size() * 2, cudaMemcpyHostToDevice));
         CREATE_TRY(cudaMemcpy(ctx->d_SVl.p, svl.data(), svl.size() * 2, cudaMemcpyHostToDevice));
-        CREATE_TRY(cudaMemcpy(ctx->d_svtab.p, tab.data(), SpadT * sizeof(float4), cudaMemcpyHostToDevice));
+        CREATE_TRY(cudaMemcpy(ctx->d_svtab.p, tab.data(), SpadT * sizeof(float2), cudaMemcpyHostToDevice));
         ctx->tc_variant = cfg->reserved[0];
         if (!make_tensor_map(&ctx->tmSh, ctx->d_SVh.p, Krow, SpadT, haftc::BN) || !make_tensor_map(&ctx->tmSl, ctx->d_SVl.p, Krow, SpadT, haftc::BN) ||
             !make_tensor_map(&ctx->tmSh2, ctx->d_SVh.p, Krow, SpadT, haftc::BN / 2) || !make_tensor_map(&ctx->tmSl2, ctx->d_SVl.p, Krow, SpadT, haftc::BN / 2)) {
@@ -487,8 +488,8 @@ static int create_impl(haf_ctx** out, const haf_config* cfg, bool svm_only, int 
         CREATE_TRY(cudaMemcpy(ctx->d_round4.p, &r4, sizeof(Round4Tab), cudaMemcpyHostToDevice));
         if (ctx->d_dimfeat.ensure(joined.size()) != 0) { haf_destroy(ctx); return create_fail(HAF_ERR_NOMEM, "out of device memory uploading the joined feature table"); }
         CREATE_TRY(cudaMemcpy(ctx->d_dimfeat.p, joined.data(), joined.size() * sizeof(DimFeat), cudaMemcpyHostToDevice));
-        CREATE_TRY(cudaFuncSetAttribute(haftc::svm_rbf_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, haftc::SMEM_BYTES));
-        CREATE_TRY(cudaFuncSetAttribute(haftc::svm_rbf_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, haftc::SMEM2_BYTES));
+        CREATE_TRY(cudaFuncSetAttribute(haftc::svm_rbf_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, haftc::SMEM_BYTES + haftc::TAB_SMEM_MAX * 8));
+        CREATE_TRY(cudaFuncSetAttribute(haftc::svm_rbf_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, haftc::SMEM2_BYTES + haftc::TAB_SMEM_MAX * 8));
         CREATE_TRY(cudaFuncSetAttribute(features_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * HAF_FT_WT * (HAF_FT_KPASS + 1) * 4 + HAF_FT_ROWS * (G + 1 + 31) * 4 + 16 + HAF_FT_KPASS * 96));
         // 4 CTAs x ~49 KB: ask for just that much shared memory so that the rest of the SM's 256 KB stays L1 (the corner-offset table)
         CREATE_TRY(cudaFuncSetAttribute(features_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 90));
@@ -835,19 +836,21 @@ static int svm_stage(haf_ctx* ctx, unsigned* cnt, size_t Wcap, size_t ldx, int G
         if (mt_cap < ctx->sm_count) nsplit = std::min(n_ntiles, (2 * ctx->sm_count + mt_cap - 1) / mt_cap);
         const int kblocks = (ctx->Krow + haftc::BK - 1) / haftc::BK;
         const int last_slices = (ctx->Krow - haftc::BK * (kblocks - 1)) / 16;
+        const int tab_smem = (ctx->SpadT <= haftc::TAB_SMEM_MAX && !ctx->cfg.reserved[3]) ? 1 : 0;   // {c|sv|^2, coef} table staged in shared memory
+        const size_t tab_bytes = tab_smem ? (size_t)ctx->SpadT * 8 : 0;
         if (ctx->tc_variant == 0) {
             const int pairs_cap = (mt_cap + 1) / 2;
             int nsplit2 = 1;
             if (pairs_cap < ctx->sm_count / 2) nsplit2 = std::min(n_ntiles, (ctx->sm_count + pairs_cap - 1) / pairs_cap);
             int grid2 = (int)std::min<long long>((long long)pairs_cap * nsplit2 * 2, ctx->sm_count);
             grid2 &= ~1;  // whole clusters
-            haftc::svm_rbf_tc2_kernel<<<grid2, haftc::THREADS, haftc::SMEM2_BYTES, st>>>(tmXh, tmXl, ctx->tmSh2, ctx->tmSl2, ctx->d_xn.p, ctx->d_svtab.p,
+            haftc::svm_rbf_tc2_kernel<<<grid2, haftc::THREADS, haftc::SMEM2_BYTES + tab_bytes, st>>>(tmXh, tmXl, ctx->tmSh2, ctx->tmSl2, ctx->d_xn.p, ctx->d_svtab.p,
                                                                                          ctx->c_log2, cnt + 0, n_ntiles, nsplit2, kblocks, last_slices,
-                                                                                         ctx->d_dec.p, ctx->d_asum.p);
+                                                                                         ctx->d_dec.p, ctx->d_asum.p, tab_smem, ctx->csvn_max);
         } else {
             const int grid = (int)std::min<long long>((long long)mt_cap * nsplit, ctx->sm_count);
-            haftc::svm_rbf_tc_kernel<<<grid, haftc::THREADS, haftc::SMEM_BYTES, st>>>(tmXh, tmXl, ctx->tmSh, ctx->tmSl, ctx->d_xn.p, ctx->d_svtab.p, ctx->c_log2,
-                                                                                      cnt + 0, n_ntiles, nsplit, kblocks, last_slices, ctx->d_dec.p, ctx->d_asum.p);
+            haftc::svm_rbf_tc_kernel<<<grid, haftc::THREADS, haftc::SMEM_BYTES + tab_bytes, st>>>(tmXh, tmXl, ctx->tmSh, ctx->tmSl, ctx->d_xn.p, ctx->d_svtab.p, ctx->c_log2,
+                                                                                      cnt + 0, n_ntiles, nsplit, kblocks, last_slices, ctx->d_dec.p, ctx->d_asum.p, tab_smem, ctx->csvn_max);
         }
         LAUNCHED(ctx);
         haftc::svm_finalize_kernel<<<(unsigned)((Wcap + 255) / 256), 256, 0, st>>>(ctx->d_dec.p, ctx->d_asum.p, ctx->d_xn.p, cnt + 0, ctx->rho, ctx->guard_rel,

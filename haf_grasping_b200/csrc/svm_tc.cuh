@@ -36,6 +36,7 @@ constexpr int B_TILE_BYTES = BN * BK * 2;   // 32 KB
 constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;  // 96 KB
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int THREADS = 192;
+constexpr int TAB_SMEM_MAX = 4096;   // support vectors whose {c|sv|^2, coef} fit next to the operand ring (8 B each)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -93,6 +94,28 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
+// entry k of the current SV tile's table: broadcast LDS from the staged copy, or a per-thread global load
+__device__ __forceinline__ float2 tab_entry(uint32_t tab_s, const float2* __restrict__ tab, int k) {
+    float2 t;
+    if (tab_s) asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(t.x), "=f"(t.y) : "r"(tab_s + 8u * (uint32_t)k));
+    else t = __ldg(tab + k);
+    return t;
+}
+
+// 32 accumulator columns of one window row: exp2 / coef / row sums  (k0 = first column of the chunk within the SV tile)
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], uint32_t tab_s, const float2* __restrict__ tab, int k0,
+                                               float c2, float u, float& ps, float& pa) {
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+        const float2 t = tab_entry(tab_s, tab, k0 + j);
+        float arg = fmaf(__uint_as_float(r[j]), c2, u + t.x);  // c * (xn + svn - 2 dot)
+        arg = fminf(arg, 0.0f);                                // d^2 >= 0
+        const float e = ex2_approx(arg);
+        ps = fmaf(t.y, e, ps);
+        pa = fmaf(fabsf(t.y), e, pa);                          // sum |coef| K
+    }
+}
+
 #define HAFTC_LD32(taddr, r)                                                                                          \
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                            \
                  "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                             \
@@ -103,10 +126,15 @@ __device__ __forceinline__ float ex2_approx(float x) {
                    "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]) \
                  : "r"(taddr))
 
-// svtab[n] = { c * ||sv_n||^2 , coef_n , |coef_n| * |c| * ||sv_n||^2 , 0 }  (padding SVs: coef = 0).
-// dec_acc / asum_acc must be zeroed before launch.
+// svtab[n] = { c * ||sv_n||^2 , coef_n }  (padding SVs: coef = 0).  dec_acc / asum_acc must be zeroed before launch.
+// tab_smem != 0: the whole table (n_ntiles * BN entries, <= TAB_SMEM_MAX) is copied to shared memory once per CTA and the
+// epilogue reads it with broadcast LDS (one wavefront per entry); read per thread from global memory the same entries
+// cost 2-4 wavefronts each and took a quarter to a half of the LSU data pipe next to the TMA traffic.
 //
-// GUARD SCALE.  Next to the decision sum the epilogue accumulates  E = sum_i |coef_i| K_i (1 + |c| (||x||^2 + ||sv_i||^2)):
+// GUARD SCALE.  Next to the decision sum the epilogue accumulates  sum_i |coef_i| K_i  and scales it to
+// E = (1 + |c| (||x||^2 + max_n ||sv_n||^2)) sum_i |coef_i| K_i  >=  sum_i |coef_i| K_i (1 + |c| (||x||^2 + ||sv_i||^2))
+// (csvn_max = |c| max_n ||sv_n||^2 is a model constant; weighting every term by its own ||sv_i||^2 cost two more FP32
+// instructions per element and put the epilogue, not the MMAs, on the critical path: tensor pipe 98 % -> 89 %):
 // a term's FP32 error is K_i times the absolute error of its exponent argument, which grows with the magnitude of the
 // three numbers the argument is assembled from (c xn, c svn, -2 c dot; |2 dot| <= xn + svn) -- a flat fraction of
 // sum |coef| K under-estimates it by that factor for models with a large gamma (measured: tools/dec_error_probe.py).
@@ -114,8 +142,8 @@ __device__ __forceinline__ float ex2_approx(float x) {
 __global__ void __launch_bounds__(THREADS, 1)
 svm_rbf_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl,
                   const __grid_constant__ CUtensorMap tmSh, const __grid_constant__ CUtensorMap tmSl,
-                  const float* __restrict__ xn, const float4* __restrict__ svtab, float c, const unsigned* __restrict__ win_count,
-                  int n_ntiles, int nsplit, int kblocks, int last_slices, double* __restrict__ dec_acc, float* __restrict__ asum_acc) {
+                  const float* __restrict__ xn, const float2* __restrict__ svtab, float c, const unsigned* __restrict__ win_count,
+                  int n_ntiles, int nsplit, int kblocks, int last_slices, double* __restrict__ dec_acc, float* __restrict__ asum_acc, int tab_smem, float csvn_max) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // 128B swizzle needs 1024-byte aligned tiles
     const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
@@ -124,7 +152,13 @@ svm_rbf_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constan
     const uint32_t bar_tfull = bar_base + 16 * STAGES;  // [2]
     const uint32_t bar_tempty = bar_tfull + 16;         // [2]
     const uint32_t tmem_slot = bar_tempty + 16;         // u32
+    const uint32_t tab_base = bar_base + 256;           // float2 [n_ntiles * BN] when tab_smem
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (tab_smem)
+        for (int k = threadIdx.x; k < n_ntiles * BN; k += THREADS) {
+            const float2 t = __ldg(svtab + k);
+            asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(tab_base + 8u * (uint32_t)k), "f"(t.x), "f"(t.y) : "memory");
+        }
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
@@ -211,29 +245,27 @@ svm_rbf_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constan
                 const uint32_t a = acc_it & 1u, aph = (acc_it >> 1) & 1u;
                 mbar_wait(bar_tfull + 8 * a, aph);
                 tc_fence_after();
-                float ps = 0.0f, pa = 0.0f, pb = 0.0f;
-                const float4* tab = svtab + (size_t)nt * BN;
+                float ps = 0.0f, pa = 0.0f;
+                const float2* tab = svtab + (size_t)nt * BN;
+                const uint32_t tab_s = tab_smem ? tab_base + (uint32_t)nt * BN * 8u : 0u;
+                // two 32-column chunks in flight: the TMEM load of the next chunk is issued before the current one is
+                // evaluated (tcgen05.wait::ld covers every load issued so far)
+                const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + a * BN;
+                uint32_t ra[32], rb[32];
+                HAFTC_LD32(taddr0, ra);
 #pragma unroll 1
-                for (int ch = 0; ch < BN / 32; ch++) {
-                    uint32_t r[32];
-                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * BN + ch * 32;
-                    HAFTC_LD32(taddr, r);
+                for (int ch = 0; ch < BN / 32; ch += 2) {
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        const float4 t = __ldg(tab + ch * 32 + j);
-                        float arg = fmaf(__uint_as_float(r[j]), c2, u + t.x);  // c * (xn + svn - 2 dot)
-                        arg = fminf(arg, 0.0f);                                // d^2 >= 0
-                        const float e = ex2_approx(arg);
-                        ps = fmaf(t.y, e, ps);
-                        pa = fmaf(fabsf(t.y), e, pa);   // sum |coef| K
-                        pb = fmaf(t.z, e, pb);          // sum |coef| K |c| svn
-                    }
+                    HAFTC_LD32(taddr0 + (ch + 1) * 32, rb);
+                    epilogue_chunk(ra, tab_s, tab, ch * 32, c2, u, ps, pa);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (ch + 2 < BN / 32) HAFTC_LD32(taddr0 + (ch + 2) * 32, ra);
+                    epilogue_chunk(rb, tab_s, tab, (ch + 1) * 32, c2, u, ps, pa);
                 }
                 tc_fence_before();
                 mbar_arrive(bar_tempty + 8 * a);
                 dsum += (double)ps;
-                asum += fmaf(1.0f - u, pa, pb);   // sum_i |coef_i| K_i (1 + |c| (xn + svn_i)): the scale of the FP32 error
+                asum += (1.0f - u + csvn_max) * pa;   // >= sum_i |coef_i| K_i (1 + |c| (xn + svn_i)): the scale of the FP32 error
             }
             if (m < W && nt1 > nt0) {
                 atomicAdd(dec_acc + m, dsum);
@@ -310,8 +342,8 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 svm_rbf_tc2_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl,
                    const __grid_constant__ CUtensorMap tmSh2, const __grid_constant__ CUtensorMap tmSl2,
-                   const float* __restrict__ xn, const float4* __restrict__ svtab, float c, const unsigned* __restrict__ win_count,
-                   int n_ntiles, int nsplit, int kblocks, int last_slices, double* __restrict__ dec_acc, float* __restrict__ asum_acc) {
+                   const float* __restrict__ xn, const float2* __restrict__ svtab, float c, const unsigned* __restrict__ win_count,
+                   int n_ntiles, int nsplit, int kblocks, int last_slices, double* __restrict__ dec_acc, float* __restrict__ asum_acc, int tab_smem, float csvn_max) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + STAGES2 * STAGE2_BYTES;
@@ -320,7 +352,13 @@ svm_rbf_tc2_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_consta
     const uint32_t bar_tfull = bar_base + 16 * STAGES2;   // [2]        (one per CTA)
     const uint32_t bar_tempty = bar_tfull + 16;           // [2]        (used in the leader CTA)
     const uint32_t tmem_slot = bar_tempty + 16;
+    const uint32_t tab_base = bar_base + 256;             // float2 [n_ntiles * BN] when tab_smem
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (tab_smem)
+        for (int k = threadIdx.x; k < n_ntiles * BN; k += THREADS) {
+            const float2 t = __ldg(svtab + k);
+            asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(tab_base + 8u * (uint32_t)k), "f"(t.x), "f"(t.y) : "memory");
+        }
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
 
@@ -412,29 +450,27 @@ svm_rbf_tc2_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_consta
                 const uint32_t a = acc_it & 1u, aph = (acc_it >> 1) & 1u;
                 mbar_wait(bar_tfull + 8 * a, aph);
                 tc_fence_after();
-                float ps = 0.0f, pa = 0.0f, pb = 0.0f;
-                const float4* tab = svtab + (size_t)nt * BN;
+                float ps = 0.0f, pa = 0.0f;
+                const float2* tab = svtab + (size_t)nt * BN;
+                const uint32_t tab_s = tab_smem ? tab_base + (uint32_t)nt * BN * 8u : 0u;
+                // two 32-column chunks in flight: the TMEM load of the next chunk is issued before the current one is
+                // evaluated (tcgen05.wait::ld covers every load issued so far)
+                const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + a * BN;
+                uint32_t ra[32], rb[32];
+                HAFTC_LD32(taddr0, ra);
 #pragma unroll 1
-                for (int ch = 0; ch < BN / 32; ch++) {
-                    uint32_t r[32];
-                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * BN + ch * 32;
-                    HAFTC_LD32(taddr, r);
+                for (int ch = 0; ch < BN / 32; ch += 2) {
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        const float4 t = __ldg(tab + ch * 32 + j);
-                        float arg = fmaf(__uint_as_float(r[j]), c2, u + t.x);  // c * (xn + svn - 2 dot)
-                        arg = fminf(arg, 0.0f);                                // d^2 >= 0
-                        const float e = ex2_approx(arg);
-                        ps = fmaf(t.y, e, ps);
-                        pa = fmaf(fabsf(t.y), e, pa);   // sum |coef| K
-                        pb = fmaf(t.z, e, pb);          // sum |coef| K |c| svn
-                    }
+                    HAFTC_LD32(taddr0 + (ch + 1) * 32, rb);
+                    epilogue_chunk(ra, tab_s, tab, ch * 32, c2, u, ps, pa);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (ch + 2 < BN / 32) HAFTC_LD32(taddr0 + (ch + 2) * 32, ra);
+                    epilogue_chunk(rb, tab_s, tab, (ch + 1) * 32, c2, u, ps, pa);
                 }
                 tc_fence_before();
                 mbar_arrive_cluster((bar_tempty + 8 * a) & PEER_MASK);  // on the LEADER's barrier (count 256)
                 dsum += (double)ps;
-                asum += fmaf(1.0f - u, pa, pb);   // sum_i |coef_i| K_i (1 + |c| (xn + svn_i)): the scale of the FP32 error
+                asum += (1.0f - u + csvn_max) * pa;   // >= sum_i |coef_i| K_i (1 + |c| (xn + svn_i)): the scale of the FP32 error
             }
             if (m < W && nt1 > nt0) {
                 atomicAdd(dec_acc + m, dsum);

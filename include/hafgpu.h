@@ -60,7 +60,9 @@ typedef struct {
     int reserved[4];           /* [0]: tensor-path kernel variant, 0 = CTA-pair (cta_group::2, default), 1 = single CTA;
                                   [1]: 1 = always use the point-parallel binning kernel (no whole-cloud CTAs);
                                   [2]: guard band tier 2 (FP64 FMA re-evaluation): 0 = on, 1 = off (every guard window goes
-                                       to the exact-order kernels), 2 = on, but every window escalates as well (tests) */
+                                       to the exact-order kernels), 2 = on, but every window escalates as well (tests);
+                                  [3]: 1 = tensor kernels read the {c|sv|^2, coef} table from global memory even when it fits in
+                                       shared memory (the path models with > 4096 support vectors take) */
 } haf_config;
 
 /* One grasp goal = the hot-path fields of GraspInput (msg/GraspInput.msg:3-15). */

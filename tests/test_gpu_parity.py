@@ -240,11 +240,14 @@ def test_tensor_mode_fast_tier_inputs_track_the_exact_scaled_values(hg, oracle_l
         gpu.close()
 
 
-def test_tensor_core_mode_synth_models_and_batch(hg, oracle_lib, tmp_models):
+@pytest.mark.parametrize("kw", [{}, {"sv_table_global": 1}, {"tc_variant": 1}, {"tc_variant": 1, "sv_table_global": 1}])
+def test_tensor_core_mode_synth_models_and_batch(hg, oracle_lib, tmp_models, kw):
+    """CTA-pair and single-CTA kernels, with the {c|sv|^2, coef} table staged in shared memory (default) or read from
+    global memory (what models with > 4096 support vectors get)."""
     from haf_grasping_b200 import synth
     for nsv in (256, 300):   # 300: support-vector count not a multiple of the 256-wide tile
         model = tmp_models(nsv)
-        p = Pair(hg, oracle_lib, model, svm_mode=hg.HAF_SVM_TENSOR_GUARD)
+        p = Pair(hg, oracle_lib, model, svm_mode=hg.HAF_SVM_TENSOR_GUARD, **kw)
         try:
             cl = [synth.synth_cloud(4321 + i, 15000 + 211 * i) for i in range(5)]
             best = p.gpu.search_batch(cl)
