@@ -494,7 +494,7 @@ def run_ours(args):
                          "kernel_ms": svm_ms, "share_of_step": acc["svm"] / ms_dev if ms_dev else None,
                          "note": {2: "FP32 SIMT contraction (CUDA cores), measured against the bf16 tensor peak for comparability",
                                   1: "FP64 exact-order path", 0: "algorithmic flops; the split-fp16 scheme issues 3 tensor-core MMAs per algorithmic MMA, "
-                                  "executed tensor flops = 3 x (Krow/D) x algorithmic (ncu: tensor pipe 98.5 % active, profiles/r1_final_full.md)"}[args.svm_mode]},
+                                  "executed tensor flops = 3 x (Krow/D) x algorithmic (ncu: tensor pipe 98.6 % active, profiles/r1_s2_full.md)"}[args.svm_mode]},
             "stage_ms_per_step": {k: acc[k] / args.steps for k in ("bin", "integral", "mask", "features", "svm", "guard", "score")},
             "stage_roofline": stage_roofline(acc, args.steps, total_pts, n_clouds * info.n_rolls, info.grid, info.n_dims, W_step, hbm),
             "guard_windows_per_step": acc["guardw"] / args.steps,

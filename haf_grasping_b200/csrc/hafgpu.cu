@@ -1063,7 +1063,7 @@ static int run_jobs(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& jobs, fl
         // 3. mask + window compaction
         if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[ci * 8 + 2], st));
         mask_windows_kernel<<<dim3((GG + 4095) / 4096, Uc), 256, 0, st>>>(ctx->d_integral.p, units_c, G, ctx->d_mask.p, ctx->d_labelgrid.p,
-                                                                         ctx->d_win.p, cnt + 0, (unsigned)Wcap, (int*)(cnt + 2), ubase);
+                                                                         ctx->d_win.p, cnt + 0, (unsigned)Wcap, (int*)(cnt + 2), ubase, ctx->d_unit_windows.p + ubase);
         LAUNCHED(ctx);
         // 4. features -> scaled SVM inputs
         if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[ci * 8 + 3], st));
@@ -1088,7 +1088,7 @@ static int run_jobs(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& jobs, fl
         // 6. labels -> grids, score stencil, argmax, tie rule
         if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[ci * 8 + 6], st));
         label_scatter_kernel<<<(unsigned)((Wcap + 255) / 256), 256, 0, st>>>(ctx->d_dec.p, ctx->d_win.p, cnt + 0, G, ubase, ctx->gv[0], ctx->gv[1],
-                                                                            ctx->d_labelgrid.p, ctx->d_unit_windows.p + ubase);
+                                                                            ctx->d_labelgrid.p);
         LAUNCHED(ctx);
         score_kernel<<<dim3((GG + 255) / 256, Uc), 256, 0, st>>>(ctx->d_labelgrid.p, G, units_c, ctx->d_evals.p, ctx->d_unit_top.p + ubase);
         LAUNCHED(ctx);

@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(256) mask_windows_kernel(const float* __restri
                                                            signed char* __restrict__ labelgrid,
                                                            int2* __restrict__ win, unsigned* __restrict__ win_count,
                                                            unsigned win_cap, int* __restrict__ overflow_flag,
-                                                           int unit_base) {
+                                                           int unit_base, unsigned* __restrict__ unit_windows) {
     const int u = blockIdx.y;
     const UnitParams up = units[u];
     const int GG = G * G, ld = G + 1;
@@ -349,6 +349,7 @@ __global__ void __launch_bounds__(256) mask_windows_kernel(const float* __restri
         for (int k = 0; k < 16; k++)
             for (int w = 0; w < 8; w++) { s_off[k][w] = run; run += s_cnt[k][w]; }
         unsigned base = run ? atomicAdd(win_count, run) : 0u;
+        if (run) atomicAdd(unit_windows + u, run);   // windows of this unit (n_windows_scored); one atomic per CTA
         if (base + run > win_cap) { *overflow_flag = 1; base = 0xFFFFFFFFu; }
         s_base = base;
     }
@@ -1221,13 +1222,12 @@ __global__ void __launch_bounds__(256) guard_fma_kernel(const ExactArgs A, const
 // label -> graspsgrid value (server.cpp:843) scattered into the unit grids
 __global__ void label_scatter_kernel(const double* __restrict__ dec, const int2* __restrict__ win,
                                      const unsigned* __restrict__ win_count, int G, int unit_base, int gv_pos, int gv_neg,
-                                     signed char* __restrict__ labelgrid, unsigned* __restrict__ unit_windows) {
+                                     signed char* __restrict__ labelgrid) {
     const unsigned W = *win_count;
     const unsigned w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= W) return;
     const int2 uc = win[w];
     labelgrid[(size_t)(uc.x - unit_base) * G * G + uc.y] = (signed char)((dec[w] > 0.0) ? gv_pos : gv_neg);  // svm.cpp:2516
-    atomicAdd(unit_windows + (uc.x - unit_base), 1u);
 }
 
 // ---------------------------------------------------------------------------------------------------
