@@ -180,6 +180,49 @@ def test_haf_svm_predict_decision_values_against_libsvm_in_process(roll_files, o
 
 
 @pytest.mark.gpu
+def test_svm_predict_empty_file_and_rows_without_features(tools, roll_files, oracle_lib, tmp_path):
+    _, ref_predict = _ref_bins(oracle_lib)
+    for name, text in (("empty.txt", ""), ("bare.txt", "1\n-1 \n+1 3:0.25\n")):
+        src = tmp_path / name
+        src.write_text(text)
+        a = subprocess.run([ref_predict, str(src), roll_files["synth"], str(tmp_path / "ref.out")], capture_output=True)
+        b = subprocess.run([tools[0], str(src), roll_files["synth"], str(tmp_path / "mine.out")], capture_output=True)
+        assert a.returncode == b.returncode == 0
+        assert a.stdout == b.stdout
+        assert open(tmp_path / "ref.out", "rb").read() == open(tmp_path / "mine.out", "rb").read()
+
+
+@pytest.mark.gpu
+def test_haf_svm_predict_chunking_is_invisible(roll_files):
+    """More rows than one pass holds (512 MB of densified doubles): results of a row must not depend on the chunk or the
+    tile it lands in -- a subset predicted on its own gives the same decision values: bit-identical outside the guard band
+    (the FP64 FMA tier sums its support-vector slices in arrival order, so band rows may differ in the last bits)."""
+    import haf_grasping_b200 as h
+    rng = np.random.default_rng(11)
+    n, width = 230000, 330                      # 230 000 x 330 doubles = 607 MB -> two chunks
+    nnz_per_row = 4
+    idx = np.sort(rng.integers(1, width + 1, size=(n, nnz_per_row)), axis=1)
+    idx[:, 1:] += (idx[:, 1:] <= idx[:, :-1]).cumsum(axis=1)  # make strictly ascending (may exceed width: clip below)
+    idx = np.minimum(idx, width - nnz_per_row + np.arange(nnz_per_row) + 1)
+    for k in range(1, nnz_per_row):
+        idx[:, k] = np.maximum(idx[:, k], idx[:, k - 1] + 1)
+    val = rng.uniform(-1, 1, size=(n, nnz_per_row))
+    rp = np.arange(0, (n + 1) * nnz_per_row, nnz_per_row, dtype=np.int64)
+    p = h.SvmPredictor(roll_files["synth"], min_dims=width + nnz_per_row)
+    try:
+        lab, dec = p.predict((rp, idx.reshape(-1).astype(np.int32), val.reshape(-1)))
+        assert p.timing().n_chunks == 2
+        sel = np.concatenate([np.arange(0, 700), np.arange(n - 900, n), rng.integers(0, n, 500)])
+        rp2 = np.arange(0, (len(sel) + 1) * nnz_per_row, nnz_per_row, dtype=np.int64)
+        lab2, dec2 = p.predict((rp2, idx[sel].reshape(-1).astype(np.int32), val[sel].reshape(-1)))
+        assert np.array_equal(lab[sel], lab2)
+        assert np.abs(dec[sel] - dec2).max() <= 1e-9
+        assert (dec[sel] == dec2).mean() >= 0.99
+    finally:
+        p.close()
+
+
+@pytest.mark.gpu
 def test_haf_scale_abi_matches_numpy_restatement(roll_files):
     """haf_scale_minmax / haf_scale_apply against a direct numpy restatement of svm-scale.c:165-198 and :333-353."""
     import haf_grasping_b200 as h
