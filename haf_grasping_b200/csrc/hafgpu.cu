@@ -842,6 +842,16 @@ static int svm_stage(haf_ctx* ctx, unsigned* cnt, size_t Wcap, size_t ldx, int G
             const int pairs_cap = (mt_cap + 1) / 2;
             int nsplit2 = 1;
             if (pairs_cap < ctx->sm_count / 2) nsplit2 = std::min(n_ntiles, (ctx->sm_count + pairs_cap - 1) / pairs_cap);
+            else {   // mid-sized launches (the chunks of a host-staged batch): split the SV tiles of an item when that fills the last round better
+                const double clusters = ctx->sm_count / 2;
+                double best_eff = 0.0;
+                for (int ns = 1; ns <= n_ntiles && ns <= 8; ns *= 2) {
+                    if (n_ntiles % ns) continue;
+                    const double rounds = (double)pairs_cap * ns / clusters;
+                    const double eff = rounds / std::ceil(rounds);
+                    if (eff > best_eff + 0.02) { best_eff = eff; nsplit2 = ns; }
+                }
+            }
             int grid2 = (int)std::min<long long>((long long)pairs_cap * nsplit2 * 2, ctx->sm_count);
             grid2 &= ~1;  // whole clusters
             haftc::svm_rbf_tc2_kernel<<<grid2, haftc::THREADS, haftc::SMEM2_BYTES + tab_bytes, st>>>(tmXh, tmXl, ctx->tmSh2, ctx->tmSl2, ctx->d_xn.p, ctx->d_svtab.p,

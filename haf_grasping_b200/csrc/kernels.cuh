@@ -583,14 +583,18 @@ __device__ __forceinline__ float fast_tier_value(PtrT I, int idx0, const FastTab
 }
 
 // Tensor-core variant: per-dimension values split into two fp16 terms and written K-major ([window][Krow], what the
-// UMMA K-major operand / TMA box wants).  A (32*WT)-window x Krow/2 tile is staged in shared memory so the global
-// writes are row-contiguous; the squared norm of the (hi + lo) representation is reduced on the way.
+// UMMA K-major operand / TMA box wants).  Lane = window (WT = 2 windows per lane), warp = one dimension at a time; a
+// 64-window x 96-dimension tile of (hi | lo << 16) words is staged in shared memory so that the global writes are whole
+// 32-byte sectors of the operand rows; the squared norm of the (hi + lo) representation is accumulated on the way.
+// The kernel is bound by the LSU data pipe and the issue rate together ("The feature kernel"): hence the
+// bank-conflict-free staging of the image rows, the per-pass copy of the table records and the power-of-ten tables in
+// shared memory, and the warp-uniform branches around the third region and the SHAF rule.
 //
 // FAST TIER.  The values written here are rounded to 22 significant bits (fp16 hi + lo) anyway and every window whose
-// decision value lands inside the guard band is re-evaluated by svm_exact_kernel with the bit-exact emulation, so this
-// tier reproduces the text round trips only to ~1e-7 (see fast_tier_value); the 6-digit "%g" rounding (<= 5e-7
-// relative: now the largest input error of this tier, see tools/dec_error_probe.py) is skipped.  Raw feature values are the same bit-exact floats as
-// everywhere else.  Each lane handles WT windows per table record, so the six 128-bit table loads are amortised.
+// decision value lands inside the guard band is re-evaluated from the bit-exact emulation (guard_inputs_kernel /
+// svm_exact_terms_kernel), so this tier reproduces the text round trips only to ~1e-7 (see fast_tier_value); the
+// 6-digit "%g" rounding (<= 5e-6 relative: the largest input error of this tier, tools/dec_error_probe.py) is skipped.
+// Raw feature values are the same bit-exact floats as everywhere else.
 // (Tables in __constant__ memory were tried and were 1.8x SLOWER: 36 KB of tables thrash the constant cache.)
 #define HAF_FT_WT 2
 #define HAF_FT_KPASS 96   // dimensions per pass of the shared-memory tile: 192 B = 6 whole sectors of a row of Xh / Xl
@@ -1150,10 +1154,23 @@ __global__ void __launch_bounds__(256) guard_fma_kernel(const ExactArgs A, const
 #pragma unroll
             for (int k = 0; k < SVT; k++) acc[b][k] = 0.0;
         const int ia = i0 + threadIdx.x;
+        // the SV matrix (L2-resident) is read two dimensions ahead: with one 176-register CTA per SM there are only
+        // 8 warps to hide an L2 round trip behind 32 DFMAs each (ncu: long-scoreboard stalls dominated)
+        double svn1[SVT], svn2[SVT];
+#pragma unroll
+        for (int k = 0; k < SVT; k++) {
+            const bool in = ia + 256 * k < Spad;
+            svn1[k] = in ? A.sv64T[ia + 256 * k] : 0.0;
+            svn2[k] = (in && Dsv > 1) ? A.sv64T[(size_t)Spad + ia + 256 * k] : 0.0;
+        }
         for (int d = 0; d < Dsv; d++) {
             double sv[SVT];
 #pragma unroll
-            for (int k = 0; k < SVT; k++) sv[k] = (ia + 256 * k < Spad) ? A.sv64T[(size_t)d * Spad + ia + 256 * k] : 0.0;
+            for (int k = 0; k < SVT; k++) {
+                sv[k] = svn1[k];
+                svn1[k] = svn2[k];
+                svn2[k] = (d + 2 < Dsv && ia + 256 * k < Spad) ? A.sv64T[(size_t)(d + 2) * Spad + ia + 256 * k] : 0.0;
+            }
             const double2* xr = reinterpret_cast<const double2*>(xs + d * WB);
 #pragma unroll
             for (int b2 = 0; b2 < WB / 2; b2++) {
