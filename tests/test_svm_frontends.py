@@ -63,13 +63,63 @@ def test_front_ends_fail_loudly_without_a_gpu(tools, tmp_models, tmp_path):
     assert e.value.code == -4
 
 
-# ---------------------------------------------------------------- GPU: byte-exact against the reference's programs
 def _ref_bins(oracle_lib):
     if not oracle_lib.ref_available():
         pytest.skip("oracle/_ref (the reference's libsvm programs compiled in place) is not on this box")
     return os.path.join(oracle_lib.REF_DIR, "svm-scale"), os.path.join(oracle_lib.REF_DIR, "svm-predict")
 
 
+# ---------------------------------------------------------------- committed golden outputs of the reference's programs
+GOLDEN_CLI = os.path.join(ROOT, "tests", "golden", "svm_cli")
+
+
+def _golden_models(tmp_path, tmp_models):
+    import gzip
+    from conftest import GOLDEN
+    trained = str(tmp_path / "trained.model")
+    with gzip.open(os.path.join(GOLDEN, "substitute_trained.model.gz"), "rb") as src, open(trained, "wb") as dst:
+        dst.write(src.read())
+    return {"trained": trained, "synth": tmp_models(256)}
+
+
+def test_golden_cli_fixtures_are_what_the_reference_programs_print(oracle_lib, tmp_path, tmp_models):
+    """Pins tests/golden/svm_cli (made by tests/golden/make_svm_cli_golden.py) against oracle/_ref where that exists."""
+    import json
+    ref_scale, ref_predict = _ref_bins(oracle_lib)
+    g = lambda n: os.path.join(GOLDEN_CLI, n)  # noqa: E731
+    r = subprocess.run([ref_scale, "-r", RANGE, g("features.txt")], capture_output=True, check=True)
+    assert r.stdout == open(g("scaled_ref.txt"), "rb").read()
+    for k, args in enumerate(json.load(open(g("manifest.json")))["fit_args"]):
+        r = subprocess.run([ref_scale] + args + ["-s", str(tmp_path / "r.range"), g("sparse.txt")], capture_output=True, check=True)
+        assert r.stdout == open(g("fit_%d_ref.txt" % k), "rb").read() and r.stderr == open(g("fit_%d_ref.stderr" % k), "rb").read()
+        assert open(tmp_path / "r.range", "rb").read() == open(g("fit_%d_ref.range" % k), "rb").read()
+    for name, model in _golden_models(tmp_path, tmp_models).items():
+        r = subprocess.run([ref_predict, g("scaled_ref.txt"), model, str(tmp_path / "o.txt")], capture_output=True, check=True)
+        assert open(tmp_path / "o.txt", "rb").read() == open(g("out_%s_ref.txt" % name), "rb").read()
+        assert r.stdout == open(g("out_%s_ref.stdout" % name), "rb").read()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("svm_mode", [0, 1, 2])
+def test_front_ends_reproduce_the_committed_reference_outputs(tools, tmp_path, tmp_models, svm_mode):
+    """The same comparison as the tests below, against the committed outputs of the reference programs: runs on a box
+    that has neither /root/reference nor oracle/_ref."""
+    import json
+    g = lambda n: os.path.join(GOLDEN_CLI, n)  # noqa: E731
+    r = subprocess.run([tools[1], "-r", RANGE, g("features.txt")], capture_output=True, check=True)
+    assert r.stdout == open(g("scaled_ref.txt"), "rb").read()
+    if svm_mode == 0:
+        for k, args in enumerate(json.load(open(g("manifest.json")))["fit_args"]):
+            r = subprocess.run([tools[1]] + args + ["-s", str(tmp_path / "r.range"), g("sparse.txt")], capture_output=True, check=True)
+            assert r.stdout == open(g("fit_%d_ref.txt" % k), "rb").read() and r.stderr == open(g("fit_%d_ref.stderr" % k), "rb").read()
+            assert open(tmp_path / "r.range", "rb").read() == open(g("fit_%d_ref.range" % k), "rb").read()
+    for name, model in _golden_models(tmp_path, tmp_models).items():
+        r = subprocess.run([tools[0], "--svm-mode", str(svm_mode), g("scaled_ref.txt"), model, str(tmp_path / "o.txt")], capture_output=True, check=True)
+        assert open(tmp_path / "o.txt", "rb").read() == open(g("out_%s_ref.txt" % name), "rb").read()
+        assert r.stdout == open(g("out_%s_ref.stdout" % name), "rb").read()
+
+
+# ---------------------------------------------------------------- GPU: byte-exact against the reference's programs
 @pytest.fixture(scope="module")
 def roll_files(oracle_lib, tmp_path_factory, tmp_models):
     """/tmp/features.txt of one roll of pcd2 written by the reference's own feature class, plus the reference programs'
