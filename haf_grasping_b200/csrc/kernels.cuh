@@ -614,7 +614,7 @@ __global__ void __launch_bounds__(256, 4) features_tc_kernel(const float* __rest
     constexpr int rs = HAF_FT_KPASS + 1;
     float* s_int = reinterpret_cast<float*>(s_words + NW * rs);  // [HAF_FT_ROWS][ld .. ld + 31]
     uint4* s_tab = reinterpret_cast<uint4*>(s_words + ((NW * rs + HAF_FT_ROWS * (ld + 31) + 3) & ~3));  // [KPASS] DimFeat records of the pass
-    __shared__ int s_box[7];       // unit A, its first row, rows (0 = no staging), row stride of the staged image; unit B, first row, rows
+    __shared__ int s_box[9];       // unit A, its first row, rows (0 = no staging), row stride of the staged image; unit B, first row, rows
     __shared__ Round4Tab s_rt;
     int unit[WT], row[WT], col[WT];
     bool valid[WT];
@@ -642,10 +642,11 @@ __global__ void __launch_bounds__(256, 4) features_tc_kernel(const float* __rest
             if (vm) uB = __shfl_sync(0xffffffffu, unit[t], 31 - __clz(vm));
         }
         bool two = true;
-        int rminA = 0x7fffffff, rmaxA = -1, rminB = 0x7fffffff, rmaxB = -1;
+        int rminA = 0x7fffffff, rmaxA = -1, rminB = 0x7fffffff, rmaxB = -1, cmin = 0x7fffffff, cmax = -1;
 #pragma unroll
         for (int t = 0; t < WT; t++) {
             two = two && (!valid[t] || unit[t] == uA || unit[t] == uB);
+            if (valid[t]) { cmin = min(cmin, col[t]); cmax = max(cmax, col[t]); }
             if (valid[t] && unit[t] == uA) { rminA = min(rminA, row[t]); rmaxA = max(rmaxA, row[t]); }
             else if (valid[t]) { rminB = min(rminB, row[t]); rmaxB = max(rmaxB, row[t]); }
         }
@@ -656,6 +657,8 @@ __global__ void __launch_bounds__(256, 4) features_tc_kernel(const float* __rest
             rmaxA = max(rmaxA, __shfl_xor_sync(0xffffffffu, rmaxA, o));
             rminB = min(rminB, __shfl_xor_sync(0xffffffffu, rminB, o));
             rmaxB = max(rmaxB, __shfl_xor_sync(0xffffffffu, rmaxB, o));
+            cmin = min(cmin, __shfl_xor_sync(0xffffffffu, cmin, o));
+            cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
         }
         // BANK-CONFLICT-FREE STAGING.  Lanes are consecutive windows of the compact list: a warp-load touches columns
         // a..b of one image row and a'..b' of the next.  With the natural row stride G + 1 the two runs overlap in banks
@@ -680,6 +683,7 @@ __global__ void __launch_bounds__(256, 4) features_tc_kernel(const float* __rest
             s_box[0] = uA; s_box[1] = rminA - 7; s_box[2] = ok ? nA : 0;
             s_box[3] = ld + (((o - ld) % 32) + 32) % 32;
             s_box[4] = uB; s_box[5] = rminB - 7; s_box[6] = ok ? nB : 0;
+            s_box[7] = cmin - 7; s_box[8] = cmax - cmin + 15;   // columns the patches touch: only these are copied
         }
     }
     for (int t = threadIdx.x; t < (int)(sizeof(Round4Tab) / 8); t += blockDim.x)
@@ -702,9 +706,12 @@ __global__ void __launch_bounds__(256, 4) features_tc_kernel(const float* __rest
         const int nB = s_box[6];
         const float* srcA = integral + (size_t)(s_box[0] - unit_base) * ld * ld + (size_t)s_box[1] * ld;
         const float* srcB = integral + (size_t)(s_box[4] - unit_base) * ld * ld + (size_t)s_box[5] * ld - (size_t)nrows * ld;
-        for (int t = threadIdx.x; t < (nrows + nB) * ld; t += blockDim.x) {
-            const int r = t / ld, c = t - r * ld;
-            s_int[r * sst + c] = (r < nrows ? srcA : srcB)[t];
+        // only the columns the CTA's patches touch (all of them at G = 56, a sixth of the row at G = 512); the staged image
+        // keeps the full-width addressing the offset tables are built for
+        const int c0 = s_box[7], wd = s_box[8];
+        for (int t = threadIdx.x; t < (nrows + nB) * wd; t += blockDim.x) {
+            const int r = t / wd, c = c0 + (t - r * wd);
+            s_int[r * sst + c] = (r < nrows ? srcA : srcB)[r * ld + c];
         }
 #pragma unroll
         for (int t = 0; t < WT; t++) {   // padding lanes read row 0 harmlessly
