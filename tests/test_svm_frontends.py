@@ -39,6 +39,40 @@ def test_predict_reader_follows_svm_predicts_tokenisation(tools, tmp_path):
         assert out[7] == ("3" if bad.startswith("1 1:1\n\n") else "2"), (bad, out)
 
 
+def test_predict_reader_accepts_and_rejects_exactly_what_the_reference_program_does(tools, oracle_lib, tmp_models, tmp_path):
+    """Fuzz: mutated rows go through the reference's own svm-predict (oracle/_ref, runs on the CPU) and through the B200
+    front end's reader (--parse-only); the first rejected line ("Wrong input format at line N") must be the same."""
+    _, ref_predict = _ref_bins(oracle_lib)
+    rng = np.random.default_rng(2024)
+    good = "1 1:0.5 2:-0.25 7:1e-3 12:3 40:-7.5e2 323:0.125"
+    snippets = [";", ":", "::", " ", "  ", "\t", "x", "-", "+", "e", "E5", "nan", "inf", "-inf", "0x1p-3", "1e-400", "1e400", ".", "5.", "+.5",
+                "99999999999999999999", "-3", "0", "7", "12:", ":3", "1 :2", "3: 4", "#", ",", "\r", "1e", "--1", "1:2:3", "٣"]
+    model = tmp_models(256)
+    checked = rejected = 0
+    for trial in range(120):
+        lines = []
+        for k in range(4):
+            ln = good
+            if rng.random() < 0.22:
+                for _ in range(int(rng.integers(1, 3))):
+                    pos = int(rng.integers(0, len(ln) + 1))
+                    snip = snippets[int(rng.integers(0, len(snippets)))]
+                    ln = ln[:pos] + snip + ln[pos + (int(rng.integers(0, 3)) if rng.random() < 0.5 else 0):]
+            lines.append(ln)
+        src = tmp_path / ("fuzz_%d.txt" % trial)
+        src.write_bytes(("\n".join(lines) + "\n").encode("utf-8"))
+        a = subprocess.run([ref_predict, str(src), model, str(tmp_path / "ref.out")], capture_output=True)
+        want = 0
+        if a.returncode != 0:
+            assert a.stderr.startswith(b"Wrong input format at line "), a.stderr
+            want = int(a.stderr.split()[-1])
+        out = subprocess.run([tools[0], "--parse-only", str(src)], capture_output=True, text=True, check=True).stdout.split()
+        assert int(out[7]) == want, (trial, lines, a.stderr, out)
+        checked += 1
+        rejected += want > 0
+    assert checked == 120 and 15 < rejected < 105     # the fuzz exercises both outcomes
+
+
 def test_scale_reader_follows_svm_scales_sscanf_pairs(tools, tmp_path):
     f = tmp_path / "rows.txt"
     f.write_text("-1 1:0.5 2:3 10:1e-3\n+1  4: 2.5 junk 6:1\n3\n")   # "%d:%lf" skips blanks before the value; a row ends at junk
