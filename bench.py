@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--clouds", type=int, default=512, help="clouds per GPU (batch workload)")
     ap.add_argument("--points", type=int, default=100000)
     ap.add_argument("--nsv", type=int, default=2048)
+    ap.add_argument("--tc-passes", type=int, default=0, help="tensor-core products per k-slice: 0 = calibrated per model (default), 1 / 2 / 3 forced")
     ap.add_argument("--sv-table-global", type=int, default=0, help="experiment: 1 = tensor kernels read the SV table from global memory")
     ap.add_argument("--svm-mode", type=int, default=0, help="0 tcgen05 split-fp16 + FP64 guard (default), 1 FP64 exact, 2 FP32 SIMT + guard")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -388,7 +389,7 @@ def run_ours(args):
     n_clouds = len(clouds)
 
     gs = h.GraspSearch(FEATURES, RANGE, model, grid=wc["grid"], roll_step_deg=wc["step"], roll_max_deg=wc["rmax"],
-                       device=local, svm_mode=args.svm_mode, sv_table_global=args.sv_table_global)
+                       device=local, svm_mode=args.svm_mode, sv_table_global=args.sv_table_global, tc_passes=args.tc_passes)
     stream = torch.cuda.current_stream()
     gs.set_stream(stream.cuda_stream)
     gs.set_profiling(True)
@@ -473,8 +474,8 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": DTYPES[args.svm_mode], "data": "synthetic",
-            "config": {"workload": describe(args, wc), "n_sv": info.n_sv, "n_dims": info.n_dims, "grid": info.grid,
+            "dtype": DTYPES[args.svm_mode].replace("x3", "x%d" % info.reserved[0]) if args.svm_mode == 0 else DTYPES[args.svm_mode], "data": "synthetic",
+            "config": {"workload": describe(args, wc), "tensor_passes": int(info.reserved[0]), "guard_rel": info.reserved[1] * 1e-9, "n_sv": info.n_sv, "n_dims": info.n_dims, "grid": info.grid,
                        "rolls": info.n_rolls, "clouds_per_gpu": n_clouds, "windows_per_step_per_gpu": W_step,
                        "svm_mode": args.svm_mode, "l2": "inputs (%.0f MB per GPU per step) larger than L2, no flush" % (total_pts * 12 / 1e6),
                        "sharding": "clouds by rank, no data-path collective; NCCL all_gather of best-grasp records"},
@@ -493,8 +494,8 @@ def run_ours(args):
                          "algorithmic": "W*S*(2D+4) flop per launch, W=%.0f S=%d D=%d" % (acc["windows"] / max(svm_launches, 1), info.n_sv, info.n_dims),
                          "kernel_ms": svm_ms, "share_of_step": acc["svm"] / ms_dev if ms_dev else None,
                          "note": {2: "FP32 SIMT contraction (CUDA cores), measured against the bf16 tensor peak for comparability",
-                                  1: "FP64 exact-order path", 0: "algorithmic flops; the split-fp16 scheme issues 3 tensor-core MMAs per algorithmic MMA, "
-                                  "executed tensor flops = 3 x (Krow/D) x algorithmic (ncu: tensor pipe 98.6 % active, profiles/r1_s2_full.md)"}[args.svm_mode]},
+                                  1: "FP64 exact-order path", 0: "algorithmic flops; the split-fp16 scheme issues %d tensor-core MMA(s) per algorithmic MMA (calibrated per model: "
+                                  "config.tensor_passes), executed tensor flops = passes x (Krow/D) x algorithmic (3 passes: ncu tensor pipe 98.6 %% active, profiles/r1_s2_full.md)" % info.reserved[0]}[args.svm_mode]},
             "stage_ms_per_step": {k: acc[k] / args.steps for k in ("bin", "integral", "mask", "features", "svm", "guard", "score")},
             "stage_roofline": stage_roofline(acc, args.steps, total_pts, n_clouds * info.n_rolls, info.grid, info.n_dims, W_step, hbm),
             "guard_windows_per_step": acc["guardw"] / args.steps,

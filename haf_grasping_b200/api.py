@@ -152,7 +152,7 @@ class GraspSearch:
 
     def __init__(self, features_path, range_path, model_path, grid=56, roll_step_deg=15, roll_max_deg=190,
                  nr_features_without_shaf=302, device=0, emulate_text_roundtrip=True, svm_mode=HAF_SVM_TENSOR_GUARD,
-                 guard_rel=0.0, tc_variant=0, guard_tier2=0, sv_table_global=0):
+                 guard_rel=0.0, tc_variant=0, guard_tier2=0, sv_table_global=0, tc_passes=0):
         self.L = load_library()
         cfg = haf_config()
         self._keep = [features_path.encode(), range_path.encode(), model_path.encode()]
@@ -163,7 +163,7 @@ class GraspSearch:
         cfg.emulate_text_roundtrip = int(bool(emulate_text_roundtrip))
         cfg.svm_mode = svm_mode
         cfg.guard_rel = guard_rel
-        cfg.reserved[0] = tc_variant
+        cfg.reserved[0] = tc_variant | (tc_passes << 4)   # tc_passes: 0 = calibrated per model, 1-3 forced
         cfg.reserved[2] = guard_tier2   # 0 on, 1 off, 2 on + escalate everything (tests)
         cfg.reserved[3] = sv_table_global   # 1: SV table read from global memory (the > 4096-SV path)
         self.h = C.c_void_p()

@@ -103,6 +103,8 @@ struct haf_ctx {
     CUtensorMap tmSh, tmSl;     // 256-row boxes (single-CTA kernel)
     CUtensorMap tmSh2, tmSl2;   // 128-row boxes (CTA-pair kernel)
     int tc_variant = 0;         // 0: CTA-pair kernel (cta_group::2), 1: single-CTA kernel
+    int tc_passes = 3;          // tensor-core products per k-slice: 3, 2 or 1 (calibrate_tensor_passes)
+    double tc_operand_err = 0;  // calibrated operand error of the chosen scheme, as a fraction of the guard scale E
 
     // per-call state
     DevBuf<unsigned char> d_xyz;       // staging for host clouds
@@ -211,6 +213,47 @@ static haf_encode_tiled_fn get_encode_tiled() {
             cudaGetLastError();
     }
     return fn;
+}
+// How many of the three split products does this model need?  The operand error of the cheaper schemes -- 2 passes:
+// x rounded to fp16, sv kept as a pair; 1 pass: both rounded to fp16 -- scales with gamma and is measured here in the
+// unit the guard band uses (E = sum_i |coef_i| K_i (1 + gamma log2e (|x|^2 + |sv_i|^2)) + |rho|), with up to 48 of the
+// model's own support vectors standing in for the windows (they ARE scaled feature vectors of training windows).
+// rel[p] = max over probes of |dec_p - dec| / E.  The caller accepts the cheapest scheme whose error, together with the
+// measured FP32 epilogue error (2.5e-7 E), keeps the default 15x margin inside a guard band of at most 1.2e-5.
+static void calibrate_tensor_passes(const hafhost::Model& model, int Dsv, double rel[4]) {
+    const int S = model.l;
+    std::vector<double> sv((size_t)S * Dsv, 0.0), sh((size_t)S * Dsv, 0.0), sn(S, 0.0);
+    for (int i = 0; i < S; i++)
+        for (size_t e = 0; e < model.sv[i].size(); e++) {
+            const int d = model.sv[i][e].first - 1;
+            const double v = model.sv[i][e].second;
+            sv[(size_t)i * Dsv + d] = v;
+            sh[(size_t)i * Dsv + d] = (double)h16f(f2h16((float)v));
+            sn[i] += v * v;
+        }
+    rel[1] = rel[2] = rel[3] = 0.0;
+    const int nprobe = std::min(S, 48);
+    const double g2 = model.gamma * 1.4426950408889634;
+    for (int k = 0; k < nprobe; k++) {
+        const int j = (int)((long long)k * S / nprobe);
+        const double* x = &sv[(size_t)j * Dsv];
+        const double* xh = &sh[(size_t)j * Dsv];
+        double dec = 0, dec1 = 0, dec2 = 0, E = fabs(model.rho);
+        for (int i = 0; i < S; i++) {
+            const double* s = &sv[(size_t)i * Dsv];
+            const double* s16 = &sh[(size_t)i * Dsv];
+            double dot = 0, dot1 = 0, dot2 = 0;   // exact, x_hi.sv_hi, x_hi.sv
+            for (int d = 0; d < Dsv; d++) { dot += x[d] * s[d]; dot1 += xh[d] * s16[d]; dot2 += xh[d] * s[d]; }
+            const double base = sn[j] + sn[i];
+            const double K = exp(-model.gamma * std::max(base - 2.0 * dot, 0.0));
+            dec += model.coef[i] * K;
+            dec1 += model.coef[i] * exp(-model.gamma * std::max(base - 2.0 * dot1, 0.0));
+            dec2 += model.coef[i] * exp(-model.gamma * std::max(base - 2.0 * dot2, 0.0));
+            E += fabs(model.coef[i]) * K * (1.0 + g2 * base);
+        }
+        rel[1] = std::max(rel[1], fabs(dec1 - dec) / E);
+        rel[2] = std::max(rel[2], fabs(dec2 - dec) / E);
+    }
 }
 // "%.4g" tables of the fast feature tier (kernels.cuh, Round4Tab): powers of ten 10^(i-48)
 static void make_round4_table(Round4Tab& tab) {
@@ -447,7 +490,19 @@ static int create_impl(haf_ctx** out, const haf_config* cfg, bool svm_only, int 
         CREATE_TRY(cudaMemcpy(ctx->d_SVh.p, svh.data(), svh.size() * 2, cudaMemcpyHostToDevice));
         CREATE_TRY(cudaMemcpy(ctx->d_SVl.p, svl.data(), svl.size() * 2, cudaMemcpyHostToDevice));
         CREATE_TRY(cudaMemcpy(ctx->d_svtab.p, tab.data(), SpadT * sizeof(float2), cudaMemcpyHostToDevice));
-        ctx->tc_variant = cfg->reserved[0];
+        ctx->tc_variant = cfg->reserved[0] & 1;
+        {   // number of tensor-core products per k-slice: forced by cfg.reserved[0] bits 4-5, else calibrated per model
+            const int forced = (cfg->reserved[0] >> 4) & 3;
+            double rel[4] = {0, 0, 0, 0};
+            if (!forced || cfg->guard_rel <= 0) calibrate_tensor_passes(model, Dsv, rel);
+            int passes = 3;
+            if (forced) passes = forced;
+            else if (rel[1] <= 5.5e-7) passes = 1;
+            else if (rel[2] <= 5.5e-7) passes = 2;
+            ctx->tc_passes = passes;
+            ctx->tc_operand_err = passes < 3 ? rel[passes] : 0.0;
+            if (cfg->guard_rel <= 0) ctx->guard_rel = std::max(4e-6f, (float)(15.0 * (ctx->tc_operand_err + 2.5e-7)));
+        }
         if (!make_tensor_map(&ctx->tmSh, ctx->d_SVh.p, Krow, SpadT, haftc::BN) || !make_tensor_map(&ctx->tmSl, ctx->d_SVl.p, Krow, SpadT, haftc::BN) ||
             !make_tensor_map(&ctx->tmSh2, ctx->d_SVh.p, Krow, SpadT, haftc::BN / 2) || !make_tensor_map(&ctx->tmSl2, ctx->d_SVl.p, Krow, SpadT, haftc::BN / 2)) {
             haf_destroy(ctx);
@@ -712,6 +767,8 @@ extern "C" int haf_get_info(const haf_ctx* ctx, haf_info* info) {
     info->n_features = ctx->F; info->n_dims = ctx->D; info->n_sv = ctx->S; info->n_rolls = ctx->R; info->grid = ctx->G;
     info->label0 = ctx->label[0]; info->label1 = ctx->label[1]; info->sm_count = ctx->sm_count;
     info->gamma = ctx->gamma; info->rho = ctx->rho;
+    info->reserved[0] = ctx->cfg.svm_mode == HAF_SVM_TENSOR_GUARD ? ctx->tc_passes : 0;   // tensor-core products per k-slice
+    info->reserved[1] = (int)lrint(ctx->guard_rel * 1e9);                                  // guard_rel in units of 1e-9
     return HAF_OK;
 }
 extern "C" int haf_set_stream(haf_ctx* ctx, void* s) { if (!ctx) return HAF_ERR_ARG; ctx->stream = (cudaStream_t)s; return HAF_OK; }
@@ -856,11 +913,11 @@ static int svm_stage(haf_ctx* ctx, unsigned* cnt, size_t Wcap, size_t ldx, int G
             grid2 &= ~1;  // whole clusters
             haftc::svm_rbf_tc2_kernel<<<grid2, haftc::THREADS, haftc::SMEM2_BYTES + tab_bytes, st>>>(tmXh, tmXl, ctx->tmSh2, ctx->tmSl2, ctx->d_xn.p, ctx->d_svtab.p,
                                                                                          ctx->c_log2, cnt + 0, n_ntiles, nsplit2, kblocks, last_slices,
-                                                                                         ctx->d_dec.p, ctx->d_asum.p, tab_smem, ctx->csvn_max);
+                                                                                         ctx->d_dec.p, ctx->d_asum.p, tab_smem, ctx->csvn_max, ctx->tc_passes);
         } else {
             const int grid = (int)std::min<long long>((long long)mt_cap * nsplit, ctx->sm_count);
             haftc::svm_rbf_tc_kernel<<<grid, haftc::THREADS, haftc::SMEM_BYTES + tab_bytes, st>>>(tmXh, tmXl, ctx->tmSh, ctx->tmSl, ctx->d_xn.p, ctx->d_svtab.p, ctx->c_log2,
-                                                                                      cnt + 0, n_ntiles, nsplit, kblocks, last_slices, ctx->d_dec.p, ctx->d_asum.p, tab_smem, ctx->csvn_max);
+                                                                                      cnt + 0, n_ntiles, nsplit, kblocks, last_slices, ctx->d_dec.p, ctx->d_asum.p, tab_smem, ctx->csvn_max, ctx->tc_passes);
         }
         LAUNCHED(ctx);
         haftc::svm_finalize_kernel<<<(unsigned)((Wcap + 255) / 256), 256, 0, st>>>(ctx->d_dec.p, ctx->d_asum.p, ctx->d_xn.p, cnt + 0, ctx->rho, ctx->guard_rel,

@@ -4,9 +4,15 @@
 //
 // x and sv are split into two fp16 terms (x = x_hi + x_lo, 22 significant bits together, absolute floor 2^-25);
 // the contraction is three tensor-core products accumulated in FP32 in TMEM:  x_hi.sv_hi + x_hi.sv_lo + x_lo.sv_hi
-// (the dropped x_lo.sv_lo term is ~2^-24 relative).  Round 1 used bf16 pairs (16 bits): same cost, 30x the error.  The error of the resulting decision value is measured in the tests and is
-// far inside the guard band; windows inside the band are re-evaluated in FP64 by svm_exact_kernel, so labels equal
-// the reference's (svm.cpp:2459-2533).
+// (the dropped x_lo.sv_lo term is ~2^-24 relative).  Round 1 used bf16 pairs (16 bits): same cost, 30x the error.
+//
+// PASSES.  The error of a term is K_i times gamma times the error of the dot product, so for a model with a small
+// gamma (libsvm's default 1 / n_features) the cross terms change the decision value by less than the FP32 epilogue
+// does.  `passes` = 3 (all three products), 2 (x_hi.(sv_hi + sv_lo): x rounded to fp16) or 1 (x_hi.sv_hi only) is chosen
+// per model at haf_create from a calibration of each scheme's operand error against the guard scale (hafgpu.cu,
+// calibrate_tensor_passes); the guard band is widened by the calibrated error.  The error of the resulting decision value
+// is measured in the tests and is far inside the guard band; windows inside the band are re-evaluated in FP64 (FMA tier,
+// then libsvm's own order), so labels equal the reference's (svm.cpp:2459-2533).
 //
 // Kernel structure (one persistent CTA per SM, 192 threads, warp specialised):
 //   warp 0   TMA producer : cp.async.bulk.tensor 2D loads of the four operand tiles of a k-block into a
@@ -143,7 +149,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 svm_rbf_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl,
                   const __grid_constant__ CUtensorMap tmSh, const __grid_constant__ CUtensorMap tmSl,
                   const float* __restrict__ xn, const float2* __restrict__ svtab, float c, const unsigned* __restrict__ win_count,
-                  int n_ntiles, int nsplit, int kblocks, int last_slices, double* __restrict__ dec_acc, float* __restrict__ asum_acc, int tab_smem, float csvn_max) {
+                  int n_ntiles, int nsplit, int kblocks, int last_slices, double* __restrict__ dec_acc, float* __restrict__ asum_acc, int tab_smem, float csvn_max, int passes) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // 128B swizzle needs 1024-byte aligned tiles
     const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
@@ -191,11 +197,12 @@ svm_rbf_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constan
                         const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
                         mbar_wait(bar_empty + 8 * s, ph ^ 1u);
                         const uint32_t st = smem_base + s * STAGE_BYTES;
-                        mbar_expect_tx(bar_full + 8 * s, STAGE_BYTES);
+                        // only the operand tiles the chosen number of passes reads are fetched
+                        mbar_expect_tx(bar_full + 8 * s, A_TILE_BYTES + B_TILE_BYTES + (passes >= 2 ? B_TILE_BYTES : 0) + (passes >= 3 ? A_TILE_BYTES : 0));
                         tma_load_2d(st, &tmXh, kb * BK, mt * BM, bar_full + 8 * s);
-                        tma_load_2d(st + A_TILE_BYTES, &tmXl, kb * BK, mt * BM, bar_full + 8 * s);
+                        if (passes >= 3) tma_load_2d(st + A_TILE_BYTES, &tmXl, kb * BK, mt * BM, bar_full + 8 * s);
                         tma_load_2d(st + 2 * A_TILE_BYTES, &tmSh, kb * BK, nt * BN, bar_full + 8 * s);
-                        tma_load_2d(st + 2 * A_TILE_BYTES + B_TILE_BYTES, &tmSl, kb * BK, nt * BN, bar_full + 8 * s);
+                        if (passes >= 2) tma_load_2d(st + 2 * A_TILE_BYTES + B_TILE_BYTES, &tmSl, kb * BK, nt * BN, bar_full + 8 * s);
                     }
             }
         }
@@ -221,8 +228,8 @@ svm_rbf_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constan
                         for (int k = 0; k < slices; k++) {
                             const uint64_t adv = (uint64_t)(k * 2);  // 16 fp16 = 32 bytes = 2 x 16-byte units
                             tc_mma(tmem_d, d_ah + adv, d_bh + adv, IDESC, (kb | k) ? 1u : 0u);
-                            tc_mma(tmem_d, d_ah + adv, d_bl + adv, IDESC, 1u);
-                            tc_mma(tmem_d, d_al + adv, d_bh + adv, IDESC, 1u);
+                            if (passes >= 2) tc_mma(tmem_d, d_ah + adv, d_bl + adv, IDESC, 1u);
+                            if (passes >= 3) tc_mma(tmem_d, d_al + adv, d_bh + adv, IDESC, 1u);
                         }
                         tc_commit(bar_empty + 8 * s);  // smem stage free once these MMAs have read it
                     }
@@ -343,7 +350,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 svm_rbf_tc2_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl,
                    const __grid_constant__ CUtensorMap tmSh2, const __grid_constant__ CUtensorMap tmSl2,
                    const float* __restrict__ xn, const float2* __restrict__ svtab, float c, const unsigned* __restrict__ win_count,
-                   int n_ntiles, int nsplit, int kblocks, int last_slices, double* __restrict__ dec_acc, float* __restrict__ asum_acc, int tab_smem, float csvn_max) {
+                   int n_ntiles, int nsplit, int kblocks, int last_slices, double* __restrict__ dec_acc, float* __restrict__ asum_acc, int tab_smem, float csvn_max, int passes) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + STAGES2 * STAGE2_BYTES;
@@ -396,11 +403,12 @@ svm_rbf_tc2_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_consta
                         mbar_wait(bar_empty + 8 * s, ph ^ 1u);
                         const uint32_t st = smem_base + s * STAGE2_BYTES;
                         const uint32_t lfull = (bar_full + 8 * s) & PEER_MASK;  // the LEADER's full barrier
-                        if (leader) mbar_expect_tx(bar_full + 8 * s, 2 * STAGE2_BYTES);
+                        // only the operand tiles the chosen number of passes reads are fetched
+                        if (leader) mbar_expect_tx(bar_full + 8 * s, 2 * (A_TILE_BYTES + B2_TILE_BYTES + (passes >= 2 ? B2_TILE_BYTES : 0) + (passes >= 3 ? A_TILE_BYTES : 0)));
                         tma_load_2d_2sm(st, &tmXh, kb * BK, mrow, lfull);
-                        tma_load_2d_2sm(st + A_TILE_BYTES, &tmXl, kb * BK, mrow, lfull);
+                        if (passes >= 3) tma_load_2d_2sm(st + A_TILE_BYTES, &tmXl, kb * BK, mrow, lfull);
                         tma_load_2d_2sm(st + 2 * A_TILE_BYTES, &tmSh2, kb * BK, nt * BN + (int)rank * (BN / 2), lfull);
-                        tma_load_2d_2sm(st + 2 * A_TILE_BYTES + B2_TILE_BYTES, &tmSl2, kb * BK, nt * BN + (int)rank * (BN / 2), lfull);
+                        if (passes >= 2) tma_load_2d_2sm(st + 2 * A_TILE_BYTES + B2_TILE_BYTES, &tmSl2, kb * BK, nt * BN + (int)rank * (BN / 2), lfull);
                     }
             }
         }
@@ -426,8 +434,8 @@ svm_rbf_tc2_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_consta
                         for (int k = 0; k < slices; k++) {
                             const uint64_t adv = (uint64_t)(k * 2);
                             tc_mma_2sm(tmem_d, d_ah + adv, d_bh + adv, IDESC2, (kb | k) ? 1u : 0u);
-                            tc_mma_2sm(tmem_d, d_ah + adv, d_bl + adv, IDESC2, 1u);
-                            tc_mma_2sm(tmem_d, d_al + adv, d_bh + adv, IDESC2, 1u);
+                            if (passes >= 2) tc_mma_2sm(tmem_d, d_ah + adv, d_bl + adv, IDESC2, 1u);
+                            if (passes >= 3) tc_mma_2sm(tmem_d, d_al + adv, d_bh + adv, IDESC2, 1u);
                         }
                         tc_commit_2sm_mc(bar_empty + 8 * s);   // stage free in BOTH CTAs
                     }

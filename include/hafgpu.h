@@ -39,7 +39,8 @@ extern "C" {
 typedef struct haf_ctx haf_ctx;
 
 /* svm_mode (0 = what a zero-initialised config gets = the production path) */
-#define HAF_SVM_TENSOR_GUARD 0 /* tcgen05 split-fp16 contraction in TMEM + FP64 re-evaluation inside the guard band (FMA tier, then exact order) */
+#define HAF_SVM_TENSOR_GUARD 0 /* tcgen05 split-fp16 contraction in TMEM (1-3 products per k-slice, calibrated per model) + FP64
+                                  re-evaluation inside the guard band (FMA tier, then exact order) */
 #define HAF_SVM_FP64_EXACT 1   /* every window in FP64, libsvm's summation order (svm.cpp:326-365, :2500-2514) */
 #define HAF_SVM_FP32_GUARD 2   /* FP32 SIMT contraction (CUDA cores) + the same FP64 guard band; conservative mode */
 
@@ -57,7 +58,8 @@ typedef struct {
     float guard_rel;           /* guard band half-width as a fraction of E + |rho|,
                                   E = sum_i |coef_i| K_i (1 + gamma log2(e) (|x|^2 + |sv_i|^2)); <=0 -> default
                                   (4e-6 tensor, 2e-6 FP32 SIMT: >= 12x the measured error)                    */
-    int reserved[4];           /* [0]: tensor-path kernel variant, 0 = CTA-pair (cta_group::2, default), 1 = single CTA;
+    int reserved[4];           /* [0]: bit 0: tensor-path kernel variant, 0 = CTA-pair (cta_group::2, default), 1 = single CTA;
+                                       bits 4-5: tensor-core products per k-slice, 0 = calibrated per model (default), 1 / 2 / 3 forced;
                                   [1]: 1 = always use the point-parallel binning kernel (no whole-cloud CTAs);
                                   [2]: guard band tier 2 (FP64 FMA re-evaluation): 0 = on, 1 = off (every guard window goes
                                        to the exact-order kernels), 2 = on, but every window escalates as well (tests);
@@ -103,7 +105,7 @@ typedef struct {
     int label0, label1; /* model label order (svm.cpp:2516-2531)                                              */
     int sm_count;
     double gamma, rho;
-    int reserved[4];
+    int reserved[4];  /* [0]: tensor-core products per k-slice in use (1-3; 0 outside tensor mode); [1]: guard_rel * 1e9 */
 } haf_info;
 
 typedef struct {

@@ -240,10 +240,12 @@ def test_tensor_mode_fast_tier_inputs_track_the_exact_scaled_values(hg, oracle_l
         gpu.close()
 
 
-@pytest.mark.parametrize("kw", [{}, {"sv_table_global": 1}, {"tc_variant": 1}, {"tc_variant": 1, "sv_table_global": 1}])
+@pytest.mark.parametrize("kw", [{}, {"sv_table_global": 1}, {"tc_variant": 1}, {"tc_variant": 1, "sv_table_global": 1},
+                                {"tc_passes": 1}, {"tc_passes": 2}, {"tc_passes": 3}, {"tc_passes": 1, "tc_variant": 1}])
 def test_tensor_core_mode_synth_models_and_batch(hg, oracle_lib, tmp_models, kw):
     """CTA-pair and single-CTA kernels, with the {c|sv|^2, coef} table staged in shared memory (default) or read from
-    global memory (what models with > 4096 support vectors get)."""
+    global memory (what models with > 4096 support vectors get), and with 1, 2 or 3 tensor-core products per k-slice
+    forced (the default calibrates the count per model and widens the guard band by the calibrated operand error)."""
     from haf_grasping_b200 import synth
     for nsv in (256, 300):   # 300: support-vector count not a multiple of the 256-wide tile
         model = tmp_models(nsv)
@@ -312,6 +314,25 @@ def test_tensor_mode_inputs_beyond_fp16_range_take_the_exact_path(hg, oracle_lib
         big = (np.abs(scaled) > 65000.0).any(axis=1)
         assert big.sum() > 0, "the narrowed range did not push any value beyond the fp16 range"
         assert guard[big].all()
+    finally:
+        p.close()
+
+
+def test_tensor_passes_are_calibrated_per_model(hg, oracle_lib, tmp_models, trained_model, clouds):
+    """gamma = 1/323 (libsvm's default) with 2048 support vectors, the bench model: the cross terms are below the FP32
+    epilogue error, the calibration drops them and widens the guard band; the trained substitute (gamma = 0.02) and the
+    small synthetic models keep all three products.  The one-product search still equals the oracle's."""
+    seen = {}
+    for name, model in (("synth2048", tmp_models(2048)), ("synth256", tmp_models(256)), ("trained", trained_model)):
+        g = hg.GraspSearch(FEATURES, RANGE, model)
+        seen[name] = (g.info.reserved[0], g.info.reserved[1] * 1e-9)
+        g.close()
+    assert seen["trained"][0] == 3 and abs(seen["trained"][1] - 4e-6) < 1e-9
+    assert seen["synth256"][0] == 3
+    assert seen["synth2048"][0] == 1 and 4e-6 < seen["synth2048"][1] <= 1.2e-5, seen
+    p = Pair(hg, oracle_lib, tmp_models(2048))
+    try:
+        check_search(p, clouds["pcd5"], hg, oracle_lib, tmp_models(2048))
     finally:
         p.close()
 

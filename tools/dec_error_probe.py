@@ -77,7 +77,10 @@ def main():
         dst.write(src.read())
     models["trained"] = tm
     clouds = {"synth100k": synth.synth_cloud(1234, 100000), "table1": np.load(os.path.join(ROOT, "tests", "golden", "clouds.npz"))["table1"]}
+    only = sys.argv[1:]   # optional model names to restrict the run to
     for mn, mp in models.items():
+        if only and mn not in only:
+            continue
         coefs = []
         with open(mp) as fh:
             sv = False
