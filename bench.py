@@ -467,7 +467,7 @@ def run_ours(args):
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
                 tr = json.load(fh).get(kname)
             w_launch = acc["windows"] / max(svm_launches, 1)
-            if tr and tr["n_sv"] == info.n_sv and abs(tr["windows_per_launch"] - w_launch) <= 0.01 * w_launch:
+            if tr and tr["n_sv"] == info.n_sv and abs(tr["windows_per_launch"] - w_launch) <= 0.01 * w_launch and (args.svm_mode != 0 or tr.get("passes", 3) == info.reserved[0]):
                 traffic = tr["dram_bytes_per_launch"]
         except Exception:
             traffic = None
