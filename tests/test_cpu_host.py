@@ -177,3 +177,38 @@ def test_cpp_pcd_reader_all_formats(tmp_path):
             out = subprocess.run([cli, "--pcd", path, "--dump-pcd"], capture_output=True, text=True, check=True).stdout.split()
             py = read_pcd(path)
             assert int(out[0]) == len(py) and int(out[1]) == _fnv1a(py.tobytes())
+
+
+def test_bench_stage_roofline_and_clock_sampler_parsing(tmp_path):
+    """bench.py helpers that run on the GPU box only: the algorithmic-byte rows of SURVEY 8d and the nvidia-smi row filter."""
+    import importlib.util
+    import time
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    acc = dict(bin=2.0, integral=0.2, mask=0.2, features=9.8, score=0.5)
+    sr = b.stage_roofline(acc, 2, n_points=1000, n_units=12, G=56, D=323, W=100.0, hbm_gbs=6447.5)
+    assert sr["bin"]["algorithmic_bytes"] == 12.0 * 1000 + 4.0 * 12 * 56 * 56
+    assert sr["integral"]["algorithmic_bytes"] == 4.0 * 12 * 56 * 56 + 4.0 * 12 * 57 * 57
+    assert sr["mask+features"]["algorithmic_bytes"] == 4.0 * 12 * 57 * 57 + 12 * 56 * 56 + 4.0 * 323 * 100.0
+    assert sr["mask+features"]["ms"] == 5.0 and abs(sr["bin"]["GBps"] - sr["bin"]["algorithmic_bytes"] / 1e-3 / 1e9) < 1e-9
+    assert abs(sr["bin"]["frac_of_hbm_peak"] - sr["bin"]["GBps"] / 6447.5) < 1e-12
+    # clock sampler: only rows stamped inside the timed region count; a throttle reason is reported
+    s = b.ClockSampler(0)
+    s.path = str(tmp_path / "clocks.csv")
+    now = time.time()
+
+    def stamp(t):
+        return time.strftime("%Y/%m/%d %H:%M:%S", time.localtime(t)) + ".%03d" % int((t % 1) * 1000)
+    with open(s.path, "w") as fh:
+        fh.write("%s, 1200, 1965, 700.0, Active, Not Active, Not Active, Not Active, Not Active\n" % stamp(now - 30))
+        fh.write("%s, 1900, 1965, 900.0, Active, Not Active, Not Active, Not Active, Active\n" % stamp(now - 0.5))
+        fh.write("%s, 1800, 1965, 900.0, Active, Not Active, Not Active, Not Active, Active\n" % stamp(now - 0.2))
+
+    class Done:
+        def terminate(self): pass
+        def wait(self, timeout=None): return 0
+    s.proc, s.fh = Done(), open(os.devnull, "w")
+    s.t_begin = now - 1.0
+    out = s.stop()
+    assert out["samples"] == 2 and out["sm_mhz"] == 1850.0 and out["reasons"] == ["sw_power_cap"] and out["window"] == "timed region"
