@@ -56,12 +56,13 @@ class haf_timing(C.Structure):
                 ("ms_features", C.c_float), ("ms_svm", C.c_float), ("ms_guard", C.c_float), ("ms_score", C.c_float),
                 ("n_points", C.c_longlong), ("n_units", C.c_longlong), ("n_windows", C.c_longlong),
                 ("n_guard", C.c_longlong), ("launches", C.c_longlong), ("n_chunks", C.c_longlong),
-                ("n_exact", C.c_longlong)]
+                ("n_exact", C.c_longlong), ("n_audit", C.c_longlong), ("audit_max_rel", C.c_float), ("tc_passes", C.c_int),
+                ("escalations", C.c_int), ("reserved", C.c_int)]
 
 
 EXPORTS = ["haf_create", "haf_destroy", "haf_last_error", "haf_get_info", "haf_set_stream", "haf_set_profiling",
-           "haf_get_timing", "haf_launch_count", "haf_search", "haf_search_batch", "haf_search_batch_packed",
-           "haf_build_transform", "haf_best_key", "haf_debug_window_count", "haf_debug_windows", "haf_debug_features",
+           "haf_get_timing", "haf_launch_count", "haf_set_debug", "haf_search", "haf_search_batch", "haf_search_batch_packed",
+           "haf_build_transform", "haf_best_key", "haf_pack_best_records", "haf_debug_window_count", "haf_debug_windows", "haf_debug_features",
            "haf_debug_decisions", "haf_debug_tensor_inputs", "haf_debug_integral", "haf_debug_cell_indices", "haf_debug_text_roundtrip",
            "haf_version", "haf_svm_create", "haf_svm_destroy", "haf_svm_predict", "haf_scale_minmax", "haf_scale_apply"]
 
@@ -92,6 +93,7 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     L.haf_get_info.argtypes = [vp, C.POINTER(haf_info)]
     L.haf_set_stream.argtypes = [vp, vp]
     L.haf_set_profiling.argtypes = [vp, ci]
+    L.haf_set_debug.argtypes = [vp, ci]
     L.haf_get_timing.argtypes = [vp, C.POINTER(haf_timing)]
     L.haf_launch_count.argtypes = [vp]
     L.haf_launch_count.restype = C.c_longlong
@@ -101,6 +103,7 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     L.haf_build_transform.argtypes = [C.POINTER(haf_request), ci, ci, C.POINTER(C.c_float)]
     L.haf_best_key.argtypes = [ci, C.c_uint32]
     L.haf_best_key.restype = C.c_uint64
+    L.haf_pack_best_records.argtypes = [vp, ci, vp]
     L.haf_debug_window_count.argtypes = [vp]
     L.haf_debug_windows.argtypes = [vp, vp, ci]
     L.haf_debug_features.argtypes = [vp, vp, vp, ci]
@@ -152,7 +155,7 @@ class GraspSearch:
 
     def __init__(self, features_path, range_path, model_path, grid=56, roll_step_deg=15, roll_max_deg=190,
                  nr_features_without_shaf=302, device=0, emulate_text_roundtrip=True, svm_mode=HAF_SVM_TENSOR_GUARD,
-                 guard_rel=0.0, tc_variant=0, guard_tier2=0, sv_table_global=0, tc_passes=0):
+                 guard_rel=0.0, tc_variant=0, guard_tier2=0, sv_table_global=0, tc_passes=0, audit_every=None, bin_variant=0):
         self.L = load_library()
         cfg = haf_config()
         self._keep = [features_path.encode(), range_path.encode(), model_path.encode()]
@@ -160,10 +163,15 @@ class GraspSearch:
         cfg.nr_features_without_shaf = nr_features_without_shaf
         cfg.grid, cfg.roll_step_deg, cfg.roll_max_deg = grid, roll_step_deg, roll_max_deg
         cfg.device = device
-        cfg.emulate_text_roundtrip = int(bool(emulate_text_roundtrip))
+        cfg.emulate_text_roundtrip = 1 if emulate_text_roundtrip else -1   # 0 would also mean "on" (zeroed config = reference-exact)
         cfg.svm_mode = svm_mode
         cfg.guard_rel = guard_rel
-        cfg.reserved[0] = tc_variant | (tc_passes << 4)   # tc_passes: 0 = calibrated per model, 1-3 forced
+        # tc_variant: 0 auto (X-resident CTA pair where eligible), 1 single CTA, 2 streaming CTA pair; tc_passes: 0 = calibrated
+        # per model, 1-3 forced; audit_every: None = library default (every 4096th window), 0 = no sample, n = every n-th window
+        cfg.reserved[0] = tc_variant | (tc_passes << 4)
+        if audit_every is not None:
+            cfg.reserved[0] |= 0x100 if audit_every == 0 else (int(audit_every) << 16)
+        cfg.reserved[1] = bin_variant   # 0 auto, 1 point-parallel binning only, 2 whole-cloud kernel with scalar loads
         cfg.reserved[2] = guard_tier2   # 0 on, 1 off, 2 on + escalate everything (tests)
         cfg.reserved[3] = sv_table_global   # 1: SV table read from global memory (the > 4096-SV path)
         self.h = C.c_void_p()
@@ -195,6 +203,10 @@ class GraspSearch:
 
     def set_profiling(self, on: bool):
         self._check(self.L.haf_set_profiling(self.h, int(on)))
+
+    def set_debug(self, keep_batch_state: bool):
+        """batch calls keep their per-window state for the debug_* accessors (single-pass batches only)"""
+        self._check(self.L.haf_set_debug(self.h, int(keep_batch_state)))
 
     def timing(self) -> haf_timing:
         t = haf_timing()
@@ -245,6 +257,12 @@ class GraspSearch:
             xyz_all = np.ascontiguousarray(xyz_all, np.float32)
         self._check(self.L.haf_search_batch_packed(self.h, _ptr(xyz_all), off, n_clouds, C.byref(rq), best))
         return best
+
+    def pack_best_records(self, best, out):
+        """haf_best array of a batch -> int32 [n, 8] records (topval, row, col, roll, tilt, approach_idx, n_windows, rolls_done)
+        written by the library into `out` (numpy array or pinned torch tensor)"""
+        self._check(self.L.haf_pack_best_records(best, len(best), _ptr(out)))
+        return out
 
     def search_batch(self, clouds, request=None):
         """clouds: list of float32 [n_i,3] host arrays or CUDA tensors."""

@@ -11,7 +11,13 @@ CSRC = os.path.join(PKG, "csrc")
 LIB_DIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIB_DIR, "libhafgpu.so")
 SOURCES = ["hafgpu.cu"]
-HEADERS = ["kernels.cuh", "decimal_round.cuh", "haf_host.hpp", os.path.join("..", "..", "include", "hafgpu.h")]
+
+
+def _lib_deps():
+    """every file libhafgpu.so is compiled from: all of csrc/*.{cu,cuh,hpp} plus the public header"""
+    deps = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".hpp", ".h"))]
+    deps.append(os.path.join(PKG, "..", "include", "hafgpu.h"))
+    return deps
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -31,7 +37,7 @@ def needs_build() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    deps = _lib_deps() + [os.path.abspath(__file__)]
     return any(os.path.getmtime(d) > t for d in deps)
 
 

@@ -95,14 +95,18 @@ struct haf_ctx {
     int Krow = 0, SpadT = 0;
     float c_log2 = 0.0f;
     float csvn_max = 0.0f;      // |c| * max_n ||sv_n||^2 (guard scale of the tensor kernels)
-    DevBuf<__half> d_SVh, d_SVl, d_Xh, d_Xl;
-    DevBuf<float2> d_svtab;
+    DevBuf<__half> d_SVh, d_SVl, d_Xh, d_Xl;   // d_Xl only with three products per k-slice
+    DevBuf<float> d_svcoef;     // coef in the tensor path's order (sorted by sign, sign groups padded to whole tiles)
+    DevBuf<double> d_dec_tc;    // audit: the contraction's decision value of every window on the guard list
+    int audit_every = 4096;     // every audit_every-th window joins the guard list as an unbiased error sample (0 = off)
+    float audit_max_rel = 0.0f; // last call: max |dec_tc - dec_fp64| / (E + |rho|) over guard + sample windows
+    int escalations = 0;        // times a call was repeated with more tensor-core products because the audit left < 4x margin
     DevBuf<DimFeat> d_dimfeat;
     DevBuf<Round4Tab> d_round4;   // "%.4g" tables of the fast tier
     DevBuf<float> d_asum;
     CUtensorMap tmSh, tmSl;     // 256-row boxes (single-CTA kernel)
     CUtensorMap tmSh2, tmSl2;   // 128-row boxes (CTA-pair kernel)
-    int tc_variant = 0;         // 0: CTA-pair kernel (cta_group::2), 1: single-CTA kernel
+    int tc_variant = 0;         // 0: auto (X-resident CTA-pair kernel where eligible, else streaming CTA pair), 1: single-CTA kernel, 2: streaming CTA pair
     int tc_passes = 3;          // tensor-core products per k-slice: 3, 2 or 1 (calibrate_tensor_passes)
     double tc_operand_err = 0;  // calibrated operand error of the chosen scheme, as a fraction of the guard scale E
 
@@ -149,6 +153,7 @@ struct haf_ctx {
     DevBuf<double> d_csr_val;
 
     // state of the last search kept for the debug entry points
+    bool debug_keep_batch = false;   // haf_set_debug: keep the per-window state of single-chunk batch calls too
     int last_units = 0, last_unit_base = 0;
     unsigned last_W = 0;
     size_t last_ldx = 0;
@@ -278,6 +283,7 @@ static int create_impl(haf_ctx** out, const haf_config* cfg, bool svm_only, int 
     *out = nullptr;
     if (!cfg->model_path || (!svm_only && (!cfg->features_path || !cfg->range_path)))
         return create_fail(HAF_ERR_ARG, "haf_create: features_path, range_path and model_path are required");
+    const int emu = cfg->emulate_text_roundtrip >= 0 ? 1 : 0;   // 0 (a zeroed config) and 1 = reference-exact; -1 = skip the text round trips
     const int G = cfg->grid > 0 ? cfg->grid : 56;
     if (G < 16 || G > 1024 || (G & 1)) return create_fail(HAF_ERR_ARG, "haf_create: grid must be even and within 16..1024");
     const int step = cfg->roll_step_deg > 0 ? cfg->roll_step_deg : 15;
@@ -354,7 +360,7 @@ static int create_impl(haf_ctx** out, const haf_config* cfg, bool svm_only, int 
                 if (v == d.fmin) val = range.lower;
                 else if (v == d.fmax) val = range.upper;
                 else val = range.lower + (range.upper - range.lower) * (v - d.fmin) / (d.fmax - d.fmin);
-                if (val != 0.0 && cfg->emulate_text_roundtrip) val = hafdec::text6(val);
+                if (val != 0.0 && emu) val = hafdec::text6(val);
             }
             d.cval = val;
         }
@@ -378,6 +384,7 @@ static int create_impl(haf_ctx** out, const haf_config* cfg, bool svm_only, int 
 
     haf_ctx* ctx = new haf_ctx();
     ctx->cfg = *cfg;
+    ctx->cfg.emulate_text_roundtrip = emu;
     ctx->cfg.grid = G; ctx->cfg.roll_step_deg = step; ctx->cfg.roll_max_deg = rmax; ctx->cfg.nr_features_without_shaf = nshaf;
     ctx->device = cfg->device;
     ctx->sm_count = prop.multiProcessorCount;
@@ -455,17 +462,29 @@ static int create_impl(haf_ctx** out, const haf_config* cfg, bool svm_only, int 
     CREATE_TRY(cudaFuncSetAttribute(svm_rbf_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SVM_STAGES * SVM_BK * (SVM_BM + SVM_BN) * 4));
     CREATE_TRY(cudaFuncSetAttribute(integral_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CREATE_TRY(cudaFuncSetAttribute(svm_exact_terms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    CREATE_TRY(cudaFuncSetAttribute(bin_maxz_cloud_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CREATE_TRY(cudaFuncSetAttribute(bin_maxz_cloud_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CREATE_TRY(cudaFuncSetAttribute(bin_maxz_cloud_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     if (cfg->svm_mode == HAF_SVM_TENSOR_GUARD) {
-        const int Krow = (int)round_up((size_t)Dsv, 16);
-        const int SpadT = (int)round_up((size_t)S, haftc::BN);
-        ctx->Krow = Krow; ctx->SpadT = SpadT;
+        const int Krow = (int)round_up((size_t)Dsv + haftc::NAUG, 16);   // dimensions + the six extra operand columns (svm_tc.cuh)
         ctx->c_log2 = (float)(-model.gamma * 1.4426950408889634);
         if (cfg->guard_rel <= 0) ctx->guard_rel = 4e-6f;  // of E (see svm_tc.cuh); measured split-fp16 + fast-tier error <= 3.3e-7 E (tools/dec_error_probe.py)
+        // tensor-path order of the support vectors: coef > 0 first, then coef <= 0, each group padded to whole tiles of BN,
+        // so that every tile is uniform in sign (the guard scale is then sum over tiles of |tile sum|)
+        std::vector<int> order;
+        for (int pass = 0; pass < 2; pass++) {
+            for (int i = 0; i < S; i++)
+                if ((model.coef[i] > 0) == (pass == 0)) order.push_back(i);
+            while (order.size() % haftc::BN) order.push_back(-1);
+        }
+        if (order.empty()) order.assign(haftc::BN, -1);
+        const int SpadT = (int)order.size();
+        ctx->Krow = Krow; ctx->SpadT = SpadT;
         std::vector<uint16_t> svh((size_t)SpadT * Krow, 0), svl((size_t)SpadT * Krow, 0);
-        std::vector<float2> tab(SpadT);
-        for (int i = 0; i < SpadT; i++) tab[i] = make_float2(0.0f, 0.0f);
-        for (int i = 0; i < S; i++) {
+        std::vector<float> tab(SpadT, 0.0f);
+        const uint16_t one16 = f2h16(1.0f);
+        for (int r = 0; r < SpadT; r++) {
+            const int i = order[r];
+            if (i < 0) continue;   // padding: all-zero row, coef 0
             float nrm = 0.0f;
             for (size_t e = 0; e < model.sv[i].size(); e++) {
                 const int d = model.sv[i][e].first - 1;
@@ -476,21 +495,34 @@ static int create_impl(haf_ctx** out, const haf_config* cfg, bool svm_only, int 
                 }
                 const uint16_t h = f2h16(fv);
                 const uint16_t l = f2h16(fv - h16f(h));
-                svh[(size_t)i * Krow + d] = h;
-                svl[(size_t)i * Krow + d] = l;
+                svh[(size_t)r * Krow + d] = h;
+                svl[(size_t)r * Krow + d] = l;
                 const float rep = h16f(h) + h16f(l);
                 nrm = fmaf(rep, rep, nrm);
             }
-            tab[i].x = ctx->c_log2 * nrm;
-            tab[i].y = (float)model.coef[i];
-            ctx->csvn_max = std::max(ctx->csvn_max, fabsf(tab[i].x));
+            if (!(nrm < 1.3e5f)) {
+                haf_destroy(ctx);
+                return create_fail(HAF_ERR_UNSUPPORTED, "a support vector's squared norm exceeds the fp16 range of the tensor path (use svm_mode HAF_SVM_FP32_GUARD)");
+            }
+            // extra operand columns: 1 1 1 (against the window's -|x|^2 / 2 terms), then -|sv|^2 / 2 as three fp16 terms
+            uint16_t* aug = &svh[(size_t)r * Krow + Dsv];
+            aug[0] = aug[1] = aug[2] = one16;
+            const float b = -0.5f * nrm;
+            const uint16_t bh = f2h16(b);
+            const float r1 = b - h16f(bh);
+            const uint16_t bm = f2h16(r1);
+            aug[3] = bh; aug[4] = bm; aug[5] = f2h16(r1 - h16f(bm));
+            tab[r] = (float)model.coef[i];
+            ctx->csvn_max = std::max(ctx->csvn_max, fabsf(ctx->c_log2 * nrm));
         }
-        bool okt = ctx->d_SVh.ensure(svh.size()) == 0 && ctx->d_SVl.ensure(svl.size()) == 0 && ctx->d_svtab.ensure(SpadT) == 0;
+        bool okt = ctx->d_SVh.ensure(svh.size()) == 0 && ctx->d_SVl.ensure(svl.size()) == 0 && ctx->d_svcoef.ensure(SpadT) == 0;
         if (!okt) { haf_destroy(ctx); return create_fail(HAF_ERR_NOMEM, "out of device memory uploading the fp16 model"); }
         CREATE_TRY(cudaMemcpy(ctx->d_SVh.p, svh.data(), svh.size() * 2, cudaMemcpyHostToDevice));
         CREATE_TRY(cudaMemcpy(ctx->d_SVl.p, svl.data(), svl.size() * 2, cudaMemcpyHostToDevice));
-        CREATE_TRY(cudaMemcpy(ctx->d_svtab.p, tab.data(), SpadT * sizeof(float2), cudaMemcpyHostToDevice));
-        ctx->tc_variant = cfg->reserved[0] & 1;
+        CREATE_TRY(cudaMemcpy(ctx->d_svcoef.p, tab.data(), SpadT * sizeof(float), cudaMemcpyHostToDevice));
+        ctx->tc_variant = cfg->reserved[0] & 3;
+        if (cfg->reserved[0] & 0x100) ctx->audit_every = 0;                       // bit 8: audit sample off (guard-band windows are still compared)
+        else if (cfg->reserved[0] >> 16) ctx->audit_every = cfg->reserved[0] >> 16;   // bits 16+: sample every n-th window (tests)
         {   // number of tensor-core products per k-slice: forced by cfg.reserved[0] bits 4-5, else calibrated per model
             const int forced = (cfg->reserved[0] >> 4) & 3;
             double rel[4] = {0, 0, 0, 0};
@@ -543,8 +575,9 @@ static int create_impl(haf_ctx** out, const haf_config* cfg, bool svm_only, int 
         CREATE_TRY(cudaMemcpy(ctx->d_round4.p, &r4, sizeof(Round4Tab), cudaMemcpyHostToDevice));
         if (ctx->d_dimfeat.ensure(joined.size()) != 0) { haf_destroy(ctx); return create_fail(HAF_ERR_NOMEM, "out of device memory uploading the joined feature table"); }
         CREATE_TRY(cudaMemcpy(ctx->d_dimfeat.p, joined.data(), joined.size() * sizeof(DimFeat), cudaMemcpyHostToDevice));
-        CREATE_TRY(cudaFuncSetAttribute(haftc::svm_rbf_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, haftc::SMEM_BYTES + haftc::TAB_SMEM_MAX * 8));
-        CREATE_TRY(cudaFuncSetAttribute(haftc::svm_rbf_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, haftc::SMEM2_BYTES + haftc::TAB_SMEM_MAX * 8));
+        CREATE_TRY(cudaFuncSetAttribute(haftc::svm_rbf_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, haftc::SMEM_BYTES + haftc::TAB_SMEM_MAX * 4));
+        CREATE_TRY(cudaFuncSetAttribute(haftc::svm_rbf_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, haftc::SMEM2_BYTES + haftc::TAB_SMEM_MAX * 4));
+        CREATE_TRY(cudaFuncSetAttribute(haftc::svm_rbf_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, haftc::TC3_SMEM_LIMIT));
         CREATE_TRY(cudaFuncSetAttribute(features_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * HAF_FT_WT * (HAF_FT_KPASS + 1) * 4 + HAF_FT_ROWS * (G + 1 + 31) * 4 + 16 + HAF_FT_KPASS * 96));
         // 4 CTAs x ~49 KB: ask for just that much shared memory so that the rest of the SM's 256 KB stays L1 (the corner-offset table)
         CREATE_TRY(cudaFuncSetAttribute(features_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 90));
@@ -609,7 +642,7 @@ extern "C" int haf_svm_predict(haf_svm* ctx, const long long* row_ptr, const int
         ENSURE(ctx, ctx->d_csr_ptr, rows + 1); ENSURE(ctx, ctx->d_csr_idx, (size_t)std::max<long long>(e1 - e0, 1)); ENSURE(ctx, ctx->d_csr_val, (size_t)std::max<long long>(e1 - e0, 1));
         ENSURE(ctx, ctx->d_xdense, rows * W); ENSURE(ctx, ctx->d_labels, rows);
         ENSURE(ctx, ctx->d_xn, ldx); ENSURE(ctx, ctx->d_dec, ldx); ENSURE(ctx, ctx->d_guardflag, ldx); ENSURE(ctx, ctx->d_guardlist, ldx);
-        if (tc) { ENSURE(ctx, ctx->d_Xh, ldx * ctx->Krow); ENSURE(ctx, ctx->d_Xl, ldx * ctx->Krow); ENSURE(ctx, ctx->d_asum, ldx); }
+        if (tc) { ENSURE(ctx, ctx->d_Xh, ldx * ctx->Krow); if (ctx->tc_passes >= 3) ENSURE(ctx, ctx->d_Xl, ldx * ctx->Krow); ENSURE(ctx, ctx->d_asum, ldx); }
         else if (ctx->cfg.svm_mode == HAF_SVM_FP32_GUARD) ENSURE(ctx, ctx->d_X, (size_t)ctx->Kpad * ldx);
         const size_t exact_cap = std::min<size_t>(ldx, std::max<size_t>(4096, ((size_t)1 << 30) / ((size_t)ctx->Spad * 8)));
         ENSURE(ctx, ctx->d_kscratch, exact_cap * ctx->Spad);
@@ -629,7 +662,7 @@ extern "C" int haf_svm_predict(haf_svm* ctx, const long long* row_ptr, const int
         LAUNCHED(ctx);
         if (ctx->cfg.svm_mode != HAF_SVM_FP64_EXACT) {
             pack_svm_inputs_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(ctx->d_xdense.p, (int)rows, W, ctx->Krow, tc ? ctx->d_Xh.p : nullptr,
-                                                                              tc ? ctx->d_Xl.p : nullptr, tc ? nullptr : ctx->d_X.p, ldx, ctx->Kpad, ctx->d_xn.p);
+                                                                              (tc && ctx->tc_passes >= 3) ? ctx->d_Xl.p : nullptr, tc ? nullptr : ctx->d_X.p, ldx, ctx->Kpad, ctx->d_xn.p);
             LAUNCHED(ctx);
         }
         ctx->cur_xdense = ctx->d_xdense.p;
@@ -648,9 +681,22 @@ extern "C" int haf_svm_predict(haf_svm* ctx, const long long* row_ptr, const int
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
     if (ctx->h_counters.p[10]) return ctx->fail(HAF_ERR_UNSUPPORTED, "the guard band holds more rows than the exact path is provisioned for (guard_rel too wide for this model)");
     total_guard = ctx->h_counters.p[9];
+    memcpy(&ctx->audit_max_rel, &ctx->h_counters.p[12], sizeof(float));
+    if (tc && ctx->tier2_mode != 1 && ctx->audit_max_rel > 0.25f * ctx->guard_rel) {   // audit (see run_jobs): repeat with one more product
+        if (ctx->tc_passes >= 3)
+            return ctx->fail(HAF_ERR_UNSUPPORTED, "audit: the tensor contraction is off by %.3g E on these rows, guard_rel = %.3g leaves less than a 4x margin",
+                             (double)ctx->audit_max_rel, (double)ctx->guard_rel);
+        ctx->tc_passes++;
+        ctx->escalations++;
+        return haf_svm_predict(ctx, row_ptr, index, value, n_rows, labels, dec_values);
+    }
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev[8], ctx->ev[9]);
     ctx->timing.ms_total = ms;
+    ctx->timing.n_audit = ctx->h_counters.p[14];
+    ctx->timing.audit_max_rel = ctx->audit_max_rel;
+    ctx->timing.tc_passes = tc ? ctx->tc_passes : 0;
+    ctx->timing.escalations = ctx->escalations;
     ctx->timing.n_windows = n_rows;
     ctx->timing.n_guard = total_guard;
     ctx->timing.n_exact = (ctx->tier2_mode == 1 && ctx->cfg.svm_mode != HAF_SVM_FP64_EXACT) ? total_guard : ctx->h_counters.p[11];
@@ -751,7 +797,7 @@ extern "C" void haf_destroy(haf_ctx* ctx) {
     ctx->d_xn.release(); ctx->d_dec.release(); ctx->d_guardflag.release(); ctx->d_guardlist.release(); ctx->d_kscratch.release();
     ctx->d_xdense.release(); ctx->d_labels.release(); ctx->d_csr_ptr.release(); ctx->d_csr_idx.release(); ctx->d_csr_val.release();
     ctx->d_svn64.release(); ctx->d_Xg.release(); ctx->d_g2accum.release(); ctx->d_g2tickets.release(); ctx->d_guardlist2.release();
-    ctx->d_SVh.release(); ctx->d_SVl.release(); ctx->d_Xh.release(); ctx->d_Xl.release(); ctx->d_svtab.release(); ctx->d_asum.release(); ctx->d_dimfeat.release(); ctx->d_round4.release();
+    ctx->d_SVh.release(); ctx->d_SVl.release(); ctx->d_Xh.release(); ctx->d_Xl.release(); ctx->d_svcoef.release(); ctx->d_dec_tc.release(); ctx->d_asum.release(); ctx->d_dimfeat.release(); ctx->d_round4.release();
     ctx->d_params.release(); ctx->d_counters.release(); ctx->h_stage.release(); ctx->h_results.release(); ctx->h_per_roll_top.release(); ctx->h_counters.release();
     if (ctx->ev_ok) for (int i = 0; i < 10; i++) cudaEventDestroy(ctx->ev[i]);
     for (size_t i = 0; i < ctx->ev_pool.size(); i++) cudaEventDestroy(ctx->ev_pool[i]);
@@ -772,6 +818,7 @@ extern "C" int haf_get_info(const haf_ctx* ctx, haf_info* info) {
     return HAF_OK;
 }
 extern "C" int haf_set_stream(haf_ctx* ctx, void* s) { if (!ctx) return HAF_ERR_ARG; ctx->stream = (cudaStream_t)s; return HAF_OK; }
+extern "C" int haf_set_debug(haf_ctx* ctx, int keep_batch_state) { if (!ctx) return HAF_ERR_ARG; ctx->debug_keep_batch = keep_batch_state != 0; return HAF_OK; }
 extern "C" int haf_set_profiling(haf_ctx* ctx, int on) { if (!ctx) return HAF_ERR_ARG; ctx->profiling = on != 0; return HAF_OK; }
 extern "C" int haf_get_timing(const haf_ctx* ctx, haf_timing* t) { if (!ctx || !t) return HAF_ERR_ARG; *t = ctx->timing; return HAF_OK; }
 extern "C" long long haf_launch_count(const haf_ctx* ctx) { return ctx ? ctx->launches : 0; }
@@ -779,6 +826,16 @@ extern "C" long long haf_launch_count(const haf_ctx* ctx) { return ctx ? ctx->la
 extern "C" int haf_build_transform(const haf_request* req, int roll, int roll_step_deg, float M[16]) {
     if (!req || !M) return HAF_ERR_ARG;
     hafhost::build_transform(*req, roll, roll_step_deg > 0 ? roll_step_deg : 15, M);
+    return HAF_OK;
+}
+// the 32-byte record of the cross-GPU best-grasp exchange, straight from the haf_best structs of a batch
+extern "C" int haf_pack_best_records(const haf_best* best, int n, int32_t* records) {
+    if (!best || !records || n < 0) return HAF_ERR_ARG;
+    for (int i = 0; i < n; i++) {
+        int32_t* r = records + (size_t)i * 8;
+        r[0] = best[i].topval; r[1] = best[i].row; r[2] = best[i].col; r[3] = best[i].roll; r[4] = best[i].tilt;
+        r[5] = best[i].approach_idx; r[6] = best[i].n_windows_scored; r[7] = best[i].rolls_done;
+    }
     return HAF_OK;
 }
 extern "C" uint64_t haf_best_key(int topval, uint32_t unit_order) {
@@ -847,6 +904,8 @@ static int launch_guard(haf_ctx* ctx, unsigned* cnt, int G, int ubase, cudaStrea
     q.list = ctx->d_guardlist.p; q.list_count = cnt + 1; q.cap = (int)cap; q.Xg = ctx->d_Xg.p; q.svn64 = ctx->d_svn64.p;
     q.accum = ctx->d_g2accum.p; q.tickets = ctx->d_g2tickets.p; q.tol2 = ctx->tier2_mode == 2 ? 1e30 : 1e-10;
     q.list2 = ctx->d_guardlist2.p; q.list2_count = cnt + 6;
+    const bool audit = ctx->cfg.svm_mode == HAF_SVM_TENSOR_GUARD && ctx->d_dec_tc.p;
+    q.dec_tc = audit ? ctx->d_dec_tc.p : nullptr; q.audit_max = cnt + 12;
     const size_t smem = ((size_t)ctx->Dsv * HAF_G2_WB + HAF_G2_WB + 8 * HAF_G2_WB * 2) * sizeof(double);
     if (smem > 100 * 1024) return launch_exact(ctx, a, st, Wcap);   // models with > ~780 dimensions: exact-order kernels only
     const bool few = Wcap < 65536;   // a single goal: a handful of guard windows -> spread the support vectors over more CTAs
@@ -883,7 +942,9 @@ static int svm_stage(haf_ctx* ctx, unsigned* cnt, size_t Wcap, size_t ldx, int G
         if (ev_guard) CUDA_TRY(ctx, cudaEventRecord(ev_guard, st));
     } else if (tc) {
         CUtensorMap tmXh, tmXl;
-        if (!make_tensor_map(&tmXh, ctx->d_Xh.p, ctx->Krow, ldx, haftc::BM) || !make_tensor_map(&tmXl, ctx->d_Xl.p, ctx->Krow, ldx, haftc::BM))
+        const bool need_lo = ctx->tc_passes >= 3;   // X_lo takes part in the third product only
+        if (!make_tensor_map(&tmXh, ctx->d_Xh.p, ctx->Krow, ldx, haftc::BM) ||
+            !make_tensor_map(&tmXl, need_lo ? ctx->d_Xl.p : ctx->d_Xh.p, ctx->Krow, ldx, haftc::BM))
             return ctx->fail(HAF_ERR_CUDA, "cuTensorMapEncodeTiled failed for the window operands");
         CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_dec.p, 0, ldx * sizeof(double), st));
         CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_asum.p, 0, ldx * sizeof(float), st));
@@ -893,9 +954,9 @@ static int svm_stage(haf_ctx* ctx, unsigned* cnt, size_t Wcap, size_t ldx, int G
         if (mt_cap < ctx->sm_count) nsplit = std::min(n_ntiles, (2 * ctx->sm_count + mt_cap - 1) / mt_cap);
         const int kblocks = (ctx->Krow + haftc::BK - 1) / haftc::BK;
         const int last_slices = (ctx->Krow - haftc::BK * (kblocks - 1)) / 16;
-        const int tab_smem = (ctx->SpadT <= haftc::TAB_SMEM_MAX && !ctx->cfg.reserved[3]) ? 1 : 0;   // {c|sv|^2, coef} table staged in shared memory
-        const size_t tab_bytes = tab_smem ? (size_t)ctx->SpadT * 8 : 0;
-        if (ctx->tc_variant == 0) {
+        const int tab_smem = (ctx->SpadT <= haftc::TAB_SMEM_MAX && !ctx->cfg.reserved[3]) ? 1 : 0;   // coef table staged in shared memory
+        const size_t tab_bytes = tab_smem ? (size_t)ctx->SpadT * 4 : 0;
+        if (ctx->tc_variant != 1) {
             const int pairs_cap = (mt_cap + 1) / 2;
             int nsplit2 = 1;
             if (pairs_cap < ctx->sm_count / 2) nsplit2 = std::min(n_ntiles, (ctx->sm_count + pairs_cap - 1) / pairs_cap);
@@ -911,17 +972,30 @@ static int svm_stage(haf_ctx* ctx, unsigned* cnt, size_t Wcap, size_t ldx, int G
             }
             int grid2 = (int)std::min<long long>((long long)pairs_cap * nsplit2 * 2, ctx->sm_count);
             grid2 &= ~1;  // whole clusters
-            haftc::svm_rbf_tc2_kernel<<<grid2, haftc::THREADS, haftc::SMEM2_BYTES + tab_bytes, st>>>(tmXh, tmXl, ctx->tmSh2, ctx->tmSl2, ctx->d_xn.p, ctx->d_svtab.p,
-                                                                                         ctx->c_log2, cnt + 0, n_ntiles, nsplit2, kblocks, last_slices,
-                                                                                         ctx->d_dec.p, ctx->d_asum.p, tab_smem, ctx->csvn_max, ctx->tc_passes);
+            // X-resident kernel: one product, the X tile (kblocks x 16 KB) + at least 3 ring stages + the table must fit
+            int stages3 = 0;
+            if (ctx->tc_variant == 0 && ctx->tc_passes == 1 && kblocks <= haftc::XK_MAX)
+                stages3 = std::min(8, (haftc::TC3_SMEM_LIMIT - haftc::tc3_smem_bytes(kblocks, 0, (int)(tab_bytes / 4))) / haftc::B2_TILE_BYTES);
+            if (stages3 >= 3)
+                haftc::svm_rbf_tc3_kernel<<<grid2, haftc::THREADS3, haftc::tc3_smem_bytes(kblocks, stages3, (int)(tab_bytes / 4)), st>>>(
+                    tmXh, ctx->tmSh2, ctx->d_xn.p, ctx->d_svcoef.p, ctx->c_log2, cnt + 0, n_ntiles, nsplit2, kblocks, last_slices, stages3, ctx->d_dec.p,
+                    ctx->d_asum.p, tab_smem, ctx->csvn_max);
+            else
+                haftc::svm_rbf_tc2_kernel<<<grid2, haftc::THREADS, haftc::SMEM2_BYTES + tab_bytes, st>>>(tmXh, tmXl, ctx->tmSh2, ctx->tmSl2, ctx->d_xn.p, ctx->d_svcoef.p,
+                                                                                                 ctx->c_log2, cnt + 0, n_ntiles, nsplit2, kblocks, last_slices,
+                                                                                                 ctx->d_dec.p, ctx->d_asum.p, tab_smem, ctx->csvn_max, ctx->tc_passes);
         } else {
             const int grid = (int)std::min<long long>((long long)mt_cap * nsplit, ctx->sm_count);
-            haftc::svm_rbf_tc_kernel<<<grid, haftc::THREADS, haftc::SMEM_BYTES + tab_bytes, st>>>(tmXh, tmXl, ctx->tmSh, ctx->tmSl, ctx->d_xn.p, ctx->d_svtab.p, ctx->c_log2,
-                                                                                      cnt + 0, n_ntiles, nsplit, kblocks, last_slices, ctx->d_dec.p, ctx->d_asum.p, tab_smem, ctx->csvn_max, ctx->tc_passes);
+            haftc::svm_rbf_tc_kernel<<<grid, haftc::THREADS, haftc::SMEM_BYTES + tab_bytes, st>>>(tmXh, tmXl, ctx->tmSh, ctx->tmSl, ctx->d_xn.p, ctx->d_svcoef.p, ctx->c_log2,
+                                                                                          cnt + 0, n_ntiles, nsplit, kblocks, last_slices, ctx->d_dec.p, ctx->d_asum.p, tab_smem, ctx->csvn_max, ctx->tc_passes);
         }
         LAUNCHED(ctx);
+        // audit (svm_tc.cuh): with the FP64 FMA tier on, every listed window's contraction value is kept and a sample of all windows joins the list
+        const bool audit = ctx->tier2_mode != 1;
+        if (audit) ENSURE(ctx, ctx->d_dec_tc, ldx);
         haftc::svm_finalize_kernel<<<(unsigned)((Wcap + 255) / 256), 256, 0, st>>>(ctx->d_dec.p, ctx->d_asum.p, ctx->d_xn.p, cnt + 0, ctx->rho, ctx->guard_rel,
-                                                                                   ctx->d_guardflag.p, ctx->d_guardlist.p, cnt + 1);
+                                                                                   ctx->d_guardflag.p, ctx->d_guardlist.p, cnt + 1, audit ? ctx->audit_every : 0,
+                                                                                   audit ? ctx->d_dec_tc.p : nullptr, cnt + 13);
         LAUNCHED(ctx);
         if (ev_guard) CUDA_TRY(ctx, cudaEventRecord(ev_guard, st));
         { int rce = launch_guard(ctx, cnt, G, ubase, st, Wcap, ldx); if (rce) return rce; }
@@ -938,8 +1012,8 @@ static int svm_stage(haf_ctx* ctx, unsigned* cnt, size_t Wcap, size_t ldx, int G
 
 // Runs the whole path for `jobs` (sorted by cloud).  Outputs land in ctx->h_results / h_per_roll_top (pinned) and,
 // when out_* are given (single-chunk calls only), in the caller's buffers.
-static int run_jobs(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& jobs, float* out_evals, unsigned char* out_mask,
-                    float* out_heights, bool keep_debug_state) {
+static int run_jobs_once(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& jobs, float* out_evals, unsigned char* out_mask,
+                         float* out_heights, bool keep_debug_state) {
     const int G = ctx->G, R = ctx->R, GG = G * G, ld = G + 1;
     const int n_jobs = (int)jobs.size();
     const int n_clouds = (int)cs.off.size() - 1;
@@ -1067,7 +1141,7 @@ static int run_jobs(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& jobs, fl
         ENSURE(ctx, ctx->d_mask, (size_t)Uc * GG); ENSURE(ctx, ctx->d_labelgrid, (size_t)Uc * GG); ENSURE(ctx, ctx->d_evals, (size_t)Uc * GG);
         const bool tc = ctx->cfg.svm_mode == HAF_SVM_TENSOR_GUARD;
         ENSURE(ctx, ctx->d_win, ldx); ENSURE(ctx, ctx->d_xn, ldx);
-        if (tc) { ENSURE(ctx, ctx->d_Xh, ldx * ctx->Krow); ENSURE(ctx, ctx->d_Xl, ldx * ctx->Krow); ENSURE(ctx, ctx->d_asum, ldx); }
+        if (tc) { ENSURE(ctx, ctx->d_Xh, ldx * ctx->Krow); if (ctx->tc_passes >= 3) ENSURE(ctx, ctx->d_Xl, ldx * ctx->Krow); ENSURE(ctx, ctx->d_asum, ldx); }
         else if (ctx->cfg.svm_mode == HAF_SVM_FP32_GUARD) ENSURE(ctx, ctx->d_X, (size_t)ctx->Kpad * ldx);
         ENSURE(ctx, ctx->d_dec, ldx); ENSURE(ctx, ctx->d_guardflag, ldx); ENSURE(ctx, ctx->d_guardlist, ldx);
         if (!smallG) ENSURE(ctx, ctx->d_rowscan, (size_t)Uc * GG);
@@ -1093,16 +1167,21 @@ static int run_jobs(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& jobs, fl
             // small grids with enough points per cloud: whole-cloud CTAs with shared-memory lower bounds (fewer REDs)
             const int upg = std::min(16, (int)((200 * 1024) / ((size_t)GG * 4)));
             const long long avg_points = (cs.off[c1] - cs.off[c0]) / std::max(1, c1 - c0);
-            if (upg >= 1 && avg_points >= 8 * (long long)GG && (c1 - c0) * 8 >= ctx->sm_count && !ctx->cfg.reserved[1]) {
+            if (upg >= 1 && avg_points >= 8 * (long long)GG && (c1 - c0) * 8 >= ctx->sm_count && ctx->cfg.reserved[1] != 1) {
                 int max_units_per_cloud = 0;
                 for (int c = c0; c < c1; c++) max_units_per_cloud = std::max(max_units_per_cloud, hub[c + 1] - hub[c]);
                 const int ug = std::min(upg, std::max(1, max_units_per_cloud));
                 // measured: the kernel is instruction-bound once the REDs are filtered; 1 slice at 256 clouds, 2-4 at 64
                 const int slices = std::max(1, std::min(8, (3 * ctx->sm_count / 2 + (c1 - c0) - 1) / (c1 - c0)));
                 dim3 gridc((unsigned)(c1 - c0), (unsigned)((max_units_per_cloud + ug - 1) / ug), (unsigned)slices);
-                bin_maxz_cloud_kernel<<<gridc, 1024, (size_t)ug * GG * 4, st>>>(cs.d_xyz, cs.stride, d_ptoff + c0, d_cloud_ubegin + c0, d_units,
-                                                                              ctx->d_keys.p - (size_t)ubase * GG, G, r, ug,
-                                                                              reinterpret_cast<unsigned long long*>(cnt + 4));
+                if (cs.stride == 12 && ctx->cfg.reserved[1] != 2)
+                    bin_maxz_cloud_kernel<4><<<gridc, 1024, (size_t)ug * GG * 4, st>>>(cs.d_xyz, cs.stride, d_ptoff + c0, d_cloud_ubegin + c0, d_units,
+                                                                                     ctx->d_keys.p - (size_t)ubase * GG, G, r, ug,
+                                                                                     reinterpret_cast<unsigned long long*>(cnt + 4));
+                else
+                    bin_maxz_cloud_kernel<1><<<gridc, 1024, (size_t)ug * GG * 4, st>>>(cs.d_xyz, cs.stride, d_ptoff + c0, d_cloud_ubegin + c0, d_units,
+                                                                                     ctx->d_keys.p - (size_t)ubase * GG, G, r, ug,
+                                                                                     reinterpret_cast<unsigned long long*>(cnt + 4));
                 LAUNCHED(ctx);
             } else {
                 const int PPT = 4;
@@ -1139,7 +1218,7 @@ static int run_jobs(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& jobs, fl
             const unsigned fblocks = (unsigned)((Wcap + 32 * HAF_FT_WT - 1) / (32 * HAF_FT_WT));
             features_tc_kernel<<<fblocks, 256, ft_smem_bytes(ctx), st>>>(ctx->d_integral.p, ctx->d_win.p, cnt + 0, G, ubase, ctx->d_dimfeat.p, ctx->D,
                                                                       ctx->Krow, (float)ctx->lower, ctx->cfg.emulate_text_roundtrip, ctx->d_round4.p, ctx->d_Xh.p,
-                                                                      ctx->d_Xl.p, ctx->d_xn.p);
+                                                                      ctx->tc_passes >= 3 ? ctx->d_Xl.p : nullptr, ctx->d_xn.p, ctx->Dsv);
             LAUNCHED(ctx);
         } else if (ctx->cfg.svm_mode != HAF_SVM_FP64_EXACT) {
             features_kernel<false><<<wblocks32, 256, 0, st>>>(ctx->d_integral.p, ctx->d_win.p, cnt + 0, G, ubase, ctx->d_feats.p, ctx->d_dims.p,
@@ -1209,8 +1288,35 @@ static int run_jobs(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& jobs, fl
     t.n_windows = total_windows; t.n_guard = total_guard; t.launches = ctx->launches - launches0;
     t.n_chunks = (long long)chunks.size();
     t.n_exact = (ctx->tier2_mode == 1 && ctx->cfg.svm_mode != HAF_SVM_FP64_EXACT) ? total_guard : ctx->h_counters.p[11];
+    t.n_audit = ctx->h_counters.p[14];
+    memcpy(&ctx->audit_max_rel, &ctx->h_counters.p[12], sizeof(float));
+    t.audit_max_rel = ctx->audit_max_rel;
+    t.tc_passes = ctx->cfg.svm_mode == HAF_SVM_TENSOR_GUARD ? ctx->tc_passes : 0;
+    t.escalations = ctx->escalations;
     if (keep_debug_state) { ctx->last_W = (unsigned)total_windows; ctx->last_valid = true; }
     return HAF_OK;
+}
+
+// AUDIT.  The number of tensor-core products per k-slice is calibrated at haf_create on stand-in windows; every call then
+// MEASURES the contraction's error on its own windows: the guard band's windows and a 1-in-audit_every sample of all
+// windows are re-evaluated in FP64 anyway / as well, and guard_fma_kernel records max |dec_tc - dec_fp64| / (E + |rho|).
+// A window outside the band keeps the contraction's sign, which is the reference's as long as the error stays below
+// guard_rel; if the measured maximum leaves less than a 4x margin, the call is repeated with one more product (and stays
+// there for the life of the context); with all three products in use it fails loudly instead of returning labels it
+// cannot vouch for.
+static int run_jobs(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& jobs, float* out_evals, unsigned char* out_mask,
+                    float* out_heights, bool keep_debug_state) {
+    for (;;) {
+        const int rc = run_jobs_once(ctx, cs, jobs, out_evals, out_mask, out_heights, keep_debug_state);
+        if (rc != HAF_OK || ctx->cfg.svm_mode != HAF_SVM_TENSOR_GUARD || ctx->tier2_mode == 1) return rc;
+        if (!(ctx->audit_max_rel > 0.25f * ctx->guard_rel)) return rc;
+        if (ctx->tc_passes >= 3)
+            return ctx->fail(HAF_ERR_UNSUPPORTED, "audit: the tensor contraction is off by %.3g E on this call's windows, guard_rel = %.3g leaves less than a 4x margin "
+                             "(widen guard_rel, or use svm_mode HAF_SVM_FP32_GUARD / HAF_SVM_FP64_EXACT)", (double)ctx->audit_max_rel, (double)ctx->guard_rel);
+        ctx->tc_passes++;
+        ctx->escalations++;
+        ctx->copy_pieces = 0;   // a host-staged batch is on the device by now
+    }
 }
 
 static void fill_best(const haf_ctx* ctx, const Job& jb, const JobResult& r, int approach_idx, long long n_guard, haf_best* b) {
@@ -1261,9 +1367,8 @@ extern "C" int haf_search(haf_ctx* ctx, const float* xyz, size_t n_points, size_
         const JobResult& r = ctx->h_results.p[a];
         if (best_per_request) fill_best(ctx, jobs[a], r, a, ctx->timing.n_guard, &best_per_request[a]);
         if (r.topval > wtop) { wtop = r.topval; win = a; }
-        if (per_roll_top)
-            for (int roll = jobs[a].roll_begin; roll < jobs[a].n_rolls_active; roll++)
-                memcpy(per_roll_top + ((size_t)a * R + roll) * 3, ctx->h_per_roll_top.p + ((size_t)a * R + roll) * 3, 3 * sizeof(int));
+        if (per_roll_top)   // every roll: the ones not evaluated (roll_begin / roll_limit) carry (-1, -1, -1000)
+            memcpy(per_roll_top + (size_t)a * R * 3, ctx->h_per_roll_top.p + (size_t)a * R * 3, (size_t)R * 3 * sizeof(int));
     }
     if (win < 0) {
         JobResult none; memset(&none, 0, sizeof none);
@@ -1328,7 +1433,7 @@ extern "C" int haf_search_batch_packed(haf_ctx* ctx, const float* xyz_all, const
     cs.d_xyz = total == 0 ? nullptr : (dev ? reinterpret_cast<const unsigned char*>(xyz_all) : ctx->d_xyz.p);
     std::vector<Job> jobs(n_clouds);
     for (int c = 0; c < n_clouds; c++) { jobs[c].cloud = c; jobs[c].rq = *req; }
-    int rc = run_jobs(ctx, cs, jobs, nullptr, nullptr, nullptr, false);
+    int rc = run_jobs(ctx, cs, jobs, nullptr, nullptr, nullptr, ctx->debug_keep_batch);
     ctx->copy_pieces = 0;
     if (rc) return rc;
     for (int c = 0; c < n_clouds; c++) fill_best(ctx, jobs[c], ctx->h_results.p[c], 0, 0, &best_per_cloud[c]);
@@ -1391,9 +1496,9 @@ extern "C" int haf_debug_tensor_inputs(haf_ctx* ctx, float* x, int cap) {
     const int W = std::min<int>(cap, (int)ctx->last_W);
     if (W <= 0) return 0;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    std::vector<uint16_t> hh((size_t)W * ctx->Krow), ll((size_t)W * ctx->Krow);
+    std::vector<uint16_t> hh((size_t)W * ctx->Krow), ll((size_t)W * ctx->Krow, 0);   // lo = 0 where the contraction reads hi only
     CUDA_TRY(ctx, cudaMemcpy(hh.data(), ctx->d_Xh.p, hh.size() * 2, cudaMemcpyDeviceToHost));
-    CUDA_TRY(ctx, cudaMemcpy(ll.data(), ctx->d_Xl.p, ll.size() * 2, cudaMemcpyDeviceToHost));
+    if (ctx->tc_passes >= 3) CUDA_TRY(ctx, cudaMemcpy(ll.data(), ctx->d_Xl.p, ll.size() * 2, cudaMemcpyDeviceToHost));
     for (int w = 0; w < W; w++)
         for (int d = 0; d < ctx->D; d++) x[(size_t)w * ctx->D + d] = h16f(hh[(size_t)w * ctx->Krow + d]) + h16f(ll[(size_t)w * ctx->Krow + d]);
     return W;

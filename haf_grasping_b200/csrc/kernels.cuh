@@ -133,6 +133,58 @@ __global__ void __launch_bounds__(256) bin_maxz_kernel(const unsigned char* __re
 // (racy) shared loads/stores: whatever value survives a race was also sent to global memory by its writer, so it never
 // exceeds the true maximum and skipping stays safe; with ~30 points per cell only the few running maxima reach L2.
 // grid = (n_clouds, unit groups, slices of the cloud), block = 1024, dynamic smem = units_per_group * G * G * 4 bytes.
+//
+// Round 2 (the kernel was instruction-bound: ~75 instructions per (point, unit), ncu issue slots 86 %):
+//   * z row hoisted: rows 0-1 of mat_transform change with the roll, row 2 does not (S * Rroll leaves row 2 = (0, 0, 1, 0)
+//     of the approach-vector transform untouched), so the transformed z of a point is computed once per run of units whose
+//     row 2 is BITWISE the same as the previous unit's (checked here on the staged matrices, not assumed);
+//   * VEC = 4 points per thread, fetched as three 128-bit loads where the slice is 16-byte aligned (packed xyz, stride 12):
+//     the unit loop is outermost per group of four points, so each unit's matrix rows are read from shared memory once per
+//     four points instead of once per point.
+template <int VEC>
+__device__ __forceinline__ void bin_points_into_units(const float (&x)[VEC], const float (&y)[VEC], const float (&z)[VEC], int npts, int nu, int GG, int G,
+                                                      float r, const float (*sM)[12], const int* sFlags, unsigned* s_bound,
+                                                      unsigned* __restrict__ gk /*keys of unit ub*/, unsigned long long* __restrict__ clamp_count) {
+    const float nr = -r;
+    float tz[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; k++) tz[k] = 0.0f;
+    for (int u = 0; u < nu; u++) {
+        const int fl = sFlags[u];
+        if (fl & 2) {   // row 2 differs from the previous unit's (always true for the first unit)
+            const float4 m2 = *reinterpret_cast<const float4*>(sM[u] + 8);
+#pragma unroll
+            for (int k = 0; k < VEC; k++)
+                tz[k] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m2.x, x[k]), __fmul_rn(m2.y, y[k])), __fmul_rn(m2.z, z[k])), m2.w);
+        }
+        if (!(fl & 1)) continue;   // inactive unit (roll outside [roll_begin, roll_limit))
+        const float4 m0 = *reinterpret_cast<const float4*>(sM[u]), m1 = *reinterpret_cast<const float4*>(sM[u] + 4);
+#pragma unroll
+        for (int k = 0; k < VEC; k++) {
+            if (k >= npts) break;
+            // pcl::transformPointCloud, left-to-right float arithmetic, no FMA (server.cpp:488)
+            const float tx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m0.x, x[k]), __fmul_rn(m0.y, y[k])), __fmul_rn(m0.z, z[k])), m0.w);
+            const float ty = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m1.x, x[k]), __fmul_rn(m1.y, y[k])), __fmul_rn(m1.z, z[k])), m1.w);
+            if (tx > nr && tx < r && ty > nr && ty < r && tz[k] > -1.0f) {  // strict (server.cpp:510-511); false for NaN; `grid < z`, grid >= -1 (:515-518)
+                int ix = (int)floorf(__fmul_rn(100.0f, __fadd_rn(tx, r)));  // :513
+                int iy = (int)floorf(__fmul_rn(100.0f, __fadd_rn(ty, r)));  // :514
+                if (ix < 0 || ix > G - 1 || iy < 0 || iy > G - 1) {
+                    atomicAdd(clamp_count, 1ull);
+                    ix = max(0, min(G - 1, ix));
+                    iy = max(0, min(G - 1, iy));
+                }
+                const int cell = ix * G + iy;
+                const unsigned key = fkey(tz[k]);
+                volatile unsigned* b = s_bound + u * GG + cell;
+                if (key > *b) {
+                    *b = key;
+                    atomicMax(gk + (size_t)u * GG + cell, key);
+                }
+            }
+        }
+    }
+}
+template <int VEC>
 __global__ void __launch_bounds__(1024, 1) bin_maxz_cloud_kernel(const unsigned char* __restrict__ xyz, size_t stride_bytes,
                                                                  const long long* __restrict__ pt_off,
                                                                  const int* __restrict__ cloud_unit_begin,
@@ -140,8 +192,8 @@ __global__ void __launch_bounds__(1024, 1) bin_maxz_cloud_kernel(const unsigned 
                                                                  unsigned* __restrict__ grid_keys, int G, float r, int units_per_group,
                                                                  unsigned long long* __restrict__ clamp_count) {
     extern __shared__ unsigned s_bound[];  // [units_per_group][G*G]
-    __shared__ float sM[16][12];
-    __shared__ int sActive[16];
+    __shared__ __align__(16) float sM[16][12];
+    __shared__ int sFlags[16];             // bit 0: unit active; bit 1: row 2 of M differs bitwise from the previous unit's
     const int c = blockIdx.x;
     long long p0 = pt_off[c], p1 = pt_off[c + 1];
     {   // blockIdx.z: contiguous slice of the cloud (several CTAs per cloud when there are few clouds)
@@ -155,37 +207,39 @@ __global__ void __launch_bounds__(1024, 1) bin_maxz_cloud_kernel(const unsigned 
     const int nu = ue - ub, GG = G * G;
     for (int t = threadIdx.x; t < nu * GG; t += blockDim.x) s_bound[t] = HAF_KEY_MINUS_ONE;
     for (int t = threadIdx.x; t < nu * 12; t += blockDim.x) sM[t / 12][t % 12] = units[ub + t / 12].M[t % 12];
-    for (int t = threadIdx.x; t < nu; t += blockDim.x) sActive[t] = units[ub + t].cloud >= 0;
     __syncthreads();
-    const float nr = -r;
-    for (long long p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
-        const float* q = reinterpret_cast<const float*>(xyz + (size_t)p * stride_bytes);
-        const float x = __ldg(q), y = __ldg(q + 1), z = __ldg(q + 2);
-        for (int u = 0; u < nu; u++) {
-            if (!sActive[u]) continue;
-            const float* m = sM[u];
-            // pcl::transformPointCloud, left-to-right float arithmetic, no FMA (server.cpp:488)
-            const float tx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[0], x), __fmul_rn(m[1], y)), __fmul_rn(m[2], z)), m[3]);
-            const float ty = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[4], x), __fmul_rn(m[5], y)), __fmul_rn(m[6], z)), m[7]);
-            if (tx > nr && tx < r && ty > nr && ty < r) {  // strict (server.cpp:510-511); false for NaN
-                int ix = (int)floorf(__fmul_rn(100.0f, __fadd_rn(tx, r)));  // :513
-                int iy = (int)floorf(__fmul_rn(100.0f, __fadd_rn(ty, r)));  // :514
-                if (ix < 0 || ix > G - 1 || iy < 0 || iy > G - 1) {
-                    atomicAdd(clamp_count, 1ull);
-                    ix = max(0, min(G - 1, ix));
-                    iy = max(0, min(G - 1, iy));
-                }
-                const int cell = ix * G + iy;
-                const float tz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[8], x), __fmul_rn(m[9], y)), __fmul_rn(m[10], z)), m[11]);
-                if (tz > -1.0f) {
-                    const unsigned key = fkey(tz);
-                    volatile unsigned* b = s_bound + u * GG + cell;
-                    if (key > *b) {
-                        *b = key;
-                        atomicMax(grid_keys + (size_t)(ub + u) * GG + cell, key);
-                    }
-                }
-            }
+    for (int t = threadIdx.x; t < nu; t += blockDim.x) {
+        bool diff = t == 0;
+        if (t > 0)
+            for (int k = 8; k < 12; k++) diff = diff || (__float_as_uint(sM[t][k]) != __float_as_uint(sM[t - 1][k]));
+        sFlags[t] = (units[ub + t].cloud >= 0 ? 1 : 0) | (diff ? 2 : 0);
+    }
+    __syncthreads();
+    unsigned* gk = grid_keys + (size_t)ub * GG;
+    if (VEC == 4 && stride_bytes == 12) {
+        // head: points up to the first 16-byte aligned one; body: groups of four points = three 128-bit loads; tail: the rest
+        const unsigned char* base = xyz + (size_t)p0 * 12;
+        long long head = 0;
+        while (head < p1 - p0 && ((reinterpret_cast<uintptr_t>(base) + (size_t)head * 12) & 15)) head++;   // <= 3
+        const long long ngroups = (p1 - p0 - head) / 4;
+        const float4* q4 = reinterpret_cast<const float4*>(base + (size_t)head * 12);
+        for (long long g = threadIdx.x; g < ngroups; g += blockDim.x) {
+            const float4 a = __ldg(q4 + 3 * g), b = __ldg(q4 + 3 * g + 1), d = __ldg(q4 + 3 * g + 2);
+            const float x[4] = {a.x, a.w, b.z, d.y}, y[4] = {a.y, b.x, b.w, d.z}, z[4] = {a.z, b.y, d.x, d.w};
+            bin_points_into_units<4>(x, y, z, 4, nu, GG, G, r, sM, sFlags, s_bound, gk, clamp_count);
+        }
+        const long long ntail = (p1 - p0) - ngroups * 4;   // head + tail points, one per thread
+        if (threadIdx.x < ntail) {
+            const long long p = threadIdx.x < head ? p0 + threadIdx.x : p0 + head + ngroups * 4 + (threadIdx.x - head);
+            const float* q = reinterpret_cast<const float*>(xyz + (size_t)p * 12);
+            const float x[1] = {__ldg(q)}, y[1] = {__ldg(q + 1)}, z[1] = {__ldg(q + 2)};
+            bin_points_into_units<1>(x, y, z, 1, nu, GG, G, r, sM, sFlags, s_bound, gk, clamp_count);
+        }
+    } else {
+        for (long long p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
+            const float* q = reinterpret_cast<const float*>(xyz + (size_t)p * stride_bytes);
+            const float x[1] = {__ldg(q)}, y[1] = {__ldg(q + 1)}, z[1] = {__ldg(q + 2)};
+            bin_points_into_units<1>(x, y, z, 1, nu, GG, G, r, sM, sFlags, s_bound, gk, clamp_count);
         }
     }
 }
@@ -349,8 +403,12 @@ __global__ void __launch_bounds__(256) mask_windows_kernel(const float* __restri
         for (int k = 0; k < 16; k++)
             for (int w = 0; w < 8; w++) { s_off[k][w] = run; run += s_cnt[k][w]; }
         unsigned base = run ? atomicAdd(win_count, run) : 0u;
-        if (run) atomicAdd(unit_windows + u, run);   // windows of this unit (n_windows_scored); one atomic per CTA
-        if (base + run > win_cap) { *overflow_flag = 1; base = 0xFFFFFFFFu; }
+        // overflow (an internal bound bug: window_bound() is an upper bound): the CTA takes its addition back, so that
+        // *win_count never ends above win_cap -- every consumer indexes its buffers with it -- and the call fails on the flag.
+        // (While an overflowing addition is in place the counter is > win_cap, so later CTAs fail as well: the successful
+        // spans stay a contiguous prefix.)
+        if (base + run > win_cap) { *overflow_flag = 1; atomicSub(win_count, run); base = 0xFFFFFFFFu; }
+        else if (run) atomicAdd(unit_windows + u, run);   // windows of this unit (n_windows_scored); one atomic per CTA
         s_base = base;
     }
     __syncthreads();
@@ -596,13 +654,27 @@ __device__ __forceinline__ float fast_tier_value(PtrT I, int idx0, const FastTab
 // 6-digit "%g" rounding (<= 5e-6 relative: the largest input error of this tier, tools/dec_error_probe.py) is skipped.
 // Raw feature values are the same bit-exact floats as everywhere else.
 // (Tables in __constant__ memory were tried and were 1.8x SLOWER: 36 KB of tables thrash the constant cache.)
+// the six extra operand columns of a window row (svm_tc.cuh, OPERAND FORMAT): -|x|^2 / 2 as three fp16 terms, then 1 1 1.
+// The splits are exact in FP32 (each remainder has fewer significant bits than its predecessor).
+__device__ __forceinline__ void write_aug_columns(__half* __restrict__ row_aug, float sq, bool ok) {
+    const float a = -0.5f * sq;
+    const __half h = __float2half_rn(a);
+    const float r1 = a - __half2float(h);
+    const __half m = __float2half_rn(r1);
+    const __half l = __float2half_rn(r1 - __half2float(m));
+    const __half one = __float2half_rn(ok ? 1.0f : 0.0f);   // a window outside the fp16 range takes the exact path: keep its row finite
+    row_aug[0] = h; row_aug[1] = m; row_aug[2] = l;
+    row_aug[3] = one; row_aug[4] = one; row_aug[5] = one;
+}
+
 #define HAF_FT_WT 2
 #define HAF_FT_KPASS 96   // dimensions per pass of the shared-memory tile: 192 B = 6 whole sectors of a row of Xh / Xl
 __global__ void __launch_bounds__(256, 4) features_tc_kernel(const float* __restrict__ integral, const int2* __restrict__ win,
                                                              const unsigned* __restrict__ win_count, int G, int unit_base,
                                                              const DimFeat* __restrict__ table, int D, int Krow, float lower,
                                                              int emulate_text, const Round4Tab* __restrict__ rtab,
-                                                             __half* __restrict__ Xh, __half* __restrict__ Xl, float* __restrict__ xn) {
+                                                             __half* __restrict__ Xh, __half* __restrict__ Xl /*NULL: hi only*/, float* __restrict__ xn,
+                                                             int aug0 /*first of the six extra operand columns (svm_tc.cuh)*/) {
     constexpr int WT = HAF_FT_WT, NW = 32 * WT;
     extern __shared__ uint32_t s_words[];  // tile [NW][KPASS+1] of (hi | lo << 16); then float s_int[ROWS][ld .. ld + 31]
     const unsigned W = *win_count;
@@ -781,12 +853,12 @@ __global__ void __launch_bounds__(256, 4) features_tc_kernel(const float* __rest
             if (ww >= W) break;
             const uint32_t* sw = s_words + wi * rs;
             uint32_t* gh = reinterpret_cast<uint32_t*>(Xh + (size_t)ww * Krow + d0);
-            uint32_t* gl = reinterpret_cast<uint32_t*>(Xl + (size_t)ww * Krow + d0);
+            uint32_t* gl = Xl ? reinterpret_cast<uint32_t*>(Xl + (size_t)ww * Krow + d0) : nullptr;   // one / two products: hi only
             for (int e = lane; e < KP / 2; e += 32) {
                 const int blk = (e >> 5) << 6, nbh = min(64, KP - blk) >> 1;
                 const uint32_t a0 = sw[blk + (e & 31)], a1 = sw[blk + nbh + (e & 31)];   // dims 2e, 2e+1: (hi | lo << 16)
                 gh[e] = __byte_perm(a0, a1, 0x5410);     // hi(2e) | hi(2e+1) << 16
-                gl[e] = __byte_perm(a0, a1, 0x7632);     // lo(2e) | lo(2e+1) << 16
+                if (gl) gl[e] = __byte_perm(a0, a1, 0x7632);     // lo(2e) | lo(2e+1) << 16
             }
         }
     }
@@ -801,7 +873,10 @@ __global__ void __launch_bounds__(256, 4) features_tc_kernel(const float* __rest
         float sq = 0.0f;
 #pragma unroll
         for (int k = 0; k < 8; k++) sq += s_nrm[k * NW + threadIdx.x];
-        xn[w0 + threadIdx.x] = (sq < 3.0e38f) ? sq : __int_as_float(0x7f800000);
+        // -|x|^2 / 2 has to fit the fp16 extra columns as well (|x|^2 / 2 <= 65504)
+        const bool ok = sq < 1.3e5f;
+        xn[w0 + threadIdx.x] = ok ? sq : __int_as_float(0x7f800000);
+        write_aug_columns(Xh + (size_t)(w0 + threadIdx.x) * Krow + aug0, ok ? sq : 0.0f, ok);
     }
 }
 
@@ -1113,6 +1188,8 @@ struct Guard2Args {
     unsigned* tickets;           // [cap / WB + 1], zero on entry, left zero
     double tol2;
     int* list2; unsigned* list2_count;   // tier-3 list
+    const double* dec_tc;        // audit: the contraction's decision value of every listed window (NaN = not comparable) or NULL
+    unsigned* audit_max;         // audit: max over listed windows of |dec_tc - dec_fp64| / (E + |rho|), as float bits
 };
 __global__ void __launch_bounds__(256) guard_inputs_kernel(const ExactArgs A, const Guard2Args Q) {
     const unsigned n = min(*Q.list_count, (unsigned)Q.cap);
@@ -1235,6 +1312,11 @@ __global__ void __launch_bounds__(256) guard_fma_kernel(const ExactArgs A, const
                 Q.accum[(size_t)e * 2] = 0.0; Q.accum[(size_t)e * 2 + 1] = 0.0;
                 const int w = Q.list[e];
                 const double dv = sum - A.rho;
+                if (Q.dec_tc) {   // audit of the FP32 / tensor contraction against this FP64 value, in the guard band's own unit
+                    const double tcv = Q.dec_tc[w];
+                    const float rel = (float)(fabs(tcv - dv) / (E + fabs(A.rho)));
+                    if (rel == rel) atomicMax(Q.audit_max, __float_as_uint(rel));
+                }
                 A.dec[w] = dv;
                 if (!(fabs(dv) > Q.tol2 * (E + fabs(A.rho)))) Q.list2[atomicAdd(Q.list2_count, 1u)] = w;
             }
@@ -1393,10 +1475,13 @@ __global__ void copy_params_kernel(const uint4* __restrict__ src_host, uint4* __
     for (; i < n16; i += stride) dst[i] = src_host[i];
 }
 
-// counters: [0] windows of this chunk, [1] guard windows, [6] exact-order windows of this chunk -> running totals in [8], [9], [11]
+// counters: [0] windows of this chunk, [1] guard list entries, [13] of which audit-only, [6] exact-order windows of this chunk
+// -> running totals in [8], [9] (guard band), [14] (audit only), [11]; [12] = audit maximum (float bits, whole call)
 __global__ void accumulate_counts_kernel(unsigned* cnt) {
     cnt[8] += cnt[0];
-    cnt[9] += cnt[1];
+    cnt[9] += cnt[1] - cnt[13];   // [1] counts the audit sample too; [13] = listed windows outside the guard band (audit only)
+    cnt[14] += cnt[13];
+    cnt[13] = 0;
     cnt[11] += cnt[6];   // windows that went on to the exact-order kernels (tier 3)
     cnt[6] = 0;
 }
@@ -1418,7 +1503,7 @@ __global__ void csr_to_dense_kernel(const long long* __restrict__ row_ptr, const
 // SVM operands of given inputs: tensor mode (Xh != NULL): fp16 hi/lo rows [row][Krow] + ||x||^2 of the float values;
 // SIMT mode (Xf != NULL): feature-major floats [Kpad][ldx] + ||x||^2.  One warp per row.
 __global__ void __launch_bounds__(256) pack_svm_inputs_kernel(const double* __restrict__ dense, int n_rows, int width, int Krow,
-                                                              __half* __restrict__ Xh, __half* __restrict__ Xl, float* __restrict__ Xf,
+                                                              __half* __restrict__ Xh, __half* __restrict__ Xl /*NULL: hi only*/, float* __restrict__ Xf,
                                                               size_t ldx, int Kpad, float* __restrict__ xn) {
     const int lane = threadIdx.x & 31;
     const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -1432,7 +1517,7 @@ __global__ void __launch_bounds__(256) pack_svm_inputs_kernel(const double* __re
             const __half hi = __float2half_rn(xc);
             const __half lo = __float2half_rn(xc - __half2float(hi));
             Xh[(size_t)r * Krow + d] = hi;
-            Xl[(size_t)r * Krow + d] = lo;
+            if (Xl) Xl[(size_t)r * Krow + d] = lo;
             const float v = __half2float(hi) + __half2float(lo);
             sq = fmaf(v, v, sq);
             if (!(fabsf(xf) < 65504.0f)) sq = __int_as_float(0x7f800000);   // clamped or NaN: force the exact path
@@ -1443,7 +1528,12 @@ __global__ void __launch_bounds__(256) pack_svm_inputs_kernel(const double* __re
     }
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-    if (lane == 0) xn[r] = sq;
+    __syncwarp();   // the zeros the lanes wrote into the extra columns above come first
+    if (lane == 0) {
+        const bool ok = !Xh || sq < 1.3e5f;
+        xn[r] = ok ? sq : __int_as_float(0x7f800000);
+        if (Xh) write_aug_columns(Xh + (size_t)r * Krow + width, ok ? sq : 0.0f, ok);   // extra operand columns (svm_tc.cuh)
+    }
 }
 // predicted label per row: dec > 0 ? label[0] : label[1]   (svm.cpp:2516-2531)
 __global__ void labels_from_dec_kernel(const double* __restrict__ dec, int n, double l0, double l1, double* __restrict__ labels) {

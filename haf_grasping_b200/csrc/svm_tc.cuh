@@ -2,29 +2,40 @@
 //
 //   dec[w] = sum_n coef[n] * exp2(c * (||x_w||^2 + ||sv_n||^2 - 2 x_w . sv_n)) - rho,     c = -gamma * log2(e)
 //
+// OPERAND FORMAT (round 2).  The K-major fp16 rows of X and SV carry six extra columns behind the Dsv dimensions
+// (there is room: Krow is padded to 16 anyway):
+//      X  row w : [ x_0 .. x_{Dsv-1} | a_hi a_mid a_lo | 1 1 1 | 0 .. ]      a = -||x_w||^2 / 2   (three fp16 terms, 33 bits)
+//      SV row n : [ s_0 .. s_{Dsv-1} | 1    1     1    | b_hi b_mid b_lo | 0 .. ]      b = -||sv_n||^2 / 2
+// so that ONE accumulator element is  acc = x.sv - (||x||^2 + ||sv||^2) / 2 = -d^2 / 2  and the epilogue is
+// FMUL (c2 = -2c), MUFU.EX2, FFMA per element -- the per-element FADD/FFMA that assembled the exponent, the clamp and the
+// LDS.64 of {c|sv|^2, coef} of round 1 are gone (the one-product kernel was bound by exactly those instructions and by
+// the MUFU pipe).  FP32 accumulation of the extra columns is what the epilogue's fmaf did before: same error
+// (tools/aug_format_check.py).  The lo operand arrays (passes >= 2) hold zeros in the extra columns.
+// Support vectors are stored SORTED BY THE SIGN OF coef, each sign group padded to a whole tile of 256: inside a tile
+// sum |coef_i| K_i = |sum coef_i K_i|, so the guard scale needs no second accumulator per element.
+//
 // x and sv are split into two fp16 terms (x = x_hi + x_lo, 22 significant bits together, absolute floor 2^-25);
-// the contraction is three tensor-core products accumulated in FP32 in TMEM:  x_hi.sv_hi + x_hi.sv_lo + x_lo.sv_hi
-// (the dropped x_lo.sv_lo term is ~2^-24 relative).  Round 1 used bf16 pairs (16 bits): same cost, 30x the error.
+// the contraction is up to three tensor-core products accumulated in FP32 in TMEM:  x_hi.sv_hi + x_hi.sv_lo + x_lo.sv_hi
+// (the dropped x_lo.sv_lo term is ~2^-24 relative).
 //
 // PASSES.  The error of a term is K_i times gamma times the error of the dot product, so for a model with a small
 // gamma (libsvm's default 1 / n_features) the cross terms change the decision value by less than the FP32 epilogue
 // does.  `passes` = 3 (all three products), 2 (x_hi.(sv_hi + sv_lo): x rounded to fp16) or 1 (x_hi.sv_hi only) is chosen
 // per model at haf_create from a calibration of each scheme's operand error against the guard scale (hafgpu.cu,
-// calibrate_tensor_passes); the guard band is widened by the calibrated error.  The error of the resulting decision value
-// is measured in the tests and is far inside the guard band; windows inside the band are re-evaluated in FP64 (FMA tier,
-// then libsvm's own order), so labels equal the reference's (svm.cpp:2459-2533).
+// calibrate_tensor_passes); the guard band is widened by the calibrated error, and every call audits the choice against
+// the FP64 re-evaluation of its own guard-band and sample windows (hafgpu.cu, "audit").  Windows inside the band are
+// re-evaluated in FP64 (FMA tier, then libsvm's own order), so labels equal the reference's (svm.cpp:2459-2533).
 //
-// Kernel structure (one persistent CTA per SM, 192 threads, warp specialised):
-//   warp 0   TMA producer : cp.async.bulk.tensor 2D loads of the four operand tiles of a k-block into a
-//                           2-stage shared-memory ring (128B-swizzled, K-major): X_hi, X_lo [128 x 64] and
-//                           SV_hi, SV_lo [256 x 64] fp16 = 96 KB per stage, mbarrier complete_tx.
-//   warp 1   MMA issuer   : one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=256, K=16),
-//                           3 products x 4 k-slices per stage, into one of two 128x256 FP32 accumulators in TMEM
-//                           (512 columns = all of TMEM); tcgen05.commit releases the smem stage / publishes the
-//                           accumulator.
-//   warps 2-5 epilogue    : tcgen05.ld 32x32b (thread = window row, registers = 32 SV columns), fused
-//                           exp2 / coef / row-sum, FP64 accumulation across SV tiles; overlaps the next tile's MMAs.
-// Work item = (window tile of 128, split of the SV tiles); small problems split the SV range over CTAs.
+// Kernels:
+//   svm_rbf_tc3_kernel (default where passes == 1 and Krow <= 512): CTA pair (cta_group::2), the pair's X tiles RESIDENT
+//       in shared memory across the SV tiles, SV half tiles streamed through a TMA ring, eight epilogue warps.
+//   svm_rbf_tc2_kernel : CTA pair, X and SV both streamed (passes 2 / 3, very wide models).
+//   svm_rbf_tc_kernel  : single CTA (cta_group::1), kept as the reference point.
+// Common structure: one persistent CTA per SM, warp specialised: warp 0 = TMA producer (cp.async.bulk.tensor 2D,
+// 128B-swizzled K-major tiles, mbarrier complete_tx), warp 1 = one elected thread issuing tcgen05.mma.kind::f16 into one
+// of two 128x256 (256x256 per pair) FP32 accumulators in TMEM (all 512 columns) and tcgen05.commit, the other warps =
+// epilogue (tcgen05.ld 32x32b, thread = window row, fused exp2 / coef / row sum, FP64 accumulation across SV tiles)
+// overlapping the next tile's MMAs.  Work item = (window tile / tile pair, split of the SV tiles).
 #pragma once
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -36,13 +47,14 @@ namespace haftc {
 constexpr int BM = 128;      // windows per tile (UMMA M)
 constexpr int BN = 256;      // support vectors per tile (UMMA N)
 constexpr int BK = 64;       // fp16 elements per k-block = 128 bytes = one swizzle row
+constexpr int NAUG = 6;      // extra operand columns (see OPERAND FORMAT)
 constexpr int STAGES = 2;
 constexpr int A_TILE_BYTES = BM * BK * 2;   // 16 KB
 constexpr int B_TILE_BYTES = BN * BK * 2;   // 32 KB
 constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;  // 96 KB
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int THREADS = 192;
-constexpr int TAB_SMEM_MAX = 4096;   // support vectors whose {c|sv|^2, coef} fit next to the operand ring (8 B each)
+constexpr int TAB_SMEM_MAX = 4096;   // support vectors whose coef fits next to the operand ring (4 B each)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -100,25 +112,26 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
-// entry k of the current SV tile's table: broadcast LDS from the staged copy, or a per-thread global load
-__device__ __forceinline__ float2 tab_entry(uint32_t tab_s, const float2* __restrict__ tab, int k) {
-    float2 t;
-    if (tab_s) asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(t.x), "=f"(t.y) : "r"(tab_s + 8u * (uint32_t)k));
-    else t = __ldg(tab + k);
+// coef of four consecutive support vectors of the current tile: one broadcast LDS.128 from the staged copy (one
+// wavefront for four columns), or a 16-byte global load when the model has more support vectors than fit (tab_s == 0)
+__device__ __forceinline__ float4 coef4(uint32_t tab_s, const float* __restrict__ tab, int k) {
+    float4 t;
+    if (tab_s) asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "r"(tab_s + 4u * (uint32_t)k));
+    else t = __ldg(reinterpret_cast<const float4*>(tab + k));
     return t;
 }
 
-// 32 accumulator columns of one window row: exp2 / coef / row sums  (k0 = first column of the chunk within the SV tile)
-__device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], uint32_t tab_s, const float2* __restrict__ tab, int k0,
-                                               float c2, float u, float& ps, float& pa) {
+// 32 accumulator columns of one window row: acc = -d^2 / 2 straight out of the contraction (OPERAND FORMAT), so an
+// element costs FMUL, MUFU.EX2, FFMA (k0 = first column of the chunk within the SV tile).  No clamp: rounding can leave
+// acc a few ulps above 0 for x == sv, which makes K a few ulps above 1 -- inside the FP32 error the guard band covers.
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], uint32_t tab_s, const float* __restrict__ tab, int k0, float c2, float& ps) {
 #pragma unroll
-    for (int j = 0; j < 32; j++) {
-        const float2 t = tab_entry(tab_s, tab, k0 + j);
-        float arg = fmaf(__uint_as_float(r[j]), c2, u + t.x);  // c * (xn + svn - 2 dot)
-        arg = fminf(arg, 0.0f);                                // d^2 >= 0
-        const float e = ex2_approx(arg);
-        ps = fmaf(t.y, e, ps);
-        pa = fmaf(fabsf(t.y), e, pa);                          // sum |coef| K
+    for (int j = 0; j < 32; j += 4) {
+        const float4 cf = coef4(tab_s, tab, k0 + j);
+        ps = fmaf(cf.x, ex2_approx(__uint_as_float(r[j]) * c2), ps);
+        ps = fmaf(cf.y, ex2_approx(__uint_as_float(r[j + 1]) * c2), ps);
+        ps = fmaf(cf.z, ex2_approx(__uint_as_float(r[j + 2]) * c2), ps);
+        ps = fmaf(cf.w, ex2_approx(__uint_as_float(r[j + 3]) * c2), ps);
     }
 }
 
@@ -132,23 +145,50 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], uint32_t
                    "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]) \
                  : "r"(taddr))
 
-// svtab[n] = { c * ||sv_n||^2 , coef_n }  (padding SVs: coef = 0).  dec_acc / asum_acc must be zeroed before launch.
+// NCOLS accumulator columns (a multiple of 64) of this thread's window row, starting at TMEM address taddr0 / table entry
+// k0: returns sum_j coef_j K_j over them.  Two 32-column chunks in flight: the TMEM load of the next chunk is issued
+// before the current one is evaluated (tcgen05.wait::ld covers every load issued so far).
+template <int NCOLS>
+__device__ __forceinline__ float epilogue_columns(uint32_t taddr0, uint32_t tab_s, const float* __restrict__ tab, int k0, float c2) {
+    float ps = 0.0f;
+    uint32_t ra[32], rb[32];
+    HAFTC_LD32(taddr0, ra);
+#pragma unroll 1
+    for (int ch = 0; ch < NCOLS / 32; ch += 2) {
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        HAFTC_LD32(taddr0 + (ch + 1) * 32, rb);
+        epilogue_chunk(ra, tab_s, tab, k0 + ch * 32, c2, ps);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (ch + 2 < NCOLS / 32) HAFTC_LD32(taddr0 + (ch + 2) * 32, ra);
+        epilogue_chunk(rb, tab_s, tab, k0 + (ch + 1) * 32, c2, ps);
+    }
+    return ps;
+}
+
+// stage the coef table of the model (n entries) in shared memory at tab_base
+__device__ __forceinline__ void stage_coef_table(uint32_t tab_base, const float* __restrict__ svcoef, int n, int nthreads) {
+    for (int k = threadIdx.x * 4; k < n; k += nthreads * 4) {   // n is a multiple of BN
+        const float4 t = __ldg(reinterpret_cast<const float4*>(svcoef + k));
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(tab_base + 4u * (uint32_t)k), "f"(t.x), "f"(t.y), "f"(t.z), "f"(t.w) : "memory");
+    }
+}
+
+// svcoef[n] = coef_n in the tensor path's own order (sorted by sign, each group padded to a tile; padding: coef = 0 and an
+// all-zero operand row).  dec_acc / asum_acc must be zeroed before launch.
 // tab_smem != 0: the whole table (n_ntiles * BN entries, <= TAB_SMEM_MAX) is copied to shared memory once per CTA and the
-// epilogue reads it with broadcast LDS (one wavefront per entry); read per thread from global memory the same entries
-// cost 2-4 wavefronts each and took a quarter to a half of the LSU data pipe next to the TMA traffic.
+// epilogue reads it with broadcast LDS.128.
 //
-// GUARD SCALE.  Next to the decision sum the epilogue accumulates  sum_i |coef_i| K_i  and scales it to
+// GUARD SCALE.  Next to the decision sum the epilogue accumulates  sum_i |coef_i| K_i  = sum over tiles of |tile sum|
+// (tiles are uniform in the sign of coef) and scales it to
 // E = (1 + |c| (||x||^2 + max_n ||sv_n||^2)) sum_i |coef_i| K_i  >=  sum_i |coef_i| K_i (1 + |c| (||x||^2 + ||sv_i||^2))
-// (csvn_max = |c| max_n ||sv_n||^2 is a model constant; weighting every term by its own ||sv_i||^2 cost two more FP32
-// instructions per element and put the epilogue, not the MMAs, on the critical path: tensor pipe 98 % -> 89 %):
-// a term's FP32 error is K_i times the absolute error of its exponent argument, which grows with the magnitude of the
-// three numbers the argument is assembled from (c xn, c svn, -2 c dot; |2 dot| <= xn + svn) -- a flat fraction of
+// (csvn_max = |c| max_n ||sv_n||^2 is a model constant): a term's FP32 error is K_i times the absolute error of its
+// exponent argument, which grows with the magnitude of the numbers the argument is assembled from -- a flat fraction of
 // sum |coef| K under-estimates it by that factor for models with a large gamma (measured: tools/dec_error_probe.py).
-// Windows with |dec| <= guard_rel * (E + |rho|) are re-evaluated by the FP64 exact path.
+// Windows with |dec| <= guard_rel * (E + |rho|) are re-evaluated by the FP64 guard tiers.
 __global__ void __launch_bounds__(THREADS, 1)
 svm_rbf_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl,
                   const __grid_constant__ CUtensorMap tmSh, const __grid_constant__ CUtensorMap tmSl,
-                  const float* __restrict__ xn, const float2* __restrict__ svtab, float c, const unsigned* __restrict__ win_count,
+                  const float* __restrict__ xn, const float* __restrict__ svcoef, float c, const unsigned* __restrict__ win_count,
                   int n_ntiles, int nsplit, int kblocks, int last_slices, double* __restrict__ dec_acc, float* __restrict__ asum_acc, int tab_smem, float csvn_max, int passes) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // 128B swizzle needs 1024-byte aligned tiles
@@ -158,13 +198,9 @@ svm_rbf_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constan
     const uint32_t bar_tfull = bar_base + 16 * STAGES;  // [2]
     const uint32_t bar_tempty = bar_tfull + 16;         // [2]
     const uint32_t tmem_slot = bar_tempty + 16;         // u32
-    const uint32_t tab_base = bar_base + 256;           // float2 [n_ntiles * BN] when tab_smem
+    const uint32_t tab_base = bar_base + 256;           // float [n_ntiles * BN] when tab_smem
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (tab_smem)
-        for (int k = threadIdx.x; k < n_ntiles * BN; k += THREADS) {
-            const float2 t = __ldg(svtab + k);
-            asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(tab_base + 8u * (uint32_t)k), "f"(t.x), "f"(t.y) : "memory");
-        }
+    if (tab_smem) stage_coef_table(tab_base, svcoef, n_ntiles * BN, THREADS);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
@@ -252,31 +288,16 @@ svm_rbf_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constan
                 const uint32_t a = acc_it & 1u, aph = (acc_it >> 1) & 1u;
                 mbar_wait(bar_tfull + 8 * a, aph);
                 tc_fence_after();
-                float ps = 0.0f, pa = 0.0f;
-                const float2* tab = svtab + (size_t)nt * BN;
-                const uint32_t tab_s = tab_smem ? tab_base + (uint32_t)nt * BN * 8u : 0u;
-                // two 32-column chunks in flight: the TMEM load of the next chunk is issued before the current one is
-                // evaluated (tcgen05.wait::ld covers every load issued so far)
-                const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + a * BN;
-                uint32_t ra[32], rb[32];
-                HAFTC_LD32(taddr0, ra);
-#pragma unroll 1
-                for (int ch = 0; ch < BN / 32; ch += 2) {
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    HAFTC_LD32(taddr0 + (ch + 1) * 32, rb);
-                    epilogue_chunk(ra, tab_s, tab, ch * 32, c2, u, ps, pa);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (ch + 2 < BN / 32) HAFTC_LD32(taddr0 + (ch + 2) * 32, ra);
-                    epilogue_chunk(rb, tab_s, tab, (ch + 1) * 32, c2, u, ps, pa);
-                }
+                const uint32_t tab_s = tab_smem ? tab_base + (uint32_t)nt * BN * 4u : 0u;
+                const float ps = epilogue_columns<BN>(tmem_base + ((uint32_t)(q * 32) << 16) + a * BN, tab_s, svcoef + (size_t)nt * BN, 0, c2);
                 tc_fence_before();
                 mbar_arrive(bar_tempty + 8 * a);
                 dsum += (double)ps;
-                asum += (1.0f - u + csvn_max) * pa;   // >= sum_i |coef_i| K_i (1 + |c| (xn + svn_i)): the scale of the FP32 error
+                asum += fabsf(ps);   // = sum |coef_i| K_i of the tile (uniform sign)
             }
             if (m < W && nt1 > nt0) {
                 atomicAdd(dec_acc + m, dsum);
-                atomicAdd(asum_acc + m, asum);
+                atomicAdd(asum_acc + m, (1.0f - u + csvn_max) * asum);   // E: the scale of the FP32 error (GUARD SCALE)
             }
         }
     }
@@ -349,7 +370,7 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 svm_rbf_tc2_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl,
                    const __grid_constant__ CUtensorMap tmSh2, const __grid_constant__ CUtensorMap tmSl2,
-                   const float* __restrict__ xn, const float2* __restrict__ svtab, float c, const unsigned* __restrict__ win_count,
+                   const float* __restrict__ xn, const float* __restrict__ svcoef, float c, const unsigned* __restrict__ win_count,
                    int n_ntiles, int nsplit, int kblocks, int last_slices, double* __restrict__ dec_acc, float* __restrict__ asum_acc, int tab_smem, float csvn_max, int passes) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -359,13 +380,9 @@ svm_rbf_tc2_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_consta
     const uint32_t bar_tfull = bar_base + 16 * STAGES2;   // [2]        (one per CTA)
     const uint32_t bar_tempty = bar_tfull + 16;           // [2]        (used in the leader CTA)
     const uint32_t tmem_slot = bar_tempty + 16;
-    const uint32_t tab_base = bar_base + 256;             // float2 [n_ntiles * BN] when tab_smem
+    const uint32_t tab_base = bar_base + 256;             // float [n_ntiles * BN] when tab_smem
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (tab_smem)
-        for (int k = threadIdx.x; k < n_ntiles * BN; k += THREADS) {
-            const float2 t = __ldg(svtab + k);
-            asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(tab_base + 8u * (uint32_t)k), "f"(t.x), "f"(t.y) : "memory");
-        }
+    if (tab_smem) stage_coef_table(tab_base, svcoef, n_ntiles * BN, THREADS);
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
 
@@ -458,31 +475,16 @@ svm_rbf_tc2_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_consta
                 const uint32_t a = acc_it & 1u, aph = (acc_it >> 1) & 1u;
                 mbar_wait(bar_tfull + 8 * a, aph);
                 tc_fence_after();
-                float ps = 0.0f, pa = 0.0f;
-                const float2* tab = svtab + (size_t)nt * BN;
-                const uint32_t tab_s = tab_smem ? tab_base + (uint32_t)nt * BN * 8u : 0u;
-                // two 32-column chunks in flight: the TMEM load of the next chunk is issued before the current one is
-                // evaluated (tcgen05.wait::ld covers every load issued so far)
-                const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + a * BN;
-                uint32_t ra[32], rb[32];
-                HAFTC_LD32(taddr0, ra);
-#pragma unroll 1
-                for (int ch = 0; ch < BN / 32; ch += 2) {
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    HAFTC_LD32(taddr0 + (ch + 1) * 32, rb);
-                    epilogue_chunk(ra, tab_s, tab, ch * 32, c2, u, ps, pa);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (ch + 2 < BN / 32) HAFTC_LD32(taddr0 + (ch + 2) * 32, ra);
-                    epilogue_chunk(rb, tab_s, tab, (ch + 1) * 32, c2, u, ps, pa);
-                }
+                const uint32_t tab_s = tab_smem ? tab_base + (uint32_t)nt * BN * 4u : 0u;
+                const float ps = epilogue_columns<BN>(tmem_base + ((uint32_t)(q * 32) << 16) + a * BN, tab_s, svcoef + (size_t)nt * BN, 0, c2);
                 tc_fence_before();
                 mbar_arrive_cluster((bar_tempty + 8 * a) & PEER_MASK);  // on the LEADER's barrier (count 256)
                 dsum += (double)ps;
-                asum += (1.0f - u + csvn_max) * pa;   // >= sum_i |coef_i| K_i (1 + |c| (xn + svn_i)): the scale of the FP32 error
+                asum += fabsf(ps);
             }
             if (m < W && nt1 > nt0) {
                 atomicAdd(dec_acc + m, dsum);
-                atomicAdd(asum_acc + m, asum);
+                atomicAdd(asum_acc + m, (1.0f - u + csvn_max) * asum);
             }
         }
     }
@@ -495,19 +497,187 @@ svm_rbf_tc2_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_consta
     }
 }
 
-// dec = sum - rho, guard test (same rule as the SIMT kernel; NaN-safe: anything not provably outside the band is inside)
+// ==================================================================================================================
+// X-RESIDENT CTA-pair kernel, one product per k-slice (the default where the calibration picks passes == 1).
+// With one product svm_rbf_tc2_kernel is bound by the L2 -> shared-memory feed (32 KB per 512 MMA clocks per CTA = 64
+// B/clk/SM against the ~42 B/clk/SM the L2 delivers chip-wide), half of which re-streams the CTA's own X tile for every
+// one of the n_ntiles SV tiles, and by its four epilogue warps.  Here
+//   * the 128 x Krow X_hi tile of the work item stays in shared memory (kblocks x 16 KB) and only the SV half tiles stream
+//     through a ring of 16 KB stages: the feed halves (36 B/clk/SM at the MMA rate);  per-k-block barriers (x_full /
+//     x_empty) let the next item's X tiles arrive while the last SV tile of the current item is still being multiplied;
+//   * eight epilogue warps, two per TMEM lane quarter (one per half of the accumulator's 256 columns): two warps per SM
+//     sub-partition keep the MUFU pipe (16 ex2 per clock per SM: 2048 clocks per 128 x 256 tile against 2688 clocks of
+//     MMAs) busy across each other's TMEM-load and barrier latencies; one mbarrier arrival per warp.
+// ==================================================================================================================
+constexpr int XK_MAX = 8;        // k-blocks of 64 dimensions the resident X tile may have (Krow <= 512)
+constexpr int THREADS3 = 320;    // TMA warp, MMA warp, 8 epilogue warps
+constexpr int TC3_SMEM_LIMIT = 227 * 1024;
+__host__ __device__ constexpr int tc3_smem_bytes(int kblocks, int stages, int tab_entries) {
+    return kblocks * A_TILE_BYTES + stages * B2_TILE_BYTES + 1024 /*align slack*/ + 512 /*barriers*/ + tab_entries * 4;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS3, 1)
+svm_rbf_tc3_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmSh2,
+                   const float* __restrict__ xn, const float* __restrict__ svcoef, float c, const unsigned* __restrict__ win_count,
+                   int n_ntiles, int nsplit, int kblocks, int last_slices, int stages, double* __restrict__ dec_acc, float* __restrict__ asum_acc,
+                   int tab_smem, float csvn_max) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t x_base = smem_base;                                     // [kblocks] X_hi tiles of the current item (16 KB each)
+    const uint32_t ring_base = x_base + (uint32_t)kblocks * A_TILE_BYTES;   // [stages]  SV_hi half tiles
+    const uint32_t bar_base = ring_base + (uint32_t)stages * B2_TILE_BYTES;
+    const uint32_t bar_sfull = bar_base;                  // [16]      (used in the leader CTA)
+    const uint32_t bar_sempty = bar_base + 128;           // [16]      (one per CTA)
+    const uint32_t bar_xfull = bar_base + 256;            // [XK_MAX]  (used in the leader CTA)
+    const uint32_t bar_xempty = bar_base + 320;           // [XK_MAX]  (one per CTA)
+    const uint32_t bar_tfull = bar_base + 384;            // [2]       (one per CTA)
+    const uint32_t bar_tempty = bar_base + 400;           // [2]       (used in the leader CTA)
+    const uint32_t tmem_slot = bar_base + 416;
+    const uint32_t tab_base = bar_base + 512;             // float [n_ntiles * BN] when tab_smem
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (tab_smem) stage_coef_table(tab_base, svcoef, n_ntiles * BN, THREADS3);
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; s++) { mbar_init(bar_sfull + 8 * s, 1); mbar_init(bar_sempty + 8 * s, 1); }
+        for (int k = 0; k < XK_MAX; k++) { mbar_init(bar_xfull + 8 * k, 1); mbar_init(bar_xempty + 8 * k, 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 16); }   // 2 CTAs x 8 epilogue warps
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    const unsigned W = *win_count;
+    const int n_pairs = (int)((W + 2 * BM - 1) / (2 * BM));
+    const int items = n_pairs * nsplit;
+    const int nt_per = (n_ntiles + nsplit - 1) / nsplit;
+    const int cid = (int)cluster_id_x(), ncl = (int)n_clusters_x();
+
+    if (warp == 0) {
+        if (lane == 0) {  // ===== TMA producer (both CTAs) =====
+            uint32_t it = 0, xi = 0;
+            for (int item = cid; item < items; item += ncl) {
+                const int mp = item / nsplit, sp = item - mp * nsplit;
+                const int nt0 = sp * nt_per, nt1 = min(n_ntiles, nt0 + nt_per);
+                if (nt0 >= nt1) continue;   // an empty split touches no barrier in any role
+                const int mrow = (2 * mp + (int)rank) * BM;
+                for (int nt = nt0; nt < nt1; nt++)
+                    for (int kb = 0; kb < kblocks; kb++, it++) {
+                        if (nt == nt0) {   // this item's X tile kb, as soon as the previous item's last SV tile has let go of it
+                            mbar_wait(bar_xempty + 8 * kb, (xi & 1u) ^ 1u);
+                            if (leader) mbar_expect_tx(bar_xfull + 8 * kb, 2 * A_TILE_BYTES);
+                            tma_load_2d_2sm(x_base + (uint32_t)kb * A_TILE_BYTES, &tmXh, kb * BK, mrow, (bar_xfull + 8 * kb) & PEER_MASK);
+                        }
+                        const uint32_t s = it % (uint32_t)stages, ph = (it / (uint32_t)stages) & 1u;
+                        mbar_wait(bar_sempty + 8 * s, ph ^ 1u);
+                        if (leader) mbar_expect_tx(bar_sfull + 8 * s, 2 * B2_TILE_BYTES);
+                        tma_load_2d_2sm(ring_base + s * B2_TILE_BYTES, &tmSh2, kb * BK, nt * BN + (int)rank * (BN / 2), (bar_sfull + 8 * s) & PEER_MASK);
+                    }
+                xi++;
+            }
+        }
+    } else if (warp == 1) {
+        if (leader && lane == 0) {  // ===== MMA issuer (leader CTA only) =====
+            uint32_t it = 0, acc_it = 0, xi = 0;
+            for (int item = cid; item < items; item += ncl) {
+                const int mp = item / nsplit, sp = item - mp * nsplit;
+                const int nt0 = sp * nt_per, nt1 = min(n_ntiles, nt0 + nt_per);
+                if (nt0 >= nt1) continue;
+                for (int nt = nt0; nt < nt1; nt++, acc_it++) {
+                    const uint32_t a = acc_it & 1u, aph = (acc_it >> 1) & 1u;
+                    mbar_wait(bar_tempty + 8 * a, aph ^ 1u);   // both CTAs' epilogue warps have drained this accumulator
+                    tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + a * BN;
+                    for (int kb = 0; kb < kblocks; kb++, it++) {
+                        if (nt == nt0) mbar_wait(bar_xfull + 8 * kb, xi & 1u);   // the item's X tile kb has landed in both CTAs
+                        const uint32_t s = it % (uint32_t)stages, ph = (it / (uint32_t)stages) & 1u;
+                        mbar_wait(bar_sfull + 8 * s, ph);
+                        tc_fence_after();
+                        const uint64_t d_a = make_desc_sw128(x_base + (uint32_t)kb * A_TILE_BYTES);
+                        const uint64_t d_b = make_desc_sw128(ring_base + s * B2_TILE_BYTES);
+                        const int slices = (kb == kblocks - 1) ? last_slices : (BK / 16);
+                        for (int k = 0; k < slices; k++) {
+                            const uint64_t adv = (uint64_t)(k * 2);
+                            tc_mma_2sm(tmem_d, d_a + adv, d_b + adv, IDESC2, (kb | k) ? 1u : 0u);
+                        }
+                        tc_commit_2sm_mc(bar_sempty + 8 * s);                       // SV stage free in BOTH CTAs
+                        if (nt == nt1 - 1) tc_commit_2sm_mc(bar_xempty + 8 * kb);   // last use of X tile kb by this item
+                    }
+                    tc_commit_2sm_mc(bar_tfull + 8 * a);
+                }
+                xi++;
+            }
+        }
+    } else {  // ===== epilogue warps 2..9 (both CTAs): lane quarter q, column half h of the accumulator =====
+        const int q = warp & 3, h = (warp - 2) >> 2;
+        uint32_t acc_it = 0;
+        const float c2 = -2.0f * c;
+        for (int item = cid; item < items; item += ncl) {
+            const int mp = item / nsplit, sp = item - mp * nsplit;
+            const int nt0 = sp * nt_per, nt1 = min(n_ntiles, nt0 + nt_per);
+            if (nt0 >= nt1) continue;
+            const unsigned m = (unsigned)(2 * mp + (int)rank) * BM + q * 32 + lane;
+            const float u = (m < W) ? c * xn[m] : 0.0f;
+            double dsum = 0.0;
+            float asum = 0.0f;
+            for (int nt = nt0; nt < nt1; nt++, acc_it++) {
+                const uint32_t a = acc_it & 1u, aph = (acc_it >> 1) & 1u;
+                mbar_wait(bar_tfull + 8 * a, aph);
+                tc_fence_after();
+                const uint32_t tab_s = tab_smem ? tab_base + (uint32_t)nt * BN * 4u : 0u;
+                const float ps = epilogue_columns<BN / 2>(tmem_base + ((uint32_t)(q * 32) << 16) + a * BN + h * (BN / 2), tab_s, svcoef + (size_t)nt * BN, h * (BN / 2), c2);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster((bar_tempty + 8 * a) & PEER_MASK);   // on the LEADER's barrier (count 16)
+                dsum += (double)ps;
+                asum += fabsf(ps);
+            }
+            if (m < W) {
+                atomicAdd(dec_acc + m, dsum);
+                atomicAdd(asum_acc + m, (1.0f - u + csvn_max) * asum);
+            }
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// dec = sum - rho, guard test (same rule as the SIMT kernel; NaN-safe: anything not provably outside the band is inside).
+// AUDIT.  audit_every > 0: every audit_every-th window (by index) is put on the guard list as well, whatever its decision
+// value -- an unbiased sample -- and the contraction's value of every listed window is kept in dec_tc, so that the FP64
+// tier can measure |dec_tc - dec_fp64| / E on THIS call's windows (guard_fma_kernel; hafgpu.cu escalates the number of
+// tensor-core products when the measured error leaves less than 4x margin inside the guard band).
 __global__ void svm_finalize_kernel(double* __restrict__ dec, const float* __restrict__ asum, const float* __restrict__ xn,
                                     const unsigned* __restrict__ win_count, double rho, float guard_rel, unsigned char* __restrict__ guard_flag, int* __restrict__ guard_list,
-                                    unsigned* __restrict__ guard_count) {
+                                    unsigned* __restrict__ guard_count, int audit_every, double* __restrict__ dec_tc, unsigned* __restrict__ audit_only_count) {
     const unsigned W = *win_count;
     const unsigned m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= W) return;
     const double dv = dec[m] - rho;
     dec[m] = dv;
     // xn = +inf marks a window whose inputs left the fp16 range (features_tc_kernel): always re-evaluated exactly
-    const bool g = !(fabs(dv) > (double)guard_rel * ((double)asum[m] + fabs(rho))) || !(xn[m] < 3.0e38f);  // asum = E above
+    const bool outside = !(xn[m] < 3.0e38f);
+    const bool g = !(fabs(dv) > (double)guard_rel * ((double)asum[m] + fabs(rho))) || outside;  // asum = E above
+    const bool audit = audit_every > 0 && (m % (unsigned)audit_every) == 0u;
     guard_flag[m] = g ? 1 : 0;
-    if (g) guard_list[atomicAdd(guard_count, 1u)] = (int)m;
+    if (g || audit) {
+        guard_list[atomicAdd(guard_count, 1u)] = (int)m;
+        if (dec_tc) dec_tc[m] = outside ? __longlong_as_double(0x7ff8000000000000ll) : dv;   // NaN: nothing to compare
+        if (!g) atomicAdd(audit_only_count, 1u);
+    }
 }
 
 }  // namespace haftc

@@ -53,7 +53,8 @@ typedef struct {
     int roll_step_deg;         /* 15  (ROLL_STEPS_DEGREE, :95)                                               */
     int roll_max_deg;          /* 190 (ROLL_MAX_DEGREE, :101) -> R = 190/15 = 12 rolls                        */
     int device;                /* CUDA ordinal; one context (and one process) per GPU                         */
-    int emulate_text_roundtrip; /* 1 = reproduce the "%.4g" / "%g" text round trips (reference-exact)         */
+    int emulate_text_roundtrip; /* 0 (a zero-initialised config) or 1 = reproduce the "%.4g" / "%g" text round
+                                   trips (reference-exact); -1 = skip them (NOT the reference's numbers)        */
     int svm_mode;              /* HAF_SVM_*                                                                   */
     float guard_rel;           /* guard band half-width as a fraction of E + |rho|,
                                   E = sum_i |coef_i| K_i (1 + gamma log2(e) (|x|^2 + |sv_i|^2)); <=0 -> default
@@ -114,6 +115,11 @@ typedef struct {
     long long n_points, n_units, n_windows, n_guard, launches;
     long long n_chunks; /* passes over the stage sequence (each launches every stage kernel once) */
     long long n_exact;  /* guard windows that went on to the exact-order FP64 kernels (tier 3); svm_mode 1: 0 */
+    long long n_audit;  /* windows OUTSIDE the guard band re-evaluated in FP64 as the audit sample (tensor mode)  */
+    float audit_max_rel; /* max |dec_tensor - dec_fp64| / (E + |rho|) over guard + audit windows of the call      */
+    int tc_passes;      /* tensor-core products per k-slice the call ended with (0 outside tensor mode)           */
+    int escalations;    /* times this context repeated a call with more products because the audit left < 4x     */
+    int reserved;
 } haf_timing;
 
 /* ---- lifetime --------------------------------------------------------------------------------------------- */
@@ -135,8 +141,9 @@ long long haf_launch_count(const haf_ctx* ctx);              /* kernels launched
  *   graspseval [n_requests][R][G][G] float  (graspseval of show_predicted_gps, :823-880)
  *   mask       [n_requests][R][G][G] uint8  (point_inside_box_grid, :138)
  *   heights    [n_requests][R][G][G] float  (heightsgridroll, :136)
- *   per_roll_top [n_requests][R][3] int     (id_row_top_all, id_col_top_all, topval_gp_all per roll, :811-815)
- * Rolls not evaluated (roll_limit) are left untouched. */
+ *   per_roll_top [n_requests][R][3] int     (id_row_top_all, id_col_top_all, topval_gp_all per roll, :811-815);
+ *                                           rolls not evaluated (roll_begin / roll_limit) get (-1, -1, -1000)
+ * In graspseval / mask / heights the rolls not evaluated are left untouched. */
 int haf_search(haf_ctx* ctx, const float* xyz_hostdev, size_t n_points, size_t stride_bytes,
                const haf_request* reqs, int n_requests, haf_best* best, haf_best* best_per_request,
                float* graspseval, unsigned char* mask, float* heights, int* per_roll_top);
@@ -181,8 +188,14 @@ int haf_scale_apply(int device, const long long* row_ptr, const int* index, cons
  * cross-GPU best-grasp exchange. */
 int haf_build_transform(const haf_request* req, int roll, int roll_step_deg, float M_rowmajor[16]);
 uint64_t haf_best_key(int topval, uint32_t unit_order);
+/* records [n][8] int32 = {topval, row, col, roll, tilt, approach_idx, n_windows_scored, rolls_done}: the 32-byte record
+ * of the cross-GPU best-grasp exchange, e.g. straight into a pinned buffer an NCCL all-gather reads */
+int haf_pack_best_records(const haf_best* best, int n, int32_t* records);
 
 /* ---- parity / inspection entry points (used by tests; they re-run stages on the state of the LAST haf_search) */
+/* 1: haf_search_batch* calls keep their per-window state for the accessors below as well; such a call must then fit one
+ * pass over the stage sequence (<= ~2.4 M windows), else it fails with HAF_ERR_UNSUPPORTED */
+int haf_set_debug(haf_ctx* ctx, int keep_batch_state);
 int haf_debug_window_count(const haf_ctx* ctx);
 /* windows of the last search: win_unit_cell [W][2] = (unit = request*R + roll, cell = row*G + col) */
 int haf_debug_windows(haf_ctx* ctx, int* win_unit_cell, int cap_windows);

@@ -11,11 +11,15 @@ import numpy as np
 import pytest
 
 from conftest import FEATURES, GOLDEN, RANGE
+from model_io import coefK_sum, load_model_arrays
 
 pytestmark = pytest.mark.gpu
 
-# |dec_gpu - dec_ref| <= DEC_RTOL * sum_i |coef_i| K_i  (FP32 contraction, FP64 accumulation of the decision sum);
-# north_star asks <= 1e-5 relative in FP32.
+# north_star: decision values within <= 1e-5 relative in FP32.  A decision value is a SUM of S signed terms coef_i K_i
+# that may cancel to anything, so "relative" is stated against what the rounding errors scale with, per window:
+#     |dec_gpu - dec_ref| <= DEC_RTOL * sum_i |coef_i| K_i(window)
+# (computed here in float64 from the oracle's scaled inputs and the model file -- NOT a flat model-wide constant).
+# Measured (tools/dec_error_probe.py, profiles/r2_dec_error_hist.txt): <= 1e-6 of that scale on every path.
 DEC_RTOL = 1e-5
 # FP64 exact-order path: only exp() implementation differences (glibc vs CUDA, <= 1 ulp each term)
 DEC64_RTOL = 1e-13
@@ -56,24 +60,8 @@ class Pair:
         self.step = kw.get("roll_step_deg", 15)
         self.rmax = kw.get("roll_max_deg", 190)
 
-    def coefK_scale(self, scaled):
-        """sum_i |coef_i| K_i >= |dec + rho|: the natural scale of the FP32 error; cheap upper bound used here."""
-        return self.abs_coef_sum
-
     def close(self):
         self.gpu.close()
-
-
-def abs_coef_sum(model_path):
-    s = 0.0
-    with open(model_path) as fh:
-        in_sv = False
-        for ln in fh:
-            if in_sv and ln.strip():
-                s += abs(float(ln.split()[0]))
-            elif ln.startswith("SV"):
-                in_sv = True
-    return s
 
 
 def mk_requests(hg, orc, **kw):
@@ -99,9 +87,8 @@ def check_search(pair, xyz, hg, orc, model_path, dec_rtol=DEC_RTOL, full=True, *
     dec, lab, guard = pair.gpu.debug_decisions()
     order = np.lexsort((win[:, 1], win[:, 0]))  # (unit, cell) row-major == the reference's file order per roll
     win, raw, scaled, dec, lab, guard = win[order], raw[order], scaled[order], dec[order], lab[order], guard[order]
-    o_dec_all = []
     pos = 0
-    scale = abs_coef_sum(model_path)
+    scaled_rolls = []
     for roll in range(lim):
         feats_o, rc = pair.orc.calc_featurevectors(ores["integral"][roll], ores["mask"][roll])
         W = len(feats_o)
@@ -111,6 +98,7 @@ def check_search(pair, xyz, hg, orc, model_path, dec_rtol=DEC_RTOL, full=True, *
         assert raw[sel].tobytes() == feats_o.tobytes(), "raw features differ (roll %d)" % roll
         scaled_o = pair.orc.scale(feats_o)[:, :pair.gpu.D]
         assert scaled[sel].tobytes() == scaled_o.tobytes(), "scaled SVM inputs differ (roll %d)" % roll
+        scaled_rolls.append(scaled_o)
         pos += W
     if nroll == len(ores["heights"]):
         assert pos == len(win)
@@ -120,7 +108,10 @@ def check_search(pair, xyz, hg, orc, model_path, dec_rtol=DEC_RTOL, full=True, *
         n = len(o_dec)
         assert n <= len(dec)
         err = np.abs(dec[:n] - o_dec)
-        assert err.max(initial=0.0) <= dec_rtol * scale, (err.max(), scale)
+        if n:
+            scale = coefK_sum(load_model_arrays(model_path), np.concatenate(scaled_rolls)[:n])   # per window
+            bad = err > dec_rtol * scale
+            assert not bad.any(), (int(bad.sum()), float((err / scale).max()))
         o_lab = np.where(o_dec > 0, pair.gpu.info.label0, pair.gpu.info.label1)
         assert np.array_equal(lab[:n], o_lab), "labels differ"
         assert np.array_equal(gres["graspseval"][0][:nroll], ores["graspseval"][:nroll])
@@ -241,11 +232,13 @@ def test_tensor_mode_fast_tier_inputs_track_the_exact_scaled_values(hg, oracle_l
 
 
 @pytest.mark.parametrize("kw", [{}, {"sv_table_global": 1}, {"tc_variant": 1}, {"tc_variant": 1, "sv_table_global": 1},
-                                {"tc_passes": 1}, {"tc_passes": 2}, {"tc_passes": 3}, {"tc_passes": 1, "tc_variant": 1}])
+                                {"tc_passes": 1}, {"tc_passes": 2}, {"tc_passes": 3}, {"tc_passes": 1, "tc_variant": 1},
+                                {"tc_passes": 1, "tc_variant": 2}, {"tc_passes": 1, "sv_table_global": 1}])
 def test_tensor_core_mode_synth_models_and_batch(hg, oracle_lib, tmp_models, kw):
-    """CTA-pair and single-CTA kernels, with the {c|sv|^2, coef} table staged in shared memory (default) or read from
-    global memory (what models with > 4096 support vectors get), and with 1, 2 or 3 tensor-core products per k-slice
-    forced (the default calibrates the count per model and widens the guard band by the calibrated operand error)."""
+    """X-resident CTA-pair (one product, tc_variant 0), streaming CTA-pair (tc_variant 2 / more products) and single-CTA
+    kernels, with the coef table staged in shared memory (default) or read from global memory (what models with > 4096
+    support vectors get), and with 1, 2 or 3 tensor-core products per k-slice forced (the default calibrates the count
+    per model and widens the guard band by the calibrated operand error)."""
     from haf_grasping_b200 import synth
     for nsv in (256, 300):   # 300: support-vector count not a multiple of the 256-wide tile
         model = tmp_models(nsv)
@@ -277,7 +270,7 @@ def test_guard_band_catches_near_zero_decisions(hg, oracle_lib, tmp_models, clou
         assert guard.sum() > 0
         t = p.gpu.timing()
         assert t.n_guard == guard.sum()
-        assert t.n_exact == (0 if tier2 == 0 else t.n_guard)
+        assert t.n_exact == (0 if tier2 == 0 else t.n_guard + t.n_audit)   # tier2 = 2 escalates the audit sample's windows as well
     finally:
         p.close()
 
@@ -479,12 +472,13 @@ def test_cpp_host_cli_matches_oracle_grasp_output(hg, oracle_lib, trained_model,
 
 
 def test_roll_begin_shards_one_goal(pair_synth, clouds, hg, oracle_lib):
-    """rolls [5, 9) only: per-roll tops equal the full run's, the others are untouched (-1)."""
+    """rolls [5, 9) only: per-roll tops equal the full run's, the others read (-1, -1, -1000)."""
     xyz = clouds["table3"]
     full = pair_synth.gpu.search(xyz, [hg.make_request()])
     part = pair_synth.gpu.search(xyz, [hg.make_request(roll_begin=5, roll_limit=9)])
     assert np.array_equal(part["per_roll_top"][0][5:9], full["per_roll_top"][0][5:9])
-    assert (part["per_roll_top"][0][:5] == -1).all() and (part["per_roll_top"][0][9:] == -1).all()
+    rest = np.concatenate([part["per_roll_top"][0][:5], part["per_roll_top"][0][9:]])
+    assert (rest == np.array([-1, -1, -1000])).all()      # rolls not evaluated
     assert np.array_equal(part["graspseval"][0][5:9], full["graspseval"][0][5:9])
     assert part["best"].rolls_done == 4
 
