@@ -62,7 +62,7 @@ class haf_timing(C.Structure):
 
 EXPORTS = ["haf_create", "haf_destroy", "haf_last_error", "haf_get_info", "haf_set_stream", "haf_set_profiling",
            "haf_get_timing", "haf_launch_count", "haf_set_debug", "haf_search", "haf_search_batch", "haf_search_batch_packed",
-           "haf_build_transform", "haf_best_key", "haf_pack_best_records", "haf_debug_window_count", "haf_debug_windows", "haf_debug_features",
+           "haf_build_transform", "haf_build_transform_wcs", "haf_best_key", "haf_pack_best_records", "haf_debug_window_count", "haf_debug_windows", "haf_debug_features",
            "haf_debug_decisions", "haf_debug_tensor_inputs", "haf_debug_integral", "haf_debug_cell_indices", "haf_debug_text_roundtrip",
            "haf_version", "haf_svm_create", "haf_svm_destroy", "haf_svm_predict", "haf_scale_minmax", "haf_scale_apply"]
 
@@ -101,6 +101,7 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     L.haf_search_batch.argtypes = [vp, C.POINTER(vp), C.POINTER(cs), ci, C.POINTER(haf_request), C.POINTER(haf_best)]
     L.haf_search_batch_packed.argtypes = [vp, vp, C.POINTER(cs), ci, C.POINTER(haf_request), C.POINTER(haf_best)]
     L.haf_build_transform.argtypes = [C.POINTER(haf_request), ci, ci, C.POINTER(C.c_float)]
+    L.haf_build_transform_wcs.argtypes = [C.POINTER(haf_request), ci, ci, C.POINTER(C.c_float)]
     L.haf_best_key.argtypes = [ci, C.c_uint32]
     L.haf_best_key.restype = C.c_uint64
     L.haf_pack_best_records.argtypes = [vp, ci, vp]

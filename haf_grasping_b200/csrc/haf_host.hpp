@@ -203,7 +203,10 @@ inline void normalize_approach(const double in[3], double out[3]) {  // server.c
     out[0] = in[0] / len; out[1] = in[1] / len; out[2] = in[2] / len;
 }
 
-inline void build_transform(const haf_request& rq, int roll, int roll_step_deg, float M[16]) {
+// wcs = false: mat_transform as generate_grid builds it (:406-484; the angles from the float PointXYZ copy of the approach
+// vector, :418-420).  wcs = true: as transform_gp_in_wcs_and_publish rebuilds it (:1276-1334; the angles from the DOUBLE
+// members this->approach_vector, :1293-1303) -- the two differ in the last bits for a tilted approach vector.
+inline void build_transform(const haf_request& rq, int roll, int roll_step_deg, float M[16], bool wcs = false) {
     double av[3];
     normalize_approach(rq.approach, av);
     const float ax = (float)av[0], ay = (float)av[1], az = (float)av[2];  // PointXYZ floats (:418-420)
@@ -213,7 +216,15 @@ inline void build_transform(const haf_request& rq, int roll, int roll_step_deg, 
     T1[3] = (float)(-rq.center[0]); T1[7] = (float)(-rq.center[1]); T1[11] = (float)(-rq.center[2]);  // :435-437
     T2[11] = 0 + 0.15f;                                                        // :441, trans_z_after_pc_transform (:214)
     float rot_z, rot_x = 0;
-    if (ay == 0 && ax == 0) {                                                  // :444-450
+    if (wcs) {                                                                 // :1293-1303
+        if (av[1] == 0 && av[0] == 0) {
+            rot_z = 0;
+            rot_x = (av[2] >= 0) ? 0.0f : (float)kPI;
+        } else {
+            rot_z = (float)(90 * kPI / 180.0 - std::atan2(av[1], av[0]));
+            rot_x = (float)(90 * kPI / 180.0 - std::atan2(av[2], std::sqrt(av[1] * av[1] + av[0] * av[0])));
+        }
+    } else if (ay == 0 && ax == 0) {                                           // :444-450
         rot_z = 0;
         rot_x = (az >= 0) ? 0.0f : (float)kPI;
     } else {                                                                   // :452-453

@@ -91,8 +91,9 @@ struct haf_ctx {
     DevBuf<DimDev> d_dims;
     DevBuf<float> d_svT, d_svn, d_coef;
     DevBuf<double> d_sv64T, d_coef64;
-    // tensor-core path (HAF_SVM_TENSOR_GUARD): fp16 hi/lo operands, K-major rows of Krow elements
-    int Krow = 0, SpadT = 0;
+    // tensor-core path (HAF_SVM_TENSOR_GUARD): fp16 hi/lo operands, K-major, k-block tiled (kernels.cuh, kt_off):
+    // Krow = columns in use (dimensions + 6 extra columns, rounded up to 16), KB = k-blocks of 64 columns stored
+    int Krow = 0, KB = 0, SpadT = 0;
     float c_log2 = 0.0f;
     float csvn_max = 0.0f;      // |c| * max_n ||sv_n||^2 (guard scale of the tensor kernels)
     DevBuf<__half> d_SVh, d_SVl, d_Xh, d_Xl;   // d_Xl only with three products per k-slice
@@ -104,9 +105,8 @@ struct haf_ctx {
     DevBuf<DimFeat> d_dimfeat;
     DevBuf<Round4Tab> d_round4;   // "%.4g" tables of the fast tier
     DevBuf<float> d_asum;
-    CUtensorMap tmSh, tmSl;     // 256-row boxes (single-CTA kernel)
-    CUtensorMap tmSh2, tmSl2;   // 128-row boxes (CTA-pair kernel)
-    int tc_variant = 0;         // 0: auto (X-resident CTA-pair kernel where eligible, else streaming CTA pair), 1: single-CTA kernel, 2: streaming CTA pair
+    CUtensorMap tmSh2, tmSl2;   // 128-row boxes: one per CTA of a pair
+    int tc_variant = 0;         // 0: auto (X-resident CTA-pair kernel where eligible, else streaming CTA pair), 2: streaming CTA pair always
     int tc_passes = 3;          // tensor-core products per k-slice: 3, 2 or 1 (calibrate_tensor_passes)
     double tc_operand_err = 0;  // calibrated operand error of the chosen scheme, as a fraction of the guard scale E
 
@@ -264,13 +264,14 @@ static void calibrate_tensor_passes(const hafhost::Model& model, int Dsv, double
 static void make_round4_table(Round4Tab& tab) {
     for (int i = 0; i < 96; i++) { tab.pwd[i] = pow(10.0, i - 48); tab.pwf[i] = (float)tab.pwd[i]; }
 }
-// 2D fp16 tensor [rows][krow] (K contiguous), box = 64 elements (128 B, one swizzle row) x box_rows, 128B swizzle
-static bool make_tensor_map(CUtensorMap* m, void* base, uint64_t krow, uint64_t rows, uint32_t box_rows) {
+// Operand tensor in the k-block tiled layout (kernels.cuh, kt_off): seen by TMA as [n_tiles * 128 rows][64 fp16], pitch 128 B
+// = fully contiguous; one box = 64 x 128 = one 16 KB tile (row tile, k-block), 128B swizzle.  rows is a multiple of 128.
+static bool make_tensor_map(CUtensorMap* m, void* base, int KB, uint64_t rows) {
     haf_encode_tiled_fn fn = get_encode_tiled();
     if (!fn) return false;
-    cuuint64_t dims[2] = {krow, rows};
-    cuuint64_t strides[1] = {krow * 2};
-    cuuint32_t box[2] = {(cuuint32_t)haftc::BK, box_rows};
+    cuuint64_t dims[2] = {(cuuint64_t)haftc::BK, rows / 128 * (cuuint64_t)KB * 128};
+    cuuint64_t strides[1] = {(cuuint64_t)haftc::BK * 2};
+    cuuint32_t box[2] = {(cuuint32_t)haftc::BK, (cuuint32_t)haftc::BM};
     cuuint32_t es[2] = {1, 1};
     return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -478,8 +479,9 @@ static int create_impl(haf_ctx** out, const haf_config* cfg, bool svm_only, int 
         }
         if (order.empty()) order.assign(haftc::BN, -1);
         const int SpadT = (int)order.size();
-        ctx->Krow = Krow; ctx->SpadT = SpadT;
-        std::vector<uint16_t> svh((size_t)SpadT * Krow, 0), svl((size_t)SpadT * Krow, 0);
+        const int KB = (Krow + haftc::BK - 1) / haftc::BK;
+        ctx->Krow = Krow; ctx->KB = KB; ctx->SpadT = SpadT;
+        std::vector<uint16_t> svh((size_t)SpadT * KB * haftc::BK, 0), svl((size_t)SpadT * KB * haftc::BK, 0);
         std::vector<float> tab(SpadT, 0.0f);
         const uint16_t one16 = f2h16(1.0f);
         for (int r = 0; r < SpadT; r++) {
@@ -495,8 +497,8 @@ static int create_impl(haf_ctx** out, const haf_config* cfg, bool svm_only, int 
                 }
                 const uint16_t h = f2h16(fv);
                 const uint16_t l = f2h16(fv - h16f(h));
-                svh[(size_t)r * Krow + d] = h;
-                svl[(size_t)r * Krow + d] = l;
+                svh[kt_off((size_t)r, d, KB)] = h;
+                svl[kt_off((size_t)r, d, KB)] = l;
                 const float rep = h16f(h) + h16f(l);
                 nrm = fmaf(rep, rep, nrm);
             }
@@ -505,13 +507,12 @@ static int create_impl(haf_ctx** out, const haf_config* cfg, bool svm_only, int 
                 return create_fail(HAF_ERR_UNSUPPORTED, "a support vector's squared norm exceeds the fp16 range of the tensor path (use svm_mode HAF_SVM_FP32_GUARD)");
             }
             // extra operand columns: 1 1 1 (against the window's -|x|^2 / 2 terms), then -|sv|^2 / 2 as three fp16 terms
-            uint16_t* aug = &svh[(size_t)r * Krow + Dsv];
-            aug[0] = aug[1] = aug[2] = one16;
             const float b = -0.5f * nrm;
             const uint16_t bh = f2h16(b);
             const float r1 = b - h16f(bh);
             const uint16_t bm = f2h16(r1);
-            aug[3] = bh; aug[4] = bm; aug[5] = f2h16(r1 - h16f(bm));
+            const uint16_t aug[6] = {one16, one16, one16, bh, bm, f2h16(r1 - h16f(bm))};
+            for (int q = 0; q < 6; q++) svh[kt_off((size_t)r, Dsv + q, KB)] = aug[q];
             tab[r] = (float)model.coef[i];
             ctx->csvn_max = std::max(ctx->csvn_max, fabsf(ctx->c_log2 * nrm));
         }
@@ -535,8 +536,7 @@ static int create_impl(haf_ctx** out, const haf_config* cfg, bool svm_only, int 
             ctx->tc_operand_err = passes < 3 ? rel[passes] : 0.0;
             if (cfg->guard_rel <= 0) ctx->guard_rel = std::max(4e-6f, (float)(15.0 * (ctx->tc_operand_err + 2.5e-7)));
         }
-        if (!make_tensor_map(&ctx->tmSh, ctx->d_SVh.p, Krow, SpadT, haftc::BN) || !make_tensor_map(&ctx->tmSl, ctx->d_SVl.p, Krow, SpadT, haftc::BN) ||
-            !make_tensor_map(&ctx->tmSh2, ctx->d_SVh.p, Krow, SpadT, haftc::BN / 2) || !make_tensor_map(&ctx->tmSl2, ctx->d_SVl.p, Krow, SpadT, haftc::BN / 2)) {
+        if (!make_tensor_map(&ctx->tmSh2, ctx->d_SVh.p, KB, SpadT) || !make_tensor_map(&ctx->tmSl2, ctx->d_SVl.p, KB, SpadT)) {
             haf_destroy(ctx);
             return create_fail(HAF_ERR_CUDA, "cuTensorMapEncodeTiled failed for the support-vector operands");
         }
@@ -575,7 +575,6 @@ static int create_impl(haf_ctx** out, const haf_config* cfg, bool svm_only, int 
         CREATE_TRY(cudaMemcpy(ctx->d_round4.p, &r4, sizeof(Round4Tab), cudaMemcpyHostToDevice));
         if (ctx->d_dimfeat.ensure(joined.size()) != 0) { haf_destroy(ctx); return create_fail(HAF_ERR_NOMEM, "out of device memory uploading the joined feature table"); }
         CREATE_TRY(cudaMemcpy(ctx->d_dimfeat.p, joined.data(), joined.size() * sizeof(DimFeat), cudaMemcpyHostToDevice));
-        CREATE_TRY(cudaFuncSetAttribute(haftc::svm_rbf_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, haftc::SMEM_BYTES + haftc::TAB_SMEM_MAX * 4));
         CREATE_TRY(cudaFuncSetAttribute(haftc::svm_rbf_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, haftc::SMEM2_BYTES + haftc::TAB_SMEM_MAX * 4));
         CREATE_TRY(cudaFuncSetAttribute(haftc::svm_rbf_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, haftc::TC3_SMEM_LIMIT));
         CREATE_TRY(cudaFuncSetAttribute(features_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * HAF_FT_WT * (HAF_FT_KPASS + 1) * 4 + HAF_FT_ROWS * (G + 1 + 31) * 4 + 16 + HAF_FT_KPASS * 96));
@@ -642,7 +641,7 @@ extern "C" int haf_svm_predict(haf_svm* ctx, const long long* row_ptr, const int
         ENSURE(ctx, ctx->d_csr_ptr, rows + 1); ENSURE(ctx, ctx->d_csr_idx, (size_t)std::max<long long>(e1 - e0, 1)); ENSURE(ctx, ctx->d_csr_val, (size_t)std::max<long long>(e1 - e0, 1));
         ENSURE(ctx, ctx->d_xdense, rows * W); ENSURE(ctx, ctx->d_labels, rows);
         ENSURE(ctx, ctx->d_xn, ldx); ENSURE(ctx, ctx->d_dec, ldx); ENSURE(ctx, ctx->d_guardflag, ldx); ENSURE(ctx, ctx->d_guardlist, ldx);
-        if (tc) { ENSURE(ctx, ctx->d_Xh, ldx * ctx->Krow); if (ctx->tc_passes >= 3) ENSURE(ctx, ctx->d_Xl, ldx * ctx->Krow); ENSURE(ctx, ctx->d_asum, ldx); }
+        if (tc) { ENSURE(ctx, ctx->d_Xh, ldx * ctx->KB * haftc::BK); if (ctx->tc_passes >= 3) ENSURE(ctx, ctx->d_Xl, ldx * ctx->KB * haftc::BK); ENSURE(ctx, ctx->d_asum, ldx); }
         else if (ctx->cfg.svm_mode == HAF_SVM_FP32_GUARD) ENSURE(ctx, ctx->d_X, (size_t)ctx->Kpad * ldx);
         const size_t exact_cap = std::min<size_t>(ldx, std::max<size_t>(4096, ((size_t)1 << 30) / ((size_t)ctx->Spad * 8)));
         ENSURE(ctx, ctx->d_kscratch, exact_cap * ctx->Spad);
@@ -661,7 +660,7 @@ extern "C" int haf_svm_predict(haf_svm* ctx, const long long* row_ptr, const int
         csr_to_dense_kernel<<<(unsigned)rows, 128, 0, st>>>(ctx->d_csr_ptr.p, ctx->d_csr_idx.p, ctx->d_csr_val.p, (int)rows, W, ctx->d_xdense.p);
         LAUNCHED(ctx);
         if (ctx->cfg.svm_mode != HAF_SVM_FP64_EXACT) {
-            pack_svm_inputs_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(ctx->d_xdense.p, (int)rows, W, ctx->Krow, tc ? ctx->d_Xh.p : nullptr,
+            pack_svm_inputs_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(ctx->d_xdense.p, (int)rows, W, ctx->Krow, ctx->KB, tc ? ctx->d_Xh.p : nullptr,
                                                                               (tc && ctx->tc_passes >= 3) ? ctx->d_Xl.p : nullptr, tc ? nullptr : ctx->d_X.p, ldx, ctx->Kpad, ctx->d_xn.p);
             LAUNCHED(ctx);
         }
@@ -828,6 +827,11 @@ extern "C" int haf_build_transform(const haf_request* req, int roll, int roll_st
     hafhost::build_transform(*req, roll, roll_step_deg > 0 ? roll_step_deg : 15, M);
     return HAF_OK;
 }
+extern "C" int haf_build_transform_wcs(const haf_request* req, int roll, int roll_step_deg, float M[16]) {
+    if (!req || !M) return HAF_ERR_ARG;
+    hafhost::build_transform(*req, roll, roll_step_deg > 0 ? roll_step_deg : 15, M, true);
+    return HAF_OK;
+}
 // the 32-byte record of the cross-GPU best-grasp exchange, straight from the haf_best structs of a batch
 extern "C" int haf_pack_best_records(const haf_best* best, int n, int32_t* records) {
     if (!best || !records || n < 0) return HAF_ERR_ARG;
@@ -930,6 +934,11 @@ static ExactArgs make_exact_args(haf_ctx* ctx, const int* list, const unsigned* 
     return a;
 }
 
+// timing experiments on the tensor kernel's pipeline (tools/tc_pipeline_probe.py); results are garbage when set
+static int tc_debug_flags() {
+    const char* e = getenv("HAF_TC_DEBUG");
+    return e ? atoi(e) : 0;
+}
 // Stage 5 of the path, also the whole of haf_svm_predict: decision values of the windows [0, *cnt[0]) whose SVM inputs
 // are in ctx->d_Xh/d_Xl (tensor mode), ctx->d_X (SIMT mode) or re-derivable by exact_scaled_input (FP64 mode / guard
 // band), then the guard band.  ev_guard (optional) is recorded between the contraction and the guard-band kernels.
@@ -943,8 +952,7 @@ static int svm_stage(haf_ctx* ctx, unsigned* cnt, size_t Wcap, size_t ldx, int G
     } else if (tc) {
         CUtensorMap tmXh, tmXl;
         const bool need_lo = ctx->tc_passes >= 3;   // X_lo takes part in the third product only
-        if (!make_tensor_map(&tmXh, ctx->d_Xh.p, ctx->Krow, ldx, haftc::BM) ||
-            !make_tensor_map(&tmXl, need_lo ? ctx->d_Xl.p : ctx->d_Xh.p, ctx->Krow, ldx, haftc::BM))
+        if (!make_tensor_map(&tmXh, ctx->d_Xh.p, ctx->KB, ldx) || !make_tensor_map(&tmXl, need_lo ? ctx->d_Xl.p : ctx->d_Xh.p, ctx->KB, ldx))
             return ctx->fail(HAF_ERR_CUDA, "cuTensorMapEncodeTiled failed for the window operands");
         CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_dec.p, 0, ldx * sizeof(double), st));
         CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_asum.p, 0, ldx * sizeof(float), st));
@@ -952,11 +960,12 @@ static int svm_stage(haf_ctx* ctx, unsigned* cnt, size_t Wcap, size_t ldx, int G
         const int mt_cap = (int)(ldx / haftc::BM);
         int nsplit = 1;
         if (mt_cap < ctx->sm_count) nsplit = std::min(n_ntiles, (2 * ctx->sm_count + mt_cap - 1) / mt_cap);
-        const int kblocks = (ctx->Krow + haftc::BK - 1) / haftc::BK;
+        const int kblocks = ctx->KB;
         const int last_slices = (ctx->Krow - haftc::BK * (kblocks - 1)) / 16;
         const int tab_smem = (ctx->SpadT <= haftc::TAB_SMEM_MAX && !ctx->cfg.reserved[3]) ? 1 : 0;   // coef table staged in shared memory
         const size_t tab_bytes = tab_smem ? (size_t)ctx->SpadT * 4 : 0;
-        if (ctx->tc_variant != 1) {
+        (void)nsplit;
+        {
             const int pairs_cap = (mt_cap + 1) / 2;
             int nsplit2 = 1;
             if (pairs_cap < ctx->sm_count / 2) nsplit2 = std::min(n_ntiles, (ctx->sm_count + pairs_cap - 1) / pairs_cap);
@@ -979,21 +988,18 @@ static int svm_stage(haf_ctx* ctx, unsigned* cnt, size_t Wcap, size_t ldx, int G
             if (stages3 >= 3)
                 haftc::svm_rbf_tc3_kernel<<<grid2, haftc::THREADS3, haftc::tc3_smem_bytes(kblocks, stages3, (int)(tab_bytes / 4)), st>>>(
                     tmXh, ctx->tmSh2, ctx->d_xn.p, ctx->d_svcoef.p, ctx->c_log2, cnt + 0, n_ntiles, nsplit2, kblocks, last_slices, stages3, ctx->d_dec.p,
-                    ctx->d_asum.p, tab_smem, ctx->csvn_max);
+                    ctx->d_asum.p, tab_smem, ctx->csvn_max, tc_debug_flags());
             else
                 haftc::svm_rbf_tc2_kernel<<<grid2, haftc::THREADS, haftc::SMEM2_BYTES + tab_bytes, st>>>(tmXh, tmXl, ctx->tmSh2, ctx->tmSl2, ctx->d_xn.p, ctx->d_svcoef.p,
                                                                                                  ctx->c_log2, cnt + 0, n_ntiles, nsplit2, kblocks, last_slices,
                                                                                                  ctx->d_dec.p, ctx->d_asum.p, tab_smem, ctx->csvn_max, ctx->tc_passes);
-        } else {
-            const int grid = (int)std::min<long long>((long long)mt_cap * nsplit, ctx->sm_count);
-            haftc::svm_rbf_tc_kernel<<<grid, haftc::THREADS, haftc::SMEM_BYTES + tab_bytes, st>>>(tmXh, tmXl, ctx->tmSh, ctx->tmSl, ctx->d_xn.p, ctx->d_svcoef.p, ctx->c_log2,
-                                                                                          cnt + 0, n_ntiles, nsplit, kblocks, last_slices, ctx->d_dec.p, ctx->d_asum.p, tab_smem, ctx->csvn_max, ctx->tc_passes);
         }
         LAUNCHED(ctx);
         // audit (svm_tc.cuh): with the FP64 FMA tier on, every listed window's contraction value is kept and a sample of all windows joins the list
-        const bool audit = ctx->tier2_mode != 1;
+        const bool audit = ctx->tier2_mode != 1 && !tc_debug_flags();
         if (audit) ENSURE(ctx, ctx->d_dec_tc, ldx);
-        haftc::svm_finalize_kernel<<<(unsigned)((Wcap + 255) / 256), 256, 0, st>>>(ctx->d_dec.p, ctx->d_asum.p, ctx->d_xn.p, cnt + 0, ctx->rho, ctx->guard_rel,
+        haftc::svm_finalize_kernel<<<(unsigned)((Wcap + 255) / 256), 256, 0, st>>>(ctx->d_dec.p, ctx->d_asum.p, ctx->d_xn.p, cnt + 0, ctx->rho,
+                                                                                   tc_debug_flags() ? -1.0f : ctx->guard_rel,   // timing experiments: empty guard band
                                                                                    ctx->d_guardflag.p, ctx->d_guardlist.p, cnt + 1, audit ? ctx->audit_every : 0,
                                                                                    audit ? ctx->d_dec_tc.p : nullptr, cnt + 13);
         LAUNCHED(ctx);
@@ -1141,7 +1147,7 @@ static int run_jobs_once(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& job
         ENSURE(ctx, ctx->d_mask, (size_t)Uc * GG); ENSURE(ctx, ctx->d_labelgrid, (size_t)Uc * GG); ENSURE(ctx, ctx->d_evals, (size_t)Uc * GG);
         const bool tc = ctx->cfg.svm_mode == HAF_SVM_TENSOR_GUARD;
         ENSURE(ctx, ctx->d_win, ldx); ENSURE(ctx, ctx->d_xn, ldx);
-        if (tc) { ENSURE(ctx, ctx->d_Xh, ldx * ctx->Krow); if (ctx->tc_passes >= 3) ENSURE(ctx, ctx->d_Xl, ldx * ctx->Krow); ENSURE(ctx, ctx->d_asum, ldx); }
+        if (tc) { ENSURE(ctx, ctx->d_Xh, ldx * ctx->KB * haftc::BK); if (ctx->tc_passes >= 3) ENSURE(ctx, ctx->d_Xl, ldx * ctx->KB * haftc::BK); ENSURE(ctx, ctx->d_asum, ldx); }
         else if (ctx->cfg.svm_mode == HAF_SVM_FP32_GUARD) ENSURE(ctx, ctx->d_X, (size_t)ctx->Kpad * ldx);
         ENSURE(ctx, ctx->d_dec, ldx); ENSURE(ctx, ctx->d_guardflag, ldx); ENSURE(ctx, ctx->d_guardlist, ldx);
         if (!smallG) ENSURE(ctx, ctx->d_rowscan, (size_t)Uc * GG);
@@ -1218,7 +1224,7 @@ static int run_jobs_once(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& job
             const unsigned fblocks = (unsigned)((Wcap + 32 * HAF_FT_WT - 1) / (32 * HAF_FT_WT));
             features_tc_kernel<<<fblocks, 256, ft_smem_bytes(ctx), st>>>(ctx->d_integral.p, ctx->d_win.p, cnt + 0, G, ubase, ctx->d_dimfeat.p, ctx->D,
                                                                       ctx->Krow, (float)ctx->lower, ctx->cfg.emulate_text_roundtrip, ctx->d_round4.p, ctx->d_Xh.p,
-                                                                      ctx->tc_passes >= 3 ? ctx->d_Xl.p : nullptr, ctx->d_xn.p, ctx->Dsv);
+                                                                      ctx->tc_passes >= 3 ? ctx->d_Xl.p : nullptr, ctx->d_xn.p, ctx->Dsv, ctx->KB);
             LAUNCHED(ctx);
         } else if (ctx->cfg.svm_mode != HAF_SVM_FP64_EXACT) {
             features_kernel<false><<<wblocks32, 256, 0, st>>>(ctx->d_integral.p, ctx->d_win.p, cnt + 0, G, ubase, ctx->d_feats.p, ctx->d_dims.p,
@@ -1308,7 +1314,7 @@ static int run_jobs(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& jobs, fl
                     float* out_heights, bool keep_debug_state) {
     for (;;) {
         const int rc = run_jobs_once(ctx, cs, jobs, out_evals, out_mask, out_heights, keep_debug_state);
-        if (rc != HAF_OK || ctx->cfg.svm_mode != HAF_SVM_TENSOR_GUARD || ctx->tier2_mode == 1) return rc;
+        if (rc != HAF_OK || ctx->cfg.svm_mode != HAF_SVM_TENSOR_GUARD || ctx->tier2_mode == 1 || tc_debug_flags()) return rc;
         if (!(ctx->audit_max_rel > 0.25f * ctx->guard_rel)) return rc;
         if (ctx->tc_passes >= 3)
             return ctx->fail(HAF_ERR_UNSUPPORTED, "audit: the tensor contraction is off by %.3g E on this call's windows, guard_rel = %.3g leaves less than a 4x margin "
@@ -1496,11 +1502,12 @@ extern "C" int haf_debug_tensor_inputs(haf_ctx* ctx, float* x, int cap) {
     const int W = std::min<int>(cap, (int)ctx->last_W);
     if (W <= 0) return 0;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    std::vector<uint16_t> hh((size_t)W * ctx->Krow), ll((size_t)W * ctx->Krow, 0);   // lo = 0 where the contraction reads hi only
-    CUDA_TRY(ctx, cudaMemcpy(hh.data(), ctx->d_Xh.p, hh.size() * 2, cudaMemcpyDeviceToHost));
-    if (ctx->tc_passes >= 3) CUDA_TRY(ctx, cudaMemcpy(ll.data(), ctx->d_Xl.p, ll.size() * 2, cudaMemcpyDeviceToHost));
+    const size_t nel = round_up((size_t)W, 128) * ctx->KB * haftc::BK;   // k-block tiled layout (kt_off)
+    std::vector<uint16_t> hh(nel), ll(nel, 0);   // lo = 0 where the contraction reads hi only
+    CUDA_TRY(ctx, cudaMemcpy(hh.data(), ctx->d_Xh.p, nel * 2, cudaMemcpyDeviceToHost));
+    if (ctx->tc_passes >= 3) CUDA_TRY(ctx, cudaMemcpy(ll.data(), ctx->d_Xl.p, nel * 2, cudaMemcpyDeviceToHost));
     for (int w = 0; w < W; w++)
-        for (int d = 0; d < ctx->D; d++) x[(size_t)w * ctx->D + d] = h16f(hh[(size_t)w * ctx->Krow + d]) + h16f(ll[(size_t)w * ctx->Krow + d]);
+        for (int d = 0; d < ctx->D; d++) x[(size_t)w * ctx->D + d] = h16f(hh[kt_off((size_t)w, d, ctx->KB)]) + h16f(ll[kt_off((size_t)w, d, ctx->KB)]);
     return W;
 }
 

@@ -114,6 +114,9 @@ public:
                             heightsgridroll.data(), per_roll_top.data());
         if (rc != HAF_OK) throw std::runtime_error(std::string("hafgpu: ") + haf_last_error(ctx_));
         published_per_roll.clear();
+        // av_trans_mat (:484) = generate_grid's matrix of the roll just evaluated; only its third row is read (:1370-1374), and
+        // that row is the same for every roll (S * Rroll leaves it untouched)
+        haf_build_transform(&rq, best.roll >= 0 ? best.roll : 0, step_deg_, av_trans_mat);
         for (int roll = 0; roll < best.rolls_done; roll++) {                      // what show_predicted_gps did per roll
             const int* t = &per_roll_top[roll * 3];
             if (!return_only_best_gp && t[2] > graspval_th) {                      // :962-972
@@ -124,7 +127,6 @@ public:
         }
         id_row_top_overall = best.row; id_col_top_overall = best.col; nr_roll_top_overall = best.roll;       // :953-960
         nr_tilt_top_overall = best.tilt; topval_gp_overall = best.topval;
-        memcpy(av_trans_mat, best.M, sizeof av_trans_mat);                        // :484 (third row is roll-independent)
         gp_result = transform_gp_in_wcs_and_publish(best.row, best.col, best.roll, best.tilt, topval_gp_overall - 20);  // :390
     }
 
@@ -139,7 +141,8 @@ public:
         rq.approach[0] = raw_approach_.x; rq.approach[1] = raw_approach_.y; rq.approach[2] = raw_approach_.z;
         rq.gripper_opening_width = gripper_opening_width;
         float M[16];
-        haf_build_transform(&rq, nr_roll_top_all < 0 ? 0 : nr_roll_top_all, step_deg_, M);     // :1276-1334 (same matrices as :423-483)
+        // :1276-1334: the same chain as :423-483, but the two angles come from the double approach_vector members (:1293-1303)
+        haf_build_transform_wcs(&rq, nr_roll_top_all < 0 ? 0 : nr_roll_top_all, step_deg_, M);
         float x_gp_roll = -((float)(G / 2 - id_row_top_all)) / 100;                              // :1339
         float y_gp_roll = -((float)(G / 2 - id_col_top_all)) / 100;                              // :1340
         float h_locmax_roll = -10;
@@ -167,7 +170,7 @@ public:
         out.averagedGraspPoint.y = (g1[1] + g2[1]) / 2.0;
         out.averagedGraspPoint.z = (g1[2] + g2[2]) / 2.0;
         // :1370-1374: appr_vec = transpose(rotation of av_trans_mat) * (0,0,1) = third ROW of av_trans_mat
-        out.approachVector.x = M[8]; out.approachVector.y = M[9]; out.approachVector.z = M[10];
+        out.approachVector.x = av_trans_mat[8]; out.approachVector.y = av_trans_mat[9]; out.approachVector.z = av_trans_mat[10];
         out.roll = (float)((nr_roll_top_all * step_deg_ * 3.141592653) / 180);                     // :1401
         return out;
     }

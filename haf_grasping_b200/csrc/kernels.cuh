@@ -640,8 +640,8 @@ __device__ __forceinline__ float fast_tier_value(PtrT I, int idx0, const FastTab
     return (f.flags & 0x400) ? 0.0f : ((f.flags & 0x200) ? f.cval : x);
 }
 
-// Tensor-core variant: per-dimension values split into two fp16 terms and written K-major ([window][Krow], what the
-// UMMA K-major operand / TMA box wants).  Lane = window (WT = 2 windows per lane), warp = one dimension at a time; a
+// Tensor-core variant: per-dimension values split into two fp16 terms and written K-major in the k-block tiled layout
+// (kt_off: what the UMMA K-major operand / TMA box wants).  Lane = window (WT = 2 windows per lane), warp = one dimension at a time; a
 // 64-window x 96-dimension tile of (hi | lo << 16) words is staged in shared memory so that the global writes are whole
 // 32-byte sectors of the operand rows; the squared norm of the (hi + lo) representation is accumulated on the way.
 // The kernel is bound by the LSU data pipe and the issue rate together ("The feature kernel"): hence the
@@ -654,17 +654,27 @@ __device__ __forceinline__ float fast_tier_value(PtrT I, int idx0, const FastTab
 // 6-digit "%g" rounding (<= 5e-6 relative: the largest input error of this tier, tools/dec_error_probe.py) is skipped.
 // Raw feature values are the same bit-exact floats as everywhere else.
 // (Tables in __constant__ memory were tried and were 1.8x SLOWER: 36 KB of tables thrash the constant cache.)
+// OPERAND LAYOUT in global memory ("k-block tiled"): element (row, d) of X / SV lives at
+//     ((row / 128) * KB + d / 64) * 8192 + (row % 128) * 64 + d % 64        (fp16 elements; KB = k-blocks of 64)
+// i.e. every 128-row x 64-column tile the tensor kernels fetch with ONE TMA box is a contiguous, 128-byte aligned 16 KB
+// block.  Round 1 stored plain rows of Krow = 336 elements: a box was then 128 separate 128-byte pieces at a 672-byte pitch,
+// every one straddling two cache lines, and the TMA unit -- not L2, not the MMAs, not the epilogue -- bounded the tensor
+// kernel at ~5 clocks per box row (profiles/r2_tc_pipeline_probe.txt: the bare TMA + barrier skeleton of the kernel took 70 %
+// of its time).
+__host__ __device__ __forceinline__ size_t kt_off(size_t row, int d, int KB) {
+    return (((row >> 7) * (size_t)KB + (size_t)(d >> 6)) << 13) + ((row & 127) << 6) + (size_t)(d & 63);
+}
 // the six extra operand columns of a window row (svm_tc.cuh, OPERAND FORMAT): -|x|^2 / 2 as three fp16 terms, then 1 1 1.
 // The splits are exact in FP32 (each remainder has fewer significant bits than its predecessor).
-__device__ __forceinline__ void write_aug_columns(__half* __restrict__ row_aug, float sq, bool ok) {
+__device__ __forceinline__ void write_aug_columns(__half* __restrict__ X, size_t row, int aug0, int KB, float sq, bool ok) {
     const float a = -0.5f * sq;
     const __half h = __float2half_rn(a);
     const float r1 = a - __half2float(h);
     const __half m = __float2half_rn(r1);
     const __half l = __float2half_rn(r1 - __half2float(m));
     const __half one = __float2half_rn(ok ? 1.0f : 0.0f);   // a window outside the fp16 range takes the exact path: keep its row finite
-    row_aug[0] = h; row_aug[1] = m; row_aug[2] = l;
-    row_aug[3] = one; row_aug[4] = one; row_aug[5] = one;
+    X[kt_off(row, aug0 + 0, KB)] = h; X[kt_off(row, aug0 + 1, KB)] = m; X[kt_off(row, aug0 + 2, KB)] = l;
+    X[kt_off(row, aug0 + 3, KB)] = one; X[kt_off(row, aug0 + 4, KB)] = one; X[kt_off(row, aug0 + 5, KB)] = one;
 }
 
 #define HAF_FT_WT 2
@@ -674,7 +684,7 @@ __global__ void __launch_bounds__(256, 4) features_tc_kernel(const float* __rest
                                                              const DimFeat* __restrict__ table, int D, int Krow, float lower,
                                                              int emulate_text, const Round4Tab* __restrict__ rtab,
                                                              __half* __restrict__ Xh, __half* __restrict__ Xl /*NULL: hi only*/, float* __restrict__ xn,
-                                                             int aug0 /*first of the six extra operand columns (svm_tc.cuh)*/) {
+                                                             int aug0 /*first of the six extra operand columns (svm_tc.cuh)*/, int KB /*k-blocks of the tiled layout*/) {
     constexpr int WT = HAF_FT_WT, NW = 32 * WT;
     extern __shared__ uint32_t s_words[];  // tile [NW][KPASS+1] of (hi | lo << 16); then float s_int[ROWS][ld .. ld + 31]
     const unsigned W = *win_count;
@@ -852,13 +862,13 @@ __global__ void __launch_bounds__(256, 4) features_tc_kernel(const float* __rest
             const unsigned ww = w0 + wi;
             if (ww >= W) break;
             const uint32_t* sw = s_words + wi * rs;
-            uint32_t* gh = reinterpret_cast<uint32_t*>(Xh + (size_t)ww * Krow + d0);
-            uint32_t* gl = Xl ? reinterpret_cast<uint32_t*>(Xl + (size_t)ww * Krow + d0) : nullptr;   // one / two products: hi only
+            // k-block tiled layout (kt_off): the 64 dimensions of a k-block are 128 contiguous bytes of this window's tile row
             for (int e = lane; e < KP / 2; e += 32) {
                 const int blk = (e >> 5) << 6, nbh = min(64, KP - blk) >> 1;
                 const uint32_t a0 = sw[blk + (e & 31)], a1 = sw[blk + nbh + (e & 31)];   // dims 2e, 2e+1: (hi | lo << 16)
-                gh[e] = __byte_perm(a0, a1, 0x5410);     // hi(2e) | hi(2e+1) << 16
-                if (gl) gl[e] = __byte_perm(a0, a1, 0x7632);     // lo(2e) | lo(2e+1) << 16
+                const size_t off = kt_off(ww, d0 + 2 * e, KB);
+                *reinterpret_cast<uint32_t*>(Xh + off) = __byte_perm(a0, a1, 0x5410);             // hi(2e) | hi(2e+1) << 16
+                if (Xl) *reinterpret_cast<uint32_t*>(Xl + off) = __byte_perm(a0, a1, 0x7632);     // lo(2e) | lo(2e+1) << 16 (three products only)
             }
         }
     }
@@ -876,7 +886,7 @@ __global__ void __launch_bounds__(256, 4) features_tc_kernel(const float* __rest
         // -|x|^2 / 2 has to fit the fp16 extra columns as well (|x|^2 / 2 <= 65504)
         const bool ok = sq < 1.3e5f;
         xn[w0 + threadIdx.x] = ok ? sq : __int_as_float(0x7f800000);
-        write_aug_columns(Xh + (size_t)(w0 + threadIdx.x) * Krow + aug0, ok ? sq : 0.0f, ok);
+        write_aug_columns(Xh, w0 + threadIdx.x, aug0, KB, ok ? sq : 0.0f, ok);
     }
 }
 
@@ -1500,9 +1510,9 @@ __global__ void csr_to_dense_kernel(const long long* __restrict__ row_ptr, const
         if (i >= 1 && i <= width) dense[(size_t)r * width + (i - 1)] = value[e];
     }
 }
-// SVM operands of given inputs: tensor mode (Xh != NULL): fp16 hi/lo rows [row][Krow] + ||x||^2 of the float values;
+// SVM operands of given inputs: tensor mode (Xh != NULL): fp16 hi/lo in the k-block tiled layout (kt_off) + ||x||^2 of the float values;
 // SIMT mode (Xf != NULL): feature-major floats [Kpad][ldx] + ||x||^2.  One warp per row.
-__global__ void __launch_bounds__(256) pack_svm_inputs_kernel(const double* __restrict__ dense, int n_rows, int width, int Krow,
+__global__ void __launch_bounds__(256) pack_svm_inputs_kernel(const double* __restrict__ dense, int n_rows, int width, int Krow, int KB,
                                                               __half* __restrict__ Xh, __half* __restrict__ Xl /*NULL: hi only*/, float* __restrict__ Xf,
                                                               size_t ldx, int Kpad, float* __restrict__ xn) {
     const int lane = threadIdx.x & 31;
@@ -1516,8 +1526,8 @@ __global__ void __launch_bounds__(256) pack_svm_inputs_kernel(const double* __re
             const float xc = fminf(fmaxf(xf, -65504.0f), 65504.0f);
             const __half hi = __float2half_rn(xc);
             const __half lo = __float2half_rn(xc - __half2float(hi));
-            Xh[(size_t)r * Krow + d] = hi;
-            if (Xl) Xl[(size_t)r * Krow + d] = lo;
+            Xh[kt_off((size_t)r, d, KB)] = hi;
+            if (Xl) Xl[kt_off((size_t)r, d, KB)] = lo;
             const float v = __half2float(hi) + __half2float(lo);
             sq = fmaf(v, v, sq);
             if (!(fabsf(xf) < 65504.0f)) sq = __int_as_float(0x7f800000);   // clamped or NaN: force the exact path
@@ -1532,7 +1542,7 @@ __global__ void __launch_bounds__(256) pack_svm_inputs_kernel(const double* __re
     if (lane == 0) {
         const bool ok = !Xh || sq < 1.3e5f;
         xn[r] = ok ? sq : __int_as_float(0x7f800000);
-        if (Xh) write_aug_columns(Xh + (size_t)r * Krow + width, ok ? sq : 0.0f, ok);   // extra operand columns (svm_tc.cuh)
+        if (Xh) write_aug_columns(Xh, (size_t)r, width, KB, ok ? sq : 0.0f, ok);   // extra operand columns (svm_tc.cuh)
     }
 }
 // predicted label per row: dec > 0 ? label[0] : label[1]   (svm.cpp:2516-2531)

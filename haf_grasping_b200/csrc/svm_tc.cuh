@@ -30,7 +30,8 @@
 //   svm_rbf_tc3_kernel (default where passes == 1 and Krow <= 512): CTA pair (cta_group::2), the pair's X tiles RESIDENT
 //       in shared memory across the SV tiles, SV half tiles streamed through a TMA ring, eight epilogue warps.
 //   svm_rbf_tc2_kernel : CTA pair, X and SV both streamed (passes 2 / 3, very wide models).
-//   svm_rbf_tc_kernel  : single CTA (cta_group::1), kept as the reference point.
+//   (round 1's single-CTA cta_group::1 kernel is gone: L2 -> SM bound by construction, DESIGN.md.)
+// Operands are stored k-block tiled (kernels.cuh, kt_off): every TMA box is one contiguous 16 KB block.
 // Common structure: one persistent CTA per SM, warp specialised: warp 0 = TMA producer (cp.async.bulk.tensor 2D,
 // 128B-swizzled K-major tiles, mbarrier complete_tx), warp 1 = one elected thread issuing tcgen05.mma.kind::f16 into one
 // of two 128x256 (256x256 per pair) FP32 accumulators in TMEM (all 512 columns) and tcgen05.commit, the other warps =
@@ -48,11 +49,7 @@ constexpr int BM = 128;      // windows per tile (UMMA M)
 constexpr int BN = 256;      // support vectors per tile (UMMA N)
 constexpr int BK = 64;       // fp16 elements per k-block = 128 bytes = one swizzle row
 constexpr int NAUG = 6;      // extra operand columns (see OPERAND FORMAT)
-constexpr int STAGES = 2;
 constexpr int A_TILE_BYTES = BM * BK * 2;   // 16 KB
-constexpr int B_TILE_BYTES = BN * BK * 2;   // 32 KB
-constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;  // 96 KB
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int THREADS = 192;
 constexpr int TAB_SMEM_MAX = 4096;   // support vectors whose coef fits next to the operand ring (4 B each)
 
@@ -185,131 +182,6 @@ __device__ __forceinline__ void stage_coef_table(uint32_t tab_base, const float*
 // exponent argument, which grows with the magnitude of the numbers the argument is assembled from -- a flat fraction of
 // sum |coef| K under-estimates it by that factor for models with a large gamma (measured: tools/dec_error_probe.py).
 // Windows with |dec| <= guard_rel * (E + |rho|) are re-evaluated by the FP64 guard tiers.
-__global__ void __launch_bounds__(THREADS, 1)
-svm_rbf_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl,
-                  const __grid_constant__ CUtensorMap tmSh, const __grid_constant__ CUtensorMap tmSl,
-                  const float* __restrict__ xn, const float* __restrict__ svcoef, float c, const unsigned* __restrict__ win_count,
-                  int n_ntiles, int nsplit, int kblocks, int last_slices, double* __restrict__ dec_acc, float* __restrict__ asum_acc, int tab_smem, float csvn_max, int passes) {
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // 128B swizzle needs 1024-byte aligned tiles
-    const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
-    const uint32_t bar_full = bar_base;                 // [STAGES]
-    const uint32_t bar_empty = bar_base + 8 * STAGES;   // [STAGES]
-    const uint32_t bar_tfull = bar_base + 16 * STAGES;  // [2]
-    const uint32_t bar_tempty = bar_tfull + 16;         // [2]
-    const uint32_t tmem_slot = bar_tempty + 16;         // u32
-    const uint32_t tab_base = bar_base + 256;           // float [n_ntiles * BN] when tab_smem
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (tab_smem) stage_coef_table(tab_base, svcoef, n_ntiles * BN, THREADS);
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        for (int a = 0; a < 2; a++) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 128); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    uint32_t tmem_base;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-
-    const unsigned W = *win_count;
-    const int n_mtiles = (int)((W + BM - 1) / BM);
-    const int items = n_mtiles * nsplit;
-    const int nt_per = (n_ntiles + nsplit - 1) / nsplit;
-
-    if (warp == 0) {
-        if (lane == 0) {  // ===== TMA producer =====
-            uint32_t it = 0;
-            for (int item = blockIdx.x; item < items; item += gridDim.x) {
-                const int mt = item / nsplit, sp = item - mt * nsplit;
-                const int nt0 = sp * nt_per, nt1 = min(n_ntiles, nt0 + nt_per);
-                for (int nt = nt0; nt < nt1; nt++)
-                    for (int kb = 0; kb < kblocks; kb++, it++) {
-                        const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
-                        mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-                        const uint32_t st = smem_base + s * STAGE_BYTES;
-                        // only the operand tiles the chosen number of passes reads are fetched
-                        mbar_expect_tx(bar_full + 8 * s, A_TILE_BYTES + B_TILE_BYTES + (passes >= 2 ? B_TILE_BYTES : 0) + (passes >= 3 ? A_TILE_BYTES : 0));
-                        tma_load_2d(st, &tmXh, kb * BK, mt * BM, bar_full + 8 * s);
-                        if (passes >= 3) tma_load_2d(st + A_TILE_BYTES, &tmXl, kb * BK, mt * BM, bar_full + 8 * s);
-                        tma_load_2d(st + 2 * A_TILE_BYTES, &tmSh, kb * BK, nt * BN, bar_full + 8 * s);
-                        if (passes >= 2) tma_load_2d(st + 2 * A_TILE_BYTES + B_TILE_BYTES, &tmSl, kb * BK, nt * BN, bar_full + 8 * s);
-                    }
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {  // ===== MMA issuer =====
-            uint32_t it = 0, acc_it = 0;
-            for (int item = blockIdx.x; item < items; item += gridDim.x) {
-                const int mt = item / nsplit, sp = item - mt * nsplit;
-                const int nt0 = sp * nt_per, nt1 = min(n_ntiles, nt0 + nt_per);
-                for (int nt = nt0; nt < nt1; nt++, acc_it++) {
-                    const uint32_t a = acc_it & 1u, aph = (acc_it >> 1) & 1u;
-                    mbar_wait(bar_tempty + 8 * a, aph ^ 1u);  // epilogue has drained this accumulator
-                    tc_fence_after();
-                    const uint32_t tmem_d = tmem_base + a * BN;
-                    for (int kb = 0; kb < kblocks; kb++, it++) {
-                        const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
-                        mbar_wait(bar_full + 8 * s, ph);
-                        tc_fence_after();
-                        const uint32_t st = smem_base + s * STAGE_BYTES;
-                        const uint64_t d_ah = make_desc_sw128(st), d_al = make_desc_sw128(st + A_TILE_BYTES);
-                        const uint64_t d_bh = make_desc_sw128(st + 2 * A_TILE_BYTES), d_bl = make_desc_sw128(st + 2 * A_TILE_BYTES + B_TILE_BYTES);
-                        const int slices = (kb == kblocks - 1) ? last_slices : (BK / 16);
-                        for (int k = 0; k < slices; k++) {
-                            const uint64_t adv = (uint64_t)(k * 2);  // 16 fp16 = 32 bytes = 2 x 16-byte units
-                            tc_mma(tmem_d, d_ah + adv, d_bh + adv, IDESC, (kb | k) ? 1u : 0u);
-                            if (passes >= 2) tc_mma(tmem_d, d_ah + adv, d_bl + adv, IDESC, 1u);
-                            if (passes >= 3) tc_mma(tmem_d, d_al + adv, d_bh + adv, IDESC, 1u);
-                        }
-                        tc_commit(bar_empty + 8 * s);  // smem stage free once these MMAs have read it
-                    }
-                    tc_commit(bar_tfull + 8 * a);      // accumulator complete
-                }
-            }
-        }
-    } else {  // ===== epilogue warps 2..5 =====
-        const int q = warp & 3;  // TMEM lane quarter this warp may access
-        uint32_t acc_it = 0;
-        const float c2 = -2.0f * c;
-        for (int item = blockIdx.x; item < items; item += gridDim.x) {
-            const int mt = item / nsplit, sp = item - mt * nsplit;
-            const int nt0 = sp * nt_per, nt1 = min(n_ntiles, nt0 + nt_per);
-            const unsigned m = (unsigned)mt * BM + q * 32 + lane;
-            const float u = (m < W) ? c * xn[m] : 0.0f;
-            double dsum = 0.0;
-            float asum = 0.0f;
-            for (int nt = nt0; nt < nt1; nt++, acc_it++) {
-                const uint32_t a = acc_it & 1u, aph = (acc_it >> 1) & 1u;
-                mbar_wait(bar_tfull + 8 * a, aph);
-                tc_fence_after();
-                const uint32_t tab_s = tab_smem ? tab_base + (uint32_t)nt * BN * 4u : 0u;
-                const float ps = epilogue_columns<BN>(tmem_base + ((uint32_t)(q * 32) << 16) + a * BN, tab_s, svcoef + (size_t)nt * BN, 0, c2);
-                tc_fence_before();
-                mbar_arrive(bar_tempty + 8 * a);
-                dsum += (double)ps;
-                asum += fabsf(ps);   // = sum |coef_i| K_i of the tile (uniform sign)
-            }
-            if (m < W && nt1 > nt0) {
-                atomicAdd(dec_acc + m, dsum);
-                atomicAdd(asum_acc + m, (1.0f - u + csvn_max) * asum);   // E: the scale of the FP32 error (GUARD SCALE)
-            }
-        }
-    }
-    __syncwarp();  // the role loops run on one elected lane: reconverge before the block-wide barrier
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
-    }
-}
-
 // ==================================================================================================================
 // CTA-pair variant (cta_group::2).  The single-CTA kernel above is bound by L2 -> shared-memory bandwidth: 96 KB per
 // 1536 MMA clocks = 64 B/clk/SM against a measured ~42-46 B/clk/SM (ncu: xbar2l1tex 11.7 TB/s, tensor pipe 60-73 %).
@@ -413,19 +285,20 @@ svm_rbf_tc2_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_consta
             for (int item = cid; item < items; item += ncl) {
                 const int mp = item / nsplit, sp = item - mp * nsplit;
                 const int nt0 = sp * nt_per, nt1 = min(n_ntiles, nt0 + nt_per);
-                const int mrow = (2 * mp + (int)rank) * BM;
+                const int xtile = (2 * mp + (int)rank) * kblocks;   // k-block tiled layout (kernels.cuh, kt_off): tile (row tile, kb) = 128 box rows
                 for (int nt = nt0; nt < nt1; nt++)
                     for (int kb = 0; kb < kblocks; kb++, it++) {
                         const uint32_t s = it % STAGES2, ph = (it / STAGES2) & 1u;
                         mbar_wait(bar_empty + 8 * s, ph ^ 1u);
                         const uint32_t st = smem_base + s * STAGE2_BYTES;
                         const uint32_t lfull = (bar_full + 8 * s) & PEER_MASK;  // the LEADER's full barrier
+                        const int svtile = ((2 * nt + (int)rank) * kblocks + kb) * BM;
                         // only the operand tiles the chosen number of passes reads are fetched
                         if (leader) mbar_expect_tx(bar_full + 8 * s, 2 * (A_TILE_BYTES + B2_TILE_BYTES + (passes >= 2 ? B2_TILE_BYTES : 0) + (passes >= 3 ? A_TILE_BYTES : 0)));
-                        tma_load_2d_2sm(st, &tmXh, kb * BK, mrow, lfull);
-                        if (passes >= 3) tma_load_2d_2sm(st + A_TILE_BYTES, &tmXl, kb * BK, mrow, lfull);
-                        tma_load_2d_2sm(st + 2 * A_TILE_BYTES, &tmSh2, kb * BK, nt * BN + (int)rank * (BN / 2), lfull);
-                        if (passes >= 2) tma_load_2d_2sm(st + 2 * A_TILE_BYTES + B2_TILE_BYTES, &tmSl2, kb * BK, nt * BN + (int)rank * (BN / 2), lfull);
+                        tma_load_2d_2sm(st, &tmXh, 0, (xtile + kb) * BM, lfull);
+                        if (passes >= 3) tma_load_2d_2sm(st + A_TILE_BYTES, &tmXl, 0, (xtile + kb) * BM, lfull);
+                        tma_load_2d_2sm(st + 2 * A_TILE_BYTES, &tmSh2, 0, svtile, lfull);
+                        if (passes >= 2) tma_load_2d_2sm(st + 2 * A_TILE_BYTES + B2_TILE_BYTES, &tmSl2, 0, svtile, lfull);
                     }
             }
         }
@@ -520,7 +393,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS3, 1)
 svm_rbf_tc3_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmSh2,
                    const float* __restrict__ xn, const float* __restrict__ svcoef, float c, const unsigned* __restrict__ win_count,
                    int n_ntiles, int nsplit, int kblocks, int last_slices, int stages, double* __restrict__ dec_acc, float* __restrict__ asum_acc,
-                   int tab_smem, float csvn_max) {
+                   int tab_smem, float csvn_max, int dbg /*timing experiments only (tools/tc_pipeline_probe.py): 1 no epilogue work, 2 no MMAs, 4 TMEM loads only, 8 math only*/) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t x_base = smem_base;                                     // [kblocks] X_hi tiles of the current item (16 KB each)
@@ -568,18 +441,18 @@ svm_rbf_tc3_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_consta
                 const int mp = item / nsplit, sp = item - mp * nsplit;
                 const int nt0 = sp * nt_per, nt1 = min(n_ntiles, nt0 + nt_per);
                 if (nt0 >= nt1) continue;   // an empty split touches no barrier in any role
-                const int mrow = (2 * mp + (int)rank) * BM;
+                const int xtile = (2 * mp + (int)rank) * kblocks;   // k-block tiled layout (kernels.cuh, kt_off): tile (row tile, kb) = 128 box rows
                 for (int nt = nt0; nt < nt1; nt++)
                     for (int kb = 0; kb < kblocks; kb++, it++) {
                         if (nt == nt0) {   // this item's X tile kb, as soon as the previous item's last SV tile has let go of it
                             mbar_wait(bar_xempty + 8 * kb, (xi & 1u) ^ 1u);
                             if (leader) mbar_expect_tx(bar_xfull + 8 * kb, 2 * A_TILE_BYTES);
-                            tma_load_2d_2sm(x_base + (uint32_t)kb * A_TILE_BYTES, &tmXh, kb * BK, mrow, (bar_xfull + 8 * kb) & PEER_MASK);
+                            tma_load_2d_2sm(x_base + (uint32_t)kb * A_TILE_BYTES, &tmXh, 0, (xtile + kb) * BM, (bar_xfull + 8 * kb) & PEER_MASK);
                         }
                         const uint32_t s = it % (uint32_t)stages, ph = (it / (uint32_t)stages) & 1u;
                         mbar_wait(bar_sempty + 8 * s, ph ^ 1u);
                         if (leader) mbar_expect_tx(bar_sfull + 8 * s, 2 * B2_TILE_BYTES);
-                        tma_load_2d_2sm(ring_base + s * B2_TILE_BYTES, &tmSh2, kb * BK, nt * BN + (int)rank * (BN / 2), (bar_sfull + 8 * s) & PEER_MASK);
+                        tma_load_2d_2sm(ring_base + s * B2_TILE_BYTES, &tmSh2, 0, ((2 * nt + (int)rank) * kblocks + kb) * BM, (bar_sfull + 8 * s) & PEER_MASK);
                     }
                 xi++;
             }
@@ -606,7 +479,7 @@ svm_rbf_tc3_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_consta
                         const int slices = (kb == kblocks - 1) ? last_slices : (BK / 16);
                         for (int k = 0; k < slices; k++) {
                             const uint64_t adv = (uint64_t)(k * 2);
-                            tc_mma_2sm(tmem_d, d_a + adv, d_b + adv, IDESC2, (kb | k) ? 1u : 0u);
+                            if (!(dbg & 2)) tc_mma_2sm(tmem_d, d_a + adv, d_b + adv, IDESC2, (kb | k) ? 1u : 0u);
                         }
                         tc_commit_2sm_mc(bar_sempty + 8 * s);                       // SV stage free in BOTH CTAs
                         if (nt == nt1 - 1) tc_commit_2sm_mc(bar_xempty + 8 * kb);   // last use of X tile kb by this item
@@ -633,7 +506,24 @@ svm_rbf_tc3_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_consta
                 mbar_wait(bar_tfull + 8 * a, aph);
                 tc_fence_after();
                 const uint32_t tab_s = tab_smem ? tab_base + (uint32_t)nt * BN * 4u : 0u;
-                const float ps = epilogue_columns<BN / 2>(tmem_base + ((uint32_t)(q * 32) << 16) + a * BN + h * (BN / 2), tab_s, svcoef + (size_t)nt * BN, h * (BN / 2), c2);
+                float ps = 0.0f;
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * BN + h * (BN / 2);
+                if (dbg == 0 || (dbg & 2)) ps = epilogue_columns<BN / 2>(taddr, tab_s, svcoef + (size_t)nt * BN, h * (BN / 2), c2);
+                else if (dbg & 4) {   // TMEM loads only
+                    uint32_t ra[32], acc = 0;
+                    for (int ch = 0; ch < BN / 64; ch++) {
+                        HAFTC_LD32(taddr + ch * 32, ra);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                        for (int j = 0; j < 32; j++) acc ^= ra[j];
+                    }
+                    ps = __uint_as_float(acc & 0x3fffffffu);
+                } else if (dbg & 8) {   // epilogue arithmetic only, on made-up accumulator values
+                    uint32_t ra[32];
+#pragma unroll
+                    for (int j = 0; j < 32; j++) ra[j] = __float_as_uint(-(float)(j + lane));
+                    for (int ch = 0; ch < BN / 64; ch++) { epilogue_chunk(ra, tab_s, svcoef + (size_t)nt * BN, h * (BN / 2) + ch * 32, c2, ps); ra[ch & 31] ^= __float_as_uint(ps) & 0xff; }
+                }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster((bar_tempty + 8 * a) & PEER_MASK);   // on the LEADER's barrier (count 16)

@@ -59,9 +59,12 @@ typedef struct {
     float guard_rel;           /* guard band half-width as a fraction of E + |rho|,
                                   E = sum_i |coef_i| K_i (1 + gamma log2(e) (|x|^2 + |sv_i|^2)); <=0 -> default
                                   (4e-6 tensor, 2e-6 FP32 SIMT: >= 12x the measured error)                    */
-    int reserved[4];           /* [0]: bit 0: tensor-path kernel variant, 0 = CTA-pair (cta_group::2, default), 1 = single CTA;
+    int reserved[4];           /* [0]: bits 0-1: tensor-path kernel, 0 = auto (X-resident CTA pair where one product is in use, else the
+                                       streaming CTA pair; both cta_group::2), 2 = streaming CTA pair always;
                                        bits 4-5: tensor-core products per k-slice, 0 = calibrated per model (default), 1 / 2 / 3 forced;
-                                  [1]: 1 = always use the point-parallel binning kernel (no whole-cloud CTAs);
+                                       bit 8: audit sample off; bits 16+: audit every n-th window (default 4096; see haf_timing);
+                                  [1]: 1 = always use the point-parallel binning kernel (no whole-cloud CTAs), 2 = whole-cloud kernel
+                                       with scalar loads;
                                   [2]: guard band tier 2 (FP64 FMA re-evaluation): 0 = on, 1 = off (every guard window goes
                                        to the exact-order kernels), 2 = on, but every window escalates as well (tests);
                                   [3]: 1 = tensor kernels read the {c|sv|^2, coef} table from global memory even when it fits in
@@ -187,6 +190,9 @@ int haf_scale_apply(int device, const long long* row_ptr, const int* index, cons
  * and the ordered key that turns "strictly greater wins, earliest unit wins ties" into a max-reduction, for the
  * cross-GPU best-grasp exchange. */
 int haf_build_transform(const haf_request* req, int roll, int roll_step_deg, float M_rowmajor[16]);
+/* the same chain as transform_gp_in_wcs_and_publish rebuilds it for the grasp points (:1276-1334): there the two angles come
+ * from the double members approach_vector.{x,y,z} (:1293-1303), not from the float copy generate_grid uses (:418-420) */
+int haf_build_transform_wcs(const haf_request* req, int roll, int roll_step_deg, float M_rowmajor[16]);
 uint64_t haf_best_key(int topval, uint32_t unit_order);
 /* records [n][8] int32 = {topval, row, col, roll, tilt, approach_idx, n_windows_scored, rolls_done}: the 32-byte record
  * of the cross-GPU best-grasp exchange, e.g. straight into a pinned buffer an NCCL all-gather reads */

@@ -68,8 +68,22 @@ static void mat4_identity(float* A) {
 // orc_normalize_approach (doubles, as stored in this->approach_vector); roll index.
 // M out: row-major mat_transform = S * Rroll * T2 * Rx * Rz * T1 evaluated left to right
 // (server.cpp:483).
+// wcs != 0: the same chain as transform_gp_in_wcs_and_publish rebuilds it (:1276-1334): there the two angles come from
+// the DOUBLE members this->approach_vector.{x,y,z} (double atan2 / sqrt, :1293-1303), not from the float PointXYZ copy
+// generate_grid uses (:418-420, :444-454) -- for a tilted approach vector the two matrices differ in the last bits
+// (found by tests/test_oracle_vs_refserver.py against the reference's own compiled server).
+static void orc_build_transform_impl(const double center[3], const double av[3], int gripper_opening_width, int roll,
+                                     int roll_step_deg, int wcs, float M[16]);
 void orc_build_transform(const double center[3], const double av[3], int gripper_opening_width, int roll,
                          int roll_step_deg, float M[16]) {
+    orc_build_transform_impl(center, av, gripper_opening_width, roll, roll_step_deg, 0, M);
+}
+void orc_build_transform_wcs(const double center[3], const double av[3], int gripper_opening_width, int roll,
+                             int roll_step_deg, float M[16]) {
+    orc_build_transform_impl(center, av, gripper_opening_width, roll, roll_step_deg, 1, M);
+}
+static void orc_build_transform_impl(const double center[3], const double av[3], int gripper_opening_width, int roll,
+                                     int roll_step_deg, int wcs, float M[16]) {
     float avx = (float)av[0], avy = (float)av[1], avz = (float)av[2];  // :418-420 (PointXYZ floats)
     float S[16], T1[16], Rz[16], Rx[16], T2[16], Rr[16];
     mat4_identity(S); mat4_identity(T1); mat4_identity(Rz); mat4_identity(Rx); mat4_identity(T2); mat4_identity(Rr);
@@ -83,7 +97,16 @@ void orc_build_transform(const double center[3], const double av[3], int gripper
     T2[11] = 0 + trans_z_after_pc_transform;  // :439-441
 
     float rot_about_z, rot_about_x = 0;
-    if (avy == 0 && avx == 0) {  // :444-450
+    if (wcs) {   // :1293-1303, double members
+        if (av[1] == 0 && av[0] == 0) {
+            rot_about_z = 0;
+            if (av[2] >= 0) rot_about_x = 0;
+            else rot_about_x = (float)ORC_PI;
+        } else {
+            rot_about_z = (float)(90 * ORC_PI / 180.0 - atan2(av[1], av[0]));
+            rot_about_x = (float)(90 * ORC_PI / 180.0 - atan2(av[2], sqrt(av[1] * av[1] + av[0] * av[0])));
+        }
+    } else if (avy == 0 && avx == 0) {  // :444-450
         rot_about_z = 0;
         if (avz >= 0) rot_about_x = 0;
         else rot_about_x = (float)ORC_PI;
@@ -728,7 +751,9 @@ void orc_transform_gp_in_wcs(const double center[3], const double av_raw[3], int
     double av[3];
     orc_normalize_approach(av_raw, av);
     float M[16], Minv[16];
-    orc_build_transform(center, av, gripper_opening_width, nr_roll_top_all < 0 ? 0 : nr_roll_top_all, roll_step_deg, M);
+    orc_build_transform_wcs(center, av, gripper_opening_width, nr_roll_top_all < 0 ? 0 : nr_roll_top_all, roll_step_deg, M);   // :1276-1334
+    float Mgrid[16];   // av_trans_mat = generate_grid's matrix of the last evaluated roll (:484); its third row is roll-invariant
+    orc_build_transform(center, av, gripper_opening_width, nr_roll_top_all < 0 ? 0 : nr_roll_top_all, roll_step_deg, Mgrid);
     float x_gp_roll = -((float)(G / 2 - id_row_top_all)) / 100;  // :1339
     float y_gp_roll = -((float)(G / 2 - id_col_top_all)) / 100;  // :1340
     float h_locmax_roll = -10;
@@ -751,7 +776,7 @@ void orc_transform_gp_in_wcs(const double center[3], const double av_raw[3], int
     out[0] = g1[0]; out[1] = g1[1]; out[2] = g1[2];
     out[3] = g2[0]; out[4] = g2[1]; out[5] = g2[2];
     out[6] = (g1[0] + g2[0]) / 2.0; out[7] = (g1[1] + g2[1]) / 2.0; out[8] = (g1[2] + g2[2]) / 2.0;  // :1395-1397
-    out[9] = M[8]; out[10] = M[9]; out[11] = M[10];  // :1370-1374
+    out[9] = Mgrid[8]; out[10] = Mgrid[9]; out[11] = Mgrid[10];  // :1370-1374: third row of av_trans_mat (generate_grid's matrix)
     out[12] = (float)((nr_roll_top_all * roll_step_deg * ORC_PI) / 180);  // :1401
 }
 

@@ -14,6 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "libhaf_oracle.so")
 REF_DIR = os.path.join(HERE, "_ref")
 REF_SO = os.path.join(REF_DIR, "libhaf_ref.so")
+REFSERVER_SO = os.path.join(REF_DIR, "libhaf_refserver.so")
 
 
 def build(ref: bool = True) -> None:
@@ -302,3 +303,54 @@ class Ref:
                 os.remove(f)
             os.rmdir(wd)
         return np.array(labels, np.int32), scaled_lines
+
+
+def refserver_available() -> bool:
+    return os.path.exists(REFSERVER_SO) and os.path.exists(os.path.join(REF_DIR, "pkg", "libsvm-3.12", "svm-predict"))
+
+
+class RefServer:
+    """The reference's own action server class CCalc_Grasppoints (src/calc_grasppoints_action_server.cpp compiled in place,
+    unmodified, against stand-in ROS / PCL / Eigen / OpenCV headers: oracle/server_shim.cpp, oracle/stub_server).  One goal
+    runs read_pc_cb -> loop_control -> ... -> transform_gp_in_wcs_and_publish as the reference wrote them, child processes
+    and /tmp/features.txt included (so: one RefServer goal at a time per machine)."""
+
+    def __init__(self, features_path: str, range_path: str, model_path: str):
+        if not refserver_available():
+            raise RuntimeError("oracle/_ref/libhaf_refserver.so not built (run `make -C oracle ref` where /root/reference exists)")
+        L = self.L = C.CDLL(REFSERVER_SO)
+        L.refsrv_new.restype = C.c_void_p
+        L.refsrv_new.argtypes = [C.c_char_p] * 4
+        L.refsrv_free.argtypes = [C.c_void_p]
+        L.refsrv_run_goal.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_int,
+                                      C.c_int, C.c_double, C.c_int] + [C.c_void_p] * 9
+        L.refsrv_transform_of_roll.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        self.G, self.R = L.refsrv_grid(), L.refsrv_rolls()
+        self.h = L.refsrv_new(features_path.encode(), range_path.encode(), model_path.encode(), os.path.join(REF_DIR, "pkg").encode())
+
+    def close(self):
+        if self.h:
+            self.L.refsrv_free(C.c_void_p(self.h))
+            self.h = None
+
+    def run_goal(self, xyz, center=(0.0, 0.0, 0.0), area=(32.0, 44.0), approach=(0.0, 0.0, 1.0), width=1, only_best=0,
+                 max_time_s=1e6, per_roll=True):
+        xyz = np.ascontiguousarray(xyz, np.float32)
+        G, R = self.G, self.R
+        out = dict(best=np.zeros(5, np.int32), grasp=np.zeros(14, np.float64), heights=np.zeros((R, G, G), np.float32),
+                   integral=np.zeros((R, G + 1, G + 1), np.float32), mask=np.zeros((R, G, G), np.uint8),
+                   per_roll_top=np.full((R, 3), -1, np.int32), eval_pos=np.zeros((R, G, G), np.float32),
+                   eval_seen=np.zeros((R, G, G), np.uint8), M_last=np.zeros(16, np.float32))
+        c = np.array(center, np.float64)
+        a = np.array(approach, np.float64)
+        rc = self.L.refsrv_run_goal(C.c_void_p(self.h), _fp(xyz), len(xyz), xyz.strides[0] if len(xyz) else 12, _fp(c), area[0], area[1], _fp(a),
+                                    int(width), int(only_best), float(max_time_s), int(per_roll), _fp(out["best"]), _fp(out["grasp"]),
+                                    _fp(out["heights"]), _fp(out["integral"]), _fp(out["mask"]), _fp(out["per_roll_top"]),
+                                    _fp(out["eval_pos"]), _fp(out["eval_seen"]), _fp(out["M_last"]))
+        assert rc == 0
+        return out
+
+    def transform_of_roll(self, roll):
+        M = np.zeros(16, np.float32)
+        self.L.refsrv_transform_of_roll(C.c_void_p(self.h), int(roll), _fp(M))
+        return M

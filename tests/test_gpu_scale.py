@@ -15,7 +15,7 @@ import numpy as np
 import pytest
 
 from conftest import FEATURES, RANGE
-from model_io import coefK_sum, load_model_arrays
+from model_io import check_decision_tolerance, load_model_arrays
 
 pytestmark = pytest.mark.gpu
 
@@ -154,9 +154,7 @@ def test_config4_grid512_one_roll_features_and_2048_sv(hg, oracle_lib, tmp_model
                 hashlib.sha1(np.ascontiguousarray(p["scaled"][:, :gpu.D]).tobytes()).hexdigest(), p["k"]
         o_lab = np.where(o["dec"] > 0, gpu.info.label0, gpu.info.label1)
         assert np.array_equal(lab, o_lab), int((lab != o_lab).sum())
-        scale = coefK_sum(load_model_arrays(model), o["scaled"][:, :gpu.D])
-        err = np.abs(dec - o["dec"])
-        assert (err <= 1e-5 * scale).all(), float((err / scale).max())
+        check_decision_tolerance(load_model_arrays(model), o["scaled"][:, :gpu.D], dec, o["dec"])
     finally:
         gpu.close()
         _XYZ.pop("g512", None)
@@ -276,10 +274,7 @@ def test_models_far_from_the_calibration_probes(hg, oracle_lib, tmp_models, clou
             assert np.array_equal(lab, np.where(ores["dec"] > 0, gpu.info.label0, gpu.info.label1))
             assert np.array_equal(res["graspseval"][0], ores["graspseval"])
             assert res["best"].astuple() == ores["best"].astuple()
-            scale = coefK_sum(mdl, scaled)
-            err = np.abs(dec - ores["dec"])
-            ok = err <= 1e-5 * scale + 1e-300
-            assert ok.all(), float((err / np.maximum(scale, 1e-300)).max())
+            check_decision_tolerance(mdl, scaled, dec, ores["dec"])
             t = gpu.timing()
             assert t.audit_max_rel <= 0.25 * gpu.info.reserved[1] * 1e-9
     finally:
