@@ -27,7 +27,8 @@ class haf_config(C.Structure):
     _fields_ = [("features_path", C.c_char_p), ("range_path", C.c_char_p), ("model_path", C.c_char_p),
                 ("nr_features_without_shaf", C.c_int), ("grid", C.c_int), ("roll_step_deg", C.c_int),
                 ("roll_max_deg", C.c_int), ("device", C.c_int), ("emulate_text_roundtrip", C.c_int),
-                ("svm_mode", C.c_int), ("guard_rel", C.c_float), ("reserved", C.c_int * 4)]
+                ("svm_mode", C.c_int), ("guard_rel", C.c_float), ("reserved", C.c_int * 4), ("n_devices", C.c_int),
+                ("devices", C.POINTER(C.c_int))]
 
 
 class haf_request(C.Structure):
@@ -63,7 +64,7 @@ class haf_timing(C.Structure):
 EXPORTS = ["haf_create", "haf_destroy", "haf_last_error", "haf_get_info", "haf_set_stream", "haf_set_profiling",
            "haf_get_timing", "haf_launch_count", "haf_set_debug", "haf_search", "haf_search_batch", "haf_search_batch_packed",
            "haf_build_transform", "haf_build_transform_wcs", "haf_best_key", "haf_pack_best_records", "haf_debug_window_count", "haf_debug_windows", "haf_debug_features",
-           "haf_debug_decisions", "haf_debug_tensor_inputs", "haf_debug_integral", "haf_debug_cell_indices", "haf_debug_text_roundtrip",
+           "haf_debug_decisions", "haf_debug_tensor_inputs", "haf_debug_integral", "haf_debug_cell_indices", "haf_debug_text_roundtrip", "haf_debug_tc_probe",
            "haf_version", "haf_svm_create", "haf_svm_destroy", "haf_svm_predict", "haf_scale_minmax", "haf_scale_apply"]
 
 _lib = None
@@ -113,6 +114,7 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     L.haf_debug_integral.argtypes = [vp, vp, cs]
     L.haf_debug_cell_indices.argtypes = [vp, vp, cs, cs, C.POINTER(haf_request), ci, vp]
     L.haf_debug_text_roundtrip.argtypes = [vp, vp, ci, vp, vp, ci, vp]
+    L.haf_debug_tc_probe.argtypes = [vp, vp, ci]
     L.haf_version.restype = C.c_char_p
     L.haf_svm_create.argtypes = [C.POINTER(vp), C.c_char_p, ci, ci, ci, C.c_float]
     L.haf_svm_destroy.argtypes = [vp]
@@ -156,7 +158,8 @@ class GraspSearch:
 
     def __init__(self, features_path, range_path, model_path, grid=56, roll_step_deg=15, roll_max_deg=190,
                  nr_features_without_shaf=302, device=0, emulate_text_roundtrip=True, svm_mode=HAF_SVM_TENSOR_GUARD,
-                 guard_rel=0.0, tc_variant=0, guard_tier2=0, sv_table_global=0, tc_passes=0, audit_every=None, bin_variant=0):
+                 guard_rel=0.0, tc_variant=0, guard_tier2=0, sv_table_global=0, tc_passes=0, audit_every=None, bin_variant=0,
+                 devices=None):
         self.L = load_library()
         cfg = haf_config()
         self._keep = [features_path.encode(), range_path.encode(), model_path.encode()]
@@ -175,6 +178,10 @@ class GraspSearch:
         cfg.reserved[1] = bin_variant   # 0 auto, 1 point-parallel binning only, 2 whole-cloud kernel with scalar loads
         cfg.reserved[2] = guard_tier2   # 0 on, 1 off, 2 on + escalate everything (tests)
         cfg.reserved[3] = sv_table_global   # 1: SV table read from global memory (the > 4096-SV path)
+        if devices is not None and len(devices) > 1:   # one context driving several GPUs (haf_config.n_devices / devices)
+            self._devs = (C.c_int * len(devices))(*devices)
+            cfg.n_devices, cfg.devices = len(devices), self._devs
+            cfg.device = devices[0]
         self.h = C.c_void_p()
         rc = self.L.haf_create(C.byref(self.h), C.byref(cfg))
         if rc != 0:
@@ -313,6 +320,11 @@ class GraspSearch:
         xyz = np.ascontiguousarray(xyz, np.float32)
         out = np.zeros(len(xyz), np.int32)
         self._check(self.L.haf_debug_cell_indices(self.h, _ptr(xyz), len(xyz), xyz.strides[0], C.byref(request), roll, _ptr(out)))
+        return out
+
+    def debug_tc_probe(self, n_ctas=148):
+        out = np.zeros((n_ctas, 16), np.uint64)
+        self._check(self.L.haf_debug_tc_probe(self.h, _ptr(out), n_ctas))
         return out
 
     def debug_text_roundtrip(self, in4=None, in6=None):

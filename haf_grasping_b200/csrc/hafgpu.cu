@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/hafgpu.h"
@@ -153,6 +154,10 @@ struct haf_ctx {
     DevBuf<double> d_csr_val;
 
     // state of the last search kept for the debug entry points
+    // several GPUs behind one context (haf_config.n_devices > 1): group[0] is this context itself, the others are member
+    // contexts, one per further device, driven by one host thread each (group_search / group_batch below)
+    std::vector<haf_ctx*> group;
+    PinBuf<unsigned> h_unit_windows;   // windows per unit of the last call (the group merge replays the early exit with them)
     bool debug_keep_batch = false;   // haf_set_debug: keep the per-window state of single-chunk batch calls too
     int last_units = 0, last_unit_base = 0;
     unsigned last_W = 0;
@@ -588,7 +593,39 @@ static int create_impl(haf_ctx** out, const haf_config* cfg, bool svm_only, int 
     return HAF_OK;
 }
 
-extern "C" int haf_create(haf_ctx** out, const haf_config* cfg) { return create_impl(out, cfg, false, 0); }
+extern "C" int haf_create(haf_ctx** out, const haf_config* cfg) {
+    if (!out || !cfg) return create_fail(HAF_ERR_ARG, "haf_create: null argument");
+    if (cfg->n_devices <= 1) {
+        haf_config one = *cfg;
+        if (cfg->n_devices == 1 && cfg->devices) one.device = cfg->devices[0];
+        one.n_devices = 0; one.devices = nullptr;
+        return create_impl(out, &one, false, 0);
+    }
+    // one context per device; the first one owns the group
+    *out = nullptr;
+    if (cfg->n_devices > 64) return create_fail(HAF_ERR_ARG, "haf_create: n_devices out of range");
+    std::vector<haf_ctx*> members;
+    for (int k = 0; k < cfg->n_devices; k++) {
+        haf_config one = *cfg;
+        one.device = cfg->devices ? cfg->devices[k] : k;
+        one.n_devices = 0; one.devices = nullptr;
+        for (size_t j = 0; j < members.size(); j++)
+            if (members[j]->device == one.device) {
+                for (size_t i = 0; i < members.size(); i++) haf_destroy(members[i]);
+                return create_fail(HAF_ERR_ARG, "haf_create: devices[] names the same GPU twice");
+            }
+        haf_ctx* c = nullptr;
+        const int rc = create_impl(&c, &one, false, 0);
+        if (rc != HAF_OK) {
+            for (size_t i = 0; i < members.size(); i++) haf_destroy(members[i]);
+            return rc;   // g_create_error is set
+        }
+        members.push_back(c);
+    }
+    members[0]->group = members;
+    *out = members[0];
+    return HAF_OK;
+}
 
 // ---- libsvm front ends -------------------------------------------------------------------------
 static int svm_stage(haf_ctx* ctx, unsigned* cnt, size_t Wcap, size_t ldx, int G, int ubase, cudaStream_t st, cudaEvent_t ev_guard);
@@ -786,6 +823,8 @@ extern "C" int haf_scale_apply(int device, const long long* row_ptr, const int* 
 
 extern "C" void haf_destroy(haf_ctx* ctx) {
     if (!ctx) return;
+    for (size_t k = 1; k < ctx->group.size(); k++) haf_destroy(ctx->group[k]);   // member contexts of a multi-GPU group
+    ctx->group.clear();
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     ctx->d_feats.release(); ctx->d_dims.release(); ctx->d_svT.release(); ctx->d_svn.release(); ctx->d_coef.release();
@@ -797,7 +836,7 @@ extern "C" void haf_destroy(haf_ctx* ctx) {
     ctx->d_xdense.release(); ctx->d_labels.release(); ctx->d_csr_ptr.release(); ctx->d_csr_idx.release(); ctx->d_csr_val.release();
     ctx->d_svn64.release(); ctx->d_Xg.release(); ctx->d_g2accum.release(); ctx->d_g2tickets.release(); ctx->d_guardlist2.release();
     ctx->d_SVh.release(); ctx->d_SVl.release(); ctx->d_Xh.release(); ctx->d_Xl.release(); ctx->d_svcoef.release(); ctx->d_dec_tc.release(); ctx->d_asum.release(); ctx->d_dimfeat.release(); ctx->d_round4.release();
-    ctx->d_params.release(); ctx->d_counters.release(); ctx->h_stage.release(); ctx->h_results.release(); ctx->h_per_roll_top.release(); ctx->h_counters.release();
+    ctx->d_params.release(); ctx->d_counters.release(); ctx->h_stage.release(); ctx->h_results.release(); ctx->h_per_roll_top.release(); ctx->h_counters.release(); ctx->h_unit_windows.release();
     if (ctx->ev_ok) for (int i = 0; i < 10; i++) cudaEventDestroy(ctx->ev[i]);
     for (size_t i = 0; i < ctx->ev_pool.size(); i++) cudaEventDestroy(ctx->ev_pool[i]);
     for (size_t i = 0; i < ctx->copy_ev.size(); i++) cudaEventDestroy(ctx->copy_ev[i]);
@@ -984,8 +1023,8 @@ static int svm_stage(haf_ctx* ctx, unsigned* cnt, size_t Wcap, size_t ldx, int G
             // X-resident kernel: one product, the X tile (kblocks x 16 KB) + at least 3 ring stages + the table must fit
             int stages3 = 0;
             if (ctx->tc_variant == 0 && ctx->tc_passes == 1 && kblocks <= haftc::XK_MAX)
-                stages3 = std::min(8, (haftc::TC3_SMEM_LIMIT - haftc::tc3_smem_bytes(kblocks, 0, (int)(tab_bytes / 4))) / haftc::B2_TILE_BYTES);
-            if (stages3 >= 3)
+                stages3 = std::min(8, (haftc::TC3_SMEM_LIMIT - haftc::tc3_smem_bytes(kblocks, 0, (int)(tab_bytes / 4))) / (haftc::KBS * haftc::B2_TILE_BYTES));
+            if (stages3 >= 2)
                 haftc::svm_rbf_tc3_kernel<<<grid2, haftc::THREADS3, haftc::tc3_smem_bytes(kblocks, stages3, (int)(tab_bytes / 4)), st>>>(
                     tmXh, ctx->tmSh2, ctx->d_xn.p, ctx->d_svcoef.p, ctx->c_log2, cnt + 0, n_ntiles, nsplit2, kblocks, last_slices, stages3, ctx->d_dec.p,
                     ctx->d_asum.p, tab_smem, ctx->csvn_max, tc_debug_flags());
@@ -1272,6 +1311,10 @@ static int run_jobs_once(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& job
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_results.p, ctx->d_results.p, (size_t)n_jobs * sizeof(JobResult), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_per_roll_top.p, ctx->d_per_roll_top.p, (size_t)U * 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_counters.p, ctx->d_counters.p, 16 * 4, cudaMemcpyDeviceToHost, st));
+    if (keep_debug_state) {   // single goals: windows per unit, for the multi-GPU merge
+        ENSURE(ctx, ctx->h_unit_windows, U);
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_unit_windows.p, ctx->d_unit_windows.p, (size_t)U * 4, cudaMemcpyDeviceToHost, st));
+    }
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[9], st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
     total_windows = ctx->h_counters.p[8];
@@ -1343,9 +1386,16 @@ static int stage_points(haf_ctx* ctx, const void* src, size_t bytes, bool* is_de
     return HAF_OK;
 }
 
+static int group_search(haf_ctx* ctx, const float* xyz, size_t n_points, size_t stride_bytes, const haf_request* reqs, int n_requests,
+                        haf_best* best, haf_best* best_per_request, float* graspseval, unsigned char* mask, float* heights, int* per_roll_top);
+static int group_batch_packed(haf_ctx* ctx, const float* xyz_all, const size_t* point_offsets, int n_clouds, const haf_request* req,
+                              haf_best* best_per_cloud);
+
 extern "C" int haf_search(haf_ctx* ctx, const float* xyz, size_t n_points, size_t stride_bytes, const haf_request* reqs, int n_requests,
                           haf_best* best, haf_best* best_per_request, float* graspseval, unsigned char* mask, float* heights, int* per_roll_top) {
     if (!ctx) return HAF_ERR_ARG;
+    if (ctx->group.size() > 1)
+        return group_search(ctx, xyz, n_points, stride_bytes, reqs, n_requests, best, best_per_request, graspseval, mask, heights, per_roll_top);
     if (!reqs || n_requests < 1 || !best) return ctx->fail(HAF_ERR_ARG, "haf_search: reqs, n_requests >= 1 and best are required");
     if (n_points > 0 && !xyz) return ctx->fail(HAF_ERR_ARG, "haf_search: xyz is null");
     if (stride_bytes == 0) stride_bytes = 12;
@@ -1392,6 +1442,7 @@ extern "C" int haf_search(haf_ctx* ctx, const float* xyz, size_t n_points, size_
 extern "C" int haf_search_batch_packed(haf_ctx* ctx, const float* xyz_all, const size_t* point_offsets, int n_clouds, const haf_request* req,
                                        haf_best* best_per_cloud) {
     if (!ctx) return HAF_ERR_ARG;
+    if (ctx->group.size() > 1) return group_batch_packed(ctx, xyz_all, point_offsets, n_clouds, req, best_per_cloud);
     if (!point_offsets || n_clouds < 1 || !req || !best_per_cloud) return ctx->fail(HAF_ERR_ARG, "haf_search_batch_packed: bad arguments");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     ctx->last_valid = false;
@@ -1450,6 +1501,20 @@ extern "C" int haf_search_batch(haf_ctx* ctx, const float* const* clouds, const 
                                 haf_best* best_per_cloud) {
     if (!ctx) return HAF_ERR_ARG;
     if (!clouds || !n_points || n_clouds < 1 || !req || !best_per_cloud) return ctx->fail(HAF_ERR_ARG, "haf_search_batch: bad arguments");
+    if (ctx->group.size() > 1) {   // several GPUs: contiguous blocks of clouds, one host thread per GPU, no cross-GPU data
+        const int n = (int)ctx->group.size();
+        std::vector<int> rcs(n, HAF_OK);
+        std::vector<std::thread> th;
+        for (int k = 0; k < n; k++) {
+            const int c0 = (int)((long long)n_clouds * k / n), c1 = (int)((long long)n_clouds * (k + 1) / n);
+            if (c1 <= c0) continue;
+            th.emplace_back([=, &rcs]() { rcs[k] = haf_search_batch(ctx->group[k], clouds + c0, n_points + c0, c1 - c0, req, best_per_cloud + c0); });
+        }
+        for (size_t i = 0; i < th.size(); i++) th[i].join();
+        for (int k = 0; k < n; k++)
+            if (rcs[k] != HAF_OK) return ctx->fail(rcs[k], "GPU %d: %s", ctx->group[k]->device, k ? ctx->group[k]->err.c_str() : "see the first error");
+        return HAF_OK;
+    }
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     std::vector<size_t> off(n_clouds + 1, 0);
     for (int c = 0; c < n_clouds; c++) off[c + 1] = off[c] + n_points[c];
@@ -1460,6 +1525,160 @@ extern "C" int haf_search_batch(haf_ctx* ctx, const float* const* clouds, const 
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_xyz.p + off[c] * 12, clouds[c], n_points[c] * 12, cudaMemcpyDefault, ctx->stream));
     }
     return haf_search_batch_packed(ctx, reinterpret_cast<const float*>(ctx->d_xyz.p), off.data(), n_clouds, req, best_per_cloud);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// several GPUs behind one context (haf_config.n_devices > 1)
+// ------------------------------------------------------------------------------------------------------------
+// A cloud given as a DEVICE pointer lives on one GPU: members on other GPUs get their own copy (UVA copy, peer or staged).
+static int member_input(haf_ctx* m, const void* src, size_t bytes, const void** use) {
+    *use = src;
+    if (!bytes || !is_device_ptr(src)) return HAF_OK;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, src) != cudaSuccess) { cudaGetLastError(); return HAF_OK; }
+    if (a.device == m->device) return HAF_OK;
+    CUDA_TRY(m, cudaSetDevice(m->device));
+    ENSURE(m, m->d_xdense, (bytes + 7) / 8);   // spare buffer of this context, otherwise used by the libsvm front end only
+    CUDA_TRY(m, cudaMemcpy(m->d_xdense.p, src, bytes, cudaMemcpyDefault));
+    *use = m->d_xdense.p;
+    return HAF_OK;
+}
+static void group_timing(haf_ctx* ctx) {
+    haf_timing t;
+    memset(&t, 0, sizeof t);
+    for (size_t k = 0; k < ctx->group.size(); k++) {
+        const haf_timing& c = ctx->group[k]->timing;
+        t.ms_total = std::max(t.ms_total, c.ms_total);   // the GPUs run concurrently
+        t.ms_bin = std::max(t.ms_bin, c.ms_bin); t.ms_integral = std::max(t.ms_integral, c.ms_integral); t.ms_mask = std::max(t.ms_mask, c.ms_mask);
+        t.ms_features = std::max(t.ms_features, c.ms_features); t.ms_svm = std::max(t.ms_svm, c.ms_svm); t.ms_guard = std::max(t.ms_guard, c.ms_guard);
+        t.ms_score = std::max(t.ms_score, c.ms_score);
+        t.n_points += c.n_points; t.n_units += c.n_units; t.n_windows += c.n_windows; t.n_guard += c.n_guard; t.launches += c.launches;
+        t.n_chunks += c.n_chunks; t.n_exact += c.n_exact; t.n_audit += c.n_audit;
+        t.audit_max_rel = std::max(t.audit_max_rel, c.audit_max_rel); t.tc_passes = std::max(t.tc_passes, c.tc_passes); t.escalations += c.escalations;
+    }
+    ctx->timing = t;
+}
+
+// One goal: the units (request, roll) -- independent until the per-roll tops exist -- go to the GPUs in contiguous
+// blocks; every member evaluates its rolls of every request in one haf_search call (roll_begin / roll_limit) and writes the
+// per-roll outputs straight into the caller's buffers; the tops are merged HERE with the loop rules of server.cpp:362-365 /
+// :953-960 (strict >, earliest roll, early exit when return_only_best), so best / rolls_done / n_windows_scored equal the
+// one-GPU result.  The only data that crosses GPUs is R x 3 ints per request.
+static int group_search(haf_ctx* ctx, const float* xyz, size_t n_points, size_t stride_bytes, const haf_request* reqs, int n_requests,
+                        haf_best* best, haf_best* best_per_request, float* graspseval, unsigned char* mask, float* heights, int* per_roll_top) {
+    if (!reqs || n_requests < 1 || !best) return ctx->fail(HAF_ERR_ARG, "haf_search: reqs, n_requests >= 1 and best are required");
+    const int n = (int)ctx->group.size(), R = ctx->R;
+    if (stride_bytes == 0) stride_bytes = 12;
+    // rolls the one-GPU loop would evaluate per request
+    std::vector<int> rb(n_requests), re(n_requests);
+    std::vector<long long> ubeg(n_requests + 1, 0);
+    for (int a = 0; a < n_requests; a++) {
+        re[a] = reqs[a].roll_limit > 0 ? std::min(R, reqs[a].roll_limit) : R;
+        rb[a] = std::max(0, std::min(reqs[a].roll_begin, re[a]));
+        ubeg[a + 1] = ubeg[a] + (re[a] - rb[a]);
+    }
+    const long long U = ubeg[n_requests];
+    std::vector<int> tops((size_t)n_requests * R * 3);
+    std::vector<unsigned> uwin((size_t)n_requests * R, 0u);
+    for (size_t u = 0; u < (size_t)n_requests * R; u++) { tops[3 * u] = -1; tops[3 * u + 1] = -1; tops[3 * u + 2] = -1000; }
+    std::vector<int> rcs(n, HAF_OK);
+    std::vector<long long> guards(n, 0);
+    std::vector<std::thread> th;
+    for (int k = 0; k < n; k++) {
+        const long long u0 = U * k / n, u1 = U * (k + 1) / n;   // this GPU's block of the active units
+        if (u1 <= u0) { memset(&ctx->group[k]->timing, 0, sizeof(haf_timing)); continue; }
+        th.emplace_back([=, &rcs, &tops, &uwin, &guards, &rb, &re, &ubeg]() {
+            haf_ctx* m = ctx->group[k];
+            std::vector<haf_request> rq(reqs, reqs + n_requests);
+            for (int a = 0; a < n_requests; a++) {
+                const long long b = std::max(u0, ubeg[a]), e = std::min(u1, ubeg[a + 1]);
+                rq[a].return_only_best = 0;   // the early exit is replayed on the merged tops
+                if (b < e) { rq[a].roll_begin = rb[a] + (int)(b - ubeg[a]); rq[a].roll_limit = rb[a] + (int)(e - ubeg[a]); }
+                else { rq[a].roll_begin = R; rq[a].roll_limit = 0; }   // no roll of this request on this GPU
+            }
+            const void* use = xyz;
+            int rc = member_input(m, xyz, n_points * stride_bytes, &use);
+            std::vector<int> local((size_t)n_requests * R * 3);
+            haf_best b0;
+            std::vector<haf_best> bpr(n_requests);
+            if (rc == HAF_OK)
+                rc = haf_search(m, (const float*)use, n_points, stride_bytes, rq.data(), n_requests, &b0, bpr.data(), graspseval, mask, heights, local.data());
+            rcs[k] = rc;
+            if (rc != HAF_OK) return;
+            guards[k] = m->timing.n_guard;
+            for (int a = 0; a < n_requests; a++)
+                for (int roll = rq[a].roll_begin; roll < (rq[a].roll_limit > 0 ? rq[a].roll_limit : 0); roll++) {
+                    const size_t u = (size_t)a * R + roll;
+                    tops[3 * u] = local[3 * u]; tops[3 * u + 1] = local[3 * u + 1]; tops[3 * u + 2] = local[3 * u + 2];
+                    uwin[u] = m->h_unit_windows.p[u];
+                }
+        });
+    }
+    for (size_t i = 0; i < th.size(); i++) th[i].join();
+    for (int k = 0; k < n; k++)
+        if (rcs[k] != HAF_OK) return ctx->fail(rcs[k], "GPU %d: %s", ctx->group[k]->device, k ? ctx->group[k]->err.c_str() : ctx->err.c_str());
+    group_timing(ctx);
+    long long n_guard = 0;
+    for (int k = 0; k < n; k++) n_guard += guards[k];
+    // merge: the reference's loop over rolls per request, then strict > over requests (earliest wins)
+    int win = -1, wtop = -1000;
+    std::vector<JobResult> res(n_requests);
+    std::vector<Job> jobs(n_requests);
+    for (int a = 0; a < n_requests; a++) {
+        jobs[a].cloud = 0; jobs[a].rq = reqs[a];
+        JobResult r; memset(&r, 0, sizeof r);
+        r.row = r.col = r.roll = -1; r.topval = -1000;
+        for (int roll = rb[a]; roll < re[a]; roll++) {
+            if (reqs[a].return_only_best && r.topval >= reqs[a].graspval_top) break;   // :362-365
+            const size_t u = (size_t)a * R + roll;
+            if (tops[3 * u + 2] > r.topval) { r.topval = tops[3 * u + 2]; r.row = tops[3 * u]; r.col = tops[3 * u + 1]; r.roll = roll; }   // :953
+            r.n_windows += (int)uwin[u];
+            r.rolls_done++;
+        }
+        res[a] = r;
+        if (best_per_request) fill_best(ctx, jobs[a], r, a, n_guard, &best_per_request[a]);
+        if (r.topval > wtop) { wtop = r.topval; win = a; }
+    }
+    if (per_roll_top) memcpy(per_roll_top, tops.data(), tops.size() * sizeof(int));
+    if (win < 0) {
+        JobResult none; memset(&none, 0, sizeof none);
+        none.row = none.col = none.roll = -1; none.topval = -1000;
+        fill_best(ctx, jobs[0], none, -1, n_guard, best);
+    } else {
+        fill_best(ctx, jobs[win], res[win], win, n_guard, best);
+        long long nw = 0; int rd = 0;
+        for (int a = 0; a < n_requests; a++) { nw += res[a].n_windows; rd += res[a].rolls_done; }
+        best->n_windows_scored = (int)nw; best->rolls_done = rd;
+    }
+    return HAF_OK;
+}
+
+// Throughput mode: contiguous blocks of clouds per GPU, one host thread each, no cross-GPU data at all.
+static int group_batch_packed(haf_ctx* ctx, const float* xyz_all, const size_t* point_offsets, int n_clouds, const haf_request* req,
+                              haf_best* best_per_cloud) {
+    if (!point_offsets || n_clouds < 1 || !req || !best_per_cloud) return ctx->fail(HAF_ERR_ARG, "haf_search_batch_packed: bad arguments");
+    const int n = (int)ctx->group.size();
+    std::vector<int> rcs(n, HAF_OK);
+    std::vector<std::thread> th;
+    for (int k = 0; k < n; k++) {
+        const int c0 = (int)((long long)n_clouds * k / n), c1 = (int)((long long)n_clouds * (k + 1) / n);
+        if (c1 <= c0) { memset(&ctx->group[k]->timing, 0, sizeof(haf_timing)); continue; }
+        th.emplace_back([=, &rcs]() {
+            haf_ctx* m = ctx->group[k];
+            std::vector<size_t> off(c1 - c0 + 1);
+            for (int c = c0; c <= c1; c++) off[c - c0] = point_offsets[c] - point_offsets[c0];
+            const float* src = xyz_all + point_offsets[c0] * 3;
+            const void* use = src;
+            int rc = member_input(m, src, off[c1 - c0] * 12, &use);
+            if (rc == HAF_OK) rc = haf_search_batch_packed(m, (const float*)use, off.data(), c1 - c0, req, best_per_cloud + c0);
+            rcs[k] = rc;
+        });
+    }
+    for (size_t i = 0; i < th.size(); i++) th[i].join();
+    for (int k = 0; k < n; k++)
+        if (rcs[k] != HAF_OK) return ctx->fail(rcs[k], "GPU %d: %s", ctx->group[k]->device, k ? ctx->group[k]->err.c_str() : ctx->err.c_str());
+    group_timing(ctx);
+    return HAF_OK;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1571,6 +1790,15 @@ extern "C" int haf_debug_cell_indices(haf_ctx* ctx, const float* xyz, size_t n_p
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     cudaFree(d_cells);
     return (int)std::min<size_t>(n_points, 0x7fffffff);
+}
+
+// cycle counters of the last svm_rbf_tc3_kernel launch run with HAF_TC_DEBUG bit 5 (svm_tc.cuh, g_tc_probe): [n_ctas][16]
+extern "C" int haf_debug_tc_probe(haf_ctx* ctx, unsigned long long* out, int n_ctas) {
+    if (!ctx || !out || n_ctas < 1 || n_ctas > 160) return HAF_ERR_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaDeviceSynchronize());
+    CUDA_TRY(ctx, cudaMemcpyFromSymbol(out, haftc::g_tc_probe, (size_t)n_ctas * 16 * sizeof(unsigned long long)));
+    return HAF_OK;
 }
 
 extern "C" int haf_debug_text_roundtrip(haf_ctx* ctx, const float* in4, int n4, double* out4, const double* in6, int n6, double* out6) {

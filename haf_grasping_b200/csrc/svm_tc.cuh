@@ -372,49 +372,79 @@ svm_rbf_tc2_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_consta
 
 // ==================================================================================================================
 // X-RESIDENT CTA-pair kernel, one product per k-slice (the default where the calibration picks passes == 1).
-// With one product svm_rbf_tc2_kernel is bound by the L2 -> shared-memory feed (32 KB per 512 MMA clocks per CTA = 64
-// B/clk/SM against the ~42 B/clk/SM the L2 delivers chip-wide), half of which re-streams the CTA's own X tile for every
-// one of the n_ntiles SV tiles, and by its four epilogue warps.  Here
-//   * the 128 x Krow X_hi tile of the work item stays in shared memory (kblocks x 16 KB) and only the SV half tiles stream
-//     through a ring of 16 KB stages: the feed halves (36 B/clk/SM at the MMA rate);  per-k-block barriers (x_full /
-//     x_empty) let the next item's X tiles arrive while the last SV tile of the current item is still being multiplied;
-//   * eight epilogue warps, two per TMEM lane quarter (one per half of the accumulator's 256 columns): two warps per SM
-//     sub-partition keep the MUFU pipe (16 ex2 per clock per SM: 2048 clocks per 128 x 256 tile against 2688 clocks of
-//     MMAs) busy across each other's TMEM-load and barrier latencies; one mbarrier arrival per warp.
+//
+// What bounded the one-product kernel (profiles/r2_tc_pipeline_probe.md -- clock64 around every wait of the role threads):
+// NOT the L2 feed, NOT the MUFU pipe, NOT the epilogue, but the single MMA-issuing THREAD.  With one product a k-block is
+// only 4 MMAs (512 clocks of tensor pipe); round 1's role loops ran on ONE lane of the warp (`if (lane == 0)`), so every
+// descriptor, predicate and barrier address was computed with ordinary dependent instructions of a lone, diverged thread
+// (no uniform datapath, R2UR per operand, a runtime `it % stages`), ~180 instructions = 500+ clocks per k-block, during
+// which the tensor pipe drained: tensor pipe 43-50 % active whatever the epilogue or the feed did.  Hence:
+//   * the role loops run WARP-CONVERGED (all 32 lanes take the same path, elect.sync picks the lane that issues the
+//     tcgen05 / TMA / arrive instructions), descriptors are one 64-bit add from precomputed bases, ring position and
+//     phase are counters, the k-slice loop is unrolled with compile-time accumulate flags;
+//   * a ring stage is TWO k-blocks (32 KB of SV half tile, two TMA boxes, one barrier): 8 MMAs per wait / commit;
+//   * the 128 x Krow X_hi tile of the work item stays in shared memory (kblocks x 16 KB) and only the SV half tiles stream:
+//     the L2 feed halves (36 B/clk/SM at the MMA rate, against the ~42 B/clk/SM the L2 delivers chip-wide); per-stage
+//     barriers (x_full / x_empty) let the next item's X tiles arrive while the last SV tile of the current item is still
+//     being multiplied;
+//   * eight epilogue warps, two per TMEM lane quarter (one per half of the accumulator's 256 columns); one mbarrier
+//     arrival per warp.
 // ==================================================================================================================
+// cycle accounting of the role warps (HAF_TC_DEBUG bit 5; tools/tc_cycle_probe.py): per CTA 16 counters
+//   [0] producer: wait x_empty  [1] producer: wait s_empty  [2] producer: issue      [3] producer: stages issued
+//   [4] MMA: wait t_empty       [5] MMA: wait x_full        [6] MMA: wait s_full     [7] MMA: issue + commit  [8] MMA: stages
+//   [9] epilogue warp 2: wait t_full  [10] epilogue warp 2: work  [11] tiles   [12] total cycles of the CTA
+__device__ unsigned long long g_tc_probe[160 * 16];
+__device__ __forceinline__ unsigned long long clk64() { unsigned long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)); return t; }
+#define HAFTC_T(var, stmt) do { if (probe) { const unsigned long long _t0 = clk64(); stmt; var += clk64() - _t0; } else { stmt; } } while (0)
+__device__ __forceinline__ bool elect_one() {   // one lane of the (converged) warp
+    uint32_t p;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(p));
+    return p != 0;
+}
+// accumulate flag as an immediate (the round-1 form materialised a predicate from a register per MMA)
+__device__ __forceinline__ void tc_mma_2sm_acc(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc) : "memory");
+}
+__device__ __forceinline__ void tc_mma_2sm_new(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc) : "memory");
+}
 constexpr int XK_MAX = 8;        // k-blocks of 64 dimensions the resident X tile may have (Krow <= 512)
+constexpr int KBS = 2;           // k-blocks per ring stage
+constexpr int XS_MAX = XK_MAX / KBS;
 constexpr int THREADS3 = 320;    // TMA warp, MMA warp, 8 epilogue warps
 constexpr int TC3_SMEM_LIMIT = 227 * 1024;
 __host__ __device__ constexpr int tc3_smem_bytes(int kblocks, int stages, int tab_entries) {
-    return kblocks * A_TILE_BYTES + stages * B2_TILE_BYTES + 1024 /*align slack*/ + 512 /*barriers*/ + tab_entries * 4;
+    return kblocks * A_TILE_BYTES + stages * KBS * B2_TILE_BYTES + 1024 /*align slack*/ + 512 /*barriers*/ + tab_entries * 4;
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS3, 1)
 svm_rbf_tc3_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmSh2,
                    const float* __restrict__ xn, const float* __restrict__ svcoef, float c, const unsigned* __restrict__ win_count,
                    int n_ntiles, int nsplit, int kblocks, int last_slices, int stages, double* __restrict__ dec_acc, float* __restrict__ asum_acc,
-                   int tab_smem, float csvn_max, int dbg /*timing experiments only (tools/tc_pipeline_probe.py): 1 no epilogue work, 2 no MMAs, 4 TMEM loads only, 8 math only*/) {
+                   int tab_smem, float csvn_max, int dbg /*timing experiments only (tools/tc_pipeline_probe.py): 1 no epilogue work, 2 no MMAs, 4 TMEM loads only, 8 math only, 16 no skew, 32 cycle probe*/) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t x_base = smem_base;                                     // [kblocks] X_hi tiles of the current item (16 KB each)
-    const uint32_t ring_base = x_base + (uint32_t)kblocks * A_TILE_BYTES;   // [stages]  SV_hi half tiles
-    const uint32_t bar_base = ring_base + (uint32_t)stages * B2_TILE_BYTES;
-    const uint32_t bar_sfull = bar_base;                  // [16]      (used in the leader CTA)
-    const uint32_t bar_sempty = bar_base + 128;           // [16]      (one per CTA)
-    const uint32_t bar_xfull = bar_base + 256;            // [XK_MAX]  (used in the leader CTA)
-    const uint32_t bar_xempty = bar_base + 320;           // [XK_MAX]  (one per CTA)
-    const uint32_t bar_tfull = bar_base + 384;            // [2]       (one per CTA)
-    const uint32_t bar_tempty = bar_base + 400;           // [2]       (used in the leader CTA)
-    const uint32_t tmem_slot = bar_base + 416;
+    const uint32_t x_base = smem_base;                                          // [kblocks] X_hi tiles of the current item (16 KB each)
+    const uint32_t ring_base = x_base + (uint32_t)kblocks * A_TILE_BYTES;        // [stages][KBS] SV_hi half tiles
+    const uint32_t bar_base = ring_base + (uint32_t)(stages * KBS) * B2_TILE_BYTES;
+    const uint32_t bar_sfull = bar_base;                  // [8]       (used in the leader CTA)
+    const uint32_t bar_sempty = bar_base + 64;            // [8]       (one per CTA)
+    const uint32_t bar_xfull = bar_base + 128;            // [XS_MAX]  (used in the leader CTA)
+    const uint32_t bar_xempty = bar_base + 192;           // [XS_MAX]  (one per CTA)
+    const uint32_t bar_tfull = bar_base + 256;            // [2]       (one per CTA)
+    const uint32_t bar_tempty = bar_base + 272;           // [2]       (used in the leader CTA)
+    const uint32_t tmem_slot = bar_base + 288;
     const uint32_t tab_base = bar_base + 512;             // float [n_ntiles * BN] when tab_smem
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (tab_smem) stage_coef_table(tab_base, svcoef, n_ntiles * BN, THREADS3);
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
+    const int xstages = (kblocks + KBS - 1) / KBS;        // ring stages per SV tile = X barrier groups
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; s++) { mbar_init(bar_sfull + 8 * s, 1); mbar_init(bar_sempty + 8 * s, 1); }
-        for (int k = 0; k < XK_MAX; k++) { mbar_init(bar_xfull + 8 * k, 1); mbar_init(bar_xempty + 8 * k, 1); }
+        for (int k = 0; k < XS_MAX; k++) { mbar_init(bar_xfull + 8 * k, 1); mbar_init(bar_xempty + 8 * k, 1); }
         for (int a = 0; a < 2; a++) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 16); }   // 2 CTAs x 8 epilogue warps
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -433,61 +463,99 @@ svm_rbf_tc3_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_consta
     const int items = n_pairs * nsplit;
     const int nt_per = (n_ntiles + nsplit - 1) / nsplit;
     const int cid = (int)cluster_id_x(), ncl = (int)n_clusters_x();
+    // SKEW: cluster c starts its walk over the support-vector tiles at tile (c mod n), so that the clusters are spread over the
+    // whole SV matrix instead of all asking the L2 for the same lines at the same moment.  (The order in which a window's tile
+    // sums are added changes with it: they are accumulated in FP64.)
+    const int skew = (dbg & 16) ? 0 : cid;
+    const bool probe = (dbg & 32) != 0;
+    unsigned long long pc0 = 0, pc1 = 0, pc2 = 0, pc3 = 0, pc4 = 0;
+    const unsigned long long t_start = clk64();
 
-    if (warp == 0) {
-        if (lane == 0) {  // ===== TMA producer (both CTAs) =====
-            uint32_t it = 0, xi = 0;
-            for (int item = cid; item < items; item += ncl) {
-                const int mp = item / nsplit, sp = item - mp * nsplit;
-                const int nt0 = sp * nt_per, nt1 = min(n_ntiles, nt0 + nt_per);
-                if (nt0 >= nt1) continue;   // an empty split touches no barrier in any role
-                const int xtile = (2 * mp + (int)rank) * kblocks;   // k-block tiled layout (kernels.cuh, kt_off): tile (row tile, kb) = 128 box rows
-                for (int nt = nt0; nt < nt1; nt++)
-                    for (int kb = 0; kb < kblocks; kb++, it++) {
-                        if (nt == nt0) {   // this item's X tile kb, as soon as the previous item's last SV tile has let go of it
-                            mbar_wait(bar_xempty + 8 * kb, (xi & 1u) ^ 1u);
-                            if (leader) mbar_expect_tx(bar_xfull + 8 * kb, 2 * A_TILE_BYTES);
-                            tma_load_2d_2sm(x_base + (uint32_t)kb * A_TILE_BYTES, &tmXh, 0, (xtile + kb) * BM, (bar_xfull + 8 * kb) & PEER_MASK);
+    if (warp == 0) {   // ===== TMA producer warp (both CTAs), warp-converged =====
+        uint32_t s = 0, sph = 0, xi = 0;
+        for (int item = cid; item < items; item += ncl) {
+            const int mp = item / nsplit, sp = item - mp * nsplit;
+            const int nt0 = sp * nt_per, nt1 = min(n_ntiles, nt0 + nt_per), ntn = nt1 - nt0;
+            if (ntn <= 0) continue;   // an empty split touches no barrier in any role
+            const int xtile = (2 * mp + (int)rank) * kblocks;   // k-block tiled layout (kernels.cuh, kt_off): tile (row tile, kb) = 128 box rows
+            for (int j = 0; j < ntn; j++) {
+                int nt = j + skew % ntn;
+                nt = nt0 + (nt >= ntn ? nt - ntn : nt);
+                const int svtile = (2 * nt + (int)rank) * kblocks;
+                for (int g = 0; g < xstages; g++) {
+                    const int kb0 = g * KBS, nkb = min(KBS, kblocks - kb0);
+                    if (j == 0) {   // this item's X tiles of group g, as soon as the previous item's last SV tile has let go of them
+                        HAFTC_T(pc0, mbar_wait(bar_xempty + 8 * g, (xi & 1u) ^ 1u));
+                        if (elect_one()) {
+                            if (leader) mbar_expect_tx(bar_xfull + 8 * g, (uint32_t)(2 * nkb) * A_TILE_BYTES);
+                            for (int q = 0; q < nkb; q++)
+                                tma_load_2d_2sm(x_base + (uint32_t)(kb0 + q) * A_TILE_BYTES, &tmXh, 0, (xtile + kb0 + q) * BM, (bar_xfull + 8 * g) & PEER_MASK);
                         }
-                        const uint32_t s = it % (uint32_t)stages, ph = (it / (uint32_t)stages) & 1u;
-                        mbar_wait(bar_sempty + 8 * s, ph ^ 1u);
-                        if (leader) mbar_expect_tx(bar_sfull + 8 * s, 2 * B2_TILE_BYTES);
-                        tma_load_2d_2sm(ring_base + s * B2_TILE_BYTES, &tmSh2, 0, ((2 * nt + (int)rank) * kblocks + kb) * BM, (bar_sfull + 8 * s) & PEER_MASK);
+                        __syncwarp();
                     }
-                xi++;
+                    HAFTC_T(pc1, mbar_wait(bar_sempty + 8 * s, sph ^ 1u));
+                    const unsigned long long t_i = probe ? clk64() : 0ull;
+                    if (elect_one()) {
+                        if (leader) mbar_expect_tx(bar_sfull + 8 * s, (uint32_t)(2 * nkb) * B2_TILE_BYTES);
+                        for (int q = 0; q < nkb; q++)
+                            tma_load_2d_2sm(ring_base + (s * KBS + (uint32_t)q) * B2_TILE_BYTES, &tmSh2, 0, (svtile + kb0 + q) * BM, (bar_sfull + 8 * s) & PEER_MASK);
+                    }
+                    __syncwarp();
+                    if (probe) { pc2 += clk64() - t_i; pc3++; }
+                    if (++s == (uint32_t)stages) { s = 0; sph ^= 1u; }
+                }
             }
+            xi++;
         }
+        if (probe && lane == 0) { unsigned long long* gp = g_tc_probe + blockIdx.x * 16; gp[0] = pc0; gp[1] = pc1; gp[2] = pc2; gp[3] = pc3; gp[12] = clk64() - t_start; }
     } else if (warp == 1) {
-        if (leader && lane == 0) {  // ===== MMA issuer (leader CTA only) =====
-            uint32_t it = 0, acc_it = 0, xi = 0;
+        if (leader) {   // ===== MMA warp (leader CTA only), warp-converged; one elected lane issues =====
+            uint32_t s = 0, sph = 0, acc_it = 0, xi = 0;
+            const uint64_t descA0 = make_desc_sw128(x_base), descB0 = make_desc_sw128(ring_base);
+            constexpr uint64_t TILE_ADV = A_TILE_BYTES >> 4;   // descriptor address field counts 16-byte units
             for (int item = cid; item < items; item += ncl) {
                 const int mp = item / nsplit, sp = item - mp * nsplit;
-                const int nt0 = sp * nt_per, nt1 = min(n_ntiles, nt0 + nt_per);
-                if (nt0 >= nt1) continue;
-                for (int nt = nt0; nt < nt1; nt++, acc_it++) {
+                const int nt0 = sp * nt_per, nt1 = min(n_ntiles, nt0 + nt_per), ntn = nt1 - nt0;
+                if (ntn <= 0) continue;
+                for (int j = 0; j < ntn; j++, acc_it++) {
                     const uint32_t a = acc_it & 1u, aph = (acc_it >> 1) & 1u;
-                    mbar_wait(bar_tempty + 8 * a, aph ^ 1u);   // both CTAs' epilogue warps have drained this accumulator
+                    HAFTC_T(pc0, mbar_wait(bar_tempty + 8 * a, aph ^ 1u));   // both CTAs' epilogue warps have drained this accumulator
                     tc_fence_after();
                     const uint32_t tmem_d = tmem_base + a * BN;
-                    for (int kb = 0; kb < kblocks; kb++, it++) {
-                        if (nt == nt0) mbar_wait(bar_xfull + 8 * kb, xi & 1u);   // the item's X tile kb has landed in both CTAs
-                        const uint32_t s = it % (uint32_t)stages, ph = (it / (uint32_t)stages) & 1u;
-                        mbar_wait(bar_sfull + 8 * s, ph);
+                    for (int g = 0; g < xstages; g++) {
+                        const int kb0 = g * KBS, nkb = min(KBS, kblocks - kb0);
+                        if (j == 0) HAFTC_T(pc1, mbar_wait(bar_xfull + 8 * g, xi & 1u));   // the item's X tiles of group g have landed in both CTAs
+                        HAFTC_T(pc2, mbar_wait(bar_sfull + 8 * s, sph));
+                        const unsigned long long t_i = probe ? clk64() : 0ull;
                         tc_fence_after();
-                        const uint64_t d_a = make_desc_sw128(x_base + (uint32_t)kb * A_TILE_BYTES);
-                        const uint64_t d_b = make_desc_sw128(ring_base + s * B2_TILE_BYTES);
-                        const int slices = (kb == kblocks - 1) ? last_slices : (BK / 16);
-                        for (int k = 0; k < slices; k++) {
-                            const uint64_t adv = (uint64_t)(k * 2);
-                            if (!(dbg & 2)) tc_mma_2sm(tmem_d, d_a + adv, d_b + adv, IDESC2, (kb | k) ? 1u : 0u);
+                        if (elect_one()) {
+                            if (!(dbg & 2)) {
+                                uint64_t da = descA0 + (uint64_t)kb0 * TILE_ADV, db = descB0 + (uint64_t)(s * KBS) * TILE_ADV;
+                                for (int q = 0; q < nkb; q++, da += TILE_ADV, db += TILE_ADV) {
+                                    const bool full = (kb0 + q) < kblocks - 1 || last_slices == BK / 16;
+                                    if (g == 0 && q == 0) tc_mma_2sm_new(tmem_d, da, db, IDESC2);   // first k-slice of the tile: overwrite
+                                    else tc_mma_2sm_acc(tmem_d, da, db, IDESC2);
+                                    if (full) {
+                                        tc_mma_2sm_acc(tmem_d, da + 2, db + 2, IDESC2);   // 16 fp16 = 32 bytes = 2 x 16-byte units
+                                        tc_mma_2sm_acc(tmem_d, da + 4, db + 4, IDESC2);
+                                        tc_mma_2sm_acc(tmem_d, da + 6, db + 6, IDESC2);
+                                    } else {
+                                        for (int k = 1; k < last_slices; k++) tc_mma_2sm_acc(tmem_d, da + 2 * k, db + 2 * k, IDESC2);
+                                    }
+                                }
+                            }
+                            tc_commit_2sm_mc(bar_sempty + 8 * s);                      // SV stage free in BOTH CTAs
+                            if (j == ntn - 1) tc_commit_2sm_mc(bar_xempty + 8 * g);    // last use of these X tiles by this item
+                            if (g == xstages - 1) tc_commit_2sm_mc(bar_tfull + 8 * a); // accumulator halves ready in BOTH CTAs
                         }
-                        tc_commit_2sm_mc(bar_sempty + 8 * s);                       // SV stage free in BOTH CTAs
-                        if (nt == nt1 - 1) tc_commit_2sm_mc(bar_xempty + 8 * kb);   // last use of X tile kb by this item
+                        __syncwarp();
+                        if (probe) { pc3 += clk64() - t_i; pc4++; }
+                        if (++s == (uint32_t)stages) { s = 0; sph ^= 1u; }
                     }
-                    tc_commit_2sm_mc(bar_tfull + 8 * a);
                 }
                 xi++;
             }
+            if (probe && lane == 0) { unsigned long long* gp = g_tc_probe + blockIdx.x * 16; gp[4] = pc0; gp[5] = pc1; gp[6] = pc2; gp[7] = pc3; gp[8] = pc4; }
         }
     } else {  // ===== epilogue warps 2..9 (both CTAs): lane quarter q, column half h of the accumulator =====
         const int q = warp & 3, h = (warp - 2) >> 2;
@@ -495,33 +563,36 @@ svm_rbf_tc3_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_consta
         const float c2 = -2.0f * c;
         for (int item = cid; item < items; item += ncl) {
             const int mp = item / nsplit, sp = item - mp * nsplit;
-            const int nt0 = sp * nt_per, nt1 = min(n_ntiles, nt0 + nt_per);
-            if (nt0 >= nt1) continue;
+            const int nt0 = sp * nt_per, nt1 = min(n_ntiles, nt0 + nt_per), ntn = nt1 - nt0;
+            if (ntn <= 0) continue;
             const unsigned m = (unsigned)(2 * mp + (int)rank) * BM + q * 32 + lane;
             const float u = (m < W) ? c * xn[m] : 0.0f;
             double dsum = 0.0;
             float asum = 0.0f;
-            for (int nt = nt0; nt < nt1; nt++, acc_it++) {
+            for (int j = 0; j < ntn; j++, acc_it++) {
+                int nt = j + skew % ntn;
+                nt = nt0 + (nt >= ntn ? nt - ntn : nt);
                 const uint32_t a = acc_it & 1u, aph = (acc_it >> 1) & 1u;
-                mbar_wait(bar_tfull + 8 * a, aph);
+                HAFTC_T(pc0, mbar_wait(bar_tfull + 8 * a, aph));
+                const unsigned long long t_work = probe ? clk64() : 0ull;
                 tc_fence_after();
                 const uint32_t tab_s = tab_smem ? tab_base + (uint32_t)nt * BN * 4u : 0u;
                 float ps = 0.0f;
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * BN + h * (BN / 2);
-                if (dbg == 0 || (dbg & 2)) ps = epilogue_columns<BN / 2>(taddr, tab_s, svcoef + (size_t)nt * BN, h * (BN / 2), c2);
+                if ((dbg & 13) == 0) ps = epilogue_columns<BN / 2>(taddr, tab_s, svcoef + (size_t)nt * BN, h * (BN / 2), c2);
                 else if (dbg & 4) {   // TMEM loads only
                     uint32_t ra[32], acc = 0;
                     for (int ch = 0; ch < BN / 64; ch++) {
                         HAFTC_LD32(taddr + ch * 32, ra);
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                        for (int j = 0; j < 32; j++) acc ^= ra[j];
+                        for (int jj = 0; jj < 32; jj++) acc ^= ra[jj];
                     }
                     ps = __uint_as_float(acc & 0x3fffffffu);
                 } else if (dbg & 8) {   // epilogue arithmetic only, on made-up accumulator values
                     uint32_t ra[32];
 #pragma unroll
-                    for (int j = 0; j < 32; j++) ra[j] = __float_as_uint(-(float)(j + lane));
+                    for (int jj = 0; jj < 32; jj++) ra[jj] = __float_as_uint(-(float)(jj + lane));
                     for (int ch = 0; ch < BN / 64; ch++) { epilogue_chunk(ra, tab_s, svcoef + (size_t)nt * BN, h * (BN / 2) + ch * 32, c2, ps); ra[ch & 31] ^= __float_as_uint(ps) & 0xff; }
                 }
                 tc_fence_before();
@@ -529,12 +600,14 @@ svm_rbf_tc3_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_consta
                 if (lane == 0) mbar_arrive_cluster((bar_tempty + 8 * a) & PEER_MASK);   // on the LEADER's barrier (count 16)
                 dsum += (double)ps;
                 asum += fabsf(ps);
+                if (probe) { pc1 += clk64() - t_work; pc2++; }
             }
             if (m < W) {
                 atomicAdd(dec_acc + m, dsum);
                 atomicAdd(asum_acc + m, (1.0f - u + csvn_max) * asum);
             }
         }
+        if (probe && warp == 2 && lane == 0) { unsigned long long* gp = g_tc_probe + blockIdx.x * 16; gp[9] = pc0; gp[10] = pc1; gp[11] = pc2; }
     }
     __syncwarp();
     tc_fence_before();

@@ -67,8 +67,14 @@ typedef struct {
                                        with scalar loads;
                                   [2]: guard band tier 2 (FP64 FMA re-evaluation): 0 = on, 1 = off (every guard window goes
                                        to the exact-order kernels), 2 = on, but every window escalates as well (tests);
-                                  [3]: 1 = tensor kernels read the {c|sv|^2, coef} table from global memory even when it fits in
+                                  [3]: 1 = tensor kernels read the coef table from global memory even when it fits in
                                        shared memory (the path models with > 4096 support vectors take) */
+    int n_devices;             /* > 1: one context drives several GPUs of the box: haf_search shards its units
+                                  (request, roll) and haf_search_batch* its clouds over them, one host thread and one stream per
+                                  GPU; the per-unit tops / per-cloud records are merged on the host with the reference's own
+                                  rules (strict >, earliest unit wins, early exit), so the result equals the one-GPU result.
+                                  0 or 1: `device` alone                                                              */
+    const int* devices;        /* [n_devices] CUDA ordinals (read at haf_create); NULL = 0 .. n_devices-1              */
 } haf_config;
 
 /* One grasp goal = the hot-path fields of GraspInput (msg/GraspInput.msg:3-15). */
@@ -219,6 +225,10 @@ int haf_debug_cell_indices(haf_ctx* ctx, const float* xyz_hostdev, size_t n_poin
 /* device evaluation of text4 (float -> "%.4g" -> double) and text6 (double -> "%g" -> double) */
 int haf_debug_text_roundtrip(haf_ctx* ctx, const float* in4, int n4, double* out4, const double* in6, int n6,
                              double* out6);
+
+/* cycle counters of the role threads of the last X-resident tensor kernel launch made under HAF_TC_DEBUG=32 (timing
+ * experiments, tools/tc_pipeline_probe.py; layout in csrc/svm_tc.cuh, g_tc_probe): out [n_ctas][16] */
+int haf_debug_tc_probe(haf_ctx* ctx, unsigned long long* out, int n_ctas);
 
 const char* haf_version(void);
 

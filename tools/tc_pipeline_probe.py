@@ -9,9 +9,8 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rows = []
-for flags, what in ((0, "full kernel"), (1, "no epilogue work (MMA + TMA pipeline alone)"), (2, "no MMAs (epilogue alone, TMA still streaming)"),
-                    (3, "neither (barrier / TMA skeleton)"), (4, "MMAs + TMEM loads, no arithmetic"), (8, "MMAs + arithmetic, no TMEM loads"),
-                    (6, "TMEM loads only"), (10, "arithmetic only")):
+for flags, what in ((0, "full kernel"), (16, "full kernel, clusters walk the SV tiles in step (no skew)"), (19, "skeleton, no skew"), (2, "no MMAs (epilogue alone, TMA still streaming)"),
+                    (3, "neither (barrier / TMA skeleton)"), (4, "MMAs + TMEM loads, no arithmetic"), (8, "MMAs + arithmetic, no TMEM loads")):
     env = dict(os.environ, HAF_TC_DEBUG=str(flags))
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "5", "--warmup", "3", "--no-cpu-baseline"], env=env,
                          capture_output=True, text=True)
