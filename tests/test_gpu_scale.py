@@ -195,7 +195,8 @@ def test_bench_batch_labels_at_scale(hg, oracle_lib, tmp_models):
             for h0 in (0, half):
                 cl = clouds[h0:h0 + half]
                 off = np.concatenate([[0], np.cumsum([len(c) for c in cl])])
-                xyz_all = np.concatenate(cl)
+                import torch
+                xyz_all = torch.from_numpy(np.concatenate(cl)).cuda()   # device-resident: one pass over the stage sequence
                 bf, wf, df, lf, gf, tf = _batch_labels(fast, xyz_all, off)
                 be, we, de, le, ge, te = _batch_labels(exact, xyz_all, off)
                 assert np.array_equal(wf, we)
@@ -227,13 +228,14 @@ def test_audit_escalates_the_number_of_products(hg, oracle_lib, trained_model_pa
     audit measures the contraction's error on the call's own windows, the call is repeated with more products, and the
     labels equal the oracle's.  With a band too narrow even for three products the call fails loudly."""
     xyz = clouds_npz["table1"]
-    gpu = hg.GraspSearch(FEATURES, RANGE, trained_model_path, tc_passes=1, guard_rel=2e-5, audit_every=8)
+    # one product on this model is off by ~4e-6 E on table1's windows (measured); a band of 8e-6 E leaves it less than 4x
+    gpu = hg.GraspSearch(FEATURES, RANGE, trained_model_path, tc_passes=1, guard_rel=8e-6, audit_every=8)
     o = oracle_lib.Oracle(FEATURES, RANGE, trained_model_path)
     try:
         res = gpu.search(xyz)
         t = gpu.timing()
         assert t.escalations >= 1 and t.tc_passes >= 2, (t.escalations, t.tc_passes, t.audit_max_rel)
-        assert t.audit_max_rel <= 0.25 * 2e-5
+        assert t.audit_max_rel <= 0.25 * 8e-6
         ores = o.search(xyz, oracle_lib.make_request())
         dec, lab, _ = gpu.debug_decisions()
         win = gpu.debug_windows()
