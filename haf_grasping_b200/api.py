@@ -34,7 +34,7 @@ class haf_config(C.Structure):
 class haf_request(C.Structure):
     _fields_ = [("center", C.c_double * 3), ("area_len_x", C.c_float), ("area_len_y", C.c_float),
                 ("approach", C.c_double * 3), ("gripper_opening_width", C.c_int), ("return_only_best", C.c_int),
-                ("graspval_top", C.c_int), ("roll_limit", C.c_int), ("roll_begin", C.c_int), ("reserved", C.c_int)]
+                ("graspval_top", C.c_int), ("roll_limit", C.c_int), ("roll_begin", C.c_int), ("svm_with_probability", C.c_int)]
 
 
 class haf_best(C.Structure):
@@ -65,7 +65,7 @@ EXPORTS = ["haf_create", "haf_destroy", "haf_last_error", "haf_get_info", "haf_s
            "haf_get_timing", "haf_launch_count", "haf_set_debug", "haf_search", "haf_search_batch", "haf_search_batch_packed",
            "haf_build_transform", "haf_build_transform_wcs", "haf_best_key", "haf_pack_best_records", "haf_debug_window_count", "haf_debug_windows", "haf_debug_features",
            "haf_debug_decisions", "haf_debug_tensor_inputs", "haf_debug_integral", "haf_debug_cell_indices", "haf_debug_text_roundtrip", "haf_debug_tc_probe",
-           "haf_version", "haf_svm_create", "haf_svm_destroy", "haf_svm_predict", "haf_scale_minmax", "haf_scale_apply"]
+           "haf_version", "haf_svm_create", "haf_svm_destroy", "haf_svm_predict", "haf_svm_predict_probability", "haf_svm_check_probability_model", "haf_scale_minmax", "haf_scale_apply"]
 
 _lib = None
 
@@ -120,6 +120,8 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     L.haf_svm_destroy.argtypes = [vp]
     L.haf_svm_destroy.restype = None
     L.haf_svm_predict.argtypes = [vp, vp, vp, vp, ci, vp, vp]
+    L.haf_svm_predict_probability.argtypes = [vp, vp, vp, vp, ci, vp, vp]
+    L.haf_svm_check_probability_model.argtypes = [vp]
     L.haf_scale_minmax.argtypes = [ci, vp, vp, vp, ci, ci, vp, vp]
     L.haf_scale_apply.argtypes = [ci, vp, vp, vp, ci, ci, vp, vp, C.c_double, C.c_double, vp]
     _lib = L
@@ -127,7 +129,7 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
 
 
 def make_request(center=(0.0, 0.0, 0.0), area=(32.0, 44.0), approach=(0.0, 0.0, 1.0), width=1, return_only_best=0,
-                 graspval_top=119, roll_limit=0, roll_begin=0) -> haf_request:
+                 graspval_top=119, roll_limit=0, roll_begin=0, svm_with_probability=0) -> haf_request:
     """GraspInput defaults of the reference client (client.cpp:79-118; area = size + 14, client.cpp:183-184)."""
     rq = haf_request()
     rq.center[:] = center
@@ -138,6 +140,7 @@ def make_request(center=(0.0, 0.0, 0.0), area=(32.0, 44.0), approach=(0.0, 0.0, 
     rq.graspval_top = graspval_top
     rq.roll_limit = roll_limit
     rq.roll_begin = roll_begin
+    rq.svm_with_probability = svm_with_probability
     return rq
 
 
@@ -377,6 +380,20 @@ class SvmPredictor:
         if rc != 0:
             raise HafError(rc, (self.L.haf_last_error(self.h) or b"").decode())
         return labels[:n], (dec[:n] if want_dec else None)
+
+    def check_probability_model(self):
+        return bool(self.L.haf_svm_check_probability_model(self.h))
+
+    def predict_probability(self, rows):
+        """svm-predict -b 1: (labels [n], prob_estimates [n][2] in the order of the model's labels)"""
+        rp, idx, val = _csr(rows)
+        n = len(rp) - 1
+        labels = np.zeros(max(n, 1), np.float64)
+        probs = np.zeros((max(n, 1), 2), np.float64)
+        rc = self.L.haf_svm_predict_probability(self.h, _ptr(rp), _ptr(idx), _ptr(val), n, _ptr(labels), _ptr(probs))
+        if rc != 0:
+            raise HafError(rc, (self.L.haf_last_error(self.h) or b"").decode())
+        return labels[:n], probs[:n]
 
     def timing(self):
         t = haf_timing()

@@ -100,6 +100,8 @@ struct Model {
     double gamma = 0, rho = 0;
     int l = 0, nr_class = 0, label[2] = {0, 0}, nSV[2] = {0, 0};
     int max_index = 0;
+    bool has_probA = false, has_probB = false;   // svm_check_probability_model (svm.cpp:3098-3104): both present
+    double probA = 0, probB = 0;                 // sigmoid of the one class pair (svm.cpp:2811-2824)
     std::vector<double> coef;  // [l] file order
     std::vector<std::vector<std::pair<int, double> > > sv;
 };
@@ -126,7 +128,8 @@ inline bool load_model(const char* path, Model& m, std::string& err, bool& unsup
         } else if (!strcmp(cmd, "total_sv")) { if (fscanf(fp, "%d", &m.l) != 1) break; }
         else if (!strcmp(cmd, "rho")) { if (fscanf(fp, "%lf", &m.rho) != 1) break; }
         else if (!strcmp(cmd, "label")) { if (fscanf(fp, "%d %d", &m.label[0], &m.label[1]) != 2) break; }
-        else if (!strcmp(cmd, "probA") || !strcmp(cmd, "probB")) { double d; if (fscanf(fp, "%lf", &d) != 1) break; }  // unused without -b
+        else if (!strcmp(cmd, "probA")) { if (fscanf(fp, "%lf", &m.probA) != 1) break; m.has_probA = true; }
+        else if (!strcmp(cmd, "probB")) { if (fscanf(fp, "%lf", &m.probB) != 1) break; m.has_probB = true; }
         else if (!strcmp(cmd, "nr_sv")) { if (fscanf(fp, "%d %d", &m.nSV[0], &m.nSV[1]) != 2) break; }
         else if (!strcmp(cmd, "SV")) {
             int ch;

@@ -97,6 +97,7 @@ struct haf_ctx {
     int Krow = 0, KB = 0, SpadT = 0;
     float c_log2 = 0.0f;
     float csvn_max = 0.0f;      // |c| * max_n ||sv_n||^2 (guard scale of the tensor kernels)
+    float e_floor = 0.0f;       // sum|coef| * 2^-100: windows whose guard scale E is below it lose terms to FP32 underflow -> FP64
     DevBuf<__half> d_SVh, d_SVl, d_Xh, d_Xl;   // d_Xl only with three products per k-slice
     DevBuf<float> d_svcoef;     // coef in the tensor path's order (sorted by sign, sign groups padded to whole tiles)
     DevBuf<double> d_dec_tc;    // audit: the contraction's decision value of every window on the guard list
@@ -145,10 +146,18 @@ struct haf_ctx {
     PinBuf<int> h_per_roll_top;
     PinBuf<unsigned> h_counters;
 
+    // probability estimates: the model's sigmoid (svm.cpp:2811-2824); probability calls evaluate EVERY row /
+    // window on the FP64 exact-order path (force_exact), whatever svm_mode the context was made with
+    bool has_prob = false, force_exact = false;
+    double probA = 0, probB = 0;
+    int prob_res[2] = {0, 0};        // (int)atof(first two characters of "%g"(label)): server.cpp:833
+    float prob_header_val = 0.0f;    // the "labels l0 l1" line parsed as a prediction: 0 * (float)l0 (server.cpp:817, :833-841)
+    DevBuf<float> d_probgrid;        // [Uc][G][G] graspsgrid as floats (probability mode)
+
     // libsvm front end (haf_svm_*): inputs given by the caller
     bool svm_only = false;
     const double* cur_xdense = nullptr;   // non-null while haf_svm_predict runs: exact_scaled_input reads it
-    DevBuf<double> d_xdense, d_labels;
+    DevBuf<double> d_xdense, d_labels, d_probs;
     DevBuf<long long> d_csr_ptr;
     DevBuf<int> d_csr_idx;
     DevBuf<double> d_csr_val;
@@ -399,6 +408,20 @@ static int create_impl(haf_ctx** out, const haf_config* cfg, bool svm_only, int 
     ctx->label[0] = model.label[0]; ctx->label[1] = model.label[1];
     ctx->gv[0] = hafhost::label_to_gridvalue(model.label[0]);
     ctx->gv[1] = hafhost::label_to_gridvalue(model.label[1]);
+    {
+        double sac = 0.0;
+        for (int i = 0; i < model.l; i++) sac += fabs(model.coef[i]);
+        ctx->e_floor = (float)(sac * 7.888609052210118e-31);   // 2^-100
+    }
+    ctx->has_prob = model.has_probA && model.has_probB;   // svm_check_probability_model (svm.cpp:3098-3104)
+    ctx->probA = model.probA; ctx->probB = model.probB;
+    for (int k = 0; k < 2; k++) {
+        char b[64];
+        snprintf(b, sizeof b, "%g", (double)model.label[k]);   // svm-predict.c:114
+        b[2] = 0;
+        ctx->prob_res[k] = (int)atof(b);                         // int res = atof(line.substr(0,2)) (server.cpp:833)
+    }
+    ctx->prob_header_val = (float)0 * (float)(double)model.label[0];
     ctx->guard_rel = cfg->guard_rel > 0 ? cfg->guard_rel : 2e-6f;   // of E = sum|coef|K(1+|c|(xn+svn)) + |rho|; measured FP32 SIMT error <= 1.3e-7 E (tools/dec_error_probe.py)
     memset(&ctx->timing, 0, sizeof ctx->timing);
     if (ctx->gv[0] < -128 || ctx->gv[0] > 127 || ctx->gv[1] < -128 || ctx->gv[1] > 127) { delete ctx; return create_fail(HAF_ERR_UNSUPPORTED, "model labels do not fit the grasp grid"); }
@@ -650,10 +673,31 @@ static int check_csr(haf_ctx* ctx, const long long* row_ptr, const int* index, c
     return HAF_OK;
 }
 
+// prob_estimates != NULL: svm_predict_probability for every row (svm.cpp:2550-2590) -- decision values on the FP64 exact-order
+// path for EVERY row (the estimates are printed with six digits: they need the reference's own decision values, not a sign),
+// then sigmoid + pairwise coupling on the device (prob_from_dec_kernel)
+static int svm_predict_impl(haf_svm* ctx, const long long* row_ptr, const int* index, const double* value, int n_rows,
+                            double* labels, double* dec_values, double* prob_estimates);
 extern "C" int haf_svm_predict(haf_svm* ctx, const long long* row_ptr, const int* index, const double* value, int n_rows,
                                double* labels, double* dec_values) {
     if (!ctx) return HAF_ERR_ARG;
+    return svm_predict_impl(ctx, row_ptr, index, value, n_rows, labels, dec_values, nullptr);
+}
+extern "C" int haf_svm_check_probability_model(const haf_svm* ctx) { return (ctx && ctx->has_prob) ? 1 : 0; }
+extern "C" int haf_svm_predict_probability(haf_svm* ctx, const long long* row_ptr, const int* index, const double* value, int n_rows,
+                                           double* labels, double* prob_estimates) {
+    if (!ctx) return HAF_ERR_ARG;
+    if (!prob_estimates) return ctx->fail(HAF_ERR_ARG, "haf_svm_predict_probability: prob_estimates is null");
+    if (!ctx->has_prob) return ctx->fail(HAF_ERR_UNSUPPORTED, "Model does not support probabiliy estimates");   // svm-predict.c:213 (sic)
+    ctx->force_exact = true;
+    const int rc = svm_predict_impl(ctx, row_ptr, index, value, n_rows, labels, nullptr, prob_estimates);
+    ctx->force_exact = false;
+    return rc;
+}
+static int svm_predict_impl(haf_svm* ctx, const long long* row_ptr, const int* index, const double* value, int n_rows,
+                            double* labels, double* dec_values, double* prob_estimates) {
     if (!ctx->svm_only) return ctx->fail(HAF_ERR_ARG, "haf_svm_predict needs a context made by haf_svm_create");
+    const bool prob = prob_estimates != nullptr;
     { int rc = check_csr(ctx, row_ptr, index, value, n_rows); if (rc) return rc; }
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
@@ -665,7 +709,7 @@ extern "C" int haf_svm_predict(haf_svm* ctx, const long long* row_ptr, const int
     memset(&ctx->timing, 0, sizeof ctx->timing);
     ctx->last_valid = false;
     if (n_rows == 0) return HAF_OK;
-    const bool tc = ctx->cfg.svm_mode == HAF_SVM_TENSOR_GUARD;
+    const bool tc = ctx->cfg.svm_mode == HAF_SVM_TENSOR_GUARD && !prob;
     const size_t chunk_rows = std::max<size_t>(256, std::min<size_t>((size_t)n_rows, ((size_t)512 << 20) / ((size_t)W * sizeof(double))));
     ENSURE(ctx, ctx->h_stage, 64);
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[8], st));
@@ -679,7 +723,8 @@ extern "C" int haf_svm_predict(haf_svm* ctx, const long long* row_ptr, const int
         ENSURE(ctx, ctx->d_xdense, rows * W); ENSURE(ctx, ctx->d_labels, rows);
         ENSURE(ctx, ctx->d_xn, ldx); ENSURE(ctx, ctx->d_dec, ldx); ENSURE(ctx, ctx->d_guardflag, ldx); ENSURE(ctx, ctx->d_guardlist, ldx);
         if (tc) { ENSURE(ctx, ctx->d_Xh, ldx * ctx->KB * haftc::BK); if (ctx->tc_passes >= 3) ENSURE(ctx, ctx->d_Xl, ldx * ctx->KB * haftc::BK); ENSURE(ctx, ctx->d_asum, ldx); }
-        else if (ctx->cfg.svm_mode == HAF_SVM_FP32_GUARD) ENSURE(ctx, ctx->d_X, (size_t)ctx->Kpad * ldx);
+        else if (ctx->cfg.svm_mode == HAF_SVM_FP32_GUARD && !prob) ENSURE(ctx, ctx->d_X, (size_t)ctx->Kpad * ldx);
+        if (prob) ENSURE(ctx, ctx->d_probs, rows * 2);
         const size_t exact_cap = std::min<size_t>(ldx, std::max<size_t>(4096, ((size_t)1 << 30) / ((size_t)ctx->Spad * 8)));
         ENSURE(ctx, ctx->d_kscratch, exact_cap * ctx->Spad);
         unsigned* cnt = ctx->d_counters.p;
@@ -696,7 +741,7 @@ extern "C" int haf_svm_predict(haf_svm* ctx, const long long* row_ptr, const int
         CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_xdense.p, 0, rows * W * sizeof(double), st));
         csr_to_dense_kernel<<<(unsigned)rows, 128, 0, st>>>(ctx->d_csr_ptr.p, ctx->d_csr_idx.p, ctx->d_csr_val.p, (int)rows, W, ctx->d_xdense.p);
         LAUNCHED(ctx);
-        if (ctx->cfg.svm_mode != HAF_SVM_FP64_EXACT) {
+        if (ctx->cfg.svm_mode != HAF_SVM_FP64_EXACT && !prob) {
             pack_svm_inputs_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(ctx->d_xdense.p, (int)rows, W, ctx->Krow, ctx->KB, tc ? ctx->d_Xh.p : nullptr,
                                                                               (tc && ctx->tc_passes >= 3) ? ctx->d_Xl.p : nullptr, tc ? nullptr : ctx->d_X.p, ldx, ctx->Kpad, ctx->d_xn.p);
             LAUNCHED(ctx);
@@ -705,8 +750,11 @@ extern "C" int haf_svm_predict(haf_svm* ctx, const long long* row_ptr, const int
         const int rcs = svm_stage(ctx, cnt, rows, ldx, ctx->G, 0, st, nullptr);
         ctx->cur_xdense = nullptr;
         if (rcs) return rcs;
-        labels_from_dec_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(ctx->d_dec.p, (int)rows, (double)ctx->label[0], (double)ctx->label[1], ctx->d_labels.p);
+        if (prob) prob_from_dec_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(ctx->d_dec.p, (int)rows, ctx->probA, ctx->probB, (double)ctx->label[0], (double)ctx->label[1],
+                                                                                      ctx->d_labels.p, ctx->d_probs.p);
+        else labels_from_dec_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(ctx->d_dec.p, (int)rows, (double)ctx->label[0], (double)ctx->label[1], ctx->d_labels.p);
         LAUNCHED(ctx);
+        if (prob) CUDA_TRY(ctx, cudaMemcpyAsync(prob_estimates + 2 * r0, ctx->d_probs.p, rows * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
         accumulate_counts_kernel<<<1, 1, 0, st>>>(cnt);
         LAUNCHED(ctx);
         if (labels) CUDA_TRY(ctx, cudaMemcpyAsync(labels + r0, ctx->d_labels.p, rows * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -724,7 +772,7 @@ extern "C" int haf_svm_predict(haf_svm* ctx, const long long* row_ptr, const int
                              (double)ctx->audit_max_rel, (double)ctx->guard_rel);
         ctx->tc_passes++;
         ctx->escalations++;
-        return haf_svm_predict(ctx, row_ptr, index, value, n_rows, labels, dec_values);
+        return svm_predict_impl(ctx, row_ptr, index, value, n_rows, labels, dec_values, prob_estimates);
     }
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev[8], ctx->ev[9]);
@@ -833,7 +881,7 @@ extern "C" void haf_destroy(haf_ctx* ctx) {
     ctx->d_integral.release(); ctx->d_rowscan.release(); ctx->d_mask.release(); ctx->d_labelgrid.release(); ctx->d_evals.release();
     ctx->d_unit_top.release(); ctx->d_unit_run.release(); ctx->d_unit_windows.release(); ctx->d_win.release(); ctx->d_X.release();
     ctx->d_xn.release(); ctx->d_dec.release(); ctx->d_guardflag.release(); ctx->d_guardlist.release(); ctx->d_kscratch.release();
-    ctx->d_xdense.release(); ctx->d_labels.release(); ctx->d_csr_ptr.release(); ctx->d_csr_idx.release(); ctx->d_csr_val.release();
+    ctx->d_xdense.release(); ctx->d_labels.release(); ctx->d_probs.release(); ctx->d_probgrid.release(); ctx->d_csr_ptr.release(); ctx->d_csr_idx.release(); ctx->d_csr_val.release();
     ctx->d_svn64.release(); ctx->d_Xg.release(); ctx->d_g2accum.release(); ctx->d_g2tickets.release(); ctx->d_guardlist2.release();
     ctx->d_SVh.release(); ctx->d_SVl.release(); ctx->d_Xh.release(); ctx->d_Xl.release(); ctx->d_svcoef.release(); ctx->d_dec_tc.release(); ctx->d_asum.release(); ctx->d_dimfeat.release(); ctx->d_round4.release();
     ctx->d_params.release(); ctx->d_counters.release(); ctx->h_stage.release(); ctx->h_results.release(); ctx->h_per_roll_top.release(); ctx->h_counters.release(); ctx->h_unit_windows.release();
@@ -948,7 +996,7 @@ static int launch_guard(haf_ctx* ctx, unsigned* cnt, int G, int ubase, cudaStrea
     q.accum = ctx->d_g2accum.p; q.tickets = ctx->d_g2tickets.p; q.tol2 = ctx->tier2_mode == 2 ? 1e30 : 1e-10;
     q.list2 = ctx->d_guardlist2.p; q.list2_count = cnt + 6;
     const bool audit = ctx->cfg.svm_mode == HAF_SVM_TENSOR_GUARD && ctx->d_dec_tc.p;
-    q.dec_tc = audit ? ctx->d_dec_tc.p : nullptr; q.audit_max = cnt + 12;
+    q.dec_tc = audit ? ctx->d_dec_tc.p : nullptr; q.audit_max = cnt + 12; q.guard_flag = audit ? ctx->d_guardflag.p : nullptr;
     const size_t smem = ((size_t)ctx->Dsv * HAF_G2_WB + HAF_G2_WB + 8 * HAF_G2_WB * 2) * sizeof(double);
     if (smem > 100 * 1024) return launch_exact(ctx, a, st, Wcap);   // models with > ~780 dimensions: exact-order kernels only
     const bool few = Wcap < 65536;   // a single goal: a handful of guard windows -> spread the support vectors over more CTAs
@@ -982,9 +1030,9 @@ static int tc_debug_flags() {
 // are in ctx->d_Xh/d_Xl (tensor mode), ctx->d_X (SIMT mode) or re-derivable by exact_scaled_input (FP64 mode / guard
 // band), then the guard band.  ev_guard (optional) is recorded between the contraction and the guard-band kernels.
 static int svm_stage(haf_ctx* ctx, unsigned* cnt, size_t Wcap, size_t ldx, int G, int ubase, cudaStream_t st, cudaEvent_t ev_guard) {
-    const bool tc = ctx->cfg.svm_mode == HAF_SVM_TENSOR_GUARD;
+    const bool tc = ctx->cfg.svm_mode == HAF_SVM_TENSOR_GUARD && !ctx->force_exact;
     const float neg_gamma_log2e = (float)(-ctx->gamma * 1.4426950408889634);
-    if (ctx->cfg.svm_mode == HAF_SVM_FP64_EXACT) {
+    if (ctx->cfg.svm_mode == HAF_SVM_FP64_EXACT || ctx->force_exact) {
         CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_guardflag.p, 0, ldx, st));
         { int rce = launch_exact(ctx, make_exact_args(ctx, nullptr, nullptr, cnt, G, ubase), st, Wcap); if (rce) return rce; }
         if (ev_guard) CUDA_TRY(ctx, cudaEventRecord(ev_guard, st));
@@ -1040,14 +1088,14 @@ static int svm_stage(haf_ctx* ctx, unsigned* cnt, size_t Wcap, size_t ldx, int G
         haftc::svm_finalize_kernel<<<(unsigned)((Wcap + 255) / 256), 256, 0, st>>>(ctx->d_dec.p, ctx->d_asum.p, ctx->d_xn.p, cnt + 0, ctx->rho,
                                                                                    tc_debug_flags() ? -1.0f : ctx->guard_rel,   // timing experiments: empty guard band
                                                                                    ctx->d_guardflag.p, ctx->d_guardlist.p, cnt + 1, audit ? ctx->audit_every : 0,
-                                                                                   audit ? ctx->d_dec_tc.p : nullptr, cnt + 13);
+                                                                                   audit ? ctx->d_dec_tc.p : nullptr, cnt + 13, ctx->e_floor);
         LAUNCHED(ctx);
         if (ev_guard) CUDA_TRY(ctx, cudaEventRecord(ev_guard, st));
         { int rce = launch_guard(ctx, cnt, G, ubase, st, Wcap, ldx); if (rce) return rce; }
     } else {
         svm_rbf_simt_kernel<<<(unsigned)(ldx / SVM_BM), 256, SVM_STAGES * SVM_BK * (SVM_BM + SVM_BN) * 4, st>>>(
             ctx->d_X.p, ldx, ctx->d_svT.p, ctx->Spad, ctx->Kpad, ctx->d_xn.p, ctx->d_svn.p, ctx->d_coef.p, neg_gamma_log2e, ctx->rho,
-            ctx->guard_rel, cnt + 0, ctx->d_dec.p, ctx->d_guardflag.p, ctx->d_guardlist.p, cnt + 1);
+            ctx->guard_rel, ctx->e_floor, cnt + 0, ctx->d_dec.p, ctx->d_guardflag.p, ctx->d_guardlist.p, cnt + 1);
         LAUNCHED(ctx);
         if (ev_guard) CUDA_TRY(ctx, cudaEventRecord(ev_guard, st));
         { int rce = launch_guard(ctx, cnt, G, ubase, st, Wcap, ldx); if (rce) return rce; }
@@ -1065,6 +1113,17 @@ static int run_jobs_once(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& job
     cudaStream_t st = ctx->stream;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     const long long launches0 = ctx->launches;
+
+    // probability mode (server.cpp:383-385 with svm_with_probability = true): all requests of a call agree
+    bool prob = false;
+    for (int j = 0; j < n_jobs; j++) {
+        const bool pj = jobs[j].rq.svm_with_probability != 0;
+        if (j == 0) prob = pj;
+        else if (pj != prob) return ctx->fail(HAF_ERR_ARG, "svm_with_probability must be the same for every request of a call");
+    }
+    if (prob && !ctx->has_prob) return ctx->fail(HAF_ERR_UNSUPPORTED, "Model does not support probabiliy estimates");   // svm-predict.c:213 (sic)
+    struct ForceExact { haf_ctx* c; bool on; ~ForceExact() { if (on) c->force_exact = false; } } force_exact_scope{ctx, prob};
+    if (prob) ctx->force_exact = true;
 
     // ---- host: unit parameters (transforms and mask constants use the HOST libm, see haf_host.hpp)
     const int U = n_jobs * R;
@@ -1096,15 +1155,22 @@ static int run_jobs_once(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& job
         jb.wbound = window_bound(G, jb.rq) * (jb.n_rolls_active - jb.roll_begin);
         hj[j].return_only_best = jb.rq.return_only_best; hj[j].graspval_top = jb.rq.graspval_top;
         hj[j].n_rolls_active = jb.n_rolls_active; hj[j].roll_begin = jb.roll_begin;
+        // a batch applies ONE request to every cloud: the transforms and mask constants (host libm, ~1 us per unit) are built
+        // once and copied -- at 6144 units per bench step they were ~1 ms of GPU idle time at the head of every call
+        const bool same_rq = j > 0 && memcmp(&jobs[j - 1].rq, &jb.rq, sizeof(haf_request)) == 0;
         for (int roll = 0; roll < R; roll++) {
             UnitParams& up = hu[j * R + roll];
-            memset(&up, 0, sizeof up);
-            float M[16];
-            hafhost::build_transform(jb.rq, roll, ctx->cfg.roll_step_deg, M);
-            memcpy(up.M, M, 12 * sizeof(float));
-            const hafhost::MaskConsts mc = hafhost::mask_consts(G, roll, ctx->cfg.roll_step_deg, ax, ay);
-            up.sa = mc.sa; up.ca = mc.ca; up.cx1 = mc.cx1; up.cy1 = mc.cy1; up.cx2 = mc.cx2; up.cy2 = mc.cy2;
-            up.cx3 = mc.cx3; up.cy3 = mc.cy3; up.cx4 = mc.cx4; up.cy4 = mc.cy4;
+            if (same_rq) {
+                up = hu[(j - 1) * R + roll];
+            } else {
+                memset(&up, 0, sizeof up);
+                float M[16];
+                hafhost::build_transform(jb.rq, roll, ctx->cfg.roll_step_deg, M);
+                memcpy(up.M, M, 12 * sizeof(float));
+                const hafhost::MaskConsts mc = hafhost::mask_consts(G, roll, ctx->cfg.roll_step_deg, ax, ay);
+                up.sa = mc.sa; up.ca = mc.ca; up.cx1 = mc.cx1; up.cy1 = mc.cy1; up.cx2 = mc.cx2; up.cy2 = mc.cy2;
+                up.cx3 = mc.cx3; up.cy3 = mc.cy3; up.cx4 = mc.cx4; up.cy4 = mc.cy4;
+            }
             up.cloud = (roll >= jb.roll_begin && roll < jb.n_rolls_active) ? jb.cloud : -1;
             up.job = j; up.roll = roll;
         }
@@ -1184,10 +1250,11 @@ static int run_jobs_once(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& job
         const int c0 = jobs[j0].cloud, c1 = jobs[j1 - 1].cloud + 1;  // clouds touched by this chunk
         ENSURE(ctx, ctx->d_keys, (size_t)Uc * GG); ENSURE(ctx, ctx->d_integral, (size_t)Uc * ld * ld);
         ENSURE(ctx, ctx->d_mask, (size_t)Uc * GG); ENSURE(ctx, ctx->d_labelgrid, (size_t)Uc * GG); ENSURE(ctx, ctx->d_evals, (size_t)Uc * GG);
-        const bool tc = ctx->cfg.svm_mode == HAF_SVM_TENSOR_GUARD;
+        const bool tc = ctx->cfg.svm_mode == HAF_SVM_TENSOR_GUARD && !prob;
+        if (prob) ENSURE(ctx, ctx->d_probgrid, (size_t)Uc * GG);
         ENSURE(ctx, ctx->d_win, ldx); ENSURE(ctx, ctx->d_xn, ldx);
         if (tc) { ENSURE(ctx, ctx->d_Xh, ldx * ctx->KB * haftc::BK); if (ctx->tc_passes >= 3) ENSURE(ctx, ctx->d_Xl, ldx * ctx->KB * haftc::BK); ENSURE(ctx, ctx->d_asum, ldx); }
-        else if (ctx->cfg.svm_mode == HAF_SVM_FP32_GUARD) ENSURE(ctx, ctx->d_X, (size_t)ctx->Kpad * ldx);
+        else if (ctx->cfg.svm_mode == HAF_SVM_FP32_GUARD && !prob) ENSURE(ctx, ctx->d_X, (size_t)ctx->Kpad * ldx);
         ENSURE(ctx, ctx->d_dec, ldx); ENSURE(ctx, ctx->d_guardflag, ldx); ENSURE(ctx, ctx->d_guardlist, ldx);
         if (!smallG) ENSURE(ctx, ctx->d_rowscan, (size_t)Uc * GG);
         // terms scratch of the exact path: one row of Spad doubles per entry; the guard list is bounded by what fits in 1 GiB
@@ -1265,7 +1332,7 @@ static int run_jobs_once(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& job
                                                                       ctx->Krow, (float)ctx->lower, ctx->cfg.emulate_text_roundtrip, ctx->d_round4.p, ctx->d_Xh.p,
                                                                       ctx->tc_passes >= 3 ? ctx->d_Xl.p : nullptr, ctx->d_xn.p, ctx->Dsv, ctx->KB);
             LAUNCHED(ctx);
-        } else if (ctx->cfg.svm_mode != HAF_SVM_FP64_EXACT) {
+        } else if (ctx->cfg.svm_mode != HAF_SVM_FP64_EXACT && !prob) {
             features_kernel<false><<<wblocks32, 256, 0, st>>>(ctx->d_integral.p, ctx->d_win.p, cnt + 0, G, ubase, ctx->d_feats.p, ctx->d_dims.p,
                                                               ctx->D, ctx->Kpad, ctx->lower, ctx->upper, ctx->cfg.emulate_text_roundtrip,
                                                               ctx->d_X.p, ldx, ctx->F, nullptr, nullptr, (int*)(cnt + 3));
@@ -1278,11 +1345,21 @@ static int run_jobs_once(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& job
         { int rcs = svm_stage(ctx, cnt, Wcap, ldx, G, ubase, st, prof ? ctx->ev_pool[ci * 8 + 5] : nullptr); if (rcs) return rcs; }
         // 6. labels -> grids, score stencil, argmax, tie rule
         if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[ci * 8 + 6], st));
-        label_scatter_kernel<<<(unsigned)((Wcap + 255) / 256), 256, 0, st>>>(ctx->d_dec.p, ctx->d_win.p, cnt + 0, G, ubase, ctx->gv[0], ctx->gv[1],
-                                                                            ctx->d_labelgrid.p);
-        LAUNCHED(ctx);
-        score_kernel<<<dim3((GG + 255) / 256, Uc), 256, 0, st>>>(ctx->d_labelgrid.p, G, units_c, ctx->d_evals.p, ctx->d_unit_top.p + ubase);
-        LAUNCHED(ctx);
+        if (prob) {   // float grid res * prob with the reference's one-line shift, then the same stencil in float (kernels.cuh)
+            prob_value_kernel<<<(unsigned)((Wcap + 127) / 128), 128, 0, st>>>(ctx->d_dec.p, ctx->d_win.p, cnt + 0, G, ubase, ctx->probA, ctx->probB,
+                                                                             ctx->prob_res[0], ctx->prob_res[1], ctx->d_evals.p, (int*)(cnt + 3));
+            LAUNCHED(ctx);
+            prob_shift_grid_kernel<<<Uc, 1024, 0, st>>>(ctx->d_mask.p, ctx->d_evals.p, G, units_c, ctx->prob_header_val, ctx->d_probgrid.p);
+            LAUNCHED(ctx);
+            score_prob_kernel<<<dim3((GG + 255) / 256, Uc), 256, 0, st>>>(ctx->d_probgrid.p, G, units_c, ctx->d_evals.p, ctx->d_unit_top.p + ubase);
+            LAUNCHED(ctx);
+        } else {
+            label_scatter_kernel<<<(unsigned)((Wcap + 255) / 256), 256, 0, st>>>(ctx->d_dec.p, ctx->d_win.p, cnt + 0, G, ubase, ctx->gv[0], ctx->gv[1],
+                                                                                ctx->d_labelgrid.p);
+            LAUNCHED(ctx);
+            score_kernel<<<dim3((GG + 255) / 256, Uc), 256, 0, st>>>(ctx->d_labelgrid.p, G, units_c, ctx->d_evals.p, ctx->d_unit_top.p + ubase);
+            LAUNCHED(ctx);
+        }
         tie_rule_kernel<<<dim3((G + 7) / 8, Uc), 256, 0, st>>>(ctx->d_evals.p, G, units_c, ctx->d_unit_top.p + ubase, ctx->d_unit_run.p + ubase);
         LAUNCHED(ctx);
         if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[ci * 8 + 7], st));
@@ -1493,7 +1570,19 @@ extern "C" int haf_search_batch_packed(haf_ctx* ctx, const float* xyz_all, const
     int rc = run_jobs(ctx, cs, jobs, nullptr, nullptr, nullptr, ctx->debug_keep_batch);
     ctx->copy_pieces = 0;
     if (rc) return rc;
-    for (int c = 0; c < n_clouds; c++) fill_best(ctx, jobs[c], ctx->h_results.p[c], 0, 0, &best_per_cloud[c]);
+    {   // one request for all clouds: the winning roll's transform is built once per roll, not once per cloud
+        std::vector<haf_best> per_roll(ctx->R);
+        std::vector<char> have(ctx->R, 0);
+        for (int c = 0; c < n_clouds; c++) {
+            const JobResult& r = ctx->h_results.p[c];
+            if (r.roll < 0 || r.roll >= ctx->R) { fill_best(ctx, jobs[c], r, 0, 0, &best_per_cloud[c]); continue; }
+            if (!have[r.roll]) { fill_best(ctx, jobs[c], r, 0, 0, &per_roll[r.roll]); have[r.roll] = 1; }
+            haf_best& b = best_per_cloud[c];
+            b = per_roll[r.roll];   // roll, roll_rad, M, tilt, approach_idx are functions of (request, roll) alone
+            b.row = r.row; b.col = r.col; b.topval = r.topval; b.eval = r.topval - 20;
+            b.rolls_done = r.rolls_done; b.n_windows_scored = r.n_windows; b.n_guard = 0;
+        }
+    }
     return HAF_OK;
 }
 

@@ -3,11 +3,13 @@
 // The action server calls   <pkg>/libsvm-3.12/svm-predict  /tmp/features.txt.scale  <model>  /tmp/output_calc_gp.txt
 // (server.cpp:786-792); pointing that path at this binary swaps the classifier without touching the server.
 //
-//   svm-predict [-b 0] [--device N] [--svm-mode 0|1|2] test_file model_file output_file
+//   svm-predict [-b 0|1] [--device N] [--svm-mode 0|1|2] test_file model_file output_file
 //
 // Same files, same "%g" label per line, same "Accuracy = ..." line on stdout, same "Wrong input format at line N" /
 // exit status 1 (rows before the bad line are still classified and written, like the reference's streaming loop).
-// -b 1 (probability estimates) is not supported: the server hard-wires it off (server.cpp:383).
+// -b 1 (svm-predict.c:53-66, :111-118; the server's svm_with_probability branch, server.cpp:795): "labels l0 l1" header, then
+// "%g %g %g" per row from haf_svm_predict_probability; the same two messages as the reference when the model and the switch
+// disagree (svm-predict.c:209-221).
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -20,7 +22,7 @@
 static void usage() {
     printf("Usage: svm-predict [options] test_file model_file output_file\n"
            "options:\n"
-           "-b probability_estimates: only 0 is supported by the B200 front end\n"
+           "-b probability_estimates: whether to predict probability estimates, 0 or 1 (default 0)\n"
            "--device N: CUDA device ordinal (default 0)\n"
            "--svm-mode M: 0 tensor cores + FP64 guard band (default), 1 FP64 libsvm order, 2 FP32 + guard band\n");
     exit(1);
@@ -55,7 +57,6 @@ int main(int argc, char** argv) {
     if (!input) { fprintf(stderr, "can't open input file %s\n", in_path); return 1; }
     FILE* output = fopen(out_path, "w");
     if (!output) { fprintf(stderr, "can't open output file %s\n", out_path); return 1; }
-    if (prob) { fprintf(stderr, "probability estimates (-b 1) are not supported by the B200 front end\n"); return 1; }
 
     hafsvmtext::Rows R;
     std::string line;
@@ -71,14 +72,24 @@ int main(int argc, char** argv) {
     int rc = haf_svm_create(&svm, model_path, device, svm_mode, R.max_index, 0.0f);
     if (rc == HAF_ERR_IO) { fprintf(stderr, "can't open model file %s\n", model_path); return 1; }
     if (rc != HAF_OK) { fprintf(stderr, "svm-predict (B200): %s\n", haf_last_error(nullptr)); return 1; }
-    std::vector<double> labels(R.n() > 0 ? R.n() : 1);
-    rc = haf_svm_predict(svm, R.row_ptr.data(), R.index.data(), R.value.data(), R.n(), labels.data(), nullptr);
+    if (prob) {   // svm-predict.c:209-221
+        if (!haf_svm_check_probability_model(svm)) { fprintf(stderr, "Model does not support probabiliy estimates\n"); haf_svm_destroy(svm); return 1; }
+    } else if (haf_svm_check_probability_model(svm)) {
+        printf("Model supports probability estimates, but disabled in prediction.\n");
+    }
+    std::vector<double> labels(R.n() > 0 ? R.n() : 1), probs(prob ? 2 * labels.size() : 0);
+    haf_info info;
+    haf_get_info(svm, &info);
+    if (prob) rc = haf_svm_predict_probability(svm, R.row_ptr.data(), R.index.data(), R.value.data(), R.n(), labels.data(), probs.data());
+    else rc = haf_svm_predict(svm, R.row_ptr.data(), R.index.data(), R.value.data(), R.n(), labels.data(), nullptr);
     if (rc != HAF_OK) { fprintf(stderr, "svm-predict (B200): %s\n", haf_last_error(svm)); haf_svm_destroy(svm); return 1; }
     haf_svm_destroy(svm);
 
     int correct = 0;
+    if (prob) fprintf(output, "labels %d %d\n", info.label0, info.label1);   // svm-predict.c:61-65
     for (int r = 0; r < R.n(); r++) {
-        fprintf(output, "%g\n", labels[r]);
+        if (prob) fprintf(output, "%g %g %g\n", labels[r], probs[2 * r], probs[2 * r + 1]);   // :113-117
+        else fprintf(output, "%g\n", labels[r]);
         if (labels[r] == R.target[r]) ++correct;
     }
     if (bad_line) {

@@ -925,7 +925,7 @@ __global__ void __launch_bounds__(256, 2) svm_rbf_simt_kernel(const float* __res
                                                                const float* __restrict__ svT, int Spad, int Kpad,
                                                                const float* __restrict__ xn, const float* __restrict__ svn,
                                                                const float* __restrict__ coef, float neg_gamma_log2e,
-                                                               double rho, float guard_rel,
+                                                               double rho, float guard_rel, float e_floor /*see svm_finalize_kernel*/,
                                                                const unsigned* __restrict__ win_count,
                                                                double* __restrict__ dec, unsigned char* __restrict__ guard_flag,
                                                                int* __restrict__ guard_list, unsigned* __restrict__ guard_count) {
@@ -1044,7 +1044,7 @@ __global__ void __launch_bounds__(256, 2) svm_rbf_simt_kernel(const float* __res
             if (m < W) {
                 const double dv = dsum[i] - rho;
                 dec[m] = dv;
-                const bool g = !(fabs(dv) > (double)guard_rel * ((double)asum[i] + fabs(rho)));   // NaN-safe
+                const bool g = !(fabs(dv) > (double)guard_rel * ((double)asum[i] + fabs(rho))) || !(asum[i] >= e_floor);   // NaN-safe
                 guard_flag[m] = g ? 1 : 0;
                 if (g) guard_list[atomicAdd(guard_count, 1u)] = (int)m;
             }
@@ -1200,6 +1200,7 @@ struct Guard2Args {
     int* list2; unsigned* list2_count;   // tier-3 list
     const double* dec_tc;        // audit: the contraction's decision value of every listed window (NaN = not comparable) or NULL
     unsigned* audit_max;         // audit: max over listed windows of |dec_tc - dec_fp64| / (E + |rho|), as float bits
+    const unsigned char* guard_flag;   // [W] 1 = inside the guard band; listed windows with 0 are the audit sample: measured, not rewritten
 };
 __global__ void __launch_bounds__(256) guard_inputs_kernel(const ExactArgs A, const Guard2Args Q) {
     const unsigned n = min(*Q.list_count, (unsigned)Q.cap);
@@ -1223,7 +1224,8 @@ __global__ void __launch_bounds__(256) guard_fma_kernel(const ExactArgs A, const
     const unsigned n = min(total, (unsigned)Q.cap);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (blockIdx.x == 0 && blockIdx.y == 0)   // overflow of the tier-2 buffers: straight to tier 3
-        for (unsigned e = (unsigned)Q.cap + threadIdx.x; e < total; e += blockDim.x) Q.list2[atomicAdd(Q.list2_count, 1u)] = Q.list[e];
+        for (unsigned e = (unsigned)Q.cap + threadIdx.x; e < total; e += blockDim.x)
+            if (!Q.guard_flag || Q.guard_flag[Q.list[e]]) Q.list2[atomicAdd(Q.list2_count, 1u)] = Q.list[e];
     const int i0 = blockIdx.y * (256 * SVT);
     const double g2 = A.gamma * 1.4426950408889634;
     for (unsigned e0 = blockIdx.x * WB; e0 < n; e0 += gridDim.x * WB) {
@@ -1327,8 +1329,11 @@ __global__ void __launch_bounds__(256) guard_fma_kernel(const ExactArgs A, const
                     const float rel = (float)(fabs(tcv - dv) / (E + fabs(A.rho)));
                     if (rel == rel) atomicMax(Q.audit_max, __float_as_uint(rel));
                 }
-                A.dec[w] = dv;
-                if (!(fabs(dv) > Q.tol2 * (E + fabs(A.rho)))) Q.list2[atomicAdd(Q.list2_count, 1u)] = w;
+                // a sample window keeps the contraction's value: what a row gets must not depend on whether its index was sampled
+                if (!Q.guard_flag || Q.guard_flag[w]) {
+                    A.dec[w] = dv;
+                    if (!(fabs(dv) > Q.tol2 * (E + fabs(A.rho)))) Q.list2[atomicAdd(Q.list2_count, 1u)] = w;
+                }
             }
             if (threadIdx.x == 0) Q.tickets[e0 / WB] = 0;
         }
@@ -1458,8 +1463,14 @@ __global__ void reduce_rolls_kernel(const unsigned long long* __restrict__ unit_
         if (roll >= jp.roll_begin && roll < jp.n_rolls_active) {
             val = (int)(unsigned)(unit_top[u] >> 32) - (1 << 20);
             const unsigned long long rk = unit_run[u];
-            row = 0xFFFF - (int)((rk >> 16) & 0xFFFFu);
-            col = (int)(rk & 0xFFFFu);
+            if (rk) {
+                row = 0xFFFF - (int)((rk >> 16) & 0xFFFFu);
+                col = (int)(rk & 0xFFFFu);
+            } else {   // no cell EQUALS topval (probability mode: topval is a truncated float): the first-maximum cell stays (:881-892)
+                const unsigned cell = 0xFFFFFFFFu - (unsigned)(unit_top[u] & 0xFFFFFFFFull);
+                row = (int)(cell / (unsigned)G);
+                col = (int)(cell % (unsigned)G);
+            }
         }
         per_roll_top[(j * R + roll) * 3 + 0] = row;
         per_roll_top[(j * R + roll) * 3 + 1] = col;
@@ -1597,6 +1608,175 @@ __global__ void scale_apply_kernel(double* __restrict__ dense, size_t n_elems, i
         else if (v == mx) v = upper;
         else v = __dadd_rn(lower, __ddiv_rn(__dmul_rn(__dsub_rn(upper, lower), __dsub_rn(v, mn)), __dsub_rn(mx, mn)));
         dense[t] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Probability estimates: svm-predict -b 1 and the server's svm_with_probability branch.
+// ---------------------------------------------------------------------------------------------------
+// svm_predict_probability for nr_class = 2 (svm.cpp:2550-2590): sigmoid_predict (:1818-1826), the clamp to
+// [1e-7, 1 - 1e-7] with libsvm's own min / max templates, then multiclass_probability (:1829-1890, "method 2" of Wu, Lin
+// and Weng) -- an ITERATION stopped at eps = 0.005 / k, so its result is not the sigmoid value and has to be replayed
+// operation by operation (double, no FMA, the reference's association).  Only exp() differs from the host (glibc vs CUDA,
+// <= 1 ulp): the estimates agree to ~1e-16 relative, i.e. the "%g" text is the same unless a value sits within that of a
+// 6-digit rounding boundary.  Returns the index of the predicted label (strict >, first wins: :2577-2580).
+__device__ __forceinline__ int svm_probability_2class(double dec, double A, double B, double p[2]) {
+    const double fApB = __dadd_rn(__dmul_rn(dec, A), B);
+    double s;
+    if (fApB >= 0) { const double e = exp(-fApB); s = __ddiv_rn(e, __dadd_rn(1.0, e)); }   // 1-p used later; avoid catastrophic cancellation
+    else s = __ddiv_rn(1.0, __dadd_rn(1.0, exp(fApB)));
+    const double min_prob = 1e-7, hi = __dsub_rn(1.0, min_prob);
+    double r01 = (s > min_prob) ? s : min_prob;     // max(x, y) = (x > y) ? x : y
+    r01 = (r01 < hi) ? r01 : hi;                    // min(x, y) = (x < y) ? x : y
+    const double r10 = __dsub_rn(1.0, r01);
+    // Q[t][t] += r[j][t] * r[j][t];  Q[t][j] = -r[j][t] * r[t][j]
+    const double Q00 = __dadd_rn(0.0, __dmul_rn(r10, r10)), Q01 = __dmul_rn(-r10, r01), Q11 = __dadd_rn(0.0, __dmul_rn(r01, r01)), Q10 = Q01;
+    const double eps = 0.005 / 2;
+    double p0 = 1.0 / 2, p1 = 1.0 / 2;
+    for (int iter = 0; iter < 100; iter++) {
+        double Qp0 = __dadd_rn(__dadd_rn(0.0, __dmul_rn(Q00, p0)), __dmul_rn(Q01, p1));
+        double pQp = __dadd_rn(0.0, __dmul_rn(p0, Qp0));
+        double Qp1 = __dadd_rn(__dadd_rn(0.0, __dmul_rn(Q10, p0)), __dmul_rn(Q11, p1));
+        pQp = __dadd_rn(pQp, __dmul_rn(p1, Qp1));
+        double max_error = 0;
+        const double e0 = fabs(__dsub_rn(Qp0, pQp)), e1 = fabs(__dsub_rn(Qp1, pQp));
+        if (e0 > max_error) max_error = e0;
+        if (e1 > max_error) max_error = e1;
+        if (max_error < eps) break;
+        {   // t = 0
+            const double diff = __ddiv_rn(__dadd_rn(-Qp0, pQp), Q00), od = __dadd_rn(1.0, diff);
+            p0 = __dadd_rn(p0, diff);
+            pQp = __ddiv_rn(__ddiv_rn(__dadd_rn(pQp, __dmul_rn(diff, __dadd_rn(__dmul_rn(diff, Q00), __dmul_rn(2.0, Qp0)))), od), od);
+            Qp0 = __ddiv_rn(__dadd_rn(Qp0, __dmul_rn(diff, Q00)), od); p0 = __ddiv_rn(p0, od);
+            Qp1 = __ddiv_rn(__dadd_rn(Qp1, __dmul_rn(diff, Q01)), od); p1 = __ddiv_rn(p1, od);
+        }
+        {   // t = 1
+            const double diff = __ddiv_rn(__dadd_rn(-Qp1, pQp), Q11), od = __dadd_rn(1.0, diff);
+            p1 = __dadd_rn(p1, diff);
+            pQp = __ddiv_rn(__ddiv_rn(__dadd_rn(pQp, __dmul_rn(diff, __dadd_rn(__dmul_rn(diff, Q11), __dmul_rn(2.0, Qp1)))), od), od);
+            Qp0 = __ddiv_rn(__dadd_rn(Qp0, __dmul_rn(diff, Q10)), od); p0 = __ddiv_rn(p0, od);
+            Qp1 = __ddiv_rn(__dadd_rn(Qp1, __dmul_rn(diff, Q11)), od); p1 = __ddiv_rn(p1, od);
+        }
+    }
+    p[0] = p0; p[1] = p1;
+    return p1 > p0 ? 1 : 0;
+}
+// haf_svm_predict_probability: labels [n], prob_estimates [n][2] (the order of the model's labels, svm-predict.c:111-118)
+__global__ void prob_from_dec_kernel(const double* __restrict__ dec, int n, double A, double B, double l0, double l1,
+                                     double* __restrict__ labels, double* __restrict__ probs) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double p[2];
+    const int idx = svm_probability_2class(dec[i], A, B, p);
+    labels[i] = idx ? l1 : l0;
+    probs[2 * (size_t)i] = p[0];
+    probs[2 * (size_t)i + 1] = p[1];
+}
+// The server's probability branch (server.cpp:831-841) reads "<label> <p0> <p1>" lines: res = atof(first two characters),
+// prob = atof of the SECOND estimate when res > 0, else of the first (whatever the model's label order is), the grid value is
+// res * prob in float.  res0 / res1: atof of the first two characters of "%g" of the two labels (host); the estimate goes
+// through the "%g" text (text6) and a double -> float conversion.  Values land in pv[unit][cell]; the reference's one-line
+// shift (below) is applied afterwards.
+__global__ void prob_value_kernel(const double* __restrict__ dec, const int2* __restrict__ win, const unsigned* __restrict__ win_count,
+                                  int G, int unit_base, double A, double B, int res0, int res1, float* __restrict__ pv,
+                                  int* __restrict__ unsupported_flag) {
+    const unsigned W = *win_count;
+    const unsigned w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= W) return;
+    double p[2];
+    const int idx = svm_probability_2class(dec[w], A, B, p);
+    const int res = idx ? res1 : res0;
+    bool uns = false;
+    const float prob = (float)hafdec::text6(res > 0 ? p[1] : p[0], &uns);
+    if (uns) *unsupported_flag = 1;
+    const int2 uc = win[w];
+    pv[(size_t)(uc.x - unit_base) * G * G + uc.y] = __fmul_rn((float)res, prob);
+}
+// THE ONE-LINE SHIFT.  show_predicted_gps reads the first line of the output file BEFORE its loop (server.cpp:817-818) and
+// the next one after every valid window (:846).  With -b 1 the file starts with the header "labels <l0> <l1>"
+// (svm-predict.c:57-66), so the k-th valid window (row-major) of a roll gets the prediction of window k - 1, the first one
+// gets the header parsed as a prediction (res = atof("la") = 0, prob = atof(" <l0>"): header_val = 0 * (float)l0, i.e. -0.0f
+// for a negative first label) and the last prediction is never read.  grid[cell] = -1 outside the mask (:828-829).
+// One CTA per unit walks the cells in order carrying the last valid cell seen.
+__global__ void __launch_bounds__(1024) prob_shift_grid_kernel(const unsigned char* __restrict__ mask, const float* __restrict__ pv, int G,
+                                                               const UnitParams* __restrict__ units, float header_val, float* __restrict__ grid) {
+    const int u = blockIdx.x;
+    if (units[u].cloud < 0) return;
+    const int GG = G * G;
+    const unsigned char* m = mask + (size_t)u * GG;
+    const float* v = pv + (size_t)u * GG;
+    float* g = grid + (size_t)u * GG;
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    if (threadIdx.x == 0) s_carry = -1;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int c0 = 0; c0 < GG; c0 += 1024) {
+        const int cell = c0 + threadIdx.x;
+        const bool valid = cell < GG && m[cell];
+        // last valid cell strictly before this one: exclusive max-scan of (valid ? cell : -1)
+        int mine = valid ? cell : -1, incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl = max(incl, up);
+        }
+        int excl = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) excl = -1;
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        int before = s_carry;
+        for (int k = 0; k < warp; k++) before = max(before, s_warp[k]);
+        const int prev = max(before, excl);
+        if (cell < GG) g[cell] = valid ? (prev >= 0 ? v[prev] : header_val) : -1.0f;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = max(prev, mine);
+        __syncthreads();
+    }
+}
+// a13 on the float grid (server.cpp:865-897): the 29 products int * float and their sum in the reference's order, in float;
+// topval_gp = (int)graspseval (truncation) whenever graspseval > topval_gp, and the overall top follows only when that
+// integer strictly grows (:881-892) -> the per-roll top is the FIRST cell reaching the maximum of trunc(graspseval):
+// the same ordered key as score_kernel with trunc(v) in the value field.  The tie rule (graspseval == topval_gp) runs
+// unchanged on evals.
+__global__ void __launch_bounds__(256) score_prob_kernel(const float* __restrict__ grid, int G, const UnitParams* __restrict__ units,
+                                                         float* __restrict__ evals, unsigned long long* __restrict__ unit_top) {
+    const int u = blockIdx.y;
+    if (units[u].cloud < 0) return;
+    const int GG = G * G;
+    const int cell = blockIdx.x * 256 + threadIdx.x;
+    const float* L = grid + (size_t)u * GG;
+    float e = 0.0f;
+    const bool have = cell < GG;
+    if (have) {
+        const int row = cell / G, col = cell - row * G;
+        if (!(L[cell] < 0.0f) && row >= 2 && row < G - 2 && col >= 4 && col < G - 4) {   // mask-true cells are >= 7 from the border
+            float s = 0.0f;
+            bool first = true;
+#define PG(w, dr, dc) { const float t = __fmul_rn((float)(w), L[(row + (dr)) * G + (col + (dc))]); s = first ? t : __fadd_rn(s, t); first = false; }
+            PG(1, -2, -2) PG(2, -2, -1) PG(3, -2, 0) PG(2, -2, 1) PG(1, -2, 2)
+            PG(2, -1, -2) PG(3, -1, -1) PG(4, -1, 0) PG(3, -1, 1) PG(2, -1, 2)
+            PG(2, 0, -4) PG(2, 0, -3) PG(3, 0, -2) PG(4, 0, -1) PG(55, 0, 0) PG(4, 0, 1) PG(3, 0, 2) PG(2, 0, 3) PG(2, 0, 4)
+            PG(2, 1, -2) PG(3, 1, -1) PG(4, 1, 0) PG(3, 1, 1) PG(2, 1, 2)
+            PG(1, 2, -2) PG(2, 2, -1) PG(3, 2, 0) PG(2, 2, 1) PG(1, 2, 2)
+#undef PG
+            e = s;
+        }
+        evals[(size_t)u * GG + cell] = e;
+    }
+    const int ti = (int)e;   // float -> int truncates toward zero, like the reference's assignment
+    unsigned long long key = have ? (((unsigned long long)(unsigned)(ti + (1 << 20))) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)cell) : 0ull;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+        key = other > key ? other : key;
+    }
+    __shared__ unsigned long long sk[8];
+    if ((threadIdx.x & 31) == 0) sk[threadIdx.x >> 5] = key;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; w++) key = sk[w] > key ? sk[w] : key;
+        atomicMax(unit_top + u, key);
     }
 }
 

@@ -625,7 +625,8 @@ svm_rbf_tc3_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_consta
 // tensor-core products when the measured error leaves less than 4x margin inside the guard band).
 __global__ void svm_finalize_kernel(double* __restrict__ dec, const float* __restrict__ asum, const float* __restrict__ xn,
                                     const unsigned* __restrict__ win_count, double rho, float guard_rel, unsigned char* __restrict__ guard_flag, int* __restrict__ guard_list,
-                                    unsigned* __restrict__ guard_count, int audit_every, double* __restrict__ dec_tc, unsigned* __restrict__ audit_only_count) {
+                                    unsigned* __restrict__ guard_count, int audit_every, double* __restrict__ dec_tc, unsigned* __restrict__ audit_only_count,
+                                    float e_floor) {
     const unsigned W = *win_count;
     const unsigned m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= W) return;
@@ -633,7 +634,10 @@ __global__ void svm_finalize_kernel(double* __restrict__ dec, const float* __res
     dec[m] = dv;
     // xn = +inf marks a window whose inputs left the fp16 range (features_tc_kernel): always re-evaluated exactly
     const bool outside = !(xn[m] < 3.0e38f);
-    const bool g = !(fabs(dv) > (double)guard_rel * ((double)asum[m] + fabs(rho))) || outside;  // asum = E above
+    // FP32 RANGE.  ex2.approx.ftz returns 0 for kernel values below 2^-126: a window far from every support vector of a
+    // large-gamma model loses terms of up to sum|coef| 2^-126 that way.  Against E >= e_floor = sum|coef| 2^-100 that is
+    // 1.5e-8 E -- nothing; a window whose E is smaller than that is evaluated in FP64 (whose range libsvm's own doubles have).
+    const bool g = !(fabs(dv) > (double)guard_rel * ((double)asum[m] + fabs(rho))) || outside || !(asum[m] >= e_floor);  // asum = E above
     const bool audit = audit_every > 0 && (m % (unsigned)audit_every) == 0u;
     guard_flag[m] = g ? 1 : 0;
     if (g || audit) {

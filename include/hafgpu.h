@@ -90,7 +90,10 @@ typedef struct {
                                   caller's time budget / preempt checks (:350-357, :367-374)                   */
     int roll_begin;            /* first roll to evaluate (0 normally); > 0 only when one goal's rolls are sharded
                                   over several GPUs -- the caller merges the per-roll tops          */
-    int reserved;
+    int svm_with_probability;  /* the `svm_with_probability` switch of loop_control (server.cpp:383-385; hard-wired false there):
+                                  1 = classify with probability estimates (svm-predict -b 1 on a model carrying probA / probB) and
+                                  score the float grid res * prob exactly as show_predicted_gps does (:831-841), one-line shift
+                                  included; every request of a call must agree.  0 = labels only (the reference as shipped) */
 } haf_request;
 
 typedef struct {
@@ -183,6 +186,15 @@ void haf_svm_destroy(haf_svm* s);
  * values carry the tolerance of the chosen svm_mode.  haf_last_error / haf_get_timing / haf_get_info take the handle. */
 int haf_svm_predict(haf_svm* s, const long long* row_ptr, const int* index, const double* value, int n_rows,
                     double* labels, double* dec_values);
+/* svm-predict -b 1 (svm-predict.c:111-118): svm_predict_probability for every row (svm.cpp:2550-2590: sigmoid_predict :1818,
+ * clamp to [1e-7, 1 - 1e-7], multiclass_probability :1829-1890).  prob_estimates [n_rows][2] in the order of the model's
+ * labels (haf_get_info: label0, label1), labels [n_rows] = the label with the larger estimate (first on ties).  Every row is
+ * evaluated on the FP64 exact-order path whatever svm_mode the handle was made with (the estimates are printed with six
+ * digits).  HAF_ERR_UNSUPPORTED with libsvm's own message when the model carries no probA / probB.
+ * haf_svm_check_probability_model: svm_check_probability_model (svm.cpp:3098-3104), 1 / 0. */
+int haf_svm_predict_probability(haf_svm* s, const long long* row_ptr, const int* index, const double* value, int n_rows,
+                                double* labels, double* prob_estimates);
+int haf_svm_check_probability_model(const haf_svm* s);
 /* svm-scale pass 2 (svm-scale.c:165-198): per-feature min / max over the rows, absent entries counting as 0.
  * fmin / fmax: [max_index + 1], entry 0 unused, IN/OUT (start from +DBL_MAX / -DBL_MAX; call per piece of a file). */
 int haf_scale_minmax(int device, const long long* row_ptr, const int* index, const double* value, int n_rows, int max_index,

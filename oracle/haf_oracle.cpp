@@ -24,6 +24,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <sstream>
 #include <string>
 #include <vector>
 
@@ -467,6 +468,8 @@ struct OrcSvm {
     double gamma, rho;
     int l, nr_class, label[2], nSV[2];
     int max_index;
+    bool has_probA, has_probB;                // svm_check_probability_model: both (svm.cpp:3098-3104)
+    double probA, probB;                      // :2811-2824 (one class pair)
     std::vector<double> coef;                 // [l]
     std::vector<std::vector<int> > idx;       // sparse SVs, file order
     std::vector<std::vector<double> > val;
@@ -478,6 +481,7 @@ void* orc_svm_load(const char* path) {
     OrcSvm* m = new OrcSvm();
     m->gamma = 0; m->rho = 0; m->l = 0; m->nr_class = 0; m->max_index = 0;
     m->label[0] = m->label[1] = 0; m->nSV[0] = m->nSV[1] = 0;
+    m->has_probA = m->has_probB = false; m->probA = m->probB = 0;
     char cmd[81];
     bool ok = true, have_sv = false;
     while (ok && fscanf(fp, "%80s", cmd) == 1) {
@@ -489,12 +493,14 @@ void* orc_svm_load(const char* path) {
         else if (!strcmp(cmd, "rho")) { if (fscanf(fp, "%lf", &m->rho) != 1) ok = false; }
         else if (!strcmp(cmd, "label")) { if (fscanf(fp, "%d %d", &m->label[0], &m->label[1]) != 2) ok = false; }
         else if (!strcmp(cmd, "nr_sv")) { if (fscanf(fp, "%d %d", &m->nSV[0], &m->nSV[1]) != 2) ok = false; }
+        else if (!strcmp(cmd, "probA")) { if (fscanf(fp, "%lf", &m->probA) != 1) ok = false; m->has_probA = true; }
+        else if (!strcmp(cmd, "probB")) { if (fscanf(fp, "%lf", &m->probB) != 1) ok = false; m->has_probB = true; }
         else if (!strcmp(cmd, "SV")) {
             int c;
             while ((c = getc(fp)) != EOF && c != '\n') {}
             have_sv = true;
             break;
-        } else ok = false;  // probA/probB/degree/coef0: not a plain 2-class RBF C-SVC model
+        } else ok = false;  // degree/coef0: not a plain 2-class RBF C-SVC model
     }
     if (!ok || !have_sv) { fclose(fp); delete m; return NULL; }
     std::string line;
@@ -563,6 +569,175 @@ void orc_svm_decision(void* h, const double* x, int W, int dim, double* dec, int
         if (dec) dec[w] = sum_dec;
         if (labels) labels[w] = (sum_dec > 0) ? m->label[0] : m->label[1];
     }
+}
+
+// =====================================================================================
+// f4  probability estimates -- svm.cpp:1818-1826 (sigmoid_predict), :1829-1890 (multiclass_probability),
+//     :2550-2590 (svm_predict_probability); svm-predict.c:53-66, :111-118 (the -b 1 output file)
+// =====================================================================================
+int orc_svm_check_probability_model(void* h) {
+    OrcSvm* m = static_cast<OrcSvm*>(h);
+    return (m->has_probA && m->has_probB) ? 1 : 0;
+}
+static double orc_sigmoid_predict(double decision_value, double A, double B) {
+    double fApB = decision_value * A + B;
+    if (fApB >= 0) return exp(-fApB) / (1.0 + exp(-fApB));
+    else return 1.0 / (1 + exp(fApB));
+}
+static void orc_multiclass_probability(int k, double** r, double* p) {
+    int t, j;
+    int iter = 0, max_iter = (100 > k) ? 100 : k;
+    std::vector<std::vector<double> > Q(k, std::vector<double>(k, 0.0));
+    std::vector<double> Qp(k, 0.0);
+    double pQp, eps = 0.005 / k;
+    for (t = 0; t < k; t++) {
+        p[t] = 1.0 / k;
+        Q[t][t] = 0;
+        for (j = 0; j < t; j++) { Q[t][t] += r[j][t] * r[j][t]; Q[t][j] = Q[j][t]; }
+        for (j = t + 1; j < k; j++) { Q[t][t] += r[j][t] * r[j][t]; Q[t][j] = -r[j][t] * r[t][j]; }
+    }
+    for (iter = 0; iter < max_iter; iter++) {
+        pQp = 0;
+        for (t = 0; t < k; t++) {
+            Qp[t] = 0;
+            for (j = 0; j < k; j++) Qp[t] += Q[t][j] * p[j];
+            pQp += p[t] * Qp[t];
+        }
+        double max_error = 0;
+        for (t = 0; t < k; t++) {
+            double error = fabs(Qp[t] - pQp);
+            if (error > max_error) max_error = error;
+        }
+        if (max_error < eps) break;
+        for (t = 0; t < k; t++) {
+            double diff = (-Qp[t] + pQp) / Q[t][t];
+            p[t] += diff;
+            pQp = (pQp + diff * (diff * Q[t][t] + 2 * Qp[t])) / (1 + diff) / (1 + diff);
+            for (j = 0; j < k; j++) {
+                Qp[j] = (Qp[j] + diff * Q[t][j]) / (1 + diff);
+                p[j] /= (1 + diff);
+            }
+        }
+    }
+}
+// x: dense [W][dim] (0 = absent).  labels [W] (as doubles, what svm-predict prints), probs [W][2] in the model's label order.
+// Returns 0, or -1 when the model carries no probA / probB (svm-predict.c:211-215 then refuses -b 1).
+int orc_svm_predict_probability(void* h, const double* x, int W, int dim, double* labels, double* probs) {
+    OrcSvm* m = static_cast<OrcSvm*>(h);
+    if (!orc_svm_check_probability_model(h)) return -1;
+    std::vector<double> dec(W > 0 ? W : 1);
+    orc_svm_decision(h, x, W, dim, dec.data(), NULL);
+    for (int w = 0; w < W; w++) {
+        const double min_prob = 1e-7;
+        double pw[2][2];
+        double* rows[2] = {pw[0], pw[1]};
+        double sp = orc_sigmoid_predict(dec[w], m->probA, m->probB);
+        double mx = (sp > min_prob) ? sp : min_prob;             // libsvm's max template: (x>y)?x:y
+        pw[0][1] = (mx < 1 - min_prob) ? mx : 1 - min_prob;      // min template: (x<y)?x:y
+        pw[1][0] = 1 - pw[0][1];
+        double pe[2];
+        orc_multiclass_probability(2, rows, pe);
+        int prob_max_idx = 0;
+        if (pe[1] > pe[prob_max_idx]) prob_max_idx = 1;
+        labels[w] = m->label[prob_max_idx];
+        probs[2 * w] = pe[0]; probs[2 * w + 1] = pe[1];
+    }
+    return 0;
+}
+// the file svm-predict -b 1 writes: "labels l0 l1\n" then "%g %g %g\n" per row (svm-predict.c:57-66, :113-118).
+// Returns the text length (excluding the terminating 0), or -1 when cap is too small.
+long orc_format_probability_output(void* h, const double* labels, const double* probs, int W, char* out, size_t cap) {
+    OrcSvm* m = static_cast<OrcSvm*>(h);
+    size_t at = 0;
+    int n = snprintf(out, cap, "labels %d %d\n", m->label[0], m->label[1]);
+    if (n < 0 || (size_t)n >= cap) return -1;
+    at += n;
+    for (int w = 0; w < W; w++) {
+        n = snprintf(out + at, cap - at, "%g %g %g\n", labels[w], probs[2 * w], probs[2 * w + 1]);
+        if (n < 0 || (size_t)n >= cap - at) return -1;
+        at += n;
+    }
+    return (long)at;
+}
+// show_predicted_gps(nr_roll, tilt, svm_with_probability = true), server.cpp:803-932, on the TEXT of /tmp/output_calc_gp.txt:
+// the file is read exactly as the reference reads it -- one getline BEFORE the loop (:817-818), so the header line of the
+// -b 1 output is consumed as the first window's prediction and every window sees the previous window's line (:831-846).
+// graspseval [G][G]; top[3] = id_row_top_all, id_col_top_all, topval_gp_all.
+void orc_show_predicted_gps_prob(const char* output_text, const unsigned char* mask, int G, float* graspsgrid_out, float* graspseval, int* top) {
+    std::istringstream file_in{std::string(output_text)};
+    int id_row_top_all = -1, id_col_top_all = -1, topval_gp_all = -1000;
+    std::string line;
+    getline(file_in, line);
+    std::vector<float> graspsgrid((size_t)G * G);
+    for (int row = 0; row < G; row++)
+        for (int col = 0; col < G; col++) {
+            if (!mask[row * G + col]) {
+                graspsgrid[row * G + col] = -1;
+            } else {
+                int start = 0, end = 0, res;
+                res = atof(line.substr(0, 2).c_str());
+                start = line.find(" ", 0);
+                end = line.find(" ", start + 1);
+                if (res > 0) {  // "is gp => have to take second probability value in file (otherwise first)"
+                    start = end;
+                    end = line.find(" ", start + 1);
+                }
+                float prob = atof(line.substr(start, end).c_str());
+                graspsgrid[row * G + col] = res * prob;
+                getline(file_in, line);
+            }
+        }
+    if (graspsgrid_out) memcpy(graspsgrid_out, graspsgrid.data(), sizeof(float) * (size_t)G * G);
+    const int w1 = 1, w2 = 2, w3 = 3, w4 = 4, w5 = 55;
+    int topval_gp = -1000;
+    int id_row_top = -1, id_col_top = -1;
+#define GG(r, c) graspsgrid[(size_t)(r) * G + (c)]
+    for (int row = 0; row < G; row++) {
+        for (int col = 0; col < G; col++) {
+            if (GG(row, col) < 0) {
+                graspseval[row * G + col] = 0;
+            } else {
+                graspseval[row * G + col] =
+                    w1 * GG(row - 2, col - 2) + w2 * GG(row - 2, col - 1) + w3 * GG(row - 2, col) + w2 * GG(row - 2, col + 1) + w1 * GG(row - 2, col + 2) +
+                    w2 * GG(row - 1, col - 2) + w3 * GG(row - 1, col - 1) + w4 * GG(row - 1, col) + w3 * GG(row - 1, col + 1) + w2 * GG(row - 1, col + 2) +
+                    w2 * GG(row, col - 4) + w2 * GG(row, col - 3) + w3 * GG(row, col - 2) + w4 * GG(row, col - 1) + w5 * GG(row, col) + w4 * GG(row, col + 1) + w3 * GG(row, col + 2) + w2 * GG(row, col + 3) + w2 * GG(row, col + 4) +
+                    w2 * GG(row + 1, col - 2) + w3 * GG(row + 1, col - 1) + w4 * GG(row + 1, col) + w3 * GG(row + 1, col + 1) + w2 * GG(row + 1, col + 2) +
+                    w1 * GG(row + 2, col - 2) + w2 * GG(row + 2, col - 1) + w3 * GG(row + 2, col) + w2 * GG(row + 2, col + 1) + w1 * GG(row + 2, col + 2);
+            }
+            if (graspseval[row * G + col] > topval_gp) {  // :881-892
+                topval_gp = graspseval[row * G + col];
+                id_row_top = row;
+                id_col_top = col;
+                if (topval_gp > topval_gp_all) {
+                    id_row_top_all = id_row_top;
+                    id_col_top_all = id_col_top;
+                    topval_gp_all = topval_gp;
+                }
+            }
+        }
+    }
+#undef GG
+    int longest_topval_len = 0, cur_topval_len = 0;  // :905-932
+    for (int row = 0; row < G; row++) {
+        cur_topval_len = 0;
+        for (int col = 0; col < G; col++) {
+            if (graspseval[row * G + col] == topval_gp) {
+                cur_topval_len++;
+                if (cur_topval_len > longest_topval_len) {
+                    longest_topval_len = cur_topval_len;
+                    if (topval_gp == topval_gp_all) {
+                        id_row_top_all = row;
+                        id_col_top_all = col - cur_topval_len / 2;
+                    }
+                }
+            } else {
+                cur_topval_len = 0;
+            }
+        }
+    }
+    top[0] = id_row_top_all;
+    top[1] = id_col_top_all;
+    top[2] = topval_gp_all;
 }
 
 // =====================================================================================

@@ -183,6 +183,73 @@ class Oracle:
                                 _fp(lab))
         return dec, lab
 
+    # ---- probability estimates (svm-predict -b 1; server.cpp:831-841) ------------------------
+    def check_probability_model(self):
+        self.L.orc_svm_check_probability_model.argtypes = [C.c_void_p]
+        return bool(self.L.orc_svm_check_probability_model(C.c_void_p(self.svm)))
+
+    def svm_predict_probability(self, scaled: np.ndarray):
+        """(labels [W] float64, prob_estimates [W][2] in the model's label order)"""
+        W, dim = scaled.shape
+        lab = np.zeros(max(W, 1), np.float64)
+        pr = np.zeros((max(W, 1), 2), np.float64)
+        rc = self.L.orc_svm_predict_probability(C.c_void_p(self.svm), _fp(np.ascontiguousarray(scaled, np.float64)), W, dim, _fp(lab), _fp(pr))
+        if rc != 0:
+            raise ValueError("Model does not support probabiliy estimates")
+        return lab[:W], pr[:W]
+
+    def format_probability_output(self, labels: np.ndarray, probs: np.ndarray) -> bytes:
+        """the file svm-predict -b 1 writes for these predictions"""
+        W = len(labels)
+        cap = 64 + 96 * W
+        buf = C.create_string_buffer(cap)
+        self.L.orc_format_probability_output.restype = C.c_long
+        self.L.orc_format_probability_output.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
+        n = self.L.orc_format_probability_output(C.c_void_p(self.svm), _fp(np.ascontiguousarray(labels, np.float64)),
+                                                 _fp(np.ascontiguousarray(probs, np.float64)), W, buf, cap)
+        assert n >= 0
+        return buf.raw[:n]
+
+    def show_predicted_gps_prob(self, output_text: bytes, mask: np.ndarray):
+        """show_predicted_gps(roll, tilt, svm_with_probability=true) on the text of /tmp/output_calc_gp.txt:
+        (graspsgrid, graspseval, (row, col, topval))"""
+        G = mask.shape[0]
+        grid = np.zeros((G, G), np.float32)
+        ev = np.zeros((G, G), np.float32)
+        top = np.zeros(3, np.int32)
+        self.L.orc_show_predicted_gps_prob.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        self.L.orc_show_predicted_gps_prob(output_text, _fp(np.ascontiguousarray(mask, np.uint8)), G, _fp(grid), _fp(ev), _fp(top))
+        return grid, ev, tuple(int(t) for t in top)
+
+    def search_prob(self, xyz: np.ndarray, rq: OrcRequest, G: int = 56, roll_step_deg: int = 15, roll_max_deg: int = 190):
+        """loop_control (server.cpp:335-402) with svm_with_probability = true: per-roll stage functions, the -b 1 output text,
+        show_predicted_gps' probability branch; strict > across rolls (:953), early exit (:362-365)."""
+        R = roll_max_deg // roll_step_deg
+        if rq.roll_limit > 0:
+            R = min(R, rq.roll_limit)
+        av = self.normalize_approach(tuple(rq.approach))
+        area = (int(rq.area_len_x), int(rq.area_len_y))
+        best = (-1, -1, -1, -1, -1000)
+        out = dict(graspseval=[], graspsgrid=[], per_roll_top=[], mask=[], probs=[], text=[])
+        for roll in range(R):
+            if rq.return_only_best and best[4] >= rq.graspval_top:
+                break
+            M = self.build_transform(tuple(rq.center), av, rq.gripper_opening_width, roll, roll_step_deg)
+            integral = self.calc_intimage(self.generate_grid(xyz, M, G))
+            mask = self.pnt_in_box(integral, roll, area, roll_step_deg)
+            feats, _ = self.calc_featurevectors(integral, mask)
+            scaled = self.scale(feats) if len(feats) else np.zeros((0, 1))
+            lab, pr = self.svm_predict_probability(scaled)
+            text = self.format_probability_output(lab, pr)
+            grid, ev, top = self.show_predicted_gps_prob(text, mask)
+            if top[2] > best[4]:
+                best = (top[0], top[1], roll, 0, top[2])
+            out["graspseval"].append(ev); out["graspsgrid"].append(grid); out["per_roll_top"].append(top)
+            out["mask"].append(mask); out["probs"].append(pr); out["text"].append(text)
+        out["best"] = best
+        out["graspseval"] = np.array(out["graspseval"]); out["per_roll_top"] = np.array(out["per_roll_top"], np.int32)
+        return out
+
     def show_predicted_gps(self, labels: np.ndarray, mask: np.ndarray):
         G = mask.shape[0]
         ev = np.zeros((G, G), np.float32)
@@ -349,6 +416,20 @@ class RefServer:
                                     _fp(out["eval_pos"]), _fp(out["eval_seen"]), _fp(out["M_last"]))
         assert rc == 0
         return out
+
+    def prob_rolls(self, xyz, prob_model_path):
+        """show_predicted_gps(roll, 0, true) for every roll of the goal last run on this server (same cloud), with the reference's
+        own svm-predict -b 1 as the child process: (per_roll_top [R][3], eval_pos [R][G][G], eval_seen [R][G][G])"""
+        xyz = np.ascontiguousarray(xyz, np.float32)
+        G, R = self.G, self.R
+        top = np.full((R, 3), -1, np.int32)
+        pos = np.zeros((R, G, G), np.float32)
+        seen = np.zeros((R, G, G), np.uint8)
+        cmd = "%s -b 1 /tmp/features.txt.scale %s /tmp/output_calc_gp.txt > /dev/null" % (os.path.join(REF_DIR, "svm-predict"), prob_model_path)
+        self.L.refsrv_prob_rolls.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        rc = self.L.refsrv_prob_rolls(C.c_void_p(self.h), _fp(xyz), len(xyz), xyz.strides[0] if len(xyz) else 12, cmd.encode(), _fp(top), _fp(pos), _fp(seen))
+        assert rc == 0
+        return top, pos, seen
 
     def transform_of_roll(self, roll):
         M = np.zeros(16, np.float32)

@@ -138,6 +138,58 @@ int refsrv_run_goal(void* hv, const float* xyz, size_t n, size_t stride_bytes, c
     return 0;
 }
 
+// PROBABILITY MODE.  loop_control hard-wires svm_with_probability = false (server.cpp:383) and the true branch of
+// predict_bestgp_withsvm names a program and a model under /usr/lib/libsvm/libsvm-3.1 that are not part of the reference
+// (:795); what IS reference code and runs here unmodified is show_predicted_gps(nr_roll, tilt, true) (:831-841): for every
+// roll the members are driven as loop_control drives them, the scaling child process runs through
+// predict_bestgp_withsvm(false), then `prob_cmd` (the reference's own svm-predict -b 1 on /tmp/features.txt.scale with a
+// probability model, writing /tmp/output_calc_gp.txt -- the one substitution) and show_predicted_gps(roll, 0, true).
+// A goal must have been run on this handle with the same cloud (refsrv_run_goal): its request members are still in place.
+//   per_roll_top [R][3]; eval_pos [R][G][G] graspseval where it is > 0 (from the published markers: scale.z = 0.001 * value,
+//   :1134), else 0; eval_seen [R][G][G] 1 where a marker was published.
+int refsrv_prob_rolls(void* hv, const float* xyz, size_t n, size_t stride_bytes, const char* prob_cmd, int* per_roll_top,
+                      float* eval_pos, unsigned char* eval_seen) {
+    Handle* h = (Handle*)hv;
+    CCalc_Grasppoints* s = h->srv;
+    pcl::PointCloud<pcl::PointXYZ> cloud_cs;
+    for (size_t i = 0; i < n; i++) {
+        pcl::PointXYZ p;
+        const float* q = (const float*)((const unsigned char*)xyz + i * stride_bytes);
+        p.x = q[0]; p.y = q[1]; p.z = q[2];
+        cloud_cs.points.push_back(p);
+    }
+    cloud_cs.width = (unsigned)n;
+    std::streambuf* old = std::cout.rdbuf();
+    std::ostringstream sink;
+    std::cout.rdbuf(sink.rdbuf());
+    hafstub::Recorder& rec = hafstub::Recorder::get();
+    int rc = 0;
+    for (int roll = 0; roll < kR; roll++) {
+        s->id_row_top_overall = s->id_col_top_overall = s->nr_roll_top_overall = s->nr_tilt_top_overall = -1;
+        s->topval_gp_overall = -1000;
+        s->generate_grid(roll, 0, cloud_cs);
+        s->calc_intimage(roll, 0);
+        s->calc_featurevectors(roll, 0);
+        s->predict_bestgp_withsvm(false);        // svm-scale -r ... > /tmp/features.txt.scale (and the label-only prediction)
+        if (system(prob_cmd) != 0) rc = -1;      // svm-predict -b 1 /tmp/features.txt.scale <probability model> /tmp/output_calc_gp.txt
+        s->show_predicted_gps(roll, 0, true);
+        per_roll_top[3 * roll] = s->id_row_top_overall; per_roll_top[3 * roll + 1] = s->id_col_top_overall; per_roll_top[3 * roll + 2] = s->topval_gp_overall;
+        size_t k = 0;
+        for (int row = 0; row < HEIGHT; row++)
+            for (int col = 0; col < WIDTH; col++) {
+                const size_t at = ((size_t)roll * HEIGHT + row) * WIDTH + col;
+                eval_pos[at] = 0.0f; eval_seen[at] = 0;
+                if (s->point_inside_box_grid[roll][0][row][col] && k < rec.marker_scale_z.size()) {
+                    eval_seen[at] = 1;
+                    if (rec.marker_green[k] > 0.0) eval_pos[at] = (float)(rec.marker_scale_z[k] / 0.001);
+                    k++;
+                }
+            }
+    }
+    std::cout.rdbuf(old);
+    return rc;
+}
+
 // the transform of one roll exactly as generate_grid builds it (server.cpp:406-484), for a request already applied by a goal
 int refsrv_transform_of_roll(void* hv, int roll, float* M) {
     Handle* h = (Handle*)hv;
