@@ -65,7 +65,7 @@ EXPORTS = ["haf_create", "haf_destroy", "haf_last_error", "haf_get_info", "haf_s
            "haf_get_timing", "haf_launch_count", "haf_set_debug", "haf_search", "haf_search_batch", "haf_search_batch_packed",
            "haf_build_transform", "haf_build_transform_wcs", "haf_best_key", "haf_pack_best_records", "haf_debug_window_count", "haf_debug_windows", "haf_debug_features",
            "haf_debug_decisions", "haf_debug_tensor_inputs", "haf_debug_integral", "haf_debug_cell_indices", "haf_debug_text_roundtrip", "haf_debug_tc_probe",
-           "haf_version", "haf_svm_create", "haf_svm_destroy", "haf_svm_predict", "haf_svm_predict_probability", "haf_svm_check_probability_model", "haf_scale_minmax", "haf_scale_apply"]
+           "haf_version", "haf_pcd_decode", "haf_search_pcd", "haf_pointcloud2_to_xyz", "haf_debug_pcd_xyz", "haf_svm_create", "haf_svm_destroy", "haf_svm_predict", "haf_svm_predict_probability", "haf_svm_check_probability_model", "haf_scale_minmax", "haf_scale_apply"]
 
 _lib = None
 
@@ -116,6 +116,10 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     L.haf_debug_text_roundtrip.argtypes = [vp, vp, ci, vp, vp, ci, vp]
     L.haf_debug_tc_probe.argtypes = [vp, vp, ci]
     L.haf_version.restype = C.c_char_p
+    L.haf_pcd_decode.argtypes = [vp, vp, cs, C.POINTER(vp), C.POINTER(cs)]
+    L.haf_search_pcd.argtypes = [vp, vp, cs, C.POINTER(haf_request), ci, C.POINTER(haf_best), C.POINTER(haf_best), vp, vp, vp, vp]
+    L.haf_pointcloud2_to_xyz.argtypes = [vp, vp, cs, cs, ci, ci, ci, C.POINTER(vp)]
+    L.haf_debug_pcd_xyz.argtypes = [vp, vp, cs]
     L.haf_svm_create.argtypes = [C.POINTER(vp), C.c_char_p, ci, ci, ci, C.c_float]
     L.haf_svm_destroy.argtypes = [vp]
     L.haf_svm_destroy.restype = None
@@ -287,6 +291,42 @@ class GraspSearch:
         return best
 
     # ---- parity / inspection -----------------------------------------------------------
+    # ---- PCD / PointCloud2 ingest on the device ----
+    def pcd_decode(self, file_bytes: bytes):
+        """the bytes of a .pcd file -> (device pointer of packed xyz, n_points); the buffer belongs to the context"""
+        buf = np.frombuffer(file_bytes, np.uint8)
+        d = C.c_void_p()
+        n = C.c_size_t()
+        self._check(self.L.haf_pcd_decode(self.h, _ptr(buf), len(buf), C.byref(d), C.byref(n)))
+        return (d.value or 0), n.value
+
+    def pcd_decode_to_host(self, file_bytes: bytes) -> np.ndarray:
+        """decode on the device, then copy the packed xyz back (parity tests)"""
+        _, n = self.pcd_decode(file_bytes)
+        return self.debug_pcd_xyz(n)
+
+    def debug_pcd_xyz(self, n_points: int) -> np.ndarray:
+        out = np.zeros((n_points, 3), np.float32)
+        if n_points:
+            self._check(self.L.haf_debug_pcd_xyz(self.h, _ptr(out), n_points))
+        return out
+
+    def pointcloud2_to_xyz(self, data, n_points, point_step, off_x=0, off_y=4, off_z=8):
+        d = C.c_void_p()
+        self._check(self.L.haf_pointcloud2_to_xyz(self.h, _ptr(data), n_points, point_step, off_x, off_y, off_z, C.byref(d)))
+        return d.value or 0
+
+    def search_pcd(self, file_bytes: bytes, requests=None):
+        """haf_search_pcd: decode on the device + search; returns the same dict as search (no per-roll grids)"""
+        buf = np.frombuffer(file_bytes, np.uint8)
+        reqs = requests or [make_request()]
+        arr = (haf_request * len(reqs))(*reqs)
+        best = haf_best()
+        per = (haf_best * len(reqs))()
+        top = np.zeros((len(reqs), self.R, 3), np.int32)
+        self._check(self.L.haf_search_pcd(self.h, _ptr(buf), len(buf), arr, len(reqs), C.byref(best), per, None, None, None, _ptr(top)))
+        return {"best": best, "best_per_request": list(per), "per_roll_top": top}
+
     def debug_windows(self):
         W = self._check(self.L.haf_debug_window_count(self.h))
         a = np.zeros((max(W, 1), 2), np.int32)

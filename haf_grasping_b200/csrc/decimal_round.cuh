@@ -298,6 +298,112 @@ HAFDEC_HD double round_sig_to_double(double a, bool* unsupported) {
     return a;
 }
 
+// ------------------------------------------------------------------------------------------
+// decimal -> binary32, correctly rounded (what strtof / `istream >> float` return): the ASCII PCD reader.
+// value = M * 10^q (M != 0; sticky: non-zero digits were dropped behind M's 19).  Slow path: exact big-integer
+// division, round half-even at 24 bits (fewer below 2^-126: subnormals), overflow -> +inf.
+// ------------------------------------------------------------------------------------------
+HAFDEC_HD_NOINLINE bool decimal_to_float_big(uint64_t M, int q, bool sticky_in, float* out) {
+    if (q > 60) { *out = INFINITY; return true; }            // M >= 1: >= 1e61 > FLT_MAX
+    if (q < -90) { *out = 0.0f; return true; }               // M < 2^64 ~ 1.8e19: < 1.8e-71, far below 2^-150
+    Big num, den;
+    big_set(num, M);
+    big_set(den, 1);
+    int e2 = q;  // value = (num / den) * 2^e2
+    if (q >= 0) big_mul_pow5(num, q); else big_mul_pow5(den, -q);
+    if (num.overflow || den.overflow) return false;
+    int t = big_bitlen(den) - big_bitlen(num) + 57;   // integer quotient of 57..58 bits
+    if (t > 0) { big_shl(num, t); e2 -= t; }
+    else if (t < 0) { big_shl(den, -t); e2 += -t; }
+    if (num.overflow || den.overflow) return false;
+    const uint64_t Q = big_divrem_small_quot(num, den, 58);
+    const bool sticky = sticky_in || !big_is_zero(num);
+    int ql = 0;
+    { uint64_t v = Q; while (v) { ql++; v >>= 1; } }
+    const int E2 = e2 + ql - 1;                       // value in [2^E2, 2^(E2+1))
+    if (E2 > 128) { *out = INFINITY; return true; }
+    int drop = ql - 24;                               // normal: 24 significant bits
+    if (E2 < -126) drop = -149 - e2;                  // subnormal: nothing below 2^-149
+    if (drop >= 63) { *out = 0.0f; return true; }     // below 2^-150 by a wide margin
+    if (drop < 1) return false;
+    uint64_t keep = Q >> drop;
+    const uint64_t rem = Q & ((1ull << drop) - 1), half = 1ull << (drop - 1);
+    if (rem > half || (rem == half && (sticky || (keep & 1)))) keep++;
+    *out = ldexpf((float)keep, e2 + drop);            // keep <= 2^24: exact; ldexpf: exact or +inf
+    return true;
+}
+// Fast path: M < 2^53 and |q| <= 22 -> v = M * 10^q or M / 10^-q is ONE correctly rounded double operation on exact
+// operands (Clinger); (float)v is then correct unless v sits exactly on the midpoint of two floats (the double rounding
+// may have moved the value there) or in the subnormal / overflow range: those go to the exact path.
+HAFDEC_HD float decimal_to_float(uint64_t M, int q, bool sticky, bool* unsupported) {
+    if (M == 0) return 0.0f;
+    if (!sticky && M < (1ull << 53) && q >= -22 && q <= 22) {
+        const double d = (double)M;
+        const double v = q >= 0 ? mul_rn(d, pow10_exact(q)) : div_rn(d, pow10_exact(-q));
+        const uint64_t b = dbl_bits(v);
+        const int be = (int)((b >> 52) & 0x7FF) - 1023;
+        if (be >= -126 && be <= 126 && (b & 0x1FFFFFFFull) != 0x10000000ull) return (float)v;
+    }
+    float f;
+    if (decimal_to_float_big(M, q, sticky, &f)) return f;
+    if (unsupported) *unsupported = true;
+    return (float)((double)M * pow(10.0, (double)q));
+}
+// One token of an ASCII PCD record as pcl::PCDReader reads a FLOAT32 field (PCL io/pcd_io.h copyStringValue<float>: "nan" ->
+// quiet NaN, else `istringstream >> float`, else (float)atof): [+-] digits [. digits] [e|E [+-] digits] of the longest valid
+// prefix, correctly rounded; "inf" / "infinity" / "nan" in any case; anything else 0.  p .. end delimit the token.
+HAFDEC_HD float parse_float_token(const unsigned char* p, const unsigned char* end, bool* unsupported) {
+    bool neg = false;
+    if (p < end && (*p == '+' || *p == '-')) { neg = *p == '-'; p++; }
+    if (end - p >= 3) {
+        const unsigned char a = p[0] | 0x20, b = p[1] | 0x20, c = p[2] | 0x20;
+        if (a == 'n' && b == 'a' && c == 'n') return neg ? -NAN : NAN;
+        if (a == 'i' && b == 'n' && c == 'f') return neg ? -INFINITY : INFINITY;
+    }
+    uint64_t M = 0;
+    int nd = 0, q = 0;          // significant digits taken into M (<= 19), decimal exponent of M's last digit
+    bool any = false, sticky = false, seen_nonzero = false;
+    for (; p < end && *p >= '0' && *p <= '9'; p++) {
+        any = true;
+        const int dg = *p - '0';
+        if (dg) seen_nonzero = true;
+        if (!seen_nonzero) continue;
+        if (nd < 19) { M = M * 10 + (uint64_t)dg; nd++; }
+        else { q++; if (dg) sticky = true; }
+    }
+    if (p < end && *p == '.') {
+        p++;
+        for (; p < end && *p >= '0' && *p <= '9'; p++) {
+            any = true;
+            const int dg = *p - '0';
+            if (dg) seen_nonzero = true;
+            if (!seen_nonzero) { q--; continue; }
+            if (nd < 19) { M = M * 10 + (uint64_t)dg; nd++; q--; }
+            else if (dg) sticky = true;
+        }
+    }
+    if (!any) return 0.0f;   // no conversion: atof gives +0
+    if (p < end && (*p == 'e' || *p == 'E')) {
+        const unsigned char* s = p + 1;
+        bool eneg = false;
+        if (s < end && (*s == '+' || *s == '-')) { eneg = *s == '-'; s++; }
+        if (s < end && *s >= '0' && *s <= '9') {
+            int ex = 0;
+            for (; s < end && *s >= '0' && *s <= '9'; s++) if (ex < 100000) ex = ex * 10 + (*s - '0');
+            q += eneg ? -ex : ex;
+        }
+    }
+    float f = decimal_to_float(M, q, sticky, unsupported);
+    if (sticky) {
+        // more than 19 significant digits: the value lies in (M, M + 1) * 10^q.  Rounding is monotonic, so when both ends give
+        // the same float that float is the answer; otherwise a rounding boundary lies within 1e-19 (relative) of the value
+        // and the dropped digits would decide: reported, not guessed (PCL writes <= 9 significant digits)
+        const float f2 = decimal_to_float(M + 1, q, false, unsupported);
+        if (!(f == f2) && unsupported) *unsupported = true;
+    }
+    return neg ? -f : f;
+}
+
 // strtod(sprintf("%.4g", (double)f))
 HAFDEC_HD double text4(float f, bool* unsupported = nullptr) {
     double x = (double)f;

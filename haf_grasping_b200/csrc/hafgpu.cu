@@ -13,7 +13,9 @@
 
 #include "../../include/hafgpu.h"
 #include "haf_host.hpp"
+#include "host/pcd_io.hpp"
 #include "kernels.cuh"
+#include "pcd_ingest.cuh"
 #include "svm_tc.cuh"
 
 using namespace hafk;
@@ -153,6 +155,12 @@ struct haf_ctx {
     int prob_res[2] = {0, 0};        // (int)atof(first two characters of "%g"(label)): server.cpp:833
     float prob_header_val = 0.0f;    // the "labels l0 l1" line parsed as a prediction: 0 * (float)l0 (server.cpp:817, :833-841)
     DevBuf<float> d_probgrid;        // [Uc][G][G] graspsgrid as floats (probability mode)
+
+    // PCD / PointCloud2 ingest on the device (pcd_ingest.cuh)
+    DevBuf<unsigned char> d_pcd_raw, d_pcd_blob;
+    DevBuf<float> d_pcd_xyz;
+    DevBuf<unsigned> d_pcd_tiles;
+    DevBuf<unsigned long long> d_pcd_words;   // [0] record count, [1] LZF stream descriptor (4 words), [8] status / flags (ints)
 
     // libsvm front end (haf_svm_*): inputs given by the caller
     bool svm_only = false;
@@ -605,7 +613,7 @@ static int create_impl(haf_ctx** out, const haf_config* cfg, bool svm_only, int 
         CREATE_TRY(cudaMemcpy(ctx->d_dimfeat.p, joined.data(), joined.size() * sizeof(DimFeat), cudaMemcpyHostToDevice));
         CREATE_TRY(cudaFuncSetAttribute(haftc::svm_rbf_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, haftc::SMEM2_BYTES + haftc::TAB_SMEM_MAX * 4));
         CREATE_TRY(cudaFuncSetAttribute(haftc::svm_rbf_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, haftc::TC3_SMEM_LIMIT));
-        CREATE_TRY(cudaFuncSetAttribute(features_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * HAF_FT_WT * (HAF_FT_KPASS + 1) * 4 + HAF_FT_ROWS * (G + 1 + 31) * 4 + 16 + HAF_FT_KPASS * 96));
+        CREATE_TRY(cudaFuncSetAttribute(features_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ft_smem_layout(G, 2)));
         // 4 CTAs x ~49 KB: ask for just that much shared memory so that the rest of the SM's 256 KB stays L1 (the corner-offset table)
         CREATE_TRY(cudaFuncSetAttribute(features_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 90));
     }
@@ -881,7 +889,7 @@ extern "C" void haf_destroy(haf_ctx* ctx) {
     ctx->d_integral.release(); ctx->d_rowscan.release(); ctx->d_mask.release(); ctx->d_labelgrid.release(); ctx->d_evals.release();
     ctx->d_unit_top.release(); ctx->d_unit_run.release(); ctx->d_unit_windows.release(); ctx->d_win.release(); ctx->d_X.release();
     ctx->d_xn.release(); ctx->d_dec.release(); ctx->d_guardflag.release(); ctx->d_guardlist.release(); ctx->d_kscratch.release();
-    ctx->d_xdense.release(); ctx->d_labels.release(); ctx->d_probs.release(); ctx->d_probgrid.release(); ctx->d_csr_ptr.release(); ctx->d_csr_idx.release(); ctx->d_csr_val.release();
+    ctx->d_xdense.release(); ctx->d_labels.release(); ctx->d_probs.release(); ctx->d_probgrid.release(); ctx->d_pcd_raw.release(); ctx->d_pcd_blob.release(); ctx->d_pcd_xyz.release(); ctx->d_pcd_tiles.release(); ctx->d_pcd_words.release(); ctx->d_csr_ptr.release(); ctx->d_csr_idx.release(); ctx->d_csr_val.release();
     ctx->d_svn64.release(); ctx->d_Xg.release(); ctx->d_g2accum.release(); ctx->d_g2tickets.release(); ctx->d_guardlist2.release();
     ctx->d_SVh.release(); ctx->d_SVl.release(); ctx->d_Xh.release(); ctx->d_Xl.release(); ctx->d_svcoef.release(); ctx->d_dec_tc.release(); ctx->d_asum.release(); ctx->d_dimfeat.release(); ctx->d_round4.release();
     ctx->d_params.release(); ctx->d_counters.release(); ctx->h_stage.release(); ctx->h_results.release(); ctx->h_per_roll_top.release(); ctx->h_counters.release(); ctx->h_unit_windows.release();
@@ -960,9 +968,7 @@ bool is_device_ptr(const void* p) {
 
 }  // namespace
 
-static size_t ft_smem_bytes(const haf_ctx* ctx) {
-    return (size_t)32 * HAF_FT_WT * (HAF_FT_KPASS + 1) * 4 + (size_t)HAF_FT_ROWS * (ctx->G + 1 + 31) * 4 + 16 + (size_t)HAF_FT_KPASS * 96;
-}
+static size_t ft_smem_bytes(const haf_ctx* ctx) { return ft_smem_layout(ctx->G, ctx->tc_passes >= 3 ? 2 : 1); }
 static size_t exact_smem_bytes(const haf_ctx* ctx) { return (size_t)HAF_EXACT_WB * ctx->Dsv * sizeof(double); }
 // launches the two phases of the FP64 exact-order path on stream st
 static int launch_exact(haf_ctx* ctx, ExactArgs a, cudaStream_t st, size_t max_windows) {
@@ -1002,8 +1008,9 @@ static int launch_guard(haf_ctx* ctx, unsigned* cnt, int G, int ubase, cudaStrea
     const bool few = Wcap < 65536;   // a single goal: a handful of guard windows -> spread the support vectors over more CTAs
     guard_inputs_kernel<<<few ? 32 : ctx->sm_count * 4, 256, 0, st>>>(a, q);
     LAUNCHED(ctx);
-    if (few) guard_fma_kernel<1><<<dim3(16, (unsigned)((ctx->Spad + 255) / 256)), 256, smem, st>>>(a, q);
-    else guard_fma_kernel<2><<<dim3((unsigned)ctx->sm_count, (unsigned)((ctx->Spad + 511) / 512)), 256, smem, st>>>(a, q);
+    // one CTA per SM walks (window group, SV slice) items; a single goal's handful of windows: slices of 256 SVs over more CTAs
+    if (few) guard_fma_kernel<1><<<(unsigned)ctx->sm_count, 256, smem, st>>>(a, q, (ctx->Spad + 255) / 256);
+    else guard_fma_kernel<2><<<(unsigned)ctx->sm_count, 256, smem, st>>>(a, q, (ctx->Spad + 511) / 512);
     LAUNCHED(ctx);
     return launch_exact(ctx, make_exact_args(ctx, ctx->d_guardlist2.p, cnt + 6, cnt, G, ubase), st, Wcap);
 }
@@ -1614,6 +1621,141 @@ extern "C" int haf_search_batch(haf_ctx* ctx, const float* const* clouds, const 
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_xyz.p + off[c] * 12, clouds[c], n_points[c] * 12, cudaMemcpyDefault, ctx->stream));
     }
     return haf_search_batch_packed(ctx, reinterpret_cast<const float*>(ctx->d_xyz.p), off.data(), n_clouds, req, best_per_cloud);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// PCD / PointCloud2 ingest on the device (kernels and the PCL semantics they restate: pcd_ingest.cuh)
+// ------------------------------------------------------------------------------------------------------------
+extern "C" int haf_pointcloud2_to_xyz(haf_ctx* ctx, const void* data, size_t n_points, size_t point_step, int off_x, int off_y, int off_z,
+                                      const float** d_xyz) {
+    if (!ctx || !d_xyz) return HAF_ERR_ARG;
+    *d_xyz = nullptr;
+    if (n_points == 0) return HAF_OK;
+    if (!data || point_step < 4 || off_x < 0 || off_y < 0 || off_z < 0 || (size_t)std::max(off_x, std::max(off_y, off_z)) + 4 > point_step)
+        return ctx->fail(HAF_ERR_ARG, "haf_pointcloud2_to_xyz: x / y / z offsets must lie inside point_step");
+    haf_ctx* c0 = ctx;
+    CUDA_TRY(c0, cudaSetDevice(c0->device));
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(data);
+    if (!is_device_ptr(data)) {
+        ENSURE(c0, c0->d_pcd_raw, n_points * point_step + 16);
+        CUDA_TRY(c0, cudaMemcpyAsync(c0->d_pcd_raw.p, data, n_points * point_step, cudaMemcpyHostToDevice, c0->stream));
+        src = c0->d_pcd_raw.p;
+    }
+    ENSURE(c0, c0->d_pcd_xyz, n_points * 3);
+    hafpcdk::gather_records_kernel<<<(unsigned)std::min<size_t>((n_points + 255) / 256, 148 * 16), 256, 0, c0->stream>>>(src, n_points, point_step, off_x, off_y, off_z,
+                                                                                                                 c0->d_pcd_xyz.p);
+    LAUNCHED(c0);
+    *d_xyz = c0->d_pcd_xyz.p;
+    return HAF_OK;
+}
+
+extern "C" int haf_pcd_decode(haf_ctx* ctx, const void* file_bytes, size_t n_bytes, const float** d_xyz, size_t* n_points) {
+    if (!ctx || !d_xyz || !n_points) return HAF_ERR_ARG;
+    *d_xyz = nullptr; *n_points = 0;
+    if (!file_bytes || n_bytes == 0) return ctx->fail(HAF_ERR_ARG, "haf_pcd_decode: empty buffer");
+    const unsigned char* raw = reinterpret_cast<const unsigned char*>(file_bytes);
+    hafpcd::PcdHeader hd;
+    std::string herr;
+    if (!hafpcd::parse_pcd_header(raw, n_bytes, hd, &herr)) return ctx->fail(HAF_ERR_IO, "%s", herr.c_str());
+    for (int a = 0; a < 3; a++)
+        if (hd.types[hd.idx[a]] != "F" || hd.sizes[hd.idx[a]] != 4) return ctx->fail(HAF_ERR_UNSUPPORTED, "PCD: x / y / z must be float32 fields");
+    const size_t npts = (size_t)hd.npts;
+    if (npts == 0) return HAF_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const unsigned char* data = raw + hd.data_begin;
+    const size_t dn = n_bytes - hd.data_begin;
+    ENSURE(ctx, ctx->d_pcd_xyz, npts * 3);
+    ENSURE(ctx, ctx->d_pcd_words, 16);
+    ENSURE(ctx, ctx->h_stage, 256);
+    const unsigned grid_pts = (unsigned)std::min<size_t>((npts + 255) / 256, 148 * 16);
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_pcd_words.p, 0, 16 * 8, st));
+    int* d_flags = reinterpret_cast<int*>(ctx->d_pcd_words.p + 8);
+    unsigned long long* h_words = reinterpret_cast<unsigned long long*>(ctx->h_stage.p);
+    if (hd.data_kind == "ascii") {
+        if (dn == 0) return ctx->fail(HAF_ERR_IO, "fewer records than POINTS in the PCD data");
+        std::vector<int> tokoff(hd.fields.size() + 1, 0);
+        for (size_t k = 0; k < hd.fields.size(); k++) tokoff[k + 1] = tokoff[k] + hd.counts[k];
+        ENSURE(ctx, ctx->d_pcd_raw, dn + 16);
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_pcd_raw.p, data, dn, cudaMemcpyHostToDevice, st));
+        const size_t tile_bytes = (size_t)HAF_PCD_TILE_THREADS * HAF_PCD_BYTES_PER_THREAD;
+        const size_t n_tiles = (dn + tile_bytes - 1) / tile_bytes;
+        if (n_tiles > 0x7fffffffu) return ctx->fail(HAF_ERR_UNSUPPORTED, "ASCII PCD too large");
+        ENSURE(ctx, ctx->d_pcd_tiles, n_tiles);
+        hafpcdk::ascii_count_kernel<<<(unsigned)n_tiles, HAF_PCD_TILE_THREADS, 0, st>>>(ctx->d_pcd_raw.p, dn, ctx->d_pcd_tiles.p);
+        LAUNCHED(ctx);
+        hafpcdk::ascii_scan_kernel<<<1, 1024, 0, st>>>(ctx->d_pcd_tiles.p, (unsigned)n_tiles, ctx->d_pcd_words.p);
+        LAUNCHED(ctx);
+        hafpcdk::ascii_parse_kernel<<<(unsigned)n_tiles, HAF_PCD_TILE_THREADS, 0, st>>>(ctx->d_pcd_raw.p, dn, ctx->d_pcd_tiles.p, (unsigned long long)npts,
+                                                                                       tokoff[hd.idx[0]], tokoff[hd.idx[1]], tokoff[hd.idx[2]], ctx->d_pcd_xyz.p, d_flags);
+        LAUNCHED(ctx);
+        CUDA_TRY(ctx, cudaMemcpyAsync(h_words, ctx->d_pcd_words.p, 16 * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        const int* hf = reinterpret_cast<const int*>(h_words + 8);
+        if (h_words[0] < npts) return ctx->fail(HAF_ERR_IO, "fewer records than POINTS in the PCD data (%llu of %zu)", h_words[0], npts);
+        if (hf[0]) return ctx->fail(HAF_ERR_IO, "short ASCII record in the PCD data");
+        if (hf[1]) return ctx->fail(HAF_ERR_UNSUPPORTED, "an ASCII token has more than 19 significant digits and lies next to a float rounding boundary");
+    } else if (hd.data_kind == "binary") {
+        size_t rec_bytes = 0;
+        std::vector<size_t> foff(hd.fields.size());
+        for (size_t k = 0; k < hd.fields.size(); k++) { foff[k] = rec_bytes; rec_bytes += (size_t)hd.sizes[k] * hd.counts[k]; }
+        if (rec_bytes * npts > dn) return ctx->fail(HAF_ERR_IO, "binary PCD truncated");
+        ENSURE(ctx, ctx->d_pcd_raw, rec_bytes * npts + 16);
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_pcd_raw.p, data, rec_bytes * npts, cudaMemcpyHostToDevice, st));
+        hafpcdk::gather_records_kernel<<<grid_pts, 256, 0, st>>>(ctx->d_pcd_raw.p, npts, rec_bytes, (int)foff[hd.idx[0]], (int)foff[hd.idx[1]], (int)foff[hd.idx[2]],
+                                                                 ctx->d_pcd_xyz.p);
+        LAUNCHED(ctx);
+    } else if (hd.data_kind == "binary_compressed") {
+        if (dn < 8) return ctx->fail(HAF_ERR_IO, "compressed PCD truncated");
+        uint32_t comp, uncomp;
+        memcpy(&comp, data, 4);
+        memcpy(&uncomp, data + 4, 4);
+        if ((size_t)comp + 8 > dn) return ctx->fail(HAF_ERR_IO, "compressed PCD truncated");
+        std::vector<size_t> foff(hd.fields.size());
+        size_t off = 0;
+        for (size_t k = 0; k < hd.fields.size(); k++) { foff[k] = off; off += npts * (size_t)hd.sizes[k] * hd.counts[k]; }
+        for (int a = 0; a < 3; a++)
+            if (foff[hd.idx[a]] + (npts - 1) * 4 * (size_t)hd.counts[hd.idx[a]] + 4 > uncomp) return ctx->fail(HAF_ERR_IO, "compressed PCD: the stream is shorter than the header's fields");
+        ENSURE(ctx, ctx->d_pcd_raw, (size_t)comp + 16);
+        ENSURE(ctx, ctx->d_pcd_blob, (size_t)uncomp + 16);
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_pcd_raw.p, data + 8, comp, cudaMemcpyHostToDevice, st));
+        hafpcdk::LzfStream ls;
+        ls.in = ctx->d_pcd_raw.p; ls.in_len = comp; ls.out = ctx->d_pcd_blob.p; ls.out_len = uncomp;
+        CUDA_TRY(ctx, cudaStreamSynchronize(st));   // h_stage may still feed an earlier call's copy
+        memcpy(ctx->h_stage.p + 128, &ls, sizeof ls);
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_pcd_words.p + 1, ctx->h_stage.p + 128, sizeof ls, cudaMemcpyHostToDevice, st));
+        hafpcdk::lzf_decompress_kernel<<<1, 32, 0, st>>>(reinterpret_cast<const hafpcdk::LzfStream*>(ctx->d_pcd_words.p + 1), d_flags);
+        LAUNCHED(ctx);
+        hafpcdk::gather_soa_kernel<<<grid_pts, 256, 0, st>>>(ctx->d_pcd_blob.p, npts, foff[hd.idx[0]], foff[hd.idx[1]], foff[hd.idx[2]], 4 * hd.counts[hd.idx[0]],
+                                                             4 * hd.counts[hd.idx[1]], 4 * hd.counts[hd.idx[2]], ctx->d_pcd_xyz.p);
+        LAUNCHED(ctx);
+        CUDA_TRY(ctx, cudaMemcpyAsync(h_words, ctx->d_pcd_words.p, 16 * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        if (reinterpret_cast<const int*>(h_words + 8)[0]) return ctx->fail(HAF_ERR_IO, "corrupt LZF stream in the PCD data");
+    } else {
+        return ctx->fail(HAF_ERR_UNSUPPORTED, "unsupported PCD DATA kind '%s'", hd.data_kind.c_str());
+    }
+    *d_xyz = ctx->d_pcd_xyz.p;
+    *n_points = npts;
+    return HAF_OK;
+}
+
+extern "C" int haf_debug_pcd_xyz(haf_ctx* ctx, float* xyz_host, size_t n_points) {
+    if (!ctx || !xyz_host) return HAF_ERR_ARG;
+    if (n_points * 3 > ctx->d_pcd_xyz.cap) return ctx->fail(HAF_ERR_ARG, "haf_debug_pcd_xyz: more points than the last ingest produced");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaMemcpyAsync(xyz_host, ctx->d_pcd_xyz.p, n_points * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return HAF_OK;
+}
+
+extern "C" int haf_search_pcd(haf_ctx* ctx, const void* file_bytes, size_t n_bytes, const haf_request* reqs, int n_requests, haf_best* best,
+                              haf_best* best_per_request, float* graspseval, unsigned char* mask, float* heights, int* per_roll_top) {
+    const float* d_xyz = nullptr;
+    size_t n = 0;
+    const int rc = haf_pcd_decode(ctx, file_bytes, n_bytes, &d_xyz, &n);
+    if (rc != HAF_OK) return rc;
+    return haf_search(ctx, d_xyz, n, 12, reqs, n_requests, best, best_per_request, graspseval, mask, heights, per_roll_top);
 }
 
 // ------------------------------------------------------------------------------------------------------------

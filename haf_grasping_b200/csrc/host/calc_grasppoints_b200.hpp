@@ -81,6 +81,17 @@ public:
     CCalc_Grasppoints_B200(const CCalc_Grasppoints_B200&) = delete;
     CCalc_Grasppoints_B200& operator=(const CCalc_Grasppoints_B200&) = delete;
 
+    // The client's open_pcd_and_trig_get_grasp_cb (src/calc_grasppoints_action_client.cpp:137-157: pcl::io::loadPCDFile, toROSMsg)
+    // followed by the server's pcl::fromROSMsg (:313-316), as ONE device-side ingest: the file's bytes are decoded by kernels
+    // (haf_pcd_decode) and the goal runs on the decoded cloud without the points ever existing in host memory.
+    size_t open_pcd_and_trig_get_grasp_cb(const GraspInput& goal, const void* file_bytes, size_t n_bytes) {
+        const float* d_xyz = NULL;
+        size_t n = 0;
+        if (haf_pcd_decode(ctx_, file_bytes, n_bytes, &d_xyz, &n) != HAF_OK) throw std::runtime_error(std::string("hafgpu: ") + haf_last_error(ctx_));
+        read_pc_cb(goal, d_xyz, n, 12);
+        return n;
+    }
+
     // read_pc_cb (:250-329): goal -> members (the tf transform of the cloud is the caller's business), then loop_control
     void read_pc_cb(const GraspInput& goal, const float* xyz, size_t n_points, size_t stride_bytes) {
         graspsearchcenter = goal.grasp_area_center;                              // :258-260

@@ -35,6 +35,47 @@ inline bool lzf_decompress(const unsigned char* ip, size_t in_len, unsigned char
     return o == out_len;
 }
 
+// The text header of a PCD v0.7 file, up to and including its DATA line (what pcl::PCDReader::readHeader takes from it for
+// an xyz cloud).  Also used by the device ingest (csrc/pcd_ingest.cuh, haf_pcd_decode): the header stays host-side text.
+struct PcdHeader {
+    std::vector<std::string> fields, types;
+    std::vector<int> sizes, counts;
+    long npts = -1, width = 0, height = 1;
+    std::string data_kind;     // "ascii" | "binary" | "binary_compressed"
+    size_t data_begin = 0;     // offset of the first byte after the DATA line
+    int idx[3] = {-1, -1, -1}; // field numbers of x, y, z
+};
+inline bool parse_pcd_header(const unsigned char* raw, size_t n_bytes, PcdHeader& h, std::string* err) {
+    size_t pos = 0;
+    while (pos < n_bytes) {
+        size_t nl = pos;
+        while (nl < n_bytes && raw[nl] != '\n') nl++;
+        std::string line((const char*)&raw[pos], nl - pos);
+        pos = nl + 1;
+        if (line.empty() || line[0] == '#') continue;
+        std::istringstream ss(line);
+        std::string key;
+        ss >> key;
+        std::string tok;
+        if (key == "FIELDS") while (ss >> tok) h.fields.push_back(tok);
+        else if (key == "SIZE") while (ss >> tok) h.sizes.push_back(atoi(tok.c_str()));
+        else if (key == "TYPE") while (ss >> tok) h.types.push_back(tok);
+        else if (key == "COUNT") while (ss >> tok) h.counts.push_back(atoi(tok.c_str()));
+        else if (key == "WIDTH") ss >> h.width;
+        else if (key == "HEIGHT") ss >> h.height;
+        else if (key == "POINTS") ss >> h.npts;
+        else if (key == "DATA") { ss >> h.data_kind; break; }
+    }
+    h.data_begin = pos < n_bytes ? pos : n_bytes;
+    if (h.npts < 0) h.npts = h.width * h.height;
+    if (h.counts.empty()) h.counts.assign(h.fields.size(), 1);
+    for (size_t k = 0; k < h.fields.size(); k++) { if (h.fields[k] == "x") h.idx[0] = (int)k; if (h.fields[k] == "y") h.idx[1] = (int)k; if (h.fields[k] == "z") h.idx[2] = (int)k; }
+    if (h.idx[0] < 0 || h.idx[1] < 0 || h.idx[2] < 0 || h.sizes.size() != h.fields.size() || h.types.size() != h.fields.size() ||
+        h.counts.size() != h.fields.size()) { if (err) *err = "PCD header lacks x/y/z fields"; return false; }
+    if (h.npts < 0) { if (err) *err = "PCD header: negative point count"; return false; }
+    return true;
+}
+
 // xyz: packed x,y,z floats.  Returns false with *err set on failure.
 inline bool read_pcd(const std::string& path, std::vector<float>& xyz, std::string* err) {
     FILE* fp = fopen(path.c_str(), "rb");
@@ -44,37 +85,15 @@ inline bool read_pcd(const std::string& path, std::vector<float>& xyz, std::stri
     size_t n;
     while ((n = fread(buf, 1, sizeof buf, fp)) > 0) raw.insert(raw.end(), buf, buf + n);
     fclose(fp);
-    size_t pos = 0;
-    std::vector<std::string> fields, types;
-    std::vector<int> sizes, counts;
-    long npts = -1, width = 0, height = 1;
-    std::string data_kind;
-    while (pos < raw.size()) {
-        size_t nl = pos;
-        while (nl < raw.size() && raw[nl] != '\n') nl++;
-        std::string line((const char*)&raw[pos], nl - pos);
-        pos = nl + 1;
-        if (line.empty() || line[0] == '#') continue;
-        std::istringstream ss(line);
-        std::string key;
-        ss >> key;
-        std::string tok;
-        if (key == "FIELDS") while (ss >> tok) fields.push_back(tok);
-        else if (key == "SIZE") while (ss >> tok) sizes.push_back(atoi(tok.c_str()));
-        else if (key == "TYPE") while (ss >> tok) types.push_back(tok);
-        else if (key == "COUNT") while (ss >> tok) counts.push_back(atoi(tok.c_str()));
-        else if (key == "WIDTH") ss >> width;
-        else if (key == "HEIGHT") ss >> height;
-        else if (key == "POINTS") ss >> npts;
-        else if (key == "DATA") { ss >> data_kind; break; }
-    }
-    if (npts < 0) npts = width * height;
-    if (counts.empty()) counts.assign(fields.size(), 1);
-    int ix = -1, iy = -1, iz = -1;
-    for (size_t k = 0; k < fields.size(); k++) { if (fields[k] == "x") ix = (int)k; if (fields[k] == "y") iy = (int)k; if (fields[k] == "z") iz = (int)k; }
-    if (ix < 0 || iy < 0 || iz < 0 || sizes.size() != fields.size() || types.size() != fields.size()) { if (err) *err = "PCD header lacks x/y/z fields"; return false; }
+    PcdHeader hd;
+    if (!parse_pcd_header(raw.data(), raw.size(), hd, err)) return false;
+    size_t pos = hd.data_begin;
+    const std::vector<std::string>&fields = hd.fields, &types = hd.types;
+    const std::vector<int>&sizes = hd.sizes, &counts = hd.counts;
+    const long npts = hd.npts;
+    const std::string& data_kind = hd.data_kind;
     xyz.assign((size_t)npts * 3, 0.0f);
-    const int idx[3] = {ix, iy, iz};
+    const int idx[3] = {hd.idx[0], hd.idx[1], hd.idx[2]};
     if (data_kind == "ascii") {
         std::vector<int> tokoff(fields.size() + 1, 0);
         for (size_t k = 0; k < fields.size(); k++) tokoff[k + 1] = tokoff[k] + counts[k];

@@ -678,7 +678,11 @@ __device__ __forceinline__ void write_aug_columns(__half* __restrict__ X, size_t
 }
 
 #define HAF_FT_WT 2
-#define HAF_FT_KPASS 96   // dimensions per pass of the shared-memory tile: 192 B = 6 whole sectors of a row of Xh / Xl
+#define HAF_FT_KPASS 128  // dimensions per pass of the shared-memory tile: 256 B = two whole k-blocks of a row of Xh / Xl
+// dynamic shared memory of features_tc_kernel: fp16 tile(s) [tiles][64 windows][KPASS] + staged image rows + the pass's table records
+__host__ __device__ constexpr size_t ft_smem_layout(int G, int tiles) {
+    return (size_t)tiles * 32 * HAF_FT_WT * HAF_FT_KPASS * 2 + (size_t)HAF_FT_ROWS * (G + 1 + 31) * 4 + 16 + (size_t)HAF_FT_KPASS * 96;
+}
 __global__ void __launch_bounds__(256, 4) features_tc_kernel(const float* __restrict__ integral, const int2* __restrict__ win,
                                                              const unsigned* __restrict__ win_count, int G, int unit_base,
                                                              const DimFeat* __restrict__ table, int D, int Krow, float lower,
@@ -686,16 +690,23 @@ __global__ void __launch_bounds__(256, 4) features_tc_kernel(const float* __rest
                                                              __half* __restrict__ Xh, __half* __restrict__ Xl /*NULL: hi only*/, float* __restrict__ xn,
                                                              int aug0 /*first of the six extra operand columns (svm_tc.cuh)*/, int KB /*k-blocks of the tiled layout*/) {
     constexpr int WT = HAF_FT_WT, NW = 32 * WT;
-    extern __shared__ uint32_t s_words[];  // tile [NW][KPASS+1] of (hi | lo << 16); then float s_int[ROWS][ld .. ld + 31]
+    // TILE.  fp16 values [window][KPASS dims] = 256-byte rows of sixteen 16-byte chunks, swizzled so that BOTH sides are free of
+    // bank conflicts: element (w, d) sits in chunk (d >> 3) ^ (w & 7), word ((d & 7) >> 1) ^ ((w >> 3) & 3) of its row.  A compute
+    // warp stores one dimension of 32 windows per instruction (32 different (chunk & 7, word) pairs = 32 banks); the write-out
+    // reads whole chunks with LDS.128 (16 lanes = the 16 chunks of a row, XOR-permuted = all banks) and writes them with
+    // STG.128: 8 dimensions per instruction.  Round 1 kept (hi | lo << 16) words and wrote 2 dimensions per STG after two LDS
+    // and a PRMT, with 64-bit kt_off arithmetic per word: a quarter of the kernel's instructions (ncu r2, source view).
+    extern __shared__ __align__(16) uint32_t s_words[];  // tile(s) [1 or 2][NW][KPASS] fp16; then float s_int[ROWS][ld .. ld + 31]
+    const int tiles = Xl ? 2 : 1;
+    constexpr int TILE_WORDS = NW * HAF_FT_KPASS / 2;
     const unsigned W = *win_count;
     const unsigned w0 = blockIdx.x * NW;
     if (w0 >= W) return;
     const int lane = threadIdx.x & 31;
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // provably warp-uniform for the compiler
     const int ld = G + 1;
-    constexpr int rs = HAF_FT_KPASS + 1;
-    float* s_int = reinterpret_cast<float*>(s_words + NW * rs);  // [HAF_FT_ROWS][ld .. ld + 31]
-    uint4* s_tab = reinterpret_cast<uint4*>(s_words + ((NW * rs + HAF_FT_ROWS * (ld + 31) + 3) & ~3));  // [KPASS] DimFeat records of the pass
+    float* s_int = reinterpret_cast<float*>(s_words + tiles * TILE_WORDS);  // [HAF_FT_ROWS][ld .. ld + 31]
+    uint4* s_tab = reinterpret_cast<uint4*>(s_words + ((tiles * TILE_WORDS + HAF_FT_ROWS * (ld + 31) + 3) & ~3));  // [KPASS] DimFeat records of the pass
     __shared__ int s_box[9];       // unit A, its first row, rows (0 = no staging), row stride of the staged image; unit B, first row, rows
     __shared__ Round4Tab s_rt;
     int unit[WT], row[WT], col[WT];
@@ -807,9 +818,9 @@ __global__ void __launch_bounds__(256, 4) features_tc_kernel(const float* __rest
     float nrm[WT];  // squared-norm partials of this lane's windows over the dimensions this warp evaluates
 #pragma unroll
     for (int t = 0; t < WT; t++) nrm[t] = 0.0f;
-    // The tile is kept small (4 passes at Krow = 336) on purpose: 4 resident CTAs then leave ~100 KB of the SM's unified
-    // memory to L1, where the 31 KB corner-offset table lives (with a 2-pass tile only ~30 KB remained, the table loads
-    // missed to L2 and their latency was the top stall).
+    const uint32_t tile_base = (uint32_t)__cvta_generic_to_shared(s_words);
+    const uint32_t row0 = tile_base + (uint32_t)lane * (HAF_FT_KPASS * 2), row1 = row0 + 32u * (HAF_FT_KPASS * 2);   // windows lane, 32 + lane
+    const uint32_t sw = (uint32_t)(((lane & 7) << 2) | ((lane >> 3) & 3));   // swizzle of this lane's two rows (same low five bits)
     for (int d0 = 0; d0 < Krow; d0 += HAF_FT_KPASS) {
         const int KP = min(HAF_FT_KPASS, Krow - d0);   // a multiple of 16
         {   // this pass's records of the stride class, coalesced
@@ -847,28 +858,38 @@ __global__ void __launch_bounds__(256, 4) features_tc_kernel(const float* __rest
                 nrm[1] = fmaf(v1, v1, nrm[1]);
             }
             const uint32_t hu = *reinterpret_cast<const uint32_t*>(&hi2), lu = *reinterpret_cast<const uint32_t*>(&lo2);
-            // tile position of dimension dl: inside each block of 64 dimensions the even ones come first, then the odd
-            // ones, so that the write-out below reads words e and e + nbh (consecutive lanes -> consecutive banks) to
-            // form the pair (2e, 2e + 1); the natural order made every one of those reads a two-way bank conflict
-            const int blk = dl & ~63, nbh = min(64, KP - blk) >> 1;
-            const int pos = blk + ((dl & 63) >> 1) + ((dl & 1) ? nbh : 0);
-            s_words[lane * rs + pos] = __byte_perm(hu, lu, 0x5410);          // hi(w0) | lo(w0) << 16
-            s_words[(32 + lane) * rs + pos] = __byte_perm(hu, lu, 0x7632);   // hi(w1) | lo(w1) << 16
+            // swizzled byte offset of dimension dl inside a tile row (see TILE above)
+            const uint32_t toff = ((((uint32_t)dl >> 1) ^ sw) << 2) | (((uint32_t)dl & 1u) << 1);
+            asm volatile("st.shared.b16 [%0], %1;" ::"r"(row0 + toff), "h"((unsigned short)(hu & 0xffffu)) : "memory");
+            asm volatile("st.shared.b16 [%0], %1;" ::"r"(row1 + toff), "h"((unsigned short)(hu >> 16)) : "memory");
+            if (Xl) {   // three products only
+                asm volatile("st.shared.b16 [%0], %1;" ::"r"(row0 + TILE_WORDS * 4 + toff), "h"((unsigned short)(lu & 0xffffu)) : "memory");
+                asm volatile("st.shared.b16 [%0], %1;" ::"r"(row1 + TILE_WORDS * 4 + toff), "h"((unsigned short)(lu >> 16)) : "memory");
+            }
         }
         __syncthreads();
+        {   // write-out: lane = (window of a pair, chunk): 16 lanes x 16 bytes = two whole 128-byte k-block rows of one window
+            const int c = lane & 15, nch = KP >> 3;
+            // k-block tiled layout (kt_off): chunk c of this pass = dimensions d0 + 8c .. + 7 = 16 contiguous bytes of the window's row
+            const size_t coff = ((size_t)((d0 >> 6) + (c >> 3)) << 13) + (size_t)((c & 7) << 3);
 #pragma unroll
-        for (int k = 0; k < NW / 8; k++) {
-            const int wi = warp + 8 * k;
-            const unsigned ww = w0 + wi;
-            if (ww >= W) break;
-            const uint32_t* sw = s_words + wi * rs;
-            // k-block tiled layout (kt_off): the 64 dimensions of a k-block are 128 contiguous bytes of this window's tile row
-            for (int e = lane; e < KP / 2; e += 32) {
-                const int blk = (e >> 5) << 6, nbh = min(64, KP - blk) >> 1;
-                const uint32_t a0 = sw[blk + (e & 31)], a1 = sw[blk + nbh + (e & 31)];   // dims 2e, 2e+1: (hi | lo << 16)
-                const size_t off = kt_off(ww, d0 + 2 * e, KB);
-                *reinterpret_cast<uint32_t*>(Xh + off) = __byte_perm(a0, a1, 0x5410);             // hi(2e) | hi(2e+1) << 16
-                if (Xl) *reinterpret_cast<uint32_t*>(Xl + off) = __byte_perm(a0, a1, 0x7632);     // lo(2e) | lo(2e+1) << 16 (three products only)
+            for (int k = 0; k < NW / 16; k++) {
+                const int wi = 16 * k + 2 * warp + (lane >> 4);
+                const unsigned ww = w0 + wi;
+                if (ww < W && c < nch) {
+                    const uint32_t a = tile_base + (uint32_t)wi * (HAF_FT_KPASS * 2) + (uint32_t)((c ^ (wi & 7)) << 4);
+                    const size_t off = ((size_t)(ww >> 7) * (size_t)KB << 13) + ((size_t)(ww & 127) << 6) + coff;
+                    const int kx = (wi >> 3) & 3;   // the row's word permutation: stored word q ^ kx holds dimensions 2q, 2q + 1
+#pragma unroll
+                    for (int tl = 0; tl < 2; tl++) {
+                        if (tl == 1 && !Xl) break;
+                        uint4 v;
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a + tl * TILE_WORDS * 4));
+                        if (kx & 1) { uint32_t t0 = v.x; v.x = v.y; v.y = t0; t0 = v.z; v.z = v.w; v.w = t0; }
+                        if (kx & 2) { uint32_t t0 = v.x; v.x = v.z; v.z = t0; t0 = v.y; v.y = v.w; v.w = t0; }
+                        *reinterpret_cast<uint4*>((tl ? Xl : Xh) + off) = v;
+                    }
+                }
             }
         }
     }
@@ -1211,9 +1232,15 @@ __global__ void __launch_bounds__(256) guard_inputs_kernel(const ExactArgs A, co
         Q.Xg[t] = d < A.D ? exact_scaled_input(A, Q.list[e], d) : 0.0;
     }
 }
+// Work item = (group of 16 windows, slice of 256 * SVT support vectors), items walked grid-stride by one CTA per SM: a
+// launch of ~5 k guard windows is 344 groups x 4 slices = 1376 items = 9.3 rounds over 148 SMs (the round-1 grid of
+// (SMs, slices) CTAs walked groups per slice: 2.3 rounds, the last one a third full).  The SV matrix (L2-resident, 5 MB)
+// is read DB = 8 dimensions ahead into registers: one 176-register CTA per SM has only two warps per scheduler, and two
+// dimensions of look-ahead (128 DFMA issue clocks) did not cover an L2 round trip (ncu r2: long-scoreboard 2.6 of 4.5 stall
+// cycles per issue, FP64 pipe 32 %).
 template <int SVT>
-__global__ void __launch_bounds__(256) guard_fma_kernel(const ExactArgs A, const Guard2Args Q) {
-    constexpr int WB = HAF_G2_WB;
+__global__ void __launch_bounds__(256, 1) guard_fma_kernel(const ExactArgs A, const Guard2Args Q, int nslices) {
+    constexpr int WB = HAF_G2_WB, DB = 8;
     extern __shared__ double g2s[];       // xs [Dsv][WB], then xn [WB], red [8][WB][2]
     const int Dsv = A.Dsv, Spad = A.Spad;
     double* xs = g2s;
@@ -1223,12 +1250,15 @@ __global__ void __launch_bounds__(256) guard_fma_kernel(const ExactArgs A, const
     const unsigned total = *Q.list_count;
     const unsigned n = min(total, (unsigned)Q.cap);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (blockIdx.x == 0 && blockIdx.y == 0)   // overflow of the tier-2 buffers: straight to tier 3
+    if (blockIdx.x == 0)   // overflow of the tier-2 buffers: straight to tier 3
         for (unsigned e = (unsigned)Q.cap + threadIdx.x; e < total; e += blockDim.x)
             if (!Q.guard_flag || Q.guard_flag[Q.list[e]]) Q.list2[atomicAdd(Q.list2_count, 1u)] = Q.list[e];
-    const int i0 = blockIdx.y * (256 * SVT);
     const double g2 = A.gamma * 1.4426950408889634;
-    for (unsigned e0 = blockIdx.x * WB; e0 < n; e0 += gridDim.x * WB) {
+    const unsigned ngroups = (n + WB - 1) / WB;
+    const unsigned nitems = ngroups * (unsigned)nslices;
+    for (unsigned item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const unsigned e0 = (item / (unsigned)nslices) * WB;
+        const int i0 = (int)(item % (unsigned)nslices) * (256 * SVT);
         const int nb = min((unsigned)WB, n - e0);
         __syncthreads();
         for (int t = threadIdx.x; t < WB * Dsv; t += blockDim.x) {
@@ -1250,33 +1280,38 @@ __global__ void __launch_bounds__(256) guard_fma_kernel(const ExactArgs A, const
 #pragma unroll
             for (int k = 0; k < SVT; k++) acc[b][k] = 0.0;
         const int ia = i0 + threadIdx.x;
-        // the SV matrix (L2-resident) is read two dimensions ahead: with one 176-register CTA per SM there are only
-        // 8 warps to hide an L2 round trip behind 32 DFMAs each (ncu: long-scoreboard stalls dominated)
-        double svn1[SVT], svn2[SVT];
+        bool in[SVT];
 #pragma unroll
-        for (int k = 0; k < SVT; k++) {
-            const bool in = ia + 256 * k < Spad;
-            svn1[k] = in ? A.sv64T[ia + 256 * k] : 0.0;
-            svn2[k] = (in && Dsv > 1) ? A.sv64T[(size_t)Spad + ia + 256 * k] : 0.0;
-        }
-        for (int d = 0; d < Dsv; d++) {
-            double sv[SVT];
+        for (int k = 0; k < SVT; k++) in[k] = ia + 256 * k < Spad;
+        double cur[DB][SVT], nxt[DB][SVT];
 #pragma unroll
-            for (int k = 0; k < SVT; k++) {
-                sv[k] = svn1[k];
-                svn1[k] = svn2[k];
-                svn2[k] = (d + 2 < Dsv && ia + 256 * k < Spad) ? A.sv64T[(size_t)(d + 2) * Spad + ia + 256 * k] : 0.0;
-            }
-            const double2* xr = reinterpret_cast<const double2*>(xs + d * WB);
+        for (int q = 0; q < DB; q++)
 #pragma unroll
-            for (int b2 = 0; b2 < WB / 2; b2++) {
-                const double2 xv = xr[b2];   // broadcast 128-bit shared load: two windows
+            for (int k = 0; k < SVT; k++) cur[q][k] = (q < Dsv && in[k]) ? A.sv64T[(size_t)q * Spad + ia + 256 * k] : 0.0;
+        for (int d0 = 0; d0 < Dsv; d0 += DB) {
 #pragma unroll
-                for (int k = 0; k < SVT; k++) {
-                    acc[2 * b2][k] = fma(xv.x, sv[k], acc[2 * b2][k]);
-                    acc[2 * b2 + 1][k] = fma(xv.y, sv[k], acc[2 * b2 + 1][k]);
+            for (int q = 0; q < DB; q++)
+#pragma unroll
+                for (int k = 0; k < SVT; k++) nxt[q][k] = (d0 + DB + q < Dsv && in[k]) ? A.sv64T[(size_t)(d0 + DB + q) * Spad + ia + 256 * k] : 0.0;
+#pragma unroll
+            for (int q = 0; q < DB; q++) {
+                if (d0 + q < Dsv) {   // uniform
+                    const double2* xr = reinterpret_cast<const double2*>(xs + (d0 + q) * WB);
+#pragma unroll
+                    for (int b2 = 0; b2 < WB / 2; b2++) {
+                        const double2 xv = xr[b2];   // broadcast 128-bit shared load: two windows
+#pragma unroll
+                        for (int k = 0; k < SVT; k++) {
+                            acc[2 * b2][k] = fma(xv.x, cur[q][k], acc[2 * b2][k]);
+                            acc[2 * b2 + 1][k] = fma(xv.y, cur[q][k], acc[2 * b2 + 1][k]);
+                        }
+                    }
                 }
             }
+#pragma unroll
+            for (int q = 0; q < DB; q++)
+#pragma unroll
+                for (int k = 0; k < SVT; k++) cur[q][k] = nxt[q][k];
         }
         double ds[WB], es[WB];
 #pragma unroll
@@ -1316,7 +1351,7 @@ __global__ void __launch_bounds__(256) guard_fma_kernel(const ExactArgs A, const
         __syncthreads();
         if (threadIdx.x == 0) s_ticket = atomicAdd(Q.tickets + e0 / WB, 1u);
         __syncthreads();
-        if (s_ticket == gridDim.y - 1) {   // every slice of these windows has been added: finalise
+        if (s_ticket == (unsigned)nslices - 1) {   // every slice of these windows has been added: finalise
             __threadfence();
             if (threadIdx.x < nb) {
                 const unsigned e = e0 + threadIdx.x;

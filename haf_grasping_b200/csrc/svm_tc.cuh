@@ -637,12 +637,15 @@ __global__ void svm_finalize_kernel(double* __restrict__ dec, const float* __res
     // FP32 RANGE.  ex2.approx.ftz returns 0 for kernel values below 2^-126: a window far from every support vector of a
     // large-gamma model loses terms of up to sum|coef| 2^-126 that way.  Against E >= e_floor = sum|coef| 2^-100 that is
     // 1.5e-8 E -- nothing; a window whose E is smaller than that is evaluated in FP64 (whose range libsvm's own doubles have).
-    const bool g = !(fabs(dv) > (double)guard_rel * ((double)asum[m] + fabs(rho))) || outside || !(asum[m] >= e_floor);  // asum = E above
+    const bool tiny = !(asum[m] >= e_floor);
+    const bool g = !(fabs(dv) > (double)guard_rel * ((double)asum[m] + fabs(rho))) || outside || tiny;  // asum = E above
     const bool audit = audit_every > 0 && (m % (unsigned)audit_every) == 0u;
     guard_flag[m] = g ? 1 : 0;
     if (g || audit) {
         guard_list[atomicAdd(guard_count, 1u)] = (int)m;
-        if (dec_tc) dec_tc[m] = outside ? __longlong_as_double(0x7ff8000000000000ll) : dv;   // NaN: nothing to compare
+        // NaN: nothing to compare -- windows sent to FP64 because FP32 / fp16 cannot represent them say nothing about the
+        // contraction's error on the windows that keep its sign
+        if (dec_tc) dec_tc[m] = (outside || tiny) ? __longlong_as_double(0x7ff8000000000000ll) : dv;
         if (!g) atomicAdd(audit_only_count, 1u);
     }
 }

@@ -60,7 +60,10 @@ def lzf_decompress(src: bytes, out_len: int) -> bytes:
 
 def read_pcd(path: str) -> np.ndarray:
     with open(path, "rb") as fh:
-        raw = fh.read()
+        return read_pcd_bytes(fh.read(), path)
+
+
+def read_pcd_bytes(raw: bytes, path: str = "<bytes>") -> np.ndarray:
     pos = 0
     hdr = {}
     data_kind = None

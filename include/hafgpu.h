@@ -168,6 +168,24 @@ int haf_search_batch(haf_ctx* ctx, const float* const* clouds, const size_t* n_p
 int haf_search_batch_packed(haf_ctx* ctx, const float* xyz_all_hostdev, const size_t* point_offsets, int n_clouds,
                             const haf_request* req, haf_best* best_per_cloud);
 
+/* ---- PCD / PointCloud2 ingest on the device -----------------------------------------------------------
+ * What the reference does on the CPU before the hot path starts: the client's pcl::io::loadPCDFile<pcl::PointXYZ>
+ * (src/calc_grasppoints_action_client.cpp:137-157) and the server's pcl::fromROSMsg (src/calc_grasppoints_action_server.cpp
+ * :313-316).  file_bytes: the whole .pcd file in host memory (v0.7; DATA ascii, binary or binary_compressed; x / y / z
+ * float32).  The text header is parsed on the host; the data section is decoded by kernels: ASCII records (correctly
+ * rounded decimal -> float, exactly POINTS records, further lines ignored), binary records, or the LZF stream + the
+ * struct-of-arrays -> xyz gather.  *d_xyz: packed xyz in DEVICE memory owned by the context (valid until the next ingest
+ * call), accepted by haf_search / haf_debug_cell_indices as xyz_hostdev.  Errors: HAF_ERR_IO (malformed / truncated file,
+ * fewer records than POINTS), HAF_ERR_UNSUPPORTED (other field types; a > 19-digit token next to a rounding boundary). */
+int haf_pcd_decode(haf_ctx* ctx, const void* file_bytes, size_t n_bytes, const float** d_xyz, size_t* n_points);
+/* haf_pcd_decode + haf_search in one call */
+int haf_search_pcd(haf_ctx* ctx, const void* file_bytes, size_t n_bytes, const haf_request* reqs, int n_requests, haf_best* best,
+                   haf_best* best_per_request, float* graspseval, unsigned char* mask, float* heights, int* per_roll_top);
+/* sensor_msgs/PointCloud2 -> packed xyz on the device (pcl::fromROSMsg for PointXYZ): n_points records of point_step bytes
+ * (host or device memory), x / y / z float32 at byte offsets off_x / off_y / off_z (any alignment). */
+int haf_pointcloud2_to_xyz(haf_ctx* ctx, const void* data_hostdev, size_t n_points, size_t point_step, int off_x, int off_y, int off_z,
+                           const float** d_xyz);
+
 /* ---- libsvm-compatible front ends ----------------------------------------------------------------
  * The reference classifies by running two child processes per roll on text files (server.cpp:775-776, :786-792):
  *     svm-scale -r <range> /tmp/features.txt > /tmp/features.txt.scale      (libsvm-3.12/svm-scale.c)
@@ -237,6 +255,9 @@ int haf_debug_cell_indices(haf_ctx* ctx, const float* xyz_hostdev, size_t n_poin
 /* device evaluation of text4 (float -> "%.4g" -> double) and text6 (double -> "%g" -> double) */
 int haf_debug_text_roundtrip(haf_ctx* ctx, const float* in4, int n4, double* out4, const double* in6, int n6,
                              double* out6);
+
+/* packed xyz of the last haf_pcd_decode / haf_pointcloud2_to_xyz, copied to host memory (n_points records) */
+int haf_debug_pcd_xyz(haf_ctx* ctx, float* xyz_host, size_t n_points);
 
 /* cycle counters of the role threads of the last X-resident tensor kernel launch made under HAF_TC_DEBUG=32 (timing
  * experiments, tools/tc_pipeline_probe.py; layout in csrc/svm_tc.cuh, g_tc_probe): out [n_ctas][16] */
