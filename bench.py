@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--tc-variant", type=int, default=0, help="tensor kernel: 0 auto (X-resident CTA pair where eligible), 1 single CTA, 2 streaming CTA pair")
     ap.add_argument("--bin-variant", type=int, default=0, help="binning: 0 auto, 1 point-parallel kernel only, 2 whole-cloud kernel with scalar loads")
     ap.add_argument("--svm-mode", type=int, default=0, help="0 tcgen05 split-fp16 + FP64 guard (default), 1 FP64 exact, 2 FP32 SIMT + guard")
+    ap.add_argument("--group", type=int, default=1, help="ONE process driving this many GPUs through the C ABI's multi-GPU context (haf_config.n_devices): "
+                                                         "the path a C++ host takes; --clouds is per GPU; timed by wall clock (the member GPUs run on their own streams)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-clouds", type=int, default=2)
     return ap.parse_args()
@@ -280,19 +282,27 @@ def run_approach(args):
     if world > 1:
         dist.barrier()
         model = model_path(args.nsv)
-    xyz = np.ascontiguousarray(np.load(os.path.join(ROOT, "tests", "golden", "clouds.npz"))["table1"])
+    wc = workload_config(args)
+    big = args.workload == "grid512"    # configs[3] as ONE goal sharded by roll (strong scaling); else configs[2]
+    if big:
+        from haf_grasping_b200 import synth
+        xyz = synth.synth_cloud(1234, wc["n_points"], r=wc["r"])
+        approaches = [(0.0, 0.0, 1.0)]
+    else:
+        xyz = np.ascontiguousarray(np.load(os.path.join(ROOT, "tests", "golden", "clouds.npz"))["table1"])
+        approaches = TILTED
     host = torch.empty((len(xyz), 3), dtype=torch.float32, pin_memory=True)
     host.numpy()[:] = xyz
     dev = host.cuda()
-    gs = h.GraspSearch(FEATURES, RANGE, model, device=local, svm_mode=args.svm_mode)
+    gs = h.GraspSearch(FEATURES, RANGE, model, grid=wc["grid"], device=local, svm_mode=args.svm_mode)
     stream = torch.cuda.current_stream()
     gs.set_stream(stream.cuda_stream)
-    R, A = gs.R, len(TILTED)
+    R, A = gs.R, len(approaches)
     windows = [0]
 
     def evaluate_on(buf):
         def evaluate(a, rb, re):
-            res = gs.search(buf, [h.make_request(approach=TILTED[a], roll_begin=rb, roll_limit=re)], outputs=False)
+            res = gs.search(buf, [h.make_request(area=wc["area"], approach=approaches[a], roll_begin=rb, roll_limit=re)], outputs=False)
             windows[0] += gs.timing().n_windows
             return res["per_roll_top"][0][rb:re]
         return evaluate
@@ -300,7 +310,7 @@ def run_approach(args):
     def step(buf):
         return hd.sharded_goal_search(evaluate_on(buf), A, R, [0] * A, [119] * A, rank, world)
 
-    ref = gs.search(dev, [h.make_request(approach=a) for a in TILTED], outputs=False)
+    ref = gs.search(dev, [h.make_request(area=wc["area"], approach=a) for a in approaches], outputs=False)
     per, overall, tops = step(dev)
     assert overall[0] == ref["best"].approach_idx and overall[1:] == ref["best"].astuple()[:3] + (ref["best"].topval,), (overall, ref["best"].astuple())
     assert np.array_equal(tops.reshape(A, R, 3), ref["per_roll_top"])
@@ -342,8 +352,10 @@ def run_approach(args):
     if rank == 0:
         line = {"metric": METRIC, "value": w_dev / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong",
-                "vs_baseline": None, "dtype": dtype_of(args.svm_mode, gs.timing().tc_passes), "data": "tests/golden/clouds.npz:table1 (= data/objects_1.pcd of the reference)",
-                "config": {"workload": "configs[2]: objects_1 scene x 5 approach vectors x 12 rolls = 60 units sharded by (approach vector, roll) over the ranks; "
+                "vs_baseline": None, "dtype": dtype_of(args.svm_mode, gs.timing().tc_passes),
+                "data": "synthetic" if big else "tests/golden/clouds.npz:table1 (= data/objects_1.pcd of the reference)",
+                "config": {"workload": ("configs[3] as ONE goal: synthetic 1M-point cloud, G=512, area 362x362, its 12 rolls sharded over the ranks (strong scaling); "
+                                        if big else "configs[2]: objects_1 scene x 5 approach vectors x 12 rolls = 60 units sharded by (approach vector, roll) over the ranks; ") +
                                        "merged best grasp verified against the unsharded search on every rank",
                            "n_sv": gs.info.n_sv, "l2": "single goal: latency-bound, working set far below L2 (no flush: that is the operating point of one goal)",
                            "units_per_rank": [sum(re - rb for _, rb, re in hd.unit_blocks(A, R, r, world)) for r in range(world)]},
@@ -384,6 +396,11 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     wc = workload_config(args)
+    group = max(1, args.group)
+    if group > 1:
+        if world > 1:
+            raise SystemExit("bench.py: --group is a single-process mode (no torchrun)")
+        wc["n_clouds"] *= group if args.workload == "batch" else 1
     model = model_path(args.nsv) if rank == 0 or world == 1 else None
     if world > 1:
         dist.barrier()
@@ -398,7 +415,7 @@ def run_ours(args):
 
     gs = h.GraspSearch(FEATURES, RANGE, model, grid=wc["grid"], roll_step_deg=wc["step"], roll_max_deg=wc["rmax"],
                        device=local, svm_mode=args.svm_mode, sv_table_global=args.sv_table_global, tc_passes=args.tc_passes,
-                       tc_variant=args.tc_variant, bin_variant=args.bin_variant)
+                       tc_variant=args.tc_variant, bin_variant=args.bin_variant, devices=list(range(group)) if group > 1 else None)
     stream = torch.cuda.current_stream()
     gs.set_stream(stream.cuda_stream)
     gs.set_profiling(True)
@@ -441,6 +458,8 @@ def run_ours(args):
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
         ms = e0.elapsed_time(e1)
+        if group > 1:
+            ms = wall * 1e3   # the member GPUs run on their own streams: the host call's wall time is the honest clock here
         if world > 1:
             tm = torch.tensor([ms], dtype=torch.float64, device="cuda")
             dist.all_reduce(tm, op=dist.ReduceOp.MAX)
@@ -464,6 +483,32 @@ def run_ours(args):
     for _ in range(2):
         step(host.numpy())
     ms_e2e, wall_e2e, acc2 = timed(host.numpy(), args.steps)
+    # what bounds the end-to-end number from below: the same bytes copied host -> device and nothing else, all ranks at once
+    def copies_only(steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            dev.copy_(host, non_blocking=True)
+        e1.record(stream)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            tm = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            ms = float(tm.item())
+        return ms / steps
+    copies_only(1)
+    ms_h2d = copies_only(max(3, min(args.steps, 5)))
+    # the real caller hands pageable memory (a pcl::PointCloud): same call, ordinary numpy buffer
+    pageable = np.array(host.numpy(), copy=True)
+    step(pageable)
+    ms_pageable, _, _ = timed(pageable, max(2, min(args.steps, 3)))
+    ms_pageable /= max(2, min(args.steps, 3))
 
     if rank == 0:
         hbm, tf_burst, tf_sust, src = peaks()
@@ -494,19 +539,26 @@ def run_ours(args):
         except Exception:
             traffic = None
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world * group, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": dtype_of(args.svm_mode, t_last.tc_passes), "data": "synthetic",
             "config": {"workload": describe(args, wc), "tensor_passes": int(t_last.tc_passes), "guard_rel": info.reserved[1] * 1e-9, "n_sv": info.n_sv, "n_dims": info.n_dims, "grid": info.grid,
                        "rolls": info.n_rolls, "clouds_per_gpu": n_clouds, "windows_per_step_per_gpu": W_step,
                        "svm_mode": args.svm_mode, "l2": "inputs (%.0f MB per GPU per step) larger than L2, no flush" % (total_pts * 12 / 1e6),
-                       "sharding": "clouds by rank, no data-path collective; NCCL all_gather of best-grasp records"},
+                       "sharding": ("one process, one C-ABI context over %d GPUs (haf_config.n_devices): clouds in contiguous blocks per GPU, one host thread "
+                                    "and stream each, records merged on the host; timed by wall clock" % group) if group > 1 else
+                                   "clouds by rank, no data-path collective; NCCL all_gather of best-grasp records"},
             "ms_per_cloud": ms_dev / args.steps / n_clouds,
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": total_pts * 12 + 0, "d2h_bytes_per_step": n_clouds * (32 + info.n_rolls * 12) + 64, "host_memory": "pinned",
                     "ms_per_step": ms_e2e / args.steps,
                     "stage_ms_per_step": {k: acc2[k] / args.steps for k in ("bin", "integral", "mask", "features", "svm", "guard", "score")},
-                    "chunks_per_step": acc2["chunks"] / args.steps},
+                    "chunks_per_step": acc2["chunks"] / args.steps,
+                    "h2d_only_ms_per_step": ms_h2d, "h2d_only_GBps_per_gpu": total_pts * 12 / (ms_h2d * 1e-3) / 1e9,
+                    "frac_of_h2d_ceiling": ms_h2d / (ms_e2e / args.steps),
+                    "note": "h2d_only = the step's input bytes copied host->device from the same pinned buffers by all ranks at once, nothing else "
+                            "(the floor of any end-to-end number on this host); frac_of_h2d_ceiling = that floor / the measured end-to-end step",
+                    "pageable_ms_per_step": ms_pageable, "pageable_value": acc2["windows_all"] / args.steps / (ms_pageable * 1e-3)},
             "gpu_launches": int(acc["launches"]),
             "roofline": {"kernel": kname, "bound": "tensor",
                          "achieved": svm_tflops, "peak": peak, "unit": "TFLOP/s", "frac": svm_tflops / peak if peak else None,
@@ -580,7 +632,7 @@ def main():
     protect_stdout()
     if args.impl == "reference":
         run_reference(args)
-    elif args.workload == "approach":
+    elif args.workload == "approach" or (args.workload == "grid512" and int(os.environ.get("WORLD_SIZE", "1")) > 1):
         run_approach(args)
     else:
         run_ours(args)

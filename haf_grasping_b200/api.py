@@ -166,7 +166,7 @@ class GraspSearch:
     def __init__(self, features_path, range_path, model_path, grid=56, roll_step_deg=15, roll_max_deg=190,
                  nr_features_without_shaf=302, device=0, emulate_text_roundtrip=True, svm_mode=HAF_SVM_TENSOR_GUARD,
                  guard_rel=0.0, tc_variant=0, guard_tier2=0, sv_table_global=0, tc_passes=0, audit_every=None, bin_variant=0,
-                 devices=None):
+                 devices=None, guard_kernel=0):
         self.L = load_library()
         cfg = haf_config()
         self._keep = [features_path.encode(), range_path.encode(), model_path.encode()]
@@ -183,7 +183,8 @@ class GraspSearch:
         if audit_every is not None:
             cfg.reserved[0] |= 0x100 if audit_every == 0 else (int(audit_every) << 16)
         cfg.reserved[1] = bin_variant   # 0 auto, 1 point-parallel binning only, 2 whole-cloud kernel with scalar loads
-        cfg.reserved[2] = guard_tier2   # 0 on, 1 off, 2 on + escalate everything (tests)
+        # guard_tier2: 0 on, 1 off, 2 on + escalate everything (tests); guard_kernel: 0 auto, 1 FP64 tensor cores (DMMA), 2 DFMA
+        cfg.reserved[2] = guard_tier2 | (guard_kernel << 2)
         cfg.reserved[3] = sv_table_global   # 1: SV table read from global memory (the > 4096-SV path)
         if devices is not None and len(devices) > 1:   # one context driving several GPUs (haf_config.n_devices / devices)
             self._devs = (C.c_int * len(devices))(*devices)

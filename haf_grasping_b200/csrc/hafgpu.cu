@@ -138,8 +138,9 @@ struct haf_ctx {
     DevBuf<int> d_guardlist;
     DevBuf<double> d_kscratch;
     // guard band tier 2 (FP64 FMA contraction on the exact inputs, kernels.cuh guard_fma_kernel)
-    int tier2_mode = 0;                 // cfg.reserved[2]: 0 on, 1 off (guard list straight to the exact-order kernels), 2 on but everything escalates (tests)
-    DevBuf<double> d_svn64, d_Xg, d_g2accum;
+    int tier2_mode = 0;                 // cfg.reserved[2] & 3: 0 on, 1 off (guard list straight to the exact-order kernels), 2 on but everything escalates (tests)
+    int tier2_kernel = 0;               // cfg.reserved[2] >> 2: 0 auto (DMMA for batches, DFMA for a single goal's handful), 1 DMMA always, 2 DFMA always
+    DevBuf<double> d_svn64, d_Xg, d_g2accum, d_xn64;
     DevBuf<unsigned> d_g2tickets;
     DevBuf<int> d_guardlist2;
     DevBuf<unsigned> d_counters;        // [0]=win_count [1]=guard_count [2]=overflow [3]=unsupported ; [4..5] clamp (u64)
@@ -465,7 +466,8 @@ static int create_impl(haf_ctx** out, const haf_config* cfg, bool svm_only, int 
         fd[k] = f;
     }
     std::vector<float> svT((size_t)Kpad * Spad, 0.0f), svn(Spad, 0.0f), coef(Spad, 0.0f);
-    std::vector<double> sv64T((size_t)Dsv * Spad, 0.0), coef64(Spad, 0.0), svn64(Spad, 0.0);
+    const int Dsv16 = (int)round_up((size_t)Dsv, 16);   // the DMMA guard tier walks k-chunks of 16 dimensions: zero rows behind Dsv
+    std::vector<double> sv64T((size_t)Dsv16 * Spad, 0.0), coef64(Spad, 0.0), svn64(Spad, 0.0);
     for (int i = 0; i < S; i++) {
         coef[i] = (float)model.coef[i];
         coef64[i] = model.coef[i];
@@ -493,7 +495,9 @@ static int create_impl(haf_ctx** out, const haf_config* cfg, bool svm_only, int 
     CREATE_TRY(cudaMemcpy(ctx->d_sv64T.p, sv64T.data(), sv64T.size() * sizeof(double), cudaMemcpyHostToDevice));
     CREATE_TRY(cudaMemcpy(ctx->d_coef64.p, coef64.data(), Spad * sizeof(double), cudaMemcpyHostToDevice));
     CREATE_TRY(cudaMemcpy(ctx->d_svn64.p, svn64.data(), Spad * sizeof(double), cudaMemcpyHostToDevice));
-    ctx->tier2_mode = cfg->reserved[2];
+    ctx->tier2_mode = cfg->reserved[2] & 3;
+    ctx->tier2_kernel = (cfg->reserved[2] >> 2) & 3;
+    CREATE_TRY(cudaFuncSetAttribute(guard_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HAF_GD_SMEM_BYTES));
     CREATE_TRY(cudaFuncSetAttribute(guard_fma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CREATE_TRY(cudaFuncSetAttribute(guard_fma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CREATE_TRY(cudaFuncSetAttribute(svm_rbf_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SVM_STAGES * SVM_BK * (SVM_BM + SVM_BN) * 4));
@@ -890,7 +894,7 @@ extern "C" void haf_destroy(haf_ctx* ctx) {
     ctx->d_unit_top.release(); ctx->d_unit_run.release(); ctx->d_unit_windows.release(); ctx->d_win.release(); ctx->d_X.release();
     ctx->d_xn.release(); ctx->d_dec.release(); ctx->d_guardflag.release(); ctx->d_guardlist.release(); ctx->d_kscratch.release();
     ctx->d_xdense.release(); ctx->d_labels.release(); ctx->d_probs.release(); ctx->d_probgrid.release(); ctx->d_pcd_raw.release(); ctx->d_pcd_blob.release(); ctx->d_pcd_xyz.release(); ctx->d_pcd_tiles.release(); ctx->d_pcd_words.release(); ctx->d_csr_ptr.release(); ctx->d_csr_idx.release(); ctx->d_csr_val.release();
-    ctx->d_svn64.release(); ctx->d_Xg.release(); ctx->d_g2accum.release(); ctx->d_g2tickets.release(); ctx->d_guardlist2.release();
+    ctx->d_svn64.release(); ctx->d_Xg.release(); ctx->d_xn64.release(); ctx->d_g2accum.release(); ctx->d_g2tickets.release(); ctx->d_guardlist2.release();
     ctx->d_SVh.release(); ctx->d_SVl.release(); ctx->d_Xh.release(); ctx->d_Xl.release(); ctx->d_svcoef.release(); ctx->d_dec_tc.release(); ctx->d_asum.release(); ctx->d_dimfeat.release(); ctx->d_round4.release();
     ctx->d_params.release(); ctx->d_counters.release(); ctx->h_stage.release(); ctx->h_results.release(); ctx->h_per_roll_top.release(); ctx->h_counters.release(); ctx->h_unit_windows.release();
     if (ctx->ev_ok) for (int i = 0; i < 10; i++) cudaEventDestroy(ctx->ev[i]);
@@ -913,9 +917,19 @@ extern "C" int haf_get_info(const haf_ctx* ctx, haf_info* info) {
 }
 extern "C" int haf_set_stream(haf_ctx* ctx, void* s) { if (!ctx) return HAF_ERR_ARG; ctx->stream = (cudaStream_t)s; return HAF_OK; }
 extern "C" int haf_set_debug(haf_ctx* ctx, int keep_batch_state) { if (!ctx) return HAF_ERR_ARG; ctx->debug_keep_batch = keep_batch_state != 0; return HAF_OK; }
-extern "C" int haf_set_profiling(haf_ctx* ctx, int on) { if (!ctx) return HAF_ERR_ARG; ctx->profiling = on != 0; return HAF_OK; }
+extern "C" int haf_set_profiling(haf_ctx* ctx, int on) {
+    if (!ctx) return HAF_ERR_ARG;
+    ctx->profiling = on != 0;
+    for (size_t k = 1; k < ctx->group.size(); k++) ctx->group[k]->profiling = on != 0;
+    return HAF_OK;
+}
 extern "C" int haf_get_timing(const haf_ctx* ctx, haf_timing* t) { if (!ctx || !t) return HAF_ERR_ARG; *t = ctx->timing; return HAF_OK; }
-extern "C" long long haf_launch_count(const haf_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" long long haf_launch_count(const haf_ctx* ctx) {
+    if (!ctx) return 0;
+    long long n = ctx->launches;
+    for (size_t k = 1; k < ctx->group.size(); k++) n += ctx->group[k]->launches;
+    return n;
+}
 
 extern "C" int haf_build_transform(const haf_request* req, int roll, int roll_step_deg, float M[16]) {
     if (!req || !M) return HAF_ERR_ARG;
@@ -992,24 +1006,33 @@ static int launch_guard(haf_ctx* ctx, unsigned* cnt, int G, int ubase, cudaStrea
     if (ctx->tier2_mode == 1) return launch_exact(ctx, make_exact_args(ctx, ctx->d_guardlist.p, cnt + 1, cnt, G, ubase), st, Wcap);
     const size_t cap = std::min<size_t>(ldx, 32768);
     const size_t acc_cap0 = ctx->d_g2accum.cap, tk_cap0 = ctx->d_g2tickets.cap;
-    ENSURE(ctx, ctx->d_Xg, cap * ctx->Dsv); ENSURE(ctx, ctx->d_g2accum, cap * 2); ENSURE(ctx, ctx->d_g2tickets, cap / HAF_G2_WB + 1);
+    const int ldxg = (int)round_up((size_t)ctx->Dsv, 16);
+    ENSURE(ctx, ctx->d_Xg, cap * ldxg); ENSURE(ctx, ctx->d_g2accum, cap * 2); ENSURE(ctx, ctx->d_g2tickets, cap / HAF_G2_WB + 1); ENSURE(ctx, ctx->d_xn64, cap);
     ENSURE(ctx, ctx->d_guardlist2, ldx);
     if (ctx->d_g2accum.cap != acc_cap0) CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_g2accum.p, 0, ctx->d_g2accum.cap * sizeof(double), st));
     if (ctx->d_g2tickets.cap != tk_cap0) CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_g2tickets.p, 0, ctx->d_g2tickets.cap * sizeof(unsigned), st));
     ExactArgs a = make_exact_args(ctx, ctx->d_guardlist.p, cnt + 1, cnt, G, ubase);
     Guard2Args q;
     q.list = ctx->d_guardlist.p; q.list_count = cnt + 1; q.cap = (int)cap; q.Xg = ctx->d_Xg.p; q.svn64 = ctx->d_svn64.p;
+    q.ldx = ldxg; q.xn64 = ctx->d_xn64.p;
     q.accum = ctx->d_g2accum.p; q.tickets = ctx->d_g2tickets.p; q.tol2 = ctx->tier2_mode == 2 ? 1e30 : 1e-10;
     q.list2 = ctx->d_guardlist2.p; q.list2_count = cnt + 6;
     const bool audit = ctx->cfg.svm_mode == HAF_SVM_TENSOR_GUARD && ctx->d_dec_tc.p;
     q.dec_tc = audit ? ctx->d_dec_tc.p : nullptr; q.audit_max = cnt + 12; q.guard_flag = audit ? ctx->d_guardflag.p : nullptr;
     const size_t smem = ((size_t)ctx->Dsv * HAF_G2_WB + HAF_G2_WB + 8 * HAF_G2_WB * 2) * sizeof(double);
-    if (smem > 100 * 1024) return launch_exact(ctx, a, st, Wcap);   // models with > ~780 dimensions: exact-order kernels only
     const bool few = Wcap < 65536;   // a single goal: a handful of guard windows -> spread the support vectors over more CTAs
+    // FP64 tensor cores (DMMA) for batches and for models too wide for the DFMA kernel's shared-memory tile; DFMA for the
+    // handful of windows of a single goal (a 64-window MMA tile would be mostly padding)
+    const bool dmma = ctx->tier2_kernel == 1 || (ctx->tier2_kernel == 0 && !few) || smem > 100 * 1024;
     guard_inputs_kernel<<<few ? 32 : ctx->sm_count * 4, 256, 0, st>>>(a, q);
     LAUNCHED(ctx);
+    if (dmma) {
+        guard_norms_kernel<<<few ? 8 : ctx->sm_count, 256, 0, st>>>(q);
+        LAUNCHED(ctx);
+        guard_dmma_kernel<<<(unsigned)ctx->sm_count * 2, 256, HAF_GD_SMEM_BYTES, st>>>(a, q, ctx->Spad / HAF_GD_SB);
+    }
     // one CTA per SM walks (window group, SV slice) items; a single goal's handful of windows: slices of 256 SVs over more CTAs
-    if (few) guard_fma_kernel<1><<<(unsigned)ctx->sm_count, 256, smem, st>>>(a, q, (ctx->Spad + 255) / 256);
+    else if (few) guard_fma_kernel<1><<<(unsigned)ctx->sm_count, 256, smem, st>>>(a, q, (ctx->Spad + 255) / 256);
     else guard_fma_kernel<2><<<(unsigned)ctx->sm_count, 256, smem, st>>>(a, q, (ctx->Spad + 511) / 512);
     LAUNCHED(ctx);
     return launch_exact(ctx, make_exact_args(ctx, ctx->d_guardlist2.p, cnt + 6, cnt, G, ubase), st, Wcap);

@@ -1213,7 +1213,9 @@ __global__ void __launch_bounds__(128) svm_exact_sum_kernel(const ExactArgs A) {
 #define HAF_G2_WB 16
 struct Guard2Args {
     const int* list; const unsigned* list_count; int cap;   // tier-1 guard list, capacity of Xg in entries
-    double* Xg;                  // [cap][Dsv]
+    double* Xg;                  // [cap][ldx]: the exact inputs of the listed windows, columns Dsv .. ldx-1 zero
+    int ldx;                     // row stride of Xg in doubles: Dsv rounded up to 16 (the DMMA kernel's k-chunks)
+    double* xn64;                // [cap] |x|^2 of the rows (guard_norms_kernel; DMMA kernel only)
     const double* svn64;         // [Spad]  sum_d sv_d^2 in double
     double* accum;               // [cap][2]  (decision sum, E), zero on entry, left zero
     unsigned* tickets;           // [cap / WB + 1], zero on entry, left zero
@@ -1225,11 +1227,40 @@ struct Guard2Args {
 };
 __global__ void __launch_bounds__(256) guard_inputs_kernel(const ExactArgs A, const Guard2Args Q) {
     const unsigned n = min(*Q.list_count, (unsigned)Q.cap);
-    const size_t total = (size_t)n * A.Dsv;
+    const size_t total = (size_t)n * Q.ldx;
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
-        const unsigned e = (unsigned)(t / A.Dsv);
-        const int d = (int)(t - (size_t)e * A.Dsv);
+        const unsigned e = (unsigned)(t / Q.ldx);
+        const int d = (int)(t - (size_t)e * Q.ldx);
         Q.Xg[t] = d < A.D ? exact_scaled_input(A, Q.list[e], d) : 0.0;
+    }
+}
+// |x|^2 of every listed row, one warp per row
+__global__ void __launch_bounds__(256) guard_norms_kernel(const Guard2Args Q) {
+    const unsigned n = min(*Q.list_count, (unsigned)Q.cap);
+    const int lane = threadIdx.x & 31;
+    for (unsigned e = blockIdx.x * 8 + (threadIdx.x >> 5); e < n; e += gridDim.x * 8) {
+        double sq = 0.0;
+        for (int d = lane; d < Q.ldx; d += 32) { const double v = Q.Xg[(size_t)e * Q.ldx + d]; sq = fma(v, v, sq); }
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        if (lane == 0) Q.xn64[e] = sq;
+    }
+}
+// one finished window of tier 2 (its decision sum and guard scale are complete in accum): audit, decision value, tier-3 list
+__device__ __forceinline__ void guard_finalize_entry(const ExactArgs& A, const Guard2Args& Q, unsigned e) {
+    const double sum = atomicAdd(Q.accum + (size_t)e * 2, 0.0), E = atomicAdd(Q.accum + (size_t)e * 2 + 1, 0.0);
+    Q.accum[(size_t)e * 2] = 0.0; Q.accum[(size_t)e * 2 + 1] = 0.0;
+    const int w = Q.list[e];
+    const double dv = sum - A.rho;
+    if (Q.dec_tc) {   // audit of the FP32 / tensor contraction against this FP64 value, in the guard band's own unit
+        const double tcv = Q.dec_tc[w];
+        const float rel = (float)(fabs(tcv - dv) / (E + fabs(A.rho)));
+        if (rel == rel) atomicMax(Q.audit_max, __float_as_uint(rel));
+    }
+    // a sample window keeps the contraction's value: what a row gets must not depend on whether its index was sampled
+    if (!Q.guard_flag || Q.guard_flag[w]) {
+        A.dec[w] = dv;
+        if (!(fabs(dv) > Q.tol2 * (E + fabs(A.rho)))) Q.list2[atomicAdd(Q.list2_count, 1u)] = w;
     }
 }
 // Work item = (group of 16 windows, slice of 256 * SVT support vectors), items walked grid-stride by one CTA per SM: a
@@ -1263,7 +1294,7 @@ __global__ void __launch_bounds__(256, 1) guard_fma_kernel(const ExactArgs A, co
         __syncthreads();
         for (int t = threadIdx.x; t < WB * Dsv; t += blockDim.x) {
             const int b = t / Dsv, d = t - b * Dsv;    // coalesced read of Xg rows
-            xs[d * WB + b] = b < nb ? Q.Xg[(size_t)(e0 + b) * Dsv + d] : 0.0;
+            xs[d * WB + b] = b < nb ? Q.Xg[(size_t)(e0 + b) * Q.ldx + d] : 0.0;
         }
         __syncthreads();
         for (int b = warp; b < WB; b += 8) {
@@ -1353,24 +1384,145 @@ __global__ void __launch_bounds__(256, 1) guard_fma_kernel(const ExactArgs A, co
         __syncthreads();
         if (s_ticket == (unsigned)nslices - 1) {   // every slice of these windows has been added: finalise
             __threadfence();
-            if (threadIdx.x < nb) {
-                const unsigned e = e0 + threadIdx.x;
-                const double sum = atomicAdd(Q.accum + (size_t)e * 2, 0.0), E = atomicAdd(Q.accum + (size_t)e * 2 + 1, 0.0);
-                Q.accum[(size_t)e * 2] = 0.0; Q.accum[(size_t)e * 2 + 1] = 0.0;
-                const int w = Q.list[e];
-                const double dv = sum - A.rho;
-                if (Q.dec_tc) {   // audit of the FP32 / tensor contraction against this FP64 value, in the guard band's own unit
-                    const double tcv = Q.dec_tc[w];
-                    const float rel = (float)(fabs(tcv - dv) / (E + fabs(A.rho)));
-                    if (rel == rel) atomicMax(Q.audit_max, __float_as_uint(rel));
-                }
-                // a sample window keeps the contraction's value: what a row gets must not depend on whether its index was sampled
-                if (!Q.guard_flag || Q.guard_flag[w]) {
-                    A.dec[w] = dv;
-                    if (!(fabs(dv) > Q.tol2 * (E + fabs(A.rho)))) Q.list2[atomicAdd(Q.list2_count, 1u)] = w;
-                }
-            }
+            if (threadIdx.x < nb) guard_finalize_entry(A, Q, e0 + threadIdx.x);
             if (threadIdx.x == 0) Q.tickets[e0 / WB] = 0;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Guard band tier 2 on the FP64 TENSOR CORES (mma.sync.m8n8k4.f64, DMMA).  The DFMA kernel above reached 29-32 % of the FP64
+// pipe (ncu r2: two warps per scheduler at 176-232 registers cannot cover the latencies of a 32-accumulator register tile)
+// and spends one issue slot per 32 FMAs; a DMMA does 256 FMAs per slot with 4 registers of operands, which frees both the
+// schedulers and the register file (2 CTAs per SM).  B200 keeps full-rate FP64 tensor cores (the B300 of the guides does not).
+// Same contraction: C[w][i] = x_w . sv_i over the zero-padded K = ldx dimensions, then d^2 = |x|^2 + |sv|^2 - 2C, the
+// exp / coef / row-sum epilogue and the ticket that lets the last SV block of a window block finalise it.  A DMMA is a chain
+// of FP64 FMAs in an unspecified order: the error is a few 1e-16 of the operands' products, the band's tolerance is 1e-10 E.
+//   CTA tile 64 windows x 128 SVs, 8 warps (2 x 4) of 32 x 32 = 4 x 4 m8n8 tiles; k-chunks of 16 dimensions through a 3-stage
+//   cp.async ring: X chunk [64][16 (+4)] from Xg, SV chunk [16][128 (+4)] from sv64T (row paddings make every fragment load
+//   conflict-free: 8-byte lanes of a half-warp fall into 16 distinct bank pairs).
+// grid-stride over items = (window blocks) x nsb SV blocks; sv64T must hold ldx rows (rows >= Dsv zero).
+// ---------------------------------------------------------------------------------------------------
+#define HAF_GD_WB 64
+#define HAF_GD_SB 128
+#define HAF_GD_KC 16
+#define HAF_GD_APAD 20
+#define HAF_GD_BPAD 132
+#define HAF_GD_STAGES 3
+#define HAF_GD_STAGE_DOUBLES (HAF_GD_WB * HAF_GD_APAD + HAF_GD_KC * HAF_GD_BPAD)
+#define HAF_GD_SMEM_BYTES (HAF_GD_STAGES * HAF_GD_STAGE_DOUBLES * 8)
+__device__ __forceinline__ void cp_async16_zfill(void* smem, const void* gmem, bool valid) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    const int n = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(n));
+}
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__global__ void __launch_bounds__(256, 2) guard_dmma_kernel(const ExactArgs A, const Guard2Args Q, int nsb) {
+    extern __shared__ __align__(16) double gds[];   // [STAGES][ X chunk | SV chunk ]
+    __shared__ unsigned s_ticket;
+    const unsigned total = *Q.list_count;
+    const unsigned n = min(total, (unsigned)Q.cap);
+    if (blockIdx.x == 0)   // overflow of the tier-2 buffers: straight to tier 3
+        for (unsigned e = (unsigned)Q.cap + threadIdx.x; e < total; e += blockDim.x)
+            if (!Q.guard_flag || Q.guard_flag[Q.list[e]]) Q.list2[atomicAdd(Q.list2_count, 1u)] = Q.list[e];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp & 1, wn = warp >> 1;           // warp tile: windows wm * 32 .., SVs wn * 32 ..
+    const int g4 = lane >> 2, t4 = lane & 3;
+    const int Spad = A.Spad, ldx = Q.ldx, nk = ldx / HAF_GD_KC;
+    const double g2 = A.gamma * 1.4426950408889634;
+    const unsigned ngroups = (n + HAF_GD_WB - 1) / HAF_GD_WB;
+    const unsigned nitems = ngroups * (unsigned)nsb;
+    for (unsigned item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const unsigned e0 = (item / (unsigned)nsb) * HAF_GD_WB;
+        const int i0 = (int)(item % (unsigned)nsb) * HAF_GD_SB;
+        const int nrows = (int)min((unsigned)HAF_GD_WB, n - e0);
+        auto load_stage = [&](int stage, int kc) {
+            double* As = gds + (size_t)stage * HAF_GD_STAGE_DOUBLES;
+            double* Bs = As + HAF_GD_WB * HAF_GD_APAD;
+            const int d0 = kc * HAF_GD_KC;
+#pragma unroll
+            for (int q = 0; q < 2; q++) {   // X chunk: 64 rows x 8 sixteen-byte pieces
+                const int idx = tid + 256 * q, row = idx >> 3, c = idx & 7;
+                const bool ok = row < nrows;
+                cp_async16_zfill(As + row * HAF_GD_APAD + 2 * c, Q.Xg + (size_t)(e0 + (ok ? row : 0)) * ldx + d0 + 2 * c, ok);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {   // SV chunk: 16 rows x 64 sixteen-byte pieces
+                const int idx = tid + 256 * q, row = idx >> 6, c = idx & 63;
+                cp_async16_zfill(Bs + row * HAF_GD_BPAD + 2 * c, A.sv64T + (size_t)(d0 + row) * Spad + i0 + 2 * c, true);
+            }
+        };
+        double acc[4][4][2];
+#pragma unroll
+        for (int mb = 0; mb < 4; mb++)
+#pragma unroll
+            for (int nb = 0; nb < 4; nb++) { acc[mb][nb][0] = 0.0; acc[mb][nb][1] = 0.0; }
+        __syncthreads();   // the previous item's readers are done with the ring
+        for (int s = 0; s < HAF_GD_STAGES - 1; s++) { if (s < nk) load_stage(s, s); cp_async_commit(); }
+        for (int kc = 0; kc < nk; kc++) {
+            cp_async_wait<HAF_GD_STAGES - 2>();
+            __syncthreads();
+            if (kc + HAF_GD_STAGES - 1 < nk) load_stage((kc + HAF_GD_STAGES - 1) % HAF_GD_STAGES, kc + HAF_GD_STAGES - 1);
+            cp_async_commit();
+            const double* As = gds + (size_t)(kc % HAF_GD_STAGES) * HAF_GD_STAGE_DOUBLES;
+            const double* Bs = As + HAF_GD_WB * HAF_GD_APAD;
+#pragma unroll
+            for (int ks = 0; ks < HAF_GD_KC / 4; ks++) {
+                double a[4], b[4];
+#pragma unroll
+                for (int mb = 0; mb < 4; mb++) a[mb] = As[(wm * 32 + mb * 8 + g4) * HAF_GD_APAD + ks * 4 + t4];
+#pragma unroll
+                for (int nb = 0; nb < 4; nb++) b[nb] = Bs[(ks * 4 + t4) * HAF_GD_BPAD + wn * 32 + nb * 8 + g4];
+#pragma unroll
+                for (int mb = 0; mb < 4; mb++)
+#pragma unroll
+                    for (int nb = 0; nb < 4; nb++) dmma_m8n8k4(acc[mb][nb][0], acc[mb][nb][1], a[mb], b[nb]);
+            }
+        }
+        cp_async_wait<0>();
+        // epilogue: this thread's rows e0 + wm*32 + mb*8 + g4, columns i0 + wn*32 + nb*8 + 2*t4 + {0, 1}
+        double cf[4][2], sn[4][2];
+#pragma unroll
+        for (int nb = 0; nb < 4; nb++)
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const int i = i0 + wn * 32 + nb * 8 + 2 * t4 + j;
+                cf[nb][j] = A.coef64[i];     // padding support vectors: coef 0
+                sn[nb][j] = Q.svn64[i];
+            }
+#pragma unroll
+        for (int mb = 0; mb < 4; mb++) {
+            const int r = wm * 32 + mb * 8 + g4;
+            const bool live = r < nrows;
+            const double xn = live ? Q.xn64[e0 + r] : 0.0;
+            double ds = 0.0, es = 0.0;
+#pragma unroll
+            for (int nb = 0; nb < 4; nb++)
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    const double base = xn + sn[nb][j];
+                    const double d2 = fmax(fma(-2.0, acc[mb][nb][j], base), 0.0);
+                    const double tk = cf[nb][j] * exp(-A.gamma * d2);
+                    ds += tk;
+                    es = fma(fabs(tk), fma(g2, base, 1.0), es);
+                }
+            ds += __shfl_xor_sync(0xffffffffu, ds, 1); es += __shfl_xor_sync(0xffffffffu, es, 1);
+            ds += __shfl_xor_sync(0xffffffffu, ds, 2); es += __shfl_xor_sync(0xffffffffu, es, 2);
+            if (t4 == 0 && live) {
+                atomicAdd(Q.accum + (size_t)(e0 + r) * 2, ds);
+                atomicAdd(Q.accum + (size_t)(e0 + r) * 2 + 1, es);
+            }
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_ticket = atomicAdd(Q.tickets + e0 / HAF_GD_WB, 1u);
+        __syncthreads();
+        if (s_ticket == (unsigned)nsb - 1) {   // every SV block of these windows has been added: finalise
+            __threadfence();
+            if (tid < nrows) guard_finalize_entry(A, Q, e0 + tid);
+            if (tid == 0) Q.tickets[e0 / HAF_GD_WB] = 0;
         }
     }
 }

@@ -65,8 +65,10 @@ typedef struct {
                                        bit 8: audit sample off; bits 16+: audit every n-th window (default 4096; see haf_timing);
                                   [1]: 1 = always use the point-parallel binning kernel (no whole-cloud CTAs), 2 = whole-cloud kernel
                                        with scalar loads;
-                                  [2]: guard band tier 2 (FP64 FMA re-evaluation): 0 = on, 1 = off (every guard window goes
-                                       to the exact-order kernels), 2 = on, but every window escalates as well (tests);
+                                  [2]: bits 0-1: guard band tier 2 (FP64 re-evaluation by contraction): 0 = on, 1 = off (every guard
+                                       window goes to the exact-order kernels), 2 = on, but every window escalates as well (tests);
+                                       bits 2-3: its kernel: 0 = auto (FP64 tensor cores / DMMA for batches, DFMA register tiles for
+                                       the handful of windows of a single goal), 1 = DMMA always, 2 = DFMA always;
                                   [3]: 1 = tensor kernels read the coef table from global memory even when it fits in
                                        shared memory (the path models with > 4096 support vectors take) */
     int n_devices;             /* > 1: one context drives several GPUs of the box: haf_search shards its units

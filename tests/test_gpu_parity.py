@@ -260,14 +260,17 @@ def test_tensor_core_mode_synth_models_and_batch(hg, oracle_lib, tmp_models, kw)
             p.close()
 
 
+@pytest.mark.parametrize("gk", [0, 1])    # tier-2 kernel: auto (DFMA for a single goal), FP64 tensor cores (DMMA) forced
 @pytest.mark.parametrize("tier2", [0, 1, 2])
 @pytest.mark.parametrize("mode", ["tensor", "simt"])
-def test_guard_band_catches_near_zero_decisions(hg, oracle_lib, tmp_models, clouds, mode, tier2):
+def test_guard_band_catches_near_zero_decisions(hg, oracle_lib, tmp_models, clouds, mode, tier2, gk):
     """rho chosen so that many decision values sit next to 0: labels must still equal the oracle's.
     tier2 = 0: guard windows are settled by the FP64 FMA tier (none should need the exact-order kernels);
     1: FMA tier off, all of them go through the exact-order kernels; 2: both tiers run on every guard window."""
     model = tmp_models(256, rho=-0.2972253)  # a decision value of pcd2 / roll 0 with the synth model is -0.2972253033...
-    p = Pair(hg, oracle_lib, model, guard_rel=1e-3, guard_tier2=tier2,
+    if gk == 1 and tier2 == 1:
+        pytest.skip("tier 2 off: no kernel to choose")
+    p = Pair(hg, oracle_lib, model, guard_rel=1e-3, guard_tier2=tier2, guard_kernel=gk,
              svm_mode=hg.HAF_SVM_TENSOR_GUARD if mode == "tensor" else hg.HAF_SVM_FP32_GUARD)
     try:
         # tier 2 alone leaves FMA-order decision values (<= 1e-12 relative) on the guard windows; the exact-order
@@ -281,11 +284,12 @@ def test_guard_band_catches_near_zero_decisions(hg, oracle_lib, tmp_models, clou
         p.close()
 
 
-def test_guard_tier2_decision_values_match_fp64_order(hg, oracle_lib, tmp_models, clouds):
-    """With a guard band so wide that EVERY window is re-evaluated by the FP64 FMA tier, all decision values must sit
+@pytest.mark.parametrize("gk", [1, 2])    # FP64 tensor cores (DMMA: what batches use), DFMA register tiles (single goals)
+def test_guard_tier2_decision_values_match_fp64_order(hg, oracle_lib, tmp_models, clouds, gk):
+    """With a guard band so wide that EVERY window is re-evaluated by the FP64 contraction tier, all decision values must sit
     within 1e-12 * sum|coef| of the oracle's libsvm-order values (the bound tier 2's own escalation test relies on)."""
     model = tmp_models(256)
-    p = Pair(hg, oracle_lib, model, guard_rel=1e6, svm_mode=hg.HAF_SVM_TENSOR_GUARD)
+    p = Pair(hg, oracle_lib, model, guard_rel=1e6, svm_mode=hg.HAF_SVM_TENSOR_GUARD, guard_kernel=gk)
     try:
         _, _, guard = check_search(p, clouds["pcd3"], hg, oracle_lib, model, dec_rtol=1e-12)
         assert guard.all()
