@@ -1227,7 +1227,8 @@ static int run_jobs_once(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& job
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, 16 * 4, st));
 
     // ---- chunking: bound the feature matrix X (Kpad x windows) per pass
-    const size_t x_budget_floats = (size_t)3 << 28;  // 3 GiB of FP32 SVM inputs per chunk at most
+    size_t x_budget_floats = (size_t)3 << 28;  // 3 GiB of FP32 SVM inputs per chunk at most
+    if (const char* e = getenv("HAF_X_BUDGET_GIB")) { const long g = atol(e); if (g >= 1 && g <= 64) x_budget_floats = (size_t)g << 28; }   // experiments
     std::vector<std::pair<int, int> > chunks;   // [job_begin, job_end)
     {
         int jb0 = 0, stage_limit = 16;
