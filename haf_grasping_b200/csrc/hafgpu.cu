@@ -1021,9 +1021,10 @@ static int launch_guard(haf_ctx* ctx, unsigned* cnt, int G, int ubase, cudaStrea
     q.dec_tc = audit ? ctx->d_dec_tc.p : nullptr; q.audit_max = cnt + 12; q.guard_flag = audit ? ctx->d_guardflag.p : nullptr;
     const size_t smem = ((size_t)ctx->Dsv * HAF_G2_WB + HAF_G2_WB + 8 * HAF_G2_WB * 2) * sizeof(double);
     const bool few = Wcap < 65536;   // a single goal: a handful of guard windows -> spread the support vectors over more CTAs
-    // FP64 tensor cores (DMMA) for batches and for models too wide for the DFMA kernel's shared-memory tile; DFMA for the
-    // handful of windows of a single goal (a 64-window MMA tile would be mostly padding)
-    const bool dmma = ctx->tier2_kernel == 1 || (ctx->tier2_kernel == 0 && !few) || smem > 100 * 1024;
+    // FP64 tensor cores (DMMA) unless the DFMA register-tile kernel is asked for (tests; it cannot hold models wider than ~780
+    // dimensions).  Measured: 2x on the bench batch; also ahead on the 13 guard windows of a single table1 goal (64 vs 71 us),
+    // although three quarters of its 64-window tile are padding there.
+    const bool dmma = ctx->tier2_kernel != 2 || smem > 100 * 1024;
     guard_inputs_kernel<<<few ? 32 : ctx->sm_count * 4, 256, 0, st>>>(a, q);
     LAUNCHED(ctx);
     if (dmma) {
@@ -1227,7 +1228,7 @@ static int run_jobs_once(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& job
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, 16 * 4, st));
 
     // ---- chunking: bound the feature matrix X (Kpad x windows) per pass
-    size_t x_budget_floats = (size_t)3 << 28;  // 3 GiB of FP32 SVM inputs per chunk at most
+    size_t x_budget_floats = (size_t)8 << 28;  // 8 GiB of FP32 SVM inputs per chunk at most (fp16 operands: a quarter of that): the 512-cloud bench batch is ONE pass
     if (const char* e = getenv("HAF_X_BUDGET_GIB")) { const long g = atol(e); if (g >= 1 && g <= 64) x_budget_floats = (size_t)g << 28; }   // experiments
     std::vector<std::pair<int, int> > chunks;   // [job_begin, job_end)
     {
@@ -1248,7 +1249,10 @@ static int run_jobs_once(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& job
             }
             chunks.push_back(std::make_pair(jb0, je));
             jb0 = je;
-            stage_limit = std::min(256, stage_limit + stage_limit / 2);
+            // ... up to 64 clouds: the host -> device copy (PCIe, ~22 us per 100 k-point cloud) is now slower than the compute
+            // (~20 us), so what follows the last copy -- the LAST chunk's compute -- has to be short; round 1's cap of 256
+            // left 180 clouds (3.6 ms) behind the copy (bench e2e 15.1 -> ~13 ms)
+            stage_limit = std::min(64, stage_limit + stage_limit / 2);
         }
     }
     if ((out_evals || out_mask || out_heights || keep_debug_state) && chunks.size() != 1)

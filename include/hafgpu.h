@@ -67,8 +67,7 @@ typedef struct {
                                        with scalar loads;
                                   [2]: bits 0-1: guard band tier 2 (FP64 re-evaluation by contraction): 0 = on, 1 = off (every guard
                                        window goes to the exact-order kernels), 2 = on, but every window escalates as well (tests);
-                                       bits 2-3: its kernel: 0 = auto (FP64 tensor cores / DMMA for batches, DFMA register tiles for
-                                       the handful of windows of a single goal), 1 = DMMA always, 2 = DFMA always;
+                                       bits 2-3: its kernel: 0 / 1 = FP64 tensor cores (DMMA), 2 = DFMA register tiles (round 1's kernel);
                                   [3]: 1 = tensor kernels read the coef table from global memory even when it fits in
                                        shared memory (the path models with > 4096 support vectors take) */
     int n_devices;             /* > 1: one context drives several GPUs of the box: haf_search shards its units

@@ -260,7 +260,7 @@ def test_tensor_core_mode_synth_models_and_batch(hg, oracle_lib, tmp_models, kw)
             p.close()
 
 
-@pytest.mark.parametrize("gk", [0, 1])    # tier-2 kernel: auto (DFMA for a single goal), FP64 tensor cores (DMMA) forced
+@pytest.mark.parametrize("gk", [0, 2])    # tier-2 kernel: FP64 tensor cores (DMMA, the default), DFMA register tiles
 @pytest.mark.parametrize("tier2", [0, 1, 2])
 @pytest.mark.parametrize("mode", ["tensor", "simt"])
 def test_guard_band_catches_near_zero_decisions(hg, oracle_lib, tmp_models, clouds, mode, tier2, gk):
@@ -268,7 +268,7 @@ def test_guard_band_catches_near_zero_decisions(hg, oracle_lib, tmp_models, clou
     tier2 = 0: guard windows are settled by the FP64 FMA tier (none should need the exact-order kernels);
     1: FMA tier off, all of them go through the exact-order kernels; 2: both tiers run on every guard window."""
     model = tmp_models(256, rho=-0.2972253)  # a decision value of pcd2 / roll 0 with the synth model is -0.2972253033...
-    if gk == 1 and tier2 == 1:
+    if gk == 2 and tier2 == 1:
         pytest.skip("tier 2 off: no kernel to choose")
     p = Pair(hg, oracle_lib, model, guard_rel=1e-3, guard_tier2=tier2, guard_kernel=gk,
              svm_mode=hg.HAF_SVM_TENSOR_GUARD if mode == "tensor" else hg.HAF_SVM_FP32_GUARD)
