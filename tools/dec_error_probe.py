@@ -100,6 +100,15 @@ def main():
                 print("%-10s %-10s %-7s W=%d max|err|=%.3e (%.2e of sum|coef|=%.1f; max err/(E+|rho|)=%.2e, rms %.2e) guard=%d labels_equal=%s best_equal=%s min|dec| outside guard=%.3e device_ms=%.3f"
                       % (mn, cn, name, len(d), err[ng].max(), err[ng].max() / scale, scale, (err[ng] / gs[ng]).max(), np.sqrt(((err[ng] / gs[ng]) ** 2).mean()),
                          int(guard.sum()), bool((lab == l64).all()), b == b64, np.abs(d[ng]).min(), t.ms_total))
+                # distributions over the windows OUTSIDE the guard band (the ones that keep the contraction's value):
+                # err / (E + |rho|), the unit the band is stated in, and err / |dec|, the plain relative error
+                def hist(v, edges):
+                    c, _ = np.histogram(v, bins=edges)
+                    return "  ".join("<%g:%d" % (e, n) for e, n in zip(edges[1:], c))
+                rel_e = err[ng] / gs[ng]
+                rel_d = err[ng] / np.maximum(np.abs(d64[ng]), 1e-300)
+                print("    err/(E+|rho|): " + hist(rel_e, [0, 1e-9, 1e-8, 1e-7, 2e-7, 5e-7, 1e-6, 1e-5, 1]))
+                print("    err/|dec|    : " + hist(rel_d, [0, 1e-8, 1e-7, 1e-6, 1e-5, 1e-4, 1e-3, 1e-2, 1e9]) + "   max %.2e" % rel_d.max())
 
 
 if __name__ == "__main__":
