@@ -165,10 +165,12 @@ __device__ __forceinline__ void bin_points_into_units(const float (&x)[VEC], con
             // pcl::transformPointCloud, left-to-right float arithmetic, no FMA (server.cpp:488)
             const float tx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m0.x, x[k]), __fmul_rn(m0.y, y[k])), __fmul_rn(m0.z, z[k])), m0.w);
             const float ty = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m1.x, x[k]), __fmul_rn(m1.y, y[k])), __fmul_rn(m1.z, z[k])), m1.w);
-            if (tx > nr && tx < r && ty > nr && ty < r && tz[k] > -1.0f) {  // strict (server.cpp:510-511); false for NaN; `grid < z`, grid >= -1 (:515-518)
+            // -r < t < r  <=>  |t| < r, exactly (both false for NaN): strict (server.cpp:510-511); `grid < z`, grid >= -1 (:515-518)
+            if (fabsf(tx) < r && fabsf(ty) < r && tz[k] > -1.0f) {
                 int ix = (int)floorf(__fmul_rn(100.0f, __fadd_rn(tx, r)));  // :513
                 int iy = (int)floorf(__fmul_rn(100.0f, __fadd_rn(ty, r)));  // :514
-                if (ix < 0 || ix > G - 1 || iy < 0 || iy > G - 1) {
+                // t > -r makes t + r >= 0, so the indices cannot be negative; rounding can push one to G (t just below r)
+                if (max(ix, iy) > G - 1) {
                     atomicAdd(clamp_count, 1ull);
                     ix = max(0, min(G - 1, ix));
                     iy = max(0, min(G - 1, iy));

@@ -57,8 +57,11 @@ typedef struct {
                                    trips (reference-exact); -1 = skip them (NOT the reference's numbers)        */
     int svm_mode;              /* HAF_SVM_*                                                                   */
     float guard_rel;           /* guard band half-width as a fraction of E + |rho|,
-                                  E = sum_i |coef_i| K_i (1 + gamma log2(e) (|x|^2 + |sv_i|^2)); <=0 -> default
-                                  (4e-6 tensor, 2e-6 FP32 SIMT: >= 12x the measured error)                    */
+                                  E = sum_i |coef_i| K_i (1 + gamma log2(e) (|x|^2 + |sv_i|^2)); <=0 -> default:
+                                  FP32 SIMT 2e-6 (measured error <= 1.3e-7 E); tensor max(4e-6, 15 x (calibrated operand
+                                  error of the chosen number of products + 2.5e-7)) -- 8.3e-6 for the 2048-SV bench model
+                                  with one product; haf_get_info reports the value in use (reserved[1], units of 1e-9).
+                                  Every tensor-mode call audits the band against its own windows (haf_timing)   */
     int reserved[4];           /* [0]: bits 0-1: tensor-path kernel, 0 = auto (X-resident CTA pair where one product is in use, else the
                                        streaming CTA pair; both cta_group::2), 2 = streaming CTA pair always;
                                        bits 4-5: tensor-core products per k-slice, 0 = calibrated per model (default), 1 / 2 / 3 forced;
