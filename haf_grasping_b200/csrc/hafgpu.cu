@@ -616,7 +616,8 @@ static int create_impl(haf_ctx** out, const haf_config* cfg, bool svm_only, int 
         if (ctx->d_dimfeat.ensure(joined.size()) != 0) { haf_destroy(ctx); return create_fail(HAF_ERR_NOMEM, "out of device memory uploading the joined feature table"); }
         CREATE_TRY(cudaMemcpy(ctx->d_dimfeat.p, joined.data(), joined.size() * sizeof(DimFeat), cudaMemcpyHostToDevice));
         CREATE_TRY(cudaFuncSetAttribute(haftc::svm_rbf_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, haftc::SMEM2_BYTES + haftc::TAB_SMEM_MAX * 4));
-        CREATE_TRY(cudaFuncSetAttribute(haftc::svm_rbf_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, haftc::TC3_SMEM_LIMIT));
+        CREATE_TRY(cudaFuncSetAttribute(haftc::svm_rbf_tc3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, haftc::TC3_SMEM_LIMIT));
+        CREATE_TRY(cudaFuncSetAttribute(haftc::svm_rbf_tc3_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, haftc::TC3_SMEM_LIMIT));
         CREATE_TRY(cudaFuncSetAttribute(features_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ft_smem_layout(G, 2)));
         // 4 CTAs x ~49 KB: ask for just that much shared memory so that the rest of the SM's 256 KB stays L1 (the corner-offset table)
         CREATE_TRY(cudaFuncSetAttribute(features_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 90));
@@ -1103,8 +1104,12 @@ static int svm_stage(haf_ctx* ctx, unsigned* cnt, size_t Wcap, size_t ldx, int G
             int stages3 = 0;
             if (ctx->tc_variant == 0 && ctx->tc_passes == 1 && kblocks <= haftc::XK_MAX)
                 stages3 = std::min(8, (haftc::TC3_SMEM_LIMIT - haftc::tc3_smem_bytes(kblocks, 0, (int)(tab_bytes / 4))) / (haftc::KBS * haftc::B2_TILE_BYTES));
-            if (stages3 >= 2)
-                haftc::svm_rbf_tc3_kernel<<<grid2, haftc::THREADS3, haftc::tc3_smem_bytes(kblocks, stages3, (int)(tab_bytes / 4)), st>>>(
+            if (stages3 >= 2 && (tc_debug_flags() & 64))   // experiment: four epilogue warps per TMEM lane quarter
+                haftc::svm_rbf_tc3_kernel<4><<<grid2, 64 + 128 * 4, haftc::tc3_smem_bytes(kblocks, stages3, (int)(tab_bytes / 4)), st>>>(
+                    tmXh, ctx->tmSh2, ctx->d_xn.p, ctx->d_svcoef.p, ctx->c_log2, cnt + 0, n_ntiles, nsplit2, kblocks, last_slices, stages3, ctx->d_dec.p,
+                    ctx->d_asum.p, tab_smem, ctx->csvn_max, tc_debug_flags() & ~64);
+            else if (stages3 >= 2)
+                haftc::svm_rbf_tc3_kernel<2><<<grid2, haftc::THREADS3, haftc::tc3_smem_bytes(kblocks, stages3, (int)(tab_bytes / 4)), st>>>(
                     tmXh, ctx->tmSh2, ctx->d_xn.p, ctx->d_svcoef.p, ctx->c_log2, cnt + 0, n_ntiles, nsplit2, kblocks, last_slices, stages3, ctx->d_dec.p,
                     ctx->d_asum.p, tab_smem, ctx->csvn_max, tc_debug_flags());
             else
@@ -1502,12 +1507,26 @@ static int group_search(haf_ctx* ctx, const float* xyz, size_t n_points, size_t 
                         haf_best* best, haf_best* best_per_request, float* graspseval, unsigned char* mask, float* heights, int* per_roll_top);
 static int group_batch_packed(haf_ctx* ctx, const float* xyz_all, const size_t* point_offsets, int n_clouds, const haf_request* req,
                               haf_best* best_per_cloud);
+static void group_timing(haf_ctx* ctx);
+
+// one GPU: the context itself (also what each member of a multi-GPU group runs -- group[0] IS the head context, so the
+// group entry points must never be re-entered from a member thread)
+static int search_single(haf_ctx* ctx, const float* xyz, size_t n_points, size_t stride_bytes, const haf_request* reqs, int n_requests,
+                         haf_best* best, haf_best* best_per_request, float* graspseval, unsigned char* mask, float* heights, int* per_roll_top);
+static int batch_packed_single(haf_ctx* ctx, const float* xyz_all, const size_t* point_offsets, int n_clouds, const haf_request* req,
+                               haf_best* best_per_cloud);
+static int batch_single(haf_ctx* ctx, const float* const* clouds, const size_t* n_points, int n_clouds, const haf_request* req,
+                        haf_best* best_per_cloud);
 
 extern "C" int haf_search(haf_ctx* ctx, const float* xyz, size_t n_points, size_t stride_bytes, const haf_request* reqs, int n_requests,
                           haf_best* best, haf_best* best_per_request, float* graspseval, unsigned char* mask, float* heights, int* per_roll_top) {
     if (!ctx) return HAF_ERR_ARG;
     if (ctx->group.size() > 1)
         return group_search(ctx, xyz, n_points, stride_bytes, reqs, n_requests, best, best_per_request, graspseval, mask, heights, per_roll_top);
+    return search_single(ctx, xyz, n_points, stride_bytes, reqs, n_requests, best, best_per_request, graspseval, mask, heights, per_roll_top);
+}
+static int search_single(haf_ctx* ctx, const float* xyz, size_t n_points, size_t stride_bytes, const haf_request* reqs, int n_requests,
+                         haf_best* best, haf_best* best_per_request, float* graspseval, unsigned char* mask, float* heights, int* per_roll_top) {
     if (!reqs || n_requests < 1 || !best) return ctx->fail(HAF_ERR_ARG, "haf_search: reqs, n_requests >= 1 and best are required");
     if (n_points > 0 && !xyz) return ctx->fail(HAF_ERR_ARG, "haf_search: xyz is null");
     if (stride_bytes == 0) stride_bytes = 12;
@@ -1555,6 +1574,10 @@ extern "C" int haf_search_batch_packed(haf_ctx* ctx, const float* xyz_all, const
                                        haf_best* best_per_cloud) {
     if (!ctx) return HAF_ERR_ARG;
     if (ctx->group.size() > 1) return group_batch_packed(ctx, xyz_all, point_offsets, n_clouds, req, best_per_cloud);
+    return batch_packed_single(ctx, xyz_all, point_offsets, n_clouds, req, best_per_cloud);
+}
+static int batch_packed_single(haf_ctx* ctx, const float* xyz_all, const size_t* point_offsets, int n_clouds, const haf_request* req,
+                               haf_best* best_per_cloud) {
     if (!point_offsets || n_clouds < 1 || !req || !best_per_cloud) return ctx->fail(HAF_ERR_ARG, "haf_search_batch_packed: bad arguments");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     ctx->last_valid = false;
@@ -1632,13 +1655,18 @@ extern "C" int haf_search_batch(haf_ctx* ctx, const float* const* clouds, const 
         for (int k = 0; k < n; k++) {
             const int c0 = (int)((long long)n_clouds * k / n), c1 = (int)((long long)n_clouds * (k + 1) / n);
             if (c1 <= c0) continue;
-            th.emplace_back([=, &rcs]() { rcs[k] = haf_search_batch(ctx->group[k], clouds + c0, n_points + c0, c1 - c0, req, best_per_cloud + c0); });
+            th.emplace_back([=, &rcs]() { rcs[k] = batch_single(ctx->group[k], clouds + c0, n_points + c0, c1 - c0, req, best_per_cloud + c0); });
         }
         for (size_t i = 0; i < th.size(); i++) th[i].join();
         for (int k = 0; k < n; k++)
-            if (rcs[k] != HAF_OK) return ctx->fail(rcs[k], "GPU %d: %s", ctx->group[k]->device, k ? ctx->group[k]->err.c_str() : "see the first error");
+            if (rcs[k] != HAF_OK) { const std::string msg = ctx->group[k]->err; return ctx->fail(rcs[k], "GPU %d: %s", ctx->group[k]->device, msg.c_str()); }
+        group_timing(ctx);
         return HAF_OK;
     }
+    return batch_single(ctx, clouds, n_points, n_clouds, req, best_per_cloud);
+}
+static int batch_single(haf_ctx* ctx, const float* const* clouds, const size_t* n_points, int n_clouds, const haf_request* req,
+                        haf_best* best_per_cloud) {
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     std::vector<size_t> off(n_clouds + 1, 0);
     for (int c = 0; c < n_clouds; c++) off[c + 1] = off[c] + n_points[c];
@@ -1648,7 +1676,7 @@ extern "C" int haf_search_batch(haf_ctx* ctx, const float* const* clouds, const 
         if (!clouds[c]) return ctx->fail(HAF_ERR_ARG, "haf_search_batch: clouds[%d] is null", c);
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_xyz.p + off[c] * 12, clouds[c], n_points[c] * 12, cudaMemcpyDefault, ctx->stream));
     }
-    return haf_search_batch_packed(ctx, reinterpret_cast<const float*>(ctx->d_xyz.p), off.data(), n_clouds, req, best_per_cloud);
+    return batch_packed_single(ctx, reinterpret_cast<const float*>(ctx->d_xyz.p), off.data(), n_clouds, req, best_per_cloud);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1861,7 +1889,7 @@ static int group_search(haf_ctx* ctx, const float* xyz, size_t n_points, size_t 
             haf_best b0;
             std::vector<haf_best> bpr(n_requests);
             if (rc == HAF_OK)
-                rc = haf_search(m, (const float*)use, n_points, stride_bytes, rq.data(), n_requests, &b0, bpr.data(), graspseval, mask, heights, local.data());
+                rc = search_single(m, (const float*)use, n_points, stride_bytes, rq.data(), n_requests, &b0, bpr.data(), graspseval, mask, heights, local.data());
             rcs[k] = rc;
             if (rc != HAF_OK) return;
             guards[k] = m->timing.n_guard;
@@ -1875,7 +1903,7 @@ static int group_search(haf_ctx* ctx, const float* xyz, size_t n_points, size_t 
     }
     for (size_t i = 0; i < th.size(); i++) th[i].join();
     for (int k = 0; k < n; k++)
-        if (rcs[k] != HAF_OK) return ctx->fail(rcs[k], "GPU %d: %s", ctx->group[k]->device, k ? ctx->group[k]->err.c_str() : ctx->err.c_str());
+        if (rcs[k] != HAF_OK) { const std::string msg = ctx->group[k]->err; return ctx->fail(rcs[k], "GPU %d: %s", ctx->group[k]->device, msg.c_str()); }
     group_timing(ctx);
     long long n_guard = 0;
     for (int k = 0; k < n; k++) n_guard += guards[k];
@@ -1929,13 +1957,13 @@ static int group_batch_packed(haf_ctx* ctx, const float* xyz_all, const size_t* 
             const float* src = xyz_all + point_offsets[c0] * 3;
             const void* use = src;
             int rc = member_input(m, src, off[c1 - c0] * 12, &use);
-            if (rc == HAF_OK) rc = haf_search_batch_packed(m, (const float*)use, off.data(), c1 - c0, req, best_per_cloud + c0);
+            if (rc == HAF_OK) rc = batch_packed_single(m, (const float*)use, off.data(), c1 - c0, req, best_per_cloud + c0);
             rcs[k] = rc;
         });
     }
     for (size_t i = 0; i < th.size(); i++) th[i].join();
     for (int k = 0; k < n; k++)
-        if (rcs[k] != HAF_OK) return ctx->fail(rcs[k], "GPU %d: %s", ctx->group[k]->device, k ? ctx->group[k]->err.c_str() : ctx->err.c_str());
+        if (rcs[k] != HAF_OK) { const std::string msg = ctx->group[k]->err; return ctx->fail(rcs[k], "GPU %d: %s", ctx->group[k]->device, msg.c_str()); }
     group_timing(ctx);
     return HAF_OK;
 }

@@ -141,47 +141,52 @@ __global__ void __launch_bounds__(256) bin_maxz_kernel(const unsigned char* __re
 //   * VEC = 4 points per thread, fetched as three 128-bit loads where the slice is 16-byte aligned (packed xyz, stride 12):
 //     the unit loop is outermost per group of four points, so each unit's matrix rows are read from shared memory once per
 //     four points instead of once per point.
+// Round 2, second pass (ncu source view: 66 warp instructions per (point, unit), 15 % of them BSSY / BSYNC / BRA around the
+// three nested `if`s, 6 % the ordered key recomputed per unit): the per-point z work -- transformed z, its ordered key and the
+// `grid < z` test -- happens once per run of units sharing row 2, and the per-(point, unit) body is straight-line code with
+// ONE predicated tail (shared-memory bound update + RED); the index clamp is a rarely taken, almost always uniform branch.
 template <int VEC>
 __device__ __forceinline__ void bin_points_into_units(const float (&x)[VEC], const float (&y)[VEC], const float (&z)[VEC], int npts, int nu, int GG, int G,
                                                       float r, const float (*sM)[12], const int* sFlags, unsigned* s_bound,
                                                       unsigned* __restrict__ gk /*keys of unit ub*/, unsigned long long* __restrict__ clamp_count) {
-    const float nr = -r;
-    float tz[VEC];
+    unsigned keyz[VEC];   // ordered key of the transformed z; 0 = the point cannot register (`grid < z` with grid >= -1: z <= -1 or NaN, :515-518)
 #pragma unroll
-    for (int k = 0; k < VEC; k++) tz[k] = 0.0f;
+    for (int k = 0; k < VEC; k++) keyz[k] = 0u;
+    const int Gm1 = G - 1;
+    const uint32_t sb0 = (uint32_t)__cvta_generic_to_shared(s_bound);
     for (int u = 0; u < nu; u++) {
         const int fl = sFlags[u];
         if (fl & 2) {   // row 2 differs from the previous unit's (always true for the first unit)
             const float4 m2 = *reinterpret_cast<const float4*>(sM[u] + 8);
 #pragma unroll
-            for (int k = 0; k < VEC; k++)
-                tz[k] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m2.x, x[k]), __fmul_rn(m2.y, y[k])), __fmul_rn(m2.z, z[k])), m2.w);
+            for (int k = 0; k < VEC; k++) {
+                const float tz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m2.x, x[k]), __fmul_rn(m2.y, y[k])), __fmul_rn(m2.z, z[k])), m2.w);
+                keyz[k] = (k < npts && tz > -1.0f) ? fkey(tz) : 0u;
+            }
         }
         if (!(fl & 1)) continue;   // inactive unit (roll outside [roll_begin, roll_limit))
         const float4 m0 = *reinterpret_cast<const float4*>(sM[u]), m1 = *reinterpret_cast<const float4*>(sM[u] + 4);
+        const uint32_t sbu = sb0 + (uint32_t)(u * GG) * 4u;
+        unsigned* gku = gk + (size_t)u * GG;
 #pragma unroll
         for (int k = 0; k < VEC; k++) {
-            if (k >= npts) break;
             // pcl::transformPointCloud, left-to-right float arithmetic, no FMA (server.cpp:488)
             const float tx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m0.x, x[k]), __fmul_rn(m0.y, y[k])), __fmul_rn(m0.z, z[k])), m0.w);
             const float ty = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m1.x, x[k]), __fmul_rn(m1.y, y[k])), __fmul_rn(m1.z, z[k])), m1.w);
-            // -r < t < r  <=>  |t| < r, exactly (both false for NaN): strict (server.cpp:510-511); `grid < z`, grid >= -1 (:515-518)
-            if (fabsf(tx) < r && fabsf(ty) < r && tz[k] > -1.0f) {
-                int ix = (int)floorf(__fmul_rn(100.0f, __fadd_rn(tx, r)));  // :513
-                int iy = (int)floorf(__fmul_rn(100.0f, __fadd_rn(ty, r)));  // :514
-                // t > -r makes t + r >= 0, so the indices cannot be negative; rounding can push one to G (t just below r)
-                if (max(ix, iy) > G - 1) {
-                    atomicAdd(clamp_count, 1ull);
-                    ix = max(0, min(G - 1, ix));
-                    iy = max(0, min(G - 1, iy));
-                }
-                const int cell = ix * G + iy;
-                const unsigned key = fkey(tz[k]);
-                volatile unsigned* b = s_bound + u * GG + cell;
-                if (key > *b) {
-                    *b = key;
-                    atomicMax(gk + (size_t)u * GG + cell, key);
-                }
+            // -r < t < r  <=>  |t| < r, exactly (both false for NaN): strict (server.cpp:510-511)
+            const bool in = fabsf(tx) < r && fabsf(ty) < r && keyz[k] != 0u;
+            int ix = __float2int_rd(__fmul_rn(100.0f, __fadd_rn(tx, r)));  // :513  (int)floorf(.)
+            int iy = __float2int_rd(__fmul_rn(100.0f, __fadd_rn(ty, r)));  // :514
+            // t > -r makes t + r >= 0, so an index of a point inside cannot be negative; rounding can push one to G (t just below r)
+            if (in && max(ix, iy) > Gm1) atomicAdd(clamp_count, 1ull);
+            ix = min(max(ix, 0), Gm1);
+            iy = min(max(iy, 0), Gm1);
+            const int cell = ix * G + iy;
+            unsigned lb;
+            asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(lb) : "r"(sbu + (uint32_t)cell * 4u));
+            if (in && keyz[k] > lb) {
+                asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(sbu + (uint32_t)cell * 4u), "r"(keyz[k]) : "memory");
+                atomicMax(gku + cell, keyz[k]);
             }
         }
     }

@@ -412,13 +412,14 @@ __device__ __forceinline__ void tc_mma_2sm_new(uint32_t tmem_d, uint64_t adesc, 
 constexpr int XK_MAX = 8;        // k-blocks of 64 dimensions the resident X tile may have (Krow <= 512)
 constexpr int KBS = 2;           // k-blocks per ring stage
 constexpr int XS_MAX = XK_MAX / KBS;
-constexpr int THREADS3 = 320;    // TMA warp, MMA warp, 8 epilogue warps
+constexpr int THREADS3 = 320;    // TMA warp, MMA warp, 8 epilogue warps (EPQ = 2 per TMEM lane quarter); EPQ = 4: 576 threads
 constexpr int TC3_SMEM_LIMIT = 227 * 1024;
 __host__ __device__ constexpr int tc3_smem_bytes(int kblocks, int stages, int tab_entries) {
     return kblocks * A_TILE_BYTES + stages * KBS * B2_TILE_BYTES + 1024 /*align slack*/ + 512 /*barriers*/ + tab_entries * 4;
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS3, 1)
+template <int EPQ /*epilogue warps per TMEM lane quarter: each takes BN / EPQ of the accumulator's columns*/>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 128 * EPQ, 1)
 svm_rbf_tc3_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmSh2,
                    const float* __restrict__ xn, const float* __restrict__ svcoef, float c, const unsigned* __restrict__ win_count,
                    int n_ntiles, int nsplit, int kblocks, int last_slices, int stages, double* __restrict__ dec_acc, float* __restrict__ asum_acc,
@@ -437,7 +438,7 @@ svm_rbf_tc3_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_consta
     const uint32_t tmem_slot = bar_base + 288;
     const uint32_t tab_base = bar_base + 512;             // float [n_ntiles * BN] when tab_smem
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (tab_smem) stage_coef_table(tab_base, svcoef, n_ntiles * BN, THREADS3);
+    if (tab_smem) stage_coef_table(tab_base, svcoef, n_ntiles * BN, 64 + 128 * EPQ);
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
     const int xstages = (kblocks + KBS - 1) / KBS;        // ring stages per SV tile = X barrier groups
@@ -445,7 +446,7 @@ svm_rbf_tc3_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_consta
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; s++) { mbar_init(bar_sfull + 8 * s, 1); mbar_init(bar_sempty + 8 * s, 1); }
         for (int k = 0; k < XS_MAX; k++) { mbar_init(bar_xfull + 8 * k, 1); mbar_init(bar_xempty + 8 * k, 1); }
-        for (int a = 0; a < 2; a++) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 16); }   // 2 CTAs x 8 epilogue warps
+        for (int a = 0; a < 2; a++) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 2 * 4 * EPQ); }   // 2 CTAs x 4 EPQ epilogue warps
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -558,7 +559,7 @@ svm_rbf_tc3_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_consta
             if (probe && lane == 0) { unsigned long long* gp = g_tc_probe + blockIdx.x * 16; gp[4] = pc0; gp[5] = pc1; gp[6] = pc2; gp[7] = pc3; gp[8] = pc4; }
         }
     } else {  // ===== epilogue warps 2..9 (both CTAs): lane quarter q, column half h of the accumulator =====
-        const int q = warp & 3, h = (warp - 2) >> 2;
+        const int q = warp & 3, h = (warp - 2) >> 2;   // lane quarter (a warp reaches TMEM lanes 32 (warp % 4) ..), column part
         uint32_t acc_it = 0;
         const float c2 = -2.0f * c;
         for (int item = cid; item < items; item += ncl) {
@@ -578,11 +579,11 @@ svm_rbf_tc3_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_consta
                 tc_fence_after();
                 const uint32_t tab_s = tab_smem ? tab_base + (uint32_t)nt * BN * 4u : 0u;
                 float ps = 0.0f;
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * BN + h * (BN / 2);
-                if ((dbg & 13) == 0) ps = epilogue_columns<BN / 2>(taddr, tab_s, svcoef + (size_t)nt * BN, h * (BN / 2), c2);
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * BN + h * (BN / EPQ);
+                if ((dbg & 13) == 0) ps = epilogue_columns<BN / EPQ>(taddr, tab_s, svcoef + (size_t)nt * BN, h * (BN / EPQ), c2);
                 else if (dbg & 4) {   // TMEM loads only
                     uint32_t ra[32], acc = 0;
-                    for (int ch = 0; ch < BN / 64; ch++) {
+                    for (int ch = 0; ch < BN / (32 * EPQ); ch++) {
                         HAFTC_LD32(taddr + ch * 32, ra);
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
@@ -593,7 +594,7 @@ svm_rbf_tc3_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_consta
                     uint32_t ra[32];
 #pragma unroll
                     for (int jj = 0; jj < 32; jj++) ra[jj] = __float_as_uint(-(float)(jj + lane));
-                    for (int ch = 0; ch < BN / 64; ch++) { epilogue_chunk(ra, tab_s, svcoef + (size_t)nt * BN, h * (BN / 2) + ch * 32, c2, ps); ra[ch & 31] ^= __float_as_uint(ps) & 0xff; }
+                    for (int ch = 0; ch < BN / (32 * EPQ); ch++) { epilogue_chunk(ra, tab_s, svcoef + (size_t)nt * BN, h * (BN / EPQ) + ch * 32, c2, ps); ra[ch & 31] ^= __float_as_uint(ps) & 0xff; }
                 }
                 tc_fence_before();
                 __syncwarp();
