@@ -1825,6 +1825,11 @@ static int member_input(haf_ctx* m, const void* src, size_t bytes, const void** 
     if (cudaPointerGetAttributes(&a, src) != cudaSuccess) { cudaGetLastError(); return HAF_OK; }
     if (a.device == m->device) return HAF_OK;
     CUDA_TRY(m, cudaSetDevice(m->device));
+    {   // NVLink / NVSwitch peer copy instead of a bounce through host memory (already enabled: fine)
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, m->device, a.device) == cudaSuccess && can) cudaDeviceEnablePeerAccess(a.device, 0);
+        cudaGetLastError();
+    }
     ENSURE(m, m->d_xdense, (bytes + 7) / 8);   // spare buffer of this context, otherwise used by the libsvm front end only
     CUDA_TRY(m, cudaMemcpy(m->d_xdense.p, src, bytes, cudaMemcpyDefault));
     *use = m->d_xdense.p;

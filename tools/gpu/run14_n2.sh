@@ -14,4 +14,4 @@ for f in ('bench_n2','bench_group2','bench_grid512_n2'):
         d=json.load(open('gpurun_out/r2n/%s.json'%f)); print(f, d['n_gpus'], d['value'], d['ms_per_step'], d['e2e'])
     except Exception as e: print(f, 'ERR', e)
 PY
-tail -5 $o/*.err
+for f in $o/*.err; do echo == $f; tail -n 5 $f; done
