@@ -688,7 +688,7 @@ __device__ __forceinline__ void write_aug_columns(__half* __restrict__ X, size_t
 #define HAF_FT_KPASS 128  // dimensions per pass of the shared-memory tile: 256 B = two whole k-blocks of a row of Xh / Xl
 // dynamic shared memory of features_tc_kernel: fp16 tile(s) [tiles][64 windows][KPASS] + staged image rows + the pass's table records
 __host__ __device__ constexpr size_t ft_smem_layout(int G, int tiles) {
-    return (size_t)tiles * 32 * HAF_FT_WT * HAF_FT_KPASS * 2 + (size_t)HAF_FT_ROWS * (G + 1 + 31) * 4 + 16 + (size_t)HAF_FT_KPASS * 96;
+    return sizeof(Round4Tab) + (size_t)tiles * 32 * HAF_FT_WT * HAF_FT_KPASS * 2 + (size_t)HAF_FT_ROWS * (G + 1 + 31) * 4 + 16 + (size_t)HAF_FT_KPASS * 96;
 }
 __global__ void __launch_bounds__(256, 4) features_tc_kernel(const float* __restrict__ integral, const int2* __restrict__ win,
                                                              const unsigned* __restrict__ win_count, int G, int unit_base,
@@ -703,7 +703,12 @@ __global__ void __launch_bounds__(256, 4) features_tc_kernel(const float* __rest
     // reads whole chunks with LDS.128 (16 lanes = the 16 chunks of a row, XOR-permuted = all banks) and writes them with
     // STG.128: 8 dimensions per instruction.  Round 1 kept (hi | lo << 16) words and wrote 2 dimensions per STG after two LDS
     // and a PRMT, with 64-bit kt_off arithmetic per word: a quarter of the kernel's instructions (ncu r2, source view).
-    extern __shared__ __align__(16) uint32_t s_words[];  // tile(s) [1 or 2][NW][KPASS] fp16; then float s_int[ROWS][ld .. ld + 31]
+    // dynamic shared memory: the "%.4g" power-of-ten tables first (their addresses are then tile_base - constant: as a static
+    // __shared__ object the compiler re-derived the address -- S2R CgaCtaId, MOV, VIADD, LEA -- for every value, ncu r2), then the
+    // tile(s) [1 or 2][NW][KPASS] fp16, then float s_int[ROWS][ld .. ld + 31], then the pass's table records
+    extern __shared__ __align__(16) uint32_t s_dyn[];
+    static_assert(sizeof(Round4Tab) % 16 == 0, "the tile behind the tables must stay 16-byte aligned");
+    uint32_t* const s_words = s_dyn + sizeof(Round4Tab) / 4;
     const int tiles = Xl ? 2 : 1;
     constexpr int TILE_WORDS = NW * HAF_FT_KPASS / 2;
     const unsigned W = *win_count;
@@ -715,7 +720,6 @@ __global__ void __launch_bounds__(256, 4) features_tc_kernel(const float* __rest
     float* s_int = reinterpret_cast<float*>(s_words + tiles * TILE_WORDS);  // [HAF_FT_ROWS][ld .. ld + 31]
     uint4* s_tab = reinterpret_cast<uint4*>(s_words + ((tiles * TILE_WORDS + HAF_FT_ROWS * (ld + 31) + 3) & ~3));  // [KPASS] DimFeat records of the pass
     __shared__ int s_box[9];       // unit A, its first row, rows (0 = no staging), row stride of the staged image; unit B, first row, rows
-    __shared__ Round4Tab s_rt;
     int unit[WT], row[WT], col[WT];
     bool valid[WT];
 #pragma unroll
@@ -787,11 +791,12 @@ __global__ void __launch_bounds__(256, 4) features_tc_kernel(const float* __rest
         }
     }
     for (int t = threadIdx.x; t < (int)(sizeof(Round4Tab) / 8); t += blockDim.x)
-        reinterpret_cast<uint2*>(&s_rt)[t] = __ldg(reinterpret_cast<const uint2*>(rtab) + t);
+        reinterpret_cast<uint2*>(s_dyn)[t] = __ldg(reinterpret_cast<const uint2*>(rtab) + t);
     __syncthreads();
     Round4Smem rt;
-    rt.pwd = (uint32_t)__cvta_generic_to_shared(s_rt.pwd);
-    rt.pwf = (uint32_t)__cvta_generic_to_shared(s_rt.pwf);
+    rt.pwd = (uint32_t)__cvta_generic_to_shared(s_dyn);                                                  // Round4Tab::pwd at offset 0
+    asm volatile("" : "+r"(rt.pwd));   // opaque: keep the base in a register instead of re-deriving it (S2R CgaCtaId, MOV, VIADD, LEA) per value
+    rt.pwf = rt.pwd + (uint32_t)(96 * sizeof(double));                                                   // Round4Tab::pwf behind it
     const int nrows = s_box[2];
     const int sst = nrows > 0 ? s_box[3] : ld;           // row stride the corner offsets must be built for
     table += (size_t)(sst - ld) * D;                      // stride class
@@ -825,7 +830,7 @@ __global__ void __launch_bounds__(256, 4) features_tc_kernel(const float* __rest
     float nrm[WT];  // squared-norm partials of this lane's windows over the dimensions this warp evaluates
 #pragma unroll
     for (int t = 0; t < WT; t++) nrm[t] = 0.0f;
-    const uint32_t tile_base = (uint32_t)__cvta_generic_to_shared(s_words);
+    const uint32_t tile_base = rt.pwd + (uint32_t)sizeof(Round4Tab);
     const uint32_t row0 = tile_base + (uint32_t)lane * (HAF_FT_KPASS * 2), row1 = row0 + 32u * (HAF_FT_KPASS * 2);   // windows lane, 32 + lane
     const uint32_t sw = (uint32_t)(((lane & 7) << 2) | ((lane >> 3) & 3));   // swizzle of this lane's two rows (same low five bits)
     for (int d0 = 0; d0 < Krow; d0 += HAF_FT_KPASS) {
