@@ -129,8 +129,7 @@ struct haf_ctx {
     DevBuf<unsigned char> d_mask;
     DevBuf<signed char> d_labelgrid;
     DevBuf<float> d_evals;
-    DevBuf<unsigned long long> d_unit_top, d_unit_run;  // [U_total]
-    DevBuf<unsigned> d_unit_windows;                    // [U_total]
+    DevBuf<unsigned long long> d_unit_block;            // one allocation, one memset per call: unit_top [U], unit_run [U] (u64), unit_windows [U] (u32)
     DevBuf<int2> d_win;
     DevBuf<float> d_X, d_xn;
     DevBuf<double> d_dec;
@@ -756,7 +755,8 @@ static int svm_predict_impl(haf_svm* ctx, const long long* row_ptr, const int* i
         LAUNCHED(ctx);
         if (ctx->cfg.svm_mode != HAF_SVM_FP64_EXACT && !prob) {
             pack_svm_inputs_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(ctx->d_xdense.p, (int)rows, W, ctx->Krow, ctx->KB, tc ? ctx->d_Xh.p : nullptr,
-                                                                              (tc && ctx->tc_passes >= 3) ? ctx->d_Xl.p : nullptr, tc ? nullptr : ctx->d_X.p, ldx, ctx->Kpad, ctx->d_xn.p);
+                                                                              (tc && ctx->tc_passes >= 3) ? ctx->d_Xl.p : nullptr, tc ? nullptr : ctx->d_X.p, ldx, ctx->Kpad, ctx->d_xn.p,
+                                                                              tc ? ctx->d_dec.p : nullptr, tc ? ctx->d_asum.p : nullptr);
             LAUNCHED(ctx);
         }
         ctx->cur_xdense = ctx->d_xdense.p;
@@ -892,7 +892,7 @@ extern "C" void haf_destroy(haf_ctx* ctx) {
     ctx->d_sv64T.release(); ctx->d_coef64.release(); ctx->d_xyz.release(); ctx->d_ptoff.release(); ctx->d_cloud_ubegin.release();
     ctx->d_units.release(); ctx->d_jobs.release(); ctx->d_results.release(); ctx->d_per_roll_top.release(); ctx->d_keys.release();
     ctx->d_integral.release(); ctx->d_rowscan.release(); ctx->d_mask.release(); ctx->d_labelgrid.release(); ctx->d_evals.release();
-    ctx->d_unit_top.release(); ctx->d_unit_run.release(); ctx->d_unit_windows.release(); ctx->d_win.release(); ctx->d_X.release();
+    ctx->d_unit_block.release(); ctx->d_win.release(); ctx->d_X.release();
     ctx->d_xn.release(); ctx->d_dec.release(); ctx->d_guardflag.release(); ctx->d_guardlist.release(); ctx->d_kscratch.release();
     ctx->d_xdense.release(); ctx->d_labels.release(); ctx->d_probs.release(); ctx->d_probgrid.release(); ctx->d_pcd_raw.release(); ctx->d_pcd_blob.release(); ctx->d_pcd_xyz.release(); ctx->d_pcd_tiles.release(); ctx->d_pcd_words.release(); ctx->d_csr_ptr.release(); ctx->d_csr_idx.release(); ctx->d_csr_val.release();
     ctx->d_svn64.release(); ctx->d_Xg.release(); ctx->d_xn64.release(); ctx->d_g2accum.release(); ctx->d_g2tickets.release(); ctx->d_guardlist2.release();
@@ -1026,11 +1026,15 @@ static int launch_guard(haf_ctx* ctx, unsigned* cnt, int G, int ubase, cudaStrea
     // dimensions).  Measured: 2x on the bench batch; also ahead on the 13 guard windows of a single table1 goal (64 vs 71 us),
     // although three quarters of its 64-window tile are padding there.
     const bool dmma = ctx->tier2_kernel != 2 || smem > 100 * 1024;
-    guard_inputs_kernel<<<few ? 32 : ctx->sm_count * 4, 256, 0, st>>>(a, q);
-    LAUNCHED(ctx);
-    if (dmma) {
-        guard_norms_kernel<<<few ? 8 : ctx->sm_count, 256, 0, st>>>(q);
+    if (few) {
+        guard_inputs_flat_kernel<<<32, 256, 0, st>>>(a, q);
         LAUNCHED(ctx);
+        if (dmma) { guard_norms_kernel<<<8, 256, 0, st>>>(q); LAUNCHED(ctx); }
+    } else {
+        guard_inputs_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(a, q);
+        LAUNCHED(ctx);
+    }
+    if (dmma) {
         guard_dmma_kernel<<<(unsigned)ctx->sm_count * 2, 256, HAF_GD_SMEM_BYTES, st>>>(a, q, ctx->Spad / HAF_GD_SB);
     }
     // one CTA per SM walks (window group, SV slice) items; a single goal's handful of windows: slices of 256 SVs over more CTAs
@@ -1073,8 +1077,7 @@ static int svm_stage(haf_ctx* ctx, unsigned* cnt, size_t Wcap, size_t ldx, int G
         const bool need_lo = ctx->tc_passes >= 3;   // X_lo takes part in the third product only
         if (!make_tensor_map(&tmXh, ctx->d_Xh.p, ctx->KB, ldx) || !make_tensor_map(&tmXl, need_lo ? ctx->d_Xl.p : ctx->d_Xh.p, ctx->KB, ldx))
             return ctx->fail(HAF_ERR_CUDA, "cuTensorMapEncodeTiled failed for the window operands");
-        CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_dec.p, 0, ldx * sizeof(double), st));
-        CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_asum.p, 0, ldx * sizeof(float), st));
+        // (the accumulators d_dec / d_asum were zeroed by the kernel that wrote the operand rows: features_tc_kernel / pack_svm_inputs_kernel)
         const int n_ntiles = ctx->SpadT / haftc::BN;
         const int mt_cap = (int)(ldx / haftc::BM);
         int nsplit = 1;
@@ -1212,7 +1215,10 @@ static int run_jobs_once(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& job
         }
     }
     ENSURE(ctx, ctx->d_params, o_ub + bytes_ub + 16); ENSURE(ctx, ctx->d_results, n_jobs); ENSURE(ctx, ctx->d_per_roll_top, (size_t)U * 3);
-    ENSURE(ctx, ctx->d_unit_top, U); ENSURE(ctx, ctx->d_unit_run, U); ENSURE(ctx, ctx->d_unit_windows, U);
+    ENSURE(ctx, ctx->d_unit_block, (size_t)2 * U + (U + 1) / 2);
+    unsigned long long* const d_unit_top = ctx->d_unit_block.p;
+    unsigned long long* const d_unit_run = d_unit_top + U;
+    unsigned* const d_unit_windows = reinterpret_cast<unsigned*>(d_unit_run + U);
     ENSURE(ctx, ctx->h_results, n_jobs); ENSURE(ctx, ctx->h_per_roll_top, (size_t)U * 3);
     // The parameter block goes up with a tiny kernel that reads the pinned staging buffer directly (UVA), NOT with a
     // copy-engine memcpy: the H2D engine is a FIFO, and behind a large staging copy of clouds (this call's, or any other
@@ -1227,9 +1233,7 @@ static int run_jobs_once(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& job
     JobParams* const d_jobs = reinterpret_cast<JobParams*>(ctx->d_params.p + o_jobs);
     long long* const d_ptoff = reinterpret_cast<long long*>(ctx->d_params.p + o_off);
     int* const d_cloud_ubegin = reinterpret_cast<int*>(ctx->d_params.p + o_ub);
-    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_unit_top.p, 0, (size_t)U * 8, st));
-    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_unit_run.p, 0, (size_t)U * 8, st));
-    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_unit_windows.p, 0, (size_t)U * 4, st));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_unit_block.p, 0, ((size_t)2 * U + (U + 1) / 2) * 8, st));
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, 16 * 4, st));
 
     // ---- chunking: bound the feature matrix X (Kpad x windows) per pass
@@ -1323,8 +1327,19 @@ static int run_jobs_once(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& job
                 int max_units_per_cloud = 0;
                 for (int c = c0; c < c1; c++) max_units_per_cloud = std::max(max_units_per_cloud, hub[c + 1] - hub[c]);
                 const int ug = std::min(upg, std::max(1, max_units_per_cloud));
-                // measured: the kernel is instruction-bound once the REDs are filtered; 1 slice at 256 clouds, 2-4 at 64
-                const int slices = std::max(1, std::min(8, (3 * ctx->sm_count / 2 + (c1 - c0) - 1) / (c1 - c0)));
+                // the kernel is instruction-bound once the REDs are filtered, one 1024-thread CTA per SM: what matters is that the
+                // CTAs (clouds x unit groups x slices) fill whole waves of the SMs.  Smallest slice count <= 12 within 2 % of the best
+                // wave efficiency (512 clouds: 2 slices = 6.92 waves -> 7, 99 %, instead of 3.46 -> 4, 86 %)
+                int slices = 1;
+                {
+                    const long long groups = (long long)(c1 - c0) * ((max_units_per_cloud + ug - 1) / ug);
+                    double best_eff = 0.0;
+                    for (int sl = 1; sl <= 12; sl++) {
+                        const double waves = (double)(groups * sl) / ctx->sm_count;
+                        const double eff = waves / std::ceil(waves);
+                        if (eff > best_eff + 0.02) { best_eff = eff; slices = sl; }
+                    }
+                }
                 dim3 gridc((unsigned)(c1 - c0), (unsigned)((max_units_per_cloud + ug - 1) / ug), (unsigned)slices);
                 if (cs.stride == 12 && ctx->cfg.reserved[1] != 2)
                     bin_maxz_cloud_kernel<4><<<gridc, 1024, (size_t)ug * GG * 4, st>>>(cs.d_xyz, cs.stride, d_ptoff + c0, d_cloud_ubegin + c0, d_units,
@@ -1361,7 +1376,7 @@ static int run_jobs_once(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& job
         // 3. mask + window compaction
         if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[ci * 8 + 2], st));
         mask_windows_kernel<<<dim3((GG + 4095) / 4096, Uc), 256, 0, st>>>(ctx->d_integral.p, units_c, G, ctx->d_mask.p, ctx->d_labelgrid.p,
-                                                                         ctx->d_win.p, cnt + 0, (unsigned)Wcap, (int*)(cnt + 2), ubase, ctx->d_unit_windows.p + ubase);
+                                                                         ctx->d_win.p, cnt + 0, (unsigned)Wcap, (int*)(cnt + 2), ubase, d_unit_windows + ubase);
         LAUNCHED(ctx);
         // 4. features -> scaled SVM inputs
         if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[ci * 8 + 3], st));
@@ -1370,7 +1385,7 @@ static int run_jobs_once(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& job
             const unsigned fblocks = (unsigned)((Wcap + 32 * HAF_FT_WT - 1) / (32 * HAF_FT_WT));
             features_tc_kernel<<<fblocks, 256, ft_smem_bytes(ctx), st>>>(ctx->d_integral.p, ctx->d_win.p, cnt + 0, G, ubase, ctx->d_dimfeat.p, ctx->D,
                                                                       ctx->Krow, (float)ctx->lower, ctx->cfg.emulate_text_roundtrip, ctx->d_round4.p, ctx->d_Xh.p,
-                                                                      ctx->tc_passes >= 3 ? ctx->d_Xl.p : nullptr, ctx->d_xn.p, ctx->Dsv, ctx->KB);
+                                                                      ctx->tc_passes >= 3 ? ctx->d_Xl.p : nullptr, ctx->d_xn.p, ctx->Dsv, ctx->KB, ctx->d_dec.p, ctx->d_asum.p);
             LAUNCHED(ctx);
         } else if (ctx->cfg.svm_mode != HAF_SVM_FP64_EXACT && !prob) {
             features_kernel<false><<<wblocks32, 256, 0, st>>>(ctx->d_integral.p, ctx->d_win.p, cnt + 0, G, ubase, ctx->d_feats.p, ctx->d_dims.p,
@@ -1391,16 +1406,16 @@ static int run_jobs_once(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& job
             LAUNCHED(ctx);
             prob_shift_grid_kernel<<<Uc, 1024, 0, st>>>(ctx->d_mask.p, ctx->d_evals.p, G, units_c, ctx->prob_header_val, ctx->d_probgrid.p);
             LAUNCHED(ctx);
-            score_prob_kernel<<<dim3((GG + 255) / 256, Uc), 256, 0, st>>>(ctx->d_probgrid.p, G, units_c, ctx->d_evals.p, ctx->d_unit_top.p + ubase);
+            score_prob_kernel<<<dim3((GG + 255) / 256, Uc), 256, 0, st>>>(ctx->d_probgrid.p, G, units_c, ctx->d_evals.p, d_unit_top + ubase);
             LAUNCHED(ctx);
         } else {
             label_scatter_kernel<<<(unsigned)((Wcap + 255) / 256), 256, 0, st>>>(ctx->d_dec.p, ctx->d_win.p, cnt + 0, G, ubase, ctx->gv[0], ctx->gv[1],
                                                                                 ctx->d_labelgrid.p);
             LAUNCHED(ctx);
-            score_kernel<<<dim3((GG + 255) / 256, Uc), 256, 0, st>>>(ctx->d_labelgrid.p, G, units_c, ctx->d_evals.p, ctx->d_unit_top.p + ubase);
+            score_kernel<<<dim3((GG + 255) / 256, Uc), 256, 0, st>>>(ctx->d_labelgrid.p, G, units_c, ctx->d_evals.p, d_unit_top + ubase);
             LAUNCHED(ctx);
         }
-        tie_rule_kernel<<<dim3((G + 7) / 8, Uc), 256, 0, st>>>(ctx->d_evals.p, G, units_c, ctx->d_unit_top.p + ubase, ctx->d_unit_run.p + ubase);
+        tie_rule_kernel<<<dim3((G + 7) / 8, Uc), 256, 0, st>>>(ctx->d_evals.p, G, units_c, d_unit_top + ubase, d_unit_run + ubase);
         LAUNCHED(ctx);
         if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_pool[ci * 8 + 7], st));
 
@@ -1422,7 +1437,7 @@ static int run_jobs_once(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& job
         }
     }
     // 7. cross-roll reduction per job, results to pinned host memory
-    reduce_rolls_kernel<<<(n_jobs + 127) / 128, 128, 0, st>>>(ctx->d_unit_top.p, ctx->d_unit_run.p, ctx->d_unit_windows.p, d_jobs, n_jobs, R, G,
+    reduce_rolls_kernel<<<(n_jobs + 127) / 128, 128, 0, st>>>(d_unit_top, d_unit_run, d_unit_windows, d_jobs, n_jobs, R, G,
                                                              ctx->d_per_roll_top.p, ctx->d_results.p);
     LAUNCHED(ctx);
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_results.p, ctx->d_results.p, (size_t)n_jobs * sizeof(JobResult), cudaMemcpyDeviceToHost, st));
@@ -1430,7 +1445,7 @@ static int run_jobs_once(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& job
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_counters.p, ctx->d_counters.p, 16 * 4, cudaMemcpyDeviceToHost, st));
     if (keep_debug_state) {   // single goals: windows per unit, for the multi-GPU merge
         ENSURE(ctx, ctx->h_unit_windows, U);
-        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_unit_windows.p, ctx->d_unit_windows.p, (size_t)U * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_unit_windows.p, d_unit_windows, (size_t)U * 4, cudaMemcpyDeviceToHost, st));
     }
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[9], st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));

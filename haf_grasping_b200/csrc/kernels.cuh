@@ -695,7 +695,8 @@ __global__ void __launch_bounds__(256, 4) features_tc_kernel(const float* __rest
                                                              const DimFeat* __restrict__ table, int D, int Krow, float lower,
                                                              int emulate_text, const Round4Tab* __restrict__ rtab,
                                                              __half* __restrict__ Xh, __half* __restrict__ Xl /*NULL: hi only*/, float* __restrict__ xn,
-                                                             int aug0 /*first of the six extra operand columns (svm_tc.cuh)*/, int KB /*k-blocks of the tiled layout*/) {
+                                                             int aug0 /*first of the six extra operand columns (svm_tc.cuh)*/, int KB /*k-blocks of the tiled layout*/,
+                                                             double* __restrict__ dec_acc, float* __restrict__ asum_acc /*the contraction's accumulators: zeroed here*/) {
     constexpr int WT = HAF_FT_WT, NW = 32 * WT;
     // TILE.  fp16 values [window][KPASS dims] = 256-byte rows of sixteen 16-byte chunks, swizzled so that BOTH sides are free of
     // bank conflicts: element (w, d) sits in chunk (d >> 3) ^ (w & 7), word ((d & 7) >> 1) ^ ((w >> 3) & 3) of its row.  A compute
@@ -919,6 +920,8 @@ __global__ void __launch_bounds__(256, 4) features_tc_kernel(const float* __rest
         // -|x|^2 / 2 has to fit the fp16 extra columns as well (|x|^2 / 2 <= 65504)
         const bool ok = sq < 1.3e5f;
         xn[w0 + threadIdx.x] = ok ? sq : __int_as_float(0x7f800000);
+        dec_acc[w0 + threadIdx.x] = 0.0;
+        asum_acc[w0 + threadIdx.x] = 0.0f;
         write_aug_columns(Xh, w0 + threadIdx.x, aug0, KB, ok ? sq : 0.0f, ok);
     }
 }
@@ -1237,7 +1240,9 @@ struct Guard2Args {
     unsigned* audit_max;         // audit: max over listed windows of |dec_tc - dec_fp64| / (E + |rho|), as float bits
     const unsigned char* guard_flag;   // [W] 1 = inside the guard band; listed windows with 0 are the audit sample: measured, not rewritten
 };
-__global__ void __launch_bounds__(256) guard_inputs_kernel(const ExactArgs A, const Guard2Args Q) {
+// a single goal's handful of guard windows: one THREAD per element (a warp per row would leave most of the GPU idle while
+// each lane walks 11 text-emulated values), |x|^2 in a second small kernel
+__global__ void __launch_bounds__(256) guard_inputs_flat_kernel(const ExactArgs A, const Guard2Args Q) {
     const unsigned n = min(*Q.list_count, (unsigned)Q.cap);
     const size_t total = (size_t)n * Q.ldx;
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
@@ -1246,13 +1251,29 @@ __global__ void __launch_bounds__(256) guard_inputs_kernel(const ExactArgs A, co
         Q.Xg[t] = d < A.D ? exact_scaled_input(A, Q.list[e], d) : 0.0;
     }
 }
-// |x|^2 of every listed row, one warp per row
 __global__ void __launch_bounds__(256) guard_norms_kernel(const Guard2Args Q) {
     const unsigned n = min(*Q.list_count, (unsigned)Q.cap);
     const int lane = threadIdx.x & 31;
     for (unsigned e = blockIdx.x * 8 + (threadIdx.x >> 5); e < n; e += gridDim.x * 8) {
         double sq = 0.0;
         for (int d = lane; d < Q.ldx; d += 32) { const double v = Q.Xg[(size_t)e * Q.ldx + d]; sq = fma(v, v, sq); }
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        if (lane == 0) Q.xn64[e] = sq;
+    }
+}
+// batches: one warp per listed row: its exact inputs (columns >= D zero up to ldx) and |x|^2 (for the DMMA kernel)
+__global__ void __launch_bounds__(256) guard_inputs_kernel(const ExactArgs A, const Guard2Args Q) {
+    const unsigned n = min(*Q.list_count, (unsigned)Q.cap);
+    const int lane = threadIdx.x & 31;
+    for (unsigned e = blockIdx.x * 8 + (threadIdx.x >> 5); e < n; e += gridDim.x * 8) {
+        const int w = Q.list[e];
+        double sq = 0.0;
+        for (int d = lane; d < Q.ldx; d += 32) {
+            const double v = d < A.D ? exact_scaled_input(A, w, d) : 0.0;
+            Q.Xg[(size_t)e * Q.ldx + d] = v;
+            sq = fma(v, v, sq);
+        }
 #pragma unroll
         for (int o = 16; o >= 1; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
         if (lane == 0) Q.xn64[e] = sq;
@@ -1724,7 +1745,7 @@ __global__ void csr_to_dense_kernel(const long long* __restrict__ row_ptr, const
 // SIMT mode (Xf != NULL): feature-major floats [Kpad][ldx] + ||x||^2.  One warp per row.
 __global__ void __launch_bounds__(256) pack_svm_inputs_kernel(const double* __restrict__ dense, int n_rows, int width, int Krow, int KB,
                                                               __half* __restrict__ Xh, __half* __restrict__ Xl /*NULL: hi only*/, float* __restrict__ Xf,
-                                                              size_t ldx, int Kpad, float* __restrict__ xn) {
+                                                              size_t ldx, int Kpad, float* __restrict__ xn, double* __restrict__ dec_acc, float* __restrict__ asum_acc) {
     const int lane = threadIdx.x & 31;
     const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (r >= n_rows) return;
@@ -1752,6 +1773,7 @@ __global__ void __launch_bounds__(256) pack_svm_inputs_kernel(const double* __re
     if (lane == 0) {
         const bool ok = !Xh || sq < 1.3e5f;
         xn[r] = ok ? sq : __int_as_float(0x7f800000);
+        if (dec_acc) { dec_acc[r] = 0.0; asum_acc[r] = 0.0f; }   // the tensor contraction accumulates into them
         if (Xh) write_aug_columns(Xh, (size_t)r, width, KB, ok ? sq : 0.0f, ok);   // extra operand columns (svm_tc.cuh)
     }
 }

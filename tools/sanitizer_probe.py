@@ -29,6 +29,35 @@ def main():
             t = g.timing()
             print("mode", mode, "tier2", tier2, "best", res["best"].astuple(), [b.astuple() for b in best], "guard", t.n_guard, "exact", t.n_exact)
             g.close()
+    # round 2: DFMA guard kernel (the DMMA one is the default above), probability mode, device PCD / PointCloud2 ingest
+    g = h.GraspSearch(F, R, model, guard_rel=1e-3, guard_kernel=2)
+    print("dfma guard", g.search(clouds[0])["best"].astuple(), g.timing().n_guard)
+    g.close()
+    pm = os.path.join(tmp, "p.model")
+    with open(model) as fh:
+        head, tail = fh.read().split("nr_sv", 1)
+    with open(pm, "w") as fh:
+        fh.write(head + "probA -2.5\nprobB 0.1\nnr_sv" + tail)
+    g = h.GraspSearch(F, R, pm)
+    print("probability", g.search(clouds[1], [h.make_request(svm_with_probability=1)])["best"].astuple())
+    xyz = clouds[2]
+    hdr = ("# .PCD v0.7\nVERSION 0.7\nFIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\nWIDTH %d\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS %d\nDATA %s\n")
+    ascii_pcd = (hdr % (len(xyz), len(xyz), "ascii")).encode() + "".join("%.9g %.9g %.9g\n" % tuple(p) for p in xyz).encode()
+    bin_pcd = (hdr % (len(xyz), len(xyz), "binary")).encode() + xyz.tobytes()
+    for name, raw in (("ascii", ascii_pcd), ("binary", bin_pcd)):
+        got = g.pcd_decode_to_host(raw)
+        print("pcd", name, bool((got == xyz).all()), g.search_pcd(raw)["best"].astuple())
+    z = np.load(os.path.join(ROOT, "tests", "golden", "pcd_files.npz"))
+    print("pcd lzf", g.pcd_decode(z["table3"].tobytes())[1])
+    buf = np.zeros((len(xyz), 16), np.uint8)
+    buf[:, :12] = xyz.view(np.uint8).reshape(len(xyz), 12)
+    g.pointcloud2_to_xyz(buf, len(xyz), 16)
+    print("pc2", bool((g.debug_pcd_xyz(len(xyz)) == xyz).all()))
+    g.close()
+    p = h.SvmPredictor(pm, min_dims=330)
+    rngp = np.random.default_rng(2)
+    print("svm prob", p.predict_probability(rngp.uniform(-1, 1, size=(300, 330)))[1][:2].tolist())
+    p.close()
     rng = np.random.default_rng(1)
     x = rng.uniform(-1, 1, size=(700, 330)) * (rng.random((700, 330)) < 0.8)
     for mode in (0, 2, 1):
