@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--bin-variant", type=int, default=0, help="binning: 0 auto, 1 point-parallel kernel only, 2 whole-cloud kernel with scalar loads")
     ap.add_argument("--svm-mode", type=int, default=0, help="0 tcgen05 split-fp16 + FP64 guard (default), 1 FP64 exact, 2 FP32 SIMT + guard")
     ap.add_argument("--guard-kernel", type=int, default=0, help="guard band tier 2: 0 auto, 1 FP64 tensor cores (DMMA) always, 2 DFMA always")
+    ap.add_argument("--graph", type=int, default=0, help="1 = capture / replay one CUDA graph per request shape (single-pass calls)")
     ap.add_argument("--group", type=int, default=1, help="ONE process driving this many GPUs through the C ABI's multi-GPU context (haf_config.n_devices): "
                                                          "the path a C++ host takes; --clouds is per GPU; timed by wall clock (the member GPUs run on their own streams)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -417,7 +418,7 @@ def run_ours(args):
     gs = h.GraspSearch(FEATURES, RANGE, model, grid=wc["grid"], roll_step_deg=wc["step"], roll_max_deg=wc["rmax"],
                        device=local, svm_mode=args.svm_mode, sv_table_global=args.sv_table_global, tc_passes=args.tc_passes,
                        tc_variant=args.tc_variant, bin_variant=args.bin_variant, devices=list(range(group)) if group > 1 else None,
-                       guard_kernel=args.guard_kernel)
+                       guard_kernel=args.guard_kernel, use_graph=bool(args.graph))
     stream = torch.cuda.current_stream()
     gs.set_stream(stream.cuda_stream)
     gs.set_profiling(True)

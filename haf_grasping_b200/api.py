@@ -58,7 +58,7 @@ class haf_timing(C.Structure):
                 ("n_points", C.c_longlong), ("n_units", C.c_longlong), ("n_windows", C.c_longlong),
                 ("n_guard", C.c_longlong), ("launches", C.c_longlong), ("n_chunks", C.c_longlong),
                 ("n_exact", C.c_longlong), ("n_audit", C.c_longlong), ("audit_max_rel", C.c_float), ("tc_passes", C.c_int),
-                ("escalations", C.c_int), ("reserved", C.c_int)]
+                ("escalations", C.c_int), ("graph_replays", C.c_int)]
 
 
 EXPORTS = ["haf_create", "haf_destroy", "haf_last_error", "haf_get_info", "haf_set_stream", "haf_set_profiling",
@@ -166,7 +166,7 @@ class GraspSearch:
     def __init__(self, features_path, range_path, model_path, grid=56, roll_step_deg=15, roll_max_deg=190,
                  nr_features_without_shaf=302, device=0, emulate_text_roundtrip=True, svm_mode=HAF_SVM_TENSOR_GUARD,
                  guard_rel=0.0, tc_variant=0, guard_tier2=0, sv_table_global=0, tc_passes=0, audit_every=None, bin_variant=0,
-                 devices=None, guard_kernel=0):
+                 devices=None, guard_kernel=0, use_graph=False):
         self.L = load_library()
         cfg = haf_config()
         self._keep = [features_path.encode(), range_path.encode(), model_path.encode()]
@@ -182,7 +182,8 @@ class GraspSearch:
         cfg.reserved[0] = tc_variant | (tc_passes << 4)
         if audit_every is not None:
             cfg.reserved[0] |= 0x100 if audit_every == 0 else (int(audit_every) << 16)
-        cfg.reserved[1] = bin_variant   # 0 auto, 1 point-parallel binning only, 2 whole-cloud kernel with scalar loads
+        # bin_variant: 0 auto, 1 point-parallel binning only, 2 whole-cloud kernel with scalar loads; bit 4: CUDA graph capture / replay
+        cfg.reserved[1] = bin_variant | (16 if use_graph else 0)
         # guard_tier2: 0 on, 1 off, 2 on + escalate everything (tests); guard_kernel: 0 auto, 1 FP64 tensor cores (DMMA), 2 DFMA
         cfg.reserved[2] = guard_tier2 | (guard_kernel << 2)
         cfg.reserved[3] = sv_table_global   # 1: SV table read from global memory (the > 4096-SV path)

@@ -26,12 +26,15 @@ static thread_local std::string g_create_error;
 
 namespace {
 
+// every (re)allocation moves this on: a captured CUDA graph bakes the buffers' addresses in and is only replayed while it stands
+static unsigned long long g_alloc_epoch = 0;
 template <typename T>
 struct DevBuf {
     T* p = nullptr;
     size_t cap = 0;  // elements
     int ensure(size_t n) {
         if (n <= cap) return 0;
+        g_alloc_epoch++;
         if (p) cudaFree(p);
         p = nullptr; cap = 0;
         size_t want = n + n / 8 + 256;
@@ -47,6 +50,7 @@ struct PinBuf {
     size_t cap = 0;
     int ensure(size_t n) {
         if (n <= cap) return 0;
+        g_alloc_epoch++;
         if (p) cudaFreeHost(p);
         p = nullptr; cap = 0;
         size_t want = n + n / 8 + 64;
@@ -147,6 +151,24 @@ struct haf_ctx {
     PinBuf<JobResult> h_results;
     PinBuf<int> h_per_roll_top;
     PinBuf<unsigned> h_counters;
+
+    // ONE CUDA GRAPH PER REQUEST SHAPE (SURVEY 7 "hard parts"; server.cpp:335-402 is one goal = ~25 dependent stream operations of a
+    // few microseconds each).  A call that fits one pass and repeats the shape of the previous one (same unit / window bounds,
+    // same buffers, same kernel choices -- GraphKey) is captured once and then replayed with cudaGraphLaunch; the request itself
+    // travels through the pinned parameter block, which the graph's first node reads afresh.  graph_mode: 0 on, 1 off (the default).
+    struct GraphKey {
+        unsigned long long epoch; const void* xyz; size_t stride, wcap; long long pts_bucket; int n_jobs, n_clouds, flags, tc_passes;
+        const void *o_evals, *o_mask, *o_heights; unsigned long long rolls_hash; cudaStream_t st;
+        bool operator==(const GraphKey& o) const { return memcmp(this, &o, sizeof *this) == 0; }
+    };
+    GraphKey graph_key, graph_seen;
+    bool graph_valid = false, graph_seen_valid = false;
+    cudaGraphExec_t graph_exec = nullptr;
+    long long graph_nodes = 0, graph_replays = 0;
+    int graph_mode = 0;
+    cudaStream_t own_stream = nullptr;     // capture is not allowed on the legacy default stream: a blocking stream of our own stands in
+    PinBuf<float> h_out_evals, h_out_heights;   // per-roll outputs asked for in HOST memory go through pinned staging (graph-capturable)
+    PinBuf<unsigned char> h_out_mask;
 
     // probability estimates: the model's sigmoid (svm.cpp:2811-2824); probability calls evaluate EVERY row /
     // window on the FP64 exact-order path (force_exact), whatever svm_mode the context was made with
@@ -494,6 +516,10 @@ static int create_impl(haf_ctx** out, const haf_config* cfg, bool svm_only, int 
     CREATE_TRY(cudaMemcpy(ctx->d_sv64T.p, sv64T.data(), sv64T.size() * sizeof(double), cudaMemcpyHostToDevice));
     CREATE_TRY(cudaMemcpy(ctx->d_coef64.p, coef64.data(), Spad * sizeof(double), cudaMemcpyHostToDevice));
     CREATE_TRY(cudaMemcpy(ctx->d_svn64.p, svn64.data(), Spad * sizeof(double), cudaMemcpyHostToDevice));
+    // CUDA graphs are opt-in (cfg.reserved[1] bit 4 or HAF_GRAPH=1): measured, replay buys nothing here -- one table1 goal takes 0.267 ms
+    // replayed against 0.268 ms launched (profiles/README.md): the goal is bound by the latencies of its ~20 dependent kernels, not by
+    // launch overhead -- so the plain path stays the default
+    ctx->graph_mode = ((cfg->reserved[1] & 16) || (getenv("HAF_GRAPH") && atoi(getenv("HAF_GRAPH")))) ? 0 : 1;
     ctx->tier2_mode = cfg->reserved[2] & 3;
     ctx->tier2_kernel = (cfg->reserved[2] >> 2) & 3;
     CREATE_TRY(cudaFuncSetAttribute(guard_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HAF_GD_SMEM_BYTES));
@@ -898,6 +924,9 @@ extern "C" void haf_destroy(haf_ctx* ctx) {
     ctx->d_svn64.release(); ctx->d_Xg.release(); ctx->d_xn64.release(); ctx->d_g2accum.release(); ctx->d_g2tickets.release(); ctx->d_guardlist2.release();
     ctx->d_SVh.release(); ctx->d_SVl.release(); ctx->d_Xh.release(); ctx->d_Xl.release(); ctx->d_svcoef.release(); ctx->d_dec_tc.release(); ctx->d_asum.release(); ctx->d_dimfeat.release(); ctx->d_round4.release();
     ctx->d_params.release(); ctx->d_counters.release(); ctx->h_stage.release(); ctx->h_results.release(); ctx->h_per_roll_top.release(); ctx->h_counters.release(); ctx->h_unit_windows.release();
+    if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    ctx->h_out_evals.release(); ctx->h_out_heights.release(); ctx->h_out_mask.release();
     if (ctx->ev_ok) for (int i = 0; i < 10; i++) cudaEventDestroy(ctx->ev[i]);
     for (size_t i = 0; i < ctx->ev_pool.size(); i++) cudaEventDestroy(ctx->ev_pool[i]);
     for (size_t i = 0; i < ctx->copy_ev.size(); i++) cudaEventDestroy(ctx->copy_ev[i]);
@@ -1149,7 +1178,7 @@ static int run_jobs_once(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& job
     const int G = ctx->G, R = ctx->R, GG = G * G, ld = G + 1;
     const int n_jobs = (int)jobs.size();
     const int n_clouds = (int)cs.off.size() - 1;
-    cudaStream_t st = ctx->stream;
+    cudaStream_t st = ctx->stream;   // (replaced by a stream of our own when the call may be captured into a graph and this is the legacy stream)
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     const long long launches0 = ctx->launches;
 
@@ -1214,28 +1243,6 @@ static int run_jobs_once(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& job
             up.job = j; up.roll = roll;
         }
     }
-    ENSURE(ctx, ctx->d_params, o_ub + bytes_ub + 16); ENSURE(ctx, ctx->d_results, n_jobs); ENSURE(ctx, ctx->d_per_roll_top, (size_t)U * 3);
-    ENSURE(ctx, ctx->d_unit_block, (size_t)2 * U + (U + 1) / 2);
-    unsigned long long* const d_unit_top = ctx->d_unit_block.p;
-    unsigned long long* const d_unit_run = d_unit_top + U;
-    unsigned* const d_unit_windows = reinterpret_cast<unsigned*>(d_unit_run + U);
-    ENSURE(ctx, ctx->h_results, n_jobs); ENSURE(ctx, ctx->h_per_roll_top, (size_t)U * 3);
-    // The parameter block goes up with a tiny kernel that reads the pinned staging buffer directly (UVA), NOT with a
-    // copy-engine memcpy: the H2D engine is a FIFO, and behind a large staging copy of clouds (this call's, or any other
-    // stream's) a small memcpy would stall every kernel of the call until that copy has finished.
-    {
-        const size_t n16 = (o_ub + bytes_ub + 15) / 16;
-        copy_params_kernel<<<(unsigned)std::min<size_t>((n16 + 255) / 256, 1024), 256, 0, st>>>(reinterpret_cast<const uint4*>(ctx->h_stage.p),
-                                                                                              reinterpret_cast<uint4*>(ctx->d_params.p), n16);
-        LAUNCHED(ctx);
-    }
-    UnitParams* const d_units = reinterpret_cast<UnitParams*>(ctx->d_params.p + o_units);
-    JobParams* const d_jobs = reinterpret_cast<JobParams*>(ctx->d_params.p + o_jobs);
-    long long* const d_ptoff = reinterpret_cast<long long*>(ctx->d_params.p + o_off);
-    int* const d_cloud_ubegin = reinterpret_cast<int*>(ctx->d_params.p + o_ub);
-    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_unit_block.p, 0, ((size_t)2 * U + (U + 1) / 2) * 8, st));
-    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, 16 * 4, st));
-
     // ---- chunking: bound the feature matrix X (Kpad x windows) per pass
     size_t x_budget_floats = (size_t)8 << 28;  // 8 GiB of FP32 SVM inputs per chunk at most (fp16 operands: a quarter of that): the 512-cloud bench batch is ONE pass
     if (const char* e = getenv("HAF_X_BUDGET_GIB")) { const long g = atol(e); if (g >= 1 && g <= 64) x_budget_floats = (size_t)g << 28; }   // experiments
@@ -1267,6 +1274,20 @@ static int run_jobs_once(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& job
     if ((out_evals || out_mask || out_heights || keep_debug_state) && chunks.size() != 1)
         return ctx->fail(HAF_ERR_UNSUPPORTED, "per-roll outputs need the whole request in one chunk (windows x dims too large)");
 
+    ENSURE(ctx, ctx->d_params, o_ub + bytes_ub + 16); ENSURE(ctx, ctx->d_results, n_jobs); ENSURE(ctx, ctx->d_per_roll_top, (size_t)U * 3);
+    ENSURE(ctx, ctx->d_unit_block, (size_t)2 * U + (U + 1) / 2);
+    unsigned long long* const d_unit_top = ctx->d_unit_block.p;
+    unsigned long long* const d_unit_run = d_unit_top + U;
+    unsigned* const d_unit_windows = reinterpret_cast<unsigned*>(d_unit_run + U);
+    ENSURE(ctx, ctx->h_results, n_jobs); ENSURE(ctx, ctx->h_per_roll_top, (size_t)U * 3);
+    ENSURE(ctx, ctx->h_unit_windows, U);
+    // per-roll outputs asked for in HOST memory: pinned staging (an async copy into pageable memory cannot be captured), copied on after the sync
+    const bool host_evals = out_evals && !is_device_ptr(out_evals), host_mask = out_mask && !is_device_ptr(out_mask),
+               host_heights = out_heights && !is_device_ptr(out_heights);
+    float* dst_evals = out_evals; unsigned char* dst_mask = out_mask; float* dst_heights = out_heights;
+    if (host_evals) { ENSURE(ctx, ctx->h_out_evals, (size_t)U * GG); dst_evals = ctx->h_out_evals.p; }
+    if (host_mask) { ENSURE(ctx, ctx->h_out_mask, (size_t)U * GG); dst_mask = ctx->h_out_mask.p; }
+    if (host_heights) { ENSURE(ctx, ctx->h_out_heights, (size_t)U * GG); dst_heights = ctx->h_out_heights.p; }
     const bool prof = ctx->profiling;
     if (prof) {
         while (ctx->ev_pool.size() < chunks.size() * 8) {
@@ -1275,9 +1296,67 @@ static int run_jobs_once(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& job
             ctx->ev_pool.push_back(e);
         }
     }
+    // ---- one CUDA graph per request shape (see haf_ctx::GraphKey): 0 = enqueue as usual, 1 = capture while enqueuing, 2 = replay
+    int gmode = 0;
+    haf_ctx::GraphKey gkey;
+    memset(&gkey, 0, sizeof gkey);
+    const long long pts_bucket = (long long)round_up((size_t)std::max<long long>(max_points, 1), 65536);
+    const bool graph_ok = ctx->graph_mode != 1 && chunks.size() == 1 && !ctx->profiling && ctx->copy_pieces == 0 && !tc_debug_flags();
+    if (graph_ok) {
+        if (!ctx->stream) {   // the legacy default stream cannot be captured: a blocking stream of our own (it orders with legacy-stream work)
+            if (!ctx->own_stream) CUDA_TRY(ctx, cudaStreamCreate(&ctx->own_stream));
+            st = ctx->own_stream;
+        }
+        cudaStreamCaptureStatus cst = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cst) == cudaSuccess && cst != cudaStreamCaptureStatusNone) {   // an earlier call failed mid-capture
+            cudaGraph_t stale = nullptr;
+            cudaStreamEndCapture(st, &stale);
+            if (stale) cudaGraphDestroy(stale);
+            cudaGetLastError();
+        }
+        unsigned long long hsh = 1469598103934665603ull;
+        for (int j = 0; j < n_jobs; j++) {
+            const unsigned long long v[3] = {(unsigned long long)jobs[j].roll_begin, (unsigned long long)jobs[j].n_rolls_active, (unsigned long long)jobs[j].wbound};
+            for (int q = 0; q < 3; q++) { hsh ^= v[q]; hsh *= 1099511628211ull; }
+        }
+        const long long avg_points_all = (cs.off[n_clouds] - cs.off[0]) / std::max(1, n_clouds);
+        gkey.epoch = g_alloc_epoch; gkey.xyz = cs.d_xyz; gkey.stride = cs.stride; gkey.wcap = (size_t)std::max<long long>(jobs.empty() ? 0 : 0, 0);
+        long long wsum_all = 0;
+        for (int j = 0; j < n_jobs; j++) wsum_all += jobs[j].wbound;
+        gkey.wcap = (size_t)wsum_all; gkey.pts_bucket = pts_bucket; gkey.n_jobs = n_jobs; gkey.n_clouds = n_clouds;
+        gkey.flags = (prob ? 1 : 0) | (keep_debug_state ? 2 : 0) | (avg_points_all >= 8 * (long long)GG ? 4 : 0) | (ctx->cfg.emulate_text_roundtrip ? 8 : 0);
+        gkey.tc_passes = ctx->tc_passes; gkey.o_evals = dst_evals; gkey.o_mask = dst_mask; gkey.o_heights = dst_heights; gkey.rolls_hash = hsh; gkey.st = st;
+        if (ctx->graph_valid && ctx->graph_key == gkey) gmode = 2;
+        else if (ctx->graph_seen_valid && ctx->graph_seen == gkey) gmode = 1;
+        else { ctx->graph_seen = gkey; ctx->graph_seen_valid = true; }
+    }
     float ms_stage[7] = {0, 0, 0, 0, 0, 0, 0};
     long long total_windows = 0, total_guard = 0;
-    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[8], st));
+    if (gmode == 2) {
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev[8], st));
+        CUDA_TRY(ctx, cudaGraphLaunch(ctx->graph_exec, st));
+        ctx->launches += ctx->graph_nodes;
+        ctx->graph_replays++;
+        if (keep_debug_state) { ctx->last_units = U; ctx->last_unit_base = 0; ctx->last_ldx = round_up((size_t)std::max<long long>((long long)gkey.wcap, 1), 2 * haftc::BM); }
+    } else {
+    if (gmode == 1) CUDA_TRY(ctx, cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+    else CUDA_TRY(ctx, cudaEventRecord(ctx->ev[8], st));
+    const long long launches_cap0 = ctx->launches;
+    // The parameter block goes up with a tiny kernel that reads the pinned staging buffer directly (UVA), NOT with a
+    // copy-engine memcpy: the H2D engine is a FIFO, and behind a large staging copy of clouds (this call's, or any other
+    // stream's) a small memcpy would stall every kernel of the call until that copy has finished.
+    {
+        const size_t n16 = (o_ub + bytes_ub + 15) / 16;
+        copy_params_kernel<<<(unsigned)std::min<size_t>((n16 + 255) / 256, 1024), 256, 0, st>>>(reinterpret_cast<const uint4*>(ctx->h_stage.p),
+                                                                                              reinterpret_cast<uint4*>(ctx->d_params.p), n16);
+        LAUNCHED(ctx);
+    }
+    UnitParams* const d_units = reinterpret_cast<UnitParams*>(ctx->d_params.p + o_units);
+    JobParams* const d_jobs = reinterpret_cast<JobParams*>(ctx->d_params.p + o_jobs);
+    long long* const d_ptoff = reinterpret_cast<long long*>(ctx->d_params.p + o_off);
+    int* const d_cloud_ubegin = reinterpret_cast<int*>(ctx->d_params.p + o_ub);
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_unit_block.p, 0, ((size_t)2 * U + (U + 1) / 2) * 8, st));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, 16 * 4, st));
 
     const float r = (float)((0.5 * (float)G) / 100.0);  // server.cpp:410-411
     const bool smallG = (size_t)G * ld * sizeof(double) <= 200 * 1024;
@@ -1323,7 +1402,7 @@ static int run_jobs_once(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& job
             // small grids with enough points per cloud: whole-cloud CTAs with shared-memory lower bounds (fewer REDs)
             const int upg = std::min(16, (int)((200 * 1024) / ((size_t)GG * 4)));
             const long long avg_points = (cs.off[c1] - cs.off[c0]) / std::max(1, c1 - c0);
-            if (upg >= 1 && avg_points >= 8 * (long long)GG && (c1 - c0) * 8 >= ctx->sm_count && ctx->cfg.reserved[1] != 1) {
+            if (upg >= 1 && avg_points >= 8 * (long long)GG && (c1 - c0) * 8 >= ctx->sm_count && (ctx->cfg.reserved[1] & 15) != 1) {
                 int max_units_per_cloud = 0;
                 for (int c = c0; c < c1; c++) max_units_per_cloud = std::max(max_units_per_cloud, hub[c + 1] - hub[c]);
                 const int ug = std::min(upg, std::max(1, max_units_per_cloud));
@@ -1341,7 +1420,7 @@ static int run_jobs_once(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& job
                     }
                 }
                 dim3 gridc((unsigned)(c1 - c0), (unsigned)((max_units_per_cloud + ug - 1) / ug), (unsigned)slices);
-                if (cs.stride == 12 && ctx->cfg.reserved[1] != 2)
+                if (cs.stride == 12 && (ctx->cfg.reserved[1] & 15) != 2)
                     bin_maxz_cloud_kernel<4><<<gridc, 1024, (size_t)ug * GG * 4, st>>>(cs.d_xyz, cs.stride, d_ptoff + c0, d_cloud_ubegin + c0, d_units,
                                                                                      ctx->d_keys.p - (size_t)ubase * GG, G, r, ug,
                                                                                      reinterpret_cast<unsigned long long*>(cnt + 4));
@@ -1352,7 +1431,9 @@ static int run_jobs_once(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& job
                 LAUNCHED(ctx);
             } else {
                 const int PPT = 4;
-                dim3 grid((unsigned)((max_points + 256 * PPT - 1) / (256 * PPT)), (unsigned)(c1 - c0));
+                // (a graph-eligible call sizes the grid for the 64 k-point bucket of the cloud: surplus CTAs return at once)
+                const long long grid_points = graph_ok ? pts_bucket : max_points;
+                dim3 grid((unsigned)((grid_points + 256 * PPT - 1) / (256 * PPT)), (unsigned)(c1 - c0));
                 if (grid.x > 0) {
                     // cloud_unit_begin is relative to unit 0 of the call: shift the key base so unit u lands at keys[u - ubase]
                     bin_maxz_kernel<PPT><<<grid, 256, 0, st>>>(cs.d_xyz, cs.stride, d_ptoff + c0, d_cloud_ubegin + c0, d_units,
@@ -1430,9 +1511,9 @@ static int run_jobs_once(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& job
                 const int na = jobs[j].n_rolls_active - jobs[j].roll_begin;
                 if (na <= 0) continue;
                 const size_t uo = (size_t)(j * R + jobs[j].roll_begin - ubase) * GG, go = ((size_t)j * R + jobs[j].roll_begin) * GG, nel = (size_t)na * GG;
-                if (out_evals) CUDA_TRY(ctx, cudaMemcpyAsync(out_evals + go, ctx->d_evals.p + uo, nel * 4, cudaMemcpyDefault, st));
-                if (out_mask) CUDA_TRY(ctx, cudaMemcpyAsync(out_mask + go, ctx->d_mask.p + uo, nel, cudaMemcpyDefault, st));
-                if (out_heights) CUDA_TRY(ctx, cudaMemcpyAsync(out_heights + go, ctx->d_keys.p + uo, nel * 4, cudaMemcpyDefault, st));
+                if (out_evals) CUDA_TRY(ctx, cudaMemcpyAsync(dst_evals + go, ctx->d_evals.p + uo, nel * 4, cudaMemcpyDefault, st));
+                if (out_mask) CUDA_TRY(ctx, cudaMemcpyAsync(dst_mask + go, ctx->d_mask.p + uo, nel, cudaMemcpyDefault, st));
+                if (out_heights) CUDA_TRY(ctx, cudaMemcpyAsync(dst_heights + go, ctx->d_keys.p + uo, nel * 4, cudaMemcpyDefault, st));
             }
         }
     }
@@ -1443,12 +1524,32 @@ static int run_jobs_once(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& job
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_results.p, ctx->d_results.p, (size_t)n_jobs * sizeof(JobResult), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_per_roll_top.p, ctx->d_per_roll_top.p, (size_t)U * 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_counters.p, ctx->d_counters.p, 16 * 4, cudaMemcpyDeviceToHost, st));
-    if (keep_debug_state) {   // single goals: windows per unit, for the multi-GPU merge
-        ENSURE(ctx, ctx->h_unit_windows, U);
+    if (keep_debug_state)   // single goals: windows per unit, for the multi-GPU merge
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_unit_windows.p, d_unit_windows, (size_t)U * 4, cudaMemcpyDeviceToHost, st));
+    if (gmode == 1) {   // everything above was recorded, not run: instantiate, keep, run
+        cudaGraph_t graph = nullptr;
+        CUDA_TRY(ctx, cudaStreamEndCapture(st, &graph));
+        if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; ctx->graph_valid = false; }
+        const cudaError_t ie = cudaGraphInstantiate(&ctx->graph_exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) { ctx->graph_exec = nullptr; return ctx->fail(HAF_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ie)); }
+        ctx->graph_nodes = ctx->launches - launches_cap0;
+        gkey.epoch = g_alloc_epoch;   // (unchanged unless a buffer grew while capturing: then the next call re-captures)
+        ctx->graph_key = gkey; ctx->graph_valid = true;
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev[8], st));
+        CUDA_TRY(ctx, cudaGraphLaunch(ctx->graph_exec, st));
     }
+    }   // gmode != 2
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[9], st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    for (int j = 0; j < n_jobs && (host_evals || host_mask || host_heights); j++) {   // pinned staging -> the caller's host buffers
+        const int na = jobs[j].n_rolls_active - jobs[j].roll_begin;
+        if (na <= 0) continue;
+        const size_t go = ((size_t)j * R + jobs[j].roll_begin) * GG, nel = (size_t)na * GG;
+        if (host_evals) memcpy(out_evals + go, dst_evals + go, nel * 4);
+        if (host_mask) memcpy(out_mask + go, dst_mask + go, nel);
+        if (host_heights) memcpy(out_heights + go, dst_heights + go, nel * 4);
+    }
     total_windows = ctx->h_counters.p[8];
     total_guard = ctx->h_counters.p[9];
     if (ctx->h_counters.p[2]) return ctx->fail(HAF_ERR_UNSUPPORTED, "window list overflow (internal bound too small)");
@@ -1474,6 +1575,7 @@ static int run_jobs_once(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& job
     t.audit_max_rel = ctx->audit_max_rel;
     t.tc_passes = ctx->cfg.svm_mode == HAF_SVM_TENSOR_GUARD ? ctx->tc_passes : 0;
     t.escalations = ctx->escalations;
+    t.graph_replays = (int)std::min<long long>(ctx->graph_replays, 0x7fffffff);
     if (keep_debug_state) { ctx->last_W = (unsigned)total_windows; ctx->last_valid = true; }
     return HAF_OK;
 }

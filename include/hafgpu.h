@@ -66,8 +66,11 @@ typedef struct {
                                        streaming CTA pair; both cta_group::2), 2 = streaming CTA pair always;
                                        bits 4-5: tensor-core products per k-slice, 0 = calibrated per model (default), 1 / 2 / 3 forced;
                                        bit 8: audit sample off; bits 16+: audit every n-th window (default 4096; see haf_timing);
-                                  [1]: 1 = always use the point-parallel binning kernel (no whole-cloud CTAs), 2 = whole-cloud kernel
-                                       with scalar loads;
+                                  [1]: bits 0-3: 1 = always use the point-parallel binning kernel (no whole-cloud CTAs), 2 = whole-cloud
+                                       kernel with scalar loads; bit 4: 1 = CUDA graphs: a call that fits one pass and repeats the
+                                       previous call's shape -- unit and window bounds, 64 k-point bucket of the cloud, buffers -- is
+                                       captured once and replayed (one goal is ~25 dependent stream operations).  Off by default:
+                                       measured on B200 a replayed goal is no faster than a launched one (0.267 vs 0.268 ms);
                                   [2]: bits 0-1: guard band tier 2 (FP64 re-evaluation by contraction): 0 = on, 1 = off (every guard
                                        window goes to the exact-order kernels), 2 = on, but every window escalates as well (tests);
                                        bits 2-3: its kernel: 0 / 1 = FP64 tensor cores (DMMA), 2 = DFMA register tiles (round 1's kernel);
@@ -135,7 +138,7 @@ typedef struct {
     float audit_max_rel; /* max |dec_tensor - dec_fp64| / (E + |rho|) over guard + audit windows of the call      */
     int tc_passes;      /* tensor-core products per k-slice the call ended with (0 outside tensor mode)           */
     int escalations;    /* times this context repeated a call with more products because the audit left < 4x     */
-    int reserved;
+    int graph_replays;  /* calls of this context served by replaying its captured CUDA graph (reserved[1] bit 4)      */
 } haf_timing;
 
 /* ---- lifetime --------------------------------------------------------------------------------------------- */

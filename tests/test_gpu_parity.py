@@ -518,3 +518,52 @@ def test_full_size_batch_properties(hg, oracle_lib, tmp_models):
         assert tup[0] == ob.astuple() and dev_windows[0] == ob.n_windows
     finally:
         gpu.close()
+
+
+def test_cuda_graph_replay_equals_plain_launches(hg, oracle_lib, tmp_models, clouds):
+    """One goal = ~25 dependent stream operations; with cfg.reserved[1] bit 4 a call that repeats the previous call's shape is captured
+    into a CUDA graph once and replayed (server.cpp:335-402 runs goal after goal with the same parameters).  Replays must return exactly what
+    plain launches return -- for the same cloud, for other clouds of the same 64 k-point bucket, for other requests of the same
+    shape -- and a change of shape must fall back and re-capture."""
+    model = tmp_models(256)
+    g = hg.GraspSearch(FEATURES, RANGE, model, use_graph=True)      # graphs on (opt-in: measured, they buy nothing on B200)
+    p = hg.GraspSearch(FEATURES, RANGE, model)                      # plain launches (the default)
+    try:
+        def same(a, b):
+            assert a["best"].astuple() == b["best"].astuple()
+            assert (a["best"].rolls_done, a["best"].n_windows_scored) == (b["best"].rolls_done, b["best"].n_windows_scored)
+            for k in ("graspseval", "mask", "heights", "per_roll_top"):
+                assert np.array_equal(a[k], b[k]), k
+        seq = [("pcd2", {}), ("pcd2", {}), ("pcd2", {}), ("pcd7", {}), ("plastic_mug2", {}), ("pcd2", {"approach": (0.5, 0.0, 0.8660254)}),
+               ("pcd3", {"center": (0.01, -0.02, 0.0)}), ("pcd2", {"return_only_best": 1, "graspval_top": 60})]
+        for name, kw in seq:                                         # all: 12 units, same window bound, clouds < 65 536 points
+            same(g.search(clouds[name], [hg.make_request(**kw)]), p.search(clouds[name], [hg.make_request(**kw)]))
+        assert g.timing().graph_replays >= 1 and p.timing().graph_replays == 0   # (a bigger cloud re-allocates the staging buffer: re-capture)
+        assert g.timing().launches == p.timing().launches
+        n0 = g.timing().graph_replays
+        # other shapes: a bigger cloud (another bucket), two requests, a narrower area, a roll range -- each captured anew after one plain call
+        for name, reqs in (("table1", [hg.make_request()]), ("pcd2", [hg.make_request(), hg.make_request(approach=(0.0, 0.5, 0.8660254))]),
+                           ("pcd2", [hg.make_request(area=(28.0, 36.0))]), ("pcd2", [hg.make_request(roll_begin=2, roll_limit=9)])):
+            for _ in range(3):
+                same(g.search(clouds[name], reqs), p.search(clouds[name], reqs))
+        assert g.timing().graph_replays >= n0 + 4
+        # batches of one shape replay too; device-resident clouds and outputs=False (no per-roll copies)
+        from haf_grasping_b200 import synth
+        cl = [synth.synth_cloud(40 + i, 30000) for i in range(5)]
+        for _ in range(3):
+            assert [b.astuple() for b in g.search_batch(cl)] == [b.astuple() for b in p.search_batch(cl)]
+        import torch
+        dev = torch.from_numpy(clouds["table2"]).cuda()
+        for _ in range(3):
+            a = g.search(dev, [hg.make_request()], outputs=False)
+            b = p.search(clouds["table2"], [hg.make_request()], outputs=False)
+            assert a["best"].astuple() == b["best"].astuple() and np.array_equal(a["per_roll_top"], b["per_roll_top"])
+        # the debug accessors read the state a replay left behind
+        g.search(clouds["pcd2"]); g.search(clouds["pcd2"]); g.search(clouds["pcd2"])
+        p.search(clouds["pcd2"])
+        dg, lg, _ = g.debug_decisions()
+        dp, lp, _ = p.debug_decisions()
+        assert np.array_equal(lg, lp) and np.array_equal(g.debug_windows(), p.debug_windows())
+    finally:
+        g.close()
+        p.close()
