@@ -26,7 +26,8 @@ static thread_local std::string g_create_error;
 
 namespace {
 
-// every (re)allocation moves this on: a captured CUDA graph bakes the buffers' addresses in and is only replayed while it stands
+// (Re)allocations done at creation time (outside ENSURE) move this on; the ENSURE macro moves the owning context's alloc_epoch on.
+// A captured CUDA graph bakes the buffers' addresses in and is only replayed while both stand.
 static unsigned long long g_alloc_epoch = 0;
 template <typename T>
 struct DevBuf {
@@ -165,6 +166,7 @@ struct haf_ctx {
     bool graph_valid = false, graph_seen_valid = false;
     cudaGraphExec_t graph_exec = nullptr;
     long long graph_nodes = 0, graph_replays = 0;
+    unsigned long long alloc_epoch = 0;   // moved on by every ENSURE that (re)allocates one of this context's buffers
     int graph_mode = 0;
     cudaStream_t own_stream = nullptr;     // capture is not allowed on the legacy default stream: a blocking stream of our own stands in
     PinBuf<float> h_out_evals, h_out_heights;   // per-roll outputs asked for in HOST memory go through pinned staging (graph-capturable)
@@ -221,7 +223,12 @@ struct haf_ctx {
     } while (0)
 #define ENSURE(ctx, buf, n)                                                                                   \
     do {                                                                                                      \
-        if ((buf).ensure(n) != 0) return (ctx)->fail(HAF_ERR_NOMEM, "out of device/pinned memory for %s (%zu elements)", #buf, (size_t)(n)); \
+        const void* _p0 = (const void*)(buf).p;                                                               \
+        const unsigned long long _g0 = g_alloc_epoch;                                                         \
+        const int _rc = (buf).ensure(n);                                                                      \
+        g_alloc_epoch = _g0; /* this context's buffer: only this context's graph goes stale */                \
+        if ((const void*)(buf).p != _p0) (ctx)->alloc_epoch++;                                                \
+        if (_rc != 0) return (ctx)->fail(HAF_ERR_NOMEM, "out of device/pinned memory for %s (%zu elements)", #buf, (size_t)(n)); \
     } while (0)
 #define LAUNCHED(ctx)                                                                                         \
     do {                                                                                                      \
@@ -1320,7 +1327,7 @@ static int run_jobs_once(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& job
             for (int q = 0; q < 3; q++) { hsh ^= v[q]; hsh *= 1099511628211ull; }
         }
         const long long avg_points_all = (cs.off[n_clouds] - cs.off[0]) / std::max(1, n_clouds);
-        gkey.epoch = g_alloc_epoch; gkey.xyz = cs.d_xyz; gkey.stride = cs.stride; gkey.wcap = (size_t)std::max<long long>(jobs.empty() ? 0 : 0, 0);
+        gkey.epoch = g_alloc_epoch + ctx->alloc_epoch; gkey.xyz = cs.d_xyz; gkey.stride = cs.stride; gkey.wcap = (size_t)std::max<long long>(jobs.empty() ? 0 : 0, 0);
         long long wsum_all = 0;
         for (int j = 0; j < n_jobs; j++) wsum_all += jobs[j].wbound;
         gkey.wcap = (size_t)wsum_all; gkey.pts_bucket = pts_bucket; gkey.n_jobs = n_jobs; gkey.n_clouds = n_clouds;
@@ -1534,10 +1541,12 @@ static int run_jobs_once(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& job
         cudaGraphDestroy(graph);
         if (ie != cudaSuccess) { ctx->graph_exec = nullptr; return ctx->fail(HAF_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ie)); }
         ctx->graph_nodes = ctx->launches - launches_cap0;
-        gkey.epoch = g_alloc_epoch;   // (unchanged unless a buffer grew while capturing: then the next call re-captures)
+        gkey.epoch = g_alloc_epoch + ctx->alloc_epoch;   // (unchanged unless a buffer grew while capturing: then the next call re-captures)
         ctx->graph_key = gkey; ctx->graph_valid = true;
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev[8], st));
         CUDA_TRY(ctx, cudaGraphLaunch(ctx->graph_exec, st));
+    } else if (graph_ok) {
+        ctx->graph_seen.epoch = g_alloc_epoch + ctx->alloc_epoch;   // buffers this first call of the shape grew: the second call captures
     }
     }   // gmode != 2
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[9], st));

@@ -8,6 +8,8 @@ set -x
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > $out/smi.txt
 python bench.py --steps 10 --warmup 3 > $out/bench_n1.json 2> $out/bench_n1.err
 python bench.py --workload table1 --steps 20 --warmup 5 > $out/bench_table1.json 2> /dev/null
+python bench.py --workload table1 --steps 50 --warmup 5 --no-cpu-baseline --graph 1 > $out/bench_table1_graph.json 2> /dev/null
+ncu --metrics gpu__time_duration.sum --clock-control none -s 90 -c 36 --csv --log-file $out/launches_table1.csv python bench.py --workload table1 --steps 2 --warmup 5 --no-cpu-baseline > /dev/null 2>&1
 python bench.py --workload grid512 --steps 5 --warmup 3 > $out/bench_grid512.json 2> /dev/null
 python bench.py --workload approach --steps 20 --warmup 5 > $out/bench_approach_n1.json 2> /dev/null
 python bench.py --impl reference --steps 1 --warmup 0 > $out/bench_reference.json 2> /dev/null
