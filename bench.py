@@ -483,9 +483,15 @@ def run_ours(args):
     ms_dev, wall_dev, acc = timed(dev, args.steps)
     clocks = sampler.stop() if rank == 0 else {}
     # end to end: host (pinned) buffers in, results out, through the same C-ABI call
+    # (timed as a caller gets it: without the per-stage events; the stage breakdown comes from a short profiled pass afterwards)
+    gs.set_profiling(False)
     for _ in range(2):
         step(host.numpy())
     ms_e2e, wall_e2e, acc2 = timed(host.numpy(), args.steps)
+    gs.set_profiling(True)
+    n_prof = max(2, min(args.steps, 3))
+    step(host.numpy())
+    ms_e2e_prof, _, acc2p = timed(host.numpy(), n_prof)
     # what bounds the end-to-end number from below: the same bytes copied host -> device and nothing else, all ranks at once
     def copies_only(steps):
         if world > 1:
@@ -557,7 +563,9 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": total_pts * 12 + 0, "d2h_bytes_per_step": n_clouds * (32 + info.n_rolls * 12) + 64, "host_memory": "pinned",
                     "ms_per_step": ms_e2e / args.steps,
-                    "stage_ms_per_step": {k: acc2[k] / args.steps for k in ("bin", "integral", "mask", "features", "svm", "guard", "score")},
+                    "stage_ms_per_step": {k: acc2p[k] / n_prof for k in ("bin", "integral", "mask", "features", "svm", "guard", "score")},
+                    "stage_note": "stages from a separate pass of %d steps with per-stage events on (%.3f ms per step); the chunks of a host-staged batch alternate "
+                                  "between several streams, so stage times overlap and sum to more than the step" % (n_prof, ms_e2e_prof / n_prof),
                     "chunks_per_step": acc2["chunks"] / args.steps,
                     "h2d_only_ms_per_step": ms_h2d, "h2d_only_GBps_per_gpu": (total_pts * 12 / (ms_h2d * 1e-3) / 1e9) if ms_h2d else None,
                     "frac_of_h2d_ceiling": (ms_h2d / (ms_e2e / args.steps)) if ms_h2d else None,

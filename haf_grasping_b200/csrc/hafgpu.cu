@@ -148,6 +148,22 @@ struct haf_ctx {
     DevBuf<unsigned> d_g2tickets;
     DevBuf<int> d_guardlist2;
     DevBuf<unsigned> d_counters;        // [0]=win_count [1]=guard_count [2]=overflow [3]=unsupported ; [4..5] clamp (u64)
+    // Host-staged batches run their chunks ALTERNATELY on two streams with two sets of the per-chunk buffers (swap_chunk_ws):
+    // a chunk is a chain of ~18 dependent kernels, half of them latency-sized (integral prefix chains, guard tiers, score,
+    // tie rule) -- the next chunk's big kernels fill the SMs those leave idle.  Set B's counters are d_counters[16..32).
+    struct ChunkWs {
+        DevBuf<__half> d_Xh, d_Xl;
+        DevBuf<float> d_asum, d_integral, d_evals, d_X, d_xn, d_probgrid;
+        DevBuf<double> d_dec_tc, d_rowscan, d_dec, d_kscratch, d_Xg, d_g2accum, d_xn64;
+        DevBuf<unsigned> d_keys, d_g2tickets;
+        DevBuf<unsigned char> d_mask, d_guardflag;
+        DevBuf<signed char> d_labelgrid;
+        DevBuf<int2> d_win;
+        DevBuf<int> d_guardlist, d_guardlist2;
+    } alt[3];
+    cudaStream_t chunk_stream2[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_dual[4];             // [0] head of the call done on the main stream, [1 + k] extra stream k drained
+    bool ev_dual_ok = false;
     PinBuf<unsigned char> h_stage;      // pinned staging for params / results
     PinBuf<JobResult> h_results;
     PinBuf<int> h_per_roll_top;
@@ -215,6 +231,16 @@ struct haf_ctx {
         return code;
     }
 };
+
+// exchanges the per-chunk buffers of the context with its second set (pointers and capacities only)
+static void swap_chunk_ws(haf_ctx* c, int k = 0) {
+#define HAF_SWAP(m) std::swap(c->m, c->alt[k].m)
+    HAF_SWAP(d_Xh); HAF_SWAP(d_Xl); HAF_SWAP(d_asum); HAF_SWAP(d_integral); HAF_SWAP(d_evals); HAF_SWAP(d_X); HAF_SWAP(d_xn); HAF_SWAP(d_probgrid);
+    HAF_SWAP(d_dec_tc); HAF_SWAP(d_rowscan); HAF_SWAP(d_dec); HAF_SWAP(d_kscratch); HAF_SWAP(d_Xg); HAF_SWAP(d_g2accum); HAF_SWAP(d_xn64);
+    HAF_SWAP(d_keys); HAF_SWAP(d_g2tickets); HAF_SWAP(d_mask); HAF_SWAP(d_guardflag); HAF_SWAP(d_labelgrid); HAF_SWAP(d_win);
+    HAF_SWAP(d_guardlist); HAF_SWAP(d_guardlist2);
+#undef HAF_SWAP
+}
 
 #define CUDA_TRY(ctx, expr)                                                                                   \
     do {                                                                                                      \
@@ -513,7 +539,7 @@ static int create_impl(haf_ctx** out, const haf_config* cfg, bool svm_only, int 
     }
     bool okb = ctx->d_feats.ensure(F) == 0 && ctx->d_dims.ensure(D) == 0 && ctx->d_svT.ensure(svT.size()) == 0 &&
                ctx->d_svn.ensure(Spad) == 0 && ctx->d_coef.ensure(Spad) == 0 && ctx->d_sv64T.ensure(sv64T.size()) == 0 &&
-               ctx->d_coef64.ensure(Spad) == 0 && ctx->d_svn64.ensure(Spad) == 0 && ctx->d_counters.ensure(16) == 0 && ctx->h_counters.ensure(16) == 0;
+               ctx->d_coef64.ensure(Spad) == 0 && ctx->d_svn64.ensure(Spad) == 0 && ctx->d_counters.ensure(64) == 0 && ctx->h_counters.ensure(16) == 0;
     if (!okb) { haf_destroy(ctx); return create_fail(HAF_ERR_NOMEM, "out of device memory uploading the model"); }
     CREATE_TRY(cudaMemcpy(ctx->d_feats.p, fd.data(), F * sizeof(FeatDev), cudaMemcpyHostToDevice));
     CREATE_TRY(cudaMemcpy(ctx->d_dims.p, dims.data(), D * sizeof(DimDev), cudaMemcpyHostToDevice));
@@ -931,6 +957,15 @@ extern "C" void haf_destroy(haf_ctx* ctx) {
     ctx->d_svn64.release(); ctx->d_Xg.release(); ctx->d_xn64.release(); ctx->d_g2accum.release(); ctx->d_g2tickets.release(); ctx->d_guardlist2.release();
     ctx->d_SVh.release(); ctx->d_SVl.release(); ctx->d_Xh.release(); ctx->d_Xl.release(); ctx->d_svcoef.release(); ctx->d_dec_tc.release(); ctx->d_asum.release(); ctx->d_dimfeat.release(); ctx->d_round4.release();
     ctx->d_params.release(); ctx->d_counters.release(); ctx->h_stage.release(); ctx->h_results.release(); ctx->h_per_roll_top.release(); ctx->h_counters.release(); ctx->h_unit_windows.release();
+    for (int k = 0; k < 3; k++) {
+    swap_chunk_ws(ctx, k);   // the further sets of per-chunk buffers (host-staged batches, one per extra stream)
+    ctx->d_keys.release(); ctx->d_integral.release(); ctx->d_rowscan.release(); ctx->d_mask.release(); ctx->d_labelgrid.release(); ctx->d_evals.release();
+    ctx->d_win.release(); ctx->d_X.release(); ctx->d_xn.release(); ctx->d_dec.release(); ctx->d_guardflag.release(); ctx->d_guardlist.release(); ctx->d_kscratch.release();
+    ctx->d_probgrid.release(); ctx->d_Xg.release(); ctx->d_xn64.release(); ctx->d_g2accum.release(); ctx->d_g2tickets.release(); ctx->d_guardlist2.release();
+    ctx->d_Xh.release(); ctx->d_Xl.release(); ctx->d_dec_tc.release(); ctx->d_asum.release();
+    if (ctx->chunk_stream2[k]) cudaStreamDestroy(ctx->chunk_stream2[k]);
+    }
+    if (ctx->ev_dual_ok) for (int k = 0; k < 4; k++) cudaEventDestroy(ctx->ev_dual[k]);
     if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     ctx->h_out_evals.release(); ctx->h_out_heights.release(); ctx->h_out_mask.release();
@@ -1254,28 +1289,44 @@ static int run_jobs_once(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& job
     size_t x_budget_floats = (size_t)8 << 28;  // 8 GiB of FP32 SVM inputs per chunk at most (fp16 operands: a quarter of that): the 512-cloud bench batch is ONE pass
     if (const char* e = getenv("HAF_X_BUDGET_GIB")) { const long g = atol(e); if (g >= 1 && g <= 64) x_budget_floats = (size_t)g << 28; }   // experiments
     std::vector<std::pair<int, int> > chunks;   // [job_begin, job_end)
+    bool split_resident = false;
     {
         int jb0 = 0, stage_limit = 16;
+        std::vector<int> sched;   // experiments: HAF_STAGE_SCHED="16,24,36,..." = clouds per chunk of a host-staged batch (last value repeats)
+        if (const char* e = getenv("HAF_STAGE_SCHED")) {
+            for (const char* q = e; *q;) { const int v = atoi(q); if (v > 0) sched.push_back(v); while (*q && *q != ',') q++; if (*q == ',') q++; }
+            if (!sched.empty()) stage_limit = sched[0];
+        }
+        // device-resident batches: optionally split into equal chunks that alternate between the streams as well (experiments)
+        int resident_split = 1;
+        if (const char* e = getenv("HAF_RESIDENT_SPLIT")) resident_split = std::max(1, std::min(16, atoi(e)));
+        if (ctx->copy_pieces > 0 || out_evals || out_mask || out_heights || keep_debug_state || n_jobs < 32 * resident_split) resident_split = 1;
+        split_resident = resident_split > 1;
+        const int split_jobs = (n_jobs + resident_split - 1) / resident_split;
         while (jb0 < n_jobs) {
             long long wsum = 0;
             int je = jb0;
             while (je < n_jobs) {
                 const long long w = jobs[je].wbound;
+                if (split_resident && (je - jb0) >= split_jobs) break;
                 if (je > jb0 && (size_t)(wsum + w) * ctx->Kpad > x_budget_floats) break;
                 if (je > jb0 && (je - jb0) * R >= 16384) break;
-                // clouds being staged from host memory: the first chunk is small so that compute starts after ~1 ms of
-                // copying, later chunks grow by 1.5x -- a chunk's compute (~0.036 ms per cloud) then always outlasts the copy
-                // of the next one (~0.023 ms per cloud), and the bulk of the work runs in large, tail-free launches
+                // clouds being staged from host memory: the first chunk is small so that compute starts after ~0.35 ms of
+                // copying; later chunks grow so that the bulk of the work runs in large launches
                 if (je > jb0 && ctx->copy_pieces > 0 && (je - jb0) >= stage_limit) break;
                 wsum += w;
                 je++;
             }
             chunks.push_back(std::make_pair(jb0, je));
             jb0 = je;
-            // ... up to 64 clouds: the host -> device copy (PCIe, ~22 us per 100 k-point cloud) is now slower than the compute
-            // (~20 us), so what follows the last copy -- the LAST chunk's compute -- has to be short; round 1's cap of 256
-            // left 180 clouds (3.6 ms) behind the copy (bench e2e 15.1 -> ~13 ms)
-            stage_limit = std::min(64, stage_limit + stage_limit / 2);
+            // ... up to 56 clouds: the host -> device copy (PCIe, ~22 us per 100 k-point cloud) is slower than the compute (~19 us),
+            // so what follows the last copy -- the LAST chunk's chain of ~15 dependent kernels -- has to be short, while every chunk
+            // pays ~0.2 ms of launch gaps and fixed kernel latencies.  Measured with the chunks alternating between three streams
+            // (bench e2e, 512 clouds): 16, 24, 32, 48, 56, 56, ... 12.9 ms; 16, 24, 36, 54, 64, ... 13.2; at most 48: 13.0; at most
+            // 32: 13.5.  (One stream, round 1: a cap of 256 left 180 clouds behind the copy, 15.1 ms; a cap of 64: 14.3 ms.)
+            static const int kSched[5] = {16, 24, 32, 48, 56};
+            stage_limit = kSched[std::min<size_t>(chunks.size(), 4)];
+            if (!sched.empty()) stage_limit = sched[std::min(chunks.size(), sched.size() - 1)];
         }
     }
     if ((out_evals || out_mask || out_heights || keep_debug_state) && chunks.size() != 1)
@@ -1363,7 +1414,25 @@ static int run_jobs_once(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& job
     long long* const d_ptoff = reinterpret_cast<long long*>(ctx->d_params.p + o_off);
     int* const d_cloud_ubegin = reinterpret_cast<int*>(ctx->d_params.p + o_ub);
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_unit_block.p, 0, ((size_t)2 * U + (U + 1) / 2) * 8, st));
-    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, 16 * 4, st));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, 64 * 4, st));
+    // host-staged batch in several chunks: chunks alternate between the call's stream and a second one (see haf_ctx::ChunkWs)
+    int nsets = ((ctx->copy_pieces > 0 || split_resident) && chunks.size() >= 2 && !graph_ok) ? 3 : 1;
+    if (const char* e = getenv("HAF_DUAL_STREAM")) { const int v = atoi(e); if (nsets > 1) nsets = v <= 0 ? 1 : std::min(4, std::max(2, v)); }   // 0 = one stream, 2..4 streams
+    nsets = (int)std::min<size_t>((size_t)nsets, chunks.size());
+    const bool dual = nsets > 1;
+    if (dual) {
+        if (!ctx->ev_dual_ok) {
+            for (int k = 0; k < 4; k++) CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_dual[k], cudaEventDisableTiming));
+            ctx->ev_dual_ok = true;
+        }
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_dual[0], st));
+        for (int k = 0; k + 1 < nsets; k++) {
+            if (!ctx->chunk_stream2[k]) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->chunk_stream2[k], cudaStreamNonBlocking));
+            CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->chunk_stream2[k], ctx->ev_dual[0], 0));
+        }
+    }
+    cudaStream_t const st_main = st;
+    struct WsSwapBack { haf_ctx* c; int set; ~WsSwapBack() { if (set > 0) swap_chunk_ws(c, set - 1); } } ws_scope{ctx, 0};   // (error returns inside a chunk)
 
     const float r = (float)((0.5 * (float)G) / 100.0);  // server.cpp:410-411
     const bool smallG = (size_t)G * ld * sizeof(double) <= 200 * 1024;
@@ -1373,6 +1442,9 @@ static int run_jobs_once(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& job
     for (size_t ci = 0; ci < chunks.size(); ci++) {
         const int j0 = chunks[ci].first, j1 = chunks[ci].second;
         const int Uc = (j1 - j0) * R, ubase = j0 * R;
+        const int set = dual ? (int)(ci % (size_t)nsets) : 0;   // 0: the call's stream and the context's own buffers
+        if (set) { swap_chunk_ws(ctx, set - 1); ws_scope.set = set; }
+        st = set ? ctx->chunk_stream2[set - 1] : st_main;
         long long wcap_ll = 0;
         for (int j = j0; j < j1; j++) wcap_ll += jobs[j].wbound;
         const size_t Wcap = (size_t)std::max<long long>(wcap_ll, 1);
@@ -1391,8 +1463,8 @@ static int run_jobs_once(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& job
         // (a guard band wider than that means a mis-configured guard_rel: the call then fails loudly below)
         const size_t exact_cap = std::min<size_t>(ldx, std::max<size_t>(4096, ((size_t)1 << 30) / ((size_t)ctx->Spad * 8)));
         ENSURE(ctx, ctx->d_kscratch, exact_cap * ctx->Spad);
-        unsigned* cnt = ctx->d_counters.p;
-        if (ci > 0) CUDA_TRY(ctx, cudaMemsetAsync(cnt, 0, 2 * 4, st));  // win_count, guard_count
+        unsigned* cnt = ctx->d_counters.p + 16 * set;
+        if (ci >= (size_t)nsets) CUDA_TRY(ctx, cudaMemsetAsync(cnt, 0, 2 * 4, st));  // win_count, guard_count
         const UnitParams* units_c = d_units + ubase;
 
         // staged host clouds: wait for the copy pieces that cover this chunk's clouds
@@ -1413,17 +1485,21 @@ static int run_jobs_once(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& job
                 int max_units_per_cloud = 0;
                 for (int c = c0; c < c1; c++) max_units_per_cloud = std::max(max_units_per_cloud, hub[c + 1] - hub[c]);
                 const int ug = std::min(upg, std::max(1, max_units_per_cloud));
-                // the kernel is instruction-bound once the REDs are filtered, one 1024-thread CTA per SM: what matters is that the
-                // CTAs (clouds x unit groups x slices) fill whole waves of the SMs.  Smallest slice count <= 12 within 2 % of the best
-                // wave efficiency (512 clouds: 2 slices = 6.92 waves -> 7, 99 %, instead of 3.46 -> 4, 86 %)
+                // The kernel is instruction-bound once the REDs are filtered, one 1024-thread CTA per SM.  A CTA costs a fixed part
+                // (150 KB of shared-memory bounds initialised and flushed, launch) plus its slice of the cloud's points; the CTAs
+                // (clouds x unit groups x slices) run in rounds of one per SM.  Slice count <= 12 that minimises
+                //     rounds x (1 / slices + fixed / whole-cloud time),   fixed / whole-cloud time ~ 4.2 G^2 / points
+                // fitted to the ncu launch list of a host-staged bench step (profiles/r2_launches_e2e.md: 144 CTAs of 1/6 cloud 86 us,
+                // of 1/4 cloud 108 us).  512 clouds: 2 slices = 7 rounds (round 2 found that by wave efficiency alone); the
+                // 64-cloud chunks of a staged batch: 2 slices = one round of 128 CTAs (167 us) where wave efficiency picked 9 (210 us).
                 int slices = 1;
                 {
                     const long long groups = (long long)(c1 - c0) * ((max_units_per_cloud + ug - 1) / ug);
-                    double best_eff = 0.0;
+                    const double fixed = std::min(1.0, 4.2 * (double)GG / (double)std::max<long long>(avg_points, 1));
+                    double best_cost = 0.0;
                     for (int sl = 1; sl <= 12; sl++) {
-                        const double waves = (double)(groups * sl) / ctx->sm_count;
-                        const double eff = waves / std::ceil(waves);
-                        if (eff > best_eff + 0.02) { best_eff = eff; slices = sl; }
+                        const double cost = std::ceil((double)(groups * sl) / ctx->sm_count) * (1.0 / sl + fixed);
+                        if (sl == 1 || cost < best_cost) { best_cost = cost; slices = sl; }
                     }
                 }
                 dim3 gridc((unsigned)(c1 - c0), (unsigned)((max_units_per_cloud + ug - 1) / ug), (unsigned)slices);
@@ -1523,6 +1599,16 @@ static int run_jobs_once(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& job
                 if (out_heights) CUDA_TRY(ctx, cudaMemcpyAsync(dst_heights + go, ctx->d_keys.p + uo, nel * 4, cudaMemcpyDefault, st));
             }
         }
+        if (set) { swap_chunk_ws(ctx, set - 1); ws_scope.set = 0; }
+    }
+    st = st_main;
+    if (dual) {   // join: the other streams' chunks, then their counters into the first set's
+        for (int k = 0; k + 1 < nsets; k++) {
+            CUDA_TRY(ctx, cudaEventRecord(ctx->ev_dual[1 + k], ctx->chunk_stream2[k]));
+            CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_dual[1 + k], 0));
+        }
+        merge_counts_kernel<<<1, 1, 0, st>>>(ctx->d_counters.p, nsets - 1);
+        LAUNCHED(ctx);
     }
     // 7. cross-roll reduction per job, results to pinned host memory
     reduce_rolls_kernel<<<(n_jobs + 127) / 128, 128, 0, st>>>(d_unit_top, d_unit_run, d_unit_windows, d_jobs, n_jobs, R, G,

@@ -1727,6 +1727,18 @@ __global__ void accumulate_counts_kernel(unsigned* cnt) {
     cnt[6] = 0;
 }
 
+// host-staged batches run their chunks alternately on several streams, each with its own counter block of 16 words: fold the
+// others' totals into the first
+__global__ void merge_counts_kernel(unsigned* cnt, int n_more) {
+    for (int k = 1; k <= n_more; k++) {
+        const unsigned* o = cnt + 16 * k;
+        cnt[8] += o[8]; cnt[9] += o[9]; cnt[14] += o[14]; cnt[11] += o[11];
+        cnt[2] |= o[2]; cnt[3] |= o[3]; cnt[10] |= o[10];
+        cnt[12] = max(cnt[12], o[12]);   // audit maximum: bits of a non-negative float order like the float
+        *reinterpret_cast<unsigned long long*>(cnt + 4) += *reinterpret_cast<const unsigned long long*>(o + 4);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // libsvm front ends: svm-predict / svm-scale on rows given in libsvm's sparse text layout (CSR here).
 // ---------------------------------------------------------------------------------------------------
