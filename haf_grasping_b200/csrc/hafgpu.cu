@@ -172,7 +172,7 @@ struct haf_ctx {
     // ONE CUDA GRAPH PER REQUEST SHAPE (SURVEY 7 "hard parts"; server.cpp:335-402 is one goal = ~25 dependent stream operations of a
     // few microseconds each).  A call that fits one pass and repeats the shape of the previous one (same unit / window bounds,
     // same buffers, same kernel choices -- GraphKey) is captured once and then replayed with cudaGraphLaunch; the request itself
-    // travels through the pinned parameter block, which the graph's first node reads afresh.  graph_mode: 0 on, 1 off (the default).
+    // travels through the pinned parameter block, which the graph's first node reads afresh.  graph_mode: 0 on, 1 off (the default of a zero-initialised config).
     struct GraphKey {
         unsigned long long epoch; const void* xyz; size_t stride, wcap; long long pts_bucket; int n_jobs, n_clouds, flags, tc_passes;
         const void *o_evals, *o_mask, *o_heights; unsigned long long rolls_hash; cudaStream_t st;
@@ -549,9 +549,9 @@ static int create_impl(haf_ctx** out, const haf_config* cfg, bool svm_only, int 
     CREATE_TRY(cudaMemcpy(ctx->d_sv64T.p, sv64T.data(), sv64T.size() * sizeof(double), cudaMemcpyHostToDevice));
     CREATE_TRY(cudaMemcpy(ctx->d_coef64.p, coef64.data(), Spad * sizeof(double), cudaMemcpyHostToDevice));
     CREATE_TRY(cudaMemcpy(ctx->d_svn64.p, svn64.data(), Spad * sizeof(double), cudaMemcpyHostToDevice));
-    // CUDA graphs are opt-in (cfg.reserved[1] bit 4 or HAF_GRAPH=1): measured, replay buys nothing here -- one table1 goal takes 0.267 ms
-    // replayed against 0.268 ms launched (profiles/README.md): the goal is bound by the latencies of its ~20 dependent kernels, not by
-    // launch overhead -- so the plain path stays the default
+    // CUDA graphs are opt-in (cfg.reserved[1] bit 4 or HAF_GRAPH=1; a zero-initialised config launches plainly).  Measured on B200
+    // WITHOUT per-stage timing events (profiling on disables graphs, and every timing event between two kernels costs ~20 us):
+    // one table1 goal 0.224 ms launched, 0.189 ms replayed; the 512-grid 1 M-point goal 4.34 vs 4.31 ms (profiles/r2_final_*).
     ctx->graph_mode = ((cfg->reserved[1] & 16) || (getenv("HAF_GRAPH") && atoi(getenv("HAF_GRAPH")))) ? 0 : 1;
     ctx->tier2_mode = cfg->reserved[2] & 3;
     ctx->tier2_kernel = (cfg->reserved[2] >> 2) & 3;

@@ -576,7 +576,7 @@ def test_cuda_graph_replay_equals_plain_launches(hg, oracle_lib, tmp_models, clo
     plain launches return -- for the same cloud, for other clouds of the same 64 k-point bucket, for other requests of the same
     shape -- and a change of shape must fall back and re-capture."""
     model = tmp_models(256)
-    g = hg.GraspSearch(FEATURES, RANGE, model, use_graph=True)      # graphs on (opt-in: measured, they buy nothing on B200)
+    g = hg.GraspSearch(FEATURES, RANGE, model, use_graph=True)      # graphs on (opt-in; one table1 goal: 0.224 ms launched, 0.189 ms replayed)
     p = hg.GraspSearch(FEATURES, RANGE, model)                      # plain launches (the default)
     try:
         def same(a, b):
