@@ -178,10 +178,16 @@ struct haf_ctx {
         const void *o_evals, *o_mask, *o_heights; unsigned long long rolls_hash; cudaStream_t st;
         bool operator==(const GraphKey& o) const { return memcmp(this, &o, sizeof *this) == 0; }
     };
-    GraphKey graph_key, graph_seen;
-    bool graph_valid = false, graph_seen_valid = false;
-    cudaGraphExec_t graph_exec = nullptr;
-    long long graph_nodes = 0, graph_replays = 0;
+    // a few graphs per context, least recently used out: a goal sharded over ranks alternates between two or three shapes
+    // (roll ranges of 12, 12 and 6 units, say), and one graph slot made every other call re-capture (instantiation costs more
+    // than the launches it saves: configs[2] on two GPUs took 1.20 ms per step that way)
+    struct GraphEntry { GraphKey key; cudaGraphExec_t exec; long long nodes; unsigned long long last_use; };
+    std::vector<GraphEntry> graphs;       // <= kMaxGraphs instantiated graphs
+    std::vector<GraphKey> graph_seen;     // shapes met once (a ring of kMaxGraphs): the second call of a shape captures
+    size_t graph_seen_next = 0;
+    unsigned long long graph_clock = 0;
+    static constexpr size_t kMaxGraphs = 8;
+    long long graph_replays = 0;
     unsigned long long alloc_epoch = 0;   // moved on by every ENSURE that (re)allocates one of this context's buffers
     int graph_mode = 0;
     cudaStream_t own_stream = nullptr;     // capture is not allowed on the legacy default stream: a blocking stream of our own stands in
@@ -966,7 +972,7 @@ extern "C" void haf_destroy(haf_ctx* ctx) {
     if (ctx->chunk_stream2[k]) cudaStreamDestroy(ctx->chunk_stream2[k]);
     }
     if (ctx->ev_dual_ok) for (int k = 0; k < 4; k++) cudaEventDestroy(ctx->ev_dual[k]);
-    if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
+    for (size_t i = 0; i < ctx->graphs.size(); i++) cudaGraphExecDestroy(ctx->graphs[i].exec);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     ctx->h_out_evals.release(); ctx->h_out_heights.release(); ctx->h_out_mask.release();
     if (ctx->ev_ok) for (int i = 0; i < 10; i++) cudaEventDestroy(ctx->ev[i]);
@@ -1355,7 +1361,7 @@ static int run_jobs_once(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& job
         }
     }
     // ---- one CUDA graph per request shape (see haf_ctx::GraphKey): 0 = enqueue as usual, 1 = capture while enqueuing, 2 = replay
-    int gmode = 0;
+    int gmode = 0, graph_slot = -1, seen_slot = -1;
     haf_ctx::GraphKey gkey;
     memset(&gkey, 0, sizeof gkey);
     const long long pts_bucket = (long long)round_up((size_t)std::max<long long>(max_points, 1), 65536);
@@ -1384,16 +1390,22 @@ static int run_jobs_once(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& job
         gkey.wcap = (size_t)wsum_all; gkey.pts_bucket = pts_bucket; gkey.n_jobs = n_jobs; gkey.n_clouds = n_clouds;
         gkey.flags = (prob ? 1 : 0) | (keep_debug_state ? 2 : 0) | (avg_points_all >= 8 * (long long)GG ? 4 : 0) | (ctx->cfg.emulate_text_roundtrip ? 8 : 0);
         gkey.tc_passes = ctx->tc_passes; gkey.o_evals = dst_evals; gkey.o_mask = dst_mask; gkey.o_heights = dst_heights; gkey.rolls_hash = hsh; gkey.st = st;
-        if (ctx->graph_valid && ctx->graph_key == gkey) gmode = 2;
-        else if (ctx->graph_seen_valid && ctx->graph_seen == gkey) gmode = 1;
-        else { ctx->graph_seen = gkey; ctx->graph_seen_valid = true; }
+        for (size_t i = 0; i < ctx->graphs.size() && gmode == 0; i++)
+            if (ctx->graphs[i].key == gkey) { gmode = 2; graph_slot = (int)i; }
+        for (size_t i = 0; i < ctx->graph_seen.size() && gmode == 0; i++)
+            if (ctx->graph_seen[i] == gkey) { gmode = 1; seen_slot = (int)i; }
+        if (gmode == 0) {   // first call of this shape: remember it (its key is completed after the call's own allocations, below)
+            if (ctx->graph_seen.size() < haf_ctx::kMaxGraphs) { ctx->graph_seen.push_back(gkey); seen_slot = (int)ctx->graph_seen.size() - 1; }
+            else { seen_slot = (int)(ctx->graph_seen_next++ % haf_ctx::kMaxGraphs); ctx->graph_seen[seen_slot] = gkey; }
+        }
     }
     float ms_stage[7] = {0, 0, 0, 0, 0, 0, 0};
     long long total_windows = 0, total_guard = 0;
     if (gmode == 2) {
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev[8], st));
-        CUDA_TRY(ctx, cudaGraphLaunch(ctx->graph_exec, st));
-        ctx->launches += ctx->graph_nodes;
+        ctx->graphs[graph_slot].last_use = ++ctx->graph_clock;
+        CUDA_TRY(ctx, cudaGraphLaunch(ctx->graphs[graph_slot].exec, st));
+        ctx->launches += ctx->graphs[graph_slot].nodes;
         ctx->graph_replays++;
         if (keep_debug_state) { ctx->last_units = U; ctx->last_unit_base = 0; ctx->last_ldx = round_up((size_t)std::max<long long>((long long)gkey.wcap, 1), 2 * haftc::BM); }
     } else {
@@ -1622,17 +1634,23 @@ static int run_jobs_once(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& job
     if (gmode == 1) {   // everything above was recorded, not run: instantiate, keep, run
         cudaGraph_t graph = nullptr;
         CUDA_TRY(ctx, cudaStreamEndCapture(st, &graph));
-        if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; ctx->graph_valid = false; }
-        const cudaError_t ie = cudaGraphInstantiate(&ctx->graph_exec, graph, 0);
+        cudaGraphExec_t gexec = nullptr;
+        const cudaError_t ie = cudaGraphInstantiate(&gexec, graph, 0);
         cudaGraphDestroy(graph);
-        if (ie != cudaSuccess) { ctx->graph_exec = nullptr; return ctx->fail(HAF_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ie)); }
-        ctx->graph_nodes = ctx->launches - launches_cap0;
+        if (ie != cudaSuccess) return ctx->fail(HAF_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ie));
+        if (ctx->graphs.size() >= haf_ctx::kMaxGraphs) {   // evict the least recently used one (stale keys -- an older allocation epoch -- age out this way)
+            size_t lru = 0;
+            for (size_t i = 1; i < ctx->graphs.size(); i++) if (ctx->graphs[i].last_use < ctx->graphs[lru].last_use) lru = i;
+            cudaGraphExecDestroy(ctx->graphs[lru].exec);
+            ctx->graphs.erase(ctx->graphs.begin() + lru);
+        }
         gkey.epoch = g_alloc_epoch + ctx->alloc_epoch;   // (unchanged unless a buffer grew while capturing: then the next call re-captures)
-        ctx->graph_key = gkey; ctx->graph_valid = true;
+        ctx->graphs.push_back(haf_ctx::GraphEntry{gkey, gexec, ctx->launches - launches_cap0, ++ctx->graph_clock});
+        if (seen_slot >= 0) memset(&ctx->graph_seen[seen_slot], 0xff, sizeof(haf_ctx::GraphKey));   // (no longer "seen once")
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev[8], st));
-        CUDA_TRY(ctx, cudaGraphLaunch(ctx->graph_exec, st));
+        CUDA_TRY(ctx, cudaGraphLaunch(gexec, st));
     } else if (graph_ok) {
-        ctx->graph_seen.epoch = g_alloc_epoch + ctx->alloc_epoch;   // buffers this first call of the shape grew: the second call captures
+        if (seen_slot >= 0) ctx->graph_seen[seen_slot].epoch = g_alloc_epoch + ctx->alloc_epoch;   // buffers this first call of the shape grew: the second call captures
     }
     }   // gmode != 2
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[9], st));

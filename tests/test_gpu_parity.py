@@ -597,6 +597,16 @@ def test_cuda_graph_replay_equals_plain_launches(hg, oracle_lib, tmp_models, clo
             for _ in range(3):
                 same(g.search(clouds[name], reqs), p.search(clouds[name], reqs))
         assert g.timing().graph_replays >= n0 + 4
+        # several graphs are kept (least recently used out): a goal sharded over ranks alternates between a few shapes
+        shapes = ([hg.make_request()], [hg.make_request(roll_begin=2, roll_limit=9)], [hg.make_request(roll_begin=0, roll_limit=6)])
+        for _ in range(2):
+            for reqs in shapes:
+                same(g.search(clouds["pcd2"], reqs), p.search(clouds["pcd2"], reqs))
+        n1 = g.timing().graph_replays
+        for _ in range(3):
+            for reqs in shapes:
+                same(g.search(clouds["pcd2"], reqs), p.search(clouds["pcd2"], reqs))
+        assert g.timing().graph_replays == n1 + 9
         # batches of one shape replay too; device-resident clouds and outputs=False (no per-roll copies)
         from haf_grasping_b200 import synth
         cl = [synth.synth_cloud(40 + i, 30000) for i in range(5)]
