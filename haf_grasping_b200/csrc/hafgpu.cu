@@ -1501,7 +1501,7 @@ static int run_jobs_once(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& job
                 // (150 KB of shared-memory bounds initialised and flushed, launch) plus its slice of the cloud's points; the CTAs
                 // (clouds x unit groups x slices) run in rounds of one per SM.  Slice count <= 12 that minimises
                 //     rounds x (1 / slices + fixed / whole-cloud time),   fixed / whole-cloud time ~ 4.2 G^2 / points
-                // fitted to the ncu launch list of a host-staged bench step (profiles/r2_launches_e2e.md: 144 CTAs of 1/6 cloud 86 us,
+                // fitted to the ncu launch list of a host-staged bench step (profiles/r2_final_launches_e2e.md: 144 CTAs of 1/6 cloud 86 us,
                 // of 1/4 cloud 108 us).  512 clouds: 2 slices = 7 rounds (round 2 found that by wave efficiency alone); the
                 // 64-cloud chunks of a staged batch: 2 slices = one round of 128 CTAs (167 us) where wave efficiency picked 9 (210 us).
                 int slices = 1;

@@ -373,7 +373,7 @@ svm_rbf_tc2_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_consta
 // ==================================================================================================================
 // X-RESIDENT CTA-pair kernel, one product per k-slice (the default where the calibration picks passes == 1).
 //
-// What bounded the one-product kernel (profiles/r2_tc_pipeline_probe.md -- clock64 around every wait of the role threads):
+// What bounded the one-product kernel (profiles/r2_tc_pipeline_probe.txt -- clock64 around every wait of the role threads):
 // NOT the L2 feed, NOT the MUFU pipe, NOT the epilogue, but the single MMA-issuing THREAD.  With one product a k-block is
 // only 4 MMAs (512 clocks of tensor pipe); round 1's role loops ran on ONE lane of the warp (`if (lane == 0)`), so every
 // descriptor, predicate and barrier address was computed with ordinary dependent instructions of a lone, diverged thread

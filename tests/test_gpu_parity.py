@@ -22,7 +22,7 @@ pytestmark = pytest.mark.gpu
 # and, for windows whose exponent arguments are moderate, |dec_gpu - dec_ref| <= 1e-5 * sum_i |coef_i| K_i
 # (model_io.check_decision_tolerance).  E is the guard band's own scale; the band is 4e-6 E wide or wider.
 DEC_RTOL = 1e-5      # plain form
-DEC_RTOL_E = 2e-6    # E form; measured <= 5e-7 on every FP32 / tensor path (profiles/r2_dec_error_hist.txt)
+DEC_RTOL_E = 2e-6    # E form; measured <= 5e-7 on every FP32 / tensor path (profiles/r2_final_dec_error_probe.txt)
 # FP64 exact-order path: only exp() implementation differences (glibc vs CUDA, <= 1 ulp each term)
 DEC64_RTOL = 1e-13
 
