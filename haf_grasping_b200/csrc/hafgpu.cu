@@ -6,7 +6,9 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <condition_variable>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -164,6 +166,21 @@ struct haf_ctx {
     cudaStream_t chunk_stream2[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev_dual[4];             // [0] head of the call done on the main stream, [1 + k] extra stream k drained
     bool ev_dual_ok = false;
+    // PAGEABLE host clouds (what the action server holds: a pcl::PointCloud): cudaMemcpyAsync from pageable
+    // memory goes through the driver's own staging at ~9 GB/s and blocks the calling thread.  Batches of 4 MB and more are
+    // staged by the library instead: a helper thread copies each piece into a ring of pinned slots with a few host threads
+    // (stage_threads, HAF_STAGE_THREADS; 0 = leave it to the driver) and issues the piece's H2D copy and event; the enqueuing
+    // thread waits (host side) until the pieces a chunk needs have been ISSUED before it makes the chunk's stream wait for them.
+    struct Stager {
+        std::thread th;
+        std::mutex mu;
+        std::condition_variable cv;
+        int issued = 0;        // pieces whose copy + event have been issued on copy_stream
+        bool failed = false, active = false;
+    } stager;
+    PinBuf<unsigned char> h_ring;       // kRingSlots pinned slots of one piece each
+    static constexpr int kRingSlots = 4;
+    int stage_threads = 8;
     PinBuf<unsigned char> h_stage;      // pinned staging for params / results
     PinBuf<JobResult> h_results;
     PinBuf<int> h_per_roll_top;
@@ -559,6 +576,10 @@ static int create_impl(haf_ctx** out, const haf_config* cfg, bool svm_only, int 
     // WITHOUT per-stage timing events (profiling on disables graphs, and every timing event between two kernels costs ~20 us):
     // one table1 goal 0.224 ms launched, 0.189 ms replayed; the 512-grid 1 M-point goal 4.34 vs 4.31 ms (profiles/r2_final_*).
     ctx->graph_mode = ((cfg->reserved[1] & 16) || (getenv("HAF_GRAPH") && atoi(getenv("HAF_GRAPH")))) ? 0 : 1;
+    // host threads that copy a pageable batch into the pinned ring: half the cores, at most 8 (measured, 614 MB per call, 16 cores:
+    // the driver's pageable path 75 ms; 2 threads 45, 4: 28, 8: 24.8, 12: 23.3 ms -- against 12.6 ms from pinned memory)
+    ctx->stage_threads = (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency() / 2));
+    if (const char* e = getenv("HAF_STAGE_THREADS")) ctx->stage_threads = std::max(0, std::min(16, atoi(e)));
     ctx->tier2_mode = cfg->reserved[2] & 3;
     ctx->tier2_kernel = (cfg->reserved[2] >> 2) & 3;
     CREATE_TRY(cudaFuncSetAttribute(guard_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HAF_GD_SMEM_BYTES));
@@ -974,7 +995,7 @@ extern "C" void haf_destroy(haf_ctx* ctx) {
     if (ctx->ev_dual_ok) for (int k = 0; k < 4; k++) cudaEventDestroy(ctx->ev_dual[k]);
     for (size_t i = 0; i < ctx->graphs.size(); i++) cudaGraphExecDestroy(ctx->graphs[i].exec);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
-    ctx->h_out_evals.release(); ctx->h_out_heights.release(); ctx->h_out_mask.release();
+    ctx->h_out_evals.release(); ctx->h_out_heights.release(); ctx->h_out_mask.release(); ctx->h_ring.release();
     if (ctx->ev_ok) for (int i = 0; i < 10; i++) cudaEventDestroy(ctx->ev[i]);
     for (size_t i = 0; i < ctx->ev_pool.size(); i++) cudaEventDestroy(ctx->ev_pool[i]);
     for (size_t i = 0; i < ctx->copy_ev.size(); i++) cudaEventDestroy(ctx->copy_ev[i]);
@@ -1052,6 +1073,12 @@ long long window_bound(int G, const haf_request& rq) {
     return std::min(full, geo);
 }
 
+// host memory the copy engine can read directly (cudaMallocHost / cudaHostRegister)
+bool is_pinned_host_ptr(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
 bool is_device_ptr(const void* p) {
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
@@ -1481,6 +1508,11 @@ static int run_jobs_once(haf_ctx* ctx, const CloudSet& cs, std::vector<Job>& job
 
         // staged host clouds: wait for the copy pieces that cover this chunk's clouds
         while (next_piece < ctx->copy_pieces && (next_piece == 0 ? 0 : ctx->copy_cloud_end[next_piece - 1]) < c1) {
+            if (ctx->stager.active) {   // pageable source: the helper thread records the event -- wait until it has (an unrecorded event does not block)
+                std::unique_lock<std::mutex> lk(ctx->stager.mu);
+                ctx->stager.cv.wait(lk, [&] { return ctx->stager.issued > next_piece; });
+                if (ctx->stager.failed) return ctx->fail(HAF_ERR_CUDA, "staging a pageable host batch failed (pinned ring copy / cudaMemcpyAsync)");
+            }
             CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->copy_ev[next_piece], 0));
             next_piece++;
         }
@@ -1724,6 +1756,36 @@ static void fill_best(const haf_ctx* ctx, const Job& jb, const JobResult& r, int
     b->rolls_done = r.rolls_done; b->n_windows_scored = r.n_windows; b->n_guard = (int)n_guard;
 }
 
+// helper thread of a pageable host batch (haf_ctx::Stager): piece by piece, src -> pinned ring slot (stage_threads host threads),
+// then the slot -> device copy and the piece's event on copy_stream.  A slot is reused once the copy that read it has finished.
+static void stager_main(haf_ctx* ctx, const unsigned char* src, std::vector<std::pair<size_t, size_t> > pieces, size_t slot_bytes) {
+    bool ok = cudaSetDevice(ctx->device) == cudaSuccess;
+    const int T = std::max(1, std::min(16, ctx->stage_threads));
+    for (size_t k = 0; k < pieces.size(); k++) {
+        const size_t b0 = pieces[k].first, n = pieces[k].second - pieces[k].first;
+        unsigned char* slot = ctx->h_ring.p + (k % haf_ctx::kRingSlots) * slot_bytes;
+        if (ok && k >= (size_t)haf_ctx::kRingSlots) ok = cudaEventSynchronize(ctx->copy_ev[k - haf_ctx::kRingSlots]) == cudaSuccess;
+        if (ok && n) {
+            std::vector<std::thread> helpers;
+            const size_t per = round_up((n + T - 1) / T, 4096);
+            for (int t = 1; t < T; t++) {
+                const size_t o = (size_t)t * per;
+                if (o < n) helpers.emplace_back([=] { memcpy(slot + o, src + b0 + o, std::min(per, n - o)); });
+            }
+            memcpy(slot, src + b0, std::min(per, n));
+            for (size_t t = 0; t < helpers.size(); t++) helpers[t].join();
+            ok = cudaMemcpyAsync(ctx->d_xyz.p + b0, slot, n, cudaMemcpyHostToDevice, ctx->copy_stream) == cudaSuccess;
+        }
+        if (cudaEventRecord(ctx->copy_ev[k], ctx->copy_stream) != cudaSuccess) ok = false;
+        {
+            std::lock_guard<std::mutex> lk(ctx->stager.mu);
+            if (!ok) ctx->stager.failed = true;
+            ctx->stager.issued = (int)k + 1;
+        }
+        ctx->stager.cv.notify_all();
+    }
+}
+
 // stage a host cloud set on the device (or use device pointers in place)
 static int stage_points(haf_ctx* ctx, const void* src, size_t bytes, bool* is_dev) {
     *is_dev = is_device_ptr(src);
@@ -1831,6 +1893,8 @@ static int batch_packed_single(haf_ctx* ctx, const float* xyz_all, const size_t*
         CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, start_ev, 0));
         cudaEventDestroy(start_ev);
         ctx->copy_cloud_end.clear();
+        const bool own_staging = ctx->stage_threads > 0 && total * 12 >= ((size_t)4 << 20) && !is_pinned_host_ptr(xyz_all);
+        std::vector<std::pair<size_t, size_t> > piece_bytes;   // [b0, b1) of every piece (own staging)
         int c = 0, k = 0;
         while (c < n_clouds) {
             int ce = c;
@@ -1844,14 +1908,26 @@ static int batch_packed_single(haf_ctx* ctx, const float* xyz_all, const size_t*
                 CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
                 ctx->copy_ev.push_back(e);
             }
-            if (b1 > b0) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_xyz.p + b0, reinterpret_cast<const unsigned char*>(xyz_all) + b0, b1 - b0, cudaMemcpyHostToDevice, ctx->copy_stream));
-            CUDA_TRY(ctx, cudaEventRecord(ctx->copy_ev[k], ctx->copy_stream));
+            if (own_staging) piece_bytes.push_back(std::make_pair(b0, b1));
+            else {
+                if (b1 > b0) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_xyz.p + b0, reinterpret_cast<const unsigned char*>(xyz_all) + b0, b1 - b0, cudaMemcpyHostToDevice, ctx->copy_stream));
+                CUDA_TRY(ctx, cudaEventRecord(ctx->copy_ev[k], ctx->copy_stream));
+            }
             ctx->copy_cloud_end.push_back(ce);
             c = ce;
             k++;
         }
         ctx->copy_pieces = k;
+        if (own_staging) {
+            size_t slot = 0;
+            for (size_t i = 0; i < piece_bytes.size(); i++) slot = std::max(slot, piece_bytes[i].second - piece_bytes[i].first);
+            slot = round_up(slot, 4096);
+            ENSURE(ctx, ctx->h_ring, slot * haf_ctx::kRingSlots);
+            ctx->stager.issued = 0; ctx->stager.failed = false; ctx->stager.active = true;
+            ctx->stager.th = std::thread(stager_main, ctx, reinterpret_cast<const unsigned char*>(xyz_all), piece_bytes, slot);
+        }
     }
+    struct StagerJoin { haf_ctx* c; ~StagerJoin() { if (c->stager.active) { c->stager.th.join(); c->stager.active = false; } } } stager_join{ctx};
     cs.d_xyz = total == 0 ? nullptr : (dev ? reinterpret_cast<const unsigned char*>(xyz_all) : ctx->d_xyz.p);
     std::vector<Job> jobs(n_clouds);
     for (int c = 0; c < n_clouds; c++) { jobs[c].cloud = c; jobs[c].rq = *req; }
