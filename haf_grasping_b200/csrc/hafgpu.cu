@@ -1768,11 +1768,16 @@ static void stager_main(haf_ctx* ctx, const unsigned char* src, std::vector<std:
         if (ok && n) {
             std::vector<std::thread> helpers;
             const size_t per = round_up((n + T - 1) / T, 4096);
-            for (int t = 1; t < T; t++) {
-                const size_t o = (size_t)t * per;
-                if (o < n) helpers.emplace_back([=] { memcpy(slot + o, src + b0 + o, std::min(per, n - o)); });
+            // slice t of T goes to helper thread t (t >= 1); this thread copies slice 0 and whatever could not get a thread
+            size_t covered = std::min(per, n);   // bytes [0, covered) are this thread's or a started helper's
+            for (int t = 1; t < T && covered < n; t++) {
+                const size_t o = covered, len = std::min(per, n - o);
+                try { helpers.emplace_back([=] { memcpy(slot + o, src + b0 + o, len); }); }
+                catch (...) { break; }
+                covered = o + len;
             }
             memcpy(slot, src + b0, std::min(per, n));
+            if (covered < n) memcpy(slot + covered, src + b0 + covered, n - covered);
             for (size_t t = 0; t < helpers.size(); t++) helpers[t].join();
             ok = cudaMemcpyAsync(ctx->d_xyz.p + b0, slot, n, cudaMemcpyHostToDevice, ctx->copy_stream) == cudaSuccess;
         }
@@ -1923,8 +1928,14 @@ static int batch_packed_single(haf_ctx* ctx, const float* xyz_all, const size_t*
             for (size_t i = 0; i < piece_bytes.size(); i++) slot = std::max(slot, piece_bytes[i].second - piece_bytes[i].first);
             slot = round_up(slot, 4096);
             ENSURE(ctx, ctx->h_ring, slot * haf_ctx::kRingSlots);
-            ctx->stager.issued = 0; ctx->stager.failed = false; ctx->stager.active = true;
-            ctx->stager.th = std::thread(stager_main, ctx, reinterpret_cast<const unsigned char*>(xyz_all), piece_bytes, slot);
+            ctx->stager.issued = 0; ctx->stager.failed = false;
+            try {
+                ctx->stager.th = std::thread(stager_main, ctx, reinterpret_cast<const unsigned char*>(xyz_all), piece_bytes, slot);
+                ctx->stager.active = true;
+            } catch (...) {
+                ctx->copy_pieces = 0;
+                return ctx->fail(HAF_ERR_NOMEM, "could not start the staging thread for a pageable host batch (set HAF_STAGE_THREADS=0 to use the driver's copy path)");
+            }
         }
     }
     struct StagerJoin { haf_ctx* c; ~StagerJoin() { if (c->stager.active) { c->stager.th.join(); c->stager.active = false; } } } stager_join{ctx};
