@@ -17,7 +17,31 @@ F = os.path.join(ROOT, "tests", "golden", "refdata", "Features.txt")
 R = os.path.join(ROOT, "tests", "golden", "refdata", "range21062012_allfeatures")
 
 
+def staged():
+    """round 2, end: host-staged batches -- chunks alternating between three streams / buffer sets, the counter merge, the
+    library's own staging of pageable memory (helper + copy threads, pinned ring); CUDA graph capture / replay of single goals"""
+    import torch
+    tmp = tempfile.mkdtemp()
+    model = synth.write_synth_model(os.path.join(tmp, "s.model"), 300, rho=-0.2972253)
+    cl = [synth.synth_cloud(500 + i, 9000 + 100 * (i % 5)) for i in range(50)]       # 16 + 24 + 10 clouds: three chunks, three streams
+    off = np.concatenate([[0], np.cumsum([len(c) for c in cl])])
+    xyz = np.concatenate(cl)                                                          # 5.5 MB pageable: the library stages it itself
+    pinned = torch.empty((len(xyz), 3), dtype=torch.float32, pin_memory=True)
+    pinned.numpy()[:] = xyz
+    g = h.GraspSearch(F, R, model, guard_rel=1e-3, use_graph=True)
+    want = [b.astuple() for b in g.search_batch_packed(torch.from_numpy(xyz).cuda(), off)]
+    for name, buf in (("pageable", xyz), ("pinned", pinned.numpy())):
+        got = [b.astuple() for b in g.search_batch_packed(buf, off)]
+        print("staged", name, "chunks", g.timing().n_chunks, "equal", got == want, "guard", g.timing().n_guard)
+    for _ in range(4):
+        r = g.search(cl[0])
+    print("graph replays", g.timing().graph_replays, r["best"].astuple() == want[0])
+    g.close()
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "staged":
+        return staged()
     tmp = tempfile.mkdtemp()
     model = synth.write_synth_model(os.path.join(tmp, "s.model"), 300, rho=-0.2972253)
     clouds = [synth.synth_cloud(77 + i, 6000 + 500 * i) for i in range(3)]
