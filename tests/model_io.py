@@ -52,7 +52,7 @@ def coefK_sum(model, scaled, block=2048, with_E=False):
 
 def check_decision_tolerance(model, scaled, dec_gpu, dec_ref, rtol_E=2e-6, rtol_plain=1e-5):
     """The stated tolerance of the FP32 / tensor decision values (north_star: <= 1e-5 relative in FP32), per window:
-         |dec_gpu - dec_ref| <= rtol_E * E(window)            E as above; measured <= 5e-7 (profiles/r2_dec_error_probe.txt);
+         |dec_gpu - dec_ref| <= rtol_E * E(window)            E as above; measured <= 5e-7 (profiles/r2_final_dec_error_probe.txt);
        and wherever the exponent arguments are moderate (gamma log2e (|x|^2 + max|sv|^2) <= 4) the plain statement
          |dec_gpu - dec_ref| <= 1e-5 * sum_i |coef_i| K_i(window).
     Returns (max err / E, max err / sum|coef|K over the moderate windows)."""
